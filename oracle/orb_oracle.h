@@ -1,0 +1,74 @@
+/*
+ * oracle/orb_oracle.h -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * Plain-C CPU restatement of the reference's ORB front-end hot path
+ * (/root/reference/src/ORBextractor.cc, ORBmatcher.cc, Frame.cc).
+ * It is the checker for the CUDA path: only tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline / --impl reference legs may load it.
+ *
+ * Pinning: the OpenCV/libm primitives underneath (cv_prims.c) are checked bit-for-bit
+ * against Python cv2 4.13.0 and glibc; the pipeline above them is checked against the
+ * reference's own unmodified sources compiled into oracle/_ref/liborbref.so
+ * (tests/test_oracle_vs_ref.py) and against fixtures generated from that library and
+ * committed under tests/golden/.  The reference itself ships no tests or golden
+ * vectors.
+ */
+#ifndef ORB_ORACLE_H
+#define ORB_ORACLE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct { float x, y, size, angle, response; int octave, class_id; } orbo_kp; /* == cv::KeyPoint */
+typedef struct { int x, y, score; } orbo_cand; /* FAST candidate, "border frame" (origin at pixel 16,16) */
+
+typedef struct orbo_extractor orbo_extractor;
+
+/* ORBextractor::ORBextractor, ORBextractor.cc:498-559 */
+orbo_extractor* orbo_create(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST);
+void orbo_destroy(orbo_extractor* e);
+int orbo_levels(const orbo_extractor* e);
+void orbo_tables(const orbo_extractor* e, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2,
+                 int* per_level, int* umax16, int* pattern1024);
+
+/* ORBextractor::operator(), ORBextractor.cc:1084-1150.  Returns n (may exceed cap; at most cap
+ * entries are written), -1 for an empty image (outputs untouched), -2 for an unsupported shape. */
+int orbo_extract(orbo_extractor* e, const uint8_t* img, int w, int h, size_t step,
+                 orbo_kp* kps, uint8_t* desc, int cap);
+
+/* Stage outputs of the last orbo_extract call on e. */
+int orbo_stage_level_size(const orbo_extractor* e, int level, int* w, int* h);
+int orbo_stage_pyramid(const orbo_extractor* e, int level, int with_border, uint8_t* dst, size_t dst_step);
+int orbo_stage_blurred(const orbo_extractor* e, int level, uint8_t* dst, size_t dst_step);
+int orbo_stage_candidates(const orbo_extractor* e, int level, orbo_cand* out, int cap);
+int orbo_stage_level_keypoints(const orbo_extractor* e, int level, orbo_kp* out, int cap);
+
+/* DistributeOctTree as a pure function (ORBextractor.cc:562-792 with the pointer
+ * tie-break of :711 replaced by creation order).  Candidates in
+ * reference order; returns the number of retained keypoints, indices into cand in
+ * list order in out_idx. */
+int orbo_distribute(const orbo_cand* cand, int n, int minX, int maxX, int minY, int maxY, int N,
+                    int* out_idx, int cap);
+
+/* CPU timing helper for the "port" baseline: frames contiguous with pitch w, round-robin
+ * over nthreads (pthreads), one extractor per thread.  Returns wall seconds. */
+double orbo_extract_bench(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST,
+                          const uint8_t* frames, int nframes, int w, int h, int nthreads,
+                          long long* total_kps);
+
+/* ---- matcher (ORBmatcher.cc, Frame.cc) ------------------------------------------- */
+
+/* ORBmatcher::DescriptorDistance, ORBmatcher.cc:46-63 */
+int orbo_descriptor_distance(const uint8_t* a, const uint8_t* b);
+
+/* All-pairs best / second-best (strict <, first wins), the brute-force kernel's checker. */
+void orbo_hamming_bf(const uint8_t* q, int nq, const uint8_t* t, int nt, int* best_idx, int* best_dist, int* second_dist);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,86 @@
+// oracle/ref_arena.cc -- TEST INFRASTRUCTURE, NOT PRODUCT CODE (see ref_arena.hpp).
+#include "ref_arena.hpp"
+
+#include <sys/mman.h>
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <new>
+
+namespace {
+const std::size_t kRegionBytes = std::size_t(8) << 30; // virtual, per thread
+const int kMaxRegions = 1024;
+
+std::atomic<char*> g_regions[kMaxRegions]; // slot == 0: free
+std::atomic<int> g_hi(0);                  // slots >= g_hi were never used
+
+struct ThreadArena {
+    char* base;
+    std::size_t off;
+    ThreadArena() : base(0), off(0) {}
+    void init()
+    {
+        void* p = mmap(0, kRegionBytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+        if (p == MAP_FAILED) { std::fprintf(stderr, "ref_arena: mmap failed\n"); std::abort(); }
+        base = (char*)p;
+        for (int i = 0; i < kMaxRegions; ++i) {
+            char* expect = 0;
+            if (g_regions[i].compare_exchange_strong(expect, base)) {
+                slot = i;
+                int hi = g_hi.load();
+                while (hi < i + 1 && !g_hi.compare_exchange_weak(hi, i + 1)) {}
+                return;
+            }
+        }
+        std::fprintf(stderr, "ref_arena: too many threads\n");
+        std::abort();
+    }
+    // thread exit: everything this thread allocated must be dead by now
+    ~ThreadArena()
+    {
+        if (base) { g_regions[slot].store(0); munmap(base, kRegionBytes); base = 0; }
+    }
+    int slot;
+};
+thread_local ThreadArena t_arena;
+} // namespace
+
+namespace ref_arena {
+void* alloc(std::size_t n)
+{
+    ThreadArena& a = t_arena;
+    if (!a.base) a.init();
+    std::size_t need = (n + 15) & ~std::size_t(15);
+    if (a.off + need > kRegionBytes) { std::fprintf(stderr, "ref_arena: region exhausted\n"); std::abort(); }
+    void* p = a.base + a.off;
+    a.off += need;
+    return p;
+}
+bool owns(const void* p)
+{
+    for (int i = 0, n = g_hi.load(std::memory_order_relaxed); i < n; ++i) {
+        const char* b = g_regions[i].load(std::memory_order_relaxed);
+        if (b && (const char*)p >= b && (const char*)p < b + kRegionBytes) return true;
+    }
+    return false;
+}
+std::size_t mark() { return t_arena.off; }
+void rewind(std::size_t m) { t_arena.off = m; }
+} // namespace ref_arena
+
+// Replace the global allocation functions for this shared object only (the link uses a
+// version script that keeps these symbols local, so nothing else in the process sees them).
+void* operator new(std::size_t n) { return ref_arena::alloc(n ? n : 1); }
+void* operator new[](std::size_t n) { return ref_arena::alloc(n ? n : 1); }
+void* operator new(std::size_t n, const std::nothrow_t&) noexcept { return ref_arena::alloc(n ? n : 1); }
+void* operator new[](std::size_t n, const std::nothrow_t&) noexcept { return ref_arena::alloc(n ? n : 1); }
+static inline void arena_delete(void* p) noexcept
+{
+    if (p && !ref_arena::owns(p)) std::free(p);
+}
+void operator delete(void* p) noexcept { arena_delete(p); }
+void operator delete[](void* p) noexcept { arena_delete(p); }
+void operator delete(void* p, std::size_t) noexcept { arena_delete(p); }
+void operator delete[](void* p, std::size_t) noexcept { arena_delete(p); }
+void operator delete(void* p, const std::nothrow_t&) noexcept { arena_delete(p); }
+void operator delete[](void* p, const std::nothrow_t&) noexcept { arena_delete(p); }
