@@ -1,0 +1,133 @@
+/*
+ * orb_b200.h -- C ABI of the B200-native ORB front end (liborb_b200.so).
+ *
+ * This is the drop-in boundary for the reference's data-parallel hot path.  Each entry
+ * point names the reference interface it replaces (paths relative to the reference
+ * checkout, Hello-Water/ORB-SLAM2-ChineseNotes).  Plain pointers and sizes only; no
+ * exceptions cross the boundary; every function returns an orbx_status (0 = OK).
+ * The library has NO CPU fallback: without a CUDA device every compute entry point
+ * fails with ORBX_E_CUDA.
+ *
+ * The C++ classes a SLAM build links against (ORB_SLAM2::ORBextractor / ORBmatcher with the
+ * reference's exact signatures) are thin forwarders over this ABI; see
+ * orb_slam2_chinesenotes_b200/host/ and INTEGRATION.md.
+ */
+#ifndef ORB_B200_H
+#define ORB_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    ORBX_OK = 0,
+    ORBX_E_ARG = 1,        /* null pointer / bad parameter */
+    ORBX_E_SHAPE = 2,      /* image shape the path cannot handle (see orbx_shape_supported) */
+    ORBX_E_CAPACITY = 3,   /* caller's keypoint capacity smaller than the result; n_out still valid */
+    ORBX_E_CUDA = 4,       /* CUDA runtime failure; orbx_last_error() has the text */
+    ORBX_E_EMPTY = 5       /* empty image: outputs untouched (src/ORBextractor.cc:1087) */
+} orbx_status;
+
+/* Binary layout of cv::KeyPoint (28 bytes): what operator() appends to its vector. */
+typedef struct { float x, y, size, angle, response; int octave, class_id; } orbx_kp;
+
+typedef struct orbx_ctx orbx_ctx; /* one per ORBextractor instance; thread-compatible, not shared */
+
+/* ---- extractor ------------------------------------------------------------------- */
+
+/* ORBextractor::ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST)
+ * include/ORBextractor.h:52, src/ORBextractor.cc:498-559.  device = CUDA ordinal. */
+int orbx_create(orbx_ctx** out, int nfeatures, float scaleFactor, int nlevels,
+                int iniThFAST, int minThFAST, int device);
+void orbx_destroy(orbx_ctx* ctx);
+
+/* GetLevels / GetScaleFactors / GetInverseScaleFactors / GetScaleSigmaSquares /
+ * GetInverseScaleSigmaSquares, include/ORBextractor.h:64-84; per_level = mnFeaturesPerLevel
+ * (:103).  Any output pointer may be NULL.  Arrays hold orbx_levels() entries. */
+int orbx_levels(const orbx_ctx* ctx);
+int orbx_tables(const orbx_ctx* ctx, float* scale, float* inv_scale, float* sigma2,
+                float* inv_sigma2, int* per_level);
+
+/* 1 if (w,h) can be processed: every pyramid level leaves a non-degenerate FAST area
+ * (the reference itself divides by zero otherwise, src/ORBextractor.cc:567-568), level
+ * sizes <= 4128 and w*h < 2^24. */
+int orbx_shape_supported(const orbx_ctx* ctx, int w, int h);
+
+/* ORBextractor::operator()(image, mask, keypoints, descriptors), include/ORBextractor.h:60,
+ * src/ORBextractor.cc:1084-1150, for one 8-bit single-channel image (mask is ignored by the
+ * reference).  img/kps/desc/n_out may each be host or device memory.  kps[capacity],
+ * desc[capacity*32]; *n_out is the number of keypoints found and can exceed nfeatures
+ * (and capacity: then ORBX_E_CAPACITY and the first capacity entries are valid). */
+int orbx_extract(orbx_ctx* ctx, const uint8_t* img, int w, int h, size_t pitch,
+                 orbx_kp* kps, uint8_t* desc, int capacity, int* n_out);
+
+/* The same over a batch of equally sized frames: frame f starts at imgs + f*frame_stride.
+ * Outputs are [batch][cap_per_frame] / [batch][cap_per_frame][32] / [batch].  This is the
+ * call Frame::ExtractORB (src/Frame.cc:262-268) would make once per camera per frame;
+ * batching independent frames is how one GPU is kept busy. */
+int orbx_extract_batch(orbx_ctx* ctx, const uint8_t* imgs, size_t frame_stride, int batch,
+                       int w, int h, size_t pitch, orbx_kp* kps, uint8_t* desc,
+                       int cap_per_frame, int* n_out);
+
+/* As above with every pointer in DEVICE memory: only enqueues work on the context's stream
+ * and returns; orbx_sync() waits.  n_out overflow is not reported here. */
+int orbx_extract_batch_async(orbx_ctx* ctx, const uint8_t* d_imgs, size_t frame_stride, int batch,
+                             int w, int h, size_t pitch, orbx_kp* d_kps, uint8_t* d_desc,
+                             int cap_per_frame, int* d_n_out);
+int orbx_sync(orbx_ctx* ctx);
+
+/* mvImagePyramid[level] of frame `frame` of the last call (include/ORBextractor.h:86; read by
+ * Frame::ComputeStereoMatches, src/Frame.cc:520,611-633).  with_border: the (w+38)x(h+38)
+ * REFLECT_101-padded buffer of src/ORBextractor.cc:1159-1174 instead of the ROI.  dst host or
+ * device, may be NULL to query the size. */
+int orbx_pyramid_level(orbx_ctx* ctx, int frame, int level, int with_border,
+                       uint8_t* dst, size_t dst_pitch, int* w, int* h);
+
+/* Use a caller-owned CUDA stream (cudaStream_t) for all work of this context; NULL restores
+ * the context's own stream.  orbx_stream returns the stream in use. */
+int orbx_set_stream(orbx_ctx* ctx, void* cuda_stream);
+void* orbx_stream(const orbx_ctx* ctx);
+
+/* Frames processed per internal pass (working-set control, default chosen for the 126 MB L2). */
+int orbx_set_chunk(orbx_ctx* ctx, int frames_per_chunk);
+
+const char* orbx_last_error(const orbx_ctx* ctx);
+
+/* ---- stage taps (parity tests and profiling; not needed by a SLAM build) -------------- */
+
+enum { ORBX_STAGE_PYRAMID = 0, ORBX_STAGE_FAST = 1, ORBX_STAGE_BLUR = 2, ORBX_STAGE_OCTREE = 3,
+       ORBX_STAGE_DESCRIBE = 4, ORBX_STAGE_COUNT = 5 };
+
+/* Blurred level (src/ORBextractor.cc:1129-1130) of a frame of the last call. */
+int orbx_debug_blurred(orbx_ctx* ctx, int frame, int level, uint8_t* dst, size_t dst_pitch);
+/* FAST candidates of a level before DistributeOctTree (src/ORBextractor.cc:853-870), as
+ * (x, y, score) int triples in the "border frame"; UNORDERED.  Returns the count in *n. */
+int orbx_debug_candidates(orbx_ctx* ctx, int frame, int level, int* xys, int cap, int* n);
+/* Keypoints of a level after DistributeOctTree in list order, (x, y, score) triples. */
+int orbx_debug_level_keypoints(orbx_ctx* ctx, int frame, int level, int* xys, int cap, int* n);
+/* Accumulate per-stage GPU time (CUDA events on the context's stream) while enabled. */
+int orbx_profile(orbx_ctx* ctx, int enable);
+int orbx_stage_ms(orbx_ctx* ctx, float* ms /*[ORBX_STAGE_COUNT]*/, int* launches, int reset);
+
+/* Host-only view of the per-shape plan (no GPU needed): level sizes, processed 30-px cells
+ * (src/ORBextractor.cc:826-850), quotas, quadtree roots (:567), candidate capacities. */
+int orbx_plan_describe(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST, int w, int h,
+                       int* level_w, int* level_h, int* cells, int* quota, int* n_ini, int* cand_cap);
+
+/* ---- matcher -------------------------------------------------------------------- */
+
+/* ORBmatcher::DescriptorDistance (src/ORBmatcher.cc:46-63) over all pairs: for each of the nq
+ * 32-byte query descriptors the index of the closest of nt train descriptors (strict <, first
+ * wins: the reference's comparison, :129), its distance and the second-best distance
+ * (256 when absent).  nprob independent problems are laid out back to back.
+ * Pointers host or device. */
+int orbm_hamming_bf(const uint8_t* q, int nq, const uint8_t* t, int nt, int nprob,
+                    int* best_idx, int* best_dist, int* second_dist, int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

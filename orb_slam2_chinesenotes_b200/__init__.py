@@ -1,0 +1,285 @@
+"""B200-native ORB front end: Python face of liborb_b200.so (ctypes over the C ABI).
+
+The product is the CUDA library; this module only loads it and mirrors the reference's
+class interface (ORB_SLAM2::ORBextractor, include/ORBextractor.h:47-111, and the Hamming part
+of ORB_SLAM2::ORBmatcher, include/ORBmatcher.h:43-100) so tests and benchmarks read like calls
+into the reference.  There is no CPU fallback: if the library or a CUDA device is missing,
+every compute call raises.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "liborb_b200.so")
+CSRC_DIR = os.path.join(_HERE, "csrc")
+
+KP_DTYPE = np.dtype([("x", "f4"), ("y", "f4"), ("size", "f4"), ("angle", "f4"), ("response", "f4"),
+                     ("octave", "i4"), ("class_id", "i4")])
+assert KP_DTYPE.itemsize == 28
+
+ORBX_OK, ORBX_E_ARG, ORBX_E_SHAPE, ORBX_E_CAPACITY, ORBX_E_CUDA, ORBX_E_EMPTY = range(6)
+STAGES = ("pyramid", "fast", "blur", "octree", "describe")
+
+
+class OrbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"orb_b200 status {code}: {msg}")
+        self.code = code
+
+
+def build(verbose=False):
+    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    r = subprocess.run(["make", "-C", CSRC_DIR], capture_output=True, text=True)
+    if verbose or r.returncode:
+        print(r.stdout[-4000:], r.stderr[-4000:])
+    if r.returncode:
+        raise RuntimeError("building liborb_b200.so failed")
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """The loaded C-ABI library.  Fails loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise OSError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        vp, i32, f32, sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+        pi = C.POINTER(C.c_int)
+        L.orbx_create.argtypes = [C.POINTER(vp), i32, f32, i32, i32, i32, i32]
+        L.orbx_destroy.argtypes = [vp]
+        L.orbx_destroy.restype = None
+        L.orbx_levels.argtypes = [vp]
+        L.orbx_tables.argtypes = [vp] * 6
+        L.orbx_shape_supported.argtypes = [vp, i32, i32]
+        L.orbx_extract.argtypes = [vp, vp, i32, i32, sz, vp, vp, i32, vp]
+        L.orbx_extract_batch.argtypes = [vp, vp, sz, i32, i32, i32, sz, vp, vp, i32, vp]
+        L.orbx_extract_batch_async.argtypes = [vp, vp, sz, i32, i32, i32, sz, vp, vp, i32, vp]
+        L.orbx_sync.argtypes = [vp]
+        L.orbx_pyramid_level.argtypes = [vp, i32, i32, i32, vp, sz, pi, pi]
+        L.orbx_set_stream.argtypes = [vp, vp]
+        L.orbx_stream.argtypes = [vp]
+        L.orbx_stream.restype = vp
+        L.orbx_set_chunk.argtypes = [vp, i32]
+        L.orbx_last_error.argtypes = [vp]
+        L.orbx_last_error.restype = C.c_char_p
+        L.orbx_debug_blurred.argtypes = [vp, i32, i32, vp, sz]
+        L.orbx_debug_candidates.argtypes = [vp, i32, i32, vp, i32, pi]
+        L.orbx_debug_level_keypoints.argtypes = [vp, i32, i32, vp, i32, pi]
+        L.orbx_profile.argtypes = [vp, i32]
+        L.orbx_stage_ms.argtypes = [vp, vp, vp, i32]
+        L.orbx_plan_describe.argtypes = [i32, f32, i32, i32, i32, i32, i32] + [vp] * 6
+        L.orbm_hamming_bf.argtypes = [vp, i32, vp, i32, i32, vp, vp, vp, i32]
+        _lib = L
+    return _lib
+
+
+def _ptr(a):
+    """Raw address of a numpy array or a torch tensor (host or CUDA)."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    return a.data_ptr()
+
+
+def plan_describe(nfeatures, scale_factor, nlevels, ini_th, min_th, w, h):
+    """Host-only geometry of the extractor for one image shape (no GPU needed)."""
+    arrs = [np.zeros(nlevels, np.int32) for _ in range(6)]
+    rc = lib().orbx_plan_describe(nfeatures, scale_factor, nlevels, ini_th, min_th, w, h, *(a.ctypes.data for a in arrs))
+    if rc:
+        raise OrbError(rc, "unsupported shape" if rc == ORBX_E_SHAPE else "bad argument")
+    return dict(zip(("level_w", "level_h", "cells", "quota", "n_ini", "cand_cap"), arrs))
+
+
+class ORBextractor:
+    """ORB_SLAM2::ORBextractor (include/ORBextractor.h:47-111) on one B200.
+
+    ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST) and
+    extractor(image, mask) -> (keypoints, descriptors) follow the reference; extract_batch
+    runs many equally sized frames per launch.
+    """
+
+    HARRIS_SCORE, FAST_SCORE = 0, 1
+
+    def __init__(self, nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, device=0):
+        self._L = lib()
+        self._h = C.c_void_p()
+        self.nfeatures, self.nlevels = int(nfeatures), int(nlevels)
+        rc = self._L.orbx_create(C.byref(self._h), nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, device)
+        if rc:
+            self._h = C.c_void_p()
+            raise OrbError(rc, "orbx_create failed (no CUDA device?)" if rc == ORBX_E_CUDA else "bad extractor parameters")
+        self._scale_factor = float(np.float32(scaleFactor))
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._L.orbx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def _check(self, rc, allow=()):
+        if rc and rc not in allow:
+            raise OrbError(rc, self._L.orbx_last_error(self._h).decode())
+        return rc
+
+    # ---- accessors, include/ORBextractor.h:64-84
+    def _tables(self):
+        n = self.nlevels
+        out = [np.zeros(n, np.float32) for _ in range(4)] + [np.zeros(n, np.int32)]
+        self._check(self._L.orbx_tables(self._h, *(a.ctypes.data for a in out)))
+        return out
+
+    def GetLevels(self):
+        return self._L.orbx_levels(self._h)
+
+    def GetScaleFactor(self):
+        return self._scale_factor
+
+    def GetScaleFactors(self):
+        return self._tables()[0]
+
+    def GetInverseScaleFactors(self):
+        return self._tables()[1]
+
+    def GetScaleSigmaSquares(self):
+        return self._tables()[2]
+
+    def GetInverseScaleSigmaSquares(self):
+        return self._tables()[3]
+
+    def features_per_level(self):
+        return self._tables()[4]
+
+    def default_capacity(self):
+        # DistributeOctTree returns >= N per level, at most N+2 (or 4*nIni): leave generous room
+        return self.nfeatures + 4 * self.nlevels + 64
+
+    # ---- operator(), include/ORBextractor.h:60
+    def __call__(self, image, mask=None, capacity=None):
+        """Returns (keypoints [n] structured as cv::KeyPoint, descriptors [n,32] uint8).
+        An empty image leaves "outputs untouched" in the reference; here it returns (None, None)."""
+        image = np.asarray(image)
+        if image.size == 0:
+            return None, None
+        assert image.dtype == np.uint8 and image.ndim == 2, "CV_8UC1 expected (src/ORBextractor.cc:1091)"
+        if not image.flags.c_contiguous and image.strides[1] != 1:
+            image = np.ascontiguousarray(image)
+        cap = capacity or self.default_capacity()
+        kps = np.zeros(cap, KP_DTYPE)
+        desc = np.zeros((cap, 32), np.uint8)
+        n = np.zeros(1, np.int32)
+        h, w = image.shape
+        self._check(self._L.orbx_extract(self._h, image.ctypes.data, w, h, image.strides[0], kps.ctypes.data,
+                                         desc.ctypes.data, cap, n.ctypes.data))
+        k = int(n[0])
+        return kps[:k].copy(), desc[:k].copy()
+
+    def extract_batch(self, frames, capacity=None, out=None):
+        """frames: [B,H,W] uint8 numpy array (host) -> (kps [B,cap], desc [B,cap,32], n [B])."""
+        frames = np.ascontiguousarray(frames)
+        assert frames.dtype == np.uint8 and frames.ndim == 3
+        b, h, w = frames.shape
+        cap = capacity or self.default_capacity()
+        if out is None:
+            out = (np.zeros((b, cap), KP_DTYPE), np.zeros((b, cap, 32), np.uint8), np.zeros(b, np.int32))
+        kps, desc, n = out
+        self._check(self._L.orbx_extract_batch(self._h, frames.ctypes.data, h * w, b, w, h, w, kps.ctypes.data,
+                                               desc.ctypes.data, cap, n.ctypes.data))
+        return kps, desc, n
+
+    def extract_batch_raw(self, imgs, frame_stride, batch, w, h, pitch, kps, desc, cap, n_out, asynchronous=False):
+        """Thin pass-through of orbx_extract_batch[_async]: every argument may be numpy or torch."""
+        fn = self._L.orbx_extract_batch_async if asynchronous else self._L.orbx_extract_batch
+        return self._check(fn(self._h, _ptr(imgs), frame_stride, batch, w, h, pitch, _ptr(kps), _ptr(desc), cap, _ptr(n_out)))
+
+    def sync(self):
+        self._check(self._L.orbx_sync(self._h))
+
+    def set_stream(self, cuda_stream_handle):
+        self._check(self._L.orbx_set_stream(self._h, cuda_stream_handle))
+
+    def set_chunk(self, frames):
+        self._check(self._L.orbx_set_chunk(self._h, frames))
+
+    # ---- mvImagePyramid, include/ORBextractor.h:86
+    def pyramid(self, level, frame=0, with_border=False):
+        w, h = C.c_int(), C.c_int()
+        self._check(self._L.orbx_pyramid_level(self._h, frame, level, int(with_border), None, 0, C.byref(w), C.byref(h)))
+        out = np.zeros((h.value, w.value), np.uint8)
+        self._check(self._L.orbx_pyramid_level(self._h, frame, level, int(with_border), out.ctypes.data, out.strides[0], None, None))
+        return out
+
+    @property
+    def mvImagePyramid(self):
+        return [self.pyramid(l) for l in range(self.nlevels)]
+
+    # ---- stage taps
+    def blurred(self, level, frame=0):
+        ref = self.pyramid(level, frame)
+        out = np.zeros_like(ref)
+        self._check(self._L.orbx_debug_blurred(self._h, frame, level, out.ctypes.data, out.strides[0]))
+        return out
+
+    def _packed(self, fn, level, frame):
+        n = C.c_int()
+        self._check(fn(self._h, frame, level, None, 0, C.byref(n)))
+        out = np.zeros((max(n.value, 1), 3), np.int32)
+        self._check(fn(self._h, frame, level, out.ctypes.data, n.value, C.byref(n)))
+        return out[:n.value]
+
+    def candidates(self, level, frame=0):
+        return self._packed(self._L.orbx_debug_candidates, level, frame)
+
+    def level_keypoints(self, level, frame=0):
+        return self._packed(self._L.orbx_debug_level_keypoints, level, frame)
+
+    def profile(self, enable=True):
+        self._check(self._L.orbx_profile(self._h, int(enable)))
+
+    def stage_ms(self, reset=True):
+        ms = np.zeros(len(STAGES), np.float32)
+        cnt = np.zeros(len(STAGES), np.int32)
+        self._check(self._L.orbx_stage_ms(self._h, ms.ctypes.data, cnt.ctypes.data, int(reset)))
+        return dict(zip(STAGES, ms.tolist())), dict(zip(STAGES, cnt.tolist()))
+
+
+class ORBmatcher:
+    """Hamming part of ORB_SLAM2::ORBmatcher (include/ORBmatcher.h:43-100)."""
+    TH_LOW, TH_HIGH, HISTO_LENGTH = 50, 100, 30   # src/ORBmatcher.cc:37-39
+
+    def __init__(self, nnratio=0.6, checkOri=True, device=0):
+        self.mfNNratio, self.mbCheckOrientation, self.device = np.float32(nnratio), bool(checkOri), device
+
+    @staticmethod
+    def DescriptorDistance(a, b, device=0):
+        """src/ORBmatcher.cc:46-63 for one pair (runs the brute-force kernel on a 1x1 problem)."""
+        _, d, _ = hamming_bf(np.asarray(a, np.uint8).reshape(1, 32), np.asarray(b, np.uint8).reshape(1, 32), device)
+        return int(d[0])
+
+
+def hamming_bf(queries, train, device=0, nprob=1):
+    """All-pairs Hamming search: per query (best index, best distance, second distance)."""
+    L = lib()
+    if isinstance(queries, np.ndarray):
+        queries = np.ascontiguousarray(queries, np.uint8)
+        train = np.ascontiguousarray(train, np.uint8)
+        nq, nt = queries.shape[-2], train.shape[-2]
+        outs = [np.zeros(nprob * nq, np.int32) for _ in range(3)]
+    else:
+        import torch
+        nq, nt = queries.shape[-2], train.shape[-2]
+        outs = [torch.zeros(nprob * nq, dtype=torch.int32, device=queries.device) for _ in range(3)]
+    rc = L.orbm_hamming_bf(_ptr(queries), nq, _ptr(train), nt, nprob, _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2]), device)
+    if rc:
+        raise OrbError(rc, "orbm_hamming_bf failed")
+    return tuple(outs)

@@ -1,0 +1,457 @@
+// orb_capi.cu -- context management and the extern "C" boundary of the extractor
+// (include/orb_b200.h).  Host code only: owns device memory, the stream, the per-shape plan
+// and the chunked batch loop; all arithmetic lives in the kernels.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "orb_device.cuh"
+#include "orb_launch.h"
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    cudaError_t reserve(size_t n)
+    {
+        if (n <= bytes) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; bytes = 0;
+        cudaError_t e = cudaMalloc(&p, n);
+        if (e == cudaSuccess) bytes = n;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+};
+
+struct StageTimer {
+    cudaEvent_t ev[2];
+    int stage;
+};
+
+} // namespace
+
+struct orbx_ctx {
+    OrbParams params;
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    int chunk = 32;
+    std::string err;
+
+    // plan of the current shape
+    bool have_plan = false;
+    OrbPlan plan;
+    DevBuf taps;
+
+    // per-chunk device buffers
+    DevBuf img_stage, pyr, blur, cand, node_of, counts, lkp, out_kps, out_desc, out_n, border_tmp;
+    int buf_frames = 0;          // frames the buffers are sized for
+    int buf_cap = 0;             // output capacity per frame the staging outputs are sized for
+
+    // what is resident from the last call (for orbx_pyramid_level / debug taps)
+    int last_first = 0, last_count = 0;    // frames [last_first, last_first+last_count) of the last batch
+    const uint8_t* last_img0 = nullptr; size_t last_img0_stride = 0; int last_img0_pitch = 0;
+
+    // profiling
+    bool profile = false;
+    std::vector<StageTimer> pending;
+    std::vector<cudaEvent_t> free_events;
+    float stage_ms[ORBX_STAGE_COUNT] = { 0 };
+    int stage_launches[ORBX_STAGE_COUNT] = { 0 };
+};
+
+namespace {
+
+int fail(orbx_ctx* c, int code, const char* fmt, ...)
+{
+    if (c) {
+        char buf[512];
+        va_list ap; va_start(ap, fmt);
+        vsnprintf(buf, sizeof(buf), fmt, ap);
+        va_end(ap);
+        c->err = buf;
+    }
+    return code;
+}
+
+#define CU(c, call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return fail((c), ORBX_E_CUDA, "%s: %s", #call, cudaGetErrorString(e__)); } while (0)
+
+bool is_device_ptr(const void* p)
+{
+    if (!p) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+int ensure_plan(orbx_ctx* c, int w, int h)
+{
+    if (c->have_plan && c->plan.w == w && c->plan.h == h) return ORBX_OK;
+    std::vector<OrbTap> taps;
+    OrbPlan plan;
+    if (orb_plan_build(&c->params, w, h, &plan, &taps)) return fail(c, ORBX_E_SHAPE, "unsupported image shape %dx%d", w, h);
+    CU(c, cudaStreamSynchronize(c->stream));
+    CU(c, c->taps.reserve(sizeof(OrbTap) * (taps.size() + 1)));
+    if (!taps.empty()) CU(c, cudaMemcpy(c->taps.p, taps.data(), sizeof(OrbTap) * taps.size(), cudaMemcpyHostToDevice));
+    c->plan = plan;
+    c->have_plan = true;
+    c->buf_frames = 0;
+    return ORBX_OK;
+}
+
+int ensure_buffers(orbx_ctx* c, int frames, int cap, bool stage_in, size_t in_frame_bytes, bool stage_out)
+{
+    const OrbPlan& P = c->plan;
+    if (frames > c->buf_frames) {
+        CU(c, cudaStreamSynchronize(c->stream));
+        CU(c, c->pyr.reserve((size_t)frames * P.pyr_bytes + 256));
+        CU(c, c->blur.reserve((size_t)frames * P.blur_bytes + 256));
+        CU(c, c->cand.reserve((size_t)frames * P.cand_per_frame * 4 + 256));
+        CU(c, c->node_of.reserve((size_t)frames * P.cand_per_frame * 2 + 256));
+        CU(c, c->counts.reserve((size_t)frames * ORB_MAX_LEVELS * 4 * 2));
+        CU(c, c->lkp.reserve((size_t)frames * P.kp_per_frame * 4 + 256));
+        c->buf_frames = frames;
+    }
+    if (stage_in) CU(c, c->img_stage.reserve((size_t)frames * in_frame_bytes + 256));
+    if (stage_out) {
+        CU(c, c->out_kps.reserve((size_t)frames * cap * sizeof(orbx_kp)));
+        CU(c, c->out_desc.reserve((size_t)frames * cap * 32));
+        CU(c, c->out_n.reserve((size_t)frames * 4));
+    }
+    return ORBX_OK;
+}
+
+cudaEvent_t get_event(orbx_ctx* c)
+{
+    if (!c->free_events.empty()) { cudaEvent_t e = c->free_events.back(); c->free_events.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+struct StageScope {
+    orbx_ctx* c; StageTimer t; bool on;
+    StageScope(orbx_ctx* ctx, int stage) : c(ctx), on(ctx->profile)
+    {
+        if (on) { t.stage = stage; t.ev[0] = get_event(c); t.ev[1] = get_event(c); cudaEventRecord(t.ev[0], c->stream); }
+    }
+    ~StageScope() { if (on) { cudaEventRecord(t.ev[1], c->stream); c->pending.push_back(t); } }
+};
+
+void collect_timers(orbx_ctx* c)
+{
+    for (StageTimer& t : c->pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, t.ev[0], t.ev[1]) == cudaSuccess) { c->stage_ms[t.stage] += ms; c->stage_launches[t.stage] += 1; }
+        else cudaGetLastError();
+        c->free_events.push_back(t.ev[0]); c->free_events.push_back(t.ev[1]);
+    }
+    c->pending.clear();
+}
+
+// Enqueue the whole extractor for `frames` frames whose level-0 images are device resident.
+int enqueue_chunk(orbx_ctx* c, const uint8_t* d_img, size_t frame_stride, int pitch, int frames,
+                  orbx_kp* d_kps, uint8_t* d_desc, int* d_n, int cap)
+{
+    const OrbPlan& P = c->plan;
+    OrbBatch io;
+    io.img0 = d_img; io.img0_stride = frame_stride; io.img0_pitch = pitch;
+    io.pyr = (uint8_t*)c->pyr.p; io.blur = (uint8_t*)c->blur.p;
+    io.cand = (uint32_t*)c->cand.p; io.node_of = (uint16_t*)c->node_of.p;
+    io.cand_count = (int*)c->counts.p;
+    io.lkp_count = io.cand_count + (size_t)c->buf_frames * ORB_MAX_LEVELS;
+    io.lkp = (uint32_t*)c->lkp.p;
+    io.kps = d_kps; io.desc = d_desc; io.n_out = d_n; io.cap = cap;
+    io.taps = (const OrbTap*)c->taps.p;
+    cudaStream_t st = c->stream;
+    CU(c, cudaMemsetAsync(io.cand_count, 0, (size_t)frames * ORB_MAX_LEVELS * 4, st));
+    { StageScope s(c, ORBX_STAGE_PYRAMID); CU(c, orb_launch_pyramid(P, io, frames, st)); }
+    { StageScope s(c, ORBX_STAGE_FAST); CU(c, orb_launch_fast(P, io, frames, st)); }
+    { StageScope s(c, ORBX_STAGE_BLUR); CU(c, orb_launch_blur(P, io, frames, st)); }
+    { StageScope s(c, ORBX_STAGE_OCTREE); CU(c, orb_launch_octree(P, io, frames, st)); }
+    { StageScope s(c, ORBX_STAGE_DESCRIBE); CU(c, orb_launch_describe(P, io, frames, st)); }
+    return ORBX_OK;
+}
+
+int run_batch(orbx_ctx* c, const uint8_t* imgs, size_t frame_stride, int batch, int w, int h, size_t pitch,
+              orbx_kp* kps, uint8_t* desc, int cap, int* n_out, bool async_only)
+{
+    if (!c) return ORBX_E_ARG;
+    if (!imgs || batch <= 0 || w <= 0 || h <= 0) return fail(c, ORBX_E_EMPTY, "empty image");
+    if (pitch < (size_t)w || cap <= 0 || !kps || !desc || !n_out) return fail(c, ORBX_E_ARG, "bad argument");
+    if (batch > 1 && frame_stride < pitch * (size_t)(h - 1) + (size_t)w) return fail(c, ORBX_E_ARG, "frame_stride too small");
+    CU(c, cudaSetDevice(c->device));
+    int rc = ensure_plan(c, w, h);
+    if (rc) return rc;
+    const bool in_dev = is_device_ptr(imgs);
+    const bool kps_dev = is_device_ptr(kps), desc_dev = is_device_ptr(desc), n_dev = is_device_ptr(n_out);
+    if (async_only && !(in_dev && kps_dev && desc_dev && n_dev)) return fail(c, ORBX_E_ARG, "async entry point needs device pointers");
+    const bool stage_out = !(kps_dev && desc_dev && n_dev);
+    const int chunk = batch < c->chunk ? batch : c->chunk;
+    const size_t in_frame_bytes = pitch * (size_t)h;
+    rc = ensure_buffers(c, chunk, cap, !in_dev, in_frame_bytes, stage_out);
+    if (rc) return rc;
+    cudaStream_t st = c->stream;
+    for (int f0 = 0; f0 < batch; f0 += chunk) {
+        const int nf = batch - f0 < chunk ? batch - f0 : chunk;
+        const uint8_t* d_img; size_t d_stride;
+        if (in_dev) { d_img = imgs + (size_t)f0 * frame_stride; d_stride = frame_stride; }
+        else {
+            // host frames -> staging, keeping the caller's row pitch (one 2-D copy: rows = frames)
+            d_img = (const uint8_t*)c->img_stage.p; d_stride = in_frame_bytes;
+            if (frame_stride == in_frame_bytes || nf == 1)
+                CU(c, cudaMemcpyAsync(c->img_stage.p, imgs + (size_t)f0 * frame_stride, (size_t)(nf - 1) * in_frame_bytes + pitch * (size_t)(h - 1) + w, cudaMemcpyHostToDevice, st));
+            else
+                CU(c, cudaMemcpy2DAsync(c->img_stage.p, in_frame_bytes, imgs + (size_t)f0 * frame_stride, frame_stride,
+                                        pitch * (size_t)(h - 1) + w, nf, cudaMemcpyHostToDevice, st));
+        }
+        orbx_kp* dk = stage_out ? (orbx_kp*)c->out_kps.p : kps + (size_t)f0 * cap;
+        uint8_t* dd = stage_out ? (uint8_t*)c->out_desc.p : desc + (size_t)f0 * cap * 32;
+        int* dn = stage_out ? (int*)c->out_n.p : n_out + f0;
+        rc = enqueue_chunk(c, d_img, d_stride, (int)pitch, nf, dk, dd, dn, cap);
+        if (rc) return rc;
+        if (stage_out) {
+            const cudaMemcpyKind kk = kps_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+            const cudaMemcpyKind kd = desc_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+            const cudaMemcpyKind kn = n_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+            CU(c, cudaMemcpyAsync(kps + (size_t)f0 * cap, dk, (size_t)nf * cap * sizeof(orbx_kp), kk, st));
+            CU(c, cudaMemcpyAsync(desc + (size_t)f0 * cap * 32, dd, (size_t)nf * cap * 32, kd, st));
+            CU(c, cudaMemcpyAsync(n_out + f0, dn, (size_t)nf * 4, kn, st));
+        }
+        c->last_first = f0; c->last_count = nf;
+        c->last_img0 = d_img; c->last_img0_stride = d_stride; c->last_img0_pitch = (int)pitch;
+        // the single set of chunk buffers is reused: the next chunk's H2D must not overtake this
+        // chunk's kernels -- guaranteed by stream order.
+    }
+    if (async_only) return ORBX_OK;
+    CU(c, cudaStreamSynchronize(st));
+    collect_timers(c);
+    if (!n_dev) for (int f = 0; f < batch; ++f) if (n_out[f] > cap) return fail(c, ORBX_E_CAPACITY, "frame %d: %d keypoints > capacity %d", f, n_out[f], cap);
+    return ORBX_OK;
+}
+
+int resident_frame(orbx_ctx* c, int frame, int level)
+{
+    if (!c || !c->have_plan || c->last_count == 0) return -1;
+    if (level < 0 || level >= c->plan.nlevels) return -1;
+    const int rel = frame - c->last_first;
+    if (rel < 0 || rel >= c->last_count) return -1;
+    return rel;
+}
+
+int copy_out_2d(orbx_ctx* c, uint8_t* dst, size_t dst_pitch, const uint8_t* d_src, size_t src_pitch, int w, int h)
+{
+    const cudaMemcpyKind k = is_device_ptr(dst) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    CU(c, cudaMemcpy2DAsync(dst, dst_pitch, d_src, src_pitch, (size_t)w, (size_t)h, k, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return ORBX_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int orbx_create(orbx_ctx** out, int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST, int device)
+{
+    if (!out) return ORBX_E_ARG;
+    *out = nullptr;
+    OrbParams p;
+    if (orb_params_init(&p, nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST)) return ORBX_E_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) { cudaGetLastError(); return ORBX_E_CUDA; }
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return ORBX_E_CUDA; }
+    orbx_ctx* c = new (std::nothrow) orbx_ctx();
+    if (!c) return ORBX_E_ARG;
+    c->params = p; c->device = device;
+    if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); delete c; return ORBX_E_CUDA; }
+    c->stream = c->own_stream;
+    *out = c;
+    return ORBX_OK;
+}
+
+void orbx_destroy(orbx_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    collect_timers(c);
+    for (cudaEvent_t e : c->free_events) cudaEventDestroy(e);
+    DevBuf* bufs[] = { &c->taps, &c->img_stage, &c->pyr, &c->blur, &c->cand, &c->node_of, &c->counts, &c->lkp,
+                       &c->out_kps, &c->out_desc, &c->out_n, &c->border_tmp };
+    for (DevBuf* b : bufs) b->release();
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+int orbx_levels(const orbx_ctx* c) { return c ? c->params.nlevels : 0; }
+
+int orbx_tables(const orbx_ctx* c, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2, int* per_level)
+{
+    if (!c) return ORBX_E_ARG;
+    for (int i = 0; i < c->params.nlevels; ++i) {
+        if (scale) scale[i] = c->params.scale[i];
+        if (inv_scale) inv_scale[i] = c->params.inv_scale[i];
+        if (sigma2) sigma2[i] = c->params.sigma2[i];
+        if (inv_sigma2) inv_sigma2[i] = c->params.inv_sigma2[i];
+        if (per_level) per_level[i] = c->params.per_level[i];
+    }
+    return ORBX_OK;
+}
+
+int orbx_shape_supported(const orbx_ctx* c, int w, int h)
+{
+    if (!c) return 0;
+    OrbPlan plan;
+    return orb_plan_build(&c->params, w, h, &plan, nullptr) == 0;
+}
+
+int orbx_extract(orbx_ctx* c, const uint8_t* img, int w, int h, size_t pitch, orbx_kp* kps, uint8_t* desc, int capacity, int* n_out)
+{
+    return run_batch(c, img, pitch * (size_t)(h > 0 ? h : 0), 1, w, h, pitch, kps, desc, capacity, n_out, false);
+}
+
+int orbx_extract_batch(orbx_ctx* c, const uint8_t* imgs, size_t frame_stride, int batch, int w, int h, size_t pitch,
+                       orbx_kp* kps, uint8_t* desc, int cap_per_frame, int* n_out)
+{
+    return run_batch(c, imgs, frame_stride, batch, w, h, pitch, kps, desc, cap_per_frame, n_out, false);
+}
+
+int orbx_extract_batch_async(orbx_ctx* c, const uint8_t* d_imgs, size_t frame_stride, int batch, int w, int h, size_t pitch,
+                             orbx_kp* d_kps, uint8_t* d_desc, int cap_per_frame, int* d_n_out)
+{
+    return run_batch(c, d_imgs, frame_stride, batch, w, h, pitch, d_kps, d_desc, cap_per_frame, d_n_out, true);
+}
+
+int orbx_sync(orbx_ctx* c)
+{
+    if (!c) return ORBX_E_ARG;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaStreamSynchronize(c->stream));
+    collect_timers(c);
+    return ORBX_OK;
+}
+
+int orbx_pyramid_level(orbx_ctx* c, int frame, int level, int with_border, uint8_t* dst, size_t dst_pitch, int* w, int* h)
+{
+    if (!c) return ORBX_E_ARG;
+    const int rel = resident_frame(c, frame, level);
+    if (rel < 0) return fail(c, ORBX_E_ARG, "frame %d level %d is not resident", frame, level);
+    const OrbLevel& L = c->plan.lv[level];
+    const int b = with_border ? ORB_EDGE : 0;
+    if (w) *w = L.w + 2 * b;
+    if (h) *h = L.h + 2 * b;
+    if (!dst) return ORBX_OK;
+    CU(c, cudaSetDevice(c->device));
+    const uint8_t* src; int spitch;
+    if (level == 0) { src = c->last_img0 + (size_t)rel * c->last_img0_stride; spitch = c->last_img0_pitch; }
+    else { src = (const uint8_t*)c->pyr.p + (size_t)rel * c->plan.pyr_bytes + L.img_off; spitch = L.pitch; }
+    if (!with_border) return copy_out_2d(c, dst, dst_pitch, src, (size_t)spitch, L.w, L.h);
+    const int bw = L.w + 2 * b, bh = L.h + 2 * b;
+    CU(c, c->border_tmp.reserve((size_t)bw * bh));
+    CU(c, orb_launch_border(src, L.w, L.h, spitch, (uint8_t*)c->border_tmp.p, bw, b, c->stream));
+    return copy_out_2d(c, dst, dst_pitch, (const uint8_t*)c->border_tmp.p, (size_t)bw, bw, bh);
+}
+
+int orbx_set_stream(orbx_ctx* c, void* cuda_stream)
+{
+    if (!c) return ORBX_E_ARG;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaStreamSynchronize(c->stream));
+    collect_timers(c);
+    c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+    return ORBX_OK;
+}
+
+void* orbx_stream(const orbx_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+int orbx_set_chunk(orbx_ctx* c, int frames_per_chunk)
+{
+    if (!c || frames_per_chunk < 1) return ORBX_E_ARG;
+    c->chunk = frames_per_chunk;
+    return ORBX_OK;
+}
+
+const char* orbx_last_error(const orbx_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+int orbx_debug_blurred(orbx_ctx* c, int frame, int level, uint8_t* dst, size_t dst_pitch)
+{
+    if (!c || !dst) return ORBX_E_ARG;
+    const int rel = resident_frame(c, frame, level);
+    if (rel < 0) return fail(c, ORBX_E_ARG, "frame %d level %d is not resident", frame, level);
+    const OrbLevel& L = c->plan.lv[level];
+    CU(c, cudaSetDevice(c->device));
+    return copy_out_2d(c, dst, dst_pitch, (const uint8_t*)c->blur.p + (size_t)rel * c->plan.blur_bytes + L.blur_off, (size_t)L.pitch, L.w, L.h);
+}
+
+static int debug_packed(orbx_ctx* c, int frame, int level, bool after_octree, int* xys, int cap, int* n)
+{
+    if (!c || !n) return ORBX_E_ARG;
+    const int rel = resident_frame(c, frame, level);
+    if (rel < 0) return fail(c, ORBX_E_ARG, "frame %d level %d is not resident", frame, level);
+    const OrbLevel& L = c->plan.lv[level];
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaStreamSynchronize(c->stream));
+    const int* counts = (const int*)c->counts.p + (after_octree ? (size_t)c->buf_frames * ORB_MAX_LEVELS : 0);
+    int cnt = 0;
+    CU(c, cudaMemcpy(&cnt, counts + (size_t)rel * ORB_MAX_LEVELS + level, 4, cudaMemcpyDeviceToHost));
+    *n = cnt;
+    if (!xys || cnt == 0) return ORBX_OK;
+    const int lim = after_octree ? L.kp_cap : L.cand_cap;
+    const int m = cnt < lim ? cnt : lim;
+    std::vector<uint32_t> tmp((size_t)m);
+    const uint32_t* src = after_octree ? (const uint32_t*)c->lkp.p + (size_t)rel * c->plan.kp_per_frame + L.kp_off
+                                       : (const uint32_t*)c->cand.p + (size_t)rel * c->plan.cand_per_frame + L.cand_off;
+    CU(c, cudaMemcpy(tmp.data(), src, (size_t)m * 4, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < m && i < cap; ++i) { xys[3 * i] = ORB_PX(tmp[i]); xys[3 * i + 1] = ORB_PY(tmp[i]); xys[3 * i + 2] = ORB_PS(tmp[i]); }
+    return ORBX_OK;
+}
+
+int orbx_debug_candidates(orbx_ctx* c, int frame, int level, int* xys, int cap, int* n) { return debug_packed(c, frame, level, false, xys, cap, n); }
+int orbx_debug_level_keypoints(orbx_ctx* c, int frame, int level, int* xys, int cap, int* n) { return debug_packed(c, frame, level, true, xys, cap, n); }
+
+int orbx_profile(orbx_ctx* c, int enable)
+{
+    if (!c) return ORBX_E_ARG;
+    c->profile = enable != 0;
+    return ORBX_OK;
+}
+
+int orbx_stage_ms(orbx_ctx* c, float* ms, int* launches, int reset)
+{
+    if (!c) return ORBX_E_ARG;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaStreamSynchronize(c->stream));
+    collect_timers(c);
+    for (int i = 0; i < ORBX_STAGE_COUNT; ++i) {
+        if (ms) ms[i] = c->stage_ms[i];
+        if (launches) launches[i] = c->stage_launches[i];
+        if (reset) { c->stage_ms[i] = 0.f; c->stage_launches[i] = 0; }
+    }
+    return ORBX_OK;
+}
+
+// Host-only view of the plan for tests (no GPU needed): level sizes, processed cells, quotas, roots.
+int orbx_plan_describe(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST, int w, int h,
+                       int* level_w, int* level_h, int* cells, int* quota, int* n_ini, int* cand_cap)
+{
+    OrbParams p;
+    if (orb_params_init(&p, nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST)) return ORBX_E_ARG;
+    OrbPlan plan;
+    if (orb_plan_build(&p, w, h, &plan, nullptr)) return ORBX_E_SHAPE;
+    for (int l = 0; l < nlevels; ++l) {
+        if (level_w) level_w[l] = plan.lv[l].w;
+        if (level_h) level_h[l] = plan.lv[l].h;
+        if (cells) cells[l] = plan.lv[l].ncx * plan.lv[l].ncy;
+        if (quota) quota[l] = plan.lv[l].quota;
+        if (n_ini) n_ini[l] = plan.lv[l].nIni;
+        if (cand_cap) cand_cap[l] = plan.lv[l].cand_cap;
+    }
+    return ORBX_OK;
+}
+
+} // extern "C"
