@@ -29,7 +29,7 @@ def check(w, h, nf, seed, verbose=True):
     for l in range(8):
         po, pg = O.pyramid(l), G.pyramid(l)
         pyr_bad = int((po != pg).sum()) if po.shape == pg.shape else -1
-        pob, pgb = O.pyramid(l, True), G.pyramid(l, True)
+        pob, pgb = O.pyramid(l, True), G.pyramid(l, with_border=True)
         brd_bad = int((pob != pgb).sum()) if pob.shape == pgb.shape else -1
         bo = O.blurred(l)
         bg = G.blurred(l)
