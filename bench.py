@@ -1,0 +1,337 @@
+#!/usr/bin/env python3
+"""Benchmark of the ORB front-end hot path (BASELINE.json metric: ORB frames/s @1241x376, nfeatures=2000).
+
+  python bench.py --gpus N --steps K --warmup W            our arm (CUDA, liborb_b200.so)
+  python bench.py --impl reference ...                      the reference's own CPU code (oracle/_ref)
+
+One step = ORBextractor::operator() over one batch of synthetic KITTI-shape frames
+(BASELINE.json configs[1]); batches are larger than the 126 MB L2 so every step starts cold.
+Multi-GPU (torchrun): frames are independent, so each rank extracts its own batch (weak scaling);
+NCCL is used only to gather timings and counts.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (w, h, nfeatures, frames per step per GPU)
+    "kitti_1241x376_nf2000": (1241, 376, 2000, 512),
+    "tum_640x480_nf1000": (640, 480, 1000, 1024),
+    "euroc_752x480_nf1200": (752, 480, 1200, 256),
+    "hd_1920x1080_nf4000": (1920, 1080, 4000, 128),
+}
+LEVELS, SCALE, INI_TH, MIN_TH = 8, 1.2, 20, 7
+
+
+def level_pixels(w, h):
+    """Sum of level pixels P, last level p7."""
+    import orb_slam2_chinesenotes_b200 as ob
+    d = ob.plan_describe(1000, SCALE, LEVELS, INI_TH, MIN_TH, w, h)
+    px = (d["level_w"].astype(np.int64) * d["level_h"].astype(np.int64))
+    return int(px.sum()), int(px[-1]), int(px[0])
+
+
+def algorithmic_bytes(w, h):
+    """Per-frame algorithmic bytes of each dense stage."""
+    P, p7, WH = level_pixels(w, h)
+    return {"pyramid": 2 * P - p7 - WH, "fast": P, "blur": 2 * P}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def synth_batch_torch(batch, w, h, seed, device):
+    """Synthetic frames on the GPU: smoothed noise, mean 128 / std 48, low-contrast bottom band,
+    hard-edged rectangles (the recipe of tests/synth.py, generated with torch for speed)."""
+    import torch
+    import torch.nn.functional as F
+    g = torch.Generator(device=device).manual_seed(seed)
+    out = torch.empty((batch, h, w), dtype=torch.uint8, device=device)
+    sigma, r = 2.5, 8
+    x = torch.arange(-r, r + 1, device=device, dtype=torch.float32)
+    k = torch.exp(-0.5 * (x / sigma) ** 2)
+    k = k / k.sum()
+    rng = np.random.default_rng(seed)
+    step = 32
+    for b0 in range(0, batch, step):
+        nb = min(step, batch - b0)
+        n = torch.randint(0, 256, (nb, 1, h, w), generator=g, device=device, dtype=torch.uint8).float()
+        n = F.conv2d(F.pad(n, (r, r, 0, 0), mode="reflect"), k.view(1, 1, 1, -1))
+        n = F.conv2d(F.pad(n, (0, 0, r, r), mode="reflect"), k.view(1, 1, -1, 1))
+        n = n[:, 0]
+        n = (n - n.mean(dim=(1, 2), keepdim=True)) / n.std(dim=(1, 2), keepdim=True) * 48 + 128
+        y0 = int(h * 0.75)
+        n[:, y0:] = (n[:, y0:] - 128) * 0.12 + 128
+        img = n.round().clamp(0, 255).to(torch.uint8)
+        for i in range(nb):
+            for _ in range(20):
+                rx = int(rng.integers(0, w - 40)); ry = int(rng.integers(0, h - 40))
+                img[i, ry:ry + int(rng.integers(8, 40)), rx:rx + int(rng.integers(8, 40))] = int(rng.integers(0, 256))
+        out[b0:b0 + nb] = img
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def load_cpu_checker():
+    """(library, kind): oracle/_ref (the reference's own sources) when built, else the oracle port.
+    bench.py may execute oracle/ only here: as the timed CPU baseline, never as the product."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    r = oracle_lib.ref()
+    if r is not None:
+        return r.orbref_extract_bench, "reference"
+    return oracle_lib.oracle().orbo_extract_bench, "port"
+
+
+def cpu_frames_per_s(frames_np, nfeatures, threads, reps=1):
+    fn, kind = load_cpu_checker()
+    nfr, h, w = frames_np.shape
+    best = None
+    tot = C.c_longlong()
+    for _ in range(reps):
+        dt = fn(nfeatures, SCALE, LEVELS, INI_TH, MIN_TH, frames_np.ctypes.data, nfr, w, h, threads, C.byref(tot))
+        best = dt if best is None else min(best, dt)
+    return nfr / best, kind, int(tot.value)
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from synth import synth_frame  # numpy generator of the parity tests (no torch / CUDA needed)
+    w, h, nf, _ = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    nsample = int(min(256, max(16, 4 * cores)))
+    frames = np.stack([synth_frame(w, h, 2000 + i) for i in range(min(nsample, 16))])
+    frames = np.concatenate([frames] * ((nsample + len(frames) - 1) // len(frames)))[:nsample]
+    for _ in range(args.warmup):
+        cpu_frames_per_s(frames[:cores], nf, cores)
+    t0 = time.perf_counter()
+    vals = []
+    for _ in range(args.steps):
+        v, kind, _ = cpu_frames_per_s(frames, nf, cores)
+        vals.append(v)
+    dt = time.perf_counter() - t0
+    value = nsample * args.steps / dt
+    sample = f"{nsample} frames per step ({min(nsample, 16)} distinct), {cores} threads, one extractor per thread"
+    print(json.dumps({
+        "impl": "reference", "metric": "orb_extract_frames_per_s", "value": value, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": args.workload, "w": w, "h": h, "nfeatures": nf, "levels": LEVELS},
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import orb_slam2_chinesenotes_b200 as ob
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    w, h, nf, batch = WORKLOADS[args.workload]
+    if args.batch:
+        batch = args.batch
+    ex = ob.ORBextractor(nf, SCALE, LEVELS, INI_TH, MIN_TH, device=local_rank)
+    if args.chunk:
+        ex.set_chunk(args.chunk)
+    cap = ex.default_capacity()
+    frames = synth_batch_torch(batch, w, h, 1000 * 2 + rank * 100003, dev)
+    d_kps = torch.zeros((batch, cap, 7), dtype=torch.float32, device=dev)
+    d_desc = torch.zeros((batch, cap, 32), dtype=torch.uint8, device=dev)
+    d_n = torch.zeros(batch, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream()
+    ex.set_stream(stream.cuda_stream)
+
+    def step_device():
+        ex.extract_batch_raw(frames, h * w, batch, w, h, w, d_kps, d_desc, cap, d_n, asynchronous=True)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    barrier()
+    # ---- device-resident throughput (`value`)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ex.profile(True)
+    ex.stage_ms(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+    e1.record(stream)
+    barrier()
+    ms_dev = e0.elapsed_time(e1)
+    stage_ms, stage_cnt = ex.stage_ms(reset=True)
+    ex.profile(False)
+    nk = d_n.cpu().numpy()
+    assert (nk > 0).all() and (nk <= cap).all(), "extraction produced no keypoints / overflowed"
+
+    # ---- end to end through the C ABI with HOST buffers (pinned): H2D + kernels + D2H per step
+    h_frames = torch.empty((batch, h, w), dtype=torch.uint8).pin_memory()
+    h_frames.copy_(frames)
+    h_kps = torch.empty((batch, cap, 7), dtype=torch.float32).pin_memory()
+    h_desc = torch.empty((batch, cap, 32), dtype=torch.uint8).pin_memory()
+    h_n = torch.empty(batch, dtype=torch.int32).pin_memory()
+
+    def step_host():
+        ex.extract_batch_raw(h_frames, h * w, batch, w, h, w, h_kps, h_desc, cap, h_n, asynchronous=False)
+
+    step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_host()
+    barrier()
+    ms_e2e = 1e3 * (time.perf_counter() - t0)
+    clocks = sampler.stop()
+    assert (h_n.numpy() == nk).all(), "host-buffer path and device-resident path disagree"
+
+    # ---- max over ranks
+    if dist is not None:
+        t = torch.tensor([ms_dev, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_dev, ms_e2e = float(t[0]), float(t[1])
+        kp = torch.tensor([float(nk.sum())], device=dev, dtype=torch.float64)
+        dist.all_reduce(kp)
+        total_kp = float(kp[0])
+    else:
+        total_kp = float(nk.sum())
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    total_frames = batch * world * args.steps
+    value = total_frames / (ms_dev * 1e-3)
+    e2e_value = total_frames / (ms_e2e * 1e-3)
+    # ---- roofline of the dominant kernel (stage times measured above with CUDA events on the stream)
+    bytes_per_frame = algorithmic_bytes(w, h)
+    dom = max(("pyramid", "fast", "blur", "octree", "describe"), key=lambda s: stage_ms[s])
+    peak, peak_src = measured_peak()
+    roof = {"bound": "hbm", "kernel": dom, "peak": peak, "unit": "GB/s", "peak_source": peak_src, "traffic": None,
+            "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()}}
+    if dom in bytes_per_frame:
+        launches = max(stage_cnt[dom], 1)
+        frames_per_launch = batch * args.steps / launches
+        dur_s = stage_ms[dom] * 1e-3 / launches
+        roof["achieved"] = bytes_per_frame[dom] * frames_per_launch / dur_s / 1e9
+        roof["frac"] = roof["achieved"] / peak
+        roof["algorithmic_bytes_per_frame"] = bytes_per_frame[dom]
+    else:
+        roof["achieved"] = None
+        roof["frac"] = None
+    roof["dense_stages"] = {s: {"GB/s": bytes_per_frame[s] * batch * args.steps / (stage_ms[s] * 1e-3) / 1e9,
+                                "frac": bytes_per_frame[s] * batch * args.steps / (stage_ms[s] * 1e-3) / 1e9 / peak}
+                            for s in bytes_per_frame if stage_ms[s] > 0}
+    # ---- CPU baseline on a bounded sample of the same frames (rank 0, N=1 only)
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        ns = int(min(batch, max(16, 4 * cores)))
+        sample = frames[:ns].cpu().numpy()
+        v, kind, _ = cpu_frames_per_s(sample, nf, cores)
+        cpu = {"value": v, "unit": "frames/s", "cores": cores, "kind": kind,
+               "sample": f"first {ns} frames of the step's batch, {cores} threads, one extractor per thread"}
+    chunks = (batch + (args.chunk or 32) - 1) // (args.chunk or 32)
+    print(json.dumps({
+        "metric": "orb_extract_frames_per_s", "value": value, "unit": "frames/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": args.workload, "w": w, "h": h, "nfeatures": nf, "levels": LEVELS,
+                   "frames_per_step_per_gpu": batch, "l2": "inputs larger than L2 (%.0f MB per step)" % (batch * w * h / 1e6),
+                   "keypoints_per_frame": total_kp / (batch * world)},
+        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": batch * w * h,
+                "d2h_bytes_per_step": batch * (cap * 60 + 4), "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": (LEVELS - 1 + 4) * chunks * args.steps,
+        "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
+    }))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="kitti_1241x376_nf2000", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--chunk", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()
