@@ -197,7 +197,10 @@ def run_ours(args, rank, world, local_rank):
     d_kps = torch.zeros((batch, cap, 7), dtype=torch.float32, device=dev)
     d_desc = torch.zeros((batch, cap, 32), dtype=torch.uint8, device=dev)
     d_n = torch.zeros(batch, dtype=torch.int32, device=dev)
-    stream = torch.cuda.current_stream()
+    # a real (non-default) stream: handle 0 would mean "use the context's own stream", and
+    # torch.cuda.Event only sees the stream it is recorded on
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     ex.set_stream(stream.cuda_stream)
 
     def step_device():

@@ -117,16 +117,15 @@ int orb_plan_build(const OrbParams* p, int w, int h, OrbPlan* plan, std::vector<
                     int x0 = ORB_BORDER0 + j * L.wCell, x1 = x0 + L.wCell + 6; if (x1 > maxBorderX) x1 = maxBorderX;
                     int ew = x1 - x0 - 6; if (ew < 0) ew = 0;
                     cap += ((ew + 1) / 2) * ((eh + 1) / 2);                // strict 3x3 maxima cannot be denser
-                    int words = (y1 - y0) * ((x1 - x0 + 3) / 4 + 1);
-                    if (words > plan->fast_tile_words) plan->fast_tile_words = words;
+                    // orb_fast.cu: rows of (4-pixel groups + 2) words; tile has eh+6 rows, score map eh+2
+                    const int tw = (ew + 3) / 4 + 2;
+                    if ((eh + 6) * tw > plan->fast_tile_words) plan->fast_tile_words = (eh + 6) * tw;
+                    if ((eh + 2) * tw > plan->fast_score_words) plan->fast_score_words = (eh + 2) * tw;
                     if (ew * eh > plan->fast_eval_max) plan->fast_eval_max = ew * eh;
-                    int sw = ((ew + 2) * (eh + 2) + 3) / 4;
-                    if (sw > plan->fast_score_words) plan->fast_score_words = sw;
                 }
             }
             // order key (cell, y-in-cell, x-in-cell) must fit 24 bits
             if ((long long)L.ncx * L.ncy * L.wCell * L.hCell >= (1 << 24)) return 1;
-            if (plan->fast_eval_max >= 32768) return 1;                    // queue entries are 15-bit
         }
         L.cell_first = cells; cells += L.ncx * L.ncy;
         L.quota = p->per_level[l];
