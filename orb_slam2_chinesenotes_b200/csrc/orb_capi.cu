@@ -1,6 +1,11 @@
 // orb_capi.cu -- context management and the extern "C" boundary of the extractor
-// (include/orb_b200.h).  Host code only: owns device memory, the stream, the per-shape plan
-// and the chunked batch loop; all arithmetic lives in the kernels.
+// (include/orb_b200.h).  Host code only: owns device memory, streams, the per-shape plan and
+// the chunked, pipelined batch loop; all arithmetic lives in the kernels.
+//
+// Batch loop: a batch is cut into chunks of ctx->chunk frames.  With host buffers the chunks
+// rotate through NSLOT buffer sets so that chunk i+1's host->device copy, chunk i's kernels and
+// chunk i-1's device->host copy run concurrently on three streams (copy engines are full
+// duplex); with device-resident inputs and outputs there are no copies and one slot is used.
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -12,6 +17,8 @@
 #include "orb_launch.h"
 
 namespace {
+
+const int NSLOT = 3;
 
 struct DevBuf {
     void* p = nullptr;
@@ -28,6 +35,20 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
 };
 
+// One set of per-chunk device buffers.
+struct Slot {
+    DevBuf img_stage, pyr, blur, cand, node_of, counts, lkp, out_kps, out_desc, out_n;
+    int frames = 0;                       // frames the work buffers are sized for
+    cudaEvent_t h2d_done = nullptr, compute_done = nullptr, d2h_done = nullptr;
+    bool used = false;
+    void release()
+    {
+        DevBuf* b[] = { &img_stage, &pyr, &blur, &cand, &node_of, &counts, &lkp, &out_kps, &out_desc, &out_n };
+        for (DevBuf* x : b) x->release();
+        frames = 0;
+    }
+};
+
 struct StageTimer {
     cudaEvent_t ev[2];
     int stage;
@@ -38,26 +59,21 @@ struct StageTimer {
 struct orbx_ctx {
     OrbParams params;
     int device = 0;
-    cudaStream_t own_stream = nullptr;
-    cudaStream_t stream = nullptr;
-    int chunk = 32;
+    cudaStream_t own_stream = nullptr;     // default compute stream
+    cudaStream_t stream = nullptr;         // compute stream in use (own or caller's)
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+    int chunk = 64;
     std::string err;
 
-    // plan of the current shape
     bool have_plan = false;
     OrbPlan plan;
-    DevBuf taps;
+    DevBuf taps, border_tmp;
+    Slot slot[NSLOT];
 
-    // per-chunk device buffers
-    DevBuf img_stage, pyr, blur, cand, node_of, counts, lkp, out_kps, out_desc, out_n, border_tmp;
-    int buf_frames = 0;          // frames the buffers are sized for
-    int buf_cap = 0;             // output capacity per frame the staging outputs are sized for
-
-    // what is resident from the last call (for orbx_pyramid_level / debug taps)
-    int last_first = 0, last_count = 0;    // frames [last_first, last_first+last_count) of the last batch
+    // what is resident from the last call (for orbx_pyramid_level / stage taps)
+    int last_slot = -1, last_first = 0, last_count = 0;
     const uint8_t* last_img0 = nullptr; size_t last_img0_stride = 0; int last_img0_pitch = 0;
 
-    // profiling
     bool profile = false;
     std::vector<StageTimer> pending;
     std::vector<cudaEvent_t> free_events;
@@ -89,39 +105,56 @@ bool is_device_ptr(const void* p)
     return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
+int sync_all(orbx_ctx* c)
+{
+    CU(c, cudaStreamSynchronize(c->h2d_stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    CU(c, cudaStreamSynchronize(c->d2h_stream));
+    return ORBX_OK;
+}
+
 int ensure_plan(orbx_ctx* c, int w, int h)
 {
     if (c->have_plan && c->plan.w == w && c->plan.h == h) return ORBX_OK;
     std::vector<OrbTap> taps;
     OrbPlan plan;
     if (orb_plan_build(&c->params, w, h, &plan, &taps)) return fail(c, ORBX_E_SHAPE, "unsupported image shape %dx%d", w, h);
-    CU(c, cudaStreamSynchronize(c->stream));
+    int rc = sync_all(c);
+    if (rc) return rc;
     CU(c, c->taps.reserve(sizeof(OrbTap) * (taps.size() + 1)));
     if (!taps.empty()) CU(c, cudaMemcpy(c->taps.p, taps.data(), sizeof(OrbTap) * taps.size(), cudaMemcpyHostToDevice));
     c->plan = plan;
     c->have_plan = true;
-    c->buf_frames = 0;
+    for (Slot& s : c->slot) s.frames = 0;   // work buffers are re-sized lazily (reserve only grows)
+    c->last_slot = -1; c->last_count = 0;
     return ORBX_OK;
 }
 
-int ensure_buffers(orbx_ctx* c, int frames, int cap, bool stage_in, size_t in_frame_bytes, bool stage_out)
+int ensure_slot(orbx_ctx* c, Slot& s, int frames, int cap, bool stage_in, size_t in_frame_bytes, bool stage_out)
 {
     const OrbPlan& P = c->plan;
-    if (frames > c->buf_frames) {
-        CU(c, cudaStreamSynchronize(c->stream));
-        CU(c, c->pyr.reserve((size_t)frames * P.pyr_bytes + 256));
-        CU(c, c->blur.reserve((size_t)frames * P.blur_bytes + 256));
-        CU(c, c->cand.reserve((size_t)frames * P.cand_per_frame * 4 + 256));
-        CU(c, c->node_of.reserve((size_t)frames * P.cand_per_frame * 2 + 256));
-        CU(c, c->counts.reserve((size_t)frames * ORB_MAX_LEVELS * 4 * 2));
-        CU(c, c->lkp.reserve((size_t)frames * P.kp_per_frame * 4 + 256));
-        c->buf_frames = frames;
+    if (frames > s.frames) {
+        int rc = sync_all(c);
+        if (rc) return rc;
+        CU(c, s.pyr.reserve((size_t)frames * P.pyr_bytes + 256));
+        CU(c, s.blur.reserve((size_t)frames * P.blur_bytes + 256));
+        CU(c, s.cand.reserve((size_t)frames * P.cand_per_frame * 4 + 256));
+        CU(c, s.node_of.reserve((size_t)frames * P.cand_per_frame * 2 + 256));
+        CU(c, s.counts.reserve((size_t)frames * ORB_MAX_LEVELS * 4 * 2));
+        CU(c, s.lkp.reserve((size_t)frames * P.kp_per_frame * 4 + 256));
+        s.frames = frames;
     }
-    if (stage_in) CU(c, c->img_stage.reserve((size_t)frames * in_frame_bytes + 256));
-    if (stage_out) {
-        CU(c, c->out_kps.reserve((size_t)frames * cap * sizeof(orbx_kp)));
-        CU(c, c->out_desc.reserve((size_t)frames * cap * 32));
-        CU(c, c->out_n.reserve((size_t)frames * 4));
+    if (stage_in && s.img_stage.bytes < (size_t)frames * in_frame_bytes + 256) {
+        int rc = sync_all(c);
+        if (rc) return rc;
+        CU(c, s.img_stage.reserve((size_t)frames * in_frame_bytes + 256));
+    }
+    if (stage_out && (s.out_kps.bytes < (size_t)frames * cap * sizeof(orbx_kp) || s.out_n.bytes < (size_t)frames * 4)) {
+        int rc = sync_all(c);
+        if (rc) return rc;
+        CU(c, s.out_kps.reserve((size_t)frames * cap * sizeof(orbx_kp)));
+        CU(c, s.out_desc.reserve((size_t)frames * cap * 32));
+        CU(c, s.out_n.reserve((size_t)frames * 4));
     }
     return ORBX_OK;
 }
@@ -155,26 +188,26 @@ void collect_timers(orbx_ctx* c)
 }
 
 // Enqueue the whole extractor for `frames` frames whose level-0 images are device resident.
-int enqueue_chunk(orbx_ctx* c, const uint8_t* d_img, size_t frame_stride, int pitch, int frames,
+int enqueue_chunk(orbx_ctx* c, Slot& s, const uint8_t* d_img, size_t frame_stride, int pitch, int frames,
                   orbx_kp* d_kps, uint8_t* d_desc, int* d_n, int cap)
 {
     const OrbPlan& P = c->plan;
     OrbBatch io;
     io.img0 = d_img; io.img0_stride = frame_stride; io.img0_pitch = pitch;
-    io.pyr = (uint8_t*)c->pyr.p; io.blur = (uint8_t*)c->blur.p;
-    io.cand = (uint32_t*)c->cand.p; io.node_of = (uint16_t*)c->node_of.p;
-    io.cand_count = (int*)c->counts.p;
-    io.lkp_count = io.cand_count + (size_t)c->buf_frames * ORB_MAX_LEVELS;
-    io.lkp = (uint32_t*)c->lkp.p;
+    io.pyr = (uint8_t*)s.pyr.p; io.blur = (uint8_t*)s.blur.p;
+    io.cand = (uint32_t*)s.cand.p; io.node_of = (uint16_t*)s.node_of.p;
+    io.cand_count = (int*)s.counts.p;
+    io.lkp_count = io.cand_count + (size_t)s.frames * ORB_MAX_LEVELS;
+    io.lkp = (uint32_t*)s.lkp.p;
     io.kps = d_kps; io.desc = d_desc; io.n_out = d_n; io.cap = cap;
     io.taps = (const OrbTap*)c->taps.p;
     cudaStream_t st = c->stream;
     CU(c, cudaMemsetAsync(io.cand_count, 0, (size_t)frames * ORB_MAX_LEVELS * 4, st));
-    { StageScope s(c, ORBX_STAGE_PYRAMID); CU(c, orb_launch_pyramid(P, io, frames, st)); }
-    { StageScope s(c, ORBX_STAGE_FAST); CU(c, orb_launch_fast(P, io, frames, st)); }
-    { StageScope s(c, ORBX_STAGE_BLUR); CU(c, orb_launch_blur(P, io, frames, st)); }
-    { StageScope s(c, ORBX_STAGE_OCTREE); CU(c, orb_launch_octree(P, io, frames, st)); }
-    { StageScope s(c, ORBX_STAGE_DESCRIBE); CU(c, orb_launch_describe(P, io, frames, st)); }
+    { StageScope t(c, ORBX_STAGE_PYRAMID); CU(c, orb_launch_pyramid(P, io, frames, st)); }
+    { StageScope t(c, ORBX_STAGE_FAST); CU(c, orb_launch_fast(P, io, frames, st)); }
+    { StageScope t(c, ORBX_STAGE_BLUR); CU(c, orb_launch_blur(P, io, frames, st)); }
+    { StageScope t(c, ORBX_STAGE_OCTREE); CU(c, orb_launch_octree(P, io, frames, st)); }
+    { StageScope t(c, ORBX_STAGE_DESCRIBE); CU(c, orb_launch_describe(P, io, frames, st)); }
     return ORBX_OK;
 }
 
@@ -192,44 +225,62 @@ int run_batch(orbx_ctx* c, const uint8_t* imgs, size_t frame_stride, int batch, 
     const bool kps_dev = is_device_ptr(kps), desc_dev = is_device_ptr(desc), n_dev = is_device_ptr(n_out);
     if (async_only && !(in_dev && kps_dev && desc_dev && n_dev)) return fail(c, ORBX_E_ARG, "async entry point needs device pointers");
     const bool stage_out = !(kps_dev && desc_dev && n_dev);
+    const bool piped = !in_dev || stage_out;           // any host buffer: rotate slots and overlap the copies
     const int chunk = batch < c->chunk ? batch : c->chunk;
+    const int nchunks = (batch + chunk - 1) / chunk;
+    const int nslot = piped ? (nchunks < NSLOT ? nchunks : NSLOT) : 1;
     const size_t in_frame_bytes = pitch * (size_t)h;
-    rc = ensure_buffers(c, chunk, cap, !in_dev, in_frame_bytes, stage_out);
-    if (rc) return rc;
+    const size_t frame_copy_bytes = pitch * (size_t)(h - 1) + (size_t)w;   // never read past the last row's pixels
+    for (int s = 0; s < nslot; ++s) {
+        rc = ensure_slot(c, c->slot[s], chunk, cap, !in_dev, in_frame_bytes, stage_out);
+        if (rc) return rc;
+    }
     cudaStream_t st = c->stream;
-    for (int f0 = 0; f0 < batch; f0 += chunk) {
+    for (int i = 0; i < nchunks; ++i) {
+        const int f0 = i * chunk;
         const int nf = batch - f0 < chunk ? batch - f0 : chunk;
+        Slot& s = c->slot[i % nslot];
         const uint8_t* d_img; size_t d_stride;
         if (in_dev) { d_img = imgs + (size_t)f0 * frame_stride; d_stride = frame_stride; }
         else {
-            // host frames -> staging, keeping the caller's row pitch (one 2-D copy: rows = frames)
-            d_img = (const uint8_t*)c->img_stage.p; d_stride = in_frame_bytes;
+            // host frames -> staging on the copy stream, keeping the caller's row pitch; the
+            // slot's previous kernels must have finished reading the staging buffer
+            d_img = (const uint8_t*)s.img_stage.p; d_stride = in_frame_bytes;
+            if (s.used) CU(c, cudaStreamWaitEvent(c->h2d_stream, s.compute_done, 0));
             if (frame_stride == in_frame_bytes || nf == 1)
-                CU(c, cudaMemcpyAsync(c->img_stage.p, imgs + (size_t)f0 * frame_stride, (size_t)(nf - 1) * in_frame_bytes + pitch * (size_t)(h - 1) + w, cudaMemcpyHostToDevice, st));
+                CU(c, cudaMemcpyAsync(s.img_stage.p, imgs + (size_t)f0 * frame_stride, (size_t)(nf - 1) * in_frame_bytes + frame_copy_bytes,
+                                      cudaMemcpyHostToDevice, c->h2d_stream));
             else
-                CU(c, cudaMemcpy2DAsync(c->img_stage.p, in_frame_bytes, imgs + (size_t)f0 * frame_stride, frame_stride,
-                                        pitch * (size_t)(h - 1) + w, nf, cudaMemcpyHostToDevice, st));
+                CU(c, cudaMemcpy2DAsync(s.img_stage.p, in_frame_bytes, imgs + (size_t)f0 * frame_stride, frame_stride,
+                                        frame_copy_bytes, nf, cudaMemcpyHostToDevice, c->h2d_stream));
+            CU(c, cudaEventRecord(s.h2d_done, c->h2d_stream));
+            CU(c, cudaStreamWaitEvent(st, s.h2d_done, 0));
         }
-        orbx_kp* dk = stage_out ? (orbx_kp*)c->out_kps.p : kps + (size_t)f0 * cap;
-        uint8_t* dd = stage_out ? (uint8_t*)c->out_desc.p : desc + (size_t)f0 * cap * 32;
-        int* dn = stage_out ? (int*)c->out_n.p : n_out + f0;
-        rc = enqueue_chunk(c, d_img, d_stride, (int)pitch, nf, dk, dd, dn, cap);
+        orbx_kp* dk = stage_out ? (orbx_kp*)s.out_kps.p : kps + (size_t)f0 * cap;
+        uint8_t* dd = stage_out ? (uint8_t*)s.out_desc.p : desc + (size_t)f0 * cap * 32;
+        int* dn = stage_out ? (int*)s.out_n.p : n_out + f0;
+        if (stage_out && s.used) CU(c, cudaStreamWaitEvent(st, s.d2h_done, 0));   // output staging still being drained
+        rc = enqueue_chunk(c, s, d_img, d_stride, (int)pitch, nf, dk, dd, dn, cap);
         if (rc) return rc;
+        if (piped) CU(c, cudaEventRecord(s.compute_done, st));
         if (stage_out) {
             const cudaMemcpyKind kk = kps_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
             const cudaMemcpyKind kd = desc_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
             const cudaMemcpyKind kn = n_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
-            CU(c, cudaMemcpyAsync(kps + (size_t)f0 * cap, dk, (size_t)nf * cap * sizeof(orbx_kp), kk, st));
-            CU(c, cudaMemcpyAsync(desc + (size_t)f0 * cap * 32, dd, (size_t)nf * cap * 32, kd, st));
-            CU(c, cudaMemcpyAsync(n_out + f0, dn, (size_t)nf * 4, kn, st));
+            CU(c, cudaStreamWaitEvent(c->d2h_stream, s.compute_done, 0));
+            CU(c, cudaMemcpyAsync(kps + (size_t)f0 * cap, dk, (size_t)nf * cap * sizeof(orbx_kp), kk, c->d2h_stream));
+            CU(c, cudaMemcpyAsync(desc + (size_t)f0 * cap * 32, dd, (size_t)nf * cap * 32, kd, c->d2h_stream));
+            CU(c, cudaMemcpyAsync(n_out + f0, dn, (size_t)nf * 4, kn, c->d2h_stream));
+            CU(c, cudaEventRecord(s.d2h_done, c->d2h_stream));
         }
-        c->last_first = f0; c->last_count = nf;
+        s.used = piped;
+        c->last_slot = i % nslot; c->last_first = f0; c->last_count = nf;
         c->last_img0 = d_img; c->last_img0_stride = d_stride; c->last_img0_pitch = (int)pitch;
-        // the single set of chunk buffers is reused: the next chunk's H2D must not overtake this
-        // chunk's kernels -- guaranteed by stream order.
     }
     if (async_only) return ORBX_OK;
-    CU(c, cudaStreamSynchronize(st));
+    rc = sync_all(c);
+    if (rc) return rc;
+    for (Slot& s : c->slot) s.used = false;
     collect_timers(c);
     if (!n_dev) for (int f = 0; f < batch; ++f) if (n_out[f] > cap) return fail(c, ORBX_E_CAPACITY, "frame %d: %d keypoints > capacity %d", f, n_out[f], cap);
     return ORBX_OK;
@@ -237,7 +288,7 @@ int run_batch(orbx_ctx* c, const uint8_t* imgs, size_t frame_stride, int batch, 
 
 int resident_frame(orbx_ctx* c, int frame, int level)
 {
-    if (!c || !c->have_plan || c->last_count == 0) return -1;
+    if (!c || !c->have_plan || c->last_count == 0 || c->last_slot < 0) return -1;
     if (level < 0 || level >= c->plan.nlevels) return -1;
     const int rel = frame - c->last_first;
     if (rel < 0 || rel >= c->last_count) return -1;
@@ -268,7 +319,14 @@ int orbx_create(orbx_ctx** out, int nfeatures, float scaleFactor, int nlevels, i
     orbx_ctx* c = new (std::nothrow) orbx_ctx();
     if (!c) return ORBX_E_ARG;
     c->params = p; c->device = device;
-    if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); delete c; return ORBX_E_CUDA; }
+    bool ok = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (Slot& s : c->slot)
+        ok = ok && cudaEventCreateWithFlags(&s.h2d_done, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&s.compute_done, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&s.d2h_done, cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) { cudaGetLastError(); delete c; return ORBX_E_CUDA; }
     c->stream = c->own_stream;
     *out = c;
     return ORBX_OK;
@@ -278,13 +336,19 @@ void orbx_destroy(orbx_ctx* c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    sync_all(c);
     collect_timers(c);
     for (cudaEvent_t e : c->free_events) cudaEventDestroy(e);
-    DevBuf* bufs[] = { &c->taps, &c->img_stage, &c->pyr, &c->blur, &c->cand, &c->node_of, &c->counts, &c->lkp,
-                       &c->out_kps, &c->out_desc, &c->out_n, &c->border_tmp };
-    for (DevBuf* b : bufs) b->release();
+    for (Slot& s : c->slot) {
+        s.release();
+        if (s.h2d_done) cudaEventDestroy(s.h2d_done);
+        if (s.compute_done) cudaEventDestroy(s.compute_done);
+        if (s.d2h_done) cudaEventDestroy(s.d2h_done);
+    }
+    c->taps.release(); c->border_tmp.release();
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
+    if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
     delete c;
 }
 
@@ -331,7 +395,8 @@ int orbx_sync(orbx_ctx* c)
 {
     if (!c) return ORBX_E_ARG;
     CU(c, cudaSetDevice(c->device));
-    CU(c, cudaStreamSynchronize(c->stream));
+    int rc = sync_all(c);
+    if (rc) return rc;
     collect_timers(c);
     return ORBX_OK;
 }
@@ -342,6 +407,7 @@ int orbx_pyramid_level(orbx_ctx* c, int frame, int level, int with_border, uint8
     const int rel = resident_frame(c, frame, level);
     if (rel < 0) return fail(c, ORBX_E_ARG, "frame %d level %d is not resident", frame, level);
     const OrbLevel& L = c->plan.lv[level];
+    const Slot& s = c->slot[c->last_slot];
     const int b = with_border ? ORB_EDGE : 0;
     if (w) *w = L.w + 2 * b;
     if (h) *h = L.h + 2 * b;
@@ -349,7 +415,7 @@ int orbx_pyramid_level(orbx_ctx* c, int frame, int level, int with_border, uint8
     CU(c, cudaSetDevice(c->device));
     const uint8_t* src; int spitch;
     if (level == 0) { src = c->last_img0 + (size_t)rel * c->last_img0_stride; spitch = c->last_img0_pitch; }
-    else { src = (const uint8_t*)c->pyr.p + (size_t)rel * c->plan.pyr_bytes + L.img_off; spitch = L.pitch; }
+    else { src = (const uint8_t*)s.pyr.p + (size_t)rel * c->plan.pyr_bytes + L.img_off; spitch = L.pitch; }
     if (!with_border) return copy_out_2d(c, dst, dst_pitch, src, (size_t)spitch, L.w, L.h);
     const int bw = L.w + 2 * b, bh = L.h + 2 * b;
     CU(c, c->border_tmp.reserve((size_t)bw * bh));
@@ -361,7 +427,8 @@ int orbx_set_stream(orbx_ctx* c, void* cuda_stream)
 {
     if (!c) return ORBX_E_ARG;
     CU(c, cudaSetDevice(c->device));
-    CU(c, cudaStreamSynchronize(c->stream));
+    int rc = sync_all(c);
+    if (rc) return rc;
     collect_timers(c);
     c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
     return ORBX_OK;
@@ -385,7 +452,8 @@ int orbx_debug_blurred(orbx_ctx* c, int frame, int level, uint8_t* dst, size_t d
     if (rel < 0) return fail(c, ORBX_E_ARG, "frame %d level %d is not resident", frame, level);
     const OrbLevel& L = c->plan.lv[level];
     CU(c, cudaSetDevice(c->device));
-    return copy_out_2d(c, dst, dst_pitch, (const uint8_t*)c->blur.p + (size_t)rel * c->plan.blur_bytes + L.blur_off, (size_t)L.pitch, L.w, L.h);
+    return copy_out_2d(c, dst, dst_pitch, (const uint8_t*)c->slot[c->last_slot].blur.p + (size_t)rel * c->plan.blur_bytes + L.blur_off,
+                       (size_t)L.pitch, L.w, L.h);
 }
 
 static int debug_packed(orbx_ctx* c, int frame, int level, bool after_octree, int* xys, int cap, int* n)
@@ -394,9 +462,10 @@ static int debug_packed(orbx_ctx* c, int frame, int level, bool after_octree, in
     const int rel = resident_frame(c, frame, level);
     if (rel < 0) return fail(c, ORBX_E_ARG, "frame %d level %d is not resident", frame, level);
     const OrbLevel& L = c->plan.lv[level];
+    const Slot& s = c->slot[c->last_slot];
     CU(c, cudaSetDevice(c->device));
     CU(c, cudaStreamSynchronize(c->stream));
-    const int* counts = (const int*)c->counts.p + (after_octree ? (size_t)c->buf_frames * ORB_MAX_LEVELS : 0);
+    const int* counts = (const int*)s.counts.p + (after_octree ? (size_t)s.frames * ORB_MAX_LEVELS : 0);
     int cnt = 0;
     CU(c, cudaMemcpy(&cnt, counts + (size_t)rel * ORB_MAX_LEVELS + level, 4, cudaMemcpyDeviceToHost));
     *n = cnt;
@@ -404,8 +473,8 @@ static int debug_packed(orbx_ctx* c, int frame, int level, bool after_octree, in
     const int lim = after_octree ? L.kp_cap : L.cand_cap;
     const int m = cnt < lim ? cnt : lim;
     std::vector<uint32_t> tmp((size_t)m);
-    const uint32_t* src = after_octree ? (const uint32_t*)c->lkp.p + (size_t)rel * c->plan.kp_per_frame + L.kp_off
-                                       : (const uint32_t*)c->cand.p + (size_t)rel * c->plan.cand_per_frame + L.cand_off;
+    const uint32_t* src = after_octree ? (const uint32_t*)s.lkp.p + (size_t)rel * c->plan.kp_per_frame + L.kp_off
+                                       : (const uint32_t*)s.cand.p + (size_t)rel * c->plan.cand_per_frame + L.cand_off;
     CU(c, cudaMemcpy(tmp.data(), src, (size_t)m * 4, cudaMemcpyDeviceToHost));
     for (int i = 0; i < m && i < cap; ++i) { xys[3 * i] = ORB_PX(tmp[i]); xys[3 * i + 1] = ORB_PY(tmp[i]); xys[3 * i + 2] = ORB_PS(tmp[i]); }
     return ORBX_OK;
@@ -425,7 +494,8 @@ int orbx_stage_ms(orbx_ctx* c, float* ms, int* launches, int reset)
 {
     if (!c) return ORBX_E_ARG;
     CU(c, cudaSetDevice(c->device));
-    CU(c, cudaStreamSynchronize(c->stream));
+    int rc = sync_all(c);
+    if (rc) return rc;
     collect_timers(c);
     for (int i = 0; i < ORBX_STAGE_COUNT; ++i) {
         if (ms) ms[i] = c->stage_ms[i];

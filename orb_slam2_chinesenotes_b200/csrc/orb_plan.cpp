@@ -83,7 +83,7 @@ int orb_plan_build(const OrbParams* p, int w, int h, OrbPlan* plan, std::vector<
     for (int i = 0; i <= ORB_HALF_PATCH; ++i) plan->umax[i] = p->umax[i];
     if ((long long)w * h >= (1 << 24)) return 1;
     uint32_t pyr = 0, blur = 0;
-    int cells = 0, tiles = 0, cand = 0, kp = 0;
+    int cells = 0, strips = 0, tiles = 0, cand = 0, kp = 0;
     const float Wcell = 30.f;                                              // src/ORBextractor.cc:799
     for (int l = 0; l < p->nlevels; ++l) {
         OrbLevel& L = plan->lv[l];
@@ -117,17 +117,26 @@ int orb_plan_build(const OrbParams* p, int w, int h, OrbPlan* plan, std::vector<
                     int x0 = ORB_BORDER0 + j * L.wCell, x1 = x0 + L.wCell + 6; if (x1 > maxBorderX) x1 = maxBorderX;
                     int ew = x1 - x0 - 6; if (ew < 0) ew = 0;
                     cap += ((ew + 1) / 2) * ((eh + 1) / 2);                // strict 3x3 maxima cannot be denser
-                    // orb_fast.cu: rows of (4-pixel groups + 2) words; tile has eh+6 rows, score map eh+2
-                    const int tw = (ew + 3) / 4 + 2;
-                    if ((eh + 6) * tw > plan->fast_tile_words) plan->fast_tile_words = (eh + 6) * tw;
-                    if ((eh + 2) * tw > plan->fast_score_words) plan->fast_score_words = (eh + 2) * tw;
                     if (ew * eh > plan->fast_eval_max) plan->fast_eval_max = ew * eh;
                 }
             }
+            // orb_fast.cu: a block takes a run of up to ORB_FAST_STRIP cells of one cell row; each cell
+            // is staged word-aligned as (4-pixel groups + 2) words per row
+            const int ncs = L.ncx < ORB_FAST_STRIP ? L.ncx : ORB_FAST_STRIP;
+            const int gq = (L.wCell + 3) / 4, tw = gq + 2;
+            const int tile = (L.hCell + 6) * ncs * tw, score = (L.hCell + 2) * ncs * tw;
+            const int items = L.hCell * ncs * gq, surv = ncs * ((L.wCell + 1) / 2) * ((L.hCell + 1) / 2);
+            if (tile > plan->fast_tile_words) plan->fast_tile_words = tile;
+            if (score > plan->fast_score_words) plan->fast_score_words = score;
+            if (items > plan->fast_items_max) plan->fast_items_max = items;
+            if (surv > plan->fast_surv_max) plan->fast_surv_max = surv;
+            if (items >= 65536) return 1;                                  // item ids are 16-bit
             // order key (cell, y-in-cell, x-in-cell) must fit 24 bits
             if ((long long)L.ncx * L.ncy * L.wCell * L.hCell >= (1 << 24)) return 1;
         }
         L.cell_first = cells; cells += L.ncx * L.ncy;
+        L.spr = (L.ncx + ORB_FAST_STRIP - 1) / ORB_FAST_STRIP;
+        L.strip_first = strips; strips += L.spr * L.ncy;
         L.quota = p->per_level[l];
         L.cand_off = cand; L.cand_cap = cap; cand += (cap + 31) / 32 * 32;
         // list size never exceeds max(N+2, 4*nIni) (see orb_octree.cuh); keep a little slack
@@ -145,7 +154,7 @@ int orb_plan_build(const OrbParams* p, int w, int h, OrbPlan* plan, std::vector<
         L.blur_tiles_y = (L.h + ORB_BLUR_TH - 1) / ORB_BLUR_TH;
         L.blur_tile_first = tiles; tiles += L.blur_tiles_x * L.blur_tiles_y;
     }
-    plan->total_cells = cells; plan->total_blur_tiles = tiles;
+    plan->total_cells = cells; plan->total_strips = strips; plan->total_blur_tiles = tiles;
     plan->cand_per_frame = cand; plan->kp_per_frame = kp;
     plan->pyr_bytes = align_up(pyr + 64, 256); plan->blur_bytes = align_up(blur + 64, 256);
     return 0;

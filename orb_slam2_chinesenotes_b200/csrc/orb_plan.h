@@ -19,6 +19,7 @@
 #define ORB_PATCH 31         // PATCH_SIZE, :72
 #define ORB_BORDER0 16       // minBorderX = EDGE_THRESHOLD-3, :804
 #define ORB_MAX_DIM 4128     // candidate coordinates are packed in 12 bits (border frame)
+#define ORB_FAST_STRIP 8     // cells per FAST block (orb_fast.cu)
 
 struct OrbLevel {
     int w, h;               // level image size
@@ -29,6 +30,8 @@ struct OrbLevel {
     int wCell, hCell;       // reference cell size
     int ncx, ncy;           // processed cell columns / rows
     int cell_first;         // index of this level's first cell in the all-level cell list
+    int spr;                // FAST strips (runs of up to ORB_FAST_STRIP cells) per cell row
+    int strip_first;        // index of this level's first strip in the all-level strip list
     // quadtree
     int W, H;               // maxBorder-minBorder extents = w-32, h-32
     int nIni;               // number of root nodes
@@ -54,9 +57,12 @@ struct OrbPlan {
     int cand_per_frame;     // candidate entries per frame (sum of cand_cap)
     int kp_per_frame;       // level-keypoint entries per frame (sum of kp_cap)
     int max_nodes;          // largest kp_cap: quadtree shared-memory sizing
-    int fast_tile_words;    // largest FAST cell tile in 32-bit words
+    int total_strips;       // sum of FAST strips over levels
+    int fast_tile_words;    // largest FAST strip tile in 32-bit words
     int fast_eval_max;      // largest evaluated area of a cell (pixels)
-    int fast_score_words;   // largest (ew+2)x(eh+2) score map in 32-bit words
+    int fast_score_words;   // largest strip score map in 32-bit words
+    int fast_items_max;     // largest number of 4-pixel groups in a strip
+    int fast_surv_max;      // largest possible number of NMS survivors in a strip
     int umax[ORB_HALF_PATCH + 1]; // row half-widths of the orientation patch
     uint32_t pyr_bytes;     // bytes of one frame's pyramid block (levels 1..)
     uint32_t blur_bytes;    // bytes of one frame's blur block (levels 0..)
