@@ -6,8 +6,6 @@
 #include <cmath>
 #include <cstring>
 
-#define ORB_BLUR_TW 128
-#define ORB_BLUR_TH 32
 
 static inline int rne_f(float v) { return (int)nearbyintf(v); }   // cvRound(float): cvtss2si
 static inline int rne_d(double v) { return (int)nearbyint(v); }   // cvRound(double)

@@ -20,6 +20,8 @@
 #define ORB_BORDER0 16       // minBorderX = EDGE_THRESHOLD-3, :804
 #define ORB_MAX_DIM 4128     // candidate coordinates are packed in 12 bits (border frame)
 #define ORB_FAST_STRIP 8     // cells per FAST block (orb_fast.cu)
+#define ORB_BLUR_TW 120      // blur tile (orb_dense.cu): 120 output pixels = 32 staged words incl. the 3-px apron
+#define ORB_BLUR_TH 32
 
 struct OrbLevel {
     int w, h;               // level image size
