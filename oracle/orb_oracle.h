@@ -68,6 +68,39 @@ int orbo_descriptor_distance(const uint8_t* a, const uint8_t* b);
 /* All-pairs best / second-best (strict <, first wins), the brute-force kernel's checker. */
 void orbo_hamming_bf(const uint8_t* q, int nq, const uint8_t* t, int nt, int* best_idx, int* best_dist, int* second_dist);
 
+/* ---- window matchers and stereo rows (orb_match_oracle.c) --------------------------- */
+
+/* Frame::GetFeaturesInArea on a 64x48 grid built like Frame::AssignFeaturesToGrid (src/Frame.cc:243-259, 348-409) */
+int orbo_features_in_area(int n, const orbo_kp* kps, float minX, float maxX, float minY, float maxY,
+                          float x, float y, float r, int minLevel, int maxLevel, int* out, int cap);
+
+/* ORBmatcher::SearchForInitialization, src/ORBmatcher.cc:1055-1180 */
+int orbo_search_for_initialization(int n1, const orbo_kp* kps1, const uint8_t* desc1,
+                                   int n2, const orbo_kp* kps2, const uint8_t* desc2,
+                                   float minX, float maxX, float minY, float maxY,
+                                   float* prev_matched, int* matches12, int windowSize, float nnratio, int checkOri);
+
+/* ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th), src/ORBmatcher.cc:73-157 */
+int orbo_search_by_projection_points(int n, const orbo_kp* kps, const uint8_t* desc, const float* u_right,
+                                     const float* scale, float minX, float maxX, float minY, float maxY,
+                                     int nq, const float* proj_xyxr, const int* level, const float* view_cos,
+                                     const uint8_t* in_view, const uint8_t* bad, const int* observations,
+                                     const uint8_t* qdesc, const int* init_assign, int* assign_out, float th, float nnratio);
+
+/* ORBmatcher::SearchByProjection(Frame& cur, const Frame& last, th, bMono), src/ORBmatcher.cc:160-300 */
+int orbo_search_by_projection_frame(int n_cur, const orbo_kp* kps_cur, const uint8_t* desc_cur, const float* u_right_cur,
+                                    int n_last, const orbo_kp* kps_last, const uint8_t* last_mp, const uint8_t* last_outlier,
+                                    const float* last_xyz, const uint8_t* last_mp_desc, const int* last_mp_obs,
+                                    const float* Tcw_cur, const float* Tcw_last, const float* K, float bf,
+                                    const float* scale, float minX, float maxX, float minY, float maxY,
+                                    const int* cur_init_obs, int* assign_out, float th, int bMono, float nnratio, int checkOri);
+
+/* Frame::ComputeStereoMatches, src/Frame.cc:513-699 */
+int orbo_stereo_matches(const orbo_extractor* eL, const orbo_extractor* eR,
+                        int nl, const orbo_kp* kps_l, const uint8_t* desc_l,
+                        int nr, const orbo_kp* kps_r, const uint8_t* desc_r,
+                        float bf, float fx, float* u_right, float* depth);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,19 +14,27 @@ const int kMaxRegions = 1024;
 std::atomic<char*> g_regions[kMaxRegions]; // slot == 0: free
 std::atomic<int> g_hi(0);                  // slots >= g_hi were never used
 
+// Regions are never unmapped: data allocated by a worker thread (e.g. the keypoint vectors that
+// Frame::ExtractORB fills on its own std::thread, src/Frame.cc:82-85) outlives the thread.  A
+// finished thread's region is parked and handed to the next new thread.
+std::atomic<char*> g_parked[kMaxRegions];
+
 struct ThreadArena {
     char* base;
     std::size_t off;
     ThreadArena() : base(0), off(0) {}
     void init()
     {
+        for (int i = 0, n = g_hi.load(); i < n; ++i) {
+            char* p = g_parked[i].exchange(0);
+            if (p) { base = p; off = 0; return; }
+        }
         void* p = mmap(0, kRegionBytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
         if (p == MAP_FAILED) { std::fprintf(stderr, "ref_arena: mmap failed\n"); std::abort(); }
         base = (char*)p;
         for (int i = 0; i < kMaxRegions; ++i) {
             char* expect = 0;
             if (g_regions[i].compare_exchange_strong(expect, base)) {
-                slot = i;
                 int hi = g_hi.load();
                 while (hi < i + 1 && !g_hi.compare_exchange_weak(hi, i + 1)) {}
                 return;
@@ -35,12 +43,15 @@ struct ThreadArena {
         std::fprintf(stderr, "ref_arena: too many threads\n");
         std::abort();
     }
-    // thread exit: everything this thread allocated must be dead by now
     ~ThreadArena()
     {
-        if (base) { g_regions[slot].store(0); munmap(base, kRegionBytes); base = 0; }
+        if (!base) return;
+        for (int i = 0; i < kMaxRegions; ++i) {
+            char* expect = 0;
+            if (g_parked[i].compare_exchange_strong(expect, base)) break;
+        }
+        base = 0;
     }
-    int slot;
 };
 thread_local ThreadArena t_arena;
 } // namespace
