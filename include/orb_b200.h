@@ -127,6 +127,54 @@ int orbx_plan_describe(int nfeatures, float scaleFactor, int nlevels, int iniThF
 int orbm_hamming_bf(const uint8_t* q, int nq, const uint8_t* t, int nt, int nprob,
                     int* best_idx, int* best_dist, int* second_dist, int device);
 
+/* The Frame fields the window searches read (include/Frame.h:120-175): undistorted keypoints,
+ * descriptors, right-image coordinates (NULL = monocular) and the image bounds mnMinX..mnMaxY.
+ * The 64x48 grid of Frame::AssignFeaturesToGrid (src/Frame.cc:243-259) is rebuilt on the device. */
+typedef struct {
+    int n;
+    const orbx_kp* kps;      /* mvKeysUn */
+    const uint8_t* desc;     /* mDescriptors, n x 32 */
+    const float* u_right;    /* mvuRight or NULL */
+    float min_x, max_x, min_y, max_y;
+} orbm_frame;
+
+/* ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th), src/ORBmatcher.cc:73-157.
+ * Map points as arrays [nq]: mTrackProjX/Y/XR (3 floats each), mnTrackScaleLevel, mTrackViewCos,
+ * mbTrackInView, isBad(), Observations(), GetDescriptor().  init_assign [n] (or NULL): index of the map
+ * point already attached to a keypoint, -1 if none.  assign_out [n]: F.mvpMapPoints afterwards.
+ * scale = F.mvScaleFactors.  All pointers are HOST memory.  *nmatches = the function's return value. */
+int orbm_search_by_projection_points(const orbm_frame* F, const float* scale, int nlevels,
+                                     int nq, const float* proj_xyxr, const int* level, const float* view_cos,
+                                     const uint8_t* in_view, const uint8_t* bad, const int* observations,
+                                     const uint8_t* qdesc, const int* init_assign, int* assign_out,
+                                     float th, float nnratio, int* nmatches, int device);
+
+/* ORBmatcher::SearchByProjection(Frame& cur, const Frame& last, th, bMono), src/ORBmatcher.cc:160-300.
+ * last_mp[i] != 0: last-frame keypoint i has a map point (world position last_xyz[3i..], descriptor
+ * last_mp_desc[32i..], Observations() last_mp_obs[i]); last_outlier = mvbOutlier.  Tcw_*: row-major 4x4
+ * poses, K = fx,fy,cx,cy, bf = mbf.  cur_init_obs [n_cur] (or NULL): Observations() of a map point
+ * already attached to a current keypoint, -1 if free.  assign_out [n_cur]: index of the last-frame
+ * keypoint whose map point is attached afterwards, -2 for a kept pre-attached point, -1 for none. */
+int orbm_search_by_projection_frame(const orbm_frame* cur, int n_last, const orbx_kp* kps_last,
+                                    const uint8_t* last_mp, const uint8_t* last_outlier, const float* last_xyz,
+                                    const uint8_t* last_mp_desc, const int* last_mp_obs,
+                                    const float* Tcw_cur, const float* Tcw_last, const float* K, float bf,
+                                    const float* scale, int nlevels, const int* cur_init_obs, int* assign_out,
+                                    float th, int bMono, int checkOri, int* nmatches, int device);
+
+/* ORBmatcher::SearchForInitialization, src/ORBmatcher.cc:1055-1180.  prev_matched [F1.n][2] is
+ * vbPrevMatched (updated in place), matches12 [F1.n] receives vnMatches12. */
+int orbm_search_for_initialization(const orbm_frame* F1, const orbm_frame* F2, float* prev_matched, int* matches12,
+                                   int windowSize, float nnratio, int checkOri, int* nmatches, int device);
+
+/* Frame::ComputeStereoMatches, src/Frame.cc:513-699.  The two extractor contexts must still hold the
+ * pyramids of the frames that produced the keypoints (mvImagePyramid of both extractors, :520,611-633):
+ * frame_l / frame_r index into their last batch.  u_right / depth [nl] receive mvuRight / mvDepth. */
+int orbm_stereo_matches(orbx_ctx* ex_left, int frame_l, orbx_ctx* ex_right, int frame_r,
+                        int nl, const orbx_kp* kps_l, const uint8_t* desc_l,
+                        int nr, const orbx_kp* kps_r, const uint8_t* desc_r,
+                        float bf, float fx, float* u_right, float* depth, int* nmatched);
+
 #ifdef __cplusplus
 }
 #endif

@@ -24,6 +24,12 @@ ORBX_OK, ORBX_E_ARG, ORBX_E_SHAPE, ORBX_E_CAPACITY, ORBX_E_CUDA, ORBX_E_EMPTY = 
 STAGES = ("pyramid", "fast", "blur", "octree", "describe")
 
 
+class OrbmFrame(C.Structure):
+    """orbm_frame of include/orb_b200.h: the Frame fields the window searches read."""
+    _fields_ = [("n", C.c_int), ("kps", C.c_void_p), ("desc", C.c_void_p), ("u_right", C.c_void_p),
+                ("min_x", C.c_float), ("max_x", C.c_float), ("min_y", C.c_float), ("max_y", C.c_float)]
+
+
 class OrbError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"orb_b200 status {code}: {msg}")
@@ -77,6 +83,11 @@ def lib():
         L.orbx_stage_ms.argtypes = [vp, vp, vp, i32]
         L.orbx_plan_describe.argtypes = [i32, f32, i32, i32, i32, i32, i32] + [vp] * 6
         L.orbm_hamming_bf.argtypes = [vp, i32, vp, i32, i32, vp, vp, vp, i32]
+        fp = C.POINTER(OrbmFrame)
+        L.orbm_search_by_projection_points.argtypes = [fp, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, f32, f32, pi, i32]
+        L.orbm_search_by_projection_frame.argtypes = [fp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, f32, vp, i32, vp, vp, f32, i32, i32, pi, i32]
+        L.orbm_search_for_initialization.argtypes = [fp, fp, vp, vp, i32, f32, i32, pi, i32]
+        L.orbm_stereo_matches.argtypes = [vp, i32, vp, i32, i32, vp, vp, i32, vp, vp, f32, f32, vp, vp, pi]
         _lib = L
     return _lib
 
@@ -253,18 +264,100 @@ class ORBextractor:
         return dict(zip(STAGES, ms.tolist())), dict(zip(STAGES, cnt.tolist()))
 
 
+def _np(a, dtype=None):
+    return None if a is None else np.ascontiguousarray(a, dtype)
+
+
+class FrameView:
+    """Host-side stand-in for the ORB_SLAM2::Frame members the matchers read: mvKeysUn, mDescriptors,
+    mvuRight, mnMinX..mnMaxY (include/Frame.h:120-175)."""
+
+    def __init__(self, kps, desc, bounds, u_right=None):
+        self.kps = _np(kps)
+        self.desc = _np(desc, np.uint8)
+        self.u_right = _np(u_right, np.float32)
+        self.bounds = tuple(float(b) for b in bounds)
+        assert self.kps.dtype == KP_DTYPE and self.desc.shape == (len(self.kps), 32)
+
+    def struct(self):
+        return OrbmFrame(len(self.kps), self.kps.ctypes.data, self.desc.ctypes.data,
+                         None if self.u_right is None else self.u_right.ctypes.data, *self.bounds)
+
+
 class ORBmatcher:
-    """Hamming part of ORB_SLAM2::ORBmatcher (include/ORBmatcher.h:43-100)."""
+    """ORB_SLAM2::ORBmatcher (include/ORBmatcher.h:43-100): the Hamming searches of the hot path."""
     TH_LOW, TH_HIGH, HISTO_LENGTH = 50, 100, 30   # src/ORBmatcher.cc:37-39
 
     def __init__(self, nnratio=0.6, checkOri=True, device=0):
-        self.mfNNratio, self.mbCheckOrientation, self.device = np.float32(nnratio), bool(checkOri), device
+        self.mfNNratio, self.mbCheckOrientation, self.device = float(np.float32(nnratio)), bool(checkOri), device
 
     @staticmethod
     def DescriptorDistance(a, b, device=0):
         """src/ORBmatcher.cc:46-63 for one pair (runs the brute-force kernel on a 1x1 problem)."""
         _, d, _ = hamming_bf(np.asarray(a, np.uint8).reshape(1, 32), np.asarray(b, np.uint8).reshape(1, 32), device)
         return int(d[0])
+
+    def _rc(self, rc, what):
+        if rc:
+            raise OrbError(rc, what + " failed")
+
+    def SearchByProjection(self, F, scale, q, th=3.0, init_assign=None):
+        """SearchByProjection(Frame&, const vector<MapPoint*>&, th), src/ORBmatcher.cc:73-157.
+        q: dict of per-map-point arrays proj [nq,3], level, view_cos, in_view, bad, obs, desc [nq,32].
+        Returns (nmatches, assign [F.n])."""
+        scale = _np(scale, np.float32)
+        proj, level, vc = _np(q["proj"], np.float32), _np(q["level"], np.int32), _np(q["view_cos"], np.float32)
+        iv, bad, obs, qd = _np(q["in_view"], np.uint8), _np(q["bad"], np.uint8), _np(q["obs"], np.int32), _np(q["desc"], np.uint8)
+        ia = _np(init_assign, np.int32)
+        out = np.zeros(len(F.kps), np.int32)
+        nm = C.c_int()
+        fs = F.struct()
+        self._rc(lib().orbm_search_by_projection_points(C.byref(fs), scale.ctypes.data, len(scale), len(level), proj.ctypes.data,
+                 level.ctypes.data, vc.ctypes.data, iv.ctypes.data, bad.ctypes.data, obs.ctypes.data, qd.ctypes.data,
+                 None if ia is None else ia.ctypes.data, out.ctypes.data, th, self.mfNNratio, C.byref(nm), self.device),
+                 "orbm_search_by_projection_points")
+        return nm.value, out
+
+    def SearchByProjectionFrame(self, cur, last, Tcw_cur, Tcw_last, K, bf, scale, th, bMono, cur_init_obs=None):
+        """SearchByProjection(Frame& cur, const Frame& last, th, bMono), src/ORBmatcher.cc:160-300.
+        last: dict kps, has_mp, outlier, xyz, mp_desc, mp_obs.  Returns (nmatches, assign [cur.n])."""
+        scale, K = _np(scale, np.float32), _np(K, np.float32)
+        Tc, Tl = _np(Tcw_cur, np.float32), _np(Tcw_last, np.float32)
+        lk, hm, ol = _np(last["kps"]), _np(last["has_mp"], np.uint8), _np(last["outlier"], np.uint8)
+        xyz, md, mo = _np(last["xyz"], np.float32), _np(last["mp_desc"], np.uint8), _np(last["mp_obs"], np.int32)
+        io = _np(cur_init_obs, np.int32)
+        out = np.zeros(len(cur.kps), np.int32)
+        nm = C.c_int()
+        fs = cur.struct()
+        self._rc(lib().orbm_search_by_projection_frame(C.byref(fs), len(lk), lk.ctypes.data, hm.ctypes.data, ol.ctypes.data, xyz.ctypes.data,
+                 md.ctypes.data, mo.ctypes.data, Tc.ctypes.data, Tl.ctypes.data, K.ctypes.data, bf, scale.ctypes.data, len(scale),
+                 None if io is None else io.ctypes.data, out.ctypes.data, th, int(bMono), int(self.mbCheckOrientation), C.byref(nm), self.device),
+                 "orbm_search_by_projection_frame")
+        return nm.value, out
+
+    def SearchForInitialization(self, F1, F2, vbPrevMatched, windowSize=10):
+        """src/ORBmatcher.cc:1055-1180.  Returns (nmatches, vnMatches12, updated vbPrevMatched)."""
+        prev = np.ascontiguousarray(vbPrevMatched, np.float32).copy()
+        m12 = np.zeros(len(F1.kps), np.int32)
+        nm = C.c_int()
+        f1, f2 = F1.struct(), F2.struct()
+        self._rc(lib().orbm_search_for_initialization(C.byref(f1), C.byref(f2), prev.ctypes.data, m12.ctypes.data, windowSize,
+                 self.mfNNratio, int(self.mbCheckOrientation), C.byref(nm), self.device), "orbm_search_for_initialization")
+        return nm.value, m12, prev
+
+
+def stereo_matches(ex_left, ex_right, kps_l, desc_l, kps_r, desc_r, bf, fx, frame_l=0, frame_r=0):
+    """Frame::ComputeStereoMatches (src/Frame.cc:513-699) on the pyramids still held by the two
+    extractors.  Returns (mvuRight, mvDepth, number of matches before the median cut)."""
+    kps_l, kps_r = _np(kps_l), _np(kps_r)
+    desc_l, desc_r = _np(desc_l, np.uint8), _np(desc_r, np.uint8)
+    ur, dep = np.zeros(len(kps_l), np.float32), np.zeros(len(kps_l), np.float32)
+    n = C.c_int()
+    rc = lib().orbm_stereo_matches(ex_left._h, frame_l, ex_right._h, frame_r, len(kps_l), kps_l.ctypes.data, desc_l.ctypes.data,
+                                   len(kps_r), kps_r.ctypes.data, desc_r.ctypes.data, bf, fx, ur.ctypes.data, dep.ctypes.data, C.byref(n))
+    if rc:
+        raise OrbError(rc, "orbm_stereo_matches failed")
+    return ur, dep, n.value
 
 
 def hamming_bf(queries, train, device=0, nprob=1):

@@ -305,6 +305,28 @@ int copy_out_2d(orbx_ctx* c, uint8_t* dst, size_t dst_pitch, const uint8_t* d_sr
 
 } // namespace
 
+int orb_ctx_levels(orbx_ctx* c, int frame, const uint8_t** ptr, int* pitch, int* w, int* h,
+                   float* scale, float* inv_scale, int* nlevels, int* device)
+{
+    const int rel = resident_frame(c, frame, 0);
+    if (rel < 0) return 1;
+    if (cudaSetDevice(c->device) != cudaSuccess || sync_all(c)) return 1;
+    const Slot& s = c->slot[c->last_slot];
+    for (int l = 0; l < c->plan.nlevels; ++l) {
+        const OrbLevel& L = c->plan.lv[l];
+        if (ptr) ptr[l] = l == 0 ? c->last_img0 + (size_t)rel * c->last_img0_stride
+                                 : (const uint8_t*)s.pyr.p + (size_t)rel * c->plan.pyr_bytes + L.img_off;
+        if (pitch) pitch[l] = l == 0 ? c->last_img0_pitch : L.pitch;
+        if (w) w[l] = L.w;
+        if (h) h[l] = L.h;
+        if (scale) scale[l] = c->params.scale[l];
+        if (inv_scale) inv_scale[l] = c->params.inv_scale[l];
+    }
+    if (nlevels) *nlevels = c->plan.nlevels;
+    if (device) *device = c->device;
+    return 0;
+}
+
 extern "C" {
 
 int orbx_create(orbx_ctx** out, int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST, int device)

@@ -1,13 +1,41 @@
 // orb_match.cu -- Hamming matching kernels (sm_100a) and their C entry points.
-//   k_hamming_bf   ORBmatcher::DescriptorDistance over all pairs, src/ORBmatcher.cc:46-63,
-//                  with the best / second-best bookkeeping of :129-141 (strict <, first wins)
-// 256-bit descriptors live in registers (query) and shared memory (train tile); the distance
-// is 8 x (LOP3 xor + POPC).  Integer pipe only.
+//   k_hamming_bf        ORBmatcher::DescriptorDistance over all pairs, src/ORBmatcher.cc:46-63, with the
+//                       best / second-best bookkeeping of :129-141 (strict <, first wins)
+//   k_grid_build        Frame::AssignFeaturesToGrid / PosInGrid           src/Frame.cc:243-259, 412-422
+//   k_window_candidates Frame::GetFeaturesInArea + DescriptorDistance for every query (parallel part)
+//   k_resolve_*         the order-dependent part of the three window matchers, one warp per problem:
+//                       SearchByProjection(Frame, MapPoints)  src/ORBmatcher.cc:73-157
+//                       SearchByProjection(Frame, Frame)      src/ORBmatcher.cc:160-300
+//                       SearchForInitialization               src/ORBmatcher.cc:1055-1180
+//                       incl. the rotation histogram and ComputeThreeMaxima (:1663-1707)
+//   k_stereo_*          Frame::ComputeStereoMatches            src/Frame.cc:513-699
+// 256-bit descriptors as 8 x u32; distance = 8 x (LOP3 xor + POPC).  Integer pipe only.
+//
+// Why two phases: a query's candidate set and distances do not depend on other queries, but the
+// reference skips candidates that an EARLIER query already claimed (:115-117, :234-236, :1094), so the
+// choice of the best candidate must follow query order.  Phase 1 lists, per query and in the
+// reference's candidate order (grid column, grid row, insertion), every candidate that passes the
+// order-independent filters together with its distance; phase 2 walks the queries in order.  The
+// reference's running best/second-best update equals "the two smallest by (distance, position)", so a
+// warp reduces 32 candidates at a time.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#include "../../include/orb_b200.h"
+#include <cmath>
+#include <vector>
 
+#include "../../include/orb_b200.h"
+#include "orb_launch.h"
+
+#define GRID_COLS 64    // FRAME_GRID_COLS, include/Frame.h:38
+#define GRID_ROWS 48    // FRAME_GRID_ROWS, include/Frame.h:37
+#define GRID_CELLS (GRID_COLS * GRID_ROWS)
+#define TH_HIGH 100     // src/ORBmatcher.cc:37
+#define TH_LOW 50       // :38
+#define HISTO_LENGTH 30 // :39
+#define MAX_KP 8192     // keypoints per frame the grid kernel sorts in shared memory
+
+// ------------------------------------------------------------------------------ brute force
 #define BF_NT 128     // threads per block = queries per block
 #define BF_TILE 128   // train descriptors per shared-memory tile
 
@@ -44,6 +72,446 @@ __global__ void __launch_bounds__(BF_NT) k_hamming_bf(const uint4* __restrict__ 
     }
 }
 
+// ------------------------------------------------------------------------------ grid
+struct DevFrame {
+    int n;
+    const orbx_kp* kps;
+    const uint32_t* desc;    // n x 8 words
+    const float* u_right;    // or nullptr
+    float min_x, min_y, inv_w, inv_h;
+    int* cell_start;         // [GRID_CELLS + 1]
+    uint16_t* items;         // keypoint indices grouped by cell, index order inside a cell
+};
+
+// One block: cell of every keypoint (round(), not floor: src/Frame.cc:414-415), keys (cell << 16 | index)
+// sorted in shared memory, so a cell's members come out in insertion (index) order.
+__global__ void __launch_bounds__(1024) k_grid_build(DevFrame F)
+{
+    extern __shared__ uint32_t keys[];
+    int sn = 32; while (sn < F.n) sn <<= 1;
+    for (int i = threadIdx.x; i < sn; i += blockDim.x) {
+        uint32_t key = 0xffffffffu;
+        if (i < F.n) {
+            const int px = (int)roundf((F.kps[i].x - F.min_x) * F.inv_w);
+            const int py = (int)roundf((F.kps[i].y - F.min_y) * F.inv_h);
+            if (!(px < 0 || px >= GRID_COLS || py < 0 || py >= GRID_ROWS)) key = ((uint32_t)(px * GRID_ROWS + py) << 16) | (uint32_t)i;
+        }
+        keys[i] = key;
+    }
+    for (int i = threadIdx.x; i <= GRID_CELLS; i += blockDim.x) F.cell_start[i] = 0;
+    __syncthreads();
+    for (int k = 2; k <= sn; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < sn; i += blockDim.x) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const uint32_t a = keys[i], b = keys[ixj];
+                    if (((i & k) == 0) ? (a > b) : (a < b)) { keys[i] = b; keys[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    // cell_start[c] = first position whose cell >= c
+    for (int i = threadIdx.x; i < sn; i += blockDim.x) {
+        const uint32_t key = keys[i];
+        const int c = key == 0xffffffffu ? GRID_CELLS : (int)(key >> 16);
+        const int cprev = i == 0 ? -1 : (keys[i - 1] == 0xffffffffu ? GRID_CELLS : (int)(keys[i - 1] >> 16));
+        for (int cc = cprev + 1; cc <= c; ++cc) F.cell_start[cc] = i;
+        if (key != 0xffffffffu) F.items[i] = (uint16_t)(key & 0xffffu);
+        if (i == sn - 1) for (int cc = c + 1; cc <= GRID_CELLS; ++cc) F.cell_start[cc] = sn;
+    }
+}
+
+// ------------------------------------------------------------------------------ phase 1
+struct WinQuery {
+    float u, v, r;          // window centre and half-size (Frame::GetFeaturesInArea x, y, r)
+    int min_level, max_level;
+    float ur, er_max;       // right-image check: skip if uRight[idx] > 0 and |ur - uRight[idx]| > er_max
+    int valid;              // 0: the reference `continue`s before the window query
+};
+
+__device__ __forceinline__ int hamming256(const uint32_t* a, const uint4 b0, const uint4 b1)
+{
+    return __popc(a[0] ^ b0.x) + __popc(a[1] ^ b0.y) + __popc(a[2] ^ b0.z) + __popc(a[3] ^ b0.w) +
+           __popc(a[4] ^ b1.x) + __popc(a[5] ^ b1.y) + __popc(a[6] ^ b1.z) + __popc(a[7] ^ b1.w);
+}
+
+// One warp per query.  list[q*cap + k] = candidate index | distance << 16, in the reference's order.
+__global__ void __launch_bounds__(256) k_window_candidates(const DevFrame F, const WinQuery* __restrict__ queries, const uint32_t* __restrict__ qdesc,
+                                                          const int nq, uint32_t* __restrict__ list, int* __restrict__ count, const int cap)
+{
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (q >= nq) return;
+    const WinQuery Q = queries[q];
+    int n = 0;
+    if (Q.valid) {
+        // src/Frame.cc:355-372
+        const int nMinCellX = max(0, (int)floorf((Q.u - F.min_x - Q.r) * F.inv_w));
+        const int nMaxCellX = min(GRID_COLS - 1, (int)ceilf((Q.u - F.min_x + Q.r) * F.inv_w));
+        const int nMinCellY = max(0, (int)floorf((Q.v - F.min_y - Q.r) * F.inv_h));
+        const int nMaxCellY = min(GRID_ROWS - 1, (int)ceilf((Q.v - F.min_y + Q.r) * F.inv_h));
+        if (nMinCellX < GRID_COLS && nMaxCellX >= 0 && nMinCellY < GRID_ROWS && nMaxCellY >= 0) {
+            const bool check_levels = Q.min_level > 0 || Q.max_level >= 0;       // :375
+            uint32_t d[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) d[i] = __ldg(qdesc + (size_t)q * 8 + i);
+            uint32_t* out = list + (size_t)q * cap;
+            for (int ix = nMinCellX; ix <= nMaxCellX; ++ix) {
+                // the cells (ix, iy0..iy1) are adjacent in the sorted item list
+                const int s0 = F.cell_start[ix * GRID_ROWS + nMinCellY], s1 = F.cell_start[ix * GRID_ROWS + nMaxCellY + 1];
+                for (int base = s0; base < s1; base += 32) {
+                    const int j = base + lane;
+                    bool ok = j < s1;
+                    int idx = 0, dist = 0;
+                    if (ok) {
+                        idx = F.items[j];
+                        const orbx_kp kp = F.kps[idx];
+                        if (check_levels) {
+                            if (kp.octave < Q.min_level) ok = false;
+                            if (Q.max_level >= 0 && kp.octave > Q.max_level) ok = false;
+                        }
+                        if (!(fabsf(kp.x - Q.u) < Q.r && fabsf(kp.y - Q.v) < Q.r)) ok = false;   // :402
+                        if (ok && F.u_right) {
+                            const float ur = F.u_right[idx];
+                            if (ur > 0 && fabsf(Q.ur - ur) > Q.er_max) ok = false;
+                        }
+                        if (ok) {
+                            const uint4* p = (const uint4*)(F.desc + (size_t)idx * 8);
+                            dist = hamming256(d, __ldg(p), __ldg(p + 1));
+                        }
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, ok);
+                    if (ok) out[n + __popc(m & ((1u << lane) - 1u))] = (uint32_t)idx | ((uint32_t)dist << 16);
+                    n += __popc(m);
+                }
+            }
+        }
+    }
+    if (lane == 0) count[q] = n;
+}
+
+// ------------------------------------------------------------------------------ phase 2 helpers
+// Two smallest (distance, position) keys of one query's list among the candidates `usable` admits.
+// key = dist << 20 | position (lists are shorter than 2^20); 0xffffffff = none.
+template <typename Usable>
+__device__ __forceinline__ void warp_top2(const uint32_t* lst, const int n, const int lane, Usable usable,
+                                         uint32_t& k1, uint32_t& k2)
+{
+    k1 = 0xffffffffu; k2 = 0xffffffffu;
+    for (int base = 0; base < n; base += 32) {
+        const int j = base + lane;
+        uint32_t key = 0xffffffffu;
+        if (j < n) {
+            const uint32_t e = lst[j];
+            if (usable((int)(e & 0xffffu), (int)(e >> 16))) key = ((e >> 16) << 20) | (uint32_t)j;
+        }
+        const uint32_t m1 = __reduce_min_sync(0xffffffffu, key);
+        const uint32_t m2 = __reduce_min_sync(0xffffffffu, key == m1 ? 0xffffffffu : key);
+        // merge (m1 <= m2) into (k1 <= k2); keys are unique or "none"
+        if (m1 < k1) { k2 = min(k1, m2); k1 = m1; }
+        else k2 = min(k2, m1);
+    }
+}
+
+// ComputeThreeMaxima, src/ORBmatcher.cc:1663-1707 (every lane computes the same result)
+__device__ __forceinline__ void three_maxima(const int* sizes, int& ind1, int& ind2, int& ind3)
+{
+    int max1 = 0, max2 = 0, max3 = 0;
+    ind1 = ind2 = ind3 = -1;
+    for (int i = 0; i < HISTO_LENGTH; ++i) {
+        const int s = sizes[i];
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+        else if (s > max3) { max3 = s; ind3 = i; }
+    }
+    if ((float)max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+    else if ((float)max3 < 0.1f * (float)max1) ind3 = -1;
+}
+
+// rotation-histogram bin, src/ORBmatcher.cc:263-268 (factor = 1.0f/HISTO_LENGTH, as in the reference)
+__device__ __forceinline__ int rot_bin(const float a1, const float a2)
+{
+    float rot = __fsub_rn(a1, a2);
+    if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+    int bin = (int)roundf(__fmul_rn(rot, 1.0f / HISTO_LENGTH));
+    if (bin == HISTO_LENGTH) bin = 0;
+    return bin;
+}
+
+// ------------------------------------------------------------------------------ phase 2: map points -> frame
+// src/ORBmatcher.cc:99-153.  assign[k]: map point attached to keypoint k (-1 none).  One warp.
+__global__ void __launch_bounds__(32) k_resolve_points(const DevFrame F, const int nq, const WinQuery* __restrict__ queries,
+                                                      const uint32_t* __restrict__ list, const int* __restrict__ count, const int cap,
+                                                      const int* __restrict__ observations, int* __restrict__ assign, const float nnratio,
+                                                      int* __restrict__ nmatches_out)
+{
+    const int lane = threadIdx.x;
+    int nmatches = 0;
+    for (int q = 0; q < nq; ++q) {
+        const int n = queries[q].valid ? count[q] : 0;
+        if (n == 0) continue;
+        const uint32_t* lst = list + (size_t)q * cap;
+        uint32_t k1, k2;
+        warp_top2(lst, n, lane, [&](int idx, int) { const int a = assign[idx]; return !(a >= 0 && observations[a] > 0); }, k1, k2);   // :115-117
+        if (k1 == 0xffffffffu) continue;
+        const int bestDist = (int)(k1 >> 20), bestIdx = (int)(lst[k1 & 0xfffffu] & 0xffffu);
+        if (bestDist <= TH_HIGH) {
+            const int bestLevel = F.kps[bestIdx].octave;
+            int bestDist2 = 256, bestLevel2 = -1;
+            if (k2 != 0xffffffffu) { bestDist2 = (int)(k2 >> 20); bestLevel2 = F.kps[lst[k2 & 0xfffffu] & 0xffffu].octave; }
+            if (bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(nnratio, (float)bestDist2)) continue;   // :146-149
+            __syncwarp();
+            if (lane == 0) assign[bestIdx] = q;
+            __syncwarp();
+            ++nmatches;
+        }
+    }
+    if (lane == 0) *nmatches_out = nmatches;
+}
+
+// ------------------------------------------------------------------------------ phase 2: last frame -> current frame
+// src/ORBmatcher.cc:187-297.  obs[k]: Observations() of the point attached to current keypoint k (-1 free).
+__global__ void __launch_bounds__(32) k_resolve_frame(const DevFrame F, const int nq, const WinQuery* __restrict__ queries,
+                                                     const uint32_t* __restrict__ list, const int* __restrict__ count, const int cap,
+                                                     const int* __restrict__ last_obs, const float* __restrict__ last_angle,
+                                                     int* __restrict__ obs, int* __restrict__ assign, const int check_ori,
+                                                     int* __restrict__ hist_entry /* [nq] kp index */, int* __restrict__ hist_bin /* [nq] */,
+                                                     int* __restrict__ nmatches_out)
+{
+    __shared__ int sizes[HISTO_LENGTH];
+    const int lane = threadIdx.x;
+    if (lane < HISTO_LENGTH) sizes[lane] = 0;
+    __syncwarp();
+    int nmatches = 0, nh = 0;
+    for (int q = 0; q < nq; ++q) {
+        const int n = queries[q].valid ? count[q] : 0;
+        if (n == 0) continue;
+        const uint32_t* lst = list + (size_t)q * cap;
+        uint32_t k1, k2;
+        warp_top2(lst, n, lane, [&](int idx, int) { return !(obs[idx] > 0); }, k1, k2);          // :234-236
+        if (k1 == 0xffffffffu) continue;
+        const int bestDist = (int)(k1 >> 20), bestIdx = (int)(lst[k1 & 0xfffffu] & 0xffffu);
+        if (bestDist <= TH_HIGH) {                                                                // :256
+            __syncwarp();
+            if (lane == 0) {
+                assign[bestIdx] = q; obs[bestIdx] = last_obs[q];
+                if (check_ori) {
+                    const int bin = rot_bin(last_angle[q], F.kps[bestIdx].angle);
+                    hist_entry[nh] = bestIdx; hist_bin[nh] = bin; sizes[bin] += 1;
+                }
+            }
+            __syncwarp();
+            ++nmatches; ++nh;
+        }
+    }
+    if (check_ori) {
+        int i1, i2, i3;
+        three_maxima(sizes, i1, i2, i3);
+        // every entry of a rejected bin clears its keypoint and decrements, duplicates included (:286-296)
+        int dec = 0;
+        for (int e = lane; e < nh; e += 32) {
+            const int b = hist_bin[e];
+            if (b != i1 && b != i2 && b != i3) { assign[hist_entry[e]] = -1; ++dec; }
+        }
+        for (int d = 16; d > 0; d >>= 1) dec += __shfl_xor_sync(0xffffffffu, dec, d);
+        nmatches -= dec;
+    }
+    if (lane == 0) *nmatches_out = nmatches;
+}
+
+// ------------------------------------------------------------------------------ phase 2: monocular initialisation
+// src/ORBmatcher.cc:1071-1177.  Queries = F1 keypoints (all of them; octave > 0 are invalid).
+__global__ void __launch_bounds__(32) k_resolve_init(const DevFrame F2, const int n1, const WinQuery* __restrict__ queries,
+                                                    const uint32_t* __restrict__ list, const int* __restrict__ count, const int cap,
+                                                    const float* __restrict__ angle1, int* __restrict__ matched_dist /* [n2] */,
+                                                    int* __restrict__ matches21 /* [n2] */, int* __restrict__ matches12 /* [n1] */,
+                                                    const float nnratio, const int check_ori, int* __restrict__ hist_entry, int* __restrict__ hist_bin,
+                                                    float* __restrict__ prev_matched, int* __restrict__ nmatches_out)
+{
+    __shared__ int sizes[HISTO_LENGTH];
+    const int lane = threadIdx.x;
+    if (lane < HISTO_LENGTH) sizes[lane] = 0;
+    __syncwarp();
+    int nmatches = 0, nh = 0;
+    for (int i1 = 0; i1 < n1; ++i1) {
+        const int n = queries[i1].valid ? count[i1] : 0;
+        if (n == 0) continue;
+        const uint32_t* lst = list + (size_t)i1 * cap;
+        uint32_t k1, k2;
+        warp_top2(lst, n, lane, [&](int idx, int dist) { return !(matched_dist[idx] <= dist); }, k1, k2);   // :1094
+        if (k1 == 0xffffffffu) continue;
+        const int bestDist = (int)(k1 >> 20), bestIdx2 = (int)(lst[k1 & 0xfffffu] & 0xffffu);
+        // INT_MAX second distance when there is none: (float)INT_MAX * nnratio is huge, the test passes
+        const float second = k2 == 0xffffffffu ? 2147483648.0f : (float)(int)(k2 >> 20);
+        if (bestDist <= TH_LOW && (float)bestDist < __fmul_rn(second, nnratio)) {                // :1109-1112
+            __syncwarp();
+            const int old = matches21[bestIdx2];
+            if (old >= 0) --nmatches;                                                             // :1115-1119
+            __syncwarp();
+            if (lane == 0) {
+                if (old >= 0) matches12[old] = -1;
+                matches12[i1] = bestIdx2; matches21[bestIdx2] = i1; matched_dist[bestIdx2] = bestDist;
+                if (check_ori) {
+                    const int bin = rot_bin(angle1[i1], F2.kps[bestIdx2].angle);
+                    hist_entry[nh] = i1; hist_bin[nh] = bin; sizes[bin] += 1;
+                }
+            }
+            __syncwarp();
+            ++nmatches; ++nh;
+        }
+    }
+    if (check_ori) {
+        int i1, i2, i3;
+        three_maxima(sizes, i1, i2, i3);
+        int dec = 0;
+        for (int e = lane; e < nh; e += 32) {
+            const int b = hist_bin[e];
+            if (b != i1 && b != i2 && b != i3) {
+                const int idx1 = hist_entry[e];
+                if (matches12[idx1] >= 0) { matches12[idx1] = -1; ++dec; }                        // :1163-1167 (an index is pushed at most once)
+            }
+        }
+        for (int d = 16; d > 0; d >>= 1) dec += __shfl_xor_sync(0xffffffffu, dec, d);
+        nmatches -= dec;
+    }
+    __syncwarp();
+    for (int i = lane; i < n1; i += 32)                                                           // :1175-1177
+        if (matches12[i] >= 0) { prev_matched[2 * i] = F2.kps[matches12[i]].x; prev_matched[2 * i + 1] = F2.kps[matches12[i]].y; }
+    if (lane == 0) *nmatches_out = nmatches;
+}
+
+// ------------------------------------------------------------------------------ stereo
+struct StereoLevels {
+    const uint8_t* l[ORB_MAX_LEVELS]; const uint8_t* r[ORB_MAX_LEVELS];
+    int lpitch[ORB_MAX_LEVELS], rpitch[ORB_MAX_LEVELS], w[ORB_MAX_LEVELS], h[ORB_MAX_LEVELS];
+    float scale[ORB_MAX_LEVELS], inv_scale[ORB_MAX_LEVELS];
+};
+
+__device__ __forceinline__ int refl101(int i, const int n)
+{
+    while (i < 0 || i >= n) i = i < 0 ? -i : 2 * (n - 1) - i;
+    return i;
+}
+
+// One warp per left keypoint: row-band Hamming search (:546-596), 11x11 SAD over 11 shifts (:599-648),
+// parabola sub-pixel (:650-663), disparity / depth (:666-679).  sad[iL] = best SAD or -1.
+__global__ void __launch_bounds__(256) k_stereo_match(const int nl, const orbx_kp* __restrict__ kl, const uint32_t* __restrict__ dl,
+                                                     const int nr, const orbx_kp* __restrict__ kr, const uint32_t* __restrict__ dr,
+                                                     const StereoLevels P, const float bf, const float mb,
+                                                     float* __restrict__ u_right, float* __restrict__ depth, int* __restrict__ sad)
+{
+    const int iL = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (iL >= nl) return;
+    float out_u = -1.0f, out_d = -1.0f; int out_s = -1;
+    const orbx_kp kp = kl[iL];
+    const int levelL = kp.octave, rowL = (int)kp.y;
+    const float uL = kp.x;
+    const float minD = 0.f, maxD = __fdiv_rn(bf, mb);
+    const float minU = __fsub_rn(uL, maxD), maxU = __fsub_rn(uL, minD);
+    uint32_t best = 0xffffffffu;     // dist << 16 | iR
+    if (!(maxU < 0)) {
+        uint32_t d[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[i] = __ldg(dl + (size_t)iL * 8 + i);
+        for (int base = 0; base < nr; base += 32) {
+            const int iR = base + lane;
+            if (iR < nr) {
+                const orbx_kp k = kr[iR];
+                const float r = __fmul_rn(2.0f, P.scale[k.octave]);
+                const int maxr = (int)ceilf(__fadd_rn(k.y, r)), minr = (int)floorf(__fsub_rn(k.y, r));   // :535-539
+                if (rowL >= minr && rowL <= maxr && !(k.octave < levelL - 1 || k.octave > levelL + 1) && k.x >= minU && k.x <= maxU) {
+                    const uint4* p = (const uint4*)(dr + (size_t)iR * 8);
+                    const int dist = hamming256(d, __ldg(p), __ldg(p + 1));
+                    if (dist < TH_HIGH) best = min(best, ((uint32_t)dist << 16) | (uint32_t)iR);   // bestDist starts at TH_HIGH (:568)
+                }
+            }
+        }
+        best = __reduce_min_sync(0xffffffffu, best);
+    }
+    const int thOrbDist = (TH_HIGH + TH_LOW) / 2;
+    if (best != 0xffffffffu && (int)(best >> 16) < thOrbDist) {
+        const int bestIdxR = (int)(best & 0xffffu);
+        const float uR0 = kr[bestIdxR].x;
+        const float sf = P.inv_scale[levelL];
+        const float scaleduL = roundf(__fmul_rn(kp.x, sf)), scaledvL = roundf(__fmul_rn(kp.y, sf)), scaleduR0 = roundf(__fmul_rn(uR0, sf));
+        const int w = 5, L = 5;
+        const int lw = P.w[levelL], lh = P.h[levelL];
+        const float iniu = scaleduR0 + L - w, endu = scaleduR0 + L + w + 1;                        // :624-625
+        if (!(iniu < 0 || endu >= (float)lw)) {
+            const uint8_t* IL = P.l[levelL]; const uint8_t* IR = P.r[levelL];
+            const int lp = P.lpitch[levelL], rp = P.rpitch[levelL];
+            const int r0 = (int)(scaledvL - w), cL0 = (int)(scaleduL - w);
+            // patch reads may leave the ROI by up to 10 px on the left: that is the REFLECT_101 border of mvImagePyramid
+            const int cL = IL[(size_t)refl101(r0 + w, lh) * lp + refl101(cL0 + w, lw)];
+            int bestDist = 2147483647, bestincR = 0;
+            float vDists[11];
+#pragma unroll 1
+            for (int incR = -L; incR <= L; ++incR) {
+                const int cR0 = (int)(scaleduR0 + incR - w);
+                const int cR = IR[(size_t)refl101(r0 + w, lh) * rp + refl101(cR0 + w, lw)];
+                int s = 0;
+                for (int p = lane; p < 121; p += 32) {
+                    const int yy = p / 11, xx = p - yy * 11;
+                    const int a = (int)IL[(size_t)refl101(r0 + yy, lh) * lp + refl101(cL0 + xx, lw)] - cL;
+                    const int b = (int)IR[(size_t)refl101(r0 + yy, lh) * rp + refl101(cR0 + xx, lw)] - cR;
+                    s += abs(a - b);
+                }
+                s = __reduce_add_sync(0xffffffffu, s);
+                const float dist = (float)s;
+                if (dist < (float)bestDist) { bestDist = (int)dist; bestincR = incR; }
+                vDists[L + incR] = dist;
+            }
+            if (!(bestincR == -L || bestincR == L)) {
+                float dist1 = 0, dist2 = 0, dist3 = 0;
+#pragma unroll
+                for (int i = 0; i < 11; ++i) {   // (indexing with a runtime value would spill the array)
+                    if (i == L + bestincR - 1) dist1 = vDists[i];
+                    if (i == L + bestincR) dist2 = vDists[i];
+                    if (i == L + bestincR + 1) dist3 = vDists[i];
+                }
+                const float deltaR = __fdiv_rn(__fsub_rn(dist1, dist3), __fmul_rn(2.0f, __fsub_rn(__fadd_rn(dist1, dist3), __fmul_rn(2.0f, dist2))));
+                if (!(deltaR < -1 || deltaR > 1)) {
+                    float bestuR = __fmul_rn(P.scale[levelL], __fadd_rn(__fadd_rn(scaleduR0, (float)bestincR), deltaR));
+                    float disparity = __fsub_rn(uL, bestuR);
+                    if (disparity >= minD && disparity < maxD) {
+                        if (disparity <= 0) { disparity = (float)0.01; bestuR = (float)((double)uL - 0.01); }
+                        out_d = __fdiv_rn(bf, disparity); out_u = bestuR; out_s = bestDist;
+                    }
+                }
+            }
+        }
+    }
+    if (lane == 0) { u_right[iL] = out_u; depth[iL] = out_d; sad[iL] = out_s; }
+}
+
+// Median cut (:685-698): threshold = 1.5f*1.4f*median of the SADs, median = element nd/2 of the sorted list.
+__global__ void __launch_bounds__(1024) k_stereo_cut(const int nl, const int* __restrict__ sad, float* __restrict__ u_right, float* __restrict__ depth, int* __restrict__ nmatched)
+{
+    __shared__ int s_nd, s_median;
+    if (threadIdx.x == 0) { s_nd = 0; s_median = -1; }
+    __syncthreads();
+    int mine = 0;
+    for (int i = threadIdx.x; i < nl; i += blockDim.x) mine += sad[i] >= 0;
+    atomicAdd(&s_nd, mine);
+    __syncthreads();
+    const int nd = s_nd;
+    if (nd == 0) { if (threadIdx.x == 0) *nmatched = 0; return; }
+    const int k = nd / 2;
+    for (int i = threadIdx.x; i < nl; i += blockDim.x) {
+        const int v = sad[i];
+        if (v < 0) continue;
+        int less = 0, leq = 0;
+        for (int j = 0; j < nl; ++j) { const int o = sad[j]; if (o >= 0) { less += o < v; leq += o <= v; } }
+        if (less <= k && k < leq) s_median = v;    // every thread that hits writes the same value
+    }
+    __syncthreads();
+    const float thDist = __fmul_rn(1.5f * 1.4f, (float)s_median);
+    for (int i = threadIdx.x; i < nl; i += blockDim.x)
+        if (sad[i] >= 0 && !((float)sad[i] < thDist)) { u_right[i] = -1.0f; depth[i] = -1.0f; }
+    if (threadIdx.x == 0) *nmatched = nd;
+}
+
+// ================================================================================ host side
 namespace {
 bool dev_ptr(const void* p)
 {
@@ -51,35 +519,298 @@ bool dev_ptr(const void* p)
     if (!p || cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
     return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
-struct Tmp {
-    void* p = nullptr;
-    ~Tmp() { if (p) cudaFree(p); }
+
+// Small RAII arena for one call: device copies of the inputs and scratch.
+struct Scratch {
+    std::vector<void*> ptrs;
+    bool ok = true;
+    ~Scratch() { for (void* p : ptrs) cudaFree(p); }
+    void* alloc(size_t bytes)
+    {
+        void* p = nullptr;
+        if (cudaMalloc(&p, bytes ? bytes : 4) != cudaSuccess) { cudaGetLastError(); ok = false; return nullptr; }
+        ptrs.push_back(p);
+        return p;
+    }
+    template <typename T> T* up(const T* h, size_t count)
+    {
+        T* d = (T*)alloc(sizeof(T) * count);
+        if (d && h && count && cudaMemcpy(d, h, sizeof(T) * count, cudaMemcpyHostToDevice) != cudaSuccess) { cudaGetLastError(); ok = false; }
+        return d;
+    }
 };
+
+bool make_frame(Scratch& S, const orbm_frame* F, DevFrame* D)
+{
+    if (!F || F->n < 0 || F->n > MAX_KP || (F->n > 0 && (!F->kps || !F->desc))) return false;
+    D->n = F->n;
+    D->kps = S.up(F->kps, (size_t)F->n);
+    D->desc = (const uint32_t*)S.up(F->desc, (size_t)F->n * 32);
+    D->u_right = F->u_right ? S.up(F->u_right, (size_t)F->n) : nullptr;
+    D->min_x = F->min_x; D->min_y = F->min_y;
+    D->inv_w = (float)GRID_COLS / (F->max_x - F->min_x);     // src/Frame.cc:108
+    D->inv_h = (float)GRID_ROWS / (F->max_y - F->min_y);     // :109
+    D->cell_start = (int*)S.alloc(sizeof(int) * (GRID_CELLS + 1));
+    D->items = (uint16_t*)S.alloc(sizeof(uint16_t) * (size_t)(F->n + 32));
+    if (!S.ok) return false;
+    int sn = 32; while (sn < F->n) sn <<= 1;
+    k_grid_build<<<1, 1024, (size_t)sn * 4>>>(*D);
+    return cudaGetLastError() == cudaSuccess;
+}
+
+#define CKM(x) do { if ((x) != cudaSuccess) { cudaGetLastError(); return ORBX_E_CUDA; } } while (0)
+
+int run_candidates(Scratch& S, const DevFrame& D, const std::vector<WinQuery>& hq, const uint8_t* qdesc_host, int nq,
+                   WinQuery** dq, uint32_t** list, int** count, int* cap)
+{
+    *cap = D.n > 0 ? D.n : 1;
+    *dq = S.up(hq.data(), (size_t)nq);
+    const uint32_t* dqd = (const uint32_t*)S.up(qdesc_host, (size_t)nq * 32);
+    *list = (uint32_t*)S.alloc(sizeof(uint32_t) * (size_t)nq * (size_t)*cap);
+    *count = (int*)S.alloc(sizeof(int) * (size_t)nq);
+    if (!S.ok) return ORBX_E_CUDA;
+    k_window_candidates<<<(nq + 7) / 8, 256>>>(D, *dq, dqd, nq, *list, *count, *cap);
+    CKM(cudaGetLastError());
+    return ORBX_OK;
+}
 } // namespace
 
-extern "C" int orbm_hamming_bf(const uint8_t* q, int nq, const uint8_t* t, int nt, int nprob,
-                               int* best_idx, int* best_dist, int* second_dist, int device)
+extern "C" {
+
+int orbm_hamming_bf(const uint8_t* q, int nq, const uint8_t* t, int nt, int nprob,
+                    int* best_idx, int* best_dist, int* second_dist, int device)
 {
     if (!q || !t || !best_idx || !best_dist || !second_dist || nq <= 0 || nt < 0 || nprob <= 0) return ORBX_E_ARG;
     if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return ORBX_E_CUDA; }
     const size_t qb = (size_t)nprob * nq * 32, tb = (size_t)nprob * nt * 32, ob = (size_t)nprob * nq * 4;
-    Tmp dq, dt, d0, d1, d2;
+    Scratch S;
     const uint8_t* pq = q; const uint8_t* pt = t;
     int* o0 = best_idx; int* o1 = best_dist; int* o2 = second_dist;
-#define CK(x) do { if ((x) != cudaSuccess) { cudaGetLastError(); return ORBX_E_CUDA; } } while (0)
-    if (!dev_ptr(q)) { CK(cudaMalloc(&dq.p, qb)); CK(cudaMemcpy(dq.p, q, qb, cudaMemcpyHostToDevice)); pq = (const uint8_t*)dq.p; }
-    if (!dev_ptr(t)) { CK(cudaMalloc(&dt.p, tb + 32)); CK(cudaMemcpy(dt.p, t, tb, cudaMemcpyHostToDevice)); pt = (const uint8_t*)dt.p; }
+    if (!dev_ptr(q)) pq = S.up(q, qb);
+    if (!dev_ptr(t)) pt = S.up(t, tb + 32);
     const bool h0 = !dev_ptr(best_idx), h1 = !dev_ptr(best_dist), h2 = !dev_ptr(second_dist);
-    if (h0) { CK(cudaMalloc(&d0.p, ob)); o0 = (int*)d0.p; }
-    if (h1) { CK(cudaMalloc(&d1.p, ob)); o1 = (int*)d1.p; }
-    if (h2) { CK(cudaMalloc(&d2.p, ob)); o2 = (int*)d2.p; }
+    if (h0) o0 = (int*)S.alloc(ob);
+    if (h1) o1 = (int*)S.alloc(ob);
+    if (h2) o2 = (int*)S.alloc(ob);
+    if (!S.ok) return ORBX_E_CUDA;
     if (((uintptr_t)pq | (uintptr_t)pt) & 15) return ORBX_E_ARG; // descriptors are read as 128-bit words
     k_hamming_bf<<<dim3((nq + BF_NT - 1) / BF_NT, nprob), BF_NT>>>((const uint4*)pq, nq, (const uint4*)pt, nt, o0, o1, o2);
-    CK(cudaGetLastError());
-    if (h0) CK(cudaMemcpy(best_idx, o0, ob, cudaMemcpyDeviceToHost));
-    if (h1) CK(cudaMemcpy(best_dist, o1, ob, cudaMemcpyDeviceToHost));
-    if (h2) CK(cudaMemcpy(second_dist, o2, ob, cudaMemcpyDeviceToHost));
-    CK(cudaDeviceSynchronize());
-#undef CK
+    CKM(cudaGetLastError());
+    if (h0) CKM(cudaMemcpy(best_idx, o0, ob, cudaMemcpyDeviceToHost));
+    if (h1) CKM(cudaMemcpy(best_dist, o1, ob, cudaMemcpyDeviceToHost));
+    if (h2) CKM(cudaMemcpy(second_dist, o2, ob, cudaMemcpyDeviceToHost));
+    CKM(cudaDeviceSynchronize());
     return ORBX_OK;
 }
+
+int orbm_search_by_projection_points(const orbm_frame* F, const float* scale, int nlevels,
+                                     int nq, const float* proj_xyxr, const int* level, const float* view_cos,
+                                     const uint8_t* in_view, const uint8_t* bad, const int* observations,
+                                     const uint8_t* qdesc, const int* init_assign, int* assign_out,
+                                     float th, float nnratio, int* nmatches, int device)
+{
+    if (!F || !scale || nq < 0 || !assign_out || !nmatches || (nq > 0 && (!proj_xyxr || !level || !view_cos || !in_view || !bad || !observations || !qdesc)))
+        return ORBX_E_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return ORBX_E_CUDA; }
+    *nmatches = 0;
+    for (int k = 0; k < F->n; ++k) assign_out[k] = init_assign ? init_assign[k] : -1;
+    if (nq == 0 || F->n == 0) return ORBX_OK;
+    Scratch S;
+    DevFrame D;
+    if (!make_frame(S, F, &D)) return S.ok ? ORBX_E_ARG : ORBX_E_CUDA;
+    // the per-query part of the reference loop that does not depend on other queries (:82-98, :119-124)
+    std::vector<WinQuery> hq((size_t)nq);
+    const bool bFactor = th != 1.0;
+    for (int i = 0; i < nq; ++i) {
+        WinQuery& Q = hq[(size_t)i];
+        Q.valid = in_view[i] && !bad[i] && level[i] >= 0 && level[i] < nlevels;
+        if (!Q.valid) continue;
+        float r = ((double)view_cos[i] > 0.998) ? 2.5f : 4.0f;              // RadiusByViewingCos, :1653-1660
+        if (bFactor) r *= th;
+        Q.u = proj_xyxr[3 * i]; Q.v = proj_xyxr[3 * i + 1];
+        Q.r = r * scale[level[i]];
+        Q.min_level = level[i] - 1; Q.max_level = level[i];
+        Q.ur = proj_xyxr[3 * i + 2]; Q.er_max = r * scale[level[i]];
+    }
+    WinQuery* dq; uint32_t* list; int* count; int cap;
+    int rc = run_candidates(S, D, hq, qdesc, nq, &dq, &list, &count, &cap);
+    if (rc) return rc;
+    int* d_obs = S.up(observations, (size_t)nq);
+    int* d_assign = S.up(assign_out, (size_t)F->n);
+    int* d_nm = (int*)S.alloc(4);
+    if (!S.ok) return ORBX_E_CUDA;
+    k_resolve_points<<<1, 32>>>(D, nq, dq, list, count, cap, d_obs, d_assign, nnratio, d_nm);
+    CKM(cudaGetLastError());
+    CKM(cudaMemcpy(assign_out, d_assign, sizeof(int) * (size_t)F->n, cudaMemcpyDeviceToHost));
+    CKM(cudaMemcpy(nmatches, d_nm, 4, cudaMemcpyDeviceToHost));
+    return ORBX_OK;
+}
+
+int orbm_search_by_projection_frame(const orbm_frame* cur, int n_last, const orbx_kp* kps_last,
+                                    const uint8_t* last_mp, const uint8_t* last_outlier, const float* last_xyz,
+                                    const uint8_t* last_mp_desc, const int* last_mp_obs,
+                                    const float* Tcw_cur, const float* Tcw_last, const float* K, float bf,
+                                    const float* scale, int nlevels, const int* cur_init_obs, int* assign_out,
+                                    float th, int bMono, int checkOri, int* nmatches, int device)
+{
+    if (!cur || n_last < 0 || !assign_out || !nmatches || !Tcw_cur || !Tcw_last || !K || !scale ||
+        (n_last > 0 && (!kps_last || !last_mp || !last_xyz || !last_mp_desc))) return ORBX_E_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return ORBX_E_CUDA; }
+    *nmatches = 0;
+    const int n_cur = cur->n;
+    std::vector<int> h_obs((size_t)(n_cur > 0 ? n_cur : 1));
+    for (int k = 0; k < n_cur; ++k) { h_obs[(size_t)k] = cur_init_obs ? cur_init_obs[k] : -1; assign_out[k] = (cur_init_obs && cur_init_obs[k] >= 0) ? -2 : -1; }
+    if (n_last == 0 || n_cur == 0) return ORBX_OK;
+    Scratch S;
+    DevFrame D;
+    if (!make_frame(S, cur, &D)) return S.ok ? ORBX_E_ARG : ORBX_E_CUDA;
+    // projection of the last frame's map points with the current pose: the float arithmetic of
+    // cv::gemm for CV_32F (products accumulated left to right, translation added last), :172-208
+    const float fx = K[0], fy = K[1], cx = K[2], cy = K[3];
+    const float mb = bf / fx;
+    float twc[3], tlc[3];
+    for (int i = 0; i < 3; ++i) {
+        float s = (-Tcw_cur[0 * 4 + i]) * Tcw_cur[3];
+        s = s + (-Tcw_cur[1 * 4 + i]) * Tcw_cur[7];
+        s = s + (-Tcw_cur[2 * 4 + i]) * Tcw_cur[11];
+        twc[i] = s;
+    }
+    for (int i = 0; i < 3; ++i) {
+        float s = Tcw_last[4 * i] * twc[0];
+        s = s + Tcw_last[4 * i + 1] * twc[1];
+        s = s + Tcw_last[4 * i + 2] * twc[2];
+        tlc[i] = s + Tcw_last[4 * i + 3];
+    }
+    const bool bForward = tlc[2] > mb && !bMono, bBackward = -tlc[2] > mb && !bMono;
+    std::vector<WinQuery> hq((size_t)n_last);
+    std::vector<float> h_angle((size_t)n_last);
+    std::vector<int> h_lobs((size_t)n_last);
+    for (int i = 0; i < n_last; ++i) {
+        WinQuery& Q = hq[(size_t)i];
+        h_angle[(size_t)i] = kps_last[i].angle;
+        h_lobs[(size_t)i] = last_mp_obs ? last_mp_obs[i] : 1;
+        Q.valid = 0;
+        if (!last_mp[i] || (last_outlier && last_outlier[i])) continue;
+        const float* x = last_xyz + 3 * i;
+        float pc[3];
+        for (int r = 0; r < 3; ++r) {
+            float s = Tcw_cur[4 * r] * x[0];
+            s = s + Tcw_cur[4 * r + 1] * x[1];
+            s = s + Tcw_cur[4 * r + 2] * x[2];
+            pc[r] = s + Tcw_cur[4 * r + 3];
+        }
+        const float invzc = (float)(1.0 / (double)pc[2]);                       // :199
+        if (invzc < 0) continue;
+        const float u = fx * pc[0] * invzc + cx, v = fy * pc[1] * invzc + cy;
+        if (u < cur->min_x || u > cur->max_x) continue;
+        if (v < cur->min_y || v > cur->max_y) continue;
+        const int oct = kps_last[i].octave;
+        if (oct < 0 || oct >= nlevels) continue;
+        Q.valid = 1; Q.u = u; Q.v = v; Q.r = th * scale[oct];
+        if (bForward) { Q.min_level = oct; Q.max_level = -1; }
+        else if (bBackward) { Q.min_level = 0; Q.max_level = oct; }
+        else { Q.min_level = oct - 1; Q.max_level = oct + 1; }
+        Q.ur = u - bf * invzc; Q.er_max = Q.r;                                  // :241-244
+    }
+    WinQuery* dq; uint32_t* list; int* count; int cap;
+    int rc = run_candidates(S, D, hq, last_mp_desc, n_last, &dq, &list, &count, &cap);
+    if (rc) return rc;
+    int* d_lobs = S.up(h_lobs.data(), (size_t)n_last);
+    float* d_angle = S.up(h_angle.data(), (size_t)n_last);
+    int* d_obs = S.up(h_obs.data(), (size_t)n_cur);
+    int* d_assign = S.up(assign_out, (size_t)n_cur);
+    int* d_he = (int*)S.alloc(sizeof(int) * (size_t)n_last);
+    int* d_hb = (int*)S.alloc(sizeof(int) * (size_t)n_last);
+    int* d_nm = (int*)S.alloc(4);
+    if (!S.ok) return ORBX_E_CUDA;
+    k_resolve_frame<<<1, 32>>>(D, n_last, dq, list, count, cap, d_lobs, d_angle, d_obs, d_assign, checkOri, d_he, d_hb, d_nm);
+    CKM(cudaGetLastError());
+    CKM(cudaMemcpy(assign_out, d_assign, sizeof(int) * (size_t)n_cur, cudaMemcpyDeviceToHost));
+    CKM(cudaMemcpy(nmatches, d_nm, 4, cudaMemcpyDeviceToHost));
+    return ORBX_OK;
+}
+
+int orbm_search_for_initialization(const orbm_frame* F1, const orbm_frame* F2, float* prev_matched, int* matches12,
+                                   int windowSize, float nnratio, int checkOri, int* nmatches, int device)
+{
+    if (!F1 || !F2 || !prev_matched || !matches12 || !nmatches || F1->n < 0 || (F1->n > 0 && (!F1->kps || !F1->desc))) return ORBX_E_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return ORBX_E_CUDA; }
+    *nmatches = 0;
+    const int n1 = F1->n, n2 = F2->n;
+    for (int i = 0; i < n1; ++i) matches12[i] = -1;
+    if (n1 == 0 || n2 == 0) return ORBX_OK;
+    Scratch S;
+    DevFrame D2;
+    if (!make_frame(S, F2, &D2)) return S.ok ? ORBX_E_ARG : ORBX_E_CUDA;
+    std::vector<WinQuery> hq((size_t)n1);
+    std::vector<float> h_angle((size_t)n1);
+    for (int i = 0; i < n1; ++i) {
+        WinQuery& Q = hq[(size_t)i];
+        h_angle[(size_t)i] = F1->kps[i].angle;
+        const int level1 = F1->kps[i].octave;
+        Q.valid = !(level1 > 0);                                                // :1075
+        Q.u = prev_matched[2 * i]; Q.v = prev_matched[2 * i + 1]; Q.r = (float)windowSize;
+        Q.min_level = level1; Q.max_level = level1; Q.ur = 0; Q.er_max = 3.0e38f;
+    }
+    DevFrame D2q = D2; D2q.u_right = nullptr;                                   // no right-image test in this matcher
+    WinQuery* dq; uint32_t* list; int* count; int cap;
+    int rc = run_candidates(S, D2q, hq, F1->desc, n1, &dq, &list, &count, &cap);
+    if (rc) return rc;
+    std::vector<int> h_md((size_t)n2, 2147483647), h_m21((size_t)n2, -1);
+    float* d_angle = S.up(h_angle.data(), (size_t)n1);
+    int* d_md = S.up(h_md.data(), (size_t)n2);
+    int* d_m21 = S.up(h_m21.data(), (size_t)n2);
+    int* d_m12 = S.up(matches12, (size_t)n1);
+    float* d_prev = S.up(prev_matched, (size_t)n1 * 2);
+    int* d_he = (int*)S.alloc(sizeof(int) * (size_t)n1);
+    int* d_hb = (int*)S.alloc(sizeof(int) * (size_t)n1);
+    int* d_nm = (int*)S.alloc(4);
+    if (!S.ok) return ORBX_E_CUDA;
+    k_resolve_init<<<1, 32>>>(D2, n1, dq, list, count, cap, d_angle, d_md, d_m21, d_m12, nnratio, checkOri, d_he, d_hb, d_prev, d_nm);
+    CKM(cudaGetLastError());
+    CKM(cudaMemcpy(matches12, d_m12, sizeof(int) * (size_t)n1, cudaMemcpyDeviceToHost));
+    CKM(cudaMemcpy(prev_matched, d_prev, sizeof(float) * (size_t)n1 * 2, cudaMemcpyDeviceToHost));
+    CKM(cudaMemcpy(nmatches, d_nm, 4, cudaMemcpyDeviceToHost));
+    return ORBX_OK;
+}
+
+int orbm_stereo_matches(orbx_ctx* ex_left, int frame_l, orbx_ctx* ex_right, int frame_r,
+                        int nl, const orbx_kp* kps_l, const uint8_t* desc_l,
+                        int nr, const orbx_kp* kps_r, const uint8_t* desc_r,
+                        float bf, float fx, float* u_right, float* depth, int* nmatched)
+{
+    if (!ex_left || !ex_right || nl < 0 || nr < 0 || !u_right || !depth || (nl > 0 && (!kps_l || !desc_l)) || (nr > 0 && (!kps_r || !desc_r)) || nr > 65535)
+        return ORBX_E_ARG;
+    StereoLevels P;
+    int dev_l = 0, dev_r = 0, nlev = 0;
+    if (orb_ctx_levels(ex_left, frame_l, P.l, P.lpitch, P.w, P.h, P.scale, P.inv_scale, &nlev, &dev_l) ||
+        orb_ctx_levels(ex_right, frame_r, P.r, P.rpitch, nullptr, nullptr, nullptr, nullptr, nullptr, &dev_r) || dev_l != dev_r)
+        return ORBX_E_ARG;
+    if (cudaSetDevice(dev_l) != cudaSuccess) { cudaGetLastError(); return ORBX_E_CUDA; }
+    if (nmatched) *nmatched = 0;
+    for (int i = 0; i < nl; ++i) { u_right[i] = -1.0f; depth[i] = -1.0f; }
+    if (nl == 0 || nr == 0) return ORBX_OK;
+    Scratch S;
+    const orbx_kp* dkl = S.up(kps_l, (size_t)nl);
+    const orbx_kp* dkr = S.up(kps_r, (size_t)nr);
+    const uint32_t* ddl = (const uint32_t*)S.up(desc_l, (size_t)nl * 32);
+    const uint32_t* ddr = (const uint32_t*)S.up(desc_r, (size_t)nr * 32);
+    float* du = (float*)S.alloc(sizeof(float) * (size_t)nl);
+    float* dd = (float*)S.alloc(sizeof(float) * (size_t)nl);
+    int* dsad = (int*)S.alloc(sizeof(int) * (size_t)nl);
+    int* dn = (int*)S.alloc(4);
+    if (!S.ok) return ORBX_E_CUDA;
+    const float mb = bf / fx;                                                    // src/Frame.cc:121
+    k_stereo_match<<<(nl + 7) / 8, 256>>>(nl, dkl, ddl, nr, dkr, ddr, P, bf, mb, du, dd, dsad);
+    CKM(cudaGetLastError());
+    k_stereo_cut<<<1, 1024>>>(nl, dsad, du, dd, dn);
+    CKM(cudaGetLastError());
+    CKM(cudaMemcpy(u_right, du, sizeof(float) * (size_t)nl, cudaMemcpyDeviceToHost));
+    CKM(cudaMemcpy(depth, dd, sizeof(float) * (size_t)nl, cudaMemcpyDeviceToHost));
+    int n = 0;
+    CKM(cudaMemcpy(&n, dn, 4, cudaMemcpyDeviceToHost));
+    if (nmatched) *nmatched = n;
+    return ORBX_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,135 @@
+"""GPU matchers through the C ABI against the oracle (and the reference fixtures): brute-force
+Hamming, the three window searches incl. their order-dependent bookkeeping and the rotation
+histogram, and the stereo row matcher.  Match indices and float outputs are bit-exact."""
+import os
+
+import numpy as np
+import pytest
+
+import orb_slam2_chinesenotes_b200 as ob
+from matcher_lib import Matcher, extract_frame, perturbed_frame, projected_queries, two_view_scene
+from oracle_lib import KP_DTYPE, OracleExtractor, oracle
+from synth import stereo_pair
+
+pytestmark = pytest.mark.gpu
+W, H, NF = 1241, 376, 2000
+BOUNDS = (0.0, float(W), 0.0, float(H))
+K = np.float32([718.856, 718.856, 607.1928, 185.2157])
+
+
+@pytest.fixture(scope="module")
+def scene():
+    kps, desc, scale = extract_frame(W, H, NF, 2)
+    k2, d2, perm = perturbed_frame(kps, desc, W, H, 11)
+    return dict(kps=kps, desc=desc, scale=scale, k2=k2, d2=d2)
+
+
+def test_hamming_bf_matches_oracle(scene):
+    O = oracle()
+    q, t = scene["desc"][:700], scene["d2"]
+    bi, bd, bd2 = ob.hamming_bf(q, t)
+    oi, od, od2 = (np.zeros(len(q), np.int32) for _ in range(3))
+    O.orbo_hamming_bf(q.ctypes.data, len(q), t.ctypes.data, len(t), oi.ctypes.data, od.ctypes.data, od2.ctypes.data)
+    assert (bi == oi).all() and (bd == od).all() and (bd2 == od2).all()
+    # edge cases: one train descriptor, duplicates (first wins), DescriptorDistance
+    bi, bd, bd2 = ob.hamming_bf(q[:5], t[:1])
+    assert (bi == 0).all() and (bd2 == 256).all()
+    tt = np.concatenate([t[:10], t[:10]])
+    bi, bd, bd2 = ob.hamming_bf(t[:10], tt)
+    assert (bi == np.arange(10)).all() and (bd == 0).all() and (bd2 == 0).all()
+    assert ob.ORBmatcher.DescriptorDistance(q[0], t[0]) == int(np.unpackbits(q[0] ^ t[0]).sum())
+
+
+def test_hamming_bf_batched_problems(scene):
+    rng = np.random.default_rng(3)
+    q = rng.integers(0, 256, (4, 300, 32), dtype=np.uint8)
+    t = rng.integers(0, 256, (4, 257, 32), dtype=np.uint8)
+    bi, bd, bd2 = ob.hamming_bf(q, t, nprob=4)
+    for p in range(4):
+        d = np.unpackbits(q[p][:, None, :] ^ t[p][None, :, :], axis=2).sum(2)
+        assert (bi[p * 300:(p + 1) * 300] == d.argmin(1)).all() and (bd[p * 300:(p + 1) * 300] == d.min(1)).all()
+
+
+@pytest.mark.parametrize("th,nnratio,with_uright", [(1.0, 0.8, False), (3.0, 0.8, False), (5.0, 0.9, True)])
+def test_search_by_projection_points(scene, th, nnratio, with_uright):
+    O = Matcher("oracle")
+    q = projected_queries(scene["k2"], scene["d2"], 2000, 5)
+    rng = np.random.default_rng(6)
+    n = len(scene["k2"])
+    ur = np.where(rng.random(n) < 0.5, scene["k2"]["x"] - 20 * rng.random(n), -1).astype(np.float32) if with_uright else None
+    init = np.where(rng.random(n) < 0.05, rng.integers(0, 2000, n), -1).astype(np.int32)
+    F = ob.FrameView(scene["k2"], scene["d2"], BOUNDS, ur)
+    M = ob.ORBmatcher(nnratio, True)
+    for ia in (None, init):
+        a = O.search_by_projection_points(scene["k2"], scene["d2"], ur, scene["scale"], BOUNDS, q, th, nnratio, ia)
+        b = M.SearchByProjection(F, scene["scale"], q, th, ia)
+        assert a[0] == b[0] and a[0] > 300
+        assert (a[1] == b[1]).all()
+
+
+@pytest.mark.parametrize("th,mono,check_ori", [(7.0, False, True), (15.0, True, True), (7.0, False, False)])
+def test_search_by_projection_frame(scene, th, mono, check_ori):
+    O = Matcher("oracle")
+    cur, last, Tc, Tl = two_view_scene(scene["kps"], scene["desc"], W, H, 21, K)
+    if mono:
+        cur = dict(cur); cur["u_right"] = None
+    rng = np.random.default_rng(8)
+    init_obs = np.where(rng.random(len(cur["kps"])) < 0.05, rng.integers(0, 2, len(cur["kps"])), -1).astype(np.int32)
+    F = ob.FrameView(cur["kps"], cur["desc"], BOUNDS, cur.get("u_right"))
+    M = ob.ORBmatcher(0.9, check_ori)
+    for io in (None, init_obs):
+        a = O.search_by_projection_frame(cur, last, Tc, Tl, K, 386.1448, scene["scale"], BOUNDS, th, mono, 0.9, check_ori, io)
+        b = M.SearchByProjectionFrame(F, last, Tc, Tl, K, 386.1448, scene["scale"], th, mono, io)
+        assert a[0] == b[0] and a[0] > 200
+        assert (a[1] == b[1]).all()
+
+
+@pytest.mark.parametrize("nnratio,check_ori,window", [(0.9, True, 100), (0.6, True, 50), (0.9, False, 100)])
+def test_search_for_initialization(scene, nnratio, check_ori, window):
+    O = Matcher("oracle")
+    prev = np.stack([scene["kps"]["x"], scene["kps"]["y"]], 1)
+    a = O.search_for_initialization(scene["kps"], scene["desc"], scene["k2"], scene["d2"], scene["scale"], BOUNDS, prev, window, nnratio, check_ori)
+    F1 = ob.FrameView(scene["kps"], scene["desc"], BOUNDS)
+    F2 = ob.FrameView(scene["k2"], scene["d2"], BOUNDS)
+    b = ob.ORBmatcher(nnratio, check_ori).SearchForInitialization(F1, F2, prev, window)
+    assert a[0] == b[0] and a[0] > 50
+    assert (a[1] == b[1]).all() and (a[2] == b[2]).all()
+
+
+def test_empty_and_degenerate_inputs(scene):
+    M = ob.ORBmatcher(0.9, True)
+    F0 = ob.FrameView(np.zeros(0, KP_DTYPE), np.zeros((0, 32), np.uint8), BOUNDS)
+    F2 = ob.FrameView(scene["k2"], scene["d2"], BOUNDS)
+    assert M.SearchForInitialization(F0, F2, np.zeros((0, 2), np.float32), 100)[0] == 0
+    n, m12, _ = M.SearchForInitialization(F2, F0, np.zeros((len(scene["k2"]), 2), np.float32), 100)
+    assert n == 0 and (m12 == -1).all()
+    q = projected_queries(scene["k2"], scene["d2"], 50, 5)
+    q["in_view"][:] = 0                                   # nothing in view: no matches, nothing attached
+    n, a = M.SearchByProjection(F2, scene["scale"], q, 3.0)
+    assert n == 0 and (a == -1).all()
+
+
+def test_stereo_pair_end_to_end():
+    """BASELINE.json configs[1]: KITTI-shape stereo pair, 2000 features per image, left/right extraction
+    + stereo row matching; everything against the oracle (which equals the reference's stereo Frame)."""
+    left, right = stereo_pair(W, H, 2)
+    GL, GR = ob.ORBextractor(NF, 1.2, 8, 20, 7), ob.ORBextractor(NF, 1.2, 8, 20, 7)
+    kl, dl = GL(left)
+    kr, dr = GR(right)
+    OL, OR = OracleExtractor(NF), OracleExtractor(NF)
+    nl, okl, odl = OL.extract(left)
+    nr, okr, odr = OR.extract(right)
+    assert nl == len(kl) and nr == len(kr) and (dl == odl).all() and (dr == odr).all()
+    bf, fx = 386.1448, float(K[0])
+    ur, dep, nm = ob.stereo_matches(GL, GR, kl, dl, kr, dr, bf, fx)
+    our, odep = np.zeros(nl, np.float32), np.zeros(nl, np.float32)
+    import ctypes as C
+    O = oracle()
+    O.orbo_stereo_matches.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                      C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+    nd = O.orbo_stereo_matches(OL.h, OR.h, nl, okl.ctypes.data, odl.ctypes.data, nr, okr.ctypes.data, odr.ctypes.data, bf, fx,
+                               our.ctypes.data, odep.ctypes.data)
+    assert nm == nd and nd > 200
+    assert (ur.view(np.uint32) == our.view(np.uint32)).all() and (dep.view(np.uint32) == odep.view(np.uint32)).all()
+    for x in (GL, GR, OL, OR):
+        x.close()
