@@ -1,0 +1,176 @@
+// ORBmatcher_b200.hpp -- host forwarders for the Hamming searches of ORB_SLAM2::ORBmatcher.
+//
+// ORBmatcher's window searches take the SLAM system's own Frame / MapPoint objects, so they cannot be
+// replaced by a standalone class.  Instead the bodies of the reference's methods become one-line calls
+// into these templates (INTEGRATION.md shows the patch), which flatten the objects into the plain arrays
+// of the C ABI (include/orb_b200.h), run the search on the GPU and write the results back:
+//
+//   int ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint*> &vpMapPoints, const float th)
+//   { return b200::SearchByProjection(F, vpMapPoints, th, mfNNratio); }                 // src/ORBmatcher.cc:73
+//   int ORBmatcher::SearchByProjection(Frame &Cur, const Frame &Last, const float th, const bool bMono)
+//   { return b200::SearchByProjection(Cur, Last, th, bMono, mbCheckOrientation); }      // src/ORBmatcher.cc:160
+//   int ORBmatcher::SearchForInitialization(Frame &F1, Frame &F2, vector<cv::Point2f> &vbPrevMatched,
+//                                           vector<int> &vnMatches12, int windowSize)
+//   { return b200::SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize, mfNNratio,
+//                                          mbCheckOrientation); }                       // src/ORBmatcher.cc:1055
+//   int ORBmatcher::DescriptorDistance(const cv::Mat &a, const cv::Mat &b)   stays on the CPU for single
+//   pairs (a 32-byte popcount); batches go through orbm_hamming_bf.
+//
+// The templates only use the members the reference's own code uses (listed per function), so they
+// compile against the unmodified include/Frame.h and include/MapPoint.h.
+#ifndef ORBMATCHER_B200_HPP
+#define ORBMATCHER_B200_HPP
+
+#include <cstring>
+#include <map>
+#include <stdexcept>
+#include <vector>
+
+#include "orb_b200.h"
+
+namespace ORB_SLAM2 { namespace b200 {
+
+inline int& Device() { static int d = 0; return d; }
+
+template <class KeyPointT>
+inline void FlattenKeys(const std::vector<KeyPointT>& keys, std::vector<orbx_kp>& out)
+{
+    out.resize(keys.size());
+    for (size_t i = 0; i < keys.size(); ++i) {
+        orbx_kp k = { keys[i].pt.x, keys[i].pt.y, keys[i].size, keys[i].angle, keys[i].response, keys[i].octave, keys[i].class_id };
+        out[i] = k;
+    }
+}
+
+template <class MatT>
+inline void FlattenDescriptors(const MatT& m, int n, std::vector<unsigned char>& out)
+{
+    out.resize((size_t)(n > 0 ? n : 1) * 32);
+    for (int i = 0; i < n; ++i) std::memcpy(&out[(size_t)i * 32], m.ptr(i), 32);
+}
+
+template <class FrameT>
+inline orbm_frame View(const FrameT& F, const std::vector<orbx_kp>& kps, const std::vector<unsigned char>& desc, bool withRight)
+{
+    orbm_frame v;
+    v.n = (int)kps.size();
+    v.kps = kps.empty() ? 0 : &kps[0];
+    v.desc = &desc[0];
+    v.u_right = (withRight && !F.mvuRight.empty()) ? &F.mvuRight[0] : 0;
+    v.min_x = FrameT::mnMinX; v.max_x = FrameT::mnMaxX; v.min_y = FrameT::mnMinY; v.max_y = FrameT::mnMaxY;
+    return v;
+}
+
+inline void Check(int rc, const char* what)
+{
+    if (rc != ORBX_OK) throw std::runtime_error(std::string(what) + " failed (B200 matcher, no CPU fallback)");
+}
+
+// ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th), src/ORBmatcher.cc:73-157.
+// Reads: F.mvKeysUn, F.mDescriptors, F.mvuRight, F.mvScaleFactors, F.mvpMapPoints, Frame::mnMin/Max*;
+// MapPoint::mbTrackInView, isBad(), mnTrackScaleLevel, mTrackViewCos, mTrackProjX/Y/XR, Observations(), GetDescriptor().
+template <class FrameT, class MapPointT>
+int SearchByProjection(FrameT& F, const std::vector<MapPointT*>& vpMapPoints, const float th, const float nnratio)
+{
+    std::vector<orbx_kp> kps; FlattenKeys(F.mvKeysUn, kps);
+    std::vector<unsigned char> desc; FlattenDescriptors(F.mDescriptors, (int)kps.size(), desc);
+    const orbm_frame view = View(F, kps, desc, true);
+    // map points already attached to the frame but not in the list still block their keypoint when
+    // Observations()>0 (:115-117): they ride along as extra, never-queried entries
+    std::vector<MapPointT*> pts(vpMapPoints.begin(), vpMapPoints.end());
+    std::map<MapPointT*, int> index;
+    for (size_t i = 0; i < pts.size(); ++i) index.insert(std::make_pair(pts[i], (int)i));
+    const int nq = (int)pts.size();
+    std::vector<int> init(kps.size(), -1);
+    for (size_t k = 0; k < kps.size(); ++k) {
+        MapPointT* p = F.mvpMapPoints[k];
+        if (!p) continue;
+        typename std::map<MapPointT*, int>::iterator it = index.find(p);
+        if (it == index.end()) { it = index.insert(std::make_pair(p, (int)pts.size())).first; pts.push_back(p); }
+        init[k] = it->second;
+    }
+    const size_t n = pts.size();
+    std::vector<float> proj(3 * n, 0.f), viewCos(n, 0.f);
+    std::vector<int> level(n, 0), obs(n, 0);
+    std::vector<unsigned char> inView(n, 0), bad(n, 0), qdesc(32 * (n ? n : 1), 0);
+    for (size_t i = 0; i < n; ++i) {
+        MapPointT* p = pts[i];
+        obs[i] = p->Observations();
+        if ((int)i >= nq) continue;                       // ride-along entry: only its Observations() matter
+        inView[i] = p->mbTrackInView ? 1 : 0;
+        bad[i] = p->isBad() ? 1 : 0;
+        level[i] = p->mnTrackScaleLevel; viewCos[i] = p->mTrackViewCos;
+        proj[3 * i] = p->mTrackProjX; proj[3 * i + 1] = p->mTrackProjY; proj[3 * i + 2] = p->mTrackProjXR;
+        if (inView[i] && !bad[i]) std::memcpy(&qdesc[32 * i], p->GetDescriptor().ptr(0), 32);
+    }
+    std::vector<int> assign(kps.size(), -1);
+    int nmatches = 0;
+    Check(orbm_search_by_projection_points(&view, &F.mvScaleFactors[0], (int)F.mvScaleFactors.size(), (int)n, &proj[0], &level[0], &viewCos[0],
+                                           &inView[0], &bad[0], &obs[0], &qdesc[0], &init[0], kps.empty() ? 0 : &assign[0], th, nnratio,
+                                           &nmatches, Device()), "orbm_search_by_projection_points");
+    for (size_t k = 0; k < kps.size(); ++k) if (assign[k] >= 0) F.mvpMapPoints[k] = pts[(size_t)assign[k]];
+    return nmatches;
+}
+
+// ORBmatcher::SearchByProjection(Frame& cur, const Frame& last, th, bMono), src/ORBmatcher.cc:160-300.
+// Reads: cur.mvKeysUn, mDescriptors, mvuRight, mvScaleFactors, mvpMapPoints, mTcw, mbf, Frame::fx/fy/cx/cy/mnMin/Max*;
+// last.N, mvKeys, mvKeysUn, mvpMapPoints, mvbOutlier, mTcw; MapPoint::GetWorldPos(), GetDescriptor(), Observations().
+template <class FrameT>
+int SearchByProjection(FrameT& Cur, const FrameT& Last, const float th, const bool bMono, const bool checkOri)
+{
+    std::vector<orbx_kp> kps; FlattenKeys(Cur.mvKeysUn, kps);
+    std::vector<unsigned char> desc; FlattenDescriptors(Cur.mDescriptors, (int)kps.size(), desc);
+    const orbm_frame view = View(Cur, kps, desc, true);
+    const int nl = Last.N;
+    std::vector<orbx_kp> lk; FlattenKeys(Last.mvKeysUn, lk);
+    for (int i = 0; i < nl; ++i) lk[(size_t)i].octave = Last.mvKeys[(size_t)i].octave;   // :211 uses mvKeys for the octave
+    std::vector<unsigned char> hasMp((size_t)(nl ? nl : 1), 0), outlier((size_t)(nl ? nl : 1), 0), mdesc((size_t)(nl ? nl : 1) * 32, 0);
+    std::vector<float> xyz((size_t)(nl ? nl : 1) * 3, 0.f);
+    std::vector<int> mobs((size_t)(nl ? nl : 1), 0);
+    for (int i = 0; i < nl; ++i) {
+        if (!Last.mvpMapPoints[(size_t)i]) continue;
+        hasMp[(size_t)i] = 1; outlier[(size_t)i] = Last.mvbOutlier[(size_t)i] ? 1 : 0;
+        const cv::Mat x = Last.mvpMapPoints[(size_t)i]->GetWorldPos();
+        for (int r = 0; r < 3; ++r) xyz[(size_t)(3 * i + r)] = x.template at<float>(r);
+        std::memcpy(&mdesc[(size_t)i * 32], Last.mvpMapPoints[(size_t)i]->GetDescriptor().ptr(0), 32);
+        mobs[(size_t)i] = Last.mvpMapPoints[(size_t)i]->Observations();
+    }
+    float Tc[16], Tl[16];
+    for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) { Tc[4 * r + c] = Cur.mTcw.template at<float>(r, c); Tl[4 * r + c] = Last.mTcw.template at<float>(r, c); }
+    const float K[4] = { FrameT::fx, FrameT::fy, FrameT::cx, FrameT::cy };
+    std::vector<int> initObs(kps.size(), -1), assign(kps.size(), -1);
+    for (size_t k = 0; k < kps.size(); ++k) if (Cur.mvpMapPoints[k]) initObs[k] = Cur.mvpMapPoints[k]->Observations();
+    int nmatches = 0;
+    Check(orbm_search_by_projection_frame(&view, nl, lk.empty() ? 0 : &lk[0], &hasMp[0], &outlier[0], &xyz[0], &mdesc[0], &mobs[0], Tc, Tl, K, Cur.mbf,
+                                          &Cur.mvScaleFactors[0], (int)Cur.mvScaleFactors.size(), kps.empty() ? 0 : &initObs[0],
+                                          kps.empty() ? 0 : &assign[0], th, bMono ? 1 : 0, checkOri ? 1 : 0, &nmatches, Device()),
+          "orbm_search_by_projection_frame");
+    for (size_t k = 0; k < kps.size(); ++k) {
+        if (assign[k] >= 0) Cur.mvpMapPoints[k] = Last.mvpMapPoints[(size_t)assign[k]];
+        else if (assign[k] == -1) Cur.mvpMapPoints[k] = 0;
+    }
+    return nmatches;
+}
+
+// ORBmatcher::SearchForInitialization, src/ORBmatcher.cc:1055-1180.
+template <class FrameT, class Point2fT>
+int SearchForInitialization(FrameT& F1, FrameT& F2, std::vector<Point2fT>& vbPrevMatched, std::vector<int>& vnMatches12,
+                            int windowSize, const float nnratio, const bool checkOri)
+{
+    std::vector<orbx_kp> k1, k2; FlattenKeys(F1.mvKeysUn, k1); FlattenKeys(F2.mvKeysUn, k2);
+    std::vector<unsigned char> d1, d2; FlattenDescriptors(F1.mDescriptors, (int)k1.size(), d1); FlattenDescriptors(F2.mDescriptors, (int)k2.size(), d2);
+    const orbm_frame v1 = View(F1, k1, d1, false), v2 = View(F2, k2, d2, false);
+    std::vector<float> prev(2 * (k1.size() ? k1.size() : 1), 0.f);
+    for (size_t i = 0; i < k1.size(); ++i) { prev[2 * i] = vbPrevMatched[i].x; prev[2 * i + 1] = vbPrevMatched[i].y; }
+    vnMatches12.assign(k1.size(), -1);
+    int nmatches = 0;
+    std::vector<int> m12(k1.size() ? k1.size() : 1, -1);
+    Check(orbm_search_for_initialization(&v1, &v2, &prev[0], &m12[0], windowSize, nnratio, checkOri ? 1 : 0, &nmatches, Device()),
+          "orbm_search_for_initialization");
+    for (size_t i = 0; i < k1.size(); ++i) { vnMatches12[i] = m12[i]; vbPrevMatched[i].x = prev[2 * i]; vbPrevMatched[i].y = prev[2 * i + 1]; }
+    return nmatches;
+}
+
+}} // namespace ORB_SLAM2::b200
+
+#endif

@@ -1,0 +1,44 @@
+// tests/cpp/matcher_compile_test.cc -- instantiates the ORBmatcher forwarders
+// (host/ORBmatcher_b200.hpp) against Frame / MapPoint types that expose the same members as the
+// reference's classes, and exposes them to pytest.  Where /root/reference exists the Makefile target
+// `matcher_ref` compiles the same header against the reference's REAL include/Frame.h instead.
+#ifdef WITH_REFERENCE_HEADERS
+#include "Frame.h"
+typedef ORB_SLAM2::Frame FrameT;
+typedef ORB_SLAM2::MapPoint MapPointT;
+#else
+#include "cvshim.hpp"
+#include <vector>
+struct MapPointT {
+    bool mbTrackInView, bad; int mnTrackScaleLevel, nObs; float mTrackViewCos, mTrackProjX, mTrackProjY, mTrackProjXR;
+    cv::Mat descriptor, pos;
+    bool isBad() { return bad; }
+    int Observations() { return nObs; }
+    cv::Mat GetDescriptor() { return descriptor.clone(); }
+    cv::Mat GetWorldPos() { return pos.clone(); }
+};
+struct FrameT {
+    int N; float mbf, mb;
+    std::vector<cv::KeyPoint> mvKeys, mvKeysUn;
+    std::vector<float> mvuRight, mvScaleFactors;
+    cv::Mat mDescriptors, mTcw;
+    std::vector<MapPointT*> mvpMapPoints;
+    std::vector<bool> mvbOutlier;
+    static float fx, fy, cx, cy, mnMinX, mnMaxX, mnMinY, mnMaxY;
+};
+float FrameT::fx, FrameT::fy, FrameT::cx, FrameT::cy, FrameT::mnMinX, FrameT::mnMaxX, FrameT::mnMinY, FrameT::mnMaxY;
+#endif
+#include "ORBmatcher_b200.hpp"
+
+extern "C" int matcher_forwarders_instantiate(int run)
+{
+    if (!run) return 0;   // instantiation is the test; running needs a GPU and populated frames
+    FrameT a, b;
+    std::vector<MapPointT*> pts;
+    std::vector<cv::Point2f> prev;
+    std::vector<int> m12;
+    int n = ORB_SLAM2::b200::SearchByProjection(a, pts, 3.0f, 0.8f);
+    n += ORB_SLAM2::b200::SearchByProjection(a, b, 7.0f, false, true);
+    n += ORB_SLAM2::b200::SearchForInitialization(a, b, prev, m12, 100, 0.9f, true);
+    return n;
+}
