@@ -52,7 +52,47 @@ def extractor():
         R.close()
 
 
+def matchers():
+    """Outputs of the reference's unmodified ORBmatcher.cc / Frame.cc on the deterministic scenes of
+    tests/matcher_lib.py (inputs are regenerated from seeds; only results are stored)."""
+    import ctypes as C
+    from matcher_lib import Matcher, extract_frame, perturbed_frame, projected_queries, two_view_scene
+    from oracle_lib import KP_DTYPE, ref
+    from synth import stereo_pair
+    W, H, NF = 1241, 376, 2000
+    B = (0.0, float(W), 0.0, float(H))
+    K = np.float32([718.856, 718.856, 607.1928, 185.2157])
+    kps, desc, scale = extract_frame(W, H, NF, 2)
+    k2, d2, _ = perturbed_frame(kps, desc, W, H, 11)
+    R = Matcher("ref")
+    out = {}
+    prev = np.stack([kps["x"], kps["y"]], 1)
+    n, m12, pv = R.search_for_initialization(kps, desc, k2, d2, scale, B, prev, 100, 0.9, True)
+    out.update(init_n=n, init_m12=m12, init_prev=pv)
+    q = projected_queries(k2, d2, 2000, 5)
+    for th in (1.0, 3.0):
+        n, a = R.search_by_projection_points(k2, d2, None, scale, B, q, th, 0.8, None)
+        out[f"points_th{int(th)}_n"] = n; out[f"points_th{int(th)}_assign"] = a
+    cur, last, Tc, Tl = two_view_scene(kps, desc, W, H, 21, K)
+    n, a = R.search_by_projection_frame(cur, last, Tc, Tl, K, 386.1448, scale, B, 7.0, False, 0.9, True, None)
+    out.update(frame_n=n, frame_assign=a)
+    left, right = stereo_pair(W, H, 2)
+    L = ref()
+    cap = 2 * NF
+    kl, kr = np.zeros(cap, KP_DTYPE), np.zeros(cap, KP_DTYPE)
+    dl, dr = np.zeros((cap, 32), np.uint8), np.zeros((cap, 32), np.uint8)
+    ur, dep, nr = np.zeros(cap, np.float32), np.zeros(cap, np.float32), C.c_int()
+    vp, ci, cf = C.c_void_p, C.c_int, C.c_float
+    L.orbref_stereo_frame.argtypes = [vp, vp, ci, ci, ci, cf, ci, ci, ci, cf, cf, cf, cf, cf, cf, vp, vp, ci, vp, vp, ci, C.POINTER(ci), vp, vp]
+    n = L.orbref_stereo_frame(left.ctypes.data, right.ctypes.data, W, H, NF, 1.2, 8, 20, 7, float(K[0]), float(K[1]), float(K[2]), float(K[3]),
+                              386.1448, 35.0, kl.ctypes.data, dl.ctypes.data, cap, kr.ctypes.data, dr.ctypes.data, cap, C.byref(nr),
+                              ur.ctypes.data, dep.ctypes.data)
+    out.update(stereo_n=n, stereo_nr=nr.value, stereo_uright=ur[:n], stereo_depth=dep[:n])
+    np.savez_compressed(os.path.join(HERE, "ref_match_kitti.npz"), **out)
+
+
 if __name__ == "__main__":
     primitives()
     extractor()
+    matchers()
     print("golden fixtures written to", HERE)

@@ -119,3 +119,35 @@ def test_stereo_frame_vs_oracle():
     assert (our.view(np.uint32) == ur[:n].view(np.uint32)).all() and (odep.view(np.uint32) == dep[:n].view(np.uint32)).all()
     assert (ur[:n] >= 0).sum() > 200
     OL.close(); OR.close()
+
+
+def test_oracle_vs_matcher_fixtures(scene):
+    """Always runs: results stored from the reference's unmodified ORBmatcher.cc / Frame.cc
+    (tests/golden/make_golden.py) against the C restatement."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_match_kitti.npz"))
+    O = Matcher("oracle")
+    prev = np.stack([scene["kps"]["x"], scene["kps"]["y"]], 1)
+    n, m12, pv = O.search_for_initialization(scene["kps"], scene["desc"], scene["k2"], scene["d2"], scene["scale"], BOUNDS, prev, 100, 0.9, True)
+    assert n == int(g["init_n"]) and (m12 == g["init_m12"]).all() and (pv == g["init_prev"]).all()
+    q = projected_queries(scene["k2"], scene["d2"], 2000, 5)
+    for th in (1.0, 3.0):
+        n, a = O.search_by_projection_points(scene["k2"], scene["d2"], None, scene["scale"], BOUNDS, q, th, 0.8, None)
+        assert n == int(g[f"points_th{int(th)}_n"]) and (a == g[f"points_th{int(th)}_assign"]).all()
+    cur, last, Tc, Tl = two_view_scene(scene["kps"], scene["desc"], W, H, 21, K)
+    n, a = O.search_by_projection_frame(cur, last, Tc, Tl, K, 386.1448, scene["scale"], BOUNDS, 7.0, False, 0.9, True, None)
+    assert n == int(g["frame_n"]) and (a == g["frame_assign"]).all()
+    left, right = stereo_pair(W, H, 2)
+    OL, OR = OracleExtractor(NF), OracleExtractor(NF)
+    nl, okl, odl = OL.extract(left)
+    nr, okr, odr = OR.extract(right)
+    assert nl == int(g["stereo_n"]) and nr == int(g["stereo_nr"])
+    our, odep = np.zeros(nl, np.float32), np.zeros(nl, np.float32)
+    Lo = oracle()
+    vp, ci, cf = C.c_void_p, C.c_int, C.c_float
+    Lo.orbo_stereo_matches.argtypes = [vp, vp, ci, vp, vp, ci, vp, vp, cf, cf, vp, vp]
+    Lo.orbo_stereo_matches(OL.h, OR.h, nl, okl.ctypes.data, odl.ctypes.data, nr, okr.ctypes.data, odr.ctypes.data, 386.1448, float(K[0]),
+                           our.ctypes.data, odep.ctypes.data)
+    assert (our.view(np.uint32) == g["stereo_uright"].view(np.uint32)).all()
+    assert (odep.view(np.uint32) == g["stereo_depth"].view(np.uint32)).all()
+    OL.close(); OR.close()
