@@ -174,6 +174,38 @@ def run_reference(args, rank, world):
     }))
 
 
+def bench_hamming(dev, device_index, nq=2000, nt=2000, nprob=256, reps=5):
+    """Second half of the BASELINE metric: brute-force Hamming matching in Gpairs/s (BASELINE.json configs[3]
+    shape, 2000 query x 2000 frame descriptors, 256 independent problems per launch, device resident).
+    Bound: integer pipe, 8 POPC per pair at 16 POPC/clk/SM (tools/ubench_pipes.cu measures that rate)."""
+    import torch
+    import orb_slam2_chinesenotes_b200 as ob
+    g = torch.Generator(device=dev).manual_seed(7)
+    q = torch.randint(0, 256, (nprob, nq, 32), generator=g, device=dev, dtype=torch.uint8)
+    t = torch.randint(0, 256, (nprob, nt, 32), generator=g, device=dev, dtype=torch.uint8)
+    outs = [torch.zeros(nprob * nq, dtype=torch.int32, device=dev) for _ in range(3)]
+    L = ob.lib()
+
+    def run():
+        rc = L.orbm_hamming_bf(q.data_ptr(), nq, t.data_ptr(), nt, nprob, outs[0].data_ptr(), outs[1].data_ptr(), outs[2].data_ptr(), device_index)
+        assert rc == 0
+
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        run()                                      # the call synchronises the device itself
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / reps
+    props = torch.cuda.get_device_properties(dev)
+    peak = props.multi_processor_count * 16 * 1.965e9 / 8 / 1e9
+    gp = nprob * nq * nt / dt / 1e9
+    return {"value": gp, "unit": "Gpairs/s", "nq": nq, "nt": nt, "problems_per_launch": nprob, "ms_per_launch": dt * 1e3,
+            "bound": "integer pipe (POPC)", "peak": peak, "frac": gp / peak,
+            "peak_note": "SMs x 16 POPC/clk x 1965 MHz / 8 POPC per pair"}
+
+
 # ------------------------------------------------------------------------------------------ our arm
 def run_ours(args, rank, world, local_rank):
     import torch
@@ -298,7 +330,9 @@ def run_ours(args, rank, world, local_rank):
         v, kind, _ = cpu_frames_per_s(sample, nf, cores)
         cpu = {"value": v, "unit": "frames/s", "cores": cores, "kind": kind,
                "sample": f"first {ns} frames of the step's batch, {cores} threads, one extractor per thread"}
-    chunks = (batch + (args.chunk or 32) - 1) // (args.chunk or 32)
+    chunk = args.chunk or 128                      # orbx_set_chunk default (orb_capi.cu)
+    chunks = (batch + chunk - 1) // chunk
+    hamming = bench_hamming(dev, local_rank) if world == 1 else None
     print(json.dumps({
         "metric": "orb_extract_frames_per_s", "value": value, "unit": "frames/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps,
@@ -309,7 +343,7 @@ def run_ours(args, rank, world, local_rank):
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": batch * w * h,
                 "d2h_bytes_per_step": batch * (cap * 60 + 4), "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": (LEVELS - 1 + 4) * chunks * args.steps,
-        "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
+        "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "hamming_bf": hamming,
     }))
     if dist is not None:
         dist.destroy_process_group()
