@@ -133,14 +133,23 @@ __global__ void __launch_bounds__(BLUR_NT) k_blur7(const __grid_constant__ OrbPl
     const uint8_t* src = orb_level_ptr(plan, io, frame, l, &pitch);
     const int w = L.w, h = L.h;
 
-    {   // stage: lane = word column (pixels x .. x+3), warps walk down the rows
+    {   // stage: lane = word column (pixels x .. x+3), warps walk down the rows.  Columns / rows more than
+        // 3 px outside the image only feed outputs that are never stored, so indices are clamped to
+        // [-3, n+2] first and ONE reflection is enough (n >= 4 always holds here).
         const int x = tx0 - 4 + 4 * lane;
         const bool fast = x >= 0 && x + 7 < w;
         int xr[4];
 #pragma unroll
-        for (int b = 0; b < 4; ++b) xr[b] = orb_refl101(x + b, w);
+        for (int b = 0; b < 4; ++b) {
+            int i = min(max(x + b, -3), w + 2);
+            i = i < 0 ? -i : i;
+            xr[b] = i >= w ? 2 * (w - 1) - i : i;
+        }
         for (int r = warp; r < ORB_BLUR_TH + 6; r += BLUR_NT / 32) {
-            const uint8_t* row = src + (size_t)orb_refl101(ty0 - 3 + r, h) * pitch;
+            int y = min(max(ty0 - 3 + r, -3), h + 2);
+            y = y < 0 ? -y : y;
+            y = y >= h ? 2 * (h - 1) - y : y;
+            const uint8_t* row = src + (size_t)y * pitch;
             uint32_t v;
             if (fast) v = orb_ld_u32_unaligned(row + x);
             else v = (uint32_t)__ldg(row + xr[0]) | ((uint32_t)__ldg(row + xr[1]) << 8) | ((uint32_t)__ldg(row + xr[2]) << 16) | ((uint32_t)__ldg(row + xr[3]) << 24);
@@ -167,22 +176,24 @@ __global__ void __launch_bounds__(BLUR_NT) k_blur7(const __grid_constant__ OrbPl
     __syncthreads();
     // row pass: group g = output pixels tx0+4g .. +3 = staged columns 4g+4 .. 4g+7; window = columns 4g+1 .. 4g+10
     uint8_t* dst = io.blur + (size_t)frame * plan.blur_bytes + L.blur_off;
-    constexpr int NG = ORB_BLUR_TW / 4;
-    for (int u = tid; u < NG * ORB_BLUR_TH; u += BLUR_NT) {
-        const int r = u / NG, g = u - r * NG;
-        const int y = ty0 + r, x = tx0 + 4 * g;
-        if (y >= h || x >= L.pitch) continue;
-        const uint2* pv = (const uint2*)&s_v[r * (2 * BLUR_IW) + 2 * g];
-        const uint2 q0 = pv[0], q1 = pv[1], q2 = pv[2];
-        uint32_t v[12];
-        v[0] = q0.x & 0xffffu; v[1] = q0.x >> 16; v[2] = q0.y & 0xffffu; v[3] = q0.y >> 16;
-        v[4] = q1.x & 0xffffu; v[5] = q1.x >> 16; v[6] = q1.y & 0xffffu; v[7] = q1.y >> 16;
-        v[8] = q2.x & 0xffffu; v[9] = q2.x >> 16; v[10] = q2.y & 0xffffu; v[11] = q2.y >> 16;
-        uint32_t o[4];
+    // lane = group (30 of 32 lanes busy), warps walk down the rows: no division, addresses advance by a pitch
+    if (lane < ORB_BLUR_TW / 4 && tx0 + 4 * lane < L.pitch) {
+        const int g = lane;
+        uint8_t* out = dst + (size_t)(ty0 + warp) * L.pitch + tx0 + 4 * g;
+        const int rmax = min(ORB_BLUR_TH, h - ty0);
+        for (int r = warp; r < rmax; r += BLUR_NT / 32, out += (size_t)(BLUR_NT / 32) * L.pitch) {
+            const uint2* pv = (const uint2*)&s_v[r * (2 * BLUR_IW) + 2 * g];
+            const uint2 q0 = pv[0], q1 = pv[1], q2 = pv[2];
+            uint32_t v[12];
+            v[0] = q0.x & 0xffffu; v[1] = q0.x >> 16; v[2] = q0.y & 0xffffu; v[3] = q0.y >> 16;
+            v[4] = q1.x & 0xffffu; v[5] = q1.x >> 16; v[6] = q1.y & 0xffffu; v[7] = q1.y >> 16;
+            v[8] = q2.x & 0xffffu; v[9] = q2.x >> 16; v[10] = q2.y & 0xffffu; v[11] = q2.y >> 16;
+            uint32_t o[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-            o[j] = (18u * (v[j + 1] + v[j + 7]) + 34u * (v[j + 2] + v[j + 6]) + 48u * (v[j + 3] + v[j + 5]) + 56u * v[j + 4] + 32768u) >> 16;
-        *(uint32_t*)(dst + (size_t)y * L.pitch + x) = o[0] | (o[1] << 8) | (o[2] << 16) | (o[3] << 24);
+            for (int j = 0; j < 4; ++j)
+                o[j] = (18u * (v[j + 1] + v[j + 7]) + 34u * (v[j + 2] + v[j + 6]) + 48u * (v[j + 3] + v[j + 5]) + 56u * v[j + 4] + 32768u) >> 16;
+            *(uint32_t*)out = o[0] | (o[1] << 8) | (o[2] << 16) | (o[3] << 24);
+        }
     }
 }
 
