@@ -162,6 +162,20 @@ int orbm_search_by_projection_frame(const orbm_frame* cur, int n_last, const orb
                                     const float* scale, int nlevels, const int* cur_init_obs, int* assign_out,
                                     float th, int bMono, int checkOri, int* nmatches, int device);
 
+/* The "best candidate only" window search that the projection overloads share once the caller has
+ * projected its points (src/ORBmatcher.cc:160-300 motion model, :303-431 relocalisation, :434-549 loop
+ * closing): per query i in order, the candidates of Frame::GetFeaturesInArea(u, v, radius, min_level,
+ * max_level) (uvr = 3 floats per query) that are still free -- a keypoint is taken while the point attached
+ * to it has Observations() > 0 (init_obs [F->n]: -1 free, else Observations() of the attached point; q_obs
+ * [nq]: Observations() of the queries' points, NULL = 1) -- and, if ur != NULL, pass |ur[i] - mvuRight[k]| <=
+ * er_max[i] when mvuRight[k] > 0; smallest distance wins (first on ties), accepted when <= th_accept
+ * (TH_HIGH, ORBdist or TH_LOW in the reference).  check_ori applies the rotation histogram with q_angle.
+ * assign_out [F->n]: query index attached to each keypoint, -2 kept pre-attached point, -1 none. */
+int orbm_window_search_best(const orbm_frame* F, int nq, const float* uvr, const int* min_level, const int* max_level,
+                            const float* ur, const float* er_max, const uint8_t* valid, const uint8_t* qdesc,
+                            const float* q_angle, const int* q_obs, const int* init_obs, int* assign_out,
+                            int th_accept, int check_ori, int* nmatches, int device);
+
 /* ORBmatcher::SearchForInitialization, src/ORBmatcher.cc:1055-1180.  prev_matched [F1.n][2] is
  * vbPrevMatched (updated in place), matches12 [F1.n] receives vnMatches12. */
 int orbm_search_for_initialization(const orbm_frame* F1, const orbm_frame* F2, float* prev_matched, int* matches12,

@@ -56,8 +56,8 @@ public:
     cv::Mat GetDescriptor() { return descriptor.clone(); }
     cv::Mat GetWorldPos() { return worldPos.clone(); }
     cv::Mat GetNormal() { return normal.clone(); }
-    float GetMaxDistanceInvariance() { return 1.2f * maxDist; }
-    float GetMinDistanceInvariance() { return 0.8f * minDist; }
+    float GetMaxDistanceInvariance() { return maxDist; }   // the harness stores the invariance bounds directly
+    float GetMinDistanceInvariance() { return minDist; }
     int PredictScale(const float&, KeyFrame*) { return mnTrackScaleLevel; }
     int PredictScale(const float&, Frame*) { return mnTrackScaleLevel; }
     int GetIndexInKeyFrame(KeyFrame*) { return -1; }

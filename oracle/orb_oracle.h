@@ -95,6 +95,23 @@ int orbo_search_by_projection_frame(int n_cur, const orbo_kp* kps_cur, const uin
                                     const float* scale, float minX, float maxX, float minY, float maxY,
                                     const int* cur_init_obs, int* assign_out, float th, int bMono, float nnratio, int checkOri);
 
+/* best-candidate-only window search with caller-side projection, and the relocalisation overload
+ * (src/ORBmatcher.cc:303-431) built on it: orb_window_oracle.c */
+int orbo_window_search_best(int n, const orbo_kp* kps, const uint8_t* desc, const float* u_right,
+                            float minX, float maxX, float minY, float maxY,
+                            int nq, const float* uvr, const int* min_level, const int* max_level,
+                            const float* ur, const float* er_max, const uint8_t* valid, const uint8_t* qdesc,
+                            const float* q_angle, const int* q_obs, const int* init_obs, int* assign_out,
+                            int th_accept, int check_ori);
+int orbo_search_by_projection_reloc(int n_cur, const orbo_kp* kps_cur, const uint8_t* desc_cur,
+                                    float minX, float maxX, float minY, float maxY, const float* scale,
+                                    int nkf, const uint8_t* has_mp, const uint8_t* bad, const uint8_t* already_found,
+                                    const float* xyz, const uint8_t* mp_desc, const int* pred_level,
+                                    const float* min_dist, const float* max_dist, const float* kf_angle,
+                                    const float* Tcw, const float* K, const uint8_t* cur_taken, int* assign_out,
+                                    float th, int ORBdist, int check_ori,
+                                    float* uvr_out, int* minl_out, int* maxl_out, uint8_t* valid_out);
+
 /* Frame::ComputeStereoMatches, src/Frame.cc:513-699 */
 int orbo_stereo_matches(const orbo_extractor* eL, const orbo_extractor* eR,
                         int nl, const orbo_kp* kps_l, const uint8_t* desc_l,

@@ -346,6 +346,28 @@ class ORBmatcher:
         return nm.value, m12, prev
 
 
+def window_search_best(F, uvr, min_level, max_level, qdesc, th_accept, check_ori=False, q_angle=None, q_obs=None,
+                       init_obs=None, ur=None, er_max=None, valid=None, device=0):
+    """orbm_window_search_best: the best-candidate-only window search shared by the projection overloads of
+    ORBmatcher (src/ORBmatcher.cc:160-300, 303-431, 434-549) once the caller has projected its points.
+    Returns (nmatches, assign [F.n])."""
+    uvr, qdesc = _np(uvr, np.float32), _np(qdesc, np.uint8)
+    minl, maxl = _np(min_level, np.int32), _np(max_level, np.int32)
+    qa, qo, io = _np(q_angle, np.float32), _np(q_obs, np.int32), _np(init_obs, np.int32)
+    ur, em, va = _np(ur, np.float32), _np(er_max, np.float32), _np(valid, np.uint8)
+    out = np.zeros(len(F.kps), np.int32)
+    nm = C.c_int()
+    fs = F.struct()
+    p = lambda a: None if a is None else a.ctypes.data
+    L = lib()
+    L.orbm_window_search_best.argtypes = [C.POINTER(OrbmFrame), C.c_int] + [C.c_void_p] * 11 + [C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int]
+    rc = L.orbm_window_search_best(C.byref(fs), len(minl), p(uvr), p(minl), p(maxl), p(ur), p(em), p(va), p(qdesc), p(qa), p(qo), p(io),
+                                   p(out), int(th_accept), int(check_ori), C.byref(nm), device)
+    if rc:
+        raise OrbError(rc, "orbm_window_search_best failed")
+    return nm.value, out
+
+
 def stereo_matches(ex_left, ex_right, kps_l, desc_l, kps_r, desc_r, bf, fx, frame_l=0, frame_r=0):
     """Frame::ComputeStereoMatches (src/Frame.cc:513-699) on the pyramids still held by the two
     extractors.  Returns (mvuRight, mvDepth, number of matches before the median cut)."""

@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(32) k_resolve_frame(const DevFrame F, const in
                                                      const int* __restrict__ last_obs, const float* __restrict__ last_angle,
                                                      int* __restrict__ obs, int* __restrict__ assign, const int check_ori,
                                                      int* __restrict__ hist_entry /* [nq] kp index */, int* __restrict__ hist_bin /* [nq] */,
-                                                     int* __restrict__ nmatches_out)
+                                                     const int th_accept, int* __restrict__ nmatches_out)
 {
     __shared__ int sizes[HISTO_LENGTH];
     const int lane = threadIdx.x;
@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(32) k_resolve_frame(const DevFrame F, const in
         warp_top2(lst, n, lane, [&](int idx, int) { return !(obs[idx] > 0); }, k1, k2);          // :234-236
         if (k1 == 0xffffffffu) continue;
         const int bestDist = (int)(k1 >> 20), bestIdx = (int)(lst[k1 & 0xfffffu] & 0xffffu);
-        if (bestDist <= TH_HIGH) {                                                                // :256
+        if (bestDist <= th_accept) {                                                              // :256 (TH_HIGH), :381 (ORBdist), :530 (TH_LOW)
             __syncwarp();
             if (lane == 0) {
                 assign[bestIdx] = q; obs[bestIdx] = last_obs[q];
@@ -573,6 +573,24 @@ int run_candidates(Scratch& S, const DevFrame& D, const std::vector<WinQuery>& h
     CKM(cudaGetLastError());
     return ORBX_OK;
 }
+// phase 2 of every "best candidate only" window matcher (frame-to-frame, relocalisation, loop closing)
+int resolve_best(Scratch& S, const DevFrame& D, int nq, const WinQuery* dq, const uint32_t* list, const int* count, int cap,
+                 const int* h_qobs, const float* h_angle, const int* h_obs, int* assign_out, int check_ori, int th_accept, int* nmatches)
+{
+    int* d_qobs = S.up(h_qobs, (size_t)nq);
+    float* d_angle = S.up(h_angle, (size_t)nq);
+    int* d_obs = S.up(h_obs, (size_t)D.n);
+    int* d_assign = S.up(assign_out, (size_t)D.n);
+    int* d_he = (int*)S.alloc(sizeof(int) * (size_t)nq);
+    int* d_hb = (int*)S.alloc(sizeof(int) * (size_t)nq);
+    int* d_nm = (int*)S.alloc(4);
+    if (!S.ok) return ORBX_E_CUDA;
+    k_resolve_frame<<<1, 32>>>(D, nq, dq, list, count, cap, d_qobs, d_angle, d_obs, d_assign, check_ori, d_he, d_hb, th_accept, d_nm);
+    CKM(cudaGetLastError());
+    CKM(cudaMemcpy(assign_out, d_assign, sizeof(int) * (size_t)D.n, cudaMemcpyDeviceToHost));
+    CKM(cudaMemcpy(nmatches, d_nm, 4, cudaMemcpyDeviceToHost));
+    return ORBX_OK;
+}
 } // namespace
 
 extern "C" {
@@ -715,19 +733,42 @@ int orbm_search_by_projection_frame(const orbm_frame* cur, int n_last, const orb
     WinQuery* dq; uint32_t* list; int* count; int cap;
     int rc = run_candidates(S, D, hq, last_mp_desc, n_last, &dq, &list, &count, &cap);
     if (rc) return rc;
-    int* d_lobs = S.up(h_lobs.data(), (size_t)n_last);
-    float* d_angle = S.up(h_angle.data(), (size_t)n_last);
-    int* d_obs = S.up(h_obs.data(), (size_t)n_cur);
-    int* d_assign = S.up(assign_out, (size_t)n_cur);
-    int* d_he = (int*)S.alloc(sizeof(int) * (size_t)n_last);
-    int* d_hb = (int*)S.alloc(sizeof(int) * (size_t)n_last);
-    int* d_nm = (int*)S.alloc(4);
-    if (!S.ok) return ORBX_E_CUDA;
-    k_resolve_frame<<<1, 32>>>(D, n_last, dq, list, count, cap, d_lobs, d_angle, d_obs, d_assign, checkOri, d_he, d_hb, d_nm);
-    CKM(cudaGetLastError());
-    CKM(cudaMemcpy(assign_out, d_assign, sizeof(int) * (size_t)n_cur, cudaMemcpyDeviceToHost));
-    CKM(cudaMemcpy(nmatches, d_nm, 4, cudaMemcpyDeviceToHost));
-    return ORBX_OK;
+    return resolve_best(S, D, n_last, dq, list, count, cap, h_lobs.data(), h_angle.data(), h_obs.data(), assign_out, checkOri, TH_HIGH, nmatches);
+}
+
+int orbm_window_search_best(const orbm_frame* F, int nq, const float* uvr, const int* min_level, const int* max_level,
+                            const float* ur, const float* er_max, const uint8_t* valid, const uint8_t* qdesc,
+                            const float* q_angle, const int* q_obs, const int* init_obs, int* assign_out,
+                            int th_accept, int check_ori, int* nmatches, int device)
+{
+    if (!F || nq < 0 || !assign_out || !nmatches || (nq > 0 && (!uvr || !min_level || !max_level || !qdesc))) return ORBX_E_ARG;
+    if (check_ori && nq > 0 && !q_angle) return ORBX_E_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return ORBX_E_CUDA; }
+    *nmatches = 0;
+    const int n = F->n;
+    std::vector<int> h_obs((size_t)(n > 0 ? n : 1));
+    for (int k = 0; k < n; ++k) { h_obs[(size_t)k] = init_obs ? init_obs[k] : -1; assign_out[k] = (init_obs && init_obs[k] >= 0) ? -2 : -1; }
+    if (nq == 0 || n == 0) return ORBX_OK;
+    Scratch S;
+    DevFrame D;
+    if (!make_frame(S, F, &D)) return S.ok ? ORBX_E_ARG : ORBX_E_CUDA;
+    std::vector<WinQuery> hq((size_t)nq);
+    std::vector<float> h_angle((size_t)nq, 0.f);
+    std::vector<int> h_qobs((size_t)nq, 1);
+    for (int i = 0; i < nq; ++i) {
+        WinQuery& Q = hq[(size_t)i];
+        Q.valid = valid ? (valid[i] != 0) : 1;
+        Q.u = uvr[3 * i]; Q.v = uvr[3 * i + 1]; Q.r = uvr[3 * i + 2];
+        Q.min_level = min_level[i]; Q.max_level = max_level[i];
+        Q.ur = ur ? ur[i] : 0.f; Q.er_max = er_max ? er_max[i] : 3.0e38f;
+        if (q_angle) h_angle[(size_t)i] = q_angle[i];
+        if (q_obs) h_qobs[(size_t)i] = q_obs[i];
+    }
+    if (!ur) D.u_right = nullptr;
+    WinQuery* dq; uint32_t* list; int* count; int cap;
+    int rc = run_candidates(S, D, hq, qdesc, nq, &dq, &list, &count, &cap);
+    if (rc) return rc;
+    return resolve_best(S, D, nq, dq, list, count, cap, h_qobs.data(), h_angle.data(), h_obs.data(), assign_out, check_ori, th_accept, nmatches);
 }
 
 int orbm_search_for_initialization(const orbm_frame* F1, const orbm_frame* F2, float* prev_matched, int* matches12,

@@ -133,3 +133,49 @@ def test_stereo_pair_end_to_end():
     assert (ur.view(np.uint32) == our.view(np.uint32)).all() and (dep.view(np.uint32) == odep.view(np.uint32)).all()
     for x in (GL, GR, OL, OR):
         x.close()
+
+
+@pytest.mark.parametrize("th,orb_dist,check_ori", [(10.0, 100, True), (3.0, 64, True), (10.0, 100, False)])
+def test_relocalisation_window_search(scene, th, orb_dist, check_ori):
+    """src/ORBmatcher.cc:303-431 through the generic device primitive: the host projects (oracle's exported
+    queries = what the C++ forwarder computes), the GPU does windows, distances, ordered claims, histogram."""
+    from reloc_lib import reloc_scene, run_reloc
+    s = reloc_scene(scene["kps"], scene["desc"], W, H, 31, K)
+    nm, assign, q = run_reloc("oracle", s, scene["scale"], BOUNDS, K, th, orb_dist, check_ori, want_queries=True)
+    F = ob.FrameView(s["cur_kps"], s["cur_desc"], BOUNDS)
+    init_obs = np.where(s["cur_taken"] > 0, 1, -1).astype(np.int32)
+    g_nm, g_assign = ob.window_search_best(F, q["uvr"], q["minl"], q["maxl"], s["mp_desc"], orb_dist, check_ori, q_angle=s["kf_angle"],
+                                           init_obs=init_obs, valid=q["valid"])
+    assert g_nm == nm and nm > 100 and (g_assign == assign).all()
+
+
+def test_window_search_generic_random_queries(scene):
+    """Random windows / level ranges / right-image gates / pre-attached points against the oracle primitive."""
+    import ctypes as C
+    rng = np.random.default_rng(12)
+    k2, d2 = scene["k2"], scene["d2"]
+    n, nq = len(k2), 1500
+    tgt = rng.integers(0, n, nq)
+    uvr = np.stack([k2["x"][tgt] + rng.normal(0, 4, nq), k2["y"][tgt] + rng.normal(0, 4, nq), rng.choice([3.0, 8.0, 20.0, 60.0], nq)], 1).astype(np.float32)
+    minl = rng.integers(-1, 4, nq).astype(np.int32)
+    maxl = np.where(rng.random(nq) < 0.3, -1, minl + rng.integers(0, 3, nq)).astype(np.int32)
+    u_right = np.where(rng.random(n) < 0.5, k2["x"] - 25 * rng.random(n), -1).astype(np.float32)
+    ur = (uvr[:, 0] - 12 + rng.normal(0, 6, nq)).astype(np.float32)
+    er_max = rng.choice([2.0, 6.0, 15.0], nq).astype(np.float32)
+    valid = (rng.random(nq) < 0.9).astype(np.uint8)
+    qd = d2[tgt].copy(); qd[:, :4] ^= rng.integers(0, 256, (nq, 4), dtype=np.uint8)
+    q_angle = (rng.random(nq) * 360).astype(np.float32)
+    q_obs = (rng.random(nq) < 0.8).astype(np.int32)
+    init_obs = np.where(rng.random(n) < 0.1, rng.integers(0, 2, n), -1).astype(np.int32)
+    O = oracle()
+    vp, ci, cf = C.c_void_p, C.c_int, C.c_float
+    O.orbo_window_search_best.argtypes = [ci, vp, vp, vp] + [cf] * 4 + [ci] + [vp] * 11 + [ci, ci]
+    for th_accept, check_ori in ((100, True), (50, False)):
+        ref_assign = np.zeros(n, np.int32)
+        p = lambda a: a.ctypes.data
+        nm = O.orbo_window_search_best(n, p(k2), p(d2), p(u_right), *BOUNDS, nq, p(uvr), p(minl), p(maxl), p(ur), p(er_max), p(valid), p(qd),
+                                       p(q_angle), p(q_obs), p(init_obs), p(ref_assign), th_accept, int(check_ori))
+        F = ob.FrameView(k2, d2, BOUNDS, u_right)
+        g_nm, g_assign = ob.window_search_best(F, uvr, minl, maxl, qd, th_accept, check_ori, q_angle=q_angle, q_obs=q_obs, init_obs=init_obs,
+                                               ur=ur, er_max=er_max, valid=valid)
+        assert g_nm == nm and nm > 100 and (g_assign == ref_assign).all()   # random query angles: the histogram prunes most

@@ -151,3 +151,15 @@ def test_oracle_vs_matcher_fixtures(scene):
     assert (our.view(np.uint32) == g["stereo_uright"].view(np.uint32)).all()
     assert (odep.view(np.uint32) == g["stereo_depth"].view(np.uint32)).all()
     OL.close(); OR.close()
+
+
+@needs_ref
+@pytest.mark.parametrize("th,orb_dist,check_ori", [(10.0, 100, True), (3.0, 64, True), (10.0, 100, False)])
+def test_relocalisation_overload(scene, th, orb_dist, check_ori):
+    """src/ORBmatcher.cc:303-431 (the th/ORBdist pairs are the ones Tracking::Relocalization passes)."""
+    from reloc_lib import reloc_scene, run_reloc
+    s = reloc_scene(scene["kps"], scene["desc"], W, H, 31, K)
+    a = run_reloc("ref", s, scene["scale"], BOUNDS, K, th, orb_dist, check_ori)
+    b = run_reloc("oracle", s, scene["scale"], BOUNDS, K, th, orb_dist, check_ori)
+    assert a[0] == b[0] and a[0] > 100, (a[0], b[0])
+    assert (a[1] == b[1]).all()
