@@ -21,8 +21,10 @@
 #ifndef ORBMATCHER_B200_HPP
 #define ORBMATCHER_B200_HPP
 
+#include <cmath>
 #include <cstring>
 #include <map>
+#include <set>
 #include <stdexcept>
 #include <vector>
 
@@ -147,6 +149,70 @@ int SearchByProjection(FrameT& Cur, const FrameT& Last, const float th, const bo
           "orbm_search_by_projection_frame");
     for (size_t k = 0; k < kps.size(); ++k) {
         if (assign[k] >= 0) Cur.mvpMapPoints[k] = Last.mvpMapPoints[(size_t)assign[k]];
+        else if (assign[k] == -1) Cur.mvpMapPoints[k] = 0;
+    }
+    return nmatches;
+}
+
+// ORBmatcher::SearchByProjection(Frame& cur, KeyFrame* pKF, const set<MapPoint*>& sAlreadyFound, th, ORBdist),
+// src/ORBmatcher.cc:303-431 (relocalisation).  The projection, the distance gate and MapPoint::PredictScale
+// stay on the host in the reference's arithmetic (cv::gemm float accumulation, cv::norm in double);
+// windows, distances, ordered claims and the rotation histogram run on the GPU (orbm_window_search_best).
+template <class FrameT, class KeyFrameT, class MapPointT>
+int SearchByProjection(FrameT& Cur, KeyFrameT* pKF, const std::set<MapPointT*>& sAlreadyFound, const float th, const int ORBdist,
+                       const bool checkOri)
+{
+    std::vector<orbx_kp> kps; FlattenKeys(Cur.mvKeysUn, kps);
+    std::vector<unsigned char> desc; FlattenDescriptors(Cur.mDescriptors, (int)kps.size(), desc);
+    const orbm_frame view = View(Cur, kps, desc, false);
+    float T[16];
+    for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) T[4 * r + c] = Cur.mTcw.template at<float>(r, c);
+    float Ow[3];
+    for (int i = 0; i < 3; ++i) {
+        float s = (-T[0 * 4 + i]) * T[3];
+        s = s + (-T[1 * 4 + i]) * T[7];
+        s = s + (-T[2 * 4 + i]) * T[11];
+        Ow[i] = s;
+    }
+    const std::vector<MapPointT*> vpMPs = pKF->GetMapPointMatches();
+    const size_t nq = vpMPs.size();
+    std::vector<float> uvr(3 * (nq ? nq : 1), 0.f), qangle(nq ? nq : 1, 0.f);
+    std::vector<int> minl(nq ? nq : 1, 0), maxl(nq ? nq : 1, 0);
+    std::vector<unsigned char> valid(nq ? nq : 1, 0), qdesc(32 * (nq ? nq : 1), 0);
+    for (size_t i = 0; i < nq; ++i) {
+        MapPointT* pMP = vpMPs[i];
+        if (!pMP || pMP->isBad() || sAlreadyFound.count(pMP)) continue;
+        const cv::Mat x3Dw = pMP->GetWorldPos();
+        const float x[3] = { x3Dw.template at<float>(0), x3Dw.template at<float>(1), x3Dw.template at<float>(2) };
+        float pc[3];
+        for (int r = 0; r < 3; ++r) {
+            float s = T[4 * r] * x[0];
+            s = s + T[4 * r + 1] * x[1];
+            s = s + T[4 * r + 2] * x[2];
+            pc[r] = s + T[4 * r + 3];
+        }
+        const float invzc = 1.0 / pc[2];
+        const float u = FrameT::fx * pc[0] * invzc + FrameT::cx, v = FrameT::fy * pc[1] * invzc + FrameT::cy;
+        if (u < FrameT::mnMinX || u > FrameT::mnMaxX) continue;
+        if (v < FrameT::mnMinY || v > FrameT::mnMaxY) continue;
+        double acc = 0;
+        for (int r = 0; r < 3; ++r) { const float d = x[r] - Ow[r]; acc += (double)d * (double)d; }
+        float dist3D = (float)std::sqrt(acc);
+        if (dist3D < pMP->GetMinDistanceInvariance() || dist3D > pMP->GetMaxDistanceInvariance()) continue;
+        const int lvl = pMP->PredictScale(dist3D, &Cur);
+        uvr[3 * i] = u; uvr[3 * i + 1] = v; uvr[3 * i + 2] = th * Cur.mvScaleFactors[(size_t)lvl];
+        minl[i] = lvl - 1; maxl[i] = lvl + 1; valid[i] = 1;
+        qangle[i] = pKF->mvKeysUn[i].angle;
+        std::memcpy(&qdesc[32 * i], pMP->GetDescriptor().ptr(0), 32);
+    }
+    std::vector<int> initObs(kps.size(), -1), assign(kps.size(), -1);
+    for (size_t k = 0; k < kps.size(); ++k) if (Cur.mvpMapPoints[k]) initObs[k] = 1;   // any attached point blocks (:373-374)
+    int nmatches = 0;
+    Check(orbm_window_search_best(&view, (int)nq, &uvr[0], &minl[0], &maxl[0], 0, 0, &valid[0], &qdesc[0], &qangle[0], 0,
+                                  kps.empty() ? 0 : &initObs[0], kps.empty() ? 0 : &assign[0], ORBdist, checkOri ? 1 : 0, &nmatches, Device()),
+          "orbm_window_search_best");
+    for (size_t k = 0; k < kps.size(); ++k) {
+        if (assign[k] >= 0) Cur.mvpMapPoints[k] = vpMPs[(size_t)assign[k]];
         else if (assign[k] == -1) Cur.mvpMapPoints[k] = 0;
     }
     return nmatches;

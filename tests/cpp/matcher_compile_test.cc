@@ -6,6 +6,7 @@
 #include "Frame.h"
 typedef ORB_SLAM2::Frame FrameT;
 typedef ORB_SLAM2::MapPoint MapPointT;
+typedef ORB_SLAM2::KeyFrame KeyFrameT;
 #else
 #include "cvshim.hpp"
 #include <vector>
@@ -13,6 +14,9 @@ struct MapPointT {
     bool mbTrackInView, bad; int mnTrackScaleLevel, nObs; float mTrackViewCos, mTrackProjX, mTrackProjY, mTrackProjXR;
     cv::Mat descriptor, pos;
     bool isBad() { return bad; }
+    float GetMinDistanceInvariance() { return 0.f; }
+    float GetMaxDistanceInvariance() { return 1e9f; }
+    template <class F> int PredictScale(const float&, F*) { return mnTrackScaleLevel; }
     int Observations() { return nObs; }
     cv::Mat GetDescriptor() { return descriptor.clone(); }
     cv::Mat GetWorldPos() { return pos.clone(); }
@@ -25,6 +29,11 @@ struct FrameT {
     std::vector<MapPointT*> mvpMapPoints;
     std::vector<bool> mvbOutlier;
     static float fx, fy, cx, cy, mnMinX, mnMaxX, mnMinY, mnMaxY;
+};
+struct KeyFrameT {
+    std::vector<cv::KeyPoint> mvKeysUn;
+    std::vector<MapPointT*> pts;
+    std::vector<MapPointT*> GetMapPointMatches() { return pts; }
 };
 float FrameT::fx, FrameT::fy, FrameT::cx, FrameT::cy, FrameT::mnMinX, FrameT::mnMaxX, FrameT::mnMinY, FrameT::mnMaxY;
 #endif
@@ -40,5 +49,8 @@ extern "C" int matcher_forwarders_instantiate(int run)
     int n = ORB_SLAM2::b200::SearchByProjection(a, pts, 3.0f, 0.8f);
     n += ORB_SLAM2::b200::SearchByProjection(a, b, 7.0f, false, true);
     n += ORB_SLAM2::b200::SearchForInitialization(a, b, prev, m12, 100, 0.9f, true);
+    KeyFrameT kf;
+    std::set<MapPointT*> found;
+    n += ORB_SLAM2::b200::SearchByProjection(a, &kf, found, 10.0f, 100, true);
     return n;
 }
