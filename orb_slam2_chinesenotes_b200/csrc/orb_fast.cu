@@ -3,19 +3,31 @@
 // (cv::FAST(cell, kps, iniThFAST, true), and again with minThFAST when that returns nothing).
 //
 // One block per STRIP: a run of up to ORB_FAST_STRIP horizontally adjacent 30-px cells of one
-// cell row.  Every cell of the strip is staged into shared memory as its own word-aligned
-// image (evaluated rectangle + 3-px ring apron), so all later accesses are aligned 32-bit
-// words and the NMS is cell-local by construction.  Everything is done on PACKED PIXEL PAIRS:
-// a work item is 4 horizontally adjacent evaluated pixels; each of the 16 ring offsets is one
-// funnel-shifted 32-bit window, widened to two 16x2 registers, and the sliding min/max network
-// runs on the 3-input DPX instructions (VIMNMX3.S16x2): one instruction advances two pixels and
-// there is no data-dependent branch in the scoring.
+// cell row.  The kernel is bound by the integer/min-max issue rate (tools/ubench_pipes.cu), so
+// it is organised around instructions per pixel:
+//   * the strip is staged into shared memory as one image (evaluated rectangle + 3-px ring
+//     apron), widened ONCE to 16 bits per pixel and stored TWICE: copy A holds pixel pairs that
+//     start on an even column, copy B pairs that start on an odd column.  Each of the 16 ring
+//     positions of a horizontally adjacent PIXEL PAIR is then one aligned 32-bit shared load of
+//     a ready-made 16x2 operand -- no funnel shifts or byte permutes in the scoring loop;
+//   * the score network works on the 16x2 operands with the full-rate 2-input half2 min/max
+//     (VHMNMX; the values 0..255 are positive fp16 denormals, whose order is the integer
+//     order), 47 operations per polarity (below) instead of the 80 of a sliding 3-input
+//     network, with no data-dependent branch;
+//   * a thread owns one pixel-pair column of the strip and walks down the rows, so index math
+//     is paid per column, not per pixel;
+//   * NMS reads a 16x2 score map with the same packing (3 rows x 3 words, column maxima,
+//     two permutes for the left/right neighbours, one carry-free packed compare).
 //
 // Score (OpenCV cornerScore<16>, threshold independent), d[k] = v - ring[k]:
 //     score = max( max_k min_{m<9} d[k+m], max_k min_{m<9} -d[k+m] ) - 1
-// v is constant over the ring, so the network runs on the RAW ring values:
-//     max_k min9(-d) = M1 - v,  M1 = max_k min_{m<9} ring[k+m]
-//     max_k min9( d) = v - M2,  M2 = min_k max_{m<9} ring[k+m]
+// v is constant over the ring, so the network runs on the RAW ring values E[0..15]:
+//     max_k min9(-d) = M1 - v,  M1 = max_k min_{m<9} E[k+m]
+//     max_k min9( d) = v - M2,  M2 = min_k max_{m<9} E[k+m]
+// Every 9-arc is an 8-arc starting at an EVEN position plus one of the two ring values next to
+// it, and min/max distribute over each other, so with F[j] = min(E[2j..2j+7]):
+//     M1 = max_j min( F[j], max(E[2j-1], E[2j+8]) )                     (indices mod 16)
+// F comes from pair minima B[j] = min(E[2j],E[2j+1]) by doubling: 8 + 8 + 8 ops, then 8 + 8 + 7.
 // A pixel is a FAST corner at threshold t iff score >= t.  NMS is the strict 3x3 maximum of the
 // score map INSIDE the cell (FAST runs on the cropped cell image, so neighbours outside the
 // cell's evaluated rectangle count as 0); both thresholds read the same map, hence the
@@ -24,225 +36,260 @@
 #include "orb_device.cuh"
 #include "orb_launch.h"
 
-#define FAST_NT 256
+#define FAST_NT (32 * ORB_FAST_STRIP)
 
-// window of 4 bytes starting DX bytes right of the middle word of (w0,w1,w2)
-template <int DX>
-__device__ __forceinline__ uint32_t fast_win(const uint32_t w0, const uint32_t w1, const uint32_t w2)
+__device__ __forceinline__ uint32_t hmin2(const uint32_t a, const uint32_t b)
 {
-    if (DX < 0) return __funnelshift_r(w0, w1, 8 * (4 + DX));
-    if (DX > 0) return __funnelshift_r(w1, w2, 8 * DX);
-    return w1;
+    uint32_t d;
+    asm("min.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+__device__ __forceinline__ uint32_t hmax2(const uint32_t a, const uint32_t b)
+{
+    uint32_t d;
+    asm("max.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
 }
 
-// sliding-window network over the 16 biased ring values of a pixel pair -> packed (M1, M2)
+// packed (M1, M2) of a pixel pair from its 16 ring operands
 __device__ __forceinline__ void fast_network(const uint32_t* E, uint32_t& M1, uint32_t& M2)
 {
-    uint32_t A[16], B[16];
+    uint32_t Bn[8], Bx[8], Qn[8], Qx[8], Y[8], Z[8];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        A[j] = __vimin3_s16x2(E[j], E[(j + 1) & 15], E[(j + 2) & 15]);
-        B[j] = __vimax3_s16x2(E[j], E[(j + 1) & 15], E[(j + 2) & 15]);
-    }
-    uint32_t mn[16], mx[16];
+    for (int j = 0; j < 8; ++j) { Bn[j] = hmin2(E[2 * j], E[2 * j + 1]); Bx[j] = hmax2(E[2 * j], E[2 * j + 1]); }
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        mn[i] = __vimin3_s16x2(A[i], A[(i + 3) & 15], A[(i + 6) & 15]);   // min E[i..i+8]
-        mx[i] = __vimax3_s16x2(B[i], B[(i + 3) & 15], B[(i + 6) & 15]);   // max E[i..i+8]
+    for (int j = 0; j < 8; ++j) { Qn[j] = hmin2(Bn[j], Bn[(j + 1) & 7]); Qx[j] = hmax2(Bx[j], Bx[(j + 1) & 7]); }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const uint32_t Fn = hmin2(Qn[j], Qn[(j + 2) & 7]);                 // min E[2j .. 2j+7]
+        const uint32_t Fx = hmax2(Qx[j], Qx[(j + 2) & 7]);                 // max E[2j .. 2j+7]
+        const uint32_t lo = E[(2 * j + 15) & 15], hi = E[(2 * j + 8) & 15];
+        Y[j] = hmin2(Fn, hmax2(lo, hi));
+        Z[j] = hmax2(Fx, hmin2(lo, hi));
     }
-    uint32_t a = __vimax3_s16x2(mn[0], mn[1], mn[2]), b = __vimax3_s16x2(mn[3], mn[4], mn[5]);
-    uint32_t c = __vimax3_s16x2(mn[6], mn[7], mn[8]), d = __vimax3_s16x2(mn[9], mn[10], mn[11]);
-    uint32_t e = __vimax3_s16x2(mn[12], mn[13], mn[14]);
-    M1 = __vimax3_s16x2(__vimax3_s16x2(a, b, c), __vimax3_s16x2(d, e, mn[15]), a);
-    a = __vimin3_s16x2(mx[0], mx[1], mx[2]); b = __vimin3_s16x2(mx[3], mx[4], mx[5]);
-    c = __vimin3_s16x2(mx[6], mx[7], mx[8]); d = __vimin3_s16x2(mx[9], mx[10], mx[11]);
-    e = __vimin3_s16x2(mx[12], mx[13], mx[14]);
-    M2 = __vimin3_s16x2(__vimin3_s16x2(a, b, c), __vimin3_s16x2(d, e, mx[15]), a);
+    M1 = hmax2(hmax2(hmax2(Y[0], Y[1]), hmax2(Y[2], Y[3])), hmax2(hmax2(Y[4], Y[5]), hmax2(Y[6], Y[7])));
+    M2 = hmin2(hmin2(hmin2(Z[0], Z[1]), hmin2(Z[2], Z[3])), hmin2(hmin2(Z[4], Z[5]), hmin2(Z[6], Z[7])));
 }
 
-// n / d for 0 <= n < 2^16, 1 <= d < 2^8: (n + 0.5) / d is never within float rounding of an integer
+// n / d for 0 <= n < 2^16, 1 <= d < 2^9: (n + 0.5) / d is never within float rounding of an integer
 __device__ __forceinline__ int fast_div(const int n, const int d)
 {
     return __float2int_rz(__fdividef((float)n + 0.5f, (float)d));
 }
 
-// bright = max_k min9(ring) - v, dark = v - min_k max9(ring)
-__device__ __forceinline__ int fast_score_of(const int bright, const int dark, const int minTh)
+// Geometry of a strip's shared-memory images.  STATIC: compile-time strides for cells up to
+// ORB_FAST_WC_STATIC wide (all offsets of the scoring loop become immediates); otherwise run-time.
+//   tile row  = [copy A: WPC words][pad][copy B: WPC words][1] of the strip as ONE image (cells are contiguous,
+//               so nothing is staged twice); copy A word j = strip columns (2j, 2j+1), copy B word j = columns
+//               (2j+1, 2j+2); strip column 0 = first column of the first cell image.  Copy B starts OB words
+//               into the row with OB = 1 (mod 32): a warp spans two cells, and when wCell is odd its second
+//               cell reads the other copy -- this offset puts the two half-warps on disjoint banks.
+//   score row = 1 + ncs * SP words, SP = np + 1: pixel pair p (evaluated columns 2p, 2p+1) of cell c at word
+//               c*SP + p + 1; word c*SP is the zero apron between cells
+// Pixel pair p of cell c has its ring window starting at strip column t = c*wCell + 2p.  For even t the odd
+// ring offsets dx are words of copy A and the even ones words of copy B; for odd t the roles swap.  Either
+// way the words are a[(3+dx)/2] (dx odd) and b[(2+dx)/2] (dx even) from two per-column base pointers.
+template <bool STATIC>
+__device__ __forceinline__ void fast_strip_body(const OrbPlan& plan, const OrbBatch& io, uint32_t* smem, uint2* s_col, int* s_ctr, int* s_any,
+                                                const int frame, const int l, const int strip)
 {
-    const int s = max(bright, dark) - 1;
-    return s >= minTh ? s : 0;
-}
-
-__global__ void __launch_bounds__(FAST_NT) k_fast_strips(const __grid_constant__ OrbPlan plan, const OrbBatch io)
-{
-    extern __shared__ uint32_t smem[];
-    __shared__ int s_nq, s_nsurv, s_nkeep, s_nwr, s_base, s_any[ORB_FAST_STRIP];
-    const int frame = blockIdx.y, tid = threadIdx.x;
-    int l = 0;
-    while (l + 1 < plan.nlevels && (int)blockIdx.x >= plan.lv[l + 1].strip_first) ++l;
     const OrbLevel& L = plan.lv[l];
-    const int strip = blockIdx.x - L.strip_first;
+    const int tid = threadIdx.x;
     const int ci = strip / L.spr, cj0 = (strip - ci * L.spr) * ORB_FAST_STRIP;
     const int ncs = min(ORB_FAST_STRIP, L.ncx - cj0);
     const int wc = L.wCell, maxBX = L.w - ORB_BORDER0;
     const int y0 = ORB_BORDER0 + ci * L.hCell, y1 = min(y0 + L.hCell + 6, L.h - ORB_BORDER0);
     const int eh = y1 - y0 - 6;                      // evaluated rows y0+3 .. y1-4
     if (eh <= 0) return;
-    const int gq = (wc + 3) >> 2;                    // 4-pixel groups per cell row
-    const int tw = gq + 2;                           // words per staged cell row; evaluated lx sits at byte lx+4
-    const int TW = ncs * tw;                         // words per staged strip row
+    const int np = (wc + 1) >> 1;                    // pixel pairs per cell row
+    const int WPC = STATIC ? ORB_FAST_WPC_STATIC : orb_fast_wpc(ncs, wc);
+    const int OB = orb_fast_ob(WPC), RS = OB + WPC + 1;         // even: rows stay 8-byte aligned
+    const int SP = np + 1, SRS = ncs * SP + 1;
     const int th = eh + 6;
-    uint32_t* tile = smem;                                            // th x TW
-    uint32_t* score = smem + plan.fast_tile_words;                    // (eh+2) x TW, pixel (ly,lx) at row ly+1, byte lx+4
-    uint16_t* queue = (uint16_t*)(score + plan.fast_score_words);     // items with a non-zero score
+    uint32_t* tile = smem;                                            // th x RS
+    uint32_t* score = smem + plan.fast_tile_words;                    // (eh+2) x SRS
     uint32_t* surv = tile;                                            // NMS survivors (tile is dead by then)
-    uint16_t* surv_tag = queue + ((plan.fast_items_max + 1) & ~1);    // cell | isA << 15
+    uint16_t* surv_tag = (uint16_t*)(score + plan.fast_score_words);  // cell | isA << 15
 
     int pitch;
     const uint8_t* src = orb_level_ptr(plan, io, frame, l, &pitch);
     const int w = L.w;
-    // staging: a lane owns a (cell, word) column and walks down the rows, so the index math and the
-    // in-range test are paid once per column
-    for (int idx = tid & 31; idx < TW; idx += 32) {
-        const int c = fast_div(idx, tw), k = idx - c * tw;
-        const int x = ORB_BORDER0 + (cj0 + c) * wc - 1 + 4 * k;
-        const uint8_t* col = src + (size_t)y0 * pitch + x;
-        if (x + 7 < w) {
-            for (int r = tid >> 5; r < th; r += FAST_NT / 32) tile[r * TW + idx] = orb_ld_u32_unaligned(col + (size_t)r * pitch);
-        } else {
-            for (int r = tid >> 5; r < th; r += FAST_NT / 32) {
-                uint32_t v = 0;
+
+    // ---- column table: col = c * np + p
+    const int ipr = ncs * np;
+    for (int col = tid; col < ipr; col += FAST_NT) {
+        const int c = fast_div(col, np), p = col - c * np;
+        const int X = (cj0 + c) * wc;                                  // border-frame x of the cell image's first column
+        const int ew = min(wc, maxBX - 6 - (ORB_BORDER0 + X));         // evaluated width of this cell
+        const int nv = min(max(ew - 2 * p, 0), 2);
+        const int t = c * wc + 2 * p, odd = t & 1;
+        const int aofs = (odd ? OB : 0) + (t >> 1), bofs = odd ? (t >> 1) + 1 : OB + (t >> 1);
+        s_col[col] = make_uint2((uint32_t)aofs | ((uint32_t)(c * SP + p + 1) << 10) | ((uint32_t)nv << 20) | ((uint32_t)c << 22),
+                                (uint32_t)(X + 3 + 2 * p) | ((uint32_t)bofs << 16));
+    }
+    // ---- staging: a thread owns a 4-column group and walks down the rows
+    {
+        const int ncolS = min(WPC >> 1, ((ncs * wc + 7) >> 2) + 1), rg = FAST_NT / ncolS;   // columns 0 .. ncs*wc+7 are read
+        const int g = fast_div(tid, ncolS), k = tid - g * ncolS;
+        if (g < rg) {
+            const int x = ORB_BORDER0 + cj0 * wc + 4 * k;
+            uint32_t* dA = tile + 2 * k + g * RS;
+            const uint8_t* sp = src + (size_t)(y0 + g) * pitch + x;
+            const size_t sstep = (size_t)rg * pitch;
+            const int dstep = rg * RS;
+            if (x + 8 <= w) {
+                for (int r = g; r < th; r += rg, sp += sstep, dA += dstep) {
+                    const uintptr_t a = (uintptr_t)sp;
+                    const uint32_t s = (uint32_t)(a & 3);
+                    const uint32_t* q = (const uint32_t*)(a - s);
+                    const uint32_t q0 = __ldg(q), q1 = __ldg(q + 1);
+                    const uint32_t w0 = __funnelshift_r(q0, q1, 8 * s);          // columns 4k .. 4k+3
+                    const uint32_t c4 = __byte_perm(q1, 0, 0x4440u | s);         // column 4k+4
+                    *(uint2*)dA = make_uint2(__byte_perm(w0, 0, 0x4140), __byte_perm(w0, 0, 0x4342));
+                    dA[OB] = __byte_perm(w0, 0, 0x4241);
+                    dA[OB + 1] = __byte_perm(w0, c4, 0x5453);
+                }
+            } else {
+                for (int r = g; r < th; r += rg, sp += sstep, dA += dstep) {
+                    uint32_t b[5];
 #pragma unroll
-                for (int b = 0; b < 4; ++b) if (x + b < w) v |= (uint32_t)__ldg(col + (size_t)r * pitch + b) << (8 * b);
-                tile[r * TW + idx] = v;
+                    for (int i = 0; i < 5; ++i) b[i] = x + i < w ? (uint32_t)__ldg(sp + i) : 0u;
+                    *(uint2*)dA = make_uint2(b[0] | (b[1] << 16), b[2] | (b[3] << 16));
+                    dA[OB] = b[1] | (b[2] << 16);
+                    dA[OB + 1] = b[3] | (b[4] << 16);
+                }
             }
         }
     }
-    for (int i = tid; i < (eh + 2) * TW; i += FAST_NT) score[i] = 0;
+    {   // score map = 0 (aprons must be; interior is only written where non-zero)
+        uint4* z = (uint4*)score;
+        const int n4 = ((eh + 2) * SRS + 3) >> 2;
+        for (int i = tid; i < n4; i += FAST_NT) z[i] = make_uint4(0, 0, 0, 0);
+    }
     if (tid < ORB_FAST_STRIP) s_any[tid] = 0;
-    if (tid == 0) { s_nq = 0; s_nsurv = 0; s_nkeep = 0; s_nwr = 0; }
+    if (tid < 4) s_ctr[tid] = 0;
     __syncthreads();
 
-    // ---- scores: one item = 4 pixels (ly, cell c, 4q..4q+3)
-    const int ipr = ncs * gq;                        // items per row
-    for (int i = tid; i < eh * ipr; i += FAST_NT) {
-        const int ly = fast_div(i, ipr), rem = i - ly * ipr, c = fast_div(rem, gq), q = rem - c * gq;
-        const int ew = min(wc, maxBX - 6 - (ORB_BORDER0 + (cj0 + c) * wc));   // evaluated width of this cell
-        const int valid = ew - 4 * q;
-        if (valid <= 0) continue;
-        const uint32_t* t0 = tile + ly * TW + c * tw + q;   // ring row dy=-3 is tile row ly, centre row is ly+3
-        uint32_t W[7][3];
-#pragma unroll
-        for (int r = 0; r < 7; ++r) { W[r][0] = t0[r * TW]; W[r][1] = t0[r * TW + 1]; W[r][2] = t0[r * TW + 2]; }
-        // ring windows in OpenCV order; row index = dy + 3
-        uint32_t win[16];
-        win[0] = fast_win<0>(W[6][0], W[6][1], W[6][2]);    //  ( 0, 3)
-        win[1] = fast_win<1>(W[6][0], W[6][1], W[6][2]);    //  ( 1, 3)
-        win[2] = fast_win<2>(W[5][0], W[5][1], W[5][2]);    //  ( 2, 2)
-        win[3] = fast_win<3>(W[4][0], W[4][1], W[4][2]);    //  ( 3, 1)
-        win[4] = fast_win<3>(W[3][0], W[3][1], W[3][2]);    //  ( 3, 0)
-        win[5] = fast_win<3>(W[2][0], W[2][1], W[2][2]);    //  ( 3,-1)
-        win[6] = fast_win<2>(W[1][0], W[1][1], W[1][2]);    //  ( 2,-2)
-        win[7] = fast_win<1>(W[0][0], W[0][1], W[0][2]);    //  ( 1,-3)
-        win[8] = fast_win<0>(W[0][0], W[0][1], W[0][2]);    //  ( 0,-3)
-        win[9] = fast_win<-1>(W[0][0], W[0][1], W[0][2]);   //  (-1,-3)
-        win[10] = fast_win<-2>(W[1][0], W[1][1], W[1][2]);  //  (-2,-2)
-        win[11] = fast_win<-3>(W[2][0], W[2][1], W[2][2]);  //  (-3,-1)
-        win[12] = fast_win<-3>(W[3][0], W[3][1], W[3][2]);  //  (-3, 0)
-        win[13] = fast_win<-3>(W[4][0], W[4][1], W[4][2]);  //  (-3, 1)
-        win[14] = fast_win<-2>(W[5][0], W[5][1], W[5][2]);  //  (-2, 2)
-        win[15] = fast_win<-1>(W[6][0], W[6][1], W[6][2]);  //  (-1, 3)
-        const uint32_t C = W[3][1];
-        uint32_t out = 0;
-#pragma unroll
-        for (int hpair = 0; hpair < 2; ++hpair) {
-            const uint32_t sel = hpair ? 0x4342u : 0x4140u;
-            uint32_t E[16];                                              // raw ring values of the pixel pair
-#pragma unroll
-            for (int k = 0; k < 16; ++k) E[k] = __byte_perm(win[k], 0, sel);
+    // ---- a thread owns a pixel-pair column of the strip and a contiguous run of rows [ya, yb)
+    const int rgc = max(FAST_NT / ipr, 1);
+    const int g = fast_div(tid, ipr), col = tid - g * ipr;
+    const int chunk = fast_div(eh + rgc - 1, rgc);
+    const int ya = g * chunk, yb = min(eh, ya + chunk);
+    uint2 e = make_uint2(0, 0);
+    if (g < rgc) e = s_col[col];
+    const int nv = (e.x >> 20) & 3;                                   // 0 for idle threads and for pairs outside the cell
+    // ---- scores.  stored score = score - (minTh - 1) where score >= minTh, else 0 (monotone, so NMS is unchanged)
+    if (nv) {
+        const uint32_t bias = 0x00010001u * (uint32_t)(65536 - 257 - (plan.minTh - 1));
+        const uint32_t lanes = nv == 2 ? 0xffffffffu : 0x0000ffffu;
+        const uint32_t* a = tile + (e.x & 1023u) + ya * RS;           // ring row dy = -3 of evaluated row ya
+        const int ab = (int)(e.y >> 16) - (int)(e.x & 1023u);
+        uint32_t* sc = score + ((e.x >> 10) & 1023u) + (ya + 1) * SRS;
+#pragma unroll 1
+        for (int ly = ya; ly < yb; ++ly, a += RS, sc += SRS) {
+            const uint32_t* b = a + ab;
+            uint32_t E[16];
+            E[0] = b[6 * RS + 1];    //  ( 0, 3)
+            E[1] = a[6 * RS + 2];    //  ( 1, 3)
+            E[2] = b[5 * RS + 2];    //  ( 2, 2)
+            E[3] = a[4 * RS + 3];    //  ( 3, 1)
+            E[4] = a[3 * RS + 3];    //  ( 3, 0)
+            E[5] = a[2 * RS + 3];    //  ( 3,-1)
+            E[6] = b[1 * RS + 2];    //  ( 2,-2)
+            E[7] = a[0 * RS + 2];    //  ( 1,-3)
+            E[8] = b[0 * RS + 1];    //  ( 0,-3)
+            E[9] = a[0 * RS + 1];    //  (-1,-3)
+            E[10] = b[1 * RS + 0];   //  (-2,-2)
+            E[11] = a[2 * RS + 0];   //  (-3,-1)
+            E[12] = a[3 * RS + 0];   //  (-3, 0)
+            E[13] = a[4 * RS + 0];   //  (-3, 1)
+            E[14] = b[5 * RS + 0];   //  (-2, 2)
+            E[15] = a[6 * RS + 1];   //  (-1, 3)
+            const uint32_t v = b[3 * RS + 1];
             uint32_t M1, M2;
             fast_network(E, M1, M2);
-            const int v0 = (int)((C >> (16 * hpair)) & 0xffu), v1 = (int)((C >> (16 * hpair + 8)) & 0xffu);
-            const int s0 = fast_score_of((int)(M1 & 0xffffu) - v0, v0 - (int)(M2 & 0xffffu), plan.minTh);
-            const int s1 = fast_score_of((int)(M1 >> 16) - v1, v1 - (int)(M2 >> 16), plan.minTh);
-            out |= ((uint32_t)s0 | ((uint32_t)s1 << 8)) << (16 * hpair);
-        }
-        // pixels past the evaluated width must stay 0 (they are "outside the cell image" for the NMS)
-        if (valid < 4) out &= (1u << (8 * valid)) - 1u;
-        if (out) {
-            score[(ly + 1) * TW + c * tw + q + 1] = out;
-            queue[atomicAdd(&s_nq, 1)] = (uint16_t)(ly | (c << 6) | (q << 9));
+            // per 16-bit lane, carry free: bright + 256 = M1 + (256 - v), dark + 256 = (v + 256) - M2
+            const uint32_t br = M1 + (0x01000100u - v), dk = (v + 0x01000100u) - M2;
+            const uint32_t t = hmax2(br, dk);                                   // score + 257
+            const uint32_t out = __viaddmax_s16x2_relu(t, bias, 0u) & lanes;    // max(score - minTh + 1, 0)
+            if (out) *sc = out;
         }
     }
     __syncthreads();
 
-    // ---- strict 3x3 maximum inside each cell, over the items that scored at all
-    const int nq = s_nq;
-    for (int j = tid; j < nq; j += FAST_NT) {
-        const int e = queue[j];
-        const int ly = e & 63, c = (e >> 6) & 7, q = e >> 9;
-        const uint32_t* sc = score + (ly + 1) * TW + c * tw + q;
-        const uint32_t cw = sc[1];
-        uint32_t nb[2] = { 0, 0 };                                 // neighbour maxima of pairs (0,1) and (2,3)
-#pragma unroll
-        for (int r = -1; r <= 1; ++r) {
-            const uint32_t a0 = sc[r * TW], a1 = sc[r * TW + 1], a2 = sc[r * TW + 2];
-            const uint32_t wl = __funnelshift_r(a0, a1, 24);       // bytes 3..6 of the 12-byte span
-            const uint32_t wr = __funnelshift_r(a1, a2, 8);        // bytes 5..8
-            const uint32_t l1 = __byte_perm(wl, 0, 0x4140), l2 = __byte_perm(wl, 0, 0x4241), l3 = __byte_perm(wl, 0, 0x4342);
-            const uint32_t r1 = __byte_perm(wr, 0, 0x4140), r2 = __byte_perm(wr, 0, 0x4241), r3 = __byte_perm(wr, 0, 0x4342);
-            if (r == 0) { nb[0] = __vimax3_s16x2(nb[0], l1, l3); nb[1] = __vimax3_s16x2(nb[1], r1, r3); }
-            else { nb[0] = __vimax3_s16x2(nb[0], __vmaxs2(l1, l2), l3); nb[1] = __vimax3_s16x2(nb[1], __vmaxs2(r1, r2), r3); }
-        }
-        // s > m per byte; nb holds 16-bit lanes (m0,m1),(m2,m3)
-        uint32_t keep = 0;
-#pragma unroll
-        for (int p = 0; p < 4; ++p) {
-            const int s = (int)((cw >> (8 * p)) & 0xffu);
-            const int m = (int)((nb[p >> 1] >> (16 * (p & 1))) & 0xffffu);
-            keep |= (s > m ? 1u : 0u) << p;
-        }
-        while (keep) {
-            const int p = __ffs(keep) - 1;
-            keep &= keep - 1;
-            const int s = (int)((cw >> (8 * p)) & 0xffu);
-            const int slot = atomicAdd(&s_nsurv, 1);
-            // border-frame coordinates (src/ORBextractor.cc:868-869): cell-local + (j*wCell, i*hCell)
-            surv[slot] = orb_pack(4 * q + p + 3 + (cj0 + c) * wc, ly + 3 + ci * L.hCell, s);
-            const bool isA = s >= plan.iniTh;
-            surv_tag[slot] = (uint16_t)(c | (isA ? 0x8000 : 0));
-            if (isA) s_any[c] = 1;
+    // ---- strict 3x3 maximum inside each cell: rows slide through registers, 3 loads per pixel pair
+    if (nv) {
+        const int iniBias = plan.iniTh - plan.minTh + 1;               // stored score of a corner at iniThFAST
+        const int c = (int)(e.x >> 22);
+        const uint32_t* sc = score + ((e.x >> 10) & 1023u) + (ya + 1) * SRS;   // row of evaluated row ya
+        uint32_t u0 = sc[-SRS - 1], u1 = sc[-SRS], u2 = sc[-SRS + 1];
+        uint32_t m0 = sc[-1], m1 = sc[0], m2 = sc[1];
+#pragma unroll 3
+        for (int ly = ya; ly < yb; ++ly, sc += SRS) {
+            const uint32_t d0 = sc[SRS - 1], d1 = sc[SRS], d2 = sc[SRS + 1];
+            const uint32_t cw = m1;
+            const uint32_t Lw = __vimax3_s16x2(u0, m0, d0), Rw = __vimax3_s16x2(u2, m2, d2);
+            const uint32_t Uw = hmax2(u1, d1), Cw = hmax2(Uw, cw);
+            // neighbours of (x | x+1): columns (x-1 | x) and (x+1 | x+2) over three rows, own column above/below
+            const uint32_t nb = __vimax3_s16x2(__byte_perm(Lw, Cw, 0x5432), __byte_perm(Cw, Rw, 0x5432), Uw);
+            // lane > neighbour maximum  <=>  bit 15 of (lane + 32768 - nb - 1); lanes stay in 0..65535, no borrow
+            uint32_t keep = ((cw | 0x80008000u) - nb - 0x00010001u) & 0x80008000u;
+            while (keep) {
+                const int hi = (keep & 0x8000u) ? 0 : 1;
+                keep &= hi ? 0u : 0x80000000u;
+                const int r = (int)((cw >> (16 * hi)) & 0xffffu);
+                const int slot = atomicAdd(&s_ctr[0], 1);
+                // border-frame coordinates (src/ORBextractor.cc:868-869): cell-local + (j*wCell, i*hCell)
+                surv[slot] = orb_pack((int)(e.y & 0xffffu) + hi, ly + 3 + ci * L.hCell, r + plan.minTh - 1);
+                const bool isA = r >= iniBias;
+                surv_tag[slot] = (uint16_t)(c | (isA ? 0x8000 : 0));
+                if (isA) s_any[c] = 1;
+            }
+            u0 = m0; u1 = m1; u2 = m2; m0 = d0; m1 = d1; m2 = d2;
         }
     }
     __syncthreads();
     // ---- per-cell cut-off: keep the iniThFAST survivors, or all of them if the cell has none (:857-861)
-    const int nsurv = s_nsurv;
+    const int nsurv = s_ctr[0];
     int mykeep = 0;
     for (int j = tid; j < nsurv; j += FAST_NT) {
         const int t = surv_tag[j];
         if ((t & 0x8000) || !s_any[t & 0x7fff]) ++mykeep;
     }
-    if (mykeep) atomicAdd(&s_nkeep, mykeep);
+    if (mykeep) atomicAdd(&s_ctr[1], mykeep);
     __syncthreads();
-    const int nkeep = s_nkeep;
+    const int nkeep = s_ctr[1];
     if (nkeep == 0) return;
-    if (tid == 0) s_base = atomicAdd(&io.cand_count[frame * ORB_MAX_LEVELS + l], nkeep);
+    if (tid == 0) s_ctr[3] = atomicAdd(&io.cand_count[frame * ORB_MAX_LEVELS + l], nkeep);
     __syncthreads();
-    const int base = s_base;
+    const int base = s_ctr[3];
     uint32_t* out = io.cand + (size_t)frame * plan.cand_per_frame + L.cand_off;
     for (int j = tid; j < nsurv; j += FAST_NT) {
         const int t = surv_tag[j];
         if ((t & 0x8000) || !s_any[t & 0x7fff]) {
-            const int slot = base + atomicAdd(&s_nwr, 1);
+            const int slot = base + atomicAdd(&s_ctr[2], 1);
             if (slot < L.cand_cap) out[slot] = surv[j];
         }
     }
 }
 
+__global__ void __launch_bounds__(FAST_NT) k_fast_strips(const __grid_constant__ OrbPlan plan, const OrbBatch io)
+{
+    extern __shared__ __align__(16) uint32_t smem[];
+    __shared__ uint2 s_col[FAST_NT];
+    __shared__ int s_ctr[4], s_any[ORB_FAST_STRIP];
+    int l = 0;
+    while (l + 1 < plan.nlevels && (int)blockIdx.x >= plan.lv[l + 1].strip_first) ++l;
+    const int strip = blockIdx.x - plan.lv[l].strip_first;
+    if (plan.lv[l].wCell <= ORB_FAST_WC_STATIC)
+        fast_strip_body<true>(plan, io, smem, s_col, s_ctr, s_any, blockIdx.y, l, strip);
+    else
+        fast_strip_body<false>(plan, io, smem, s_col, s_ctr, s_any, blockIdx.y, l, strip);
+}
+
 size_t orb_fast_smem_bytes(const OrbPlan& plan)
 {
-    return ((size_t)plan.fast_tile_words + plan.fast_score_words) * 4 + ((size_t)((plan.fast_items_max + 1) & ~1)) * 2 +
-           (size_t)plan.fast_surv_max * 2 + 32;
+    return ((size_t)plan.fast_tile_words + plan.fast_score_words) * 4 + (size_t)plan.fast_surv_max * 2 + 32;
 }
 
 cudaError_t orb_launch_fast(const OrbPlan& plan, const OrbBatch& io, int batch, cudaStream_t st)

@@ -118,17 +118,18 @@ int orb_plan_build(const OrbParams* p, int w, int h, OrbPlan* plan, std::vector<
                     if (ew * eh > plan->fast_eval_max) plan->fast_eval_max = ew * eh;
                 }
             }
-            // orb_fast.cu: a block takes a run of up to ORB_FAST_STRIP cells of one cell row; each cell
-            // is staged word-aligned as (4-pixel groups + 2) words per row
+            // orb_fast.cu: a block takes a run of up to ORB_FAST_STRIP cells of one cell row, staged as two
+            // 16-bit copies of the strip image, plus a 16-bit score map with a zero apron per cell
             const int ncs = L.ncx < ORB_FAST_STRIP ? L.ncx : ORB_FAST_STRIP;
-            const int gq = (L.wCell + 3) / 4, tw = gq + 2;
-            const int tile = (L.hCell + 6) * ncs * tw, score = (L.hCell + 2) * ncs * tw;
-            const int items = L.hCell * ncs * gq, surv = ncs * ((L.wCell + 1) / 2) * ((L.hCell + 1) / 2);
+            const int np = (L.wCell + 1) / 2;
+            const int wpc = L.wCell <= ORB_FAST_WC_STATIC ? ORB_FAST_WPC_STATIC : orb_fast_wpc(ncs, L.wCell);
+            const int rs = orb_fast_ob(wpc) + wpc + 1;
+            const int tile = ((L.hCell + 6) * rs + 3) & ~3, score = ((L.hCell + 2) * (ncs * (np + 1) + 1) + 3) & ~3;
+            const int surv = ncs * np * ((L.hCell + 1) / 2);
             if (tile > plan->fast_tile_words) plan->fast_tile_words = tile;
             if (score > plan->fast_score_words) plan->fast_score_words = score;
-            if (items > plan->fast_items_max) plan->fast_items_max = items;
             if (surv > plan->fast_surv_max) plan->fast_surv_max = surv;
-            if (items >= 65536) return 1;                                  // item ids are 16-bit
+            if (surv > tile || ncs * np > 32 * ORB_FAST_STRIP || rs >= 1024) return 1;  // survivors reuse the tile; table / offset widths
             // order key (cell, y-in-cell, x-in-cell) must fit 24 bits
             if ((long long)L.ncx * L.ncy * L.wCell * L.hCell >= (1 << 24)) return 1;
         }
