@@ -71,11 +71,18 @@ __device__ __forceinline__ void fast_network(const uint32_t* E, uint32_t& M1, ui
     M2 = hmin2(hmin2(hmin2(Z[0], Z[1]), hmin2(Z[2], Z[3])), hmin2(hmin2(Z[4], Z[5]), hmin2(Z[6], Z[7])));
 }
 
-// n / d for 0 <= n < 2^16, 1 <= d < 2^9: (n + 0.5) / d is never within float rounding of an integer
+// n / d for 0 <= n < 2^20, 1 <= d < 2^10: (n + 0.5) / d is never within float rounding of an integer
 __device__ __forceinline__ int fast_div(const int n, const int d)
 {
-    return __float2int_rz(__fdividef((float)n + 0.5f, (float)d));
+    return __float2int_rz(__fmul_rn((float)n + 0.5f, __frcp_rn((float)d)));
 }
+
+// Which (level, strip column, cell rows) a block works on: filled per launch (rows_per_block follows the batch
+// size: whole strip columns for big batches, single cell rows when few frames must fill the GPU).
+struct FastGrid {
+    int first[ORB_MAX_LEVELS + 1];   // first block of each level; [nlevels] = total
+    int rows_per_block;
+};
 
 // Geometry of a strip's shared-memory images.  STATIC: compile-time strides for cells up to
 // ORB_FAST_WC_STATIC wide (all offsets of the scoring loop become immediates); otherwise run-time.
@@ -89,207 +96,236 @@ __device__ __forceinline__ int fast_div(const int n, const int d)
 // Pixel pair p of cell c has its ring window starting at strip column t = c*wCell + 2p.  For even t the odd
 // ring offsets dx are words of copy A and the even ones words of copy B; for odd t the roles swap.  Either
 // way the words are a[(3+dx)/2] (dx odd) and b[(2+dx)/2] (dx even) from two per-column base pointers.
+// Everything that depends only on the strip column is set up once; the block then walks down its cell rows.
 template <bool STATIC>
-__device__ __forceinline__ void fast_strip_body(const OrbPlan& plan, const OrbBatch& io, uint32_t* smem, uint2* s_col, int* s_ctr, int* s_any,
-                                                const int frame, const int l, const int strip)
+__device__ __forceinline__ void fast_strip_body(const OrbPlan& plan, const OrbBatch& io, uint32_t* smem, int* s_ctr, int* s_any,
+                                                const int frame, const int l, const int sx, const int ci0, const int ci1)
 {
     const OrbLevel& L = plan.lv[l];
     const int tid = threadIdx.x;
-    const int ci = strip / L.spr, cj0 = (strip - ci * L.spr) * ORB_FAST_STRIP;
+    const int cj0 = sx * ORB_FAST_STRIP;
     const int ncs = min(ORB_FAST_STRIP, L.ncx - cj0);
-    const int wc = L.wCell, maxBX = L.w - ORB_BORDER0;
-    const int y0 = ORB_BORDER0 + ci * L.hCell, y1 = min(y0 + L.hCell + 6, L.h - ORB_BORDER0);
-    const int eh = y1 - y0 - 6;                      // evaluated rows y0+3 .. y1-4
-    if (eh <= 0) return;
+    const int wc = L.wCell, hc = L.hCell, maxBX = L.w - ORB_BORDER0, maxBY = L.h - ORB_BORDER0;
     const int np = (wc + 1) >> 1;                    // pixel pairs per cell row
     const int WPC = STATIC ? ORB_FAST_WPC_STATIC : orb_fast_wpc(ncs, wc);
     const int OB = orb_fast_ob(WPC), RS = OB + WPC + 1;         // even: rows stay 8-byte aligned
     const int SP = np + 1, SRS = ncs * SP + 1;
-    const int th = eh + 6;
-    uint32_t* tile = smem;                                            // th x RS
+    uint32_t* tile = smem;                                            // (eh+6) x RS
     uint32_t* score = smem + plan.fast_tile_words;                    // (eh+2) x SRS
     uint32_t* surv = tile;                                            // NMS survivors (tile is dead by then)
     uint16_t* surv_tag = (uint16_t*)(score + plan.fast_score_words);  // cell | isA << 15
+    uint32_t* raw = score + plan.fast_score_words + ((plan.fast_surv_max + 1) >> 1);   // (eh+6) x RW image words, as fetched
+    const int RW = STATIC ? ORB_FAST_RW_STATIC : orb_fast_rw(ncs, wc);
 
     int pitch;
     const uint8_t* src = orb_level_ptr(plan, io, frame, l, &pitch);
     const int w = L.w;
 
-    // ---- column table: col = c * np + p
+    // ---- this thread's pixel-pair column: col = c * np + p, row group g of rgc
     const int ipr = ncs * np;
-    for (int col = tid; col < ipr; col += FAST_NT) {
-        const int c = fast_div(col, np), p = col - c * np;
+    const int rgc = max(fast_div(FAST_NT, ipr), 1);
+    const int g = fast_div(tid, ipr), col = tid - g * ipr;
+    int nv = 0, c = 0, xb = 0, aofs = 0, ab = 0, sofs = 0;
+    if (g < rgc) {
+        c = fast_div(col, np);
+        const int p = col - c * np;
         const int X = (cj0 + c) * wc;                                  // border-frame x of the cell image's first column
         const int ew = min(wc, maxBX - 6 - (ORB_BORDER0 + X));         // evaluated width of this cell
-        const int nv = min(max(ew - 2 * p, 0), 2);
+        nv = min(max(ew - 2 * p, 0), 2);                               // valid pixels of the pair
         const int t = c * wc + 2 * p, odd = t & 1;
-        const int aofs = (odd ? OB : 0) + (t >> 1), bofs = odd ? (t >> 1) + 1 : OB + (t >> 1);
-        s_col[col] = make_uint2((uint32_t)aofs | ((uint32_t)(c * SP + p + 1) << 10) | ((uint32_t)nv << 20) | ((uint32_t)c << 22),
-                                (uint32_t)(X + 3 + 2 * p) | ((uint32_t)bofs << 16));
+        aofs = (odd ? OB : 0) + (t >> 1);
+        ab = (odd ? (t >> 1) + 1 : OB + (t >> 1)) - aofs;
+        sofs = c * SP + p + 1;
+        xb = X + 3 + 2 * p;
     }
-    // ---- staging: a thread owns a 4-column group and walks down the rows
-    {
-        const int ncolS = min(WPC >> 1, ((ncs * wc + 7) >> 2) + 1), rg = FAST_NT / ncolS;   // columns 0 .. ncs*wc+7 are read
-        const int g = fast_div(tid, ncolS), k = tid - g * ncolS;
-        if (g < rg) {
-            const int x = ORB_BORDER0 + cj0 * wc + 4 * k;
-            uint32_t* dA = tile + 2 * k + g * RS;
-            const uint8_t* sp = src + (size_t)(y0 + g) * pitch + x;
-            const size_t sstep = (size_t)rg * pitch;
-            const int dstep = rg * RS;
-            if (x + 8 <= w) {
-                for (int r = g; r < th; r += rg, sp += sstep, dA += dstep) {
-                    const uintptr_t a = (uintptr_t)sp;
-                    const uint32_t s = (uint32_t)(a & 3);
-                    const uint32_t* q = (const uint32_t*)(a - s);
-                    const uint32_t q0 = __ldg(q), q1 = __ldg(q + 1);
-                    const uint32_t w0 = __funnelshift_r(q0, q1, 8 * s);          // columns 4k .. 4k+3
-                    const uint32_t c4 = __byte_perm(q1, 0, 0x4440u | s);         // column 4k+4
-                    *(uint2*)dA = make_uint2(__byte_perm(w0, 0, 0x4140), __byte_perm(w0, 0, 0x4342));
-                    dA[OB] = __byte_perm(w0, 0, 0x4241);
-                    dA[OB + 1] = __byte_perm(w0, c4, 0x5453);
-                }
-            } else {
-                for (int r = g; r < th; r += rg, sp += sstep, dA += dstep) {
-                    uint32_t b[5];
-#pragma unroll
-                    for (int i = 0; i < 5; ++i) b[i] = x + i < w ? (uint32_t)__ldg(sp + i) : 0u;
-                    *(uint2*)dA = make_uint2(b[0] | (b[1] << 16), b[2] | (b[3] << 16));
-                    dA[OB] = b[1] | (b[2] << 16);
-                    dA[OB + 1] = b[3] | (b[4] << 16);
-                }
+    const uint32_t lanes = nv == 2 ? 0xffffffffu : 0x0000ffffu;
+    // stored score = score - (minTh - 1) where score >= minTh, else 0 (monotone, so NMS is unchanged)
+    const uint32_t bias = 0x00010001u * (uint32_t)(65536 - 257 - (plan.minTh - 1));
+    const int iniBias = plan.iniTh - plan.minTh + 1;                   // stored score of a corner at iniThFAST
+    // ---- this thread's staging column: 4-column group k, row group gs of rgs
+    const int ncolS = min(WPC >> 1, ((ncs * wc + 7) >> 2) + 1);        // columns 0 .. ncs*wc+7 are read
+    const int rgs = fast_div(FAST_NT, ncolS);
+    const int gs = fast_div(tid, ncolS), ks = tid - gs * ncolS;
+    const int x0 = ORB_BORDER0 + cj0 * wc;                             // level x of strip column 0
+    const int dstep = rgs * RS;
+    // ---- this thread's fetch column: image word jp of every rgp-th row.  Rows are fetched from the 4-byte
+    // aligned address at or below their first pixel; bytes past the image width are zero-filled.
+    const int rgp = fast_div(FAST_NT, RW);
+    const int gp = fast_div(tid, RW), jp = tid - gp * RW;
+    const bool fetch_full = x0 + 4 * jp + 8 <= w;
+
+    auto prefetch = [&](const int ci) {
+        const int y0 = ORB_BORDER0 + ci * hc, th = min(y0 + hc + 6, maxBY) - y0;
+        if (gp < rgp) {
+            const uint8_t* rowp = src + (size_t)(y0 + gp) * pitch + x0;
+            uint32_t dst = (uint32_t)__cvta_generic_to_shared(raw + gp * RW + jp);
+            for (int r = gp; r < th; r += rgp, rowp += (size_t)rgp * pitch, dst += 4u * rgp * RW) {
+                const uintptr_t a = (uintptr_t)rowp;
+                const int s = (int)(a & 3);
+                const uint8_t* q = (const uint8_t*)(a - s) + 4 * jp;
+                int n = 4;
+                if (!fetch_full) n = min(max(w - (x0 - s + 4 * jp), 0), 4);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(q), "r"(n) : "memory");
             }
         }
-    }
-    {   // score map = 0 (aprons must be; interior is only written where non-zero)
-        uint4* z = (uint4*)score;
-        const int n4 = ((eh + 2) * SRS + 3) >> 2;
-        for (int i = tid; i < n4; i += FAST_NT) z[i] = make_uint4(0, 0, 0, 0);
-    }
-    if (tid < ORB_FAST_STRIP) s_any[tid] = 0;
-    if (tid < 4) s_ctr[tid] = 0;
-    __syncthreads();
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    prefetch(ci0);
 
-    // ---- a thread owns a pixel-pair column of the strip and a contiguous run of rows [ya, yb)
-    const int rgc = max(FAST_NT / ipr, 1);
-    const int g = fast_div(tid, ipr), col = tid - g * ipr;
-    const int chunk = fast_div(eh + rgc - 1, rgc);
-    const int ya = g * chunk, yb = min(eh, ya + chunk);
-    uint2 e = make_uint2(0, 0);
-    if (g < rgc) e = s_col[col];
-    const int nv = (e.x >> 20) & 3;                                   // 0 for idle threads and for pairs outside the cell
-    // ---- scores.  stored score = score - (minTh - 1) where score >= minTh, else 0 (monotone, so NMS is unchanged)
-    if (nv) {
-        const uint32_t bias = 0x00010001u * (uint32_t)(65536 - 257 - (plan.minTh - 1));
-        const uint32_t lanes = nv == 2 ? 0xffffffffu : 0x0000ffffu;
-        const uint32_t* a = tile + (e.x & 1023u) + ya * RS;           // ring row dy = -3 of evaluated row ya
-        const int ab = (int)(e.y >> 16) - (int)(e.x & 1023u);
-        uint32_t* sc = score + ((e.x >> 10) & 1023u) + (ya + 1) * SRS;
+    for (int ci = ci0; ci < ci1; ++ci) {
+        const int y0 = ORB_BORDER0 + ci * hc, y1 = min(y0 + hc + 6, maxBY);
+        const int eh = y1 - y0 - 6;                  // evaluated rows y0+3 .. y1-4
+        if (eh <= 0) break;
+        const int th = eh + 6;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        // ---- staging: a thread owns a 4-column group and walks down the rows of the fetched image words
+        if (gs < rgs) {
+            uint32_t* dA = tile + 2 * ks + gs * RS;
+            const uint32_t* rq = raw + gs * RW + ks;
+            uint32_t s = (uint32_t)((uintptr_t)(src + (size_t)(y0 + gs) * pitch + x0) & 3);
+            const uint32_t sinc = (uint32_t)(rgs * pitch) & 3u;
+#pragma unroll 4
+            for (int r = gs; r < th; r += rgs, rq += rgs * RW, dA += dstep, s = (s + sinc) & 3u) {
+                const uint32_t q0 = rq[0], q1 = rq[1];
+                const uint32_t w0 = __funnelshift_r(q0, q1, 8 * s);          // columns 4k .. 4k+3
+                const uint32_t c4 = __byte_perm(q1, 0, 0x4440u | s);         // column 4k+4
+                *(uint2*)dA = make_uint2(__byte_perm(w0, 0, 0x4140), __byte_perm(w0, 0, 0x4342));
+                dA[OB] = __byte_perm(w0, 0, 0x4241);
+                dA[OB + 1] = __byte_perm(w0, c4, 0x5453);
+            }
+        }
+        {   // score map = 0 (aprons must be; interior is only written where non-zero)
+            uint4* z = (uint4*)score;
+            const int n4 = ((eh + 2) * SRS + 3) >> 2;
+            for (int i = tid; i < n4; i += FAST_NT) z[i] = make_uint4(0, 0, 0, 0);
+        }
+        if (tid < ORB_FAST_STRIP) s_any[tid] = 0;
+        if (tid < 4) s_ctr[tid] = 0;
+        __syncthreads();
+        if (ci + 1 < ci1) prefetch(ci + 1);                           // overlaps the scoring of this cell row
+
+        // ---- a thread owns a pixel-pair column of the strip and a contiguous run of rows [ya, yb)
+        const int chunk = fast_div(eh + rgc - 1, rgc);
+        const int ya = g * chunk, yb = min(eh, ya + chunk);
+        if (nv) {   // scores
+            const uint32_t* a = tile + aofs + ya * RS;                    // ring row dy = -3 of evaluated row ya
+            uint32_t* sc = score + sofs + (ya + 1) * SRS;
 #pragma unroll 1
-        for (int ly = ya; ly < yb; ++ly, a += RS, sc += SRS) {
-            const uint32_t* b = a + ab;
-            uint32_t E[16];
-            E[0] = b[6 * RS + 1];    //  ( 0, 3)
-            E[1] = a[6 * RS + 2];    //  ( 1, 3)
-            E[2] = b[5 * RS + 2];    //  ( 2, 2)
-            E[3] = a[4 * RS + 3];    //  ( 3, 1)
-            E[4] = a[3 * RS + 3];    //  ( 3, 0)
-            E[5] = a[2 * RS + 3];    //  ( 3,-1)
-            E[6] = b[1 * RS + 2];    //  ( 2,-2)
-            E[7] = a[0 * RS + 2];    //  ( 1,-3)
-            E[8] = b[0 * RS + 1];    //  ( 0,-3)
-            E[9] = a[0 * RS + 1];    //  (-1,-3)
-            E[10] = b[1 * RS + 0];   //  (-2,-2)
-            E[11] = a[2 * RS + 0];   //  (-3,-1)
-            E[12] = a[3 * RS + 0];   //  (-3, 0)
-            E[13] = a[4 * RS + 0];   //  (-3, 1)
-            E[14] = b[5 * RS + 0];   //  (-2, 2)
-            E[15] = a[6 * RS + 1];   //  (-1, 3)
-            const uint32_t v = b[3 * RS + 1];
-            uint32_t M1, M2;
-            fast_network(E, M1, M2);
-            // per 16-bit lane, carry free: bright + 256 = M1 + (256 - v), dark + 256 = (v + 256) - M2
-            const uint32_t br = M1 + (0x01000100u - v), dk = (v + 0x01000100u) - M2;
-            const uint32_t t = hmax2(br, dk);                                   // score + 257
-            const uint32_t out = __viaddmax_s16x2_relu(t, bias, 0u) & lanes;    // max(score - minTh + 1, 0)
-            if (out) *sc = out;
-        }
-    }
-    __syncthreads();
-
-    // ---- strict 3x3 maximum inside each cell: rows slide through registers, 3 loads per pixel pair
-    if (nv) {
-        const int iniBias = plan.iniTh - plan.minTh + 1;               // stored score of a corner at iniThFAST
-        const int c = (int)(e.x >> 22);
-        const uint32_t* sc = score + ((e.x >> 10) & 1023u) + (ya + 1) * SRS;   // row of evaluated row ya
-        uint32_t u0 = sc[-SRS - 1], u1 = sc[-SRS], u2 = sc[-SRS + 1];
-        uint32_t m0 = sc[-1], m1 = sc[0], m2 = sc[1];
-#pragma unroll 3
-        for (int ly = ya; ly < yb; ++ly, sc += SRS) {
-            const uint32_t d0 = sc[SRS - 1], d1 = sc[SRS], d2 = sc[SRS + 1];
-            const uint32_t cw = m1;
-            const uint32_t Lw = __vimax3_s16x2(u0, m0, d0), Rw = __vimax3_s16x2(u2, m2, d2);
-            const uint32_t Uw = hmax2(u1, d1), Cw = hmax2(Uw, cw);
-            // neighbours of (x | x+1): columns (x-1 | x) and (x+1 | x+2) over three rows, own column above/below
-            const uint32_t nb = __vimax3_s16x2(__byte_perm(Lw, Cw, 0x5432), __byte_perm(Cw, Rw, 0x5432), Uw);
-            // lane > neighbour maximum  <=>  bit 15 of (lane + 32768 - nb - 1); lanes stay in 0..65535, no borrow
-            uint32_t keep = ((cw | 0x80008000u) - nb - 0x00010001u) & 0x80008000u;
-            while (keep) {
-                const int hi = (keep & 0x8000u) ? 0 : 1;
-                keep &= hi ? 0u : 0x80000000u;
-                const int r = (int)((cw >> (16 * hi)) & 0xffffu);
-                const int slot = atomicAdd(&s_ctr[0], 1);
-                // border-frame coordinates (src/ORBextractor.cc:868-869): cell-local + (j*wCell, i*hCell)
-                surv[slot] = orb_pack((int)(e.y & 0xffffu) + hi, ly + 3 + ci * L.hCell, r + plan.minTh - 1);
-                const bool isA = r >= iniBias;
-                surv_tag[slot] = (uint16_t)(c | (isA ? 0x8000 : 0));
-                if (isA) s_any[c] = 1;
+            for (int ly = ya; ly < yb; ++ly, a += RS, sc += SRS) {
+                const uint32_t* b = a + ab;
+                uint32_t E[16];
+                E[0] = b[6 * RS + 1];    //  ( 0, 3)
+                E[1] = a[6 * RS + 2];    //  ( 1, 3)
+                E[2] = b[5 * RS + 2];    //  ( 2, 2)
+                E[3] = a[4 * RS + 3];    //  ( 3, 1)
+                E[4] = a[3 * RS + 3];    //  ( 3, 0)
+                E[5] = a[2 * RS + 3];    //  ( 3,-1)
+                E[6] = b[1 * RS + 2];    //  ( 2,-2)
+                E[7] = a[0 * RS + 2];    //  ( 1,-3)
+                E[8] = b[0 * RS + 1];    //  ( 0,-3)
+                E[9] = a[0 * RS + 1];    //  (-1,-3)
+                E[10] = b[1 * RS + 0];   //  (-2,-2)
+                E[11] = a[2 * RS + 0];   //  (-3,-1)
+                E[12] = a[3 * RS + 0];   //  (-3, 0)
+                E[13] = a[4 * RS + 0];   //  (-3, 1)
+                E[14] = b[5 * RS + 0];   //  (-2, 2)
+                E[15] = a[6 * RS + 1];   //  (-1, 3)
+                const uint32_t v = b[3 * RS + 1];
+                uint32_t M1, M2;
+                fast_network(E, M1, M2);
+                // per 16-bit lane, carry free: bright + 256 = M1 + (256 - v), dark + 256 = (v + 256) - M2
+                const uint32_t br = M1 + (0x01000100u - v), dk = (v + 0x01000100u) - M2;
+                const uint32_t t = hmax2(br, dk);                                   // score + 257
+                const uint32_t out = __viaddmax_s16x2_relu(t, bias, 0u) & lanes;    // max(score - minTh + 1, 0)
+                if (out) *sc = out;
             }
-            u0 = m0; u1 = m1; u2 = m2; m0 = d0; m1 = d1; m2 = d2;
         }
-    }
-    __syncthreads();
-    // ---- per-cell cut-off: keep the iniThFAST survivors, or all of them if the cell has none (:857-861)
-    const int nsurv = s_ctr[0];
-    int mykeep = 0;
-    for (int j = tid; j < nsurv; j += FAST_NT) {
-        const int t = surv_tag[j];
-        if ((t & 0x8000) || !s_any[t & 0x7fff]) ++mykeep;
-    }
-    if (mykeep) atomicAdd(&s_ctr[1], mykeep);
-    __syncthreads();
-    const int nkeep = s_ctr[1];
-    if (nkeep == 0) return;
-    if (tid == 0) s_ctr[3] = atomicAdd(&io.cand_count[frame * ORB_MAX_LEVELS + l], nkeep);
-    __syncthreads();
-    const int base = s_ctr[3];
-    uint32_t* out = io.cand + (size_t)frame * plan.cand_per_frame + L.cand_off;
-    for (int j = tid; j < nsurv; j += FAST_NT) {
-        const int t = surv_tag[j];
-        if ((t & 0x8000) || !s_any[t & 0x7fff]) {
-            const int slot = base + atomicAdd(&s_ctr[2], 1);
-            if (slot < L.cand_cap) out[slot] = surv[j];
+        __syncthreads();
+
+        // ---- strict 3x3 maximum inside each cell: rows slide through registers, 3 loads per pixel pair.
+        // The loop only records WHICH lanes survive (2 bits per row); the rare survivors are pushed afterwards.
+        if (nv) {
+            const uint32_t* sc = score + sofs + (ya + 1) * SRS;           // row of evaluated row ya
+            uint32_t u0 = sc[-SRS - 1], u1 = sc[-SRS], u2 = sc[-SRS + 1];
+            uint32_t m0 = sc[-1], m1 = sc[0], m2 = sc[1];
+            for (int yq = ya; yq < yb; yq += 32) {                        // 2 bits per row in a 64-bit mask
+                const int ye = min(yb, yq + 32);
+                unsigned long long kept = 0;
+#pragma unroll 3
+                for (int ly = yq; ly < ye; ++ly, sc += SRS) {
+                    const uint32_t d0 = sc[SRS - 1], d1 = sc[SRS], d2 = sc[SRS + 1];
+                    const uint32_t Lw = __vimax3_s16x2(u0, m0, d0), Rw = __vimax3_s16x2(u2, m2, d2);
+                    const uint32_t Uw = hmax2(u1, d1), Cw = hmax2(Uw, m1);
+                    // neighbours of (x | x+1): columns (x-1 | x) and (x+1 | x+2) over three rows, own column above/below
+                    const uint32_t nb = __vimax3_s16x2(__byte_perm(Lw, Cw, 0x5432), __byte_perm(Cw, Rw, 0x5432), Uw);
+                    // lane > neighbour maximum  <=>  bit 15 of (lane + 32768 - nb - 1); lanes stay in 0..65535, no borrow
+                    const uint32_t keep = ((m1 | 0x80008000u) - nb - 0x00010001u) & 0x80008000u;
+                    kept = (kept << 2) | ((keep >> 15) & 1u) | (keep >> 30);
+                    u0 = m0; u1 = m1; u2 = m2; m0 = d0; m1 = d1; m2 = d2;
+                }
+                // kept: row ye-1 in bits 0..1, row ye-2 in bits 2..3, ...; sc is now the row of evaluated row ye
+                while (kept) {
+                    const int bit = __ffsll((long long)kept) - 1;
+                    kept &= kept - 1;
+                    const int back = bit >> 1, hi = bit & 1;
+                    const int r = (int)((sc[-(back + 1) * SRS] >> (16 * hi)) & 0xffffu);
+                    const int slot = atomicAdd(&s_ctr[0], 1);
+                    // border-frame coordinates (src/ORBextractor.cc:868-869): cell-local + (j*wCell, i*hCell)
+                    surv[slot] = orb_pack(xb + hi, ye - 1 - back + 3 + ci * hc, r + plan.minTh - 1);
+                    const bool isA = r >= iniBias;
+                    surv_tag[slot] = (uint16_t)(c | (isA ? 0x8000 : 0));
+                    if (isA) s_any[c] = 1;
+                }
+            }
         }
+        __syncthreads();
+        // ---- per-cell cut-off: keep the iniThFAST survivors, or all of them if the cell has none (:857-861)
+        const int nsurv = s_ctr[0];
+        int mykeep = 0;
+        for (int j = tid; j < nsurv; j += FAST_NT) {
+            const int t = surv_tag[j];
+            if ((t & 0x8000) || !s_any[t & 0x7fff]) ++mykeep;
+        }
+        if (mykeep) atomicAdd(&s_ctr[1], mykeep);
+        __syncthreads();
+        const int nkeep = s_ctr[1];
+        if (nkeep) {
+            if (tid == 0) s_ctr[3] = atomicAdd(&io.cand_count[frame * ORB_MAX_LEVELS + l], nkeep);
+            __syncthreads();
+            const int base = s_ctr[3];
+            uint32_t* out = io.cand + (size_t)frame * plan.cand_per_frame + L.cand_off;
+            for (int j = tid; j < nsurv; j += FAST_NT) {
+                const int t = surv_tag[j];
+                if ((t & 0x8000) || !s_any[t & 0x7fff]) {
+                    const int slot = base + atomicAdd(&s_ctr[2], 1);
+                    if (slot < L.cand_cap) out[slot] = surv[j];
+                }
+            }
+        }
+        __syncthreads();                                              // the next cell row reuses everything
     }
 }
 
-__global__ void __launch_bounds__(FAST_NT) k_fast_strips(const __grid_constant__ OrbPlan plan, const OrbBatch io)
+__global__ void __launch_bounds__(FAST_NT) k_fast_strips(const __grid_constant__ OrbPlan plan, const OrbBatch io, const __grid_constant__ FastGrid fg)
 {
     extern __shared__ __align__(16) uint32_t smem[];
-    __shared__ uint2 s_col[FAST_NT];
     __shared__ int s_ctr[4], s_any[ORB_FAST_STRIP];
     int l = 0;
-    while (l + 1 < plan.nlevels && (int)blockIdx.x >= plan.lv[l + 1].strip_first) ++l;
-    const int strip = blockIdx.x - plan.lv[l].strip_first;
+    while (l + 1 < plan.nlevels && (int)blockIdx.x >= fg.first[l + 1]) ++l;
+    const int idx = blockIdx.x - fg.first[l];
+    const int spr = plan.lv[l].spr;
+    const int rb = fast_div(idx, spr), sx = idx - rb * spr;
+    const int ci0 = rb * fg.rows_per_block, ci1 = min(plan.lv[l].ncy, ci0 + fg.rows_per_block);
     if (plan.lv[l].wCell <= ORB_FAST_WC_STATIC)
-        fast_strip_body<true>(plan, io, smem, s_col, s_ctr, s_any, blockIdx.y, l, strip);
+        fast_strip_body<true>(plan, io, smem, s_ctr, s_any, blockIdx.y, l, sx, ci0, ci1);
     else
-        fast_strip_body<false>(plan, io, smem, s_col, s_ctr, s_any, blockIdx.y, l, strip);
+        fast_strip_body<false>(plan, io, smem, s_ctr, s_any, blockIdx.y, l, sx, ci0, ci1);
 }
 
 size_t orb_fast_smem_bytes(const OrbPlan& plan)
 {
-    return ((size_t)plan.fast_tile_words + plan.fast_score_words) * 4 + (size_t)plan.fast_surv_max * 2 + 32;
+    return ((size_t)plan.fast_tile_words + plan.fast_score_words + ((plan.fast_surv_max + 1) >> 1) + plan.fast_raw_words) * 4 + 32;
 }
 
 cudaError_t orb_launch_fast(const OrbPlan& plan, const OrbBatch& io, int batch, cudaStream_t st)
@@ -300,6 +336,19 @@ cudaError_t orb_launch_fast(const OrbPlan& plan, const OrbBatch& io, int batch, 
         cudaError_t e = cudaFuncSetAttribute(k_fast_strips, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    k_fast_strips<<<dim3(plan.total_strips, batch), FAST_NT, smem, st>>>(plan, io);
+    // Cell rows per block: whole strip columns once the batch alone fills the GPU several times over (the
+    // per-column setup is then paid once per column), single cell rows for a few frames (latency).
+    int maxrows = 1;
+    for (int l = 0; l < plan.nlevels; ++l) if (plan.lv[l].ncy > maxrows) maxrows = plan.lv[l].ncy;
+    FastGrid fg;
+    fg.rows_per_block = batch >= 64 ? maxrows : batch >= 16 ? 4 : 1;
+    int n = 0;
+    for (int l = 0; l < plan.nlevels; ++l) {
+        fg.first[l] = n;
+        n += plan.lv[l].spr * ((plan.lv[l].ncy + fg.rows_per_block - 1) / fg.rows_per_block);
+    }
+    for (int l = plan.nlevels; l <= ORB_MAX_LEVELS; ++l) fg.first[l] = n;
+    if (n == 0) return cudaSuccess;
+    k_fast_strips<<<dim3(n, batch), FAST_NT, smem, st>>>(plan, io, fg);
     return cudaGetLastError();
 }

@@ -129,6 +129,8 @@ int orb_plan_build(const OrbParams* p, int w, int h, OrbPlan* plan, std::vector<
             if (tile > plan->fast_tile_words) plan->fast_tile_words = tile;
             if (score > plan->fast_score_words) plan->fast_score_words = score;
             if (surv > plan->fast_surv_max) plan->fast_surv_max = surv;
+            const int rawW = (L.hCell + 6) * (L.wCell <= ORB_FAST_WC_STATIC ? ORB_FAST_RW_STATIC : orb_fast_rw(ncs, L.wCell));
+            if (rawW > plan->fast_raw_words) plan->fast_raw_words = rawW;
             if (surv > tile || ncs * np > 32 * ORB_FAST_STRIP || rs >= 1024) return 1;  // survivors reuse the tile; table / offset widths
             // order key (cell, y-in-cell, x-in-cell) must fit 24 bits
             if ((long long)L.ncx * L.ncy * L.wCell * L.hCell >= (1 << 24)) return 1;

@@ -22,6 +22,7 @@
 #define ORB_FAST_STRIP 4     // cells per FAST block (orb_fast.cu); the block has 32 threads per cell
 #define ORB_FAST_WC_STATIC 32    // widest cell handled with compile-time tile geometry
 #define ORB_FAST_WPC_STATIC (((ORB_FAST_STRIP * ORB_FAST_WC_STATIC + 9) / 2 + 2) & ~1)   // orb_fast_wpc(ORB_FAST_STRIP, 32)
+#define ORB_FAST_RW_STATIC (((ORB_FAST_STRIP * ORB_FAST_WC_STATIC + 15) >> 2) + 1)            // orb_fast_rw(ORB_FAST_STRIP, 32)
 #define ORB_BLUR_TW 120      // blur tile (orb_dense.cu): 120 output pixels = 32 staged words incl. the 3-px apron
 #define ORB_BLUR_TH 32
 
@@ -66,6 +67,7 @@ struct OrbPlan {
     int fast_eval_max;      // largest evaluated area of a cell (pixels)
     int fast_score_words;   // largest strip score map in 32-bit words, multiple of 4
     int fast_surv_max;      // largest possible number of NMS survivors in a strip
+    int fast_raw_words;     // largest fetched strip image in 32-bit words
     int umax[ORB_HALF_PATCH + 1]; // row half-widths of the orientation patch
     uint32_t pyr_bytes;     // bytes of one frame's pyramid block (levels 1..)
     uint32_t blur_bytes;    // bytes of one frame's blur block (levels 0..)
@@ -75,6 +77,8 @@ struct OrbPlan {
 // FAST strip tile (orb_fast.cu): 32-bit words per row of ONE of the two 16-bit copies of a strip of ncs
 // cells of width wc.  Strip columns 0 .. ncs*wc+7 are read; a word holds two columns; even count.
 static inline __host__ __device__ int orb_fast_wpc(int ncs, int wc) { return (((ncs * wc + 8 + 1) >> 1) + 1 + 1) & ~1; }
+// image words fetched per strip row (from the aligned address at or below the first pixel)
+static inline __host__ __device__ int orb_fast_rw(int ncs, int wc) { return ((ncs * wc + 15) >> 2) + 1; }
 // word offset of the second copy inside a tile row: the first value >= wpc that is 1 (mod 32) (bank spreading)
 static inline __host__ __device__ int orb_fast_ob(int wpc) { return ((wpc + 30) & ~31) + 1; }
 
