@@ -3,10 +3,10 @@
 //   k_blur7        GaussianBlur 7x7 sigma 2  src/ORBextractor.cc:1129-1130
 //   k_border       REFLECT_101 border of mvImagePyramid               src/ORBextractor.cc:1168-1174
 // Integer / byte arithmetic only; results are bit-identical to OpenCV 4.13.
-// Both filters are separable and staged through shared memory; on this part they are bound by
-// instruction issue (ncu: ALU pipe ~70 %), not by HBM, so the kernels are organised to spend as
-// few instructions per pixel as possible: index math is hoisted per thread, the 8-bit pass of
-// the blur runs on packed 16x2 lanes (two pixels per IMAD), and every store is a 32-bit word.
+// Both filters are separable; on this part they are bound by instruction issue before HBM, so
+// the kernels are organised to spend as few instructions per pixel as possible: index math is
+// hoisted per thread, the 8-bit pass of the blur runs on packed 16x2 lanes (two pixels per
+// IMAD), its 16-bit pass on IDP.2A, and every store is a 32-bit word.
 #include "orb_device.cuh"
 #include "orb_launch.h"
 
@@ -108,91 +108,102 @@ __global__ void __launch_bounds__(256) k_pyr_resize_generic(const __grid_constan
 // ------------------------------------------------------------------------------ blur
 // Separable fixed-point Gaussian, kernel {18,34,48,56,48,34,18}/256 per axis, one rounding
 // (acc + 2^15) >> 16 at the end; REFLECT_101 at the level's own edges (the reference blurs a
-// clone of the ROI).  A block produces an ORB_BLUR_TW x ORB_BLUR_TH tile:
-//   stage   (TH+6) rows x 32 words (pixels tx0-4 .. tx0+123), a lane owns one word column;
-//   column pass on the BYTES first: sums <= 255*256 fit 16 bits, so two pixels share one
-//           register lane pair and one IMAD advances both (no carry between the halves);
-//   row pass on the 16-bit sums with 32-bit accumulators, 4 pixels per thread from a sliding
-//           window of 12 values, one 32-bit store.
+// clone of the ROI).  No shared memory and no barriers: a WARP owns a column of ORB_BLUR_TW
+// output pixels (lane = 4 adjacent pixels; lanes 0 and 31 only carry the 3-px apron) and walks
+// down ORB_BLUR_TH rows:
+//   load    one 32-bit word per lane and row, issued 7 rows ahead of its use;
+//   column pass on the BYTES first: the 7 rows slide through registers as packed 16x2 lanes
+//           (sums <= 255*256 fit 16 bits, no carry between the halves), one IMAD advances two pixels;
+//   row pass on the 16-bit column sums: the neighbours' sums arrive by shuffle, and each output is
+//           four IDP.2A (two 16-bit sums x two 8-bit weights + accumulate, rounding constant folded in);
+//   store   one 32-bit word per lane and row.
 // (Column-then-row equals row-then-column: the sums are exact integers.)
-#define BLUR_NT 256
-#define BLUR_IW 32   // staged words per row
+#define BLUR_NT 128
+
+__device__ __forceinline__ uint32_t dp2a_lo(const uint32_t a, const uint32_t b, const uint32_t c)
+{
+    uint32_t d;
+    asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t dp2a_hi(const uint32_t a, const uint32_t b, const uint32_t c)
+{
+    uint32_t d;
+    asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
 
 __global__ void __launch_bounds__(BLUR_NT) k_blur7(const __grid_constant__ OrbPlan plan, const OrbBatch io)
 {
-    __shared__ uint32_t s_in[(ORB_BLUR_TH + 6) * BLUR_IW];
-    __shared__ __align__(8) uint32_t s_v[ORB_BLUR_TH * 2 * BLUR_IW];   // column-pass sums, 16-bit, two per word
-    const int frame = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int frame = blockIdx.y, lane = threadIdx.x & 31;
+    const int wt = blockIdx.x * (BLUR_NT / 32) + (threadIdx.x >> 5);       // this warp's tile within the frame
+    if (wt >= plan.total_blur_tiles) return;
     int l = 0;
-    while (l + 1 < plan.nlevels && (int)blockIdx.x >= plan.lv[l + 1].blur_tile_first) ++l;
+    while (l + 1 < plan.nlevels && wt >= plan.lv[l + 1].blur_tile_first) ++l;
     const OrbLevel& L = plan.lv[l];
-    const int t = blockIdx.x - L.blur_tile_first;
-    const int tyi = t / L.blur_tiles_x;
-    const int tx0 = (t - tyi * L.blur_tiles_x) * ORB_BLUR_TW, ty0 = tyi * ORB_BLUR_TH;
+    const int t = wt - L.blur_tile_first;
+    const int tyi = __float2int_rz(__fmul_rn((float)t + 0.5f, __frcp_rn((float)L.blur_tiles_x)));
+    const int tx0 = (t - tyi * L.blur_tiles_x) * ORB_BLUR_TW, yb = tyi * ORB_BLUR_TH;
     int pitch;
-    const uint8_t* src = orb_level_ptr(plan, io, frame, l, &pitch);
+    const uint8_t* __restrict__ src = orb_level_ptr(plan, io, frame, l, &pitch);
     const int w = L.w, h = L.h;
+    const int ye = min(yb + ORB_BLUR_TH, h);
+    // columns: lane owns pixels x .. x+3.  Columns more than 3 px outside the image only feed outputs that are
+    // never stored, so indices are clamped to [-3, w+2] first and ONE reflection is enough (w >= 4 holds here).
+    const int x = tx0 - 4 + 4 * lane;
+    const bool fast = x >= 0 && x + 7 < w;
+    int xr[4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        int i = min(max(x + b, -3), w + 2);
+        i = i < 0 ? -i : i;
+        xr[b] = i >= w ? 2 * (w - 1) - i : i;
+    }
+    auto load_row = [&](int y) -> uint32_t {                              // y in [-3, h+2]
+        y = abs(y);
+        y = min(y, 2 * (h - 1) - y);
+        const uint8_t* row = src + (size_t)y * pitch;
+        if (fast) return orb_ld_u32_unaligned(row + x);
+        return (uint32_t)__ldg(row + xr[0]) | ((uint32_t)__ldg(row + xr[1]) << 8) | ((uint32_t)__ldg(row + xr[2]) << 16) |
+               ((uint32_t)__ldg(row + xr[3]) << 24);
+    };
+    // weights as bytes for IDP.2A: .lo uses bytes 0-1, .hi bytes 2-3
+    const uint32_t W0 = 0x30221200u, W1 = 0x12223038u, W2 = 0x38302212u, W3 = 0x00122230u;
+    uint8_t* __restrict__ out = io.blur + (size_t)frame * plan.blur_bytes + L.blur_off + (size_t)yb * L.pitch + x;
+    const bool writer = lane >= 1 && lane <= ORB_BLUR_TW / 4 && x < w;
 
-    {   // stage: lane = word column (pixels x .. x+3), warps walk down the rows.  Columns / rows more than
-        // 3 px outside the image only feed outputs that are never stored, so indices are clamped to
-        // [-3, n+2] first and ONE reflection is enough (n >= 4 always holds here).
-        const int x = tx0 - 4 + 4 * lane;
-        const bool fast = x >= 0 && x + 7 < w;
-        int xr[4];
+    uint32_t lo[7], hi[7], raw[7];
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            int i = min(max(x + b, -3), w + 2);
-            i = i < 0 ? -i : i;
-            xr[b] = i >= w ? 2 * (w - 1) - i : i;
-        }
-        for (int r = warp; r < ORB_BLUR_TH + 6; r += BLUR_NT / 32) {
-            int y = min(max(ty0 - 3 + r, -3), h + 2);
-            y = y < 0 ? -y : y;
-            y = y >= h ? 2 * (h - 1) - y : y;
-            const uint8_t* row = src + (size_t)y * pitch;
-            uint32_t v;
-            if (fast) v = orb_ld_u32_unaligned(row + x);
-            else v = (uint32_t)__ldg(row + xr[0]) | ((uint32_t)__ldg(row + xr[1]) << 8) | ((uint32_t)__ldg(row + xr[2]) << 16) | ((uint32_t)__ldg(row + xr[3]) << 24);
-            s_in[r * BLUR_IW + lane] = v;
-        }
+    for (int i = 0; i < 6; ++i) {                                          // rows yb-3 .. yb+2
+        const uint32_t v = load_row(yb - 3 + i);
+        lo[i] = __byte_perm(v, 0, 0x4140);
+        hi[i] = __byte_perm(v, 0, 0x4342);
     }
-    __syncthreads();
-    {   // column pass: (word column = lane, block of 4 output rows = warp)
-        uint32_t lo[10], hi[10];
 #pragma unroll
-        for (int i = 0; i < 10; ++i) {
-            const uint32_t v = s_in[(4 * warp + i) * BLUR_IW + lane];
-            lo[i] = __byte_perm(v, 0, 0x4140);   // (p0, p1) as 16-bit lanes
-            hi[i] = __byte_perm(v, 0, 0x4342);   // (p2, p3)
-        }
+    for (int i = 0; i < 7; ++i) raw[i] = yb + 3 + i <= ye + 2 ? load_row(yb + 3 + i) : 0u;   // rows yb+3 .. yb+9
+    for (int y7 = yb; y7 < ye; y7 += 7) {
 #pragma unroll
-        for (int o = 0; o < 4; ++o) {
-            uint2 r;
-            r.x = 18u * (lo[o] + lo[o + 6]) + 34u * (lo[o + 1] + lo[o + 5]) + 48u * (lo[o + 2] + lo[o + 4]) + 56u * lo[o + 3];
-            r.y = 18u * (hi[o] + hi[o + 6]) + 34u * (hi[o + 1] + hi[o + 5]) + 48u * (hi[o + 2] + hi[o + 4]) + 56u * hi[o + 3];
-            *(uint2*)&s_v[(4 * warp + o) * (2 * BLUR_IW) + 2 * lane] = r;
-        }
-    }
-    __syncthreads();
-    // row pass: group g = output pixels tx0+4g .. +3 = staged columns 4g+4 .. 4g+7; window = columns 4g+1 .. 4g+10
-    uint8_t* dst = io.blur + (size_t)frame * plan.blur_bytes + L.blur_off;
-    // lane = group (30 of 32 lanes busy), warps walk down the rows: no division, addresses advance by a pitch
-    if (lane < ORB_BLUR_TW / 4 && tx0 + 4 * lane < L.pitch) {
-        const int g = lane;
-        uint8_t* out = dst + (size_t)(ty0 + warp) * L.pitch + tx0 + 4 * g;
-        const int rmax = min(ORB_BLUR_TH, h - ty0);
-        for (int r = warp; r < rmax; r += BLUR_NT / 32, out += (size_t)(BLUR_NT / 32) * L.pitch) {
-            const uint2* pv = (const uint2*)&s_v[r * (2 * BLUR_IW) + 2 * g];
-            const uint2 q0 = pv[0], q1 = pv[1], q2 = pv[2];
-            uint32_t v[12];
-            v[0] = q0.x & 0xffffu; v[1] = q0.x >> 16; v[2] = q0.y & 0xffffu; v[3] = q0.y >> 16;
-            v[4] = q1.x & 0xffffu; v[5] = q1.x >> 16; v[6] = q1.y & 0xffffu; v[7] = q1.y >> 16;
-            v[8] = q2.x & 0xffffu; v[9] = q2.x >> 16; v[10] = q2.y & 0xffffu; v[11] = q2.y >> 16;
-            uint32_t o[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                o[j] = (18u * (v[j + 1] + v[j + 7]) + 34u * (v[j + 2] + v[j + 6]) + 48u * (v[j + 3] + v[j + 5]) + 56u * v[j + 4] + 32768u) >> 16;
-            *(uint32_t*)out = o[0] | (o[1] << 8) | (o[2] << 16) | (o[3] << 24);
+        for (int u = 0; u < 7; ++u) {
+            const int y = y7 + u;
+            if (y >= ye) break;
+#define SL(i) ((u + (i)) % 7)
+            // row y-3+i sits in slot SL(i); the new row y+3 was fetched 7 iterations ago
+            lo[SL(6)] = __byte_perm(raw[u], 0, 0x4140);
+            hi[SL(6)] = __byte_perm(raw[u], 0, 0x4342);
+            if (y + 10 <= ye + 2) raw[u] = load_row(y + 10);
+            const uint32_t vlo = 18u * (lo[SL(0)] + lo[SL(6)]) + 34u * (lo[SL(1)] + lo[SL(5)]) + 48u * (lo[SL(2)] + lo[SL(4)]) + 56u * lo[SL(3)];
+            const uint32_t vhi = 18u * (hi[SL(0)] + hi[SL(6)]) + 34u * (hi[SL(1)] + hi[SL(5)]) + 48u * (hi[SL(2)] + hi[SL(4)]) + 56u * hi[SL(3)];
+#undef SL
+            // column sums of pixels x-4..x-1 (left lane) and x+4..x+7 (right lane)
+            const uint32_t llo = __shfl_up_sync(0xffffffffu, vlo, 1), lhi = __shfl_up_sync(0xffffffffu, vhi, 1);
+            const uint32_t rlo = __shfl_down_sync(0xffffffffu, vlo, 1), rhi = __shfl_down_sync(0xffffffffu, vhi, 1);
+            // out(x+j) = 18 s[j-3] + 34 s[j-2] + 48 s[j-1] + 56 s[j] + 48 s[j+1] + 34 s[j+2] + 18 s[j+3] + 2^15
+            const uint32_t o0 = dp2a_hi(vhi, W1, dp2a_lo(vlo, W1, dp2a_hi(lhi, W0, dp2a_lo(llo, W0, 32768u))));
+            const uint32_t o1 = dp2a_hi(rlo, W3, dp2a_lo(vhi, W3, dp2a_hi(vlo, W2, dp2a_lo(lhi, W2, 32768u))));
+            const uint32_t o2 = dp2a_hi(rlo, W1, dp2a_lo(vhi, W1, dp2a_hi(vlo, W0, dp2a_lo(lhi, W0, 32768u))));
+            const uint32_t o3 = dp2a_hi(rhi, W3, dp2a_lo(rlo, W3, dp2a_hi(vhi, W2, dp2a_lo(vlo, W2, 32768u))));
+            if (writer) *(uint32_t*)out = __byte_perm(__byte_perm(o0, o1, 0x0062), __byte_perm(o2, o3, 0x0062), 0x5410);
+            out += L.pitch;
         }
     }
 }
@@ -227,7 +238,7 @@ cudaError_t orb_launch_pyramid(const OrbPlan& plan, const OrbBatch& io, int batc
 
 cudaError_t orb_launch_blur(const OrbPlan& plan, const OrbBatch& io, int batch, cudaStream_t st)
 {
-    k_blur7<<<dim3(plan.total_blur_tiles, batch), BLUR_NT, 0, st>>>(plan, io);
+    k_blur7<<<dim3((plan.total_blur_tiles + BLUR_NT / 32 - 1) / (BLUR_NT / 32), batch), BLUR_NT, 0, st>>>(plan, io);
     return cudaGetLastError();
 }
 

@@ -23,8 +23,8 @@
 #define ORB_FAST_WC_STATIC 32    // widest cell handled with compile-time tile geometry
 #define ORB_FAST_WPC_STATIC (((ORB_FAST_STRIP * ORB_FAST_WC_STATIC + 9) / 2 + 2) & ~1)   // orb_fast_wpc(ORB_FAST_STRIP, 32)
 #define ORB_FAST_RW_STATIC (((ORB_FAST_STRIP * ORB_FAST_WC_STATIC + 15) >> 2) + 1)            // orb_fast_rw(ORB_FAST_STRIP, 32)
-#define ORB_BLUR_TW 120      // blur tile (orb_dense.cu): 120 output pixels = 32 staged words incl. the 3-px apron
-#define ORB_BLUR_TH 32
+#define ORB_BLUR_TW 120      // blur tile (orb_dense.cu): a warp makes 120 output pixels per row (30 lanes x 4 + 2 apron lanes)
+#define ORB_BLUR_TH 64       // ... and walks down this many rows
 
 struct OrbLevel {
     int w, h;               // level image size
