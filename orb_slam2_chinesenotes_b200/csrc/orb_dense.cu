@@ -10,64 +10,124 @@
 #include "orb_device.cuh"
 #include "orb_launch.h"
 
+__device__ __forceinline__ uint32_t dp2a_lo(const uint32_t a, const uint32_t b, const uint32_t c)
+{
+    uint32_t d;
+    asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t dp2a_hi(const uint32_t a, const uint32_t b, const uint32_t c)
+{
+    uint32_t d;
+    asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
 // ------------------------------------------------------------------------------ pyramid
 // cv::resize INTER_LINEAR on 8U (OpenCV HResizeLinear / VResizeLinear<uchar,int,short>):
 //   H(r,x)   = s[r][ofs]*a0 + s[r][ofs+1]*a1            (11-bit weights, int32)
 //   dst(y,x) = ( ((b0*(H(r0,x)>>4))>>16) + ((b1*(H(r1,x)>>4))>>16) + 2 ) >> 2
-// A block makes a PYR_TW x PYR_TH tile: first the horizontal pass for the source rows the tile
-// needs (a thread owns one destination column, so its tap is loaded once), stored as H>>4 in
-// 16 bits; then the vertical pass, 4 pixels per thread, one 32-bit store.
+// No shared memory and no barriers: a WARP owns a column of 128 destination pixels (lane = 4
+// adjacent pixels) and walks down PYR_TH destination rows.
+//   horizontal pass of ONE source row: the lane's 8 taps lie in 8 consecutive source bytes (scale <= 1.25);
+//           they are fetched as aligned words, funnel-shifted to the lane's first tap, permuted into two
+//           (p0,p0+1,p1,p1+1) byte quads (selectors fixed per lane), and each H is one IDP.2A with the
+//           (a0,a1) pair as the 16-bit operand;
+//   vertical pass: consecutive destination rows share a source row four times out of five, so the two H rows
+//           live in registers and only the new one is computed; (b*h)>>16 is IMAD.HI with b pre-shifted.
+#define PYR_NT 128
 #define PYR_TW 128
-#define PYR_TH 16
-#define PYR_NT 256
-#define PYR_ROWS (2 * PYR_TH + 3)   // source rows per tile for scale factors up to 2
+#define PYR_TH 64
 
-__global__ void __launch_bounds__(PYR_NT) k_pyr_resize(const __grid_constant__ OrbPlan plan, const OrbBatch io, const int l)
+__device__ __forceinline__ uint32_t mad_hi(const uint32_t a, const uint32_t b, const uint32_t c)
 {
-    __shared__ __align__(8) uint32_t s_h[PYR_ROWS * (PYR_TW / 2)];   // (H >> 4) as 16-bit, two per word
-    const int frame = blockIdx.z, tid = threadIdx.x;
+    uint32_t d;
+    asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+__global__ void __launch_bounds__(PYR_NT) k_pyr_resize(const __grid_constant__ OrbPlan plan, const OrbBatch io, const int l, const int th)
+{
+    const int frame = blockIdx.z, lane = threadIdx.x & 31;
     const OrbLevel& D = plan.lv[l];
     const OrbLevel& S = plan.lv[l - 1];
-    const int tx0 = blockIdx.x * PYR_TW, ty0 = blockIdx.y * PYR_TH;
+    const int tiles_x = (D.w + PYR_TW - 1) / PYR_TW, tiles_y = (D.h + th - 1) / th;
+    const int wt = blockIdx.x * (PYR_NT / 32) + (threadIdx.x >> 5);
+    if (wt >= tiles_x * tiles_y) return;
+    const int tyi = __float2int_rz(__fmul_rn((float)wt + 0.5f, __frcp_rn((float)tiles_x)));
+    const int d0 = (wt - tyi * tiles_x) * PYR_TW + 4 * lane;              // first destination column of the lane
+    const int yb = tyi * th, ye = min(yb + th, D.h);
     int spitch;
-    const uint8_t* src = orb_level_ptr(plan, io, frame, l - 1, &spitch);
-    const int2* xtab = (const int2*)io.taps + D.xtab;
-    const int2* ytab = (const int2*)io.taps + D.ytab;
-    const int ylast = min(ty0 + PYR_TH, D.h) - 1;
-    const int rs0 = __ldg(&ytab[ty0]).x;
-    const int rs1 = min(__ldg(&ytab[ylast]).x + 1, S.h - 1);
-    const int nrows = rs1 - rs0 + 1;                     // <= PYR_ROWS (checked by the launcher)
-    {   // horizontal pass
-        const int c = tid & (PYR_TW - 1);
-        const int2 t = __ldg(&xtab[min(tx0 + c, D.w - 1)]);
-        const int sx0 = t.x, sx1 = min(t.x + 1, S.w - 1);
-        const int a0 = t.y & 0xffff, a1 = (int)((uint32_t)t.y >> 16);
-        const uint8_t* p = src + (size_t)rs0 * spitch;
-        uint16_t* hs = (uint16_t*)s_h;
-        for (int r = tid / PYR_TW; r < nrows; r += PYR_NT / PYR_TW) {
-            const uint8_t* row = p + (size_t)r * spitch;
-            const int H = (int)__ldg(row + sx0) * a0 + (int)__ldg(row + sx1) * a1;
-            hs[r * PYR_TW + c] = (uint16_t)(H >> 4);
-        }
+    const uint8_t* __restrict__ src = orb_level_ptr(plan, io, frame, l - 1, &spitch);
+    const int2* __restrict__ xtab = (const int2*)io.taps + D.xtab;
+    const int2* __restrict__ ytab = (const int2*)io.taps + D.ytab;
+    const int sw = S.w, sh = S.h, dw = D.w, dpitch = D.pitch;
+    if (d0 >= dw) return;                                                  // no warp-wide operation below
+    // ---- column setup: taps of the 4 destination pixels relative to the first one
+    uint32_t C[4];
+    int rel[4];
+    const int2 t0 = __ldg(&xtab[min(d0, dw - 1)]);
+    const int sx0 = t0.x;
+    C[0] = (uint32_t)t0.y; rel[0] = 0;
+#pragma unroll
+    for (int j = 1; j < 4; ++j) {
+        const int2 t = __ldg(&xtab[min(d0 + j, dw - 1)]);
+        C[j] = (uint32_t)t.y; rel[j] = min(t.x - sx0, 6);
     }
-    __syncthreads();
-    uint8_t* dst = io.pyr + (size_t)frame * plan.pyr_bytes + D.img_off;
-    const int g = tid & 31;                              // 4-pixel group
-    const int x = tx0 + 4 * g;
-    if (x >= D.pitch) return;
-    for (int yy = tid >> 5; yy < PYR_TH; yy += PYR_NT / 32) {
-        const int y = ty0 + yy;
-        if (y >= D.h) break;
-        const int2 t = __ldg(&ytab[y]);
-        const int r0 = t.x - rs0, r1 = min(t.x + 1, S.h - 1) - rs0;
-        const int b0 = t.y & 0xffff, b1 = (int)((uint32_t)t.y >> 16);
-        const uint2 h0 = *(const uint2*)&s_h[r0 * (PYR_TW / 2) + 2 * g];
-        const uint2 h1 = *(const uint2*)&s_h[r1 * (PYR_TW / 2) + 2 * g];
-        const int v0 = (((b0 * (int)(h0.x & 0xffffu)) >> 16) + ((b1 * (int)(h1.x & 0xffffu)) >> 16) + 2) >> 2;
-        const int v1 = (((b0 * (int)(h0.x >> 16)) >> 16) + ((b1 * (int)(h1.x >> 16)) >> 16) + 2) >> 2;
-        const int v2 = (((b0 * (int)(h0.y & 0xffffu)) >> 16) + ((b1 * (int)(h1.y & 0xffffu)) >> 16) + 2) >> 2;
-        const int v3 = (((b0 * (int)(h0.y >> 16)) >> 16) + ((b1 * (int)(h1.y >> 16)) >> 16) + 2) >> 2;
-        *(uint32_t*)(dst + (size_t)y * D.pitch + x) = (uint32_t)v0 | ((uint32_t)v1 << 8) | ((uint32_t)v2 << 16) | ((uint32_t)v3 << 24);
+    const uint32_t selA = (uint32_t)(rel[0] | ((rel[0] + 1) << 4) | (rel[1] << 8) | ((rel[1] + 1) << 12));
+    const uint32_t selB = (uint32_t)(rel[2] | ((rel[2] + 1) << 4) | (rel[3] << 8) | ((rel[3] + 1) << 12));
+    // bytes sx0 .. sx0+7 are fetched through three aligned words; lanes that would run past the row's last
+    // pixel (right edge) gather clamped bytes instead
+    const bool fast = sx0 + 12 <= sw;
+    auto hrow = [&](const int r, uint32_t* H) {
+        const uint8_t* row = src + (size_t)r * spitch;
+        uint32_t w0, w1;
+        if (fast) {
+            const uintptr_t a = (uintptr_t)(row + sx0);
+            const uint32_t sft = 8u * (uint32_t)(a & 3);
+            const uint32_t* q = (const uint32_t*)(a & ~(uintptr_t)3);
+            const uint32_t q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
+            w0 = __funnelshift_r(q0, q1, sft);
+            w1 = __funnelshift_r(q1, q2, sft);
+        } else {
+            uint32_t b[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) b[i] = __ldg(row + min(sx0 + i, sw - 1));
+            w0 = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
+            w1 = b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24);
+        }
+        const uint32_t A = __byte_perm(w0, w1, selA), B = __byte_perm(w0, w1, selB);
+        H[0] = dp2a_lo(C[0], A, 0u) >> 4;
+        H[1] = dp2a_hi(C[1], A, 0u) >> 4;
+        H[2] = dp2a_lo(C[2], B, 0u) >> 4;
+        H[3] = dp2a_hi(C[3], B, 0u) >> 4;
+    };
+    uint8_t* __restrict__ out = io.pyr + (size_t)frame * plan.pyr_bytes + D.img_off + (size_t)yb * dpitch + d0;
+    uint32_t Ha[4], Hb[4];
+    int ra = -1, rb = -1;                                                  // source rows held in Ha / Hb
+    int2 ty = __ldg(&ytab[yb]);
+    for (int y = yb; y < ye; ++y, out += dpitch) {
+        const int r0 = ty.x, r1 = min(r0 + 1, sh - 1);
+        const uint32_t b0s = (uint32_t)ty.y << 16, b1s = (uint32_t)ty.y & 0xffff0000u;
+        if (y + 1 < ye) ty = __ldg(&ytab[y + 1]);
+        if (r0 != ra) {
+            if (r0 == rb) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) Ha[j] = Hb[j];
+            } else hrow(r0, Ha);
+            ra = r0;
+        }
+        if (r1 != rb) {
+            if (r1 == ra) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) Hb[j] = Ha[j];
+            } else hrow(r1, Hb);
+            rb = r1;
+        }
+        uint32_t v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = mad_hi(Hb[j], b1s, mad_hi(Ha[j], b0s, 2u)) >> 2;
+        *(uint32_t*)out = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
     }
 }
 
@@ -119,19 +179,6 @@ __global__ void __launch_bounds__(256) k_pyr_resize_generic(const __grid_constan
 //   store   one 32-bit word per lane and row.
 // (Column-then-row equals row-then-column: the sums are exact integers.)
 #define BLUR_NT 128
-
-__device__ __forceinline__ uint32_t dp2a_lo(const uint32_t a, const uint32_t b, const uint32_t c)
-{
-    uint32_t d;
-    asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    return d;
-}
-__device__ __forceinline__ uint32_t dp2a_hi(const uint32_t a, const uint32_t b, const uint32_t c)
-{
-    uint32_t d;
-    asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    return d;
-}
 
 __global__ void __launch_bounds__(BLUR_NT) k_blur7(const __grid_constant__ OrbPlan plan, const OrbBatch io)
 {
@@ -223,11 +270,16 @@ cudaError_t orb_launch_pyramid(const OrbPlan& plan, const OrbBatch& io, int batc
     for (int l = 1; l < plan.nlevels; ++l) {
         const OrbLevel& D = plan.lv[l];
         const OrbLevel& S = plan.lv[l - 1];
-        // source rows spanned by PYR_TH destination rows: <= PYR_TH * (S.h / D.h) + 2
-        const bool tiled = (long long)PYR_TH * S.h + 3LL * D.h <= (long long)PYR_ROWS * D.h;
-        if (tiled) {
-            dim3 grd((D.pitch + PYR_TW - 1) / PYR_TW, (D.h + PYR_TH - 1) / PYR_TH, batch);
-            k_pyr_resize<<<grd, PYR_NT, 0, st>>>(plan, io, l);
+        // the walker needs the 4 destination pixels of a lane to span at most 7 source pixels
+        const bool walker = 4LL * S.w <= 5LL * D.w && S.w >= 12;
+        if (walker) {
+            // rows per warp: as many as still leave every SM a few dozen warps (each row waits for its loads)
+            int th = PYR_TH, tiles;
+            for (;; th >>= 1) {
+                tiles = ((D.w + PYR_TW - 1) / PYR_TW) * ((D.h + th - 1) / th);
+                if (th <= 8 || (long long)tiles * batch >= 148LL * 64) break;
+            }
+            k_pyr_resize<<<dim3((tiles + PYR_NT / 32 - 1) / (PYR_NT / 32), 1, batch), PYR_NT, 0, st>>>(plan, io, l, th);
         } else {
             dim3 blk(32, 8), grd((D.pitch / 4 + 31) / 32, (D.h + 7) / 8, batch);
             k_pyr_resize_generic<<<grd, blk, 0, st>>>(plan, io, l);
