@@ -97,36 +97,35 @@ __global__ void __launch_bounds__(PYR_NT) k_pyr_resize(const __grid_constant__ O
             w1 = b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24);
         }
         const uint32_t A = __byte_perm(w0, w1, selA), B = __byte_perm(w0, w1, selB);
-        H[0] = dp2a_lo(C[0], A, 0u) >> 4;
-        H[1] = dp2a_hi(C[1], A, 0u) >> 4;
-        H[2] = dp2a_lo(C[2], B, 0u) >> 4;
-        H[3] = dp2a_hi(C[3], B, 0u) >> 4;
+        // kept as (H >> 4) << 16, so that ((H >> 4) * b) >> 16 is one IMAD.HI
+        H[0] = (dp2a_lo(C[0], A, 0u) << 12) & 0xffff0000u;
+        H[1] = (dp2a_hi(C[1], A, 0u) << 12) & 0xffff0000u;
+        H[2] = (dp2a_lo(C[2], B, 0u) << 12) & 0xffff0000u;
+        H[3] = (dp2a_hi(C[3], B, 0u) << 12) & 0xffff0000u;
     };
     uint8_t* __restrict__ out = io.pyr + (size_t)frame * plan.pyr_bytes + D.img_off + (size_t)yb * dpitch + d0;
-    uint32_t Ha[4], Hb[4];
-    int ra = -1, rb = -1;                                                  // source rows held in Ha / Hb
+    // Two register slots X, Y hold the H rows rX, rY.  A destination row needs source rows r0 and r1 = r0+1; one
+    // of them is usually already in a slot, so the WEIGHTS are routed to the slots instead of moving the data.
+    // (At the bottom clamp r1 == r0 the weight of r1 is 0, so whatever the other slot holds contributes 0.)
+    uint32_t HX[4], HY[4];
+    int rX = -1, rY = -1;
     int2 ty = __ldg(&ytab[yb]);
     for (int y = yb; y < ye; ++y, out += dpitch) {
         const int r0 = ty.x, r1 = min(r0 + 1, sh - 1);
-        const uint32_t b0s = (uint32_t)ty.y << 16, b1s = (uint32_t)ty.y & 0xffff0000u;
+        const uint32_t b0 = (uint32_t)ty.y & 0xffffu, b1 = (uint32_t)ty.y >> 16;
         if (y + 1 < ye) ty = __ldg(&ytab[y + 1]);
-        if (r0 != ra) {
-            if (r0 == rb) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) Ha[j] = Hb[j];
-            } else hrow(r0, Ha);
-            ra = r0;
-        }
-        if (r1 != rb) {
-            if (r1 == ra) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) Hb[j] = Ha[j];
-            } else hrow(r1, Hb);
-            rb = r1;
+        uint32_t wX, wY;
+        if (r0 == rY) {
+            wY = b0; wX = b1;
+            if (rX != r1) { hrow(r1, HX); rX = r1; }
+        } else {
+            if (r0 != rX) { hrow(r0, HX); rX = r0; }
+            wX = b0; wY = b1;
+            if (rY != r1) { hrow(r1, HY); rY = r1; }
         }
         uint32_t v[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = mad_hi(Hb[j], b1s, mad_hi(Ha[j], b0s, 2u)) >> 2;
+        for (int j = 0; j < 4; ++j) v[j] = (__umulhi(HX[j], wX) + __umulhi(HY[j], wY) + 2u) >> 2;
         *(uint32_t*)out = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
     }
 }
