@@ -5,7 +5,10 @@
 // Batch loop: a batch is cut into chunks of ctx->chunk frames.  With host buffers the chunks
 // rotate through NSLOT buffer sets so that chunk i+1's host->device copy, chunk i's kernels and
 // chunk i-1's device->host copy run concurrently on three streams (copy engines are full
-// duplex); with device-resident inputs and outputs there are no copies and one slot is used.
+// duplex).  Chunks also alternate between NSLOT compute streams (forked from / joined to the
+// context's stream by events), so that the latency-bound sparse kernels of one chunk (quadtree,
+// descriptors) share the SMs with the issue-bound dense kernels of the next; while stage timing
+// is enabled (orbx_profile) everything runs on the one stream so the CUDA events bracket kernels.
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -40,6 +43,8 @@ struct Slot {
     DevBuf img_stage, pyr, blur, cand, node_of, counts, lkp, out_kps, out_desc, out_n;
     int frames = 0;                       // frames the work buffers are sized for
     cudaEvent_t h2d_done = nullptr, compute_done = nullptr, d2h_done = nullptr;
+    cudaStream_t aux = nullptr;            // the blur runs here, beside FAST + quadtree (both only need the pyramid)
+    cudaEvent_t pyr_done = nullptr, blur_done = nullptr;
     bool used = false;
     void release()
     {
@@ -62,6 +67,8 @@ struct orbx_ctx {
     cudaStream_t own_stream = nullptr;     // default compute stream
     cudaStream_t stream = nullptr;         // compute stream in use (own or caller's)
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+    cudaStream_t xstream[NSLOT - 1] = { nullptr };   // extra compute streams (slots 1..)
+    cudaEvent_t fork_ev = nullptr, join_ev[NSLOT - 1] = { nullptr };
     int chunk = 128;           // frames per internal pass (measured: larger chunks amortise tails; 128 x ~4.5 MB fits easily)
     std::string err;
 
@@ -109,6 +116,8 @@ int sync_all(orbx_ctx* c)
 {
     CU(c, cudaStreamSynchronize(c->h2d_stream));
     CU(c, cudaStreamSynchronize(c->stream));
+    for (cudaStream_t x : c->xstream) CU(c, cudaStreamSynchronize(x));
+    for (Slot& s : c->slot) CU(c, cudaStreamSynchronize(s.aux));
     CU(c, cudaStreamSynchronize(c->d2h_stream));
     return ORBX_OK;
 }
@@ -168,12 +177,12 @@ cudaEvent_t get_event(orbx_ctx* c)
 }
 
 struct StageScope {
-    orbx_ctx* c; StageTimer t; bool on;
-    StageScope(orbx_ctx* ctx, int stage) : c(ctx), on(ctx->profile)
+    orbx_ctx* c; StageTimer t; bool on; cudaStream_t st;
+    StageScope(orbx_ctx* ctx, int stage, cudaStream_t stream) : c(ctx), on(ctx->profile), st(stream)
     {
-        if (on) { t.stage = stage; t.ev[0] = get_event(c); t.ev[1] = get_event(c); cudaEventRecord(t.ev[0], c->stream); }
+        if (on) { t.stage = stage; t.ev[0] = get_event(c); t.ev[1] = get_event(c); cudaEventRecord(t.ev[0], st); }
     }
-    ~StageScope() { if (on) { cudaEventRecord(t.ev[1], c->stream); c->pending.push_back(t); } }
+    ~StageScope() { if (on) { cudaEventRecord(t.ev[1], st); c->pending.push_back(t); } }
 };
 
 void collect_timers(orbx_ctx* c)
@@ -188,7 +197,7 @@ void collect_timers(orbx_ctx* c)
 }
 
 // Enqueue the whole extractor for `frames` frames whose level-0 images are device resident.
-int enqueue_chunk(orbx_ctx* c, Slot& s, const uint8_t* d_img, size_t frame_stride, int pitch, int frames,
+int enqueue_chunk(orbx_ctx* c, Slot& s, cudaStream_t st, const uint8_t* d_img, size_t frame_stride, int pitch, int frames,
                   orbx_kp* d_kps, uint8_t* d_desc, int* d_n, int cap)
 {
     const OrbPlan& P = c->plan;
@@ -201,13 +210,22 @@ int enqueue_chunk(orbx_ctx* c, Slot& s, const uint8_t* d_img, size_t frame_strid
     io.lkp = (uint32_t*)s.lkp.p;
     io.kps = d_kps; io.desc = d_desc; io.n_out = d_n; io.cap = cap;
     io.taps = (const OrbTap*)c->taps.p;
-    cudaStream_t st = c->stream;
     CU(c, cudaMemsetAsync(io.cand_count, 0, (size_t)frames * ORB_MAX_LEVELS * 4, st));
-    { StageScope t(c, ORBX_STAGE_PYRAMID); CU(c, orb_launch_pyramid(P, io, frames, st)); }
-    { StageScope t(c, ORBX_STAGE_FAST); CU(c, orb_launch_fast(P, io, frames, st)); }
-    { StageScope t(c, ORBX_STAGE_BLUR); CU(c, orb_launch_blur(P, io, frames, st)); }
-    { StageScope t(c, ORBX_STAGE_OCTREE); CU(c, orb_launch_octree(P, io, frames, st)); }
-    { StageScope t(c, ORBX_STAGE_DESCRIBE); CU(c, orb_launch_describe(P, io, frames, st)); }
+    { StageScope t(c, ORBX_STAGE_PYRAMID, st); CU(c, orb_launch_pyramid(P, io, frames, st)); }
+    if (c->profile) {
+        { StageScope t(c, ORBX_STAGE_FAST, st); CU(c, orb_launch_fast(P, io, frames, st)); }
+        { StageScope t(c, ORBX_STAGE_BLUR, st); CU(c, orb_launch_blur(P, io, frames, st)); }
+        { StageScope t(c, ORBX_STAGE_OCTREE, st); CU(c, orb_launch_octree(P, io, frames, st)); }
+    } else {
+        CU(c, cudaEventRecord(s.pyr_done, st));
+        CU(c, cudaStreamWaitEvent(s.aux, s.pyr_done, 0));
+        CU(c, orb_launch_blur(P, io, frames, s.aux));
+        CU(c, cudaEventRecord(s.blur_done, s.aux));
+        CU(c, orb_launch_fast(P, io, frames, st));
+        CU(c, orb_launch_octree(P, io, frames, st));
+        CU(c, cudaStreamWaitEvent(st, s.blur_done, 0));
+    }
+    { StageScope t(c, ORBX_STAGE_DESCRIBE, st); CU(c, orb_launch_describe(P, io, frames, st)); }
     return ORBX_OK;
 }
 
@@ -228,18 +246,23 @@ int run_batch(orbx_ctx* c, const uint8_t* imgs, size_t frame_stride, int batch, 
     const bool piped = !in_dev || stage_out;           // any host buffer: rotate slots and overlap the copies
     const int chunk = batch < c->chunk ? batch : c->chunk;
     const int nchunks = (batch + chunk - 1) / chunk;
-    const int nslot = piped ? (nchunks < NSLOT ? nchunks : NSLOT) : 1;
+    const int nslot = nchunks < NSLOT ? nchunks : NSLOT;
+    const bool multi = nslot > 1 && !c->profile;       // chunks alternate between compute streams
     const size_t in_frame_bytes = pitch * (size_t)h;
     const size_t frame_copy_bytes = pitch * (size_t)(h - 1) + (size_t)w;   // never read past the last row's pixels
     for (int s = 0; s < nslot; ++s) {
         rc = ensure_slot(c, c->slot[s], chunk, cap, !in_dev, in_frame_bytes, stage_out);
         if (rc) return rc;
     }
-    cudaStream_t st = c->stream;
+    if (multi) {                                       // fork: the extra streams start after what is already queued
+        CU(c, cudaEventRecord(c->fork_ev, c->stream));
+        for (int k = 1; k < nslot; ++k) CU(c, cudaStreamWaitEvent(c->xstream[k - 1], c->fork_ev, 0));
+    }
     for (int i = 0; i < nchunks; ++i) {
         const int f0 = i * chunk;
         const int nf = batch - f0 < chunk ? batch - f0 : chunk;
         Slot& s = c->slot[i % nslot];
+        cudaStream_t st = multi && i % nslot ? c->xstream[i % nslot - 1] : c->stream;
         const uint8_t* d_img; size_t d_stride;
         if (in_dev) { d_img = imgs + (size_t)f0 * frame_stride; d_stride = frame_stride; }
         else {
@@ -260,9 +283,10 @@ int run_batch(orbx_ctx* c, const uint8_t* imgs, size_t frame_stride, int batch, 
         uint8_t* dd = stage_out ? (uint8_t*)s.out_desc.p : desc + (size_t)f0 * cap * 32;
         int* dn = stage_out ? (int*)s.out_n.p : n_out + f0;
         if (stage_out && s.used) CU(c, cudaStreamWaitEvent(st, s.d2h_done, 0));   // output staging still being drained
-        rc = enqueue_chunk(c, s, d_img, d_stride, (int)pitch, nf, dk, dd, dn, cap);
+        if (!multi && !piped && nslot > 1 && s.used) CU(c, cudaStreamWaitEvent(st, s.compute_done, 0));
+        rc = enqueue_chunk(c, s, st, d_img, d_stride, (int)pitch, nf, dk, dd, dn, cap);
         if (rc) return rc;
-        if (piped) CU(c, cudaEventRecord(s.compute_done, st));
+        CU(c, cudaEventRecord(s.compute_done, st));
         if (stage_out) {
             const cudaMemcpyKind kk = kps_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
             const cudaMemcpyKind kd = desc_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
@@ -273,11 +297,17 @@ int run_batch(orbx_ctx* c, const uint8_t* imgs, size_t frame_stride, int batch, 
             CU(c, cudaMemcpyAsync(n_out + f0, dn, (size_t)nf * 4, kn, c->d2h_stream));
             CU(c, cudaEventRecord(s.d2h_done, c->d2h_stream));
         }
-        s.used = piped;
+        s.used = true;
         c->last_slot = i % nslot; c->last_first = f0; c->last_count = nf;
         c->last_img0 = d_img; c->last_img0_stride = d_stride; c->last_img0_pitch = (int)pitch;
     }
-    if (async_only) return ORBX_OK;
+    if (multi) {                                       // join: later work on the context's stream sees every chunk
+        for (int k = 1; k < nslot; ++k) {
+            CU(c, cudaEventRecord(c->join_ev[k - 1], c->xstream[k - 1]));
+            CU(c, cudaStreamWaitEvent(c->stream, c->join_ev[k - 1], 0));
+        }
+    }
+    if (async_only) { for (Slot& s : c->slot) s.used = false; return ORBX_OK; }
     rc = sync_all(c);
     if (rc) return rc;
     for (Slot& s : c->slot) s.used = false;
@@ -343,11 +373,18 @@ int orbx_create(orbx_ctx** out, int nfeatures, float scaleFactor, int nlevels, i
     c->params = p; c->device = device;
     bool ok = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking) == cudaSuccess &&
-              cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking) == cudaSuccess;
+              cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreateWithFlags(&c->fork_ev, cudaEventDisableTiming) == cudaSuccess;
+    for (int k = 0; k < NSLOT - 1; ++k)
+        ok = ok && cudaStreamCreateWithFlags(&c->xstream[k], cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&c->join_ev[k], cudaEventDisableTiming) == cudaSuccess;
     for (Slot& s : c->slot)
         ok = ok && cudaEventCreateWithFlags(&s.h2d_done, cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&s.compute_done, cudaEventDisableTiming) == cudaSuccess &&
-             cudaEventCreateWithFlags(&s.d2h_done, cudaEventDisableTiming) == cudaSuccess;
+             cudaEventCreateWithFlags(&s.d2h_done, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&s.pyr_done, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&s.blur_done, cudaEventDisableTiming) == cudaSuccess &&
+             cudaStreamCreateWithFlags(&s.aux, cudaStreamNonBlocking) == cudaSuccess;
     if (!ok) { cudaGetLastError(); delete c; return ORBX_E_CUDA; }
     c->stream = c->own_stream;
     *out = c;
@@ -366,11 +403,17 @@ void orbx_destroy(orbx_ctx* c)
         if (s.h2d_done) cudaEventDestroy(s.h2d_done);
         if (s.compute_done) cudaEventDestroy(s.compute_done);
         if (s.d2h_done) cudaEventDestroy(s.d2h_done);
+        if (s.pyr_done) cudaEventDestroy(s.pyr_done);
+        if (s.blur_done) cudaEventDestroy(s.blur_done);
+        if (s.aux) cudaStreamDestroy(s.aux);
     }
     c->taps.release(); c->border_tmp.release();
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
     if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
+    for (cudaStream_t x : c->xstream) if (x) cudaStreamDestroy(x);
+    for (cudaEvent_t e : c->join_ev) if (e) cudaEventDestroy(e);
+    if (c->fork_ev) cudaEventDestroy(c->fork_ev);
     delete c;
 }
 
