@@ -9,7 +9,9 @@
 #ifndef ORACLE_MOCK_SLAM_HPP
 #define ORACLE_MOCK_SLAM_HPP
 
+#include <algorithm>
 #include <cassert>
+#include <cmath>
 #include <list>
 #include <map>
 #include <mutex>
@@ -70,7 +72,8 @@ public:
 
 class KeyFrame {
 public:
-    KeyFrame() : N(0), fx(0), fy(0), cx(0), cy(0), invfx(0), invfy(0), mbf(0), mb(0), mThDepth(0), mnId(0) {}
+    KeyFrame() : N(0), fx(0), fy(0), cx(0), cy(0), invfx(0), invfy(0), mbf(0), mb(0), mThDepth(0), mnId(0),
+                 mnMinX(0), mnMinY(0), mnMaxX(0), mnMaxY(0), mfGridElementWidthInv(0), mfGridElementHeightInv(0) {}
     int N;
     float fx, fy, cx, cy, invfx, invfy, mbf, mb, mThDepth;
     long unsigned int mnId;
@@ -82,8 +85,33 @@ public:
     std::vector<float> mvScaleFactors, mvLevelSigma2, mvInvLevelSigma2;
     std::vector<MapPoint*> mapPoints;
     cv::Mat R, t, Ow;
-    std::vector<size_t> GetFeaturesInArea(const float&, const float&, const float&) const { return std::vector<size_t>(); }
-    bool IsInImage(const float&, const float&) const { return true; }
+    // The key frame's copy of the frame grid (src/KeyFrame.cc:33-55 copies F.mGrid and the cell sizes); the harness
+    // fills it from a real ORB_SLAM2::Frame gridded by the reference's own AssignFeaturesToGrid.
+    int mnMinX, mnMinY, mnMaxX, mnMaxY;
+    float mfGridElementWidthInv, mfGridElementHeightInv;
+    std::vector<std::vector<std::vector<size_t> > > mGrid;      // [col][row] -> keypoint indices
+    // Restatement of KeyFrame::GetFeaturesInArea, src/KeyFrame.cc:637-676 (KeyFrame.cc itself drags in Map,
+    // KeyFrameDatabase and the vocabulary, so it is not compiled): cells floor/ceil of the window, clamped;
+    // columns outer, rows inner, insertion order inside a cell; strict |dx| < r and |dy| < r.  Empty grid = no hits.
+    std::vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r) const
+    {
+        std::vector<size_t> hits;
+        const int ncols = (int)mGrid.size(), nrows = ncols ? (int)mGrid[0].size() : 0;
+        if (!ncols || !nrows) return hits;
+        const int c0 = std::max(0, (int)std::floor((x - mnMinX - r) * mfGridElementWidthInv));
+        const int c1 = std::min(ncols - 1, (int)std::ceil((x - mnMinX + r) * mfGridElementWidthInv));
+        const int r0 = std::max(0, (int)std::floor((y - mnMinY - r) * mfGridElementHeightInv));
+        const int r1 = std::min(nrows - 1, (int)std::ceil((y - mnMinY + r) * mfGridElementHeightInv));
+        if (c0 >= ncols || c1 < 0 || r0 >= nrows || r1 < 0) return hits;
+        for (int c = c0; c <= c1; ++c)
+            for (int q = r0; q <= r1; ++q)
+                for (size_t j = 0; j < mGrid[c][q].size(); ++j) {
+                    const cv::KeyPoint& kp = mvKeysUn[mGrid[c][q][j]];
+                    if (std::fabs(kp.pt.x - x) < r && std::fabs(kp.pt.y - y) < r) hits.push_back(mGrid[c][q][j]);
+                }
+        return hits;
+    }
+    bool IsInImage(const float& x, const float& y) const { return x >= mnMinX && x < mnMaxX && y >= mnMinY && y < mnMaxY; }   // :679-682
     std::vector<MapPoint*> GetMapPointMatches() { return mapPoints; }
     std::set<MapPoint*> GetMapPoints() { return std::set<MapPoint*>(mapPoints.begin(), mapPoints.end()); }
     MapPoint* GetMapPoint(const size_t& i) { return mapPoints[i]; }

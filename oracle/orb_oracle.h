@@ -112,6 +112,14 @@ int orbo_search_by_projection_reloc(int n_cur, const orbo_kp* kps_cur, const uin
                                     float th, int ORBdist, int check_ori,
                                     float* uvr_out, int* minl_out, int* maxl_out, uint8_t* valid_out);
 
+/* ORBmatcher::SearchByProjection(KeyFrame*, cv::Mat Scw, vpPoints, vpMatched, th), src/ORBmatcher.cc:434-549 (orb_window_oracle.c) */
+int orbo_search_by_projection_sim3(int n, const orbo_kp* kps, const uint8_t* desc,
+                                   float minX, float maxX, float minY, float maxY, const float* scale,
+                                   const float* K, const float* Scw, int npts, const uint8_t* bad, const float* xyz, const float* normal,
+                                   const uint8_t* mp_desc, const int* pred_level, const float* min_dist, const float* max_dist,
+                                   const int* matched_in, int* assign_out, int th,
+                                   float* uvr_out, int* minl_out, int* maxl_out, uint8_t* valid_out);
+
 /* Frame::ComputeStereoMatches, src/Frame.cc:513-699 */
 int orbo_stereo_matches(const orbo_extractor* eL, const orbo_extractor* eR,
                         int nl, const orbo_kp* kps_l, const uint8_t* desc_l,

@@ -4,7 +4,8 @@
  * The "best candidate only" window search shared by the reference's projection overloads once the
  * points are projected, and the relocalisation overload built on it:
  *   ORBmatcher::SearchByProjection(Frame&, KeyFrame*, const set<MapPoint*>&, th, ORBdist)  src/ORBmatcher.cc:303-431
- * Pinned against the reference's unmodified code by tests/test_matcher_oracle.py (reloc overload) and
+ *   ORBmatcher::SearchByProjection(KeyFrame*, cv::Mat Scw, const vector<MapPoint*>&, vector<MapPoint*>&, th)  :434-549
+ * Pinned against the reference's unmodified code by tests/test_matcher_oracle.py (reloc and loop-closing overloads) and
  * against orbo_search_by_projection_frame (same loop, TH_HIGH).
  */
 #include "orb_oracle.h"
@@ -146,5 +147,82 @@ int orbo_search_by_projection_reloc(int n_cur, const orbo_kp* kps_cur, const uin
     if (maxl_out) memcpy(maxl_out, maxl, sizeof(int) * (size_t)nkf);
     if (valid_out) memcpy(valid_out, valid, (size_t)nkf);
     free(init_obs); free(valid); free(maxl); free(minl); free(uvr);
+    return nm;
+}
+
+/* ORBmatcher::SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const vector<MapPoint*>& vpPoints, vector<MapPoint*>& vpMatched, int th),
+ * src/ORBmatcher.cc:434-549 (loop closing).  Candidate points as arrays [npts]; matched_in [n]: -1 free, k >= 0 candidate k already
+ * matched to the keypoint (such candidates are not searched again, :449-450, 460), -2 some other point.  Accept at TH_LOW, no
+ * orientation check.  The Sim3 is decomposed and the points projected in the reference's arithmetic (cv::Mat algebra of
+ * oracle/cvshim: dot / norm accumulate in double, Mat/scalar multiplies by the double reciprocal, products accumulate in float). */
+int orbo_search_by_projection_sim3(int n, const orbo_kp* kps, const uint8_t* desc,
+                                   float minX, float maxX, float minY, float maxY, const float* scale,
+                                   const float* K, const float* Scw, int npts, const uint8_t* bad, const float* xyz, const float* normal,
+                                   const uint8_t* mp_desc, const int* pred_level, const float* min_dist, const float* max_dist,
+                                   const int* matched_in, int* assign_out, int th,
+                                   float* uvr_out, int* minl_out, int* maxl_out, uint8_t* valid_out)
+{
+    const float fx = K[0], fy = K[1], cx = K[2], cy = K[3];
+    /* scw = sqrt(sRcw.row(0).dot(sRcw.row(0))) (:446); Rcw = sRcw/scw; tcw = Scw(0:3,3)/scw (:447-448) */
+    double d = 0;
+    for (int c = 0; c < 3; ++c) d += (double)Scw[c] * (double)Scw[c];
+    const float scw = (float)sqrt(d);
+    const double inv = 1.0 / (double)scw;
+    float R[9], t[3], Ow[3];
+    for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c) R[3 * r + c] = (float)((double)Scw[4 * r + c] * inv);
+        t[r] = (float)((double)Scw[4 * r + 3] * inv);
+    }
+    for (int i = 0; i < 3; ++i) {                          /* Ow = -Rcw.t()*tcw (:449) */
+        float s = (float)((double)R[0 * 3 + i] * -1.0) * t[0];
+        s = s + (float)((double)R[1 * 3 + i] * -1.0) * t[1];
+        s = s + (float)((double)R[2 * 3 + i] * -1.0) * t[2];
+        Ow[i] = s;
+    }
+    const int iminX = (int)minX, imaxX = (int)maxX, iminY = (int)minY, imaxY = (int)maxY;   /* KeyFrame keeps int bounds */
+    float* uvr = (float*)calloc((size_t)(npts > 0 ? npts : 1) * 3, sizeof(float));
+    int* minl = (int*)calloc((size_t)(npts > 0 ? npts : 1), sizeof(int));
+    int* maxl = (int*)calloc((size_t)(npts > 0 ? npts : 1), sizeof(int));
+    uint8_t* valid = (uint8_t*)calloc((size_t)(npts > 0 ? npts : 1), 1);
+    uint8_t* found = (uint8_t*)calloc((size_t)(npts > 0 ? npts : 1), 1);
+    for (int k = 0; k < n; ++k) if (matched_in[k] >= 0) found[matched_in[k]] = 1;
+    for (int i = 0; i < npts; ++i) {
+        if (bad[i] || found[i]) continue;
+        const float* x = xyz + 3 * i;
+        float pc[3];
+        for (int r = 0; r < 3; ++r) {                      /* p3Dc = Rcw*p3Dw + tcw (:465) */
+            float s = R[3 * r] * x[0];
+            s = s + R[3 * r + 1] * x[1];
+            s = s + R[3 * r + 2] * x[2];
+            pc[r] = s + t[r];
+        }
+        if (pc[2] < 0.0) continue;
+        const float invz = 1 / pc[2];                      /* float division here (:472), unlike the other overloads */
+        const float xn = pc[0] * invz, yn = pc[1] * invz;
+        const float u = fx * xn + cx, v = fy * yn + cy;
+        if (!(u >= iminX && u < imaxX && v >= iminY && v < imaxY)) continue;   /* KeyFrame::IsInImage */
+        float PO[3];
+        double acc = 0;
+        for (int r = 0; r < 3; ++r) { PO[r] = x[r] - Ow[r]; acc += (double)PO[r] * (double)PO[r]; }
+        const float dist = (float)sqrt(acc);
+        if (dist < min_dist[i] || dist > max_dist[i]) continue;
+        double dn = 0;                                     /* PO.dot(Pn) < 0.5*dist (:495) */
+        for (int r = 0; r < 3; ++r) dn += (double)PO[r] * (double)normal[3 * i + r];
+        if (dn < 0.5 * dist) continue;
+        const int lvl = pred_level[i];
+        uvr[3 * i] = u; uvr[3 * i + 1] = v; uvr[3 * i + 2] = th * scale[lvl];
+        minl[i] = lvl - 1; maxl[i] = lvl; valid[i] = 1;    /* level test of the loop (:526) */
+    }
+    int* init_obs = (int*)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
+    for (int k = 0; k < n; ++k) init_obs[k] = matched_in[k] != -1 ? 1 : -1;
+    /* the key frame's bounds are ints: its grid origin is (float)(int)minX */
+    const int nm = orbo_window_search_best(n, kps, desc, NULL, (float)iminX, maxX, (float)iminY, maxY, npts, uvr, minl, maxl, NULL, NULL, valid,
+                                           mp_desc, NULL, NULL, init_obs, assign_out, 50, 0);
+    for (int k = 0; k < n; ++k) if (assign_out[k] == -2) assign_out[k] = matched_in[k];   /* pre-matched entries stay as they were */
+    if (uvr_out) memcpy(uvr_out, uvr, sizeof(float) * 3 * (size_t)npts);
+    if (minl_out) memcpy(minl_out, minl, sizeof(int) * (size_t)npts);
+    if (maxl_out) memcpy(maxl_out, maxl, sizeof(int) * (size_t)npts);
+    if (valid_out) memcpy(valid_out, valid, (size_t)npts);
+    free(init_obs); free(found); free(valid); free(maxl); free(minl); free(uvr);
     return nm;
 }

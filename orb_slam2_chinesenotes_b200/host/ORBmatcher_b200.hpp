@@ -13,6 +13,10 @@
 //                                           vector<int> &vnMatches12, int windowSize)
 //   { return b200::SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize, mfNNratio,
 //                                          mbCheckOrientation); }                       // src/ORBmatcher.cc:1055
+//   int ORBmatcher::SearchByProjection(Frame &Cur, KeyFrame *pKF, const set<MapPoint*> &sAlreadyFound, const float th, const int ORBdist)
+//   { return b200::SearchByProjection(Cur, pKF, sAlreadyFound, th, ORBdist, mbCheckOrientation); }   // src/ORBmatcher.cc:303
+//   int ORBmatcher::SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const vector<MapPoint*> &vpPoints, vector<MapPoint*> &vpMatched, int th)
+//   { return b200::SearchByProjection(pKF, Scw, vpPoints, vpMatched, th); }              // src/ORBmatcher.cc:434
 //   int ORBmatcher::DescriptorDistance(const cv::Mat &a, const cv::Mat &b)   stays on the CPU for single
 //   pairs (a 32-byte popcount); batches go through orbm_hamming_bf.
 //
@@ -215,6 +219,87 @@ int SearchByProjection(FrameT& Cur, KeyFrameT* pKF, const std::set<MapPointT*>& 
         if (assign[k] >= 0) Cur.mvpMapPoints[k] = vpMPs[(size_t)assign[k]];
         else if (assign[k] == -1) Cur.mvpMapPoints[k] = 0;
     }
+    return nmatches;
+}
+
+// ORBmatcher::SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const vector<MapPoint*>& vpPoints, vector<MapPoint*>& vpMatched, int th),
+// src/ORBmatcher.cc:434-549 (loop closing).  The Sim3 decomposition, projection, distance / viewing-angle gates and
+// MapPoint::PredictScale stay on the host in the reference's arithmetic (cv::Mat::dot and cv::norm accumulate in double,
+// Mat / scalar multiplies by the double reciprocal, matrix products accumulate in float); windows over the key frame's grid,
+// distances and the ordered "keypoint already matched" rule run on the GPU (orbm_window_search_best, TH_LOW, no
+// orientation check).  Reads pKF->fx, fy, cx, cy, mnMinX..mnMaxY, mvKeysUn, mDescriptors, mvScaleFactors.
+// (The key frame's grid origin is the int-truncated bound, include/KeyFrame.h:186-189; results are exact whenever the
+// image bounds are integers, i.e. for undistorted / rectified input.)
+template <class KeyFrameT, class MatT, class MapPointT>
+int SearchByProjection(KeyFrameT* pKF, const MatT& Scw, const std::vector<MapPointT*>& vpPoints, std::vector<MapPointT*>& vpMatched, int th)
+{
+    const int TH_LOW = 50;                                                               // src/ORBmatcher.cc:38
+    std::vector<orbx_kp> kps; FlattenKeys(pKF->mvKeysUn, kps);
+    std::vector<unsigned char> desc; FlattenDescriptors(pKF->mDescriptors, (int)kps.size(), desc);
+    orbm_frame view;
+    view.n = (int)kps.size(); view.kps = kps.empty() ? 0 : &kps[0]; view.desc = &desc[0]; view.u_right = 0;
+    view.min_x = (float)pKF->mnMinX; view.max_x = (float)pKF->mnMaxX; view.min_y = (float)pKF->mnMinY; view.max_y = (float)pKF->mnMaxY;
+    const float fx = pKF->fx, fy = pKF->fy, cx = pKF->cx, cy = pKF->cy;
+    float S[12];
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 4; ++c) S[4 * r + c] = Scw.template at<float>(r, c);
+    double d = 0;
+    for (int c = 0; c < 3; ++c) d += (double)S[c] * (double)S[c];
+    const float scw = (float)std::sqrt(d);
+    const double inv = 1.0 / (double)scw;
+    float R[9], t[3], Ow[3];
+    for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c) R[3 * r + c] = (float)((double)S[4 * r + c] * inv);
+        t[r] = (float)((double)S[4 * r + 3] * inv);
+    }
+    for (int i = 0; i < 3; ++i) {
+        float s = (float)((double)R[i] * -1.0) * t[0];
+        s = s + (float)((double)R[3 + i] * -1.0) * t[1];
+        s = s + (float)((double)R[6 + i] * -1.0) * t[2];
+        Ow[i] = s;
+    }
+    const std::set<MapPointT*> found(vpMatched.begin(), vpMatched.end());                // :449-450 (NULL is never a candidate)
+    const size_t nq = vpPoints.size();
+    std::vector<float> uvr(3 * (nq ? nq : 1), 0.f);
+    std::vector<int> minl(nq ? nq : 1, 0), maxl(nq ? nq : 1, 0);
+    std::vector<unsigned char> valid(nq ? nq : 1, 0), qdesc(32 * (nq ? nq : 1), 0);
+    for (size_t i = 0; i < nq; ++i) {
+        MapPointT* pMP = vpPoints[i];
+        if (pMP->isBad() || found.count(pMP)) continue;
+        const MatT p3Dw = pMP->GetWorldPos();
+        const float x[3] = { p3Dw.template at<float>(0), p3Dw.template at<float>(1), p3Dw.template at<float>(2) };
+        float pc[3];
+        for (int r = 0; r < 3; ++r) {
+            float s = R[3 * r] * x[0];
+            s = s + R[3 * r + 1] * x[1];
+            s = s + R[3 * r + 2] * x[2];
+            pc[r] = s + t[r];
+        }
+        if (pc[2] < 0.0) continue;
+        const float invz = 1 / pc[2];
+        const float xn = pc[0] * invz, yn = pc[1] * invz;
+        const float u = fx * xn + cx, v = fy * yn + cy;
+        if (!(u >= pKF->mnMinX && u < pKF->mnMaxX && v >= pKF->mnMinY && v < pKF->mnMaxY)) continue;
+        float PO[3];
+        double acc = 0;
+        for (int r = 0; r < 3; ++r) { PO[r] = x[r] - Ow[r]; acc += (double)PO[r] * (double)PO[r]; }
+        const float dist = (float)std::sqrt(acc);
+        if (dist < pMP->GetMinDistanceInvariance() || dist > pMP->GetMaxDistanceInvariance()) continue;
+        const MatT Pn = pMP->GetNormal();
+        double dn = 0;
+        for (int r = 0; r < 3; ++r) dn += (double)PO[r] * (double)Pn.template at<float>(r);
+        if (dn < 0.5 * dist) continue;
+        const int lvl = pMP->PredictScale(dist, pKF);
+        uvr[3 * i] = u; uvr[3 * i + 1] = v; uvr[3 * i + 2] = th * pKF->mvScaleFactors[(size_t)lvl];
+        minl[i] = lvl - 1; maxl[i] = lvl; valid[i] = 1;
+        std::memcpy(&qdesc[32 * i], pMP->GetDescriptor().ptr(0), 32);
+    }
+    std::vector<int> initObs(kps.size(), -1), assign(kps.size(), -1);
+    for (size_t k = 0; k < kps.size(); ++k) if (vpMatched[k]) initObs[k] = 1;
+    int nmatches = 0;
+    Check(orbm_window_search_best(&view, (int)nq, &uvr[0], &minl[0], &maxl[0], 0, 0, &valid[0], &qdesc[0], 0, 0,
+                                  kps.empty() ? 0 : &initObs[0], kps.empty() ? 0 : &assign[0], TH_LOW, 0, &nmatches, Device()),
+          "orbm_window_search_best");
+    for (size_t k = 0; k < kps.size(); ++k) if (assign[k] >= 0) vpMatched[k] = vpPoints[(size_t)assign[k]];
     return nmatches;
 }
 

@@ -20,6 +20,7 @@ struct MapPointT {
     int Observations() { return nObs; }
     cv::Mat GetDescriptor() { return descriptor.clone(); }
     cv::Mat GetWorldPos() { return pos.clone(); }
+    cv::Mat GetNormal() { return pos.clone(); }
 };
 struct FrameT {
     int N; float mbf, mb;
@@ -31,6 +32,9 @@ struct FrameT {
     static float fx, fy, cx, cy, mnMinX, mnMaxX, mnMinY, mnMaxY;
 };
 struct KeyFrameT {
+    float fx, fy, cx, cy; int mnMinX, mnMinY, mnMaxX, mnMaxY;
+    cv::Mat mDescriptors;
+    std::vector<float> mvScaleFactors;
     std::vector<cv::KeyPoint> mvKeysUn;
     std::vector<MapPointT*> pts;
     std::vector<MapPointT*> GetMapPointMatches() { return pts; }
@@ -52,5 +56,7 @@ extern "C" int matcher_forwarders_instantiate(int run)
     KeyFrameT kf;
     std::set<MapPointT*> found;
     n += ORB_SLAM2::b200::SearchByProjection(a, &kf, found, 10.0f, 100, true);
+    std::vector<MapPointT*> matched;
+    n += ORB_SLAM2::b200::SearchByProjection(&kf, cv::Mat(), pts, matched, 10);
     return n;
 }

@@ -149,6 +149,20 @@ def test_relocalisation_window_search(scene, th, orb_dist, check_ori):
     assert g_nm == nm and nm > 100 and (g_assign == assign).all()
 
 
+@pytest.mark.parametrize("th,seed", [(10, 41), (4, 42)])
+def test_loop_closing_window_search(scene, th, seed):
+    """src/ORBmatcher.cc:434-549 through the generic device primitive: the host decomposes the Sim3 and projects (the
+    oracle's exported queries = what the C++ forwarder computes); the GPU does windows, distances and ordered claims."""
+    from sim3_lib import run_sim3, sim3_scene
+    s = sim3_scene(scene["k2"], scene["d2"], W, H, seed, K)
+    nm, assign, q = run_sim3("oracle", scene["k2"], scene["d2"], s, scene["scale"], BOUNDS, K, th, want_queries=True)
+    F = ob.FrameView(scene["k2"], scene["d2"], BOUNDS)
+    init_obs = np.where(s["matched"] != -1, 1, -1).astype(np.int32)
+    g_nm, g_assign = ob.window_search_best(F, q["uvr"], q["minl"], q["maxl"], s["mp_desc"], 50, False, init_obs=init_obs, valid=q["valid"])
+    g_assign = np.where(g_assign == -2, s["matched"], g_assign)
+    assert g_nm == nm and nm > 100 and (g_assign == assign).all()
+
+
 def test_window_search_generic_random_queries(scene):
     """Random windows / level ranges / right-image gates / pre-attached points against the oracle primitive."""
     import ctypes as C

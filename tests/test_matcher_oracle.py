@@ -163,3 +163,16 @@ def test_relocalisation_overload(scene, th, orb_dist, check_ori):
     b = run_reloc("oracle", s, scene["scale"], BOUNDS, K, th, orb_dist, check_ori)
     assert a[0] == b[0] and a[0] > 100, (a[0], b[0])
     assert (a[1] == b[1]).all()
+
+
+@needs_ref
+@pytest.mark.parametrize("th,seed", [(10, 41), (4, 42), (20, 43)])
+def test_loop_closing_overload(scene, th, seed):
+    """src/ORBmatcher.cc:434-549 (KeyFrame, Sim3): the restatement against the reference's unmodified code."""
+    from sim3_lib import run_sim3, sim3_scene
+    s = sim3_scene(scene["k2"], scene["d2"], W, H, seed, K)
+    a = run_sim3("ref", scene["k2"], scene["d2"], s, scene["scale"], BOUNDS, K, th)
+    b = run_sim3("oracle", scene["k2"], scene["d2"], s, scene["scale"], BOUNDS, K, th)
+    assert a[0] == b[0] and a[0] > 100
+    assert (a[1] == b[1]).all()
+    assert ((a[1] != s["matched"]) & (s["matched"] != -1)).sum() == 0          # pre-matched keypoints are never overwritten
