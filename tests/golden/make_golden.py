@@ -91,8 +91,31 @@ def matchers():
     np.savez_compressed(os.path.join(HERE, "ref_match_kitti.npz"), **out)
 
 
+def projection_overloads():
+    """Relocalisation (src/ORBmatcher.cc:303-431) and loop-closing (:434-549) overloads of the reference's unmodified
+    ORBmatcher.cc on the scenes of tests/reloc_lib.py / tests/sim3_lib.py (regenerated from seeds; results stored)."""
+    from matcher_lib import extract_frame, perturbed_frame
+    from reloc_lib import reloc_scene, run_reloc
+    from sim3_lib import run_sim3, sim3_scene
+    W, H, NF = 1241, 376, 2000
+    B = (0.0, float(W), 0.0, float(H))
+    K = np.float32([718.856, 718.856, 607.1928, 185.2157])
+    kps, desc, scale = extract_frame(W, H, NF, 2)
+    k2, d2, _ = perturbed_frame(kps, desc, W, H, 11)
+    out = {}
+    s = reloc_scene(kps, desc, W, H, 31, K)
+    for th, od, co in ((10.0, 100, True), (3.0, 64, True)):
+        n, a = run_reloc("ref", s, scale, B, K, th, od, co)
+        out[f"reloc_th{int(th)}_n"] = n; out[f"reloc_th{int(th)}_assign"] = a
+    for th, seed in ((10, 41), (4, 42)):
+        s3 = sim3_scene(k2, d2, W, H, seed, K)
+        n, a = run_sim3("ref", k2, d2, s3, scale, B, K, th)
+        out[f"sim3_th{th}_n"] = n; out[f"sim3_th{th}_assign"] = a
+    np.savez_compressed(os.path.join(HERE, "ref_match_projection.npz"), **out)
+
+
 if __name__ == "__main__":
-    primitives()
-    extractor()
-    matchers()
+    which = sys.argv[1:] or ["primitives", "extractor", "matchers", "projection_overloads"]
+    for name in which:
+        globals()[name]()
     print("golden fixtures written to", HERE)

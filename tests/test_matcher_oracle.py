@@ -165,6 +165,22 @@ def test_relocalisation_overload(scene, th, orb_dist, check_ori):
     assert (a[1] == b[1]).all()
 
 
+def test_oracle_vs_projection_overload_fixtures(scene):
+    """Always runs: relocalisation and loop-closing overloads, results stored from the reference's unmodified code."""
+    import os
+    from reloc_lib import reloc_scene, run_reloc
+    from sim3_lib import run_sim3, sim3_scene
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_match_projection.npz"))
+    s = reloc_scene(scene["kps"], scene["desc"], W, H, 31, K)
+    for th, od, co in ((10.0, 100, True), (3.0, 64, True)):
+        n, a = run_reloc("oracle", s, scene["scale"], BOUNDS, K, th, od, co)
+        assert n == int(g[f"reloc_th{int(th)}_n"]) and (a == g[f"reloc_th{int(th)}_assign"]).all()
+    for th, seed in ((10, 41), (4, 42)):
+        s3 = sim3_scene(scene["k2"], scene["d2"], W, H, seed, K)
+        n, a = run_sim3("oracle", scene["k2"], scene["d2"], s3, scene["scale"], BOUNDS, K, th)
+        assert n == int(g[f"sim3_th{th}_n"]) and (a == g[f"sim3_th{th}_assign"]).all()
+
+
 @needs_ref
 @pytest.mark.parametrize("th,seed", [(10, 41), (4, 42), (20, 43)])
 def test_loop_closing_overload(scene, th, seed):
