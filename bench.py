@@ -336,7 +336,7 @@ def run_ours(args, rank, world, local_rank):
         v, kind, _ = cpu_frames_per_s(sample, nf, cores)
         cpu = {"value": v, "unit": "frames/s", "cores": cores, "kind": kind,
                "sample": f"first {ns} frames of the step's batch, {cores} threads, one extractor per thread"}
-    chunk = args.chunk or 128                      # orbx_set_chunk default (orb_capi.cu)
+    chunk = args.chunk or 64                       # orbx_set_chunk default (orb_capi.cu)
     chunks = (batch + chunk - 1) // chunk
     hamming = bench_hamming(dev, local_rank) if world == 1 else None
     print(json.dumps({

@@ -69,7 +69,8 @@ struct orbx_ctx {
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
     cudaStream_t xstream[NSLOT - 1] = { nullptr };   // extra compute streams (slots 1..)
     cudaEvent_t fork_ev = nullptr, join_ev[NSLOT - 1] = { nullptr };
-    int chunk = 128;           // frames per internal pass (measured: larger chunks amortise tails; 128 x ~4.5 MB fits easily)
+    int chunk = 64;            // frames per internal pass (measured with chunks alternating between streams: 32..256 give the same
+                               // device-resident rate, 64 the best rate with host buffers)
     std::string err;
 
     bool have_plan = false;

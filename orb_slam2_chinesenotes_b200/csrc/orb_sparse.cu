@@ -378,19 +378,24 @@ __global__ void __launch_bounds__(DESC_NT) k_describe(const __grid_constant__ Or
     // ---- IC_Angle (:78-105): integer moments over the 749-px disc
     int pitch;
     const uint8_t* img = orb_level_ptr(plan, io, frame, l, &pitch);
+    // lane = column u of the disc.  The disc is symmetric (the reference forces it, :552-558), so column u holds
+    // the rows |v| <= umax[|u|]; u is constant per lane, so m10 = u * (column sum) and only m01 needs a multiply
+    // per row; the row pointer advances by the pitch.
     const int u = lane - ORB_HALF_PATCH;
     int m10 = 0, m01 = 0;
     if (lane < ORB_PATCH) {
-        const int au = u < 0 ? -u : u;
-        const uint8_t* c = img + (size_t)cy * pitch + cx + u;
+        const int vmax = plan.umax[u < 0 ? -u : u];
+        const uint8_t* c = img + (size_t)(cy - ORB_HALF_PATCH) * pitch + cx + u;
+        int colsum = 0;
 #pragma unroll
-        for (int v = -ORB_HALF_PATCH; v <= ORB_HALF_PATCH; ++v) {
-            if (au <= plan.umax[v < 0 ? -v : v]) {
-                const int val = __ldg(c + v * pitch);
-                m10 += u * val;
+        for (int v = -ORB_HALF_PATCH; v <= ORB_HALF_PATCH; ++v, c += pitch) {
+            if ((v < 0 ? -v : v) <= vmax) {
+                const int val = __ldg(c);
+                colsum += val;
                 m01 += v * val;
             }
         }
+        m10 = u * colsum;
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
