@@ -55,6 +55,17 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_traffic(kernel, frames_per_launch):
+    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture (profiles/ncu_traffic.json,
+    written by tools/ncu_traffic.py): dram__bytes_read.sum + dram__bytes_write.sum per frame x frames per launch."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            t = json.load(f)
+        return float(t["dram_bytes_per_frame"][kernel]) * frames_per_launch
+    except Exception:
+        return None
+
+
 def synth_batch_torch(batch, w, h, seed, device):
     """Synthetic frames on the GPU: smoothed noise, mean 128 / std 48, low-contrast bottom band,
     hard-edged rectangles (the recipe of tests/synth.py, generated with torch for speed)."""
@@ -321,6 +332,8 @@ def run_ours(args, rank, world, local_rank):
         roof["achieved"] = bytes_per_frame[dom] * frames_per_launch / dur_s / 1e9
         roof["frac"] = roof["achieved"] / peak
         roof["algorithmic_bytes_per_frame"] = bytes_per_frame[dom]
+        roof["algorithmic_bytes_per_launch"] = bytes_per_frame[dom] * frames_per_launch
+        roof["traffic"] = measured_traffic(dom, frames_per_launch)
     else:
         roof["achieved"] = None
         roof["frac"] = None

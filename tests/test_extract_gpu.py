@@ -107,14 +107,17 @@ def test_non_contiguous_pitch():
 
 
 def test_batch_equals_single_and_chunking():
-    w, h, nf, B = 416, 240, 600, 13
+    """Chunk sizes pick different launch shapes (FAST blocks take 1 / 4 / all cell rows for < 16 / < 64 / >= 64 frames) and
+    chunks alternate between compute streams; every frame must still equal its single-frame result."""
+    w, h, nf, B = 416, 240, 600, 20
     frames = np.stack([synth_frame(w, h, 100 + i) for i in range(B)])
     G, O = ob.ORBextractor(nf, 1.2, 8, 20, 7), OracleExtractor(nf)
-    for chunk in (32, 4, 1):
+    want = [O.extract(frames[i]) for i in range(B)]
+    for chunk in (32, 16, 4, 1):
         G.set_chunk(chunk)
         kps, desc, n = G.extract_batch(frames)
         for i in range(B):
-            no, k_o, d_o = O.extract(frames[i])
+            no, k_o, d_o = want[i]
             assert no == n[i]
             assert same_kps(k_o, kps[i, :no]) and (d_o == desc[i, :no]).all(), (chunk, i)
     G.close(); O.close()
