@@ -25,12 +25,17 @@ sys.path.insert(0, ROOT)
 
 WORKLOADS = {
     # name: (w, h, nfeatures, frames per step per GPU)
+    # kitti = BASELINE.json configs[1]: rectified stereo pairs (frames L0,R0,L1,R1,...), left/right extraction +
+    # Frame::ComputeStereoMatches per pair; the others are extraction only
     "kitti_1241x376_nf2000": (1241, 376, 2000, 512),
     "tum_640x480_nf1000": (640, 480, 1000, 1024),
     "euroc_752x480_nf1200": (752, 480, 1200, 256),
     "hd_1920x1080_nf4000": (1920, 1080, 4000, 128),
 }
 LEVELS, SCALE, INI_TH, MIN_TH = 8, 1.2, 20, 7
+STEREO = {"kitti_1241x376_nf2000"}
+# KITTI 00-02 calibration (synthetic-test constants): fx, fy, cx, cy, bf, ThDepth * bf / fx
+CAM = dict(fx=718.856, fy=718.856, cx=607.1928, cy=185.2157, bf=386.1448, th_depth=35.0 * 386.1448 / 718.856)
 
 
 def level_pixels(w, h):
@@ -97,6 +102,25 @@ def synth_batch_torch(batch, w, h, seed, device):
     return out
 
 
+def stereo_right_torch(left, seed):
+    """Right images for a batch of left images (tests/synth.py stereo_pair): every block of 16..63 rows is the left
+    block shifted by its own disparity of 5..60 px, plus +-2 grey levels of noise."""
+    import torch
+    b, h, w = left.shape
+    rng = np.random.default_rng(seed + 7919)
+    right = torch.empty_like(left)
+    for i in range(b):
+        y = 0
+        while y < h:
+            bh, d = int(rng.integers(16, 64)), int(rng.integers(5, 61))
+            right[i, y:y + bh, :w - d] = left[i, y:y + bh, d:]
+            right[i, y:y + bh, w - d:] = left[i, y:y + bh, w - d - 1:w - d]
+            y += bh
+    g = torch.Generator(device=left.device).manual_seed(seed + 1)
+    noise = torch.randint(-2, 3, right.shape, generator=g, device=left.device, dtype=torch.int16)
+    return (right.to(torch.int16) + noise).clamp_(0, 255).to(torch.uint8)
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -156,25 +180,51 @@ def cpu_frames_per_s(frames_np, nfeatures, threads, reps=1):
     return nfr / best, kind, int(tot.value)
 
 
+def cpu_stereo_frames_per_s(frames_np, nfeatures, threads):
+    """Frames/s of the reference's own stereo Frame constructor (two ExtractORB threads + ComputeStereoMatches,
+    src/Frame.cc:61-115) over pairs L0,R0,L1,R1,...; None when oracle/_ref was not built."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    r = oracle_lib.ref()
+    if r is None or not hasattr(r, "orbref_stereo_bench"):
+        return None
+    nfr, h, w = frames_np.shape
+    tot = C.c_longlong()
+    dt = r.orbref_stereo_bench(nfeatures, SCALE, LEVELS, INI_TH, MIN_TH, frames_np.ctypes.data, nfr // 2, w, h, max(threads // 2, 1),
+                               CAM["fx"], CAM["fy"], CAM["cx"], CAM["cy"], CAM["bf"], CAM["th_depth"], C.byref(tot), None, 0)
+    return nfr / dt, int(tot.value)
+
+
+def cpu_workload_frames_per_s(workload, frames_np, nfeatures, cores):
+    """(frames/s, kind, what ran) of the CPU implementation of one bench workload."""
+    if workload in STEREO:
+        r = cpu_stereo_frames_per_s(frames_np, nfeatures, cores)
+        if r is not None:
+            return r[0], "reference", f"stereo Frame constructor, {max(cores // 2, 1)} frames in flight x 2 extractor threads"
+    v, kind, _ = cpu_frames_per_s(frames_np, nfeatures, cores)
+    return v, kind, f"{cores} threads, one extractor per thread" + (" (extraction only)" if workload in STEREO else "")
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    from synth import synth_frame  # numpy generator of the parity tests (no torch / CUDA needed)
+    from synth import stereo_pair, synth_frame  # numpy generators of the parity tests (no torch / CUDA needed)
     w, h, nf, _ = WORKLOADS[args.workload]
     cores = os.cpu_count() or 1
     nsample = int(min(256, max(16, 4 * cores)))
-    frames = np.stack([synth_frame(w, h, 2000 + i) for i in range(min(nsample, 16))])
+    if args.workload in STEREO:
+        frames = np.stack([im for i in range(min(nsample, 16) // 2) for im in stereo_pair(w, h, 2000 + i)])
+    else:
+        frames = np.stack([synth_frame(w, h, 2000 + i) for i in range(min(nsample, 16))])
     frames = np.concatenate([frames] * ((nsample + len(frames) - 1) // len(frames)))[:nsample]
     for _ in range(args.warmup):
-        cpu_frames_per_s(frames[:cores], nf, cores)
+        cpu_workload_frames_per_s(args.workload, frames[:max(2, cores & ~1)], nf, cores)
     t0 = time.perf_counter()
-    vals = []
     for _ in range(args.steps):
-        v, kind, _ = cpu_frames_per_s(frames, nf, cores)
-        vals.append(v)
+        v, kind, what = cpu_workload_frames_per_s(args.workload, frames, nf, cores)
     dt = time.perf_counter() - t0
     value = nsample * args.steps / dt
-    sample = f"{nsample} frames per step ({min(nsample, 16)} distinct), {cores} threads, one extractor per thread"
+    sample = f"{nsample} frames per step ({min(nsample, 16)} distinct), {what}"
     print(json.dumps({
         "impl": "reference", "metric": "orb_extract_frames_per_s", "value": value, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
@@ -236,7 +286,18 @@ def run_ours(args, rank, world, local_rank):
     if args.chunk:
         ex.set_chunk(args.chunk)
     cap = ex.default_capacity()
-    frames = synth_batch_torch(batch, w, h, 1000 * 2 + rank * 100003, dev)
+    stereo = args.workload in STEREO
+    if stereo:
+        batch += batch % 2
+        left = synth_batch_torch(batch // 2, w, h, 1000 * 2 + rank * 100003, dev)
+        frames = torch.stack([left, stereo_right_torch(left, 1000 * 2 + rank * 100003)], dim=1).reshape(batch, h, w).contiguous()
+        del left
+    else:
+        frames = synth_batch_torch(batch, w, h, 1000 * 2 + rank * 100003, dev)
+    pairs = batch // 2
+    d_ur = torch.full((pairs, cap), -1.0, dtype=torch.float32, device=dev)
+    d_dep = torch.full((pairs, cap), -1.0, dtype=torch.float32, device=dev)
+    d_ns = torch.zeros(pairs, dtype=torch.int32, device=dev)
     d_kps = torch.zeros((batch, cap, 7), dtype=torch.float32, device=dev)
     d_desc = torch.zeros((batch, cap, 32), dtype=torch.uint8, device=dev)
     d_n = torch.zeros(batch, dtype=torch.int32, device=dev)
@@ -247,7 +308,11 @@ def run_ours(args, rank, world, local_rank):
     ex.set_stream(stream.cuda_stream)
 
     def step_device():
-        ex.extract_batch_raw(frames, h * w, batch, w, h, w, d_kps, d_desc, cap, d_n, asynchronous=True)
+        if stereo:
+            ex.extract_stereo_batch_raw(frames, h * w, pairs, w, h, w, d_kps, d_desc, cap, d_n, CAM["bf"], CAM["fx"],
+                                        d_ur, d_dep, d_ns, asynchronous=True)
+        else:
+            ex.extract_batch_raw(frames, h * w, batch, w, h, w, d_kps, d_desc, cap, d_n, asynchronous=True)
 
     def barrier():
         torch.cuda.synchronize()
@@ -280,6 +345,10 @@ def run_ours(args, rank, world, local_rank):
     ex.profile(False)
     nk = d_n.cpu().numpy()
     assert (nk > 0).all() and (nk <= cap).all(), "extraction produced no keypoints / overflowed"
+    ns_dev = d_ns.cpu().numpy()
+    if stereo:
+        assert (ns_dev > 0).all(), "stereo matching found nothing"
+        n_depth = int((d_dep > 0).sum().item())
 
     # ---- end to end through the C ABI with HOST buffers (pinned): H2D + kernels + D2H per step
     h_frames = torch.empty((batch, h, w), dtype=torch.uint8).pin_memory()
@@ -287,9 +356,16 @@ def run_ours(args, rank, world, local_rank):
     h_kps = torch.empty((batch, cap, 7), dtype=torch.float32).pin_memory()
     h_desc = torch.empty((batch, cap, 32), dtype=torch.uint8).pin_memory()
     h_n = torch.empty(batch, dtype=torch.int32).pin_memory()
+    h_ur = torch.empty((pairs, cap), dtype=torch.float32).pin_memory()
+    h_dep = torch.empty((pairs, cap), dtype=torch.float32).pin_memory()
+    h_ns = torch.empty(pairs, dtype=torch.int32).pin_memory()
 
     def step_host():
-        ex.extract_batch_raw(h_frames, h * w, batch, w, h, w, h_kps, h_desc, cap, h_n, asynchronous=False)
+        if stereo:
+            ex.extract_stereo_batch_raw(h_frames, h * w, pairs, w, h, w, h_kps, h_desc, cap, h_n, CAM["bf"], CAM["fx"],
+                                        h_ur, h_dep, h_ns, asynchronous=False)
+        else:
+            ex.extract_batch_raw(h_frames, h * w, batch, w, h, w, h_kps, h_desc, cap, h_n, asynchronous=False)
 
     step_host()
     barrier()
@@ -300,6 +376,8 @@ def run_ours(args, rank, world, local_rank):
     ms_e2e = 1e3 * (time.perf_counter() - t0)
     clocks = sampler.stop()
     assert (h_n.numpy() == nk).all(), "host-buffer path and device-resident path disagree"
+    if stereo:
+        assert (h_ns.numpy() == ns_dev).all(), "stereo: host-buffer path and device-resident path disagree"
 
     # ---- max over ranks
     if dist is not None:
@@ -320,7 +398,7 @@ def run_ours(args, rank, world, local_rank):
     e2e_value = total_frames / (ms_e2e * 1e-3)
     # ---- roofline of the dominant kernel (stage times measured above with CUDA events on the stream)
     bytes_per_frame = algorithmic_bytes(w, h)
-    dom = max(("pyramid", "fast", "blur", "octree", "describe"), key=lambda s: stage_ms[s])
+    dom = max(("pyramid", "fast", "blur", "octree", "describe", "stereo"), key=lambda s: stage_ms[s])
     peak, peak_src = measured_peak()
     roof = {"bound": "hbm", "kernel": dom, "peak": peak, "unit": "GB/s", "peak_source": peak_src, "traffic": None,
             "stage_timing": "second pass of the same steps, kernels serialised on one stream, CUDA events around each launch",
@@ -344,13 +422,17 @@ def run_ours(args, rank, world, local_rank):
     cpu = None
     if world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
-        ns = int(min(batch, max(16, 4 * cores)))
+        ns = int(min(batch, max(16, 4 * cores))) & ~1
         sample = frames[:ns].cpu().numpy()
-        v, kind, _ = cpu_frames_per_s(sample, nf, cores)
+        v, kind, what = cpu_workload_frames_per_s(args.workload, sample, nf, cores)
         cpu = {"value": v, "unit": "frames/s", "cores": cores, "kind": kind,
-               "sample": f"first {ns} frames of the step's batch, {cores} threads, one extractor per thread"}
+               "sample": f"first {ns} frames of the step's batch, {what}"}
     chunk = args.chunk or 64                       # orbx_set_chunk default (orb_capi.cu)
     chunks = (batch + chunk - 1) // chunk
+    cfg_stereo = {}
+    if stereo:
+        cfg_stereo = {"stereo": "frames are rectified pairs L0,R0,L1,R1,...: left/right extraction + Frame::ComputeStereoMatches per pair",
+                      "pairs_per_step_per_gpu": pairs, "depth_points_per_pair": n_depth / pairs}
     hamming = bench_hamming(dev, local_rank) if world == 1 else None
     print(json.dumps({
         "metric": "orb_extract_frames_per_s", "value": value, "unit": "frames/s", "n_gpus": world,
@@ -358,10 +440,11 @@ def run_ours(args, rank, world, local_rank):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": args.workload, "w": w, "h": h, "nfeatures": nf, "levels": LEVELS,
                    "frames_per_step_per_gpu": batch, "l2": "inputs larger than L2 (%.0f MB per step)" % (batch * w * h / 1e6),
-                   "keypoints_per_frame": total_kp / (batch * world)},
+                   "keypoints_per_frame": total_kp / (batch * world), **cfg_stereo},
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": batch * w * h,
-                "d2h_bytes_per_step": batch * (cap * 60 + 4), "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": (LEVELS - 1 + 4) * chunks * args.steps,
+                "d2h_bytes_per_step": batch * (cap * 60 + 4) + (pairs * (cap * 8 + 4) if stereo else 0),
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": (LEVELS - 1 + 4 + (3 if stereo else 0)) * chunks * args.steps,
         "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "hamming_bf": hamming,
     }))
     if dist is not None:

@@ -79,6 +79,23 @@ int orbx_extract_batch_async(orbx_ctx* ctx, const uint8_t* d_imgs, size_t frame_
                              int cap_per_frame, int* d_n_out);
 int orbx_sync(orbx_ctx* ctx);
 
+/* The front end of the stereo Frame constructor (src/Frame.cc:61-115): ExtractORB on the left and the right
+ * image (:82-85) followed by ComputeStereoMatches (:107, :513-699), for `pairs` rectified pairs stored as
+ * L0,R0,L1,R1,... (frame 2p = left, 2p+1 = right; both extractors of the reference are built from the same
+ * settings, so one context serves both).  kps/desc/n_out are as in orbx_extract_batch with batch = 2*pairs;
+ * u_right/depth [pairs][cap_per_frame] receive mvuRight/mvDepth of the LEFT keypoints (-1 = no match; entries
+ * past n_out[2p] are not written), n_stereo [pairs] the number of matches before the median cut.  bf = mbf,
+ * fx = K(0,0) (mb = bf/fx, :121).  Keypoints, descriptors and pyramids stay on the device between the two
+ * steps.  Pointers host or device; the _async form takes device pointers only and just enqueues. */
+int orbx_extract_stereo_batch(orbx_ctx* ctx, const uint8_t* imgs, size_t frame_stride, int pairs,
+                              int w, int h, size_t pitch, orbx_kp* kps, uint8_t* desc,
+                              int cap_per_frame, int* n_out, float bf, float fx,
+                              float* u_right, float* depth, int* n_stereo);
+int orbx_extract_stereo_batch_async(orbx_ctx* ctx, const uint8_t* d_imgs, size_t frame_stride, int pairs,
+                                    int w, int h, size_t pitch, orbx_kp* d_kps, uint8_t* d_desc,
+                                    int cap_per_frame, int* d_n_out, float bf, float fx,
+                                    float* d_u_right, float* d_depth, int* d_n_stereo);
+
 /* mvImagePyramid[level] of frame `frame` of the last call (include/ORBextractor.h:86; read by
  * Frame::ComputeStereoMatches, src/Frame.cc:520,611-633).  with_border: the (w+38)x(h+38)
  * REFLECT_101-padded buffer of src/ORBextractor.cc:1159-1174 instead of the ROI.  dst host or
@@ -99,7 +116,7 @@ const char* orbx_last_error(const orbx_ctx* ctx);
 /* ---- stage taps (parity tests and profiling; not needed by a SLAM build) -------------- */
 
 enum { ORBX_STAGE_PYRAMID = 0, ORBX_STAGE_FAST = 1, ORBX_STAGE_BLUR = 2, ORBX_STAGE_OCTREE = 3,
-       ORBX_STAGE_DESCRIBE = 4, ORBX_STAGE_COUNT = 5 };
+       ORBX_STAGE_DESCRIBE = 4, ORBX_STAGE_STEREO = 5, ORBX_STAGE_COUNT = 6 };
 
 /* Blurred level (src/ORBextractor.cc:1129-1130) of a frame of the last call. */
 int orbx_debug_blurred(orbx_ctx* ctx, int frame, int level, uint8_t* dst, size_t dst_pitch);

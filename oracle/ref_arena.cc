@@ -17,7 +17,11 @@ std::atomic<int> g_hi(0);                  // slots >= g_hi were never used
 // Regions are never unmapped: data allocated by a worker thread (e.g. the keypoint vectors that
 // Frame::ExtractORB fills on its own std::thread, src/Frame.cc:82-85) outlives the thread.  A
 // finished thread's region is parked and handed to the next new thread.
+// A parked region keeps its bump offset: with several Frames in flight (orbref_stereo_bench) another worker's new
+// thread may adopt it while the Frame that owns the data is still alive, so it must continue, not restart.
+// reset_parked() rewinds all parked regions; harness entry points call it when nothing allocated is alive.
 std::atomic<char*> g_parked[kMaxRegions];
+std::atomic<std::size_t> g_parked_off[kMaxRegions];
 
 struct ThreadArena {
     char* base;
@@ -26,8 +30,9 @@ struct ThreadArena {
     void init()
     {
         for (int i = 0, n = g_hi.load(); i < n; ++i) {
+            const std::size_t o = g_parked_off[i].load();
             char* p = g_parked[i].exchange(0);
-            if (p) { base = p; off = 0; return; }
+            if (p) { base = p; off = o; return; }
         }
         void* p = mmap(0, kRegionBytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
         if (p == MAP_FAILED) { std::fprintf(stderr, "ref_arena: mmap failed\n"); std::abort(); }
@@ -48,7 +53,11 @@ struct ThreadArena {
         if (!base) return;
         for (int i = 0; i < kMaxRegions; ++i) {
             char* expect = 0;
-            if (g_parked[i].compare_exchange_strong(expect, base)) break;
+            // the slot's offset is written before the region becomes visible (a slot is owned by whoever emptied it)
+            if (g_parked[i].load() == 0) {
+                g_parked_off[i].store(off);
+                if (g_parked[i].compare_exchange_strong(expect, base)) break;
+            }
         }
         base = 0;
     }
@@ -74,6 +83,10 @@ bool owns(const void* p)
         if (b && (const char*)p >= b && (const char*)p < b + kRegionBytes) return true;
     }
     return false;
+}
+void reset_parked()
+{
+    for (int i = 0; i < kMaxRegions; ++i) g_parked_off[i].store(0);
 }
 std::size_t mark() { return t_arena.off; }
 void rewind(std::size_t m) { t_arena.off = m; }

@@ -24,6 +24,7 @@ void* alloc(std::size_t n);
 bool owns(const void* p);
 std::size_t mark();
 void rewind(std::size_t m);
+void reset_parked();   // rewind the regions of finished threads; only while nothing they allocated is alive
 struct Scope {
     std::size_t m;
     Scope() : m(mark()) {}

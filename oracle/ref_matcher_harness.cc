@@ -12,6 +12,13 @@
 #undef private
 #undef protected
 
+#include <chrono>
+#include <cstddef>
+#include <cstring>
+#include <new>
+#include <thread>
+#include <vector>
+
 #include "ref_arena.hpp"
 
 using namespace ORB_SLAM2;
@@ -57,6 +64,24 @@ cv::Mat mat_from(const float* p, int r, int c)
     return m;
 }
 } // namespace
+
+// A stereo Frame built in storage whose `mb` member already holds mbf/fx: the constructor reads mb (through
+// ComputeStereoMatches, src/Frame.cc:93 -> :523) before it assigns it (:121); in the running system the storage is
+// the previous Frame's (Tracking builds every Frame at the same address), which is the steady state modelled here.
+struct SteadyStereoFrame {
+    alignas(Frame) unsigned char buf[sizeof(Frame)];
+    Frame* F;
+    SteadyStereoFrame(const cv::Mat& imL, const cv::Mat& imR, ORBextractor* exl, ORBextractor* exr, ORBVocabulary* voc,
+                      cv::Mat& K, cv::Mat& dist, float bf, float thDepth)
+    {
+        std::memset(buf, 0, sizeof(buf));
+        const float mb = bf / K.at<float>(0, 0);
+        std::memcpy(buf + offsetof(Frame, mb), &mb, sizeof(mb));
+        F = new (buf) Frame(imL, imR, 0.0, exl, exr, voc, K, dist, bf, thDepth);
+    }
+    ~SteadyStereoFrame() { F->~Frame(); }
+    SteadyStereoFrame(const SteadyStereoFrame&) = delete;
+};
 
 extern "C" {
 
@@ -200,6 +225,7 @@ int orbref_stereo_frame(const unsigned char* left, const unsigned char* right, i
                         float* u_right, float* depth)
 {
     ref_arena::Scope scope;
+    ref_arena::reset_parked();
     int n;
     {
         ORBextractor exl(nfeatures, scaleFactor, nlevels, iniTh, minTh), exr(nfeatures, scaleFactor, nlevels, iniTh, minTh);
@@ -210,7 +236,8 @@ int orbref_stereo_frame(const unsigned char* left, const unsigned char* right, i
         cv::Mat dist = mat_from(Dd, 4, 1);
         Frame::mbInitialComputations = true;     // recompute the image bounds / grid scale for this shape
         ORBVocabulary voc;
-        Frame F(imL, imR, 0.0, &exl, &exr, &voc, K, dist, bf, thDepth);
+        SteadyStereoFrame SF(imL, imR, &exl, &exr, &voc, K, dist, bf, thDepth);
+        Frame& F = *SF.F;
         n = F.N;
         for (int i = 0; i < n && i < cap_l; ++i) {
             const cv::KeyPoint& k = F.mvKeys[i];
@@ -228,6 +255,58 @@ int orbref_stereo_frame(const unsigned char* left, const unsigned char* right, i
         }
     }
     return n;
+}
+
+// CPU baseline for BASELINE.json configs[1]: npairs rectified pairs (L0,R0,L1,R1,..., pitch == w) through the
+// reference's stereo Frame constructor, round-robin over nworkers threads; every Frame runs its two extractors on
+// two threads of its own (src/Frame.cc:82-85), so 2*nworkers threads are busy.  Returns the wall time in seconds;
+// total_depth receives the number of keypoints that got a depth.
+// Reference quirk: the constructor calls ComputeStereoMatches() (:93) BEFORE it sets mb = mbf/fx (:121), so minZ = mb
+// (:523) is whatever the member's storage held -- the previous Frame's mb when Frames are built at the same address
+// (what Tracking does), zero/garbage for the very first one (maxD = inf then).  The oracle and the CUDA path
+// implement the steady state, mb = mbf/fx; SteadyStereoFrame above pins the reference to it.
+double orbref_stereo_bench(int nfeatures, float scaleFactor, int nlevels, int iniTh, int minTh,
+                           const unsigned char* frames, int npairs, int w, int h, int nworkers,
+                           float fx, float fy, float cx, float cy, float bf, float thDepth, long long* total_depth,
+                           float* depth_out /* [npairs][cap] or NULL */, int cap)
+{
+    if (nworkers < 1) nworkers = 1;
+    std::vector<long long> counts((size_t)nworkers, 0);
+    std::vector<std::thread> workers;
+    ref_arena::reset_parked();
+    Frame::mbInitialComputations = true;
+    {   // the static image bounds / grid scale are computed by the first Frame: do that before the threads start
+        ORBextractor exl(nfeatures, scaleFactor, nlevels, iniTh, minTh), exr(nfeatures, scaleFactor, nlevels, iniTh, minTh);
+        ref_arena::Scope scope;
+        float Kd[9] = { fx, 0, cx, 0, fy, cy, 0, 0, 1 };
+        float Dd[4] = { 0, 0, 0, 0 };
+        cv::Mat imL(h, w, CV_8UC1, (void*)frames, (size_t)w), imR(h, w, CV_8UC1, (void*)(frames + (size_t)w * h), (size_t)w);
+        cv::Mat K = mat_from(Kd, 3, 3), dist = mat_from(Dd, 4, 1);
+        ORBVocabulary voc;
+        SteadyStereoFrame SF(imL, imR, &exl, &exr, &voc, K, dist, bf, thDepth);
+    }
+    auto t0 = std::chrono::steady_clock::now();
+    for (int t = 0; t < nworkers; ++t)
+        workers.emplace_back([&, t]() {
+            ORBextractor exl(nfeatures, scaleFactor, nlevels, iniTh, minTh), exr(nfeatures, scaleFactor, nlevels, iniTh, minTh);
+            float Kd[9] = { fx, 0, cx, 0, fy, cy, 0, 0, 1 };
+            float Dd[4] = { 0, 0, 0, 0 };
+            for (int p = t; p < npairs; p += nworkers) {
+                ref_arena::Scope scope;
+                const unsigned char* left = frames + (size_t)(2 * p) * w * h;
+                cv::Mat imL(h, w, CV_8UC1, (void*)left, (size_t)w), imR(h, w, CV_8UC1, (void*)(left + (size_t)w * h), (size_t)w);
+                cv::Mat K = mat_from(Kd, 3, 3), dist = mat_from(Dd, 4, 1);
+                ORBVocabulary voc;
+                SteadyStereoFrame SF(imL, imR, &exl, &exr, &voc, K, dist, bf, thDepth);
+                Frame& F = *SF.F;
+                for (int i = 0; i < F.N; ++i) counts[(size_t)t] += F.mvDepth[i] > 0;
+                if (depth_out) for (int i = 0; i < F.N && i < cap; ++i) depth_out[(size_t)p * cap + i] = F.mvDepth[i];
+            }
+        });
+    for (auto& th : workers) th.join();
+    const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (total_depth) { *total_depth = 0; for (long long c : counts) *total_depth += c; }
+    return dt;
 }
 
 } // extern "C"

@@ -21,7 +21,7 @@ KP_DTYPE = np.dtype([("x", "f4"), ("y", "f4"), ("size", "f4"), ("angle", "f4"), 
 assert KP_DTYPE.itemsize == 28
 
 ORBX_OK, ORBX_E_ARG, ORBX_E_SHAPE, ORBX_E_CAPACITY, ORBX_E_CUDA, ORBX_E_EMPTY = range(6)
-STAGES = ("pyramid", "fast", "blur", "octree", "describe")
+STAGES = ("pyramid", "fast", "blur", "octree", "describe", "stereo")
 
 
 class OrbmFrame(C.Structure):
@@ -69,6 +69,8 @@ def lib():
         L.orbx_extract_batch.argtypes = [vp, vp, sz, i32, i32, i32, sz, vp, vp, i32, vp]
         L.orbx_extract_batch_async.argtypes = [vp, vp, sz, i32, i32, i32, sz, vp, vp, i32, vp]
         L.orbx_sync.argtypes = [vp]
+        L.orbx_extract_stereo_batch.argtypes = [vp, vp, sz, i32, i32, i32, sz, vp, vp, i32, vp, f32, f32, vp, vp, vp]
+        L.orbx_extract_stereo_batch_async.argtypes = [vp, vp, sz, i32, i32, i32, sz, vp, vp, i32, vp, f32, f32, vp, vp, vp]
         L.orbx_pyramid_level.argtypes = [vp, i32, i32, i32, vp, sz, pi, pi]
         L.orbx_set_stream.argtypes = [vp, vp]
         L.orbx_stream.argtypes = [vp]
@@ -212,6 +214,28 @@ class ORBextractor:
         """Thin pass-through of orbx_extract_batch[_async]: every argument may be numpy or torch."""
         fn = self._L.orbx_extract_batch_async if asynchronous else self._L.orbx_extract_batch
         return self._check(fn(self._h, _ptr(imgs), frame_stride, batch, w, h, pitch, _ptr(kps), _ptr(desc), cap, _ptr(n_out)))
+
+    def extract_stereo_batch(self, frames, bf, fx, capacity=None):
+        """The stereo Frame constructor's front end (src/Frame.cc:61-115) for rectified pairs stored as
+        L0,R0,L1,R1,...: frames [2P,H,W] uint8 -> (kps [2P,cap], desc [2P,cap,32], n [2P], u_right [P,cap],
+        depth [P,cap], n_stereo [P]); u_right/depth are mvuRight/mvDepth of the left keypoints."""
+        frames = np.ascontiguousarray(frames)
+        assert frames.dtype == np.uint8 and frames.ndim == 3 and frames.shape[0] % 2 == 0
+        b, h, w = frames.shape
+        cap = capacity or self.default_capacity()
+        kps, desc, n = np.zeros((b, cap), KP_DTYPE), np.zeros((b, cap, 32), np.uint8), np.zeros(b, np.int32)
+        ur, dep, ns = np.full((b // 2, cap), -1, np.float32), np.full((b // 2, cap), -1, np.float32), np.zeros(b // 2, np.int32)
+        self._check(self._L.orbx_extract_stereo_batch(self._h, frames.ctypes.data, h * w, b // 2, w, h, w, kps.ctypes.data,
+                                                      desc.ctypes.data, cap, n.ctypes.data, bf, fx, ur.ctypes.data,
+                                                      dep.ctypes.data, ns.ctypes.data))
+        return kps, desc, n, ur, dep, ns
+
+    def extract_stereo_batch_raw(self, imgs, frame_stride, pairs, w, h, pitch, kps, desc, cap, n_out, bf, fx,
+                                 u_right, depth, n_stereo, asynchronous=False):
+        """Thin pass-through of orbx_extract_stereo_batch[_async]: every argument may be numpy or torch."""
+        fn = self._L.orbx_extract_stereo_batch_async if asynchronous else self._L.orbx_extract_stereo_batch
+        return self._check(fn(self._h, _ptr(imgs), frame_stride, pairs, w, h, pitch, _ptr(kps), _ptr(desc), cap, _ptr(n_out),
+                              bf, fx, _ptr(u_right), _ptr(depth), _ptr(n_stereo)))
 
     def sync(self):
         self._check(self._L.orbx_sync(self._h))

@@ -18,6 +18,7 @@
 
 #include "orb_device.cuh"
 #include "orb_launch.h"
+#include "orb_stereo.h"
 
 namespace {
 
@@ -41,6 +42,7 @@ struct DevBuf {
 // One set of per-chunk device buffers.
 struct Slot {
     DevBuf img_stage, pyr, blur, cand, node_of, counts, lkp, out_kps, out_desc, out_n;
+    DevBuf st_sad, st_sorted, st_rows, out_ur, out_depth, out_ns;   // stereo: scratch and staged mvuRight / mvDepth / counts
     int frames = 0;                       // frames the work buffers are sized for
     cudaEvent_t h2d_done = nullptr, compute_done = nullptr, d2h_done = nullptr;
     cudaStream_t aux = nullptr;            // the blur runs here, beside FAST + quadtree (both only need the pyramid)
@@ -48,10 +50,17 @@ struct Slot {
     bool used = false;
     void release()
     {
-        DevBuf* b[] = { &img_stage, &pyr, &blur, &cand, &node_of, &counts, &lkp, &out_kps, &out_desc, &out_n };
+        DevBuf* b[] = { &img_stage, &pyr, &blur, &cand, &node_of, &counts, &lkp, &out_kps, &out_desc, &out_n,
+                        &st_sad, &st_sorted, &st_rows, &out_ur, &out_depth, &out_ns };
         for (DevBuf* x : b) x->release();
         frames = 0;
     }
+};
+
+// What orbx_extract_stereo_batch adds to a batch call: frames are L0,R0,L1,R1,...
+struct StereoReq {
+    float bf, fx;
+    float* u_right; float* depth; int* n_stereo;
 };
 
 struct StageTimer {
@@ -140,9 +149,24 @@ int ensure_plan(orbx_ctx* c, int w, int h)
     return ORBX_OK;
 }
 
-int ensure_slot(orbx_ctx* c, Slot& s, int frames, int cap, bool stage_in, size_t in_frame_bytes, bool stage_out)
+int ensure_slot(orbx_ctx* c, Slot& s, int frames, int cap, bool stage_in, size_t in_frame_bytes, bool stage_out, bool stereo)
 {
     const OrbPlan& P = c->plan;
+    if (stereo) {
+        const size_t pairs = (size_t)(frames + 1) / 2;
+        if (s.st_sad.bytes < pairs * cap * 4 || s.st_rows.bytes < pairs * (P.h + 2) * 4 || (stage_out && s.out_ur.bytes < pairs * cap * 4)) {
+            int rc = sync_all(c);
+            if (rc) return rc;
+            CU(c, s.st_sad.reserve(pairs * cap * 4));
+            CU(c, s.st_sorted.reserve(pairs * cap * 2));
+            CU(c, s.st_rows.reserve(pairs * (P.h + 2) * 4));
+            if (stage_out) {
+                CU(c, s.out_ur.reserve(pairs * cap * 4));
+                CU(c, s.out_depth.reserve(pairs * cap * 4));
+                CU(c, s.out_ns.reserve(pairs * 4));
+            }
+        }
+    }
     if (frames > s.frames) {
         int rc = sync_all(c);
         if (rc) return rc;
@@ -199,7 +223,8 @@ void collect_timers(orbx_ctx* c)
 
 // Enqueue the whole extractor for `frames` frames whose level-0 images are device resident.
 int enqueue_chunk(orbx_ctx* c, Slot& s, cudaStream_t st, const uint8_t* d_img, size_t frame_stride, int pitch, int frames,
-                  orbx_kp* d_kps, uint8_t* d_desc, int* d_n, int cap)
+                  orbx_kp* d_kps, uint8_t* d_desc, int* d_n, int cap,
+                  const StereoReq* sr = nullptr, float* d_ur = nullptr, float* d_depth = nullptr, int* d_ns = nullptr)
 {
     const OrbPlan& P = c->plan;
     OrbBatch io;
@@ -227,13 +252,42 @@ int enqueue_chunk(orbx_ctx* c, Slot& s, cudaStream_t st, const uint8_t* d_img, s
         CU(c, cudaStreamWaitEvent(st, s.blur_done, 0));
     }
     { StageScope t(c, ORBX_STAGE_DESCRIBE, st); CU(c, orb_launch_describe(P, io, frames, st)); }
+    if (sr) {
+        // ComputeStereoMatches on the pairs (2p, 2p+1) of this chunk, straight from the buffers written above
+        OrbStereoView V;
+        memset(&V, 0, sizeof(V));
+        V.nlevels = P.nlevels;
+        for (int l = 0; l < P.nlevels; ++l) {
+            const OrbLevel& L = P.lv[l];
+            if (l == 0) { V.l[l] = d_img; V.r[l] = d_img + frame_stride; V.lstride[l] = V.rstride[l] = 2 * frame_stride; V.lpitch[l] = V.rpitch[l] = pitch; }
+            else {
+                V.l[l] = io.pyr + L.img_off; V.r[l] = io.pyr + P.pyr_bytes + L.img_off;
+                V.lstride[l] = V.rstride[l] = 2 * (size_t)P.pyr_bytes; V.lpitch[l] = V.rpitch[l] = L.pitch;
+            }
+            V.w[l] = L.w; V.h[l] = L.h;
+            V.scale[l] = c->params.scale[l]; V.inv_scale[l] = c->params.inv_scale[l];
+        }
+        V.kl = d_kps; V.kr = d_kps + cap;
+        V.dl = (const uint32_t*)d_desc; V.dr = (const uint32_t*)(d_desc + (size_t)cap * 32);
+        V.kstride = 2 * (size_t)cap;
+        V.nl = d_n; V.nr = d_n + 1; V.nstride = 2;
+        V.cap = cap;
+        V.bf = sr->bf; V.mb = sr->bf / sr->fx;                                  // src/Frame.cc:121
+        V.u_right = d_ur; V.depth = d_depth; V.ostride = (size_t)cap; V.n_stereo = d_ns;
+        V.sad = (int*)s.st_sad.p; V.sorted = (uint16_t*)s.st_sorted.p; V.row_start = (int*)s.st_rows.p;
+        V.band = orb_stereo_band(c->params.scale[P.nlevels - 1]);
+        StageScope t(c, ORBX_STAGE_STEREO, st);
+        CU(c, orb_launch_stereo(V, frames / 2, cap, st));
+    }
     return ORBX_OK;
 }
 
 int run_batch(orbx_ctx* c, const uint8_t* imgs, size_t frame_stride, int batch, int w, int h, size_t pitch,
-              orbx_kp* kps, uint8_t* desc, int cap, int* n_out, bool async_only)
+              orbx_kp* kps, uint8_t* desc, int cap, int* n_out, bool async_only, const StereoReq* sr = nullptr)
 {
     if (!c) return ORBX_E_ARG;
+    if (sr && (batch % 2 || cap > 65535 || !sr->u_right || !sr->depth || !sr->n_stereo || !(sr->fx > 0.f)))
+        return fail(c, ORBX_E_ARG, "bad stereo argument");
     if (!imgs || batch <= 0 || w <= 0 || h <= 0) return fail(c, ORBX_E_EMPTY, "empty image");
     if (pitch < (size_t)w || cap <= 0 || !kps || !desc || !n_out) return fail(c, ORBX_E_ARG, "bad argument");
     if (batch > 1 && frame_stride < pitch * (size_t)(h - 1) + (size_t)w) return fail(c, ORBX_E_ARG, "frame_stride too small");
@@ -242,17 +296,20 @@ int run_batch(orbx_ctx* c, const uint8_t* imgs, size_t frame_stride, int batch, 
     if (rc) return rc;
     const bool in_dev = is_device_ptr(imgs);
     const bool kps_dev = is_device_ptr(kps), desc_dev = is_device_ptr(desc), n_dev = is_device_ptr(n_out);
-    if (async_only && !(in_dev && kps_dev && desc_dev && n_dev)) return fail(c, ORBX_E_ARG, "async entry point needs device pointers");
-    const bool stage_out = !(kps_dev && desc_dev && n_dev);
+    const bool ur_dev = sr && is_device_ptr(sr->u_right), dep_dev = sr && is_device_ptr(sr->depth), ns_dev = sr && is_device_ptr(sr->n_stereo);
+    if (async_only && !(in_dev && kps_dev && desc_dev && n_dev && (!sr || (ur_dev && dep_dev && ns_dev))))
+        return fail(c, ORBX_E_ARG, "async entry point needs device pointers");
+    const bool stage_out = !(kps_dev && desc_dev && n_dev) || (sr && !(ur_dev && dep_dev && ns_dev));
     const bool piped = !in_dev || stage_out;           // any host buffer: rotate slots and overlap the copies
-    const int chunk = batch < c->chunk ? batch : c->chunk;
+    int chunk = batch < c->chunk ? batch : c->chunk;
+    if (sr && chunk % 2) chunk = chunk > 1 ? chunk - 1 : 2;      // a pair never straddles two chunks
     const int nchunks = (batch + chunk - 1) / chunk;
     const int nslot = nchunks < NSLOT ? nchunks : NSLOT;
     const bool multi = nslot > 1 && !c->profile;       // chunks alternate between compute streams
     const size_t in_frame_bytes = pitch * (size_t)h;
     const size_t frame_copy_bytes = pitch * (size_t)(h - 1) + (size_t)w;   // never read past the last row's pixels
     for (int s = 0; s < nslot; ++s) {
-        rc = ensure_slot(c, c->slot[s], chunk, cap, !in_dev, in_frame_bytes, stage_out);
+        rc = ensure_slot(c, c->slot[s], chunk, cap, !in_dev, in_frame_bytes, stage_out, sr != nullptr);
         if (rc) return rc;
     }
     if (multi) {                                       // fork: the extra streams start after what is already queued
@@ -285,7 +342,13 @@ int run_batch(orbx_ctx* c, const uint8_t* imgs, size_t frame_stride, int batch, 
         int* dn = stage_out ? (int*)s.out_n.p : n_out + f0;
         if (stage_out && s.used) CU(c, cudaStreamWaitEvent(st, s.d2h_done, 0));   // output staging still being drained
         if (!multi && !piped && nslot > 1 && s.used) CU(c, cudaStreamWaitEvent(st, s.compute_done, 0));
-        rc = enqueue_chunk(c, s, st, d_img, d_stride, (int)pitch, nf, dk, dd, dn, cap);
+        float* dur = nullptr; float* ddep = nullptr; int* dns = nullptr;
+        if (sr) {
+            dur = stage_out ? (float*)s.out_ur.p : sr->u_right + (size_t)(f0 / 2) * cap;
+            ddep = stage_out ? (float*)s.out_depth.p : sr->depth + (size_t)(f0 / 2) * cap;
+            dns = stage_out ? (int*)s.out_ns.p : sr->n_stereo + f0 / 2;
+        }
+        rc = enqueue_chunk(c, s, st, d_img, d_stride, (int)pitch, nf, dk, dd, dn, cap, sr, dur, ddep, dns);
         if (rc) return rc;
         CU(c, cudaEventRecord(s.compute_done, st));
         if (stage_out) {
@@ -296,6 +359,12 @@ int run_batch(orbx_ctx* c, const uint8_t* imgs, size_t frame_stride, int batch, 
             CU(c, cudaMemcpyAsync(kps + (size_t)f0 * cap, dk, (size_t)nf * cap * sizeof(orbx_kp), kk, c->d2h_stream));
             CU(c, cudaMemcpyAsync(desc + (size_t)f0 * cap * 32, dd, (size_t)nf * cap * 32, kd, c->d2h_stream));
             CU(c, cudaMemcpyAsync(n_out + f0, dn, (size_t)nf * 4, kn, c->d2h_stream));
+            if (sr) {
+                const size_t np = (size_t)nf / 2;
+                CU(c, cudaMemcpyAsync(sr->u_right + (size_t)(f0 / 2) * cap, dur, np * cap * 4, ur_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->d2h_stream));
+                CU(c, cudaMemcpyAsync(sr->depth + (size_t)(f0 / 2) * cap, ddep, np * cap * 4, dep_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->d2h_stream));
+                CU(c, cudaMemcpyAsync(sr->n_stereo + f0 / 2, dns, np * 4, ns_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->d2h_stream));
+            }
             CU(c, cudaEventRecord(s.d2h_done, c->d2h_stream));
         }
         s.used = true;
@@ -455,6 +524,22 @@ int orbx_extract_batch_async(orbx_ctx* c, const uint8_t* d_imgs, size_t frame_st
                              orbx_kp* d_kps, uint8_t* d_desc, int cap_per_frame, int* d_n_out)
 {
     return run_batch(c, d_imgs, frame_stride, batch, w, h, pitch, d_kps, d_desc, cap_per_frame, d_n_out, true);
+}
+
+int orbx_extract_stereo_batch(orbx_ctx* c, const uint8_t* imgs, size_t frame_stride, int pairs, int w, int h, size_t pitch,
+                              orbx_kp* kps, uint8_t* desc, int cap_per_frame, int* n_out, float bf, float fx,
+                              float* u_right, float* depth, int* n_stereo)
+{
+    const StereoReq sr = { bf, fx, u_right, depth, n_stereo };
+    return run_batch(c, imgs, frame_stride, 2 * pairs, w, h, pitch, kps, desc, cap_per_frame, n_out, false, &sr);
+}
+
+int orbx_extract_stereo_batch_async(orbx_ctx* c, const uint8_t* d_imgs, size_t frame_stride, int pairs, int w, int h, size_t pitch,
+                                    orbx_kp* d_kps, uint8_t* d_desc, int cap_per_frame, int* d_n_out, float bf, float fx,
+                                    float* d_u_right, float* d_depth, int* d_n_stereo)
+{
+    const StereoReq sr = { bf, fx, d_u_right, d_depth, d_n_stereo };
+    return run_batch(c, d_imgs, frame_stride, 2 * pairs, w, h, pitch, d_kps, d_desc, cap_per_frame, d_n_out, true, &sr);
 }
 
 int orbx_sync(orbx_ctx* c)

@@ -51,21 +51,48 @@ __device__ __forceinline__ uint32_t hmax2(const uint32_t a, const uint32_t b)
     return d;
 }
 
+// The min/max network is bound by the ALU pipe (HMNMX2 issues at half the warp rate), while the FMA pipe idles.
+// Where a min AND a max of the same two operands are needed, the pair is computed on the FMA pipe instead:
+//     r = relu(a - b) (HFMA2.RELU: b * -1 + a),  max = b + r,  min = a - r            (HADD2)
+// exact, because the operands are integers 0..255 held as fp16 denormals (multiples of 2^-24 below 2^-14:
+// sums and differences are representable, nothing rounds, f16 arithmetic keeps subnormals).
+#ifndef ORB_FAST_FMA
+#define ORB_FAST_FMA 3
+#endif
+#ifndef ORB_FAST_UNROLL
+#define ORB_FAST_UNROLL 2
+#endif
+constexpr int kFastUnroll = ORB_FAST_UNROLL;
+__device__ __forceinline__ void hminmax_fma(const uint32_t a, const uint32_t b, uint32_t& mn, uint32_t& mx)
+{
+    uint32_t r;
+    asm("fma.rn.relu.f16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(b), "r"(0xbc00bc00u), "r"(a));
+    asm("add.rn.f16x2 %0, %1, %2;" : "=r"(mx) : "r"(b), "r"(r));
+    asm("sub.rn.f16x2 %0, %1, %2;" : "=r"(mn) : "r"(a), "r"(r));
+}
+template <bool FMA>
+__device__ __forceinline__ void hminmax(const uint32_t a, const uint32_t b, uint32_t& mn, uint32_t& mx)
+{
+    if (FMA) hminmax_fma(a, b, mn, mx);
+    else { mn = hmin2(a, b); mx = hmax2(a, b); }
+}
+
 // packed (M1, M2) of a pixel pair from its 16 ring operands
 __device__ __forceinline__ void fast_network(const uint32_t* E, uint32_t& M1, uint32_t& M2)
 {
     uint32_t Bn[8], Bx[8], Qn[8], Qx[8], Y[8], Z[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { Bn[j] = hmin2(E[2 * j], E[2 * j + 1]); Bx[j] = hmax2(E[2 * j], E[2 * j + 1]); }
+    for (int j = 0; j < 8; ++j) hminmax<(ORB_FAST_FMA & 1) != 0>(E[2 * j], E[2 * j + 1], Bn[j], Bx[j]);
 #pragma unroll
     for (int j = 0; j < 8; ++j) { Qn[j] = hmin2(Bn[j], Bn[(j + 1) & 7]); Qx[j] = hmax2(Bx[j], Bx[(j + 1) & 7]); }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const uint32_t Fn = hmin2(Qn[j], Qn[(j + 2) & 7]);                 // min E[2j .. 2j+7]
         const uint32_t Fx = hmax2(Qx[j], Qx[(j + 2) & 7]);                 // max E[2j .. 2j+7]
-        const uint32_t lo = E[(2 * j + 15) & 15], hi = E[(2 * j + 8) & 15];
-        Y[j] = hmin2(Fn, hmax2(lo, hi));
-        Z[j] = hmax2(Fx, hmin2(lo, hi));
+        uint32_t ln, lx;
+        hminmax<(ORB_FAST_FMA & 2) != 0>(E[(2 * j + 15) & 15], E[(2 * j + 8) & 15], ln, lx);
+        Y[j] = hmin2(Fn, lx);
+        Z[j] = hmax2(Fx, ln);
     }
     M1 = hmax2(hmax2(hmax2(Y[0], Y[1]), hmax2(Y[2], Y[3])), hmax2(hmax2(Y[4], Y[5]), hmax2(Y[6], Y[7])));
     M2 = hmin2(hmin2(hmin2(Z[0], Z[1]), hmin2(Z[2], Z[3])), hmin2(hmin2(Z[4], Z[5]), hmin2(Z[6], Z[7])));
@@ -211,7 +238,7 @@ __device__ __forceinline__ void fast_strip_body(const OrbPlan& plan, const OrbBa
         if (nv) {   // scores
             const uint32_t* a = tile + aofs + ya * RS;                    // ring row dy = -3 of evaluated row ya
             uint32_t* sc = score + sofs + (ya + 1) * SRS;
-#pragma unroll 1
+#pragma unroll (kFastUnroll)
             for (int ly = ya; ly < yb; ++ly, a += RS, sc += SRS) {
                 const uint32_t* b = a + ab;
                 uint32_t E[16];

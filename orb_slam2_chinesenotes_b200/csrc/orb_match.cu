@@ -8,7 +8,7 @@
 //                       SearchByProjection(Frame, Frame)      src/ORBmatcher.cc:160-300
 //                       SearchForInitialization               src/ORBmatcher.cc:1055-1180
 //                       incl. the rotation histogram and ComputeThreeMaxima (:1663-1707)
-//   k_stereo_*          Frame::ComputeStereoMatches            src/Frame.cc:513-699
+//   (Frame::ComputeStereoMatches, src/Frame.cc:513-699: kernels in orb_stereo.cu, entry point here)
 // 256-bit descriptors as 8 x u32; distance = 8 x (LOP3 xor + POPC).  Integer pipe only.
 //
 // Why two phases: a query's candidate set and distances do not depend on other queries, but the
@@ -22,10 +22,12 @@
 #include <stdint.h>
 
 #include <cmath>
+#include <cstring>
 #include <vector>
 
 #include "../../include/orb_b200.h"
 #include "orb_launch.h"
+#include "orb_stereo.h"
 
 #define GRID_COLS 64    // FRAME_GRID_COLS, include/Frame.h:38
 #define GRID_ROWS 48    // FRAME_GRID_ROWS, include/Frame.h:37
@@ -380,137 +382,6 @@ __global__ void __launch_bounds__(32) k_resolve_init(const DevFrame F2, const in
     if (lane == 0) *nmatches_out = nmatches;
 }
 
-// ------------------------------------------------------------------------------ stereo
-struct StereoLevels {
-    const uint8_t* l[ORB_MAX_LEVELS]; const uint8_t* r[ORB_MAX_LEVELS];
-    int lpitch[ORB_MAX_LEVELS], rpitch[ORB_MAX_LEVELS], w[ORB_MAX_LEVELS], h[ORB_MAX_LEVELS];
-    float scale[ORB_MAX_LEVELS], inv_scale[ORB_MAX_LEVELS];
-};
-
-__device__ __forceinline__ int refl101(int i, const int n)
-{
-    while (i < 0 || i >= n) i = i < 0 ? -i : 2 * (n - 1) - i;
-    return i;
-}
-
-// One warp per left keypoint: row-band Hamming search (:546-596), 11x11 SAD over 11 shifts (:599-648),
-// parabola sub-pixel (:650-663), disparity / depth (:666-679).  sad[iL] = best SAD or -1.
-__global__ void __launch_bounds__(256) k_stereo_match(const int nl, const orbx_kp* __restrict__ kl, const uint32_t* __restrict__ dl,
-                                                     const int nr, const orbx_kp* __restrict__ kr, const uint32_t* __restrict__ dr,
-                                                     const StereoLevels P, const float bf, const float mb,
-                                                     float* __restrict__ u_right, float* __restrict__ depth, int* __restrict__ sad)
-{
-    const int iL = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (iL >= nl) return;
-    float out_u = -1.0f, out_d = -1.0f; int out_s = -1;
-    const orbx_kp kp = kl[iL];
-    const int levelL = kp.octave, rowL = (int)kp.y;
-    const float uL = kp.x;
-    const float minD = 0.f, maxD = __fdiv_rn(bf, mb);
-    const float minU = __fsub_rn(uL, maxD), maxU = __fsub_rn(uL, minD);
-    uint32_t best = 0xffffffffu;     // dist << 16 | iR
-    if (!(maxU < 0)) {
-        uint32_t d[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) d[i] = __ldg(dl + (size_t)iL * 8 + i);
-        for (int base = 0; base < nr; base += 32) {
-            const int iR = base + lane;
-            if (iR < nr) {
-                const orbx_kp k = kr[iR];
-                const float r = __fmul_rn(2.0f, P.scale[k.octave]);
-                const int maxr = (int)ceilf(__fadd_rn(k.y, r)), minr = (int)floorf(__fsub_rn(k.y, r));   // :535-539
-                if (rowL >= minr && rowL <= maxr && !(k.octave < levelL - 1 || k.octave > levelL + 1) && k.x >= minU && k.x <= maxU) {
-                    const uint4* p = (const uint4*)(dr + (size_t)iR * 8);
-                    const int dist = hamming256(d, __ldg(p), __ldg(p + 1));
-                    if (dist < TH_HIGH) best = min(best, ((uint32_t)dist << 16) | (uint32_t)iR);   // bestDist starts at TH_HIGH (:568)
-                }
-            }
-        }
-        best = __reduce_min_sync(0xffffffffu, best);
-    }
-    const int thOrbDist = (TH_HIGH + TH_LOW) / 2;
-    if (best != 0xffffffffu && (int)(best >> 16) < thOrbDist) {
-        const int bestIdxR = (int)(best & 0xffffu);
-        const float uR0 = kr[bestIdxR].x;
-        const float sf = P.inv_scale[levelL];
-        const float scaleduL = roundf(__fmul_rn(kp.x, sf)), scaledvL = roundf(__fmul_rn(kp.y, sf)), scaleduR0 = roundf(__fmul_rn(uR0, sf));
-        const int w = 5, L = 5;
-        const int lw = P.w[levelL], lh = P.h[levelL];
-        const float iniu = scaleduR0 + L - w, endu = scaleduR0 + L + w + 1;                        // :624-625
-        if (!(iniu < 0 || endu >= (float)lw)) {
-            const uint8_t* IL = P.l[levelL]; const uint8_t* IR = P.r[levelL];
-            const int lp = P.lpitch[levelL], rp = P.rpitch[levelL];
-            const int r0 = (int)(scaledvL - w), cL0 = (int)(scaleduL - w);
-            // patch reads may leave the ROI by up to 10 px on the left: that is the REFLECT_101 border of mvImagePyramid
-            const int cL = IL[(size_t)refl101(r0 + w, lh) * lp + refl101(cL0 + w, lw)];
-            int bestDist = 2147483647, bestincR = 0;
-            float vDists[11];
-#pragma unroll 1
-            for (int incR = -L; incR <= L; ++incR) {
-                const int cR0 = (int)(scaleduR0 + incR - w);
-                const int cR = IR[(size_t)refl101(r0 + w, lh) * rp + refl101(cR0 + w, lw)];
-                int s = 0;
-                for (int p = lane; p < 121; p += 32) {
-                    const int yy = p / 11, xx = p - yy * 11;
-                    const int a = (int)IL[(size_t)refl101(r0 + yy, lh) * lp + refl101(cL0 + xx, lw)] - cL;
-                    const int b = (int)IR[(size_t)refl101(r0 + yy, lh) * rp + refl101(cR0 + xx, lw)] - cR;
-                    s += abs(a - b);
-                }
-                s = __reduce_add_sync(0xffffffffu, s);
-                const float dist = (float)s;
-                if (dist < (float)bestDist) { bestDist = (int)dist; bestincR = incR; }
-                vDists[L + incR] = dist;
-            }
-            if (!(bestincR == -L || bestincR == L)) {
-                float dist1 = 0, dist2 = 0, dist3 = 0;
-#pragma unroll
-                for (int i = 0; i < 11; ++i) {   // (indexing with a runtime value would spill the array)
-                    if (i == L + bestincR - 1) dist1 = vDists[i];
-                    if (i == L + bestincR) dist2 = vDists[i];
-                    if (i == L + bestincR + 1) dist3 = vDists[i];
-                }
-                const float deltaR = __fdiv_rn(__fsub_rn(dist1, dist3), __fmul_rn(2.0f, __fsub_rn(__fadd_rn(dist1, dist3), __fmul_rn(2.0f, dist2))));
-                if (!(deltaR < -1 || deltaR > 1)) {
-                    float bestuR = __fmul_rn(P.scale[levelL], __fadd_rn(__fadd_rn(scaleduR0, (float)bestincR), deltaR));
-                    float disparity = __fsub_rn(uL, bestuR);
-                    if (disparity >= minD && disparity < maxD) {
-                        if (disparity <= 0) { disparity = (float)0.01; bestuR = (float)((double)uL - 0.01); }
-                        out_d = __fdiv_rn(bf, disparity); out_u = bestuR; out_s = bestDist;
-                    }
-                }
-            }
-        }
-    }
-    if (lane == 0) { u_right[iL] = out_u; depth[iL] = out_d; sad[iL] = out_s; }
-}
-
-// Median cut (:685-698): threshold = 1.5f*1.4f*median of the SADs, median = element nd/2 of the sorted list.
-__global__ void __launch_bounds__(1024) k_stereo_cut(const int nl, const int* __restrict__ sad, float* __restrict__ u_right, float* __restrict__ depth, int* __restrict__ nmatched)
-{
-    __shared__ int s_nd, s_median;
-    if (threadIdx.x == 0) { s_nd = 0; s_median = -1; }
-    __syncthreads();
-    int mine = 0;
-    for (int i = threadIdx.x; i < nl; i += blockDim.x) mine += sad[i] >= 0;
-    atomicAdd(&s_nd, mine);
-    __syncthreads();
-    const int nd = s_nd;
-    if (nd == 0) { if (threadIdx.x == 0) *nmatched = 0; return; }
-    const int k = nd / 2;
-    for (int i = threadIdx.x; i < nl; i += blockDim.x) {
-        const int v = sad[i];
-        if (v < 0) continue;
-        int less = 0, leq = 0;
-        for (int j = 0; j < nl; ++j) { const int o = sad[j]; if (o >= 0) { less += o < v; leq += o <= v; } }
-        if (less <= k && k < leq) s_median = v;    // every thread that hits writes the same value
-    }
-    __syncthreads();
-    const float thDist = __fmul_rn(1.5f * 1.4f, (float)s_median);
-    for (int i = threadIdx.x; i < nl; i += blockDim.x)
-        if (sad[i] >= 0 && !((float)sad[i] < thDist)) { u_right[i] = -1.0f; depth[i] = -1.0f; }
-    if (threadIdx.x == 0) *nmatched = nd;
-}
-
 // ================================================================================ host side
 namespace {
 bool dev_ptr(const void* p)
@@ -822,34 +693,42 @@ int orbm_stereo_matches(orbx_ctx* ex_left, int frame_l, orbx_ctx* ex_right, int 
 {
     if (!ex_left || !ex_right || nl < 0 || nr < 0 || !u_right || !depth || (nl > 0 && (!kps_l || !desc_l)) || (nr > 0 && (!kps_r || !desc_r)) || nr > 65535)
         return ORBX_E_ARG;
-    StereoLevels P;
-    int dev_l = 0, dev_r = 0, nlev = 0;
-    if (orb_ctx_levels(ex_left, frame_l, P.l, P.lpitch, P.w, P.h, P.scale, P.inv_scale, &nlev, &dev_l) ||
-        orb_ctx_levels(ex_right, frame_r, P.r, P.rpitch, nullptr, nullptr, nullptr, nullptr, nullptr, &dev_r) || dev_l != dev_r)
+    OrbStereoView V;
+    memset(&V, 0, sizeof(V));
+    int dev_l = 0, dev_r = 0;
+    if (orb_ctx_levels(ex_left, frame_l, V.l, V.lpitch, V.w, V.h, V.scale, V.inv_scale, &V.nlevels, &dev_l) ||
+        orb_ctx_levels(ex_right, frame_r, V.r, V.rpitch, nullptr, nullptr, nullptr, nullptr, nullptr, &dev_r) || dev_l != dev_r)
         return ORBX_E_ARG;
     if (cudaSetDevice(dev_l) != cudaSuccess) { cudaGetLastError(); return ORBX_E_CUDA; }
     if (nmatched) *nmatched = 0;
     for (int i = 0; i < nl; ++i) { u_right[i] = -1.0f; depth[i] = -1.0f; }
     if (nl == 0 || nr == 0) return ORBX_OK;
     Scratch S;
-    const orbx_kp* dkl = S.up(kps_l, (size_t)nl);
-    const orbx_kp* dkr = S.up(kps_r, (size_t)nr);
-    const uint32_t* ddl = (const uint32_t*)S.up(desc_l, (size_t)nl * 32);
-    const uint32_t* ddr = (const uint32_t*)S.up(desc_r, (size_t)nr * 32);
-    float* du = (float*)S.alloc(sizeof(float) * (size_t)nl);
-    float* dd = (float*)S.alloc(sizeof(float) * (size_t)nl);
-    int* dsad = (int*)S.alloc(sizeof(int) * (size_t)nl);
-    int* dn = (int*)S.alloc(4);
+    const int cap = nl > nr ? nl : nr;
+    const int counts[2] = { nl, nr };
+    V.kl = S.up(kps_l, (size_t)nl);
+    V.kr = S.up(kps_r, (size_t)nr);
+    V.dl = (const uint32_t*)S.up(desc_l, (size_t)nl * 32);
+    V.dr = (const uint32_t*)S.up(desc_r, (size_t)nr * 32);
+    const int* dcounts = S.up(counts, 2);
+    V.nl = dcounts; V.nr = dcounts + 1; V.nstride = 0; V.kstride = 0; V.cap = cap;
+    V.bf = bf; V.mb = bf / fx;                                                   // src/Frame.cc:121
+    V.u_right = (float*)S.alloc(sizeof(float) * (size_t)nl);
+    V.depth = (float*)S.alloc(sizeof(float) * (size_t)nl);
+    V.ostride = 0;
+    V.n_stereo = (int*)S.alloc(4);
+    V.sad = (int*)S.alloc(sizeof(int) * (size_t)cap);
+    V.sorted = (uint16_t*)S.alloc(sizeof(uint16_t) * (size_t)cap);
+    V.row_start = (int*)S.alloc(sizeof(int) * (size_t)(V.h[0] + 2));
+    float max_scale = 1.0f;
+    for (int l = 0; l < V.nlevels; ++l) if (V.scale[l] > max_scale) max_scale = V.scale[l];
+    V.band = orb_stereo_band(max_scale);
     if (!S.ok) return ORBX_E_CUDA;
-    const float mb = bf / fx;                                                    // src/Frame.cc:121
-    k_stereo_match<<<(nl + 7) / 8, 256>>>(nl, dkl, ddl, nr, dkr, ddr, P, bf, mb, du, dd, dsad);
-    CKM(cudaGetLastError());
-    k_stereo_cut<<<1, 1024>>>(nl, dsad, du, dd, dn);
-    CKM(cudaGetLastError());
-    CKM(cudaMemcpy(u_right, du, sizeof(float) * (size_t)nl, cudaMemcpyDeviceToHost));
-    CKM(cudaMemcpy(depth, dd, sizeof(float) * (size_t)nl, cudaMemcpyDeviceToHost));
+    CKM(orb_launch_stereo(V, 1, nl, 0));
+    CKM(cudaMemcpy(u_right, V.u_right, sizeof(float) * (size_t)nl, cudaMemcpyDeviceToHost));
+    CKM(cudaMemcpy(depth, V.depth, sizeof(float) * (size_t)nl, cudaMemcpyDeviceToHost));
     int n = 0;
-    CKM(cudaMemcpy(&n, dn, 4, cudaMemcpyDeviceToHost));
+    CKM(cudaMemcpy(&n, V.n_stereo, 4, cudaMemcpyDeviceToHost));
     if (nmatched) *nmatched = n;
     return ORBX_OK;
 }

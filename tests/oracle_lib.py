@@ -98,6 +98,10 @@ def ref():
         L.orbref_extract_bench.restype = C.c_double
         L.orbref_extract_bench.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                            C.c_int, C.c_int, C.POINTER(C.c_longlong)]
+        if hasattr(L, "orbref_stereo_bench"):
+            L.orbref_stereo_bench.restype = C.c_double
+            L.orbref_stereo_bench.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                              C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.POINTER(C.c_longlong), C.c_void_p, C.c_int]
         _ref = L
     return _ref
 

@@ -135,6 +135,71 @@ def test_stereo_pair_end_to_end():
         x.close()
 
 
+def _oracle_stereo(left, right, nf, bf, fx):
+    import ctypes as C
+    OL, OR = OracleExtractor(nf), OracleExtractor(nf)
+    nl, okl, odl = OL.extract(left)
+    nr, okr, odr = OR.extract(right)
+    our, odep = np.zeros(nl, np.float32), np.zeros(nl, np.float32)
+    O = oracle()
+    O.orbo_stereo_matches.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                      C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+    nd = O.orbo_stereo_matches(OL.h, OR.h, nl, okl.ctypes.data, odl.ctypes.data, nr, okr.ctypes.data, odr.ctypes.data, bf, fx,
+                               our.ctypes.data, odep.ctypes.data)
+    OL.close(); OR.close()
+    return (nl, okl, odl), (nr, okr, odr), our, odep, nd
+
+
+@pytest.mark.parametrize("w,h,nf,pairs,chunk", [(1241, 376, 2000, 3, 64), (640, 480, 1000, 5, 4), (752, 480, 1200, 2, 3)])
+def test_stereo_batch_device_resident(w, h, nf, pairs, chunk):
+    """orbx_extract_stereo_batch: L/R extraction + ComputeStereoMatches without leaving the GPU, pairs cut into
+    chunks (a pair never straddles two); every pair equals the oracle's stereo Frame bit for bit."""
+    bf, fx = 386.1448, float(K[0])
+    frames = np.stack([im for p in range(pairs) for im in stereo_pair(w, h, 40 + p)])
+    G = ob.ORBextractor(nf, 1.2, 8, 20, 7)
+    G.set_chunk(chunk)
+    kps, desc, n, ur, dep, ns = G.extract_stereo_batch(frames, bf, fx)
+    for p in range(pairs):
+        (nl, okl, odl), (nr, okr, odr), our, odep, nd = _oracle_stereo(frames[2 * p], frames[2 * p + 1], nf, bf, fx)
+        assert n[2 * p] == nl and n[2 * p + 1] == nr
+        assert (kps[2 * p, :nl] == okl).all() and (desc[2 * p, :nl] == odl).all() and (desc[2 * p + 1, :nr] == odr).all()
+        assert ns[p] == nd and nd > 50
+        assert (ur[p, :nl].view(np.uint32) == our.view(np.uint32)).all(), p
+        assert (dep[p, :nl].view(np.uint32) == odep.view(np.uint32)).all(), p
+    G.close()
+
+
+def test_stereo_batch_device_pointers_async():
+    """The same through the _async entry point with every buffer in device memory (torch tensors)."""
+    import torch
+    w, h, nf, pairs = 640, 480, 1000, 4
+    bf, fx = 386.1448, float(K[0])
+    frames = np.stack([im for p in range(pairs) for im in stereo_pair(w, h, 60 + p)])
+    G = ob.ORBextractor(nf, 1.2, 8, 20, 7)
+    want = G.extract_stereo_batch(frames, bf, fx)
+    cap = want[0].shape[1]
+    dev = torch.device("cuda:0")
+    d_img = torch.from_numpy(frames).to(dev)
+    d_kps = torch.zeros((2 * pairs, cap, 28), dtype=torch.uint8, device=dev)
+    d_desc = torch.zeros((2 * pairs, cap, 32), dtype=torch.uint8, device=dev)
+    d_n = torch.zeros(2 * pairs, dtype=torch.int32, device=dev)
+    d_ur = torch.full((pairs, cap), -1.0, dtype=torch.float32, device=dev)
+    d_dep = torch.full((pairs, cap), -1.0, dtype=torch.float32, device=dev)
+    d_ns = torch.zeros(pairs, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    G.extract_stereo_batch_raw(d_img, h * w, pairs, w, h, w, d_kps, d_desc, cap, d_n, bf, fx, d_ur, d_dep, d_ns, asynchronous=True)
+    G.sync()
+    n = d_n.cpu().numpy()
+    assert (n == want[2]).all() and (d_ns.cpu().numpy() == want[5]).all()
+    ur, dep = d_ur.cpu().numpy(), d_dep.cpu().numpy()
+    for p in range(pairs):
+        nl = n[2 * p]
+        assert (ur[p, :nl].view(np.uint32) == want[3][p, :nl].view(np.uint32)).all()
+        assert (dep[p, :nl].view(np.uint32) == want[4][p, :nl].view(np.uint32)).all()
+    assert (d_desc.cpu().numpy() == want[1]).all()
+    G.close()
+
+
 @pytest.mark.parametrize("th,orb_dist,check_ori", [(10.0, 100, True), (3.0, 64, True), (10.0, 100, False)])
 def test_relocalisation_window_search(scene, th, orb_dist, check_ori):
     """src/ORBmatcher.cc:303-431 through the generic device primitive: the host projects (oracle's exported

@@ -121,6 +121,32 @@ def test_stereo_frame_vs_oracle():
     OL.close(); OR.close()
 
 
+@needs_ref
+def test_stereo_bench_harness_is_deterministic():
+    """orbref_stereo_bench (the CPU baseline of bench.py: several Frames in flight, persistent extractors) gives every
+    pair the depths of the single-frame harness whatever the worker count -- the reference reads Frame::mb before the
+    constructor sets it (src/Frame.cc:93 vs :121); the harness pins the steady-state value mbf/fx."""
+    R = ref()
+    w, h, nf, pairs, cap = 640, 480, 1000, 3, 1200
+    frames = np.stack([im for p in range(pairs) for im in stereo_pair(w, h, 70 + p)])
+    vp, ci, cf = C.c_void_p, C.c_int, C.c_float
+    R.orbref_stereo_frame.argtypes = [vp, vp, ci, ci, ci, cf, ci, ci, ci, cf, cf, cf, cf, cf, cf, vp, vp, ci, vp, vp, ci, C.POINTER(ci), vp, vp]
+    bf, fx = 386.1448, float(K[0])
+    want = np.full((pairs, cap), -2, np.float32)
+    for p in range(pairs):
+        kl, dl = np.zeros(cap, KP_DTYPE), np.zeros((cap, 32), np.uint8)
+        n = R.orbref_stereo_frame(frames[2 * p].ctypes.data, frames[2 * p + 1].ctypes.data, w, h, nf, 1.2, 8, 20, 7, fx, float(K[1]), float(K[2]),
+                                  float(K[3]), bf, 35.0, kl.ctypes.data, dl.ctypes.data, cap, None, None, 0, None, None, want[p].ctypes.data)
+        assert 0 < n <= cap
+    for workers in (1, 2):
+        got = np.full((pairs, cap), -2, np.float32)
+        tot = C.c_longlong()
+        R.orbref_stereo_bench(nf, 1.2, 8, 20, 7, frames.ctypes.data, pairs, w, h, workers, fx, float(K[1]), float(K[2]), float(K[3]), bf, 35.0,
+                              C.byref(tot), got.ctypes.data, cap)
+        assert (got.view(np.uint32) == want.view(np.uint32)).all(), workers
+        assert tot.value == int((want > 0).sum()) > 100
+
+
 def test_oracle_vs_matcher_fixtures(scene):
     """Always runs: results stored from the reference's unmodified ORBmatcher.cc / Frame.cc
     (tests/golden/make_golden.py) against the C restatement."""
