@@ -158,7 +158,7 @@ int ensure_slot(orbx_ctx* c, Slot& s, int frames, int cap, bool stage_in, size_t
             int rc = sync_all(c);
             if (rc) return rc;
             CU(c, s.st_sad.reserve(pairs * cap * 4));
-            CU(c, s.st_sorted.reserve(pairs * cap * 2));
+            CU(c, s.st_sorted.reserve(pairs * cap * 16));
             CU(c, s.st_rows.reserve(pairs * (P.h + 2) * 4));
             if (stage_out) {
                 CU(c, s.out_ur.reserve(pairs * cap * 4));
@@ -274,8 +274,7 @@ int enqueue_chunk(orbx_ctx* c, Slot& s, cudaStream_t st, const uint8_t* d_img, s
         V.cap = cap;
         V.bf = sr->bf; V.mb = sr->bf / sr->fx;                                  // src/Frame.cc:121
         V.u_right = d_ur; V.depth = d_depth; V.ostride = (size_t)cap; V.n_stereo = d_ns;
-        V.sad = (int*)s.st_sad.p; V.sorted = (uint16_t*)s.st_sorted.p; V.row_start = (int*)s.st_rows.p;
-        V.band = orb_stereo_band(c->params.scale[P.nlevels - 1]);
+        V.sad = (int*)s.st_sad.p; V.rec = (uint4*)s.st_sorted.p; V.row_start = (int*)s.st_rows.p;
         StageScope t(c, ORBX_STAGE_STEREO, st);
         CU(c, orb_launch_stereo(V, frames / 2, cap, st));
     }

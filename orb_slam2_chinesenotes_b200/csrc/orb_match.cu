@@ -718,11 +718,8 @@ int orbm_stereo_matches(orbx_ctx* ex_left, int frame_l, orbx_ctx* ex_right, int 
     V.ostride = 0;
     V.n_stereo = (int*)S.alloc(4);
     V.sad = (int*)S.alloc(sizeof(int) * (size_t)cap);
-    V.sorted = (uint16_t*)S.alloc(sizeof(uint16_t) * (size_t)cap);
+    V.rec = (uint4*)S.alloc(sizeof(uint4) * (size_t)cap);
     V.row_start = (int*)S.alloc(sizeof(int) * (size_t)(V.h[0] + 2));
-    float max_scale = 1.0f;
-    for (int l = 0; l < V.nlevels; ++l) if (V.scale[l] > max_scale) max_scale = V.scale[l];
-    V.band = orb_stereo_band(max_scale);
     if (!S.ok) return ORBX_E_CUDA;
     CKM(orb_launch_stereo(V, 1, nl, 0));
     CKM(cudaMemcpy(u_right, V.u_right, sizeof(float) * (size_t)nl, cudaMemcpyDeviceToHost));

@@ -3,7 +3,8 @@
 // pyramids exactly where the extractor left them.
 //
 //   k_stereo_rows   one block per pair: right keypoints bucketed by integer row (counting sort in shared
-//                   memory).  Stands in for vRowIndices (:529-544): the reference lists every right keypoint
+//                   memory) into 16-byte records {x, band rows minr/maxr (:535-539), index, octave}, so the band
+//                   scan reads them with one coalesced load per lane.  Stands in for vRowIndices (:529-544): the reference lists every right keypoint
 //                   under each row of its band [floor(y-r), ceil(y+r)], r = 2*scale[octave]; here a left
 //                   keypoint scans the buckets of rows rowL-band .. rowL+band (a superset) and applies the
 //                   exact band test, so the candidate SET is the reference's.  Candidate order does not
@@ -11,7 +12,8 @@
 //                   equals, the smallest iR -- the minimum of dist<<16 | iR.
 //   k_stereo_match  one warp per left keypoint: band scan with 256-bit Hamming (:546-596), 11x11 SAD over 11
 //                   shifts on the level images (:599-648), parabola (:650-663), disparity/depth (:666-679).
-//                   The left patch is loaded once; only the right window moves.
+//                   The left patch and the 11 x 21 right strip are staged once in shared memory (per warp); the 11
+//                   SADs read them from there.
 //   k_stereo_cut    one block per pair: median of the SADs by two 256-bin histogram passes (SAD < 2^16),
 //                   threshold 1.5f*1.4f*median (:685-698).
 // Integer work except the sub-pixel parabola, which is evaluated operation by operation (_rn).
@@ -20,6 +22,13 @@
 
 #define TH_HIGH 100     // src/ORBmatcher.cc:37
 #define TH_LOW 50       // :38
+
+// REFLECT_101 for indices at most n-1 outside [0, n): one reflection, branch free
+__device__ __forceinline__ int st_refl1(const int i, const int n)
+{
+    const int a = abs(i);
+    return min(a, 2 * (n - 1) - a);
+}
 
 __device__ __forceinline__ int st_hamming256(const uint32_t* a, const uint4 b0, const uint4 b1)
 {
@@ -35,7 +44,7 @@ __global__ void __launch_bounds__(256) k_stereo_rows(const __grid_constant__ Orb
     const int nr = min(V.nr[(size_t)pair * V.nstride], V.cap);
     const orbx_kp* kr = V.kr + (size_t)pair * V.kstride;
     int* row_start = V.row_start + (size_t)pair * (h0 + 2);
-    uint16_t* sorted = V.sorted + (size_t)pair * V.cap;
+    uint4* rec = V.rec + (size_t)pair * V.cap;
     for (int i = tid; i <= h0; i += 256) s_cnt[i] = 0;
     __syncthreads();
     for (int i = tid; i < nr; i += 256) atomicAdd(&s_cnt[min(max((int)kr[i].y, 0), h0 - 1)], 1);
@@ -45,11 +54,19 @@ __global__ void __launch_bounds__(256) k_stereo_rows(const __grid_constant__ Orb
     if (tid == 0) row_start[0] = 0;
     __syncthreads();
     // scatter: a row's slots are filled from its end (inclusive count) downwards
-    for (int i = tid; i < nr; i += 256) sorted[atomicSub(&s_cnt[min(max((int)kr[i].y, 0), h0 - 1)], 1) - 1] = (uint16_t)i;
+    for (int i = tid; i < nr; i += 256) {
+        const orbx_kp k = kr[i];
+        const float r = __fmul_rn(2.0f, V.scale[k.octave]);
+        const int maxr = (int)ceilf(__fadd_rn(k.y, r)), minr = (int)floorf(__fsub_rn(k.y, r));       // :535-539
+        const int lo = min(max(minr, -32768), 32767), hi = min(max(maxr, -32768), 32767);
+        rec[atomicSub(&s_cnt[min(max((int)k.y, 0), h0 - 1)], 1) - 1] =
+            make_uint4(__float_as_uint(k.x), (uint32_t)(lo & 0xffff) | ((uint32_t)hi << 16), (uint32_t)i | ((uint32_t)k.octave << 16), 0u);
+    }
 }
 
 __global__ void __launch_bounds__(256) k_stereo_match(const __grid_constant__ OrbStereoView V)
 {
+    __shared__ __align__(16) uint8_t s_patch[8][384];      // per warp: left patch [121] at 0, right strip [11][21] at 128
     const int pair = blockIdx.y, lane = threadIdx.x & 31;
     const int iL = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int nl = min(V.nl[(size_t)pair * V.nstride], V.cap);
@@ -71,17 +88,19 @@ __global__ void __launch_bounds__(256) k_stereo_match(const __grid_constant__ Or
         for (int i = 0; i < 8; ++i) d[i] = __ldg(dl + i);
         const int h0 = V.h[0];
         const int* row_start = V.row_start + (size_t)pair * (h0 + 2);
-        const uint16_t* sorted = V.sorted + (size_t)pair * V.cap;
-        const int r_lo = min(max(rowL - V.band, 0), h0 - 1), r_hi = min(max(rowL + V.band, 0), h0 - 1);
+        const uint4* rec = V.rec + (size_t)pair * V.cap;
+        // candidates sit at most one level away: their band is at most 2 * (largest scale of the three levels) rows
+        const int band = orb_stereo_band(fmaxf(V.scale[levelL], fmaxf(V.scale[max(levelL - 1, 0)], V.scale[min(levelL + 1, V.nlevels - 1)])));
+        const int r_lo = min(max(rowL - band, 0), h0 - 1), r_hi = min(max(rowL + band, 0), h0 - 1);
         const int c0 = row_start[r_lo], c1 = row_start[r_hi + 1];
         for (int base = c0; base < c1; base += 32) {
             const int c = base + lane;
             if (c < c1) {
-                const int iR = sorted[c];
-                const orbx_kp k = kr[iR];
-                const float r = __fmul_rn(2.0f, V.scale[k.octave]);
-                const int maxr = (int)ceilf(__fadd_rn(k.y, r)), minr = (int)floorf(__fsub_rn(k.y, r));   // :535-539
-                if (rowL >= minr && rowL <= maxr && !(k.octave < levelL - 1 || k.octave > levelL + 1) && k.x >= minU && k.x <= maxU) {
+                const uint4 R = __ldg(rec + c);
+                const float x = __uint_as_float(R.x);
+                const int minr = (int)(short)(R.y & 0xffffu), maxr = (int)R.y >> 16;
+                const int iR = (int)(R.z & 0xffffu), oct = (int)(R.z >> 16);
+                if (rowL >= minr && rowL <= maxr && !(oct < levelL - 1 || oct > levelL + 1) && x >= minU && x <= maxU) {
                     const uint4* p = (const uint4*)(dr + (size_t)iR * 8);
                     const int dist = st_hamming256(d, __ldg(p), __ldg(p + 1));
                     if (dist < TH_HIGH) best = min(best, ((uint32_t)dist << 16) | (uint32_t)iR);   // bestDist starts at TH_HIGH (:568)
@@ -99,42 +118,51 @@ __global__ void __launch_bounds__(256) k_stereo_match(const __grid_constant__ Or
         const int w = 5, L = 5;
         const int lw = V.w[levelL], lh = V.h[levelL];
         const float iniu = scaleduR0 + L - w, endu = scaleduR0 + L + w + 1;    // :624-625
-        if (!(iniu < 0 || endu >= (float)lw)) {
+        if (!(iniu < 0 || endu >= (float)lw) && lw > 16 && lh > 16) {   // (levels are never that small: orbx_shape_supported)
             const uint8_t* IL = V.l[levelL] + (size_t)pair * V.lstride[levelL];
             const uint8_t* IR = V.r[levelL] + (size_t)pair * V.rstride[levelL];
             const int lp = V.lpitch[levelL], rp = V.rpitch[levelL];
             const int r0 = (int)(scaledvL - w), cL0 = (int)(scaleduL - w), cRm = (int)(scaleduR0 - w);
             // Reads may leave the level image by up to 10 px on the left: that is the REFLECT_101 border of
-            // mvImagePyramid (never materialised here).  Lane owns patch positions p = lane + 32k.
-            const int rc = orb_refl101(r0 + w, lh);
-            const int cL = IL[(size_t)rc * lp + orb_refl101(cL0 + w, lw)];
-            int a[4], xx[4];
-            const uint8_t* rrow[4];
+            // mvImagePyramid (never materialised here).  Stage the 11x11 left patch and the 11x21 right strip
+            // (columns scaleduR0-10 .. scaleduR0+10) once; lane owns patch positions p = lane + 32k.
+            uint8_t* sL = s_patch[threadIdx.x >> 5];
+            uint8_t* sR = sL + 128;
+            __syncwarp();
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const int p = min(lane + 32 * k, 120), yy = p / 11;
-                xx[k] = p - yy * 11;
-                const int ry = orb_refl101(r0 + yy, lh);
-                a[k] = (int)IL[(size_t)ry * lp + orb_refl101(cL0 + xx[k], lw)] - cL;
-                rrow[k] = IR + (size_t)ry * rp;
+                const int p = lane + 32 * k;
+                if (p < 121) { const int yy = p / 11, xx = p - yy * 11; sL[p] = IL[(size_t)st_refl1(r0 + yy, lh) * lp + st_refl1(cL0 + xx, lw)]; }
             }
-            const uint8_t* rcen = IR + (size_t)rc * rp;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int q = lane + 32 * k;
+                if (q < 231) { const int yy = q / 21, xx = q - yy * 21; sR[q] = IR[(size_t)st_refl1(r0 + yy, lh) * rp + st_refl1(cRm - L + xx, lw)]; }
+            }
+            __syncwarp();
+            const int cL = sL[5 * 11 + 5];
+            int a[4], ro[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int p = min(lane + 32 * k, 120), yy = p / 11, xx = p - yy * 11;
+                a[k] = (int)sL[p] - cL;
+                ro[k] = yy * 21 + xx;
+            }
             const bool last = lane + 96 < 121;                                 // k = 3 exists for lanes 0..24
             int bestDist = 2147483647, bestincR = 0;
             float vDists[11];
 #pragma unroll
             for (int i = 0; i < 11; ++i) {
-                const int incR = i - L, cR0 = cRm + incR;
-                const int cR = rcen[orb_refl101(cR0 + w, lw)];
+                const int cR = sR[5 * 21 + 5 + i];
                 int s = 0;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const int b = (int)rrow[k][orb_refl101(cR0 + xx[k], lw)] - cR;
+                    const int b = (int)sR[ro[k] + i] - cR;
                     if (k < 3 || last) s += abs(a[k] - b);
                 }
                 s = __reduce_add_sync(0xffffffffu, s);
                 const float dist = (float)s;
-                if (dist < (float)bestDist) { bestDist = (int)dist; bestincR = incR; }   // :641-645
+                if (dist < (float)bestDist) { bestDist = (int)dist; bestincR = i - L; }   // :641-645
                 vDists[i] = dist;
             }
             if (!(bestincR == -L || bestincR == L)) {                          // :650

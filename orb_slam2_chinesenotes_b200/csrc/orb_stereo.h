@@ -25,12 +25,11 @@ struct OrbStereoView {
     float* u_right; float* depth; size_t ostride;               // mvuRight / mvDepth, [pairs][ostride]
     int* n_stereo;                                              // [pairs] matches before the median cut
     int* sad;                                                   // scratch [pairs][cap]
-    uint16_t* sorted;                                           // scratch [pairs][cap]: right keypoints by row
+    uint4* rec;                                                 // scratch [pairs][cap]: right keypoints by row, {x, minr|maxr<<16, index|octave<<16, 0}
     int* row_start;                                             // scratch [pairs][h[0] + 2]
-    int band;                                                   // rows scanned either side of a left keypoint's row
 };
 
 // rows either side that certainly cover every band [floor(y - r), ceil(y + r)], r = 2 * scale <= 2 * max_scale
-static inline int orb_stereo_band(float max_scale) { return (int)(2.0f * max_scale) + 3; }
+static inline __host__ __device__ int orb_stereo_band(float max_scale) { return (int)(2.0f * max_scale) + 3; }
 
 cudaError_t orb_launch_stereo(const OrbStereoView& V, int pairs, int max_left, cudaStream_t st);
