@@ -36,7 +36,10 @@
 #include "orb_device.cuh"
 #include "orb_launch.h"
 
-#define FAST_NT (32 * ORB_FAST_STRIP)
+#ifndef ORB_FAST_TPC
+#define ORB_FAST_TPC 32      // threads per cell of the strip
+#endif
+#define FAST_NT (ORB_FAST_TPC * ORB_FAST_STRIP)
 
 __device__ __forceinline__ uint32_t hmin2(const uint32_t a, const uint32_t b)
 {
