@@ -27,7 +27,7 @@ WORKLOADS = {
     # name: (w, h, nfeatures, frames per step per GPU)
     # kitti = BASELINE.json configs[1]: rectified stereo pairs (frames L0,R0,L1,R1,...), left/right extraction +
     # Frame::ComputeStereoMatches per pair; the others are extraction only
-    "kitti_1241x376_nf2000": (1241, 376, 2000, 512),
+    "kitti_1241x376_nf2000": (1241, 376, 2000, 1024),
     "tum_640x480_nf1000": (640, 480, 1000, 1024),
     "euroc_752x480_nf1200": (752, 480, 1200, 256),
     "hd_1920x1080_nf4000": (1920, 1080, 4000, 128),
@@ -427,7 +427,7 @@ def run_ours(args, rank, world, local_rank):
         v, kind, what = cpu_workload_frames_per_s(args.workload, sample, nf, cores)
         cpu = {"value": v, "unit": "frames/s", "cores": cores, "kind": kind,
                "sample": f"first {ns} frames of the step's batch, {what}"}
-    chunk = args.chunk or 64                       # orbx_set_chunk default (orb_capi.cu)
+    chunk = args.chunk or 512                      # device-resident default of orb_capi.cu (the timed `value` path)
     chunks = (batch + chunk - 1) // chunk
     cfg_stereo = {}
     if stereo:

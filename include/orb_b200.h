@@ -108,7 +108,8 @@ int orbx_pyramid_level(orbx_ctx* ctx, int frame, int level, int with_border,
 int orbx_set_stream(orbx_ctx* ctx, void* cuda_stream);
 void* orbx_stream(const orbx_ctx* ctx);
 
-/* Frames processed per internal pass (working-set control, default chosen for the 126 MB L2). */
+/* Frames processed per internal pass.  Defaults: 64 when any buffer is host memory (the passes are what the copy /
+ * compute pipeline overlaps), 512 when everything is device resident (bounds the work buffers only).  Sets both. */
 int orbx_set_chunk(orbx_ctx* ctx, int frames_per_chunk);
 
 const char* orbx_last_error(const orbx_ctx* ctx);

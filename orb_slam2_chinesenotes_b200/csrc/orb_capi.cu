@@ -78,8 +78,11 @@ struct orbx_ctx {
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
     cudaStream_t xstream[NSLOT - 1] = { nullptr };   // extra compute streams (slots 1..)
     cudaEvent_t fork_ev = nullptr, join_ev[NSLOT - 1] = { nullptr };
-    int chunk = 64;            // frames per internal pass (measured with chunks alternating between streams: 32..256 give the same
-                               // device-resident rate, 64 the best rate with host buffers)
+    // Frames per internal pass.  With host buffers the chunks are what the copy / compute pipeline overlaps: 64 is the
+    // measured optimum (smaller: launch tails, larger: longer pipeline fill).  With everything device resident there
+    // is nothing to overlap and bigger launches are simply more efficient (1241x376: 6.66 ms per 512 frames in chunks
+    // of 64, 6.03 ms as one chunk), so the chunk only bounds the work buffers (about 2.6 MB per frame at that shape).
+    int chunk = 64, chunk_resident = 512;
     std::string err;
 
     bool have_plan = false;
@@ -300,11 +303,15 @@ int run_batch(orbx_ctx* c, const uint8_t* imgs, size_t frame_stride, int batch, 
         return fail(c, ORBX_E_ARG, "async entry point needs device pointers");
     const bool stage_out = !(kps_dev && desc_dev && n_dev) || (sr && !(ur_dev && dep_dev && ns_dev));
     const bool piped = !in_dev || stage_out;           // any host buffer: rotate slots and overlap the copies
-    int chunk = batch < c->chunk ? batch : c->chunk;
+    const int want = piped ? c->chunk : c->chunk_resident;
+    int chunk = batch < want ? batch : want;
     if (sr && chunk % 2) chunk = chunk > 1 ? chunk - 1 : 2;      // a pair never straddles two chunks
     const int nchunks = (batch + chunk - 1) / chunk;
     const int nslot = nchunks < NSLOT ? nchunks : NSLOT;
-    const bool multi = nslot > 1 && !c->profile;       // chunks alternate between compute streams
+    // Chunks alternate between compute streams only on the piped path (small chunks: one chunk's latency-bound sparse
+    // kernels share the SMs with the next chunk's dense ones).  Device-resident chunks are large; running two of
+    // them side by side measured slower than back to back (6.84 vs 6.40 ms per 512 frames in chunks of 256).
+    const bool multi = nslot > 1 && !c->profile && piped;
     const size_t in_frame_bytes = pitch * (size_t)h;
     const size_t frame_copy_bytes = pitch * (size_t)(h - 1) + (size_t)w;   // never read past the last row's pixels
     for (int s = 0; s < nslot; ++s) {
@@ -589,7 +596,7 @@ void* orbx_stream(const orbx_ctx* c) { return c ? (void*)c->stream : nullptr; }
 int orbx_set_chunk(orbx_ctx* c, int frames_per_chunk)
 {
     if (!c || frames_per_chunk < 1) return ORBX_E_ARG;
-    c->chunk = frames_per_chunk;
+    c->chunk = c->chunk_resident = frames_per_chunk;
     return ORBX_OK;
 }
 
