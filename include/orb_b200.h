@@ -207,6 +207,49 @@ int orbm_stereo_matches(orbx_ctx* ex_left, int frame_l, orbx_ctx* ex_right, int 
                         int nr, const orbx_kp* kps_r, const uint8_t* desc_r,
                         float bf, float fx, float* u_right, float* depth, int* nmatched);
 
+/* ---- matcher, batched and device resident ------------------------------------------------
+ * Many independent (frame, query set) problems per launch, one thread block each; every pointer
+ * (except `scale`) is DEVICE memory and the calls only enqueue work on `cuda_stream` (cudaStream_t,
+ * NULL = default stream).  Frames are taken exactly as orbx_extract_batch leaves them, so
+ * extraction -> matching never leaves the GPU.  Results equal those of the single-problem entry
+ * points above (and of the reference) problem by problem; a problem whose n exceeds 8192 or
+ * kp_stride, or whose nq exceeds nq_stride, gets nmatches = -1.  rounds (or NULL) [nprob] receives
+ * the number of passes the order-resolution needed (orb_match_batch.cu). */
+typedef struct {
+    int nprob;
+    const orbx_kp* kps;      /* mvKeysUn of frame p at kps + p*kp_stride */
+    const uint8_t* desc;     /* mDescriptors of frame p at desc + p*kp_stride*32 (16-byte aligned) */
+    const float* u_right;    /* mvuRight, [nprob][kp_stride], or NULL */
+    const int* n;            /* [nprob] keypoints per frame (<= min(kp_stride, 8192)) */
+    int kp_stride;
+    float min_x, max_x, min_y, max_y;   /* mnMinX..mnMaxY, shared by all frames */
+} orbm_frames;
+
+/* The map points of SearchByProjection(Frame&, const vector<MapPoint*>&, th): arrays [nprob][nq_stride]
+ * with the meaning of orbm_search_by_projection_points. */
+typedef struct {
+    const int* nq; int nq_stride;
+    const float* proj_xyxr; const int* level; const float* view_cos;
+    const uint8_t* in_view; const uint8_t* bad; const int* observations; const uint8_t* qdesc;
+} orbm_points;
+
+/* src/ORBmatcher.cc:73-157 for every problem.  init_assign / assign_out are [nprob][kp_stride]. */
+int orbm_search_by_projection_points_batch(const orbm_frames* F, const float* scale, int nlevels, const orbm_points* Q,
+                                           const int* init_assign, int* assign_out, float th, float nnratio,
+                                           int* nmatches, int* rounds, void* cuda_stream);
+
+/* Already projected queries of the best-candidate-only overloads (orbm_window_search_best): arrays
+ * [nprob][nq_stride]; ur, er_max, valid, q_angle (unless check_ori) and q_obs may be NULL. */
+typedef struct {
+    const int* nq; int nq_stride;
+    const float* uvr; const int* min_level; const int* max_level; const float* ur; const float* er_max;
+    const uint8_t* valid; const uint8_t* qdesc; const float* q_angle; const int* q_obs;
+} orbm_windows;
+
+/* src/ORBmatcher.cc:160-300 / :303-431 / :434-549 after the projection, for every problem. */
+int orbm_window_search_best_batch(const orbm_frames* F, const orbm_windows* Q, const int* init_obs, int* assign_out,
+                                  int th_accept, int check_ori, int* nmatches, int* rounds, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -30,6 +30,25 @@ class OrbmFrame(C.Structure):
                 ("min_x", C.c_float), ("max_x", C.c_float), ("min_y", C.c_float), ("max_y", C.c_float)]
 
 
+class OrbmFrames(C.Structure):
+    """orbm_frames: a batch of device-resident frames in the layout orbx_extract_batch writes."""
+    _fields_ = [("nprob", C.c_int), ("kps", C.c_void_p), ("desc", C.c_void_p), ("u_right", C.c_void_p), ("n", C.c_void_p),
+                ("kp_stride", C.c_int), ("min_x", C.c_float), ("max_x", C.c_float), ("min_y", C.c_float), ("max_y", C.c_float)]
+
+
+class OrbmPoints(C.Structure):
+    """orbm_points: device arrays [nprob][nq_stride] of the map points' tracking fields."""
+    _fields_ = [("nq", C.c_void_p), ("nq_stride", C.c_int), ("proj_xyxr", C.c_void_p), ("level", C.c_void_p), ("view_cos", C.c_void_p),
+                ("in_view", C.c_void_p), ("bad", C.c_void_p), ("observations", C.c_void_p), ("qdesc", C.c_void_p)]
+
+
+class OrbmWindows(C.Structure):
+    """orbm_windows: device arrays [nprob][nq_stride] of already projected best-only queries."""
+    _fields_ = [("nq", C.c_void_p), ("nq_stride", C.c_int), ("uvr", C.c_void_p), ("min_level", C.c_void_p), ("max_level", C.c_void_p),
+                ("ur", C.c_void_p), ("er_max", C.c_void_p), ("valid", C.c_void_p), ("qdesc", C.c_void_p), ("q_angle", C.c_void_p),
+                ("q_obs", C.c_void_p)]
+
+
 class OrbError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"orb_b200 status {code}: {msg}")
@@ -89,6 +108,9 @@ def lib():
         L.orbm_search_by_projection_points.argtypes = [fp, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, f32, f32, pi, i32]
         L.orbm_search_by_projection_frame.argtypes = [fp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, f32, vp, i32, vp, vp, f32, i32, i32, pi, i32]
         L.orbm_search_for_initialization.argtypes = [fp, fp, vp, vp, i32, f32, i32, pi, i32]
+        L.orbm_window_search_best.argtypes = [fp, i32] + [vp] * 11 + [i32, i32, pi, i32]
+        L.orbm_search_by_projection_points_batch.argtypes = [C.POINTER(OrbmFrames), vp, i32, C.POINTER(OrbmPoints), vp, vp, f32, f32, vp, vp, vp]
+        L.orbm_window_search_best_batch.argtypes = [C.POINTER(OrbmFrames), C.POINTER(OrbmWindows), vp, vp, i32, i32, vp, vp, vp]
         L.orbm_stereo_matches.argtypes = [vp, i32, vp, i32, i32, vp, vp, i32, vp, vp, f32, f32, vp, vp, pi]
         _lib = L
     return _lib
@@ -384,12 +406,43 @@ def window_search_best(F, uvr, min_level, max_level, qdesc, th_accept, check_ori
     fs = F.struct()
     p = lambda a: None if a is None else a.ctypes.data
     L = lib()
-    L.orbm_window_search_best.argtypes = [C.POINTER(OrbmFrame), C.c_int] + [C.c_void_p] * 11 + [C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int]
     rc = L.orbm_window_search_best(C.byref(fs), len(minl), p(uvr), p(minl), p(maxl), p(ur), p(em), p(va), p(qdesc), p(qa), p(qo), p(io),
                                    p(out), int(th_accept), int(check_ori), C.byref(nm), device)
     if rc:
         raise OrbError(rc, "orbm_window_search_best failed")
     return nm.value, out
+
+
+def frames_batch(kps, desc, n, bounds, u_right=None):
+    """orbm_frames over CUDA tensors laid out as orbx_extract_batch leaves them: kps [P,cap] (28-byte records, any
+    dtype), desc [P,cap,32] uint8, n [P] int32, u_right [P,cap] float32 or None."""
+    nprob, cap = int(desc.shape[0]), int(desc.shape[1])
+    return OrbmFrames(nprob, _ptr(kps), _ptr(desc), _ptr(u_right), _ptr(n), cap, *(float(b) for b in bounds))
+
+
+def search_by_projection_points_batch(frames, scale, q, nq, nq_stride, assign_out, nmatches, th, nnratio, init_assign=None,
+                                      rounds=None, stream=None):
+    """orbm_search_by_projection_points_batch (src/ORBmatcher.cc:73-157 for every problem).  q: dict of CUDA tensors
+    [P,nq_stride(,3|32)] proj, level, view_cos, in_view, bad, obs, desc; nq [P] int32.  Only enqueues."""
+    scale = np.ascontiguousarray(scale, np.float32)
+    pts = OrbmPoints(_ptr(nq), nq_stride, _ptr(q["proj"]), _ptr(q["level"]), _ptr(q["view_cos"]), _ptr(q["in_view"]), _ptr(q["bad"]),
+                     _ptr(q["obs"]), _ptr(q["desc"]))
+    rc = lib().orbm_search_by_projection_points_batch(C.byref(frames), scale.ctypes.data, len(scale), C.byref(pts), _ptr(init_assign),
+                                                      _ptr(assign_out), th, float(np.float32(nnratio)), _ptr(nmatches), _ptr(rounds), stream)
+    if rc:
+        raise OrbError(rc, "orbm_search_by_projection_points_batch failed")
+
+
+def window_search_best_batch(frames, q, nq, nq_stride, assign_out, nmatches, th_accept, check_ori, init_obs=None, rounds=None,
+                             stream=None):
+    """orbm_window_search_best_batch.  q: dict of CUDA tensors uvr, min_level, max_level, desc and optionally ur, er_max,
+    valid, q_angle, q_obs, each [P,nq_stride(,3|32)].  Only enqueues."""
+    w = OrbmWindows(_ptr(nq), nq_stride, _ptr(q["uvr"]), _ptr(q["min_level"]), _ptr(q["max_level"]), _ptr(q.get("ur")),
+                    _ptr(q.get("er_max")), _ptr(q.get("valid")), _ptr(q["desc"]), _ptr(q.get("q_angle")), _ptr(q.get("q_obs")))
+    rc = lib().orbm_window_search_best_batch(C.byref(frames), C.byref(w), _ptr(init_obs), _ptr(assign_out), int(th_accept),
+                                             int(check_ori), _ptr(nmatches), _ptr(rounds), stream)
+    if rc:
+        raise OrbError(rc, "orbm_window_search_best_batch failed")
 
 
 def stereo_matches(ex_left, ex_right, kps_l, desc_l, kps_r, desc_r, bf, fx, frame_l=0, frame_r=0):

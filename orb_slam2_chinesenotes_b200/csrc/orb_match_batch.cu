@@ -1,0 +1,442 @@
+// orb_match_batch.cu -- batched, device-resident window matchers (sm_100a): one thread block per
+// (frame, query set) problem, many problems per launch, nothing leaves the GPU between extraction
+// and matching.
+//   MODE_POINTS  ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th)   src/ORBmatcher.cc:73-157
+//   MODE_BEST    the best-candidate-only overloads once the caller has projected its points
+//                (motion model :160-300, relocalisation :303-431, loop closing :434-549)
+//   + Frame::AssignFeaturesToGrid / GetFeaturesInArea (src/Frame.cc:243-259, 348-409) and the rotation
+//     histogram with ComputeThreeMaxima (src/ORBmatcher.cc:1663-1707)
+//
+// How the reference's query ORDER is kept without walking the queries one after another.  A query skips a
+// keypoint k when the map point attached to k has Observations() > 0 (:115-117, :234-236).  Attached points only
+// change by earlier queries claiming k, and once a claimant with Observations() > 0 holds k nobody later can take
+// it, so "k is taken when query q runs"  <=>  blocker[k] < q, where blocker[k] is the FIRST query that claimed k
+// with Observations() > 0 (-1 when the point attached before the call has Observations() > 0).  Given every
+// query's decision, blocker[] follows; given blocker[], every query's decision follows independently of the
+// others.  The kernel iterates the two steps to their fixpoint: after round r the decisions of the first r
+// queries are the sequential ones (a query only reads blockers of earlier queries), so the fixpoint is reached,
+// is unique and equals the sequential result; in practice 2-4 rounds.  After the first round a query is only
+// recomputed when one of its two best candidates became blocked, or when it had skipped a blocked candidate and
+// some decision changed -- nothing else can alter its result.
+//
+// Layout per problem (built once per launch in the block): keypoints sorted by (grid column, grid row, index) --
+// the order GetFeaturesInArea returns them in -- as 16-byte records {x, y, octave | index << 8 | taken << 31,
+// uRight} plus their descriptors in the same order, so the candidates of one grid column of a window are
+// CONTIGUOUS: a warp reads 32 records and 32 descriptors with unit stride, no index indirection.  Position in
+// that order doubles as the tie-break of the reference's running best/second-best ("two smallest by
+// (distance, position)").
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <climits>
+
+#include "../../include/orb_b200.h"
+
+#define GRID_COLS 64    // FRAME_GRID_COLS, include/Frame.h:38
+#define GRID_ROWS 48    // FRAME_GRID_ROWS, include/Frame.h:37
+#define GRID_CELLS (GRID_COLS * GRID_ROWS)
+#define TH_HIGH 100     // src/ORBmatcher.cc:37
+#define HISTO_LENGTH 30 // :39
+#define MB_MAX_KP 8192
+#define MB_MAX_LEVELS 32
+#define MB_NT 512
+#define MB_NONE 0xffffffffu
+
+enum { MODE_POINTS = 0, MODE_BEST = 1 };
+
+struct MbParams {
+    // frames
+    const orbx_kp* kps; const uint32_t* desc; const float* u_right; const int* n; int kp_stride;
+    float min_x, min_y, max_x, max_y, inv_w, inv_h;
+    // queries
+    const int* nq; int nq_stride;
+    const float* f0;          // POINTS: proj_xyxr [.,3]            BEST: uvr [.,3]
+    const int* i0;            // POINTS: level                      BEST: min_level
+    const int* i1;            //                                    BEST: max_level
+    const float* f1;          // POINTS: view_cos                   BEST: ur (or null)
+    const float* f2;          //                                    BEST: er_max (or null)
+    const uint8_t* b0;        // POINTS: in_view                    BEST: valid (or null)
+    const uint8_t* b1;        // POINTS: bad
+    const int* qobs;          // Observations() of the queries' points (BEST: null = 1)
+    const uint32_t* qdesc;
+    const float* q_angle;     // BEST + check_ori
+    const int* init;          // POINTS: init_assign [.,kp_stride]  BEST: init_obs [.,kp_stride]   (or null)
+    int* assign_out; int* nmatches;
+    float th, nnratio; int nlevels, th_accept, check_ori;
+    float scale[MB_MAX_LEVELS];
+    // workspace
+    uint4* rec; uint32_t* sdesc;     // [nprob][kp_stride], [nprob][kp_stride][8]
+    int sn_max, nq_max;              // shared-memory sizing
+    int* rounds;                     // [nprob] or null: fixpoint rounds used (profiling / tests)
+};
+
+struct WinQ { float u, v, r, ur, er_max; int min_level, max_level, valid; };
+
+template <int MODE>
+__device__ __forceinline__ WinQ load_query(const MbParams& P, const size_t qo)
+{
+    WinQ Q;
+    if (MODE == MODE_POINTS) {
+        const int level = P.i0[qo];
+        Q.valid = P.b0[qo] && !P.b1[qo] && level >= 0 && level < P.nlevels;     // :82-85
+        float r = ((double)P.f1[qo] > 0.998) ? 2.5f : 4.0f;                     // RadiusByViewingCos, :1653-1660
+        if (P.th != 1.0f) r = __fmul_rn(r, P.th);                               // :76, :90-91
+        const float rs = Q.valid ? __fmul_rn(r, P.scale[level]) : 0.f;
+        Q.u = P.f0[3 * qo]; Q.v = P.f0[3 * qo + 1]; Q.ur = P.f0[3 * qo + 2];
+        Q.r = rs; Q.er_max = rs;                                                // :93-95, :121-123
+        Q.min_level = level - 1; Q.max_level = level;
+    } else {
+        Q.valid = P.b0 ? (P.b0[qo] != 0) : 1;
+        Q.u = P.f0[3 * qo]; Q.v = P.f0[3 * qo + 1]; Q.r = P.f0[3 * qo + 2];
+        Q.min_level = P.i0[qo]; Q.max_level = P.i1[qo];
+        Q.ur = P.f1 ? P.f1[qo] : 0.f; Q.er_max = P.f2 ? P.f2[qo] : 3.0e38f;
+    }
+    return Q;
+}
+
+__device__ __forceinline__ int mb_rot_bin(const float a1, const float a2)   // src/ORBmatcher.cc:263-268
+{
+    float rot = __fsub_rn(a1, a2);
+    if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+    int bin = (int)roundf(__fmul_rn(rot, 1.0f / HISTO_LENGTH));
+    if (bin == HISTO_LENGTH) bin = 0;
+    return bin;
+}
+
+// One query, one warp: the two smallest (distance << 16 | position) keys among the candidates that are not
+// taken, and whether a taken candidate was skipped.
+template <int MODE>
+__device__ __forceinline__ void query_top2(const MbParams& P, const WinQ& Q, const int q, const uint32_t* __restrict__ qd,
+                                           const uint4* rec, const uint4* sdesc, const int* cell_start,
+                                           const int* blk, const bool use_ur, const int lane, uint32_t& k1, uint32_t& k2, bool& skipped)
+{
+    k1 = MB_NONE; k2 = MB_NONE; skipped = false;
+    // src/Frame.cc:355-372
+    const int nMinCellX = max(0, (int)floorf((Q.u - P.min_x - Q.r) * P.inv_w));
+    const int nMaxCellX = min(GRID_COLS - 1, (int)ceilf((Q.u - P.min_x + Q.r) * P.inv_w));
+    const int nMinCellY = max(0, (int)floorf((Q.v - P.min_y - Q.r) * P.inv_h));
+    const int nMaxCellY = min(GRID_ROWS - 1, (int)ceilf((Q.v - P.min_y + Q.r) * P.inv_h));
+    if (nMinCellX >= GRID_COLS || nMaxCellX < 0 || nMinCellY >= GRID_ROWS || nMaxCellY < 0) return;
+    const bool check_levels = Q.min_level > 0 || Q.max_level >= 0;               // :375
+    const uint32_t d0 = __ldg(qd), d1 = __ldg(qd + 1), d2 = __ldg(qd + 2), d3 = __ldg(qd + 3),
+                   d4 = __ldg(qd + 4), d5 = __ldg(qd + 5), d6 = __ldg(qd + 6), d7 = __ldg(qd + 7);
+    uint32_t a1 = MB_NONE, a2 = MB_NONE;
+    int nb = 0;
+    for (int ix = nMinCellX; ix <= nMaxCellX; ++ix) {
+        const int s0 = cell_start[ix * GRID_ROWS + nMinCellY], s1 = cell_start[ix * GRID_ROWS + nMaxCellY + 1];
+        for (int j = s0 + lane; j < s1; j += 32) {
+            const uint4 r = rec[j];
+            const int oct = (int)(r.z & 0xffu);
+            if (check_levels) {
+                if (oct < Q.min_level) continue;
+                if (Q.max_level >= 0 && oct > Q.max_level) continue;
+            }
+            if (!(fabsf(__uint_as_float(r.x) - Q.u) < Q.r && fabsf(__uint_as_float(r.y) - Q.v) < Q.r)) continue;   // :402
+            if (blk[j] < q) { ++nb; continue; }                                   // src/ORBmatcher.cc:115-117 / :234-236
+            if (use_ur) {
+                const float ur = __uint_as_float(r.w);
+                if (ur > 0 && fabsf(Q.ur - ur) > Q.er_max) continue;             // :119-124 / :238-244
+            }
+            const uint4 b0 = sdesc[2 * j], b1 = sdesc[2 * j + 1];
+            const uint32_t dist = __popc(d0 ^ b0.x) + __popc(d1 ^ b0.y) + __popc(d2 ^ b0.z) + __popc(d3 ^ b0.w) +
+                                  __popc(d4 ^ b1.x) + __popc(d5 ^ b1.y) + __popc(d6 ^ b1.z) + __popc(d7 ^ b1.w);
+            const uint32_t key = (dist << 16) | (uint32_t)j;
+            if (key < a1) { a2 = a1; a1 = key; }
+            else if (key < a2) a2 = key;
+        }
+    }
+    k1 = __reduce_min_sync(0xffffffffu, a1);
+    if (a1 == k1) a1 = a2;                        // keys are unique (position) or "none"
+    k2 = __reduce_min_sync(0xffffffffu, a1);
+    skipped = __any_sync(0xffffffffu, nb > 0);
+    (void)MODE;
+}
+
+// The blocked-candidate order matters: in the reference the "taken" test comes BEFORE the right-image test, and
+// both only `continue`, so their order does not change the candidate set.
+
+template <int MODE>
+__global__ void __launch_bounds__(MB_NT) k_match_fixpoint(const __grid_constant__ MbParams P)
+{
+    extern __shared__ __align__(16) uint32_t smem[];
+    __shared__ int s_flag[2], s_cnt[2], s_sizes[HISTO_LENGTH], s_ind[3];
+    const int prob = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = MB_NT >> 5;
+    const int n = P.n[prob], nq = P.nq[prob];
+    int* const nm_out = P.nmatches + prob;
+    if (n < 0 || n > MB_MAX_KP || n > P.kp_stride || nq < 0 || nq > P.nq_stride) { if (tid == 0) *nm_out = -1; return; }
+    const size_t ko = (size_t)prob * P.kp_stride, qo = (size_t)prob * P.nq_stride;
+    const orbx_kp* kps = P.kps + ko;
+    const int* init = P.init ? P.init + ko : nullptr;
+    int* assign_out = P.assign_out + ko;
+    const int* qobs = P.qobs ? P.qobs + qo : nullptr;
+    int sn = 32; while (sn < n) sn <<= 1;
+    uint32_t* keys = smem;                                  // [sn_max]
+    int* cell_start = (int*)(smem + P.sn_max);              // [GRID_CELLS + 1] (+3 pad)
+    int* blk = cell_start + GRID_CELLS + 4;                 // [sn_max]
+    uint32_t* st_top = (uint32_t*)(blk + P.sn_max);         // [nq_max]  k1 position | k2 position << 16 (0xffff none)
+    uint32_t* st_best = st_top + P.nq_max;                  // [nq_max]  (accepted position + 1) | skipped << 16 | bin << 24
+    uint4* rec = P.rec + ko;
+    uint4* sdesc = (uint4*)(P.sdesc + ko * 8);
+
+    // ---- Frame::AssignFeaturesToGrid (src/Frame.cc:243-259): cell of every keypoint (round(), :414-415), sorted
+    for (int i = tid; i < sn; i += MB_NT) {
+        uint32_t key = MB_NONE;
+        if (i < n) {
+            const int px = (int)roundf((kps[i].x - P.min_x) * P.inv_w);
+            const int py = (int)roundf((kps[i].y - P.min_y) * P.inv_h);
+            if (!(px < 0 || px >= GRID_COLS || py < 0 || py >= GRID_ROWS)) key = ((uint32_t)(px * GRID_ROWS + py) << 16) | (uint32_t)i;
+        }
+        keys[i] = key;
+    }
+    __syncthreads();
+    for (int k = 2; k <= sn; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < (sn >> 1); t += MB_NT) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), ixj = i | j;
+                const uint32_t a = keys[i], b = keys[ixj];
+                if (((i & k) == 0) ? (a > b) : (a < b)) { keys[i] = b; keys[ixj] = a; }
+            }
+            __syncthreads();
+        }
+    for (int i = tid; i < sn; i += MB_NT) {
+        const uint32_t key = keys[i];
+        const int c = key == MB_NONE ? GRID_CELLS : (int)(key >> 16);
+        const int cprev = i == 0 ? -1 : (keys[i - 1] == MB_NONE ? GRID_CELLS : (int)(keys[i - 1] >> 16));
+        for (int cc = cprev + 1; cc <= c; ++cc) cell_start[cc] = i;
+        if (i == sn - 1) for (int cc = c + 1; cc <= GRID_CELLS; ++cc) cell_start[cc] = sn;
+    }
+    __syncthreads();
+    const int nvalid = cell_start[GRID_CELLS];
+    const bool use_ur = P.u_right != nullptr && (MODE == MODE_POINTS || P.f1 != nullptr);
+    for (int j = tid; j < nvalid; j += MB_NT) {
+        const int idx = (int)(keys[j] & 0xffffu);
+        const orbx_kp kp = kps[idx];
+        uint32_t taken = 0;
+        if (init) {
+            const int a = init[idx];
+            if (MODE == MODE_POINTS) taken = (a >= 0 && qobs[a] > 0) ? 1u : 0u;   // attached point with Observations() > 0
+            else taken = a > 0 ? 1u : 0u;
+        }
+        rec[j] = make_uint4(__float_as_uint(kp.x), __float_as_uint(kp.y), (uint32_t)(kp.octave & 0xff) | ((uint32_t)idx << 8) | (taken << 31),
+                            __float_as_uint(use_ur ? P.u_right[ko + idx] : -1.0f));
+        blk[j] = taken ? -1 : INT_MAX;
+    }
+    // descriptors into position order: 8 threads move one descriptor (coalesced 32-byte rows on both sides)
+    for (int t = tid; t < nvalid * 8; t += MB_NT) {
+        const int j = t >> 3, wd = t & 7;
+        ((uint32_t*)sdesc)[(size_t)j * 8 + wd] = P.desc[(ko + (keys[j] & 0xffffu)) * 8 + wd];
+    }
+    for (int q = tid; q < nq; q += MB_NT) { st_top[q] = MB_NONE; st_best[q] = 0; }
+    if (tid == 0) { s_flag[0] = 0; s_flag[1] = 0; s_cnt[0] = 0; s_cnt[1] = 0; }
+    if (tid < HISTO_LENGTH) s_sizes[tid] = 0;
+    __syncthreads();       // rec / sdesc are read back by this block only
+
+    // ---- rounds
+    int round = 0;
+    bool prev_changed = true;
+    for (;; ++round) {
+        const int par = round & 1;
+        for (int base = warp * 32; base < nq; base += nwarps * 32) {
+            const int q = base + lane;
+            bool need = false;
+            if (q < nq) {
+                if (round == 0) need = true;
+                else {
+                    const uint32_t top = st_top[q], sb = st_best[q];
+                    const uint32_t p1 = top & 0xffffu, p2 = top >> 16;
+                    need = (p1 != 0xffffu && blk[p1] < q) || (p2 != 0xffffu && blk[p2] < q) || (((sb >> 16) & 1u) && prev_changed);
+                }
+            }
+            unsigned m = __ballot_sync(0xffffffffu, need);
+            while (m) {
+                const int b = __ffs(m) - 1;
+                m &= m - 1;
+                const int qq = base + b;
+                const WinQ Q = load_query<MODE>(P, qo + qq);
+                uint32_t k1 = MB_NONE, k2 = MB_NONE;
+                bool skipped = false;
+                if (Q.valid) query_top2<MODE>(P, Q, qq, P.qdesc + (qo + qq) * 8, rec, sdesc, cell_start, blk, use_ur, lane, k1, k2, skipped);
+                if (lane == 0) {
+                    int best = -1;
+                    if (k1 != MB_NONE) {
+                        const int bestDist = (int)(k1 >> 16);
+                        if (MODE == MODE_POINTS) {
+                            if (bestDist <= TH_HIGH) {                                                  // :143
+                                const int bestLevel = (int)(rec[k1 & 0xffffu].z & 0xffu);
+                                int bestDist2 = 256, bestLevel2 = -1;
+                                if (k2 != MB_NONE) { bestDist2 = (int)(k2 >> 16); bestLevel2 = (int)(rec[k2 & 0xffffu].z & 0xffu); }
+                                if (!(bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(P.nnratio, (float)bestDist2)))   // :146-149
+                                    best = (int)(k1 & 0xffffu);
+                            }
+                        } else if (bestDist <= P.th_accept) best = (int)(k1 & 0xffffu);                // :256 / :381 / :530
+                    }
+                    const uint32_t nb = (uint32_t)(best + 1) | (skipped ? 0x10000u : 0u);
+                    if ((st_best[qq] & 0xffffu) != (uint32_t)(best + 1)) s_flag[par] = 1;
+                    st_best[qq] = nb;
+                    st_top[qq] = (k1 == MB_NONE ? 0xffffu : (k1 & 0xffffu)) | ((k2 == MB_NONE ? 0xffffu : (k2 & 0xffffu)) << 16);
+                }
+            }
+        }
+        __syncthreads();
+        const bool changed = s_flag[par] != 0;
+        if (!changed) break;
+        // blocker[] from the decisions
+        for (int j = tid; j < nvalid; j += MB_NT) blk[j] = (rec[j].z >> 31) ? -1 : INT_MAX;
+        if (tid == 0) s_flag[par ^ 1] = 0;
+        __syncthreads();
+        for (int q = tid; q < nq; q += MB_NT) {
+            const int b = (int)(st_best[q] & 0xffffu) - 1;
+            if (b >= 0 && (qobs ? qobs[q] : 1) > 0) atomicMin(&blk[b], q);
+        }
+        __syncthreads();
+        prev_changed = true;
+    }
+    if (P.rounds && tid == 0) P.rounds[prob] = round + 1;
+
+    // ---- results.  Last writer of a keypoint = its largest claimant (every claimant precedes the blocker or is it).
+    for (int k = tid; k < n; k += MB_NT) {
+        int a = -1;
+        if (init) a = MODE == MODE_POINTS ? init[k] : (init[k] >= 0 ? -2 : -1);
+        assign_out[k] = a;
+    }
+    for (int j = tid; j < nvalid; j += MB_NT) blk[j] = -1;
+    __syncthreads();
+    int mine = 0;
+    for (int q = tid; q < nq; q += MB_NT) {
+        const int b = (int)(st_best[q] & 0xffffu) - 1;
+        if (b < 0) continue;
+        ++mine;
+        atomicMax(&blk[b], q);
+        if (MODE == MODE_BEST && P.check_ori) {
+            const int bin = mb_rot_bin(P.q_angle[qo + q], kps[rec[b].z >> 8 & 0x7fffffu].angle);
+            st_top[q] = (uint32_t)bin;
+            atomicAdd(&s_sizes[bin], 1);
+        }
+    }
+    if (mine) atomicAdd(&s_cnt[0], mine);
+    __syncthreads();
+    if (MODE == MODE_BEST && P.check_ori) {
+        if (tid == 0) {   // ComputeThreeMaxima, src/ORBmatcher.cc:1663-1707
+            int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
+            for (int i = 0; i < HISTO_LENGTH; ++i) {
+                const int s = s_sizes[i];
+                if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+                else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+                else if (s > max3) { max3 = s; ind3 = i; }
+            }
+            if ((float)max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+            else if ((float)max3 < 0.1f * (float)max1) ind3 = -1;
+            s_ind[0] = ind1; s_ind[1] = ind2; s_ind[2] = ind3;
+        }
+        __syncthreads();
+        // every entry of a rejected bin clears its keypoint and decrements, duplicates included (:286-296)
+        int dec = 0;
+        for (int q = tid; q < nq; q += MB_NT) {
+            const int b = (int)(st_best[q] & 0xffffu) - 1;
+            if (b < 0) continue;
+            const int bin = (int)st_top[q];
+            if (bin != s_ind[0] && bin != s_ind[1] && bin != s_ind[2]) { blk[b] = -3; ++dec; }
+        }
+        if (dec) atomicAdd(&s_cnt[1], dec);
+        __syncthreads();
+    }
+    for (int j = tid; j < nvalid; j += MB_NT) {
+        const int w = blk[j];
+        if (w >= 0) assign_out[rec[j].z >> 8 & 0x7fffffu] = w;
+        else if (w == -3) assign_out[rec[j].z >> 8 & 0x7fffffu] = -1;
+    }
+    if (tid == 0) *nm_out = s_cnt[0] - s_cnt[1];
+}
+
+// ================================================================================ host side
+namespace {
+struct DevGuard {   // restores the caller's current device
+    int prev = -1;
+    ~DevGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+int device_of(const void* p)
+{
+    cudaPointerAttributes a;
+    if (!p || cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return -1; }
+    if (a.type != cudaMemoryTypeDevice && a.type != cudaMemoryTypeManaged) return -1;
+    return a.device;
+}
+
+template <int MODE>
+int launch(MbParams& P, int nprob, cudaStream_t st)
+{
+    const int dev = device_of(P.kps);
+    if (dev < 0 || device_of(P.assign_out) != dev || device_of(P.nmatches) != dev || device_of(P.qdesc) != dev) return ORBX_E_ARG;
+    DevGuard g;
+    if (cudaGetDevice(&g.prev) != cudaSuccess || cudaSetDevice(dev) != cudaSuccess) { cudaGetLastError(); return ORBX_E_CUDA; }
+    int sn = 32; while (sn < P.kp_stride && sn < MB_MAX_KP) sn <<= 1;
+    P.sn_max = sn;
+    P.nq_max = (P.nq_stride + 3) & ~3;
+    const size_t smem = ((size_t)P.sn_max * 2 + GRID_CELLS + 4 + (size_t)P.nq_max * 2) * 4;
+    if (smem > 220 * 1024) return ORBX_E_ARG;
+    void* ws = nullptr;
+    const size_t rec_bytes = (size_t)nprob * P.kp_stride * sizeof(uint4), ws_bytes = rec_bytes + (size_t)nprob * P.kp_stride * 32;
+    if (cudaMallocAsync(&ws, ws_bytes, st) != cudaSuccess) { cudaGetLastError(); return ORBX_E_CUDA; }
+    P.rec = (uint4*)ws;
+    P.sdesc = (uint32_t*)((char*)ws + rec_bytes);
+    cudaError_t e = cudaSuccess;
+    if (smem > 48 * 1024) e = cudaFuncSetAttribute(k_match_fixpoint<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) {
+        k_match_fixpoint<MODE><<<nprob, MB_NT, smem, st>>>(P);
+        e = cudaGetLastError();
+    }
+    cudaFreeAsync(ws, st);
+    if (e != cudaSuccess) { cudaGetLastError(); return ORBX_E_CUDA; }
+    return ORBX_OK;
+}
+
+bool fill_frames(MbParams& P, const orbm_frames* F)
+{
+    if (!F || F->nprob <= 0 || !F->kps || !F->desc || !F->n || F->kp_stride <= 0) return false;
+    if (((uintptr_t)F->desc & 15) || ((uintptr_t)F->kps & 3)) return false;
+    P.kps = F->kps; P.desc = (const uint32_t*)F->desc; P.u_right = F->u_right; P.n = F->n; P.kp_stride = F->kp_stride;
+    P.min_x = F->min_x; P.min_y = F->min_y; P.max_x = F->max_x; P.max_y = F->max_y;
+    P.inv_w = (float)GRID_COLS / (F->max_x - F->min_x);     // src/Frame.cc:108
+    P.inv_h = (float)GRID_ROWS / (F->max_y - F->min_y);     // :109
+    return true;
+}
+} // namespace
+
+extern "C" {
+
+int orbm_search_by_projection_points_batch(const orbm_frames* F, const float* scale, int nlevels, const orbm_points* Q,
+                                           const int* init_assign, int* assign_out, float th, float nnratio,
+                                           int* nmatches, int* rounds, void* cuda_stream)
+{
+    MbParams P = {};
+    if (!fill_frames(P, F) || !scale || nlevels <= 0 || nlevels > MB_MAX_LEVELS || !Q || !Q->nq || Q->nq_stride <= 0 || Q->nq_stride > MB_MAX_KP * 4 ||
+        !Q->proj_xyxr || !Q->level || !Q->view_cos || !Q->in_view || !Q->bad || !Q->observations || !Q->qdesc || !assign_out || !nmatches)
+        return ORBX_E_ARG;
+    if ((uintptr_t)Q->qdesc & 15) return ORBX_E_ARG;
+    P.nq = Q->nq; P.nq_stride = Q->nq_stride;
+    P.f0 = Q->proj_xyxr; P.i0 = Q->level; P.f1 = Q->view_cos; P.b0 = Q->in_view; P.b1 = Q->bad; P.qobs = Q->observations;
+    P.qdesc = (const uint32_t*)Q->qdesc;
+    P.init = init_assign; P.assign_out = assign_out; P.nmatches = nmatches; P.rounds = rounds;
+    P.th = th; P.nnratio = nnratio; P.nlevels = nlevels;
+    for (int i = 0; i < nlevels; ++i) P.scale[i] = scale[i];
+    return launch<MODE_POINTS>(P, F->nprob, (cudaStream_t)cuda_stream);
+}
+
+int orbm_window_search_best_batch(const orbm_frames* F, const orbm_windows* Q, const int* init_obs, int* assign_out,
+                                  int th_accept, int check_ori, int* nmatches, int* rounds, void* cuda_stream)
+{
+    MbParams P = {};
+    if (!fill_frames(P, F) || !Q || !Q->nq || Q->nq_stride <= 0 || Q->nq_stride > MB_MAX_KP * 4 || !Q->uvr || !Q->min_level || !Q->max_level ||
+        !Q->qdesc || !assign_out || !nmatches || (check_ori && !Q->q_angle))
+        return ORBX_E_ARG;
+    if ((uintptr_t)Q->qdesc & 15) return ORBX_E_ARG;
+    P.nq = Q->nq; P.nq_stride = Q->nq_stride;
+    P.f0 = Q->uvr; P.i0 = Q->min_level; P.i1 = Q->max_level; P.f1 = Q->ur; P.f2 = Q->er_max; P.b0 = Q->valid; P.qobs = Q->q_obs;
+    P.qdesc = (const uint32_t*)Q->qdesc; P.q_angle = Q->q_angle;
+    P.init = init_obs; P.assign_out = assign_out; P.nmatches = nmatches; P.rounds = rounds;
+    P.th_accept = th_accept; P.check_ori = check_ori;
+    return launch<MODE_BEST>(P, F->nprob, (cudaStream_t)cuda_stream);
+}
+
+} // extern "C"

@@ -1,0 +1,175 @@
+"""Batched, device-resident window matchers (orbm_*_batch, csrc/orb_match_batch.cu) through the C ABI against
+the oracle, problem by problem: match indices and counts identical, including the order-dependent "keypoint
+already taken" bookkeeping that the kernel resolves by fixpoint rounds instead of walking the queries in order."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import orb_slam2_chinesenotes_b200 as ob
+from matcher_lib import Matcher, extract_frame, perturbed_frame, projected_queries
+from oracle_lib import KP_DTYPE, oracle
+
+pytestmark = pytest.mark.gpu
+W, H, NF = 1241, 376, 2000
+
+
+@pytest.fixture(scope="module")
+def scene():
+    kps, desc, scale = extract_frame(W, H, NF, 2)
+    k2, d2, _ = perturbed_frame(kps, desc, W, H, 11)
+    return dict(kps=kps, desc=desc, scale=scale, k2=k2, d2=d2)
+
+
+def _dev(a):
+    import torch
+    a = np.ascontiguousarray(a)
+    if a.dtype == KP_DTYPE:
+        a = a.view(np.uint8).reshape(a.shape + (28,))
+    return torch.from_numpy(a).cuda()
+
+
+def _pad(rows, stride, fill=0):
+    """list of [n_i, ...] arrays -> [P, stride, ...]"""
+    out = np.full((len(rows), stride) + rows[0].shape[1:], fill, rows[0].dtype)
+    for i, r in enumerate(rows):
+        out[i, :len(r)] = r
+    return out
+
+
+def _frames(problems, bounds, cap, with_ur):
+    import torch
+    kps = np.zeros((len(problems), cap), KP_DTYPE)
+    for i, p in enumerate(problems):
+        kps[i, :len(p["kps"])] = p["kps"]
+    d_kps = _dev(kps)
+    d_desc = _dev(_pad([p["desc"] for p in problems], cap))
+    d_n = _dev(np.int32([len(p["kps"]) for p in problems]))
+    d_ur = _dev(_pad([p["ur"] for p in problems], cap, -1)) if with_ur else None
+    keep = (d_kps, d_desc, d_n, d_ur)
+    return ob.frames_batch(d_kps, d_desc, d_n, bounds, d_ur), keep
+
+
+@pytest.mark.parametrize("th,nnratio,with_ur,bounds", [(3.0, 0.8, False, (0.0, float(W), 0.0, float(H))),
+                                                      (5.0, 0.9, True, (0.0, float(W), 0.0, float(H))),
+                                                      (1.0, 0.9, True, (40.0, W - 60.0, 25.0, H - 30.0))])
+def test_points_batch_equals_oracle(scene, th, nnratio, with_ur, bounds):
+    import torch
+    O = Matcher("oracle")
+    rng = np.random.default_rng(100)
+    k2, d2 = scene["k2"], scene["d2"]
+    problems = []
+    for i, (n, nq) in enumerate([(len(k2), 2000), (1500, 2500), (len(k2), 700), (0, 50), (300, 0), (1999, 1999), (64, 3000)]):
+        sel = rng.permutation(len(k2))[:n]
+        kp, de = k2[sel].copy(), d2[sel].copy()
+        q = projected_queries(kp, de, max(nq, 1), 200 + i) if n else projected_queries(k2, d2, max(nq, 1), 200 + i)
+        q = {k: v[:nq] for k, v in q.items()}
+        ur = np.where(rng.random(n) < 0.5, kp["x"] - 20 * rng.random(n), -1).astype(np.float32)
+        init = np.where(rng.random(n) < 0.05, rng.integers(0, max(nq, 1), n), -1).astype(np.int32) if nq else np.full(n, -1, np.int32)
+        problems.append(dict(kps=kp, desc=de, q=q, ur=ur, init=init, nq=nq))
+    cap, nqs = 2100, 3000
+    F, keep = _frames(problems, bounds, cap, with_ur)
+    dq = {k: _dev(_pad([p["q"][k] for p in problems], nqs)) for k in ("proj", "level", "view_cos", "in_view", "bad", "obs", "desc")}
+    d_nq = _dev(np.int32([p["nq"] for p in problems]))
+    for use_init in (False, True):
+        d_init = _dev(_pad([p["init"] for p in problems], cap, -1)) if use_init else None
+        d_assign = torch.full((len(problems), cap), -7, dtype=torch.int32, device="cuda")
+        d_nm = torch.zeros(len(problems), dtype=torch.int32, device="cuda")
+        d_rounds = torch.zeros(len(problems), dtype=torch.int32, device="cuda")
+        ob.search_by_projection_points_batch(F, scene["scale"], dq, d_nq, nqs, d_assign, d_nm, th, nnratio, d_init, d_rounds)
+        torch.cuda.synchronize()
+        assign, nm, rounds = d_assign.cpu().numpy(), d_nm.cpu().numpy(), d_rounds.cpu().numpy()
+        total = 0
+        for i, p in enumerate(problems):
+            n = len(p["kps"])
+            want = O.search_by_projection_points(p["kps"], p["desc"], p["ur"] if with_ur else None, scene["scale"], bounds, p["q"], th, nnratio,
+                                                 p["init"] if use_init else None) if n and p["nq"] else (0, p["init"] if use_init else np.full(n, -1, np.int32))
+            assert nm[i] == want[0], (i, nm[i], want[0])
+            assert (assign[i, :n] == want[1]).all(), i
+            assert (assign[i, n:] == -7).all()
+            total += want[0]
+        assert total > 800 and rounds.max() >= 2 and rounds.max() < 64, rounds   # conflicts were exercised and resolved in a few rounds
+
+
+def test_best_batch_equals_oracle(scene):
+    import torch
+    rng = np.random.default_rng(12)
+    k2, d2 = scene["k2"], scene["d2"]
+    bounds = (0.0, float(W), 0.0, float(H))
+    O = oracle()
+    vp, ci, cf = C.c_void_p, C.c_int, C.c_float
+    O.orbo_window_search_best.argtypes = [ci, vp, vp, vp] + [cf] * 4 + [ci] + [vp] * 11 + [ci, ci]
+    problems = []
+    for n, nq in [(len(k2), 1500), (1200, 2200), (len(k2), 1)]:
+        sel = rng.permutation(len(k2))[:n]
+        kp, de = k2[sel].copy(), d2[sel].copy()
+        tgt = rng.integers(0, n, nq)
+        tgt[::4] = rng.integers(0, 30, len(tgt[::4]))       # many queries compete for the same keypoints
+        q = dict(uvr=np.stack([kp["x"][tgt] + rng.normal(0, 4, nq), kp["y"][tgt] + rng.normal(0, 4, nq), rng.choice([3.0, 8.0, 20.0, 60.0], nq)], 1).astype(np.float32),
+                 min_level=rng.integers(-1, 4, nq).astype(np.int32))
+        q["max_level"] = np.where(rng.random(nq) < 0.3, -1, q["min_level"] + rng.integers(0, 3, nq)).astype(np.int32)
+        q["ur"] = (q["uvr"][:, 0] - 12 + rng.normal(0, 6, nq)).astype(np.float32)
+        q["er_max"] = rng.choice([2.0, 6.0, 15.0], nq).astype(np.float32)
+        q["valid"] = (rng.random(nq) < 0.9).astype(np.uint8)
+        qd = de[tgt].copy(); qd[:, :4] ^= rng.integers(0, 256, (nq, 4), dtype=np.uint8)
+        q["desc"] = qd
+        q["q_angle"] = ((kp["angle"][tgt] + 40 + rng.normal(0, 8, nq)) % 360).astype(np.float32)
+        q["q_obs"] = (rng.random(nq) < 0.8).astype(np.int32)
+        problems.append(dict(kps=kp, desc=de, q=q, nq=nq, ur=np.where(rng.random(n) < 0.5, kp["x"] - 25 * rng.random(n), -1).astype(np.float32),
+                             init=np.where(rng.random(n) < 0.1, rng.integers(0, 2, n), -1).astype(np.int32)))
+    cap, nqs = 2048, 2200
+    F, keep = _frames(problems, bounds, cap, True)
+    dq = {k: _dev(_pad([p["q"][k] for p in problems], nqs)) for k in problems[0]["q"]}
+    d_nq = _dev(np.int32([p["nq"] for p in problems]))
+    d_init = _dev(_pad([p["init"] for p in problems], cap, -1))
+    for th_accept, check_ori in ((100, True), (50, False), (64, True)):
+        d_assign = torch.full((len(problems), cap), -7, dtype=torch.int32, device="cuda")
+        d_nm = torch.zeros(len(problems), dtype=torch.int32, device="cuda")
+        ob.window_search_best_batch(F, dq, d_nq, nqs, d_assign, d_nm, th_accept, check_ori, d_init)
+        torch.cuda.synchronize()
+        assign, nm = d_assign.cpu().numpy(), d_nm.cpu().numpy()
+        for i, pr in enumerate(problems):
+            n, nq, q = len(pr["kps"]), pr["nq"], pr["q"]
+            ref_assign = np.zeros(n, np.int32)
+            p = lambda a: a.ctypes.data
+            want = O.orbo_window_search_best(n, p(pr["kps"]), p(pr["desc"]), p(pr["ur"]), *bounds, nq, p(q["uvr"]), p(q["min_level"]), p(q["max_level"]),
+                                             p(q["ur"]), p(q["er_max"]), p(q["valid"]), p(q["desc"]), p(q["q_angle"]), p(q["q_obs"]), p(pr["init"]),
+                                             p(ref_assign), th_accept, int(check_ori))
+            assert nm[i] == want, (i, nm[i], want)
+            assert (assign[i, :n] == ref_assign).all(), i
+        assert nm[:2].min() > 100
+
+
+def test_batch_equals_single_problem_entry_point(scene):
+    """The batch kernel and the single-problem entry point (host arrays, three kernels) agree."""
+    import torch
+    bounds = (0.0, float(W), 0.0, float(H))
+    k2, d2 = scene["k2"], scene["d2"]
+    q = projected_queries(k2, d2, 2000, 5)
+    F1 = ob.FrameView(k2, d2, bounds)
+    want = ob.ORBmatcher(0.9, True).SearchByProjection(F1, scene["scale"], q, 3.0)
+    pr = [dict(kps=k2, desc=d2)]
+    F, keep = _frames(pr, bounds, len(k2), False)
+    dq = {k: _dev(q[k][None]) for k in q}
+    d_assign = torch.zeros((1, len(k2)), dtype=torch.int32, device="cuda")
+    d_nm = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ob.search_by_projection_points_batch(F, scene["scale"], dq, _dev(np.int32([2000])), 2000, d_assign, d_nm, 3.0, 0.9)
+    torch.cuda.synchronize()
+    assert int(d_nm[0]) == want[0] and (d_assign[0].cpu().numpy() == want[1]).all()
+
+
+def test_batch_rejects_oversized_problems(scene):
+    import torch
+    bounds = (0.0, float(W), 0.0, float(H))
+    pr = [dict(kps=scene["k2"][:100], desc=scene["d2"][:100])]
+    F, keep = _frames(pr, bounds, 128, False)
+    keep[2].fill_(500)                                   # n > kp_stride
+    q = projected_queries(scene["k2"][:100], scene["d2"][:100], 10, 1)
+    dq = {k: _dev(q[k][None]) for k in q}
+    d_assign = torch.zeros((1, 128), dtype=torch.int32, device="cuda")
+    d_nm = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ob.search_by_projection_points_batch(F, scene["scale"], dq, _dev(np.int32([10])), 10, d_assign, d_nm, 3.0, 0.9)
+    torch.cuda.synchronize()
+    assert int(d_nm[0]) == -1
+    with pytest.raises(ob.OrbError):
+        ob.search_by_projection_points_batch(F, scene["scale"], {k: v.cpu() for k, v in dq.items()}, _dev(np.int32([10])), 10, d_assign, d_nm, 3.0, 0.9)
