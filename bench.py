@@ -267,6 +267,84 @@ def bench_hamming(dev, device_index, nq=2000, nt=2000, nprob=256, reps=5):
             "peak_note": "SMs x 16 POPC/clk x 1965 MHz / 8 POPC per pair"}
 
 
+def bench_window_match(dev, d_kps, d_desc, d_n, cap, w, h, scale, nprob=512, nq=2000, reps=5, cpu=True):
+    """BASELINE.json configs[3]: windowed SearchByProjection(Frame, MapPoints) matching (src/ORBmatcher.cc:73-157),
+    2000 map points against the ~2000 keypoints of a frame, TH_HIGH = 100, nnratio = 0.9, th = 3, for `nprob` frames per
+    launch.  The frames are the left images the extractor just produced and stay where it left them in HBM; the
+    queries are built on the device as SURVEY.md section 8d describes (descriptor of a random keypoint with
+    k ~ U[0,80] bit flips, projection = keypoint + N(0, 3 px), level = its octave)."""
+    import torch
+    import orb_slam2_chinesenotes_b200 as ob
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    nprob = min(nprob, d_kps.shape[0] // 2)
+    nprob = (nprob // sms) * sms or nprob                           # whole waves: one block per SM
+    kps, desc, n = d_kps[0:2 * nprob:2].contiguous(), d_desc[0:2 * nprob:2].contiguous(), d_n[0:2 * nprob:2].contiguous()
+    g = torch.Generator(device=dev).manual_seed(11)
+    tgt = (torch.rand((nprob, nq), generator=g, device=dev) * n[:, None]).long().clamp_(max=cap - 1)
+    tgt[:, ::5] = tgt[:, ::5] % 40                                  # every 5th query competes for the first 40 keypoints
+    gi = tgt[..., None].expand(-1, -1, 7)
+    kq = torch.gather(kps, 1, gi)
+    proj = torch.stack([kq[..., 0] + 3 * torch.randn((nprob, nq), generator=g, device=dev),
+                        kq[..., 1] + 3 * torch.randn((nprob, nq), generator=g, device=dev),
+                        kq[..., 0] - 30 * torch.rand((nprob, nq), generator=g, device=dev)], dim=2).contiguous()
+    level = kq[..., 5].contiguous().view(torch.int32).clone()
+    qd = torch.gather(desc, 1, tgt[..., None].expand(-1, -1, 32)).clone()
+    pflip = torch.rand((nprob, nq, 1, 1), generator=g, device=dev) * (80.0 / 256.0)
+    weights = (2 ** torch.arange(8, device=dev, dtype=torch.int32)).view(1, 1, 1, 8)
+    for p0 in range(0, nprob, 32):
+        bits = (torch.rand((min(32, nprob - p0), nq, 32, 8), generator=g, device=dev) < pflip[p0:p0 + 32]).to(torch.int32)
+        qd[p0:p0 + 32] ^= (bits * weights).sum(-1).to(torch.uint8)
+    q = dict(proj=proj, level=level, desc=qd,
+             view_cos=torch.where(torch.rand((nprob, nq), generator=g, device=dev) < 0.5, 0.9995, 0.9).float().contiguous(),
+             in_view=torch.ones((nprob, nq), dtype=torch.uint8, device=dev), bad=torch.zeros((nprob, nq), dtype=torch.uint8, device=dev),
+             obs=torch.ones((nprob, nq), dtype=torch.int32, device=dev))
+    d_nq = torch.full((nprob,), nq, dtype=torch.int32, device=dev)
+    d_assign = torch.zeros((nprob, cap), dtype=torch.int32, device=dev)
+    d_nm = torch.zeros(nprob, dtype=torch.int32, device=dev)
+    d_rounds = torch.zeros(nprob, dtype=torch.int32, device=dev)
+    bounds = (0.0, float(w), 0.0, float(h))
+    F = ob.frames_batch(kps, desc, n, bounds)
+    stream = torch.cuda.current_stream()
+    th, nnratio = 3.0, 0.9
+
+    def run():
+        ob.search_by_projection_points_batch(F, scale, q, d_nq, nq, d_assign, d_nm, th, nnratio, None, d_rounds, stream.cuda_stream)
+
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(reps):
+        run()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    nm = d_nm.cpu().numpy()
+    assert (nm > 0).all(), "window matcher found nothing"
+    out = {"value": nprob / (ms * 1e-3), "unit": "problems/s", "what": "SearchByProjection(Frame, MapPoints), th=3, nnratio=0.9",
+           "nq": nq, "nt": float(n.float().mean().item()), "problems_per_launch": nprob, "ms_per_launch": ms,
+           "queries_per_s": nprob * nq / (ms * 1e-3), "matches_per_problem": float(nm.mean()),
+           "rounds_max": int(d_rounds.max().item()), "rounds_mean": float(d_rounds.float().mean().item()), "launches": 1}
+    if cpu:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib
+        from matcher_lib import Matcher
+        M = Matcher("ref" if oracle_lib.ref() is not None else "oracle")
+        n0 = int(n[0].item())
+        kp0 = np.ascontiguousarray(kps[0, :n0].cpu().numpy()).view(oracle_lib.KP_DTYPE).reshape(n0)
+        de0 = np.ascontiguousarray(desc[0, :n0].cpu().numpy())
+        q0 = {k: np.ascontiguousarray(v[0].cpu().numpy()) for k, v in q.items()}
+        t0 = time.perf_counter()
+        for _ in range(20):
+            want = M.search_by_projection_points(kp0, de0, None, np.ascontiguousarray(scale, np.float32), bounds, q0, th, nnratio)
+        dt = (time.perf_counter() - t0) / 20
+        assert want[0] == int(nm[0]) and (want[1] == d_assign[0, :n0].cpu().numpy()).all(), "window matcher disagrees with the CPU checker"
+        out["cpu_baseline"] = {"value": 1.0 / dt, "unit": "problems/s", "cores": 1, "kind": "reference" if M.impl == "ref" else "port",
+                               "sample": "problem 0 of the launch, 20 repetitions, results compared"}
+    return out
+
+
 # ------------------------------------------------------------------------------------------ our arm
 def run_ours(args, rank, world, local_rank):
     import torch
@@ -434,6 +512,9 @@ def run_ours(args, rank, world, local_rank):
         cfg_stereo = {"stereo": "frames are rectified pairs L0,R0,L1,R1,...: left/right extraction + Frame::ComputeStereoMatches per pair",
                       "pairs_per_step_per_gpu": pairs, "depth_points_per_pair": n_depth / pairs}
     hamming = bench_hamming(dev, local_rank) if world == 1 else None
+    window = None
+    if world == 1 and stereo:
+        window = bench_window_match(dev, d_kps, d_desc, d_n, cap, w, h, ex.GetScaleFactors(), cpu=not args.no_cpu)
     print(json.dumps({
         "metric": "orb_extract_frames_per_s", "value": value, "unit": "frames/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps,
@@ -446,6 +527,7 @@ def run_ours(args, rank, world, local_rank):
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": (LEVELS - 1 + 4 + (3 if stereo else 0)) * chunks * args.steps,
         "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "hamming_bf": hamming,
+        "window_match": window,
     }))
     if dist is not None:
         dist.destroy_process_group()

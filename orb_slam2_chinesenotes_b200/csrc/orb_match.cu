@@ -464,6 +464,68 @@ int resolve_best(Scratch& S, const DevFrame& D, int nq, const WinQuery* dq, cons
 }
 } // namespace
 
+bool orb_match_batch_fits(int kp_stride, int nq_stride);   // orb_match_batch.cu
+
+namespace {
+// One problem through the block-per-problem kernels of orb_match_batch.cu (the low-latency path: one launch,
+// queries resolved in parallel).  Frame already uploaded in D (kps / desc / u_right).
+struct OneFrame {
+    orbm_frames F;
+    int* d_n;
+};
+bool one_frame(Scratch& S, const orbm_frame* F, OneFrame* O)
+{
+    if (!F || F->n <= 0 || F->n > MAX_KP || !F->kps || !F->desc) return false;
+    O->F.nprob = 1;
+    O->F.kps = S.up(F->kps, (size_t)F->n);
+    O->F.desc = S.up(F->desc, (size_t)F->n * 32);
+    O->F.u_right = F->u_right ? S.up(F->u_right, (size_t)F->n) : nullptr;
+    O->d_n = S.up(&F->n, 1);
+    O->F.n = O->d_n;
+    O->F.kp_stride = F->n;
+    O->F.min_x = F->min_x; O->F.max_x = F->max_x; O->F.min_y = F->min_y; O->F.max_y = F->max_y;
+    return S.ok;
+}
+
+// best-candidate-only search of already projected queries (hq) through orbm_window_search_best_batch
+int best_via_batch(Scratch& S, const orbm_frame* F, bool use_ur, const std::vector<WinQuery>& hq, const uint8_t* qdesc, const float* h_angle,
+                   const int* h_qobs, const int* h_init_obs, int* assign_out, int check_ori, int th_accept, int* nmatches)
+{
+    const int nq = (int)hq.size(), n = F->n;
+    OneFrame O;
+    if (!one_frame(S, F, &O)) return S.ok ? ORBX_E_ARG : ORBX_E_CUDA;
+    std::vector<float> uvr((size_t)nq * 3), ur((size_t)nq), er((size_t)nq);
+    std::vector<int> minl((size_t)nq), maxl((size_t)nq);
+    std::vector<uint8_t> valid((size_t)nq);
+    for (int i = 0; i < nq; ++i) {
+        const WinQuery& Q = hq[(size_t)i];
+        valid[(size_t)i] = (uint8_t)(Q.valid != 0);
+        uvr[3 * (size_t)i] = Q.valid ? Q.u : 0.f; uvr[3 * (size_t)i + 1] = Q.valid ? Q.v : 0.f; uvr[3 * (size_t)i + 2] = Q.valid ? Q.r : 0.f;
+        minl[(size_t)i] = Q.valid ? Q.min_level : 0; maxl[(size_t)i] = Q.valid ? Q.max_level : 0;
+        ur[(size_t)i] = Q.valid ? Q.ur : 0.f; er[(size_t)i] = Q.valid ? Q.er_max : 0.f;
+    }
+    orbm_windows W;
+    int* d_nq = S.up(&nq, 1);
+    W.nq = d_nq; W.nq_stride = nq;
+    W.uvr = S.up(uvr.data(), uvr.size()); W.min_level = S.up(minl.data(), minl.size()); W.max_level = S.up(maxl.data(), maxl.size());
+    W.ur = use_ur ? S.up(ur.data(), ur.size()) : nullptr; W.er_max = use_ur ? S.up(er.data(), er.size()) : nullptr;
+    W.valid = S.up(valid.data(), valid.size());
+    W.qdesc = S.up(qdesc, (size_t)nq * 32);
+    W.q_angle = h_angle ? S.up(h_angle, (size_t)nq) : nullptr;
+    W.q_obs = h_qobs ? S.up(h_qobs, (size_t)nq) : nullptr;
+    int* d_init = h_init_obs ? S.up(h_init_obs, (size_t)n) : nullptr;
+    int* d_assign = (int*)S.alloc(sizeof(int) * (size_t)n);
+    int* d_nm = (int*)S.alloc(4);
+    if (!S.ok) return ORBX_E_CUDA;
+    if (!use_ur) O.F.u_right = nullptr;
+    const int rc = orbm_window_search_best_batch(&O.F, &W, d_init, d_assign, th_accept, check_ori, d_nm, nullptr, nullptr);
+    if (rc) return rc;
+    CKM(cudaMemcpy(assign_out, d_assign, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost));
+    CKM(cudaMemcpy(nmatches, d_nm, 4, cudaMemcpyDeviceToHost));
+    return ORBX_OK;
+}
+} // namespace
+
 extern "C" {
 
 int orbm_hamming_bf(const uint8_t* q, int nq, const uint8_t* t, int nt, int nprob,
@@ -505,6 +567,26 @@ int orbm_search_by_projection_points(const orbm_frame* F, const float* scale, in
     for (int k = 0; k < F->n; ++k) assign_out[k] = init_assign ? init_assign[k] : -1;
     if (nq == 0 || F->n == 0) return ORBX_OK;
     Scratch S;
+    if (nlevels <= 32 && orb_match_batch_fits(F->n, nq)) {
+        // one launch of the block-per-problem kernel (orb_match_batch.cu): queries are built and resolved on the device
+        OneFrame O;
+        if (!one_frame(S, F, &O)) return S.ok ? ORBX_E_ARG : ORBX_E_CUDA;
+        orbm_points Qp;
+        int* d_nq = S.up(&nq, 1);
+        Qp.nq = d_nq; Qp.nq_stride = nq;
+        Qp.proj_xyxr = S.up(proj_xyxr, (size_t)nq * 3); Qp.level = S.up(level, (size_t)nq); Qp.view_cos = S.up(view_cos, (size_t)nq);
+        Qp.in_view = S.up(in_view, (size_t)nq); Qp.bad = S.up(bad, (size_t)nq); Qp.observations = S.up(observations, (size_t)nq);
+        Qp.qdesc = S.up(qdesc, (size_t)nq * 32);
+        int* d_init = init_assign ? S.up(init_assign, (size_t)F->n) : nullptr;
+        int* d_assign = (int*)S.alloc(sizeof(int) * (size_t)F->n);
+        int* d_nm = (int*)S.alloc(4);
+        if (!S.ok) return ORBX_E_CUDA;
+        const int rc = orbm_search_by_projection_points_batch(&O.F, scale, nlevels, &Qp, d_init, d_assign, th, nnratio, d_nm, nullptr, nullptr);
+        if (rc) return rc;
+        CKM(cudaMemcpy(assign_out, d_assign, sizeof(int) * (size_t)F->n, cudaMemcpyDeviceToHost));
+        CKM(cudaMemcpy(nmatches, d_nm, 4, cudaMemcpyDeviceToHost));
+        return ORBX_OK;
+    }
     DevFrame D;
     if (!make_frame(S, F, &D)) return S.ok ? ORBX_E_ARG : ORBX_E_CUDA;
     // the per-query part of the reference loop that does not depend on other queries (:82-98, :119-124)
@@ -552,7 +634,8 @@ int orbm_search_by_projection_frame(const orbm_frame* cur, int n_last, const orb
     if (n_last == 0 || n_cur == 0) return ORBX_OK;
     Scratch S;
     DevFrame D;
-    if (!make_frame(S, cur, &D)) return S.ok ? ORBX_E_ARG : ORBX_E_CUDA;
+    const bool via_batch = orb_match_batch_fits(n_cur, n_last);
+    if (!via_batch && !make_frame(S, cur, &D)) return S.ok ? ORBX_E_ARG : ORBX_E_CUDA;
     // projection of the last frame's map points with the current pose: the float arithmetic of
     // cv::gemm for CV_32F (products accumulated left to right, translation added last), :172-208
     const float fx = K[0], fy = K[1], cx = K[2], cy = K[3];
@@ -601,6 +684,9 @@ int orbm_search_by_projection_frame(const orbm_frame* cur, int n_last, const orb
         else { Q.min_level = oct - 1; Q.max_level = oct + 1; }
         Q.ur = u - bf * invzc; Q.er_max = Q.r;                                  // :241-244
     }
+    if (via_batch)
+        return best_via_batch(S, cur, cur->u_right != nullptr, hq, last_mp_desc, h_angle.data(), h_lobs.data(), cur_init_obs ? h_obs.data() : nullptr,
+                              assign_out, checkOri, TH_HIGH, nmatches);
     WinQuery* dq; uint32_t* list; int* count; int cap;
     int rc = run_candidates(S, D, hq, last_mp_desc, n_last, &dq, &list, &count, &cap);
     if (rc) return rc;
@@ -622,7 +708,8 @@ int orbm_window_search_best(const orbm_frame* F, int nq, const float* uvr, const
     if (nq == 0 || n == 0) return ORBX_OK;
     Scratch S;
     DevFrame D;
-    if (!make_frame(S, F, &D)) return S.ok ? ORBX_E_ARG : ORBX_E_CUDA;
+    const bool via_batch = orb_match_batch_fits(n, nq);
+    if (!via_batch && !make_frame(S, F, &D)) return S.ok ? ORBX_E_ARG : ORBX_E_CUDA;
     std::vector<WinQuery> hq((size_t)nq);
     std::vector<float> h_angle((size_t)nq, 0.f);
     std::vector<int> h_qobs((size_t)nq, 1);
@@ -635,6 +722,9 @@ int orbm_window_search_best(const orbm_frame* F, int nq, const float* uvr, const
         if (q_angle) h_angle[(size_t)i] = q_angle[i];
         if (q_obs) h_qobs[(size_t)i] = q_obs[i];
     }
+    if (via_batch)
+        return best_via_batch(S, F, ur != nullptr && F->u_right != nullptr, hq, qdesc, h_angle.data(), h_qobs.data(), init_obs ? h_obs.data() : nullptr,
+                              assign_out, check_ori, th_accept, nmatches);
     if (!ur) D.u_right = nullptr;
     WinQuery* dq; uint32_t* list; int* count; int cap;
     int rc = run_candidates(S, D, hq, qdesc, nq, &dq, &list, &count, &cap);

@@ -39,7 +39,7 @@
 #define HISTO_LENGTH 30 // :39
 #define MB_MAX_KP 8192
 #define MB_MAX_LEVELS 32
-#define MB_NT 512
+#define MB_NT 1024
 #define MB_NONE 0xffffffffu
 
 enum { MODE_POINTS = 0, MODE_BEST = 1 };
@@ -67,6 +67,7 @@ struct MbParams {
     // workspace
     uint4* rec; uint32_t* sdesc;     // [nprob][kp_stride], [nprob][kp_stride][8]
     int sn_max, nq_max;              // shared-memory sizing
+    int rec_in_smem, desc_in_smem;   // the sorted records / descriptors live in shared memory when they fit
     int* rounds;                     // [nprob] or null: fixpoint rounds used (profiling / tests)
 };
 
@@ -103,63 +104,71 @@ __device__ __forceinline__ int mb_rot_bin(const float a1, const float a2)   // s
     return bin;
 }
 
-// One query, one warp: the two smallest (distance << 16 | position) keys among the candidates that are not
-// taken, and whether a taken candidate was skipped.
+// One query, one GROUP of MB_G lanes (a window holds a few candidates per grid column, far fewer than 32): the two
+// smallest (distance << 16 | position) keys among the candidates that are not taken, and whether a taken
+// candidate was skipped.  gmask = the lanes of the group; all four groups of a warp run this together.
+#define MB_G 8
 template <int MODE>
-__device__ __forceinline__ void query_top2(const MbParams& P, const WinQ& Q, const int q, const uint32_t* __restrict__ qd,
+__device__ __forceinline__ void query_top2(const MbParams& P, const WinQ& Q, const int q, const uint32_t (&qd)[8],
                                            const uint4* rec, const uint4* sdesc, const int* cell_start,
-                                           const int* blk, const bool use_ur, const int lane, uint32_t& k1, uint32_t& k2, bool& skipped)
+                                           const int* blk, const bool use_ur, const int sub, const unsigned gmask,
+                                           uint32_t& k1, uint32_t& k2, bool& skipped)
 {
-    k1 = MB_NONE; k2 = MB_NONE; skipped = false;
+    uint32_t a1 = MB_NONE, a2 = MB_NONE;
+    int nb = 0;
     // src/Frame.cc:355-372
     const int nMinCellX = max(0, (int)floorf((Q.u - P.min_x - Q.r) * P.inv_w));
     const int nMaxCellX = min(GRID_COLS - 1, (int)ceilf((Q.u - P.min_x + Q.r) * P.inv_w));
     const int nMinCellY = max(0, (int)floorf((Q.v - P.min_y - Q.r) * P.inv_h));
     const int nMaxCellY = min(GRID_ROWS - 1, (int)ceilf((Q.v - P.min_y + Q.r) * P.inv_h));
-    if (nMinCellX >= GRID_COLS || nMaxCellX < 0 || nMinCellY >= GRID_ROWS || nMaxCellY < 0) return;
-    const bool check_levels = Q.min_level > 0 || Q.max_level >= 0;               // :375
-    const uint32_t d0 = __ldg(qd), d1 = __ldg(qd + 1), d2 = __ldg(qd + 2), d3 = __ldg(qd + 3),
-                   d4 = __ldg(qd + 4), d5 = __ldg(qd + 5), d6 = __ldg(qd + 6), d7 = __ldg(qd + 7);
-    uint32_t a1 = MB_NONE, a2 = MB_NONE;
-    int nb = 0;
-    for (int ix = nMinCellX; ix <= nMaxCellX; ++ix) {
-        const int s0 = cell_start[ix * GRID_ROWS + nMinCellY], s1 = cell_start[ix * GRID_ROWS + nMaxCellY + 1];
-        for (int j = s0 + lane; j < s1; j += 32) {
-            const uint4 r = rec[j];
-            const int oct = (int)(r.z & 0xffu);
-            if (check_levels) {
-                if (oct < Q.min_level) continue;
-                if (Q.max_level >= 0 && oct > Q.max_level) continue;
+    if (Q.valid && !(nMinCellX >= GRID_COLS || nMaxCellX < 0 || nMinCellY >= GRID_ROWS || nMaxCellY < 0)) {
+        const bool check_levels = Q.min_level > 0 || Q.max_level >= 0;               // :375
+        for (int ix = nMinCellX; ix <= nMaxCellX; ++ix) {
+            const int s0 = cell_start[ix * GRID_ROWS + nMinCellY], s1 = cell_start[ix * GRID_ROWS + nMaxCellY + 1];
+            for (int j = s0 + sub; j < s1; j += MB_G) {
+                const uint4 r = rec[j];
+                const int oct = (int)(r.z & 0xffu);
+                if (check_levels) {
+                    if (oct < Q.min_level) continue;
+                    if (Q.max_level >= 0 && oct > Q.max_level) continue;
+                }
+                if (!(fabsf(__uint_as_float(r.x) - Q.u) < Q.r && fabsf(__uint_as_float(r.y) - Q.v) < Q.r)) continue;   // :402
+                if (blk[j] < q) { ++nb; continue; }                                   // src/ORBmatcher.cc:115-117 / :234-236
+                if (use_ur) {
+                    const float ur = __uint_as_float(r.w);
+                    if (ur > 0 && fabsf(Q.ur - ur) > Q.er_max) continue;             // :119-124 / :238-244
+                }
+                const uint4 b0 = sdesc[2 * j], b1 = sdesc[2 * j + 1];
+                const uint32_t dist = __popc(qd[0] ^ b0.x) + __popc(qd[1] ^ b0.y) + __popc(qd[2] ^ b0.z) + __popc(qd[3] ^ b0.w) +
+                                      __popc(qd[4] ^ b1.x) + __popc(qd[5] ^ b1.y) + __popc(qd[6] ^ b1.z) + __popc(qd[7] ^ b1.w);
+                const uint32_t key = (dist << 16) | (uint32_t)j;
+                if (key < a1) { a2 = a1; a1 = key; }
+                else if (key < a2) a2 = key;
             }
-            if (!(fabsf(__uint_as_float(r.x) - Q.u) < Q.r && fabsf(__uint_as_float(r.y) - Q.v) < Q.r)) continue;   // :402
-            if (blk[j] < q) { ++nb; continue; }                                   // src/ORBmatcher.cc:115-117 / :234-236
-            if (use_ur) {
-                const float ur = __uint_as_float(r.w);
-                if (ur > 0 && fabsf(Q.ur - ur) > Q.er_max) continue;             // :119-124 / :238-244
-            }
-            const uint4 b0 = sdesc[2 * j], b1 = sdesc[2 * j + 1];
-            const uint32_t dist = __popc(d0 ^ b0.x) + __popc(d1 ^ b0.y) + __popc(d2 ^ b0.z) + __popc(d3 ^ b0.w) +
-                                  __popc(d4 ^ b1.x) + __popc(d5 ^ b1.y) + __popc(d6 ^ b1.z) + __popc(d7 ^ b1.w);
-            const uint32_t key = (dist << 16) | (uint32_t)j;
-            if (key < a1) { a2 = a1; a1 = key; }
-            else if (key < a2) a2 = key;
         }
     }
-    k1 = __reduce_min_sync(0xffffffffu, a1);
+    k1 = __reduce_min_sync(gmask, a1);
     if (a1 == k1) a1 = a2;                        // keys are unique (position) or "none"
-    k2 = __reduce_min_sync(0xffffffffu, a1);
-    skipped = __any_sync(0xffffffffu, nb > 0);
+    k2 = __reduce_min_sync(gmask, a1);
+    skipped = __reduce_max_sync(gmask, (unsigned)(nb > 0)) != 0;
     (void)MODE;
 }
 
 // The blocked-candidate order matters: in the reference the "taken" test comes BEFORE the right-image test, and
 // both only `continue`, so their order does not change the candidate set.
 
+#ifdef ORB_MATCH_CLOCKS
+__device__ long long g_clk[16];
+#define CLK(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_clk[i] = clock64(); } while (0)
+#else
+#define CLK(i)
+#endif
+
 template <int MODE>
 __global__ void __launch_bounds__(MB_NT) k_match_fixpoint(const __grid_constant__ MbParams P)
 {
     extern __shared__ __align__(16) uint32_t smem[];
-    __shared__ int s_flag[2], s_cnt[2], s_sizes[HISTO_LENGTH], s_ind[3];
+    __shared__ int s_flag[3], s_cnt[2], s_sizes[HISTO_LENGTH], s_ind[3];
     const int prob = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = MB_NT >> 5;
     const int n = P.n[prob], nq = P.nq[prob];
     int* const nm_out = P.nmatches + prob;
@@ -172,12 +181,18 @@ __global__ void __launch_bounds__(MB_NT) k_match_fixpoint(const __grid_constant_
     int sn = 32; while (sn < n) sn <<= 1;
     uint32_t* keys = smem;                                  // [sn_max]
     int* cell_start = (int*)(smem + P.sn_max);              // [GRID_CELLS + 1] (+3 pad)
-    int* blk = cell_start + GRID_CELLS + 4;                 // [sn_max]
-    uint32_t* st_top = (uint32_t*)(blk + P.sn_max);         // [nq_max]  k1 position | k2 position << 16 (0xffff none)
+    int* const blk_a = cell_start + GRID_CELLS + 4;         // [sn_max] blocker of every position, double buffered
+    int* const blk_b = blk_a + P.sn_max;                    // [sn_max]
+    int* blk = blk_a;
+    uint32_t* st_top = (uint32_t*)(blk_b + P.sn_max);       // [nq_max]  k1 position | k2 position << 16 (0xffff none)
     uint32_t* st_best = st_top + P.nq_max;                  // [nq_max]  (accepted position + 1) | skipped << 16 | bin << 24
-    uint4* rec = P.rec + ko;
-    uint4* sdesc = (uint4*)(P.sdesc + ko * 8);
+    // sorted records and descriptors: shared memory when the problem fits (the window walk is a chain of dependent
+    // loads, so their latency is what a query costs), else the global workspace
+    uint4* const sm16 = (uint4*)(st_best + P.nq_max);
+    uint4* rec = P.rec_in_smem ? sm16 : P.rec + ko;
+    uint4* sdesc = P.desc_in_smem ? sm16 + (P.rec_in_smem ? P.sn_max : 0) : (uint4*)(P.sdesc + ko * 8);
 
+    CLK(0);
     // ---- Frame::AssignFeaturesToGrid (src/Frame.cc:243-259): cell of every keypoint (round(), :414-415), sorted
     for (int i = tid; i < sn; i += MB_NT) {
         uint32_t key = MB_NONE;
@@ -189,6 +204,7 @@ __global__ void __launch_bounds__(MB_NT) k_match_fixpoint(const __grid_constant_
         keys[i] = key;
     }
     __syncthreads();
+    CLK(1);
     for (int k = 2; k <= sn; k <<= 1)
         for (int j = k >> 1; j > 0; j >>= 1) {
             for (int t = tid; t < (sn >> 1); t += MB_NT) {
@@ -207,6 +223,7 @@ __global__ void __launch_bounds__(MB_NT) k_match_fixpoint(const __grid_constant_
     }
     __syncthreads();
     const int nvalid = cell_start[GRID_CELLS];
+    CLK(2);
     const bool use_ur = P.u_right != nullptr && (MODE == MODE_POINTS || P.f1 != nullptr);
     for (int j = tid; j < nvalid; j += MB_NT) {
         const int idx = (int)(keys[j] & 0xffffu);
@@ -227,15 +244,16 @@ __global__ void __launch_bounds__(MB_NT) k_match_fixpoint(const __grid_constant_
         ((uint32_t*)sdesc)[(size_t)j * 8 + wd] = P.desc[(ko + (keys[j] & 0xffffu)) * 8 + wd];
     }
     for (int q = tid; q < nq; q += MB_NT) { st_top[q] = MB_NONE; st_best[q] = 0; }
-    if (tid == 0) { s_flag[0] = 0; s_flag[1] = 0; s_cnt[0] = 0; s_cnt[1] = 0; }
+    if (tid == 0) { s_flag[0] = 0; s_flag[1] = 0; s_flag[2] = 0; s_cnt[0] = 0; s_cnt[1] = 0; }
     if (tid < HISTO_LENGTH) s_sizes[tid] = 0;
     __syncthreads();       // rec / sdesc are read back by this block only
 
+    CLK(3);
     // ---- rounds
     int round = 0;
-    bool prev_changed = true;
     for (;; ++round) {
         const int par = round & 1;
+        const bool unblocked = round > 0 && s_flag[2] != 0;     // some keypoint became free again in the last rebuild
         for (int base = warp * 32; base < nq; base += nwarps * 32) {
             const int q = base + lane;
             bool need = false;
@@ -244,19 +262,43 @@ __global__ void __launch_bounds__(MB_NT) k_match_fixpoint(const __grid_constant_
                 else {
                     const uint32_t top = st_top[q], sb = st_best[q];
                     const uint32_t p1 = top & 0xffffu, p2 = top >> 16;
-                    need = (p1 != 0xffffu && blk[p1] < q) || (p2 != 0xffffu && blk[p2] < q) || (((sb >> 16) & 1u) && prev_changed);
+                    need = (p1 != 0xffffu && blk[p1] < q) || (p2 != 0xffffu && blk[p2] < q) || (((sb >> 16) & 1u) && unblocked);
                 }
             }
-            unsigned m = __ballot_sync(0xffffffffu, need);
-            while (m) {
-                const int b = __ffs(m) - 1;
-                m &= m - 1;
-                const int qq = base + b;
-                const WinQ Q = load_query<MODE>(P, qo + qq);
+            // every lane fetches ITS query (unit-stride loads, one memory round trip per 32 queries); the warp
+            // then works through the queries one at a time with the parameters broadcast by shuffles
+            WinQ myQ;
+            uint4 myd0 = make_uint4(0, 0, 0, 0), myd1 = myd0;
+            myQ.valid = 0;
+            if (need) {
+                myQ = load_query<MODE>(P, qo + q);
+                if (myQ.valid) {
+                    const uint4* qd = (const uint4*)(P.qdesc + (qo + q) * 8);
+                    myd0 = __ldg(qd); myd1 = __ldg(qd + 1);
+                } else if (st_best[q] & 0xffffu) { st_best[q] = 0; st_top[q] = MB_NONE; s_flag[par] = 1; }   // cannot happen: validity is fixed
+            }
+            // four groups of 8 lanes, each working through the 8 queries its own lanes fetched
+            const bool go = need && myQ.valid;
+            if (!__any_sync(0xffffffffu, go)) continue;
+            const int sub = lane & (MB_G - 1), g0 = lane & ~(MB_G - 1);
+            const unsigned gmask = ((1u << MB_G) - 1u) << g0;
+            for (int i = 0; i < MB_G; ++i) {
+                const int src = g0 + i, qq = base + src;
+                WinQ Q;
+                Q.valid = __shfl_sync(0xffffffffu, (int)go, src);
+                if (!__any_sync(0xffffffffu, Q.valid)) continue;
+                Q.u = __shfl_sync(0xffffffffu, myQ.u, src); Q.v = __shfl_sync(0xffffffffu, myQ.v, src); Q.r = __shfl_sync(0xffffffffu, myQ.r, src);
+                Q.ur = __shfl_sync(0xffffffffu, myQ.ur, src); Q.er_max = __shfl_sync(0xffffffffu, myQ.er_max, src);
+                Q.min_level = __shfl_sync(0xffffffffu, myQ.min_level, src); Q.max_level = __shfl_sync(0xffffffffu, myQ.max_level, src);
+                uint32_t d[8];
+                d[0] = __shfl_sync(0xffffffffu, myd0.x, src); d[1] = __shfl_sync(0xffffffffu, myd0.y, src);
+                d[2] = __shfl_sync(0xffffffffu, myd0.z, src); d[3] = __shfl_sync(0xffffffffu, myd0.w, src);
+                d[4] = __shfl_sync(0xffffffffu, myd1.x, src); d[5] = __shfl_sync(0xffffffffu, myd1.y, src);
+                d[6] = __shfl_sync(0xffffffffu, myd1.z, src); d[7] = __shfl_sync(0xffffffffu, myd1.w, src);
                 uint32_t k1 = MB_NONE, k2 = MB_NONE;
                 bool skipped = false;
-                if (Q.valid) query_top2<MODE>(P, Q, qq, P.qdesc + (qo + qq) * 8, rec, sdesc, cell_start, blk, use_ur, lane, k1, k2, skipped);
-                if (lane == 0) {
+                query_top2<MODE>(P, Q, qq, d, rec, sdesc, cell_start, blk, use_ur, sub, gmask, k1, k2, skipped);
+                if (sub == 0 && Q.valid) {
                     int best = -1;
                     if (k1 != MB_NONE) {
                         const int bestDist = (int)(k1 >> 16);
@@ -278,18 +320,25 @@ __global__ void __launch_bounds__(MB_NT) k_match_fixpoint(const __grid_constant_
             }
         }
         __syncthreads();
+        if (round < 8) CLK(4 + round);
         const bool changed = s_flag[par] != 0;
         if (!changed) break;
-        // blocker[] from the decisions
-        for (int j = tid; j < nvalid; j += MB_NT) blk[j] = (rec[j].z >> 31) ? -1 : INT_MAX;
-        if (tid == 0) s_flag[par ^ 1] = 0;
+        // blocker[] from the decisions, into the other buffer; a keypoint whose blocker moved to a LATER query (or
+        // went away) is the only thing that can change the result of a query that skipped taken candidates
+        int* const nblk = blk == blk_a ? blk_b : blk_a;
+        for (int j = tid; j < nvalid; j += MB_NT) nblk[j] = (rec[j].z >> 31) ? -1 : INT_MAX;
+        if (tid == 0) { s_flag[par ^ 1] = 0; s_flag[2] = 0; }
         __syncthreads();
         for (int q = tid; q < nq; q += MB_NT) {
             const int b = (int)(st_best[q] & 0xffffu) - 1;
-            if (b >= 0 && (qobs ? qobs[q] : 1) > 0) atomicMin(&blk[b], q);
+            if (b >= 0 && (qobs ? qobs[q] : 1) > 0) atomicMin(&nblk[b], q);
         }
         __syncthreads();
-        prev_changed = true;
+        bool freed = false;
+        for (int j = tid; j < nvalid; j += MB_NT) freed |= nblk[j] > blk[j];
+        if (freed) s_flag[2] = 1;
+        blk = nblk;
+        __syncthreads();
     }
     if (P.rounds && tid == 0) P.rounds[prob] = round + 1;
 
@@ -346,6 +395,7 @@ __global__ void __launch_bounds__(MB_NT) k_match_fixpoint(const __grid_constant_
         else if (w == -3) assign_out[rec[j].z >> 8 & 0x7fffffu] = -1;
     }
     if (tid == 0) *nm_out = s_cnt[0] - s_cnt[1];
+    CLK(12);
 }
 
 // ================================================================================ host side
@@ -363,6 +413,16 @@ int device_of(const void* p)
     return a.device;
 }
 
+size_t base_smem(int kp_stride, int nq_stride, int* sn_out, int* nq_out)
+{
+    int sn = 32; while (sn < kp_stride && sn < MB_MAX_KP) sn <<= 1;
+    const int nqm = (nq_stride + 3) & ~3;
+    if (sn_out) *sn_out = sn;
+    if (nq_out) *nq_out = nqm;
+    return ((size_t)sn * 3 + GRID_CELLS + 4 + (size_t)nqm * 2) * 4;
+}
+const size_t kSmemMax = 224 * 1024;
+
 template <int MODE>
 int launch(MbParams& P, int nprob, cudaStream_t st)
 {
@@ -370,13 +430,16 @@ int launch(MbParams& P, int nprob, cudaStream_t st)
     if (dev < 0 || device_of(P.assign_out) != dev || device_of(P.nmatches) != dev || device_of(P.qdesc) != dev) return ORBX_E_ARG;
     DevGuard g;
     if (cudaGetDevice(&g.prev) != cudaSuccess || cudaSetDevice(dev) != cudaSuccess) { cudaGetLastError(); return ORBX_E_CUDA; }
-    int sn = 32; while (sn < P.kp_stride && sn < MB_MAX_KP) sn <<= 1;
-    P.sn_max = sn;
-    P.nq_max = (P.nq_stride + 3) & ~3;
-    const size_t smem = ((size_t)P.sn_max * 2 + GRID_CELLS + 4 + (size_t)P.nq_max * 2) * 4;
-    if (smem > 220 * 1024) return ORBX_E_ARG;
+    size_t smem = base_smem(P.kp_stride, P.nq_stride, &P.sn_max, &P.nq_max);
+    const size_t smem_max = kSmemMax;
+    if (smem > smem_max) return ORBX_E_ARG;
+    P.rec_in_smem = smem + (size_t)P.sn_max * 16 <= smem_max;
+    if (P.rec_in_smem) smem += (size_t)P.sn_max * 16;
+    P.desc_in_smem = smem + (size_t)P.sn_max * 32 <= smem_max;
+    if (P.desc_in_smem) smem += (size_t)P.sn_max * 32;
     void* ws = nullptr;
-    const size_t rec_bytes = (size_t)nprob * P.kp_stride * sizeof(uint4), ws_bytes = rec_bytes + (size_t)nprob * P.kp_stride * 32;
+    const size_t rec_bytes = P.rec_in_smem ? 0 : (size_t)nprob * P.kp_stride * sizeof(uint4);
+    const size_t ws_bytes = rec_bytes + (P.desc_in_smem ? 0 : (size_t)nprob * P.kp_stride * 32) + 16;
     if (cudaMallocAsync(&ws, ws_bytes, st) != cudaSuccess) { cudaGetLastError(); return ORBX_E_CUDA; }
     P.rec = (uint4*)ws;
     P.sdesc = (uint32_t*)((char*)ws + rec_bytes);
@@ -403,7 +466,17 @@ bool fill_frames(MbParams& P, const orbm_frames* F)
 }
 } // namespace
 
+// Internal (orb_match.cu): can one problem of this size run in the block-per-problem kernel?
+bool orb_match_batch_fits(int kp_stride, int nq_stride)
+{
+    return kp_stride > 0 && nq_stride > 0 && nq_stride <= MB_MAX_KP * 4 && base_smem(kp_stride, nq_stride, nullptr, nullptr) <= kSmemMax;
+}
+
 extern "C" {
+
+#ifdef ORB_MATCH_CLOCKS
+int orbm_debug_clocks(long long* out) { return cudaMemcpyFromSymbol(out, g_clk, sizeof(long long) * 16) == cudaSuccess ? 0 : 4; }
+#endif
 
 int orbm_search_by_projection_points_batch(const orbm_frames* F, const float* scale, int nlevels, const orbm_points* Q,
                                            const int* init_assign, int* assign_out, float th, float nnratio,

@@ -258,3 +258,14 @@ def test_window_search_generic_random_queries(scene):
         g_nm, g_assign = ob.window_search_best(F, uvr, minl, maxl, qd, th_accept, check_ori, q_angle=q_angle, q_obs=q_obs, init_obs=init_obs,
                                                ur=ur, er_max=er_max, valid=valid)
         assert g_nm == nm and nm > 100 and (g_assign == ref_assign).all()   # random query angles: the histogram prunes most
+
+
+def test_very_large_query_set_takes_the_list_path(scene):
+    """More queries than the block-per-problem kernel holds in shared memory: the entry point falls back to the
+    candidate-list kernels with the in-order resolve; same results."""
+    O = Matcher("oracle")
+    k, d = scene["k2"][:600].copy(), scene["d2"][:600].copy()
+    q = projected_queries(k, d, 30000, 77)
+    a = O.search_by_projection_points(k, d, None, scene["scale"], BOUNDS, q, 3.0, 0.9, None)
+    b = ob.ORBmatcher(0.9, True).SearchByProjection(ob.FrameView(k, d, BOUNDS), scene["scale"], q, 3.0)
+    assert a[0] == b[0] and a[0] > 100 and (a[1] == b[1]).all()
