@@ -354,3 +354,51 @@ static float sincosf_impl(float y, int want_cos)
 
 float cvp_sinf(float x) { return sincosf_impl(x, 0); }
 float cvp_cosf(float x) { return sincosf_impl(x, 1); }
+
+/* ------------------------------------------------------------------------------------------------
+ * glibc 2.39 logf (sysdeps/ieee754/flt-32/e_logf.c, e_logf_data.c; table bits = 4, degree-3
+ * polynomial, double arithmetic, operations in the source's order, no FMA).  Called by
+ * MapPoint::PredictScale (src/MapPoint.cc:450, :468: log(float) resolves to the float overload)
+ * and for mfLogScaleFactor (src/Frame.cc:75).  The table was checked against the bytes of this
+ * image's libm.so.6; tests compare the function with libm's logf. */
+static const double logf_tab[16][2] = {
+    { 0x1.661ec79f8f3bep+0, -0x1.57bf7808caadep-2 }, { 0x1.571ed4aaf883dp+0, -0x1.2bef0a7c06ddbp-2 },
+    { 0x1.49539f0f010bp+0, -0x1.01eae7f513a67p-2 },  { 0x1.3c995b0b80385p+0, -0x1.b31d8a68224e9p-3 },
+    { 0x1.30d190c8864a5p+0, -0x1.6574f0ac07758p-3 }, { 0x1.25e227b0b8eap+0, -0x1.1aa2bc79c81p-3 },
+    { 0x1.1bb4a4a1a343fp+0, -0x1.a4e76ce8c0e5ep-4 }, { 0x1.12358f08ae5bap+0, -0x1.1973c5a611cccp-4 },
+    { 0x1.0953f419900a7p+0, -0x1.252f438e10c1ep-5 }, { 0x1p+0, 0x0p+0 },
+    { 0x1.e608cfd9a47acp-1, 0x1.aa5aa5df25984p-5 },  { 0x1.ca4b31f026aap-1, 0x1.c5e53aa362eb4p-4 },
+    { 0x1.b2036576afce6p-1, 0x1.526e57720db08p-3 },  { 0x1.9c2d163a1aa2dp-1, 0x1.bc2860d22477p-3 },
+    { 0x1.886e6037841edp-1, 0x1.1058bc8a07ee1p-2 },  { 0x1.767dcf5534862p-1, 0x1.4043057b6ee09p-2 },
+};
+static const double logf_ln2 = 0x1.62e42fefa39efp-1;
+static const double logf_poly[3] = { -0x1.00ea348b88334p-2, 0x1.5575b0be00b6ap-2, -0x1.ffffef20a4123p-2 };
+
+float cvp_logf(float x)
+{
+    uint32_t ix;
+    memcpy(&ix, &x, 4);
+    if (ix == 0x3f800000u) return 0.0f;
+    if (ix - 0x00800000u >= 0x7f800000u - 0x00800000u) {
+        if (ix * 2u == 0) return -INFINITY;                        /* log(+-0) */
+        if (ix == 0x7f800000u) return x;                           /* log(inf) */
+        if ((ix & 0x80000000u) || ix * 2u >= 0xff000000u) return NAN;
+        x = x * 0x1p23f;                                           /* subnormal: normalise */
+        memcpy(&ix, &x, 4);
+        ix -= 23u << 23;
+    }
+    const uint32_t tmp = ix - 0x3f330000u;
+    const int i = (int)((tmp >> (23 - 4)) % 16u);
+    const int k = (int32_t)tmp >> 23;
+    const uint32_t iz = ix - (tmp & (0x1ffu << 23));
+    float zf;
+    memcpy(&zf, &iz, 4);
+    const double invc = logf_tab[i][0], logc = logf_tab[i][1], z = (double)zf;
+    const double r = z * invc - 1;
+    const double y0 = logc + (double)k * logf_ln2;
+    const double r2 = r * r;
+    double y = logf_poly[1] * r + logf_poly[2];
+    y = logf_poly[0] * r2 + y;
+    y = y * r2 + (y0 + r);
+    return (float)y;
+}

@@ -61,6 +61,9 @@ float cvp_fast_atan2(float y, float x);
 float cvp_sinf(float x);
 float cvp_cosf(float x);
 
+/* glibc 2.39 logf restated (double arithmetic, no FMA). */
+float cvp_logf(float x);
+
 /* cvRound(double) on x86-64: round-half-to-even. */
 int cvp_round(double v);
 

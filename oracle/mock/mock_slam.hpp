@@ -41,7 +41,7 @@ class MapPoint {
 public:
     MapPoint() : mTrackProjX(0), mTrackProjY(0), mTrackProjXR(0), mbTrackInView(false), mnTrackScaleLevel(0),
                  mTrackViewCos(0), mnTrackReferenceForFrame(0), mnLastFrameSeen(0), mnId(0), nObs(0), bad(false),
-                 maxDist(1e9f), minDist(0.f) {}
+                 maxDist(1e9f), minDist(0.f), maxDistRaw(0.f), realPredict(false) {}
     // tracking variables read by ORBmatcher::SearchByProjection (src/ORBmatcher.cc:82-124)
     float mTrackProjX, mTrackProjY, mTrackProjXR;
     bool mbTrackInView;
@@ -61,7 +61,13 @@ public:
     float GetMaxDistanceInvariance() { return maxDist; }   // the harness stores the invariance bounds directly
     float GetMinDistanceInvariance() { return minDist; }
     int PredictScale(const float&, KeyFrame*) { return mnTrackScaleLevel; }
-    int PredictScale(const float&, Frame*) { return mnTrackScaleLevel; }
+    // realPredict: the arithmetic of src/MapPoint.cc:459-475 on maxDistRaw (= mfMaxDistance), defined in
+    // ref_frustum_harness.cc where Frame is complete; pinned against the reference's own MapPoint.cc through
+    // oracle/_ref/libmappointref.so (tests/test_projection_oracle.py).  Otherwise the preset level.
+    float maxDistRaw;
+    bool realPredict;
+    int PredictScale(const float& d, Frame* pF) { return realPredict ? PredictScaleReal(d, pF) : mnTrackScaleLevel; }
+    int PredictScaleReal(const float& currentDist, Frame* pF);
     int GetIndexInKeyFrame(KeyFrame*) { return -1; }
     bool IsInKeyFrame(KeyFrame*) { return false; }
     void Replace(MapPoint*) {}

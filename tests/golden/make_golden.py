@@ -114,8 +114,26 @@ def projection_overloads():
     np.savez_compressed(os.path.join(HERE, "ref_match_projection.npz"), **out)
 
 
+def mappoint():
+    """Outputs of the reference's unmodified MapPoint.cc (ComputeDistinctiveDescriptors, PredictScale) and
+    Frame::isInFrustum on the deterministic scenes of tests/mappoint_lib.py."""
+    from mappoint_lib import descriptor_groups, distinctive, frustum_scene, is_in_frustum, predict_scale
+    out = dict(desc_seed=9, frustum_seed=7, predict_max=np.float32(12.5))
+    for k, (d, bad) in enumerate(descriptor_groups(9)):
+        for tag, b in (("all", None), ("bad", bad)):
+            w = distinctive("ref", d, b)[0]
+            out[f"distinctive_{tag}_{k}"] = np.zeros(0, np.uint8) if w is None else w
+    rng = np.random.default_rng(3)
+    cur = np.concatenate([np.float32(12.5) / np.float32(1.2) ** np.arange(-3, 12), rng.uniform(0.05, 200, 2000)]).astype(np.float32)
+    out["predict_cur"] = cur
+    out["predict_level"] = predict_scale("ref", 12.5, cur)
+    iv, proj, lv, vc = is_in_frustum("ref", frustum_scene(7))
+    out.update(frustum_in_view=iv, frustum_proj=proj, frustum_level=lv, frustum_view_cos=vc)
+    np.savez_compressed(os.path.join(HERE, "ref_mappoint.npz"), **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["primitives", "extractor", "matchers", "projection_overloads"]
+    which = sys.argv[1:] or ["primitives", "extractor", "matchers", "projection_overloads", "mappoint"]
     for name in which:
         globals()[name]()
     print("golden fixtures written to", HERE)
