@@ -250,6 +250,32 @@ typedef struct {
 int orbm_window_search_best_batch(const orbm_frames* F, const orbm_windows* Q, const int* init_obs, int* assign_out,
                                   int th_accept, int check_ori, int* nmatches, int* rounds, void* cuda_stream);
 
+/* ---- map-point side of the matching path (device resident, only enqueue) ------------------
+ * Frame::isInFrustum (src/Frame.cc:288-345, camera centre as Frame::UpdatePoseMatrices :280-285, level by
+ * MapPoint::PredictScale src/MapPoint.cc:459-475) for every (frame, map point): the loop of
+ * Tracking::SearchLocalPoints that prepares SearchByProjection(Frame&, vector<MapPoint*>&, th).
+ * Tcw [nprob][16] row-major poses (device); K = fx, fy, cx, cy (host); scale_factor = mfScaleFactor.
+ * Map points: xyz / normal [.][3] (GetWorldPos / GetNormal), max_distance / min_distance = mfMaxDistance /
+ * mfMinDistance (the 1.2 / 0.8 invariance factors are applied here); [nprob][nq_stride] or, with
+ * points_shared, one set [nq_stride] for all frames.  Outputs [nprob][nq_stride] in the layout of orbm_points:
+ * in_view = mbTrackInView, proj_xyxr = mTrackProjX/Y/XR, level = mnTrackScaleLevel, view_cos = mTrackViewCos
+ * (entries of points not in view keep their old contents, as the reference leaves those members alone);
+ * n_in_view [nprob] or NULL. */
+int orbm_project_points_batch(int nprob, const float* Tcw, const float* K, float bf, float min_x, float max_x, float min_y,
+                              float max_y, float scale_factor, int nlevels, float viewing_cos_limit,
+                              const int* nq, int nq_stride, int points_shared, const float* xyz, const float* normal,
+                              const float* max_distance, const float* min_distance, uint8_t* in_view, float* proj_xyxr,
+                              int* level, float* view_cos, int* n_in_view, void* cuda_stream);
+
+/* MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:275-340) for npoints map points at once: the
+ * observations of point p are the descriptors desc[offsets[p] .. offsets[p+1]) in the order the reference
+ * iterates its observation map (key-frame pointer order); bad (or NULL) marks observations whose key frame
+ * isBad().  best_idx [npoints] = index inside the point's own range of the descriptor with the least median
+ * distance to the others (first on ties), -1 when there is none (mDescriptor stays as it is), -2 when the
+ * point has more than 4096 observations; best_median [npoints] (or NULL) = that median. */
+int orbm_distinctive_descriptors(const uint8_t* desc, const int* offsets, int npoints, const uint8_t* bad,
+                                 int* best_idx, int* best_median, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

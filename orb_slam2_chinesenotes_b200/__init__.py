@@ -111,6 +111,8 @@ def lib():
         L.orbm_window_search_best.argtypes = [fp, i32] + [vp] * 11 + [i32, i32, pi, i32]
         L.orbm_search_by_projection_points_batch.argtypes = [C.POINTER(OrbmFrames), vp, i32, C.POINTER(OrbmPoints), vp, vp, f32, f32, vp, vp, vp]
         L.orbm_window_search_best_batch.argtypes = [C.POINTER(OrbmFrames), C.POINTER(OrbmWindows), vp, vp, i32, i32, vp, vp, vp]
+        L.orbm_project_points_batch.argtypes = [i32, vp, vp, f32, f32, f32, f32, f32, f32, i32, f32, vp, i32, i32] + [vp] * 9 + [vp]
+        L.orbm_distinctive_descriptors.argtypes = [vp, vp, i32, vp, vp, vp, vp]
         L.orbm_stereo_matches.argtypes = [vp, i32, vp, i32, i32, vp, vp, i32, vp, vp, f32, f32, vp, vp, pi]
         _lib = L
     return _lib
@@ -443,6 +445,30 @@ def window_search_best_batch(frames, q, nq, nq_stride, assign_out, nmatches, th_
                                              int(check_ori), _ptr(nmatches), _ptr(rounds), stream)
     if rc:
         raise OrbError(rc, "orbm_window_search_best_batch failed")
+
+
+def project_points_batch(Tcw, K, bf, bounds, scale_factor, nlevels, nq, nq_stride, pts, out, cos_limit=0.5, points_shared=False,
+                         n_in_view=None, stream=None):
+    """orbm_project_points_batch: Frame::isInFrustum + MapPoint::PredictScale for every (frame, map point).
+    Tcw [P,16], nq [P] and pts = dict(xyz, normal, max_d, min_d) are CUDA tensors; out = dict(in_view, proj, level,
+    view_cos) CUDA tensors [P,nq_stride(,3)] -- the same arrays search_by_projection_points_batch takes.  Only enqueues."""
+    K = np.ascontiguousarray(K, np.float32)
+    rc = lib().orbm_project_points_batch(int(Tcw.shape[0]), _ptr(Tcw), K.ctypes.data, float(bf), *(float(b) for b in bounds),
+                                         float(np.float32(scale_factor)), nlevels, cos_limit, _ptr(nq), nq_stride, int(points_shared),
+                                         _ptr(pts["xyz"]), _ptr(pts["normal"]), _ptr(pts["max_d"]), _ptr(pts["min_d"]),
+                                         _ptr(out["in_view"]), _ptr(out["proj"]), _ptr(out["level"]), _ptr(out["view_cos"]),
+                                         _ptr(n_in_view), stream)
+    if rc:
+        raise OrbError(rc, "orbm_project_points_batch failed")
+
+
+def distinctive_descriptors(desc, offsets, best_idx, best_median=None, bad=None, stream=None):
+    """orbm_distinctive_descriptors: MapPoint::ComputeDistinctiveDescriptors for len(offsets)-1 map points whose
+    observations are desc[offsets[p]:offsets[p+1]] (CUDA tensors).  Only enqueues."""
+    rc = lib().orbm_distinctive_descriptors(_ptr(desc), _ptr(offsets), int(offsets.shape[0]) - 1, _ptr(bad), _ptr(best_idx),
+                                            _ptr(best_median), stream)
+    if rc:
+        raise OrbError(rc, "orbm_distinctive_descriptors failed")
 
 
 def stereo_matches(ex_left, ex_right, kps_l, desc_l, kps_r, desc_r, bf, fx, frame_l=0, frame_r=0):
