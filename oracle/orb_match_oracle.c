@@ -449,3 +449,65 @@ int orbo_stereo_matches(const orbo_extractor* eL, const orbo_extractor* eR,
     free(rows); free(vDistIdx);
     return nd;
 }
+
+/* ORBmatcher::SearchByBoW, src/ORBmatcher.cc:552-697 (KeyFrame -> Frame; valid2 == NULL, strict == 0) and
+ * :700-832 (KeyFrame -> KeyFrame; valid2 = "has a map point that is not bad", strict == 1: bestDist1 < TH_LOW).
+ * The DBoW2::FeatureVector of each side in CSR form: node_id [nn] ascending, node_off [nn + 1], feat [node_off[nn]].
+ * valid1 [n1]: key-frame-1 feature has a map point that is not bad.  match12 [n1] = matched feature of side 2 or -1,
+ * match21 [n2] (or NULL) the inverse.  Returns nmatches. */
+int orbo_search_by_bow(int n1, const orbo_kp* kps1, const uint8_t* desc1, const uint8_t* valid1,
+                       int nn1, const int* node_id1, const int* node_off1, const int* feat1,
+                       int n2, const orbo_kp* kps2, const uint8_t* desc2, const uint8_t* valid2,
+                       int nn2, const int* node_id2, const int* node_off2, const int* feat2,
+                       float nnratio, int checkOri, int strict, int* match12, int* match21)
+{
+    int nmatches = 0;
+    uint8_t* matched2 = (uint8_t*)calloc((size_t)(n2 > 0 ? n2 : 1), 1);
+    ivec hist[HISTO_LENGTH];
+    memset(hist, 0, sizeof(hist));
+    for (int i = 0; i < n1; ++i) match12[i] = -1;
+    if (match21) for (int i = 0; i < n2; ++i) match21[i] = -1;
+    int a = 0, b = 0;
+    while (a < nn1 && b < nn2) {
+        if (node_id1[a] == node_id2[b]) {
+            for (int p1 = node_off1[a]; p1 < node_off1[a + 1]; ++p1) {
+                const int idx1 = feat1[p1];
+                if (!valid1[idx1]) continue;
+                int bestDist1 = 256, bestDist2 = 256, bestIdx2 = -1;
+                for (int p2 = node_off2[b]; p2 < node_off2[b + 1]; ++p2) {
+                    const int idx2 = feat2[p2];
+                    if (matched2[idx2] || (valid2 && !valid2[idx2])) continue;
+                    const int dist = orbo_descriptor_distance(desc1 + (size_t)idx1 * 32, desc2 + (size_t)idx2 * 32);
+                    if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdx2 = idx2; }
+                    else if (dist < bestDist2) bestDist2 = dist;
+                }
+                if (strict ? bestDist1 < TH_LOW : bestDist1 <= TH_LOW) {                        /* :768 / :618 */
+                    if ((float)bestDist1 < nnratio * (float)bestDist2) {
+                        match12[idx1] = bestIdx2;
+                        matched2[bestIdx2] = 1;
+                        if (checkOri) ivec_push(&hist[rot_bin(kps1[idx1].angle, kps2[bestIdx2].angle)], idx1);
+                        nmatches++;
+                    }
+                }
+            }
+            ++a; ++b;
+        } else if (node_id1[a] < node_id2[b]) {
+            while (a < nn1 && node_id1[a] < node_id2[b]) ++a;                                   /* lower_bound */
+        } else {
+            while (b < nn2 && node_id2[b] < node_id1[a]) ++b;
+        }
+    }
+    if (checkOri) {
+        int sizes[HISTO_LENGTH], i1, i2, i3;
+        for (int i = 0; i < HISTO_LENGTH; ++i) sizes[i] = hist[i].n;
+        three_maxima(sizes, HISTO_LENGTH, &i1, &i2, &i3);
+        for (int i = 0; i < HISTO_LENGTH; ++i) {
+            if (i == i1 || i == i2 || i == i3) continue;
+            for (int j = 0; j < hist[i].n; ++j) { match12[hist[i].v[j]] = -1; nmatches--; }
+        }
+    }
+    if (match21) for (int i = 0; i < n1; ++i) if (match12[i] >= 0) match21[match12[i]] = i;
+    for (int i = 0; i < HISTO_LENGTH; ++i) free(hist[i].v);
+    free(matched2);
+    return nmatches;
+}

@@ -121,6 +121,22 @@ int orbo_search_by_projection_sim3(int n, const orbo_kp* kps, const uint8_t* des
                                    float* uvr_out, int* minl_out, int* maxl_out, uint8_t* valid_out);
 
 /* Frame::ComputeStereoMatches, src/Frame.cc:513-699 */
+/* ORBmatcher::SearchByBoW, src/ORBmatcher.cc:552-697 (strict = 0, valid2 = NULL) and :700-832 (strict = 1). */
+int orbo_search_by_bow(int n1, const orbo_kp* kps1, const uint8_t* desc1, const uint8_t* valid1,
+                       int nn1, const int* node_id1, const int* node_off1, const int* feat1,
+                       int n2, const orbo_kp* kps2, const uint8_t* desc2, const uint8_t* valid2,
+                       int nn2, const int* node_id2, const int* node_off2, const int* feat2,
+                       float nnratio, int checkOri, int strict, int* match12, int* match21);
+
+/* map-point side, orb_mappoint_oracle.c */
+int orbo_distinctive_descriptor(const uint8_t* desc, int n, const uint8_t* bad, int* median_out);
+int orbo_predict_scale(float max_distance, float current_dist, float log_scale_factor, int nlevels);
+float orbo_log_scale_factor(float scale_factor);
+int orbo_is_in_frustum(const float* Tcw, const float* K, float bf, float minX, float maxX, float minY, float maxY,
+                       float scale_factor, int nlevels, float viewing_cos_limit, int n, const float* xyz, const float* normal,
+                       const float* max_distance, const float* min_distance, unsigned char* in_view, float* proj_xyxr,
+                       int* level, float* view_cos);
+
 int orbo_stereo_matches(const orbo_extractor* eL, const orbo_extractor* eR,
                         int nl, const orbo_kp* kps_l, const uint8_t* desc_l,
                         int nr, const orbo_kp* kps_r, const uint8_t* desc_r,

@@ -132,8 +132,23 @@ def mappoint():
     np.savez_compressed(os.path.join(HERE, "ref_mappoint.npz"), **out)
 
 
+def bow():
+    """Outputs of the reference's unmodified ORBmatcher::SearchByBoW overloads on the scene of tests/bow_lib.py."""
+    from bow_lib import bow_scene, search_by_bow
+    from matcher_lib import extract_frame
+    from test_bow_oracle import CASES
+    kps, desc, _ = extract_frame(1241, 376, 2000, 2)
+    s = bow_scene(kps, desc, 5)
+    out = dict(seed=5)
+    for k, (nnratio, check_ori, kf_kf) in enumerate(CASES):
+        nm, m = search_by_bow("ref", s, nnratio, check_ori, kf_kf)
+        out[f"nm_{k}"] = nm
+        out[f"match_{k}"] = m
+    np.savez_compressed(os.path.join(HERE, "ref_bow.npz"), **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["primitives", "extractor", "matchers", "projection_overloads", "mappoint"]
+    which = sys.argv[1:] or ["primitives", "extractor", "matchers", "projection_overloads", "mappoint", "bow"]
     for name in which:
         globals()[name]()
     print("golden fixtures written to", HERE)
