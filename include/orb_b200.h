@@ -276,6 +276,26 @@ int orbm_project_points_batch(int nprob, const float* Tcw, const float* K, float
 int orbm_distinctive_descriptors(const uint8_t* desc, const int* offsets, int npoints, const uint8_t* bad,
                                  int* best_idx, int* best_median, void* cuda_stream);
 
+/* A DBoW2::FeatureVector (std::map<NodeId, vector<unsigned>>, Thirdparty/DBoW2 in upstream ORB-SLAM2; read at
+ * src/ORBmatcher.cc:560-577) per frame in CSR form, device memory: node_id [nprob][node_stride] ascending NodeIds,
+ * node_off [nprob][node_stride + 1] offsets into feat, n_nodes [nprob], feat [nprob][kp_stride of the frame]
+ * feature indices node by node, in the order the vocabulary added them. */
+typedef struct {
+    const int* node_id; const int* node_off; const int* n_nodes; const int* feat; int node_stride;
+} orbm_featvec;
+
+/* ORBmatcher::SearchByBoW for nprob (side A, side B) problems: kf_kf = 0: (KeyFrame*, Frame&, matches),
+ * src/ORBmatcher.cc:552-697 (A = key frame, B = frame, bestDist1 <= TH_LOW, b_valid = NULL); kf_kf = 1:
+ * (KeyFrame*, KeyFrame*, matches12), :700-832 (bestDist1 < TH_LOW, b_valid marks side-B features whose map point
+ * exists and is not bad).  a_valid [nprob][A.kp_stride] likewise for side A.  The frames' kps supply the angles of
+ * the rotation histogram (check_ori).  match12 [nprob][A.kp_stride] = matched feature of side B or -1 (the
+ * reference's vpMatches12 / vpMapPointMatches hold that feature's map point); match21 [nprob][B.kp_stride] (or
+ * NULL) the inverse; nmatches [nprob] the return value (-1: sizes exceed 8192 or the strides).  Only enqueues. */
+int orbm_search_by_bow_batch(const orbm_frames* A, const orbm_featvec* VA, const uint8_t* a_valid,
+                             const orbm_frames* B, const orbm_featvec* VB, const uint8_t* b_valid,
+                             int kf_kf, float nnratio, int check_ori, int* match12, int* match21,
+                             int* nmatches, int* rounds, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

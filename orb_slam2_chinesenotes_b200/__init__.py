@@ -49,6 +49,11 @@ class OrbmWindows(C.Structure):
                 ("q_obs", C.c_void_p)]
 
 
+class OrbmFeatVec(C.Structure):
+    """orbm_featvec: DBoW2::FeatureVector per frame in CSR form (device arrays)."""
+    _fields_ = [("node_id", C.c_void_p), ("node_off", C.c_void_p), ("n_nodes", C.c_void_p), ("feat", C.c_void_p), ("node_stride", C.c_int)]
+
+
 class OrbError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"orb_b200 status {code}: {msg}")
@@ -113,6 +118,8 @@ def lib():
         L.orbm_window_search_best_batch.argtypes = [C.POINTER(OrbmFrames), C.POINTER(OrbmWindows), vp, vp, i32, i32, vp, vp, vp]
         L.orbm_project_points_batch.argtypes = [i32, vp, vp, f32, f32, f32, f32, f32, f32, i32, f32, vp, i32, i32] + [vp] * 9 + [vp]
         L.orbm_distinctive_descriptors.argtypes = [vp, vp, i32, vp, vp, vp, vp]
+        L.orbm_search_by_bow_batch.argtypes = [C.POINTER(OrbmFrames), C.POINTER(OrbmFeatVec), vp, C.POINTER(OrbmFrames), C.POINTER(OrbmFeatVec), vp,
+                                               i32, f32, i32, vp, vp, vp, vp, vp]
         L.orbm_stereo_matches.argtypes = [vp, i32, vp, i32, i32, vp, vp, i32, vp, vp, f32, f32, vp, vp, pi]
         _lib = L
     return _lib
@@ -469,6 +476,18 @@ def distinctive_descriptors(desc, offsets, best_idx, best_median=None, bad=None,
                                             _ptr(best_median), stream)
     if rc:
         raise OrbError(rc, "orbm_distinctive_descriptors failed")
+
+
+def search_by_bow_batch(A, VA, a_valid, B, VB, b_valid, kf_kf, nnratio, check_ori, match12, nmatches, match21=None, rounds=None, stream=None):
+    """orbm_search_by_bow_batch: ORBmatcher::SearchByBoW (src/ORBmatcher.cc:552-832) for every (A, B) problem.  A, B:
+    frames_batch(...); VA, VB: (node_id [P,S], node_off [P,S+1], n_nodes [P], feat [P,cap]) CUDA int32 tensors."""
+    fa = OrbmFeatVec(_ptr(VA[0]), _ptr(VA[1]), _ptr(VA[2]), _ptr(VA[3]), int(VA[0].shape[1]))
+    fb = OrbmFeatVec(_ptr(VB[0]), _ptr(VB[1]), _ptr(VB[2]), _ptr(VB[3]), int(VB[0].shape[1]))
+    rc = lib().orbm_search_by_bow_batch(C.byref(A), C.byref(fa), _ptr(a_valid), C.byref(B), C.byref(fb), _ptr(b_valid), int(kf_kf),
+                                        float(np.float32(nnratio)), int(check_ori), _ptr(match12), _ptr(match21), _ptr(nmatches),
+                                        _ptr(rounds), stream)
+    if rc:
+        raise OrbError(rc, "orbm_search_by_bow_batch failed")
 
 
 def stereo_matches(ex_left, ex_right, kps_l, desc_l, kps_r, desc_r, bf, fx, frame_l=0, frame_r=0):
