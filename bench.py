@@ -267,7 +267,7 @@ def bench_hamming(dev, device_index, nq=2000, nt=2000, nprob=256, reps=5):
             "peak_note": "SMs x 16 POPC/clk x 1965 MHz / 8 POPC per pair"}
 
 
-def bench_window_match(dev, d_kps, d_desc, d_n, cap, w, h, scale, nprob=512, nq=2000, reps=5, cpu=True):
+def bench_window_match(dev, d_kps, d_desc, d_n, cap, w, h, scale, nprob=512, nq=2000, reps=40, cpu=True):
     """BASELINE.json configs[3]: windowed SearchByProjection(Frame, MapPoints) matching (src/ORBmatcher.cc:73-157),
     2000 map points against the ~2000 keypoints of a frame, TH_HIGH = 100, nnratio = 0.9, th = 3, for `nprob` frames per
     launch.  The frames are the left images the extractor just produced and stay where it left them in HBM; the
@@ -310,7 +310,7 @@ def bench_window_match(dev, d_kps, d_desc, d_n, cap, w, h, scale, nprob=512, nq=
     def run():
         ob.search_by_projection_points_batch(F, scale, q, d_nq, nq, d_assign, d_nm, th, nnratio, None, d_rounds, stream.cuda_stream)
 
-    for _ in range(3):
+    for _ in range(20):                                             # short kernels: let the clocks settle
         run()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -342,6 +342,144 @@ def bench_window_match(dev, d_kps, d_desc, d_n, cap, w, h, scale, nprob=512, nq=
         assert want[0] == int(nm[0]) and (want[1] == d_assign[0, :n0].cpu().numpy()).all(), "window matcher disagrees with the CPU checker"
         out["cpu_baseline"] = {"value": 1.0 / dt, "unit": "problems/s", "cores": 1, "kind": "reference" if M.impl == "ref" else "port",
                                "sample": "problem 0 of the launch, 20 repetitions, results compared"}
+    return out
+
+
+def bench_mappoint_side(dev, d_kps, d_desc, d_n, cap, w, h, scale_factor, reps=40, cpu=True):
+    """SURVEY.md section 8f rows on the frames the extractor just produced (device resident, one launch each):
+      projection   Frame::isInFrustum + MapPoint::PredictScale, 4000 map points x nprob frames (src/Frame.cc:288-345)
+      bow          ORBmatcher::SearchByBoW(KeyFrame, KeyFrame): left frame p against left frame p+1 with a synthetic
+                   256-node feature vector (src/ORBmatcher.cc:700-832)
+      distinctive  MapPoint::ComputeDistinctiveDescriptors for 65536 map points with 2..33 observations each
+    CPU figures: the oracle's C restatement of the same functions on one core (kind "port"), problem 0, results compared."""
+    import torch
+    import orb_slam2_chinesenotes_b200 as ob
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    stream = torch.cuda.current_stream()
+    out = {}
+
+    def timed(fn):
+        for _ in range(20):                                         # short kernels: let the clocks settle
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    g = torch.Generator(device=dev).manual_seed(5)
+    # ---- projection
+    nprob, npts = 2 * sms, 4000
+    K = np.float32([CAM["fx"], CAM["fy"], CAM["cx"], CAM["cy"]])
+    Tcw = torch.eye(4, device=dev).repeat(nprob, 1, 1)
+    Tcw[:, :3, 3] = 0.3 * torch.randn((nprob, 3), generator=g, device=dev)
+    Tcw = Tcw.reshape(nprob, 16).contiguous()
+    z = 2 + 58 * torch.rand(npts, generator=g, device=dev)
+    xyz = torch.stack([(torch.rand(npts, generator=g, device=dev) * 1.4 - 0.2) * w, (torch.rand(npts, generator=g, device=dev) * 1.4 - 0.2) * h, z], 1)
+    xyz[:, 0] = (xyz[:, 0] - CAM["cx"]) / CAM["fx"] * z
+    xyz[:, 1] = (xyz[:, 1] - CAM["cy"]) / CAM["fy"] * z
+    xyz = xyz.contiguous()
+    dist = xyz.norm(dim=1)
+    normal = (xyz / dist[:, None] + 0.3 * torch.randn((npts, 3), generator=g, device=dev))
+    normal = (normal / normal.norm(dim=1, keepdim=True)).contiguous()
+    max_d = (dist * (0.7 + 2.0 * torch.rand(npts, generator=g, device=dev))).contiguous()
+    min_d = (max_d / 1.2 ** 7).contiguous()
+    pts = dict(xyz=xyz, normal=normal, max_d=max_d, min_d=min_d)
+    po = dict(in_view=torch.zeros((nprob, npts), dtype=torch.uint8, device=dev), proj=torch.zeros((nprob, npts, 3), device=dev),
+              level=torch.zeros((nprob, npts), dtype=torch.int32, device=dev), view_cos=torch.zeros((nprob, npts), device=dev))
+    nq = torch.full((nprob,), npts, dtype=torch.int32, device=dev)
+    cnt = torch.zeros(nprob, dtype=torch.int32, device=dev)
+    bounds = (0.0, float(w), 0.0, float(h))
+    ms = timed(lambda: ob.project_points_batch(Tcw, K, CAM["bf"], bounds, scale_factor, LEVELS, nq, npts, pts, po, 0.5, True, cnt, stream.cuda_stream))
+    out["projection"] = {"value": nprob * npts / (ms * 1e-3), "unit": "points/s", "frames_per_launch": nprob, "points_per_frame": npts,
+                         "ms_per_launch": ms, "in_view_fraction": float(cnt.float().mean().item()) / npts}
+    # ---- bow
+    nb = min((d_kps.shape[0] // 2 - 1) // sms * sms or 1, 3 * sms)
+    kA, dA, nA = d_kps[0:2 * nb:2].contiguous(), d_desc[0:2 * nb:2].contiguous(), d_n[0:2 * nb:2].contiguous()
+    kB, dB, nB = d_kps[2:2 * nb + 2:2].contiguous(), d_desc[2:2 * nb + 2:2].contiguous(), d_n[2:2 * nb + 2:2].contiguous()
+
+    def featvec(desc, n):
+        P = desc.shape[0]
+        node = (desc[:, :, 0].to(torch.int32) >> 4) * 16 + (desc[:, :, 1].to(torch.int32) >> 4)
+        node = torch.where(torch.arange(cap, device=dev)[None, :] < n[:, None], node, 1 << 20)   # padding sorts last
+        order = torch.argsort(node, dim=1, stable=True).to(torch.int32).contiguous()
+        counts = torch.zeros((P, 256), dtype=torch.int32, device=dev)
+        counts.scatter_add_(1, node.clamp(max=255).long(), (node < 256).to(torch.int32))
+        off = torch.zeros((P, 257), dtype=torch.int32, device=dev)
+        off[:, 1:] = counts.cumsum(1)
+        ids = torch.arange(256, device=dev, dtype=torch.int32).repeat(P, 1).contiguous()           # empty nodes keep empty runs
+        return ids, off.contiguous(), torch.full((P,), 256, dtype=torch.int32, device=dev), order
+
+    VA, VB = featvec(dA, nA), featvec(dB, nB)
+    # the two left frames are different scenes: make side B a noisy copy of side A so that there is something to match
+    dB = dA.clone()
+    dB[:, :, 4:] ^= (torch.rand(dB[:, :, 4:].shape, generator=g, device=dev) < 0.02).to(torch.uint8) * 16
+    kB, nB, VB = kA, nA, featvec(dB, nA)
+    valid = torch.ones((nb, cap), dtype=torch.uint8, device=dev)
+    FA, FB = ob.frames_batch(kA, dA, nA, bounds), ob.frames_batch(kB, dB, nB, bounds)
+    m12 = torch.zeros((nb, cap), dtype=torch.int32, device=dev)
+    nm = torch.zeros(nb, dtype=torch.int32, device=dev)
+    rounds = torch.zeros(nb, dtype=torch.int32, device=dev)
+    ms = timed(lambda: ob.search_by_bow_batch(FA, VA, valid, FB, VB, valid, True, 0.75, True, m12, nm, None, rounds, stream.cuda_stream))
+    out["bow"] = {"value": nb / (ms * 1e-3), "unit": "problems/s", "what": "SearchByBoW(KeyFrame, KeyFrame), nnratio 0.75, 256 nodes",
+                  "problems_per_launch": nb, "ms_per_launch": ms, "matches_per_problem": float(nm.float().mean().item()),
+                  "rounds_max": int(rounds.max().item())}
+    # ---- distinctive descriptors
+    npnt = 65536
+    sizes = torch.randint(2, 34, (npnt,), generator=g, device=dev, dtype=torch.int32)
+    off = torch.zeros(npnt + 1, dtype=torch.int32, device=dev)
+    off[1:] = sizes.cumsum(0)
+    total = int(off[-1].item())
+    owner = torch.repeat_interleave(torch.arange(npnt, device=dev), sizes.long())
+    base = torch.randint(0, 256, (npnt, 32), generator=g, device=dev, dtype=torch.uint8)
+    obs = base[owner] ^ ((torch.rand((total, 32), generator=g, device=dev) < 0.25).to(torch.uint8) * torch.randint(1, 256, (total, 32), generator=g, device=dev, dtype=torch.uint8))
+    obs = obs.contiguous()
+    bi = torch.zeros(npnt, dtype=torch.int32, device=dev)
+    bm = torch.zeros(npnt, dtype=torch.int32, device=dev)
+    ms = timed(lambda: ob.distinctive_descriptors(obs, off, bi, bm, None, stream.cuda_stream))
+    pairs = float((sizes.double() ** 2).sum().item())
+    out["distinctive"] = {"value": npnt / (ms * 1e-3), "unit": "map points/s", "points_per_launch": npnt, "observations": total,
+                          "ms_per_launch": ms, "Gpairs_per_s": pairs / (ms * 1e-3) / 1e9}
+    if cpu:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from bow_lib import search_by_bow
+        from mappoint_lib import distinctive, is_in_frustum
+        import oracle_lib
+        # projection, frame 0
+        sc = dict(Tcw=Tcw[0].cpu().numpy().reshape(4, 4).copy(), K=K, bf=np.float32(CAM["bf"]), bounds=bounds, xyz=xyz.cpu().numpy(),
+                  normal=normal.cpu().numpy(), max_d=max_d.cpu().numpy(), min_d=min_d.cpu().numpy())
+        t0 = time.perf_counter()
+        for _ in range(20):
+            iv, pj, lv, vc = is_in_frustum("oracle", sc, scale_factor=scale_factor, nlevels=LEVELS)
+        dt = (time.perf_counter() - t0) / 20
+        m = iv.astype(bool)
+        assert (po["in_view"][0].cpu().numpy() == iv).all() and (po["proj"][0].cpu().numpy()[m].view(np.uint32) == pj[m].view(np.uint32)).all() \
+            and (po["level"][0].cpu().numpy()[m] == lv[m]).all(), "projection disagrees with the CPU checker"
+        out["projection"]["cpu_baseline"] = {"value": npts / dt, "unit": "points/s", "cores": 1, "kind": "port", "sample": "frame 0, 20 repetitions, results compared"}
+        # bow, problem 0
+        n0 = int(nA[0].item())
+        tonp = lambda t: np.ascontiguousarray(t.cpu().numpy())
+        kp0 = tonp(kA[0, :n0]).view(oracle_lib.KP_DTYPE).reshape(n0)
+        fv = lambda V: (tonp(V[0][0]), tonp(V[1][0]), tonp(V[3][0, :n0]))
+        s = dict(k1=kp0, d1=tonp(dA[0, :n0]), k2=kp0, d2=tonp(dB[0, :n0]), valid1=np.ones(n0, np.uint8), bad1=np.zeros(n0, np.uint8),
+                 valid2=np.ones(n0, np.uint8), bad2=np.zeros(n0, np.uint8), fv1=fv(VA), fv2=fv(VB))
+        t0 = time.perf_counter()
+        for _ in range(20):
+            want = search_by_bow("oracle", s, 0.75, True, True)
+        dt = (time.perf_counter() - t0) / 20
+        assert want[0] == int(nm[0].item()) and (want[1] == m12[0, :n0].cpu().numpy()).all(), "SearchByBoW disagrees with the CPU checker"
+        out["bow"]["cpu_baseline"] = {"value": 1.0 / dt, "unit": "problems/s", "cores": 1, "kind": "port", "sample": "problem 0, 20 repetitions, results compared"}
+        # distinctive, first 2000 points
+        offh, obsh = off.cpu().numpy(), obs.cpu().numpy()
+        t0 = time.perf_counter()
+        got = [distinctive("oracle", obsh[offh[p]:offh[p + 1]])[1:] for p in range(2000)]
+        dt = time.perf_counter() - t0
+        assert [g_[0] for g_ in got] == bi[:2000].cpu().tolist() and [g_[1] for g_ in got] == bm[:2000].cpu().tolist(), "distinctive descriptors disagree"
+        out["distinctive"]["cpu_baseline"] = {"value": 2000 / dt, "unit": "map points/s", "cores": 1, "kind": "port",
+                                              "sample": "first 2000 points through ctypes (call overhead included), results compared"}
     return out
 
 
@@ -512,9 +650,10 @@ def run_ours(args, rank, world, local_rank):
         cfg_stereo = {"stereo": "frames are rectified pairs L0,R0,L1,R1,...: left/right extraction + Frame::ComputeStereoMatches per pair",
                       "pairs_per_step_per_gpu": pairs, "depth_points_per_pair": n_depth / pairs}
     hamming = bench_hamming(dev, local_rank) if world == 1 else None
-    window = None
+    window = mappoint = None
     if world == 1 and stereo:
         window = bench_window_match(dev, d_kps, d_desc, d_n, cap, w, h, ex.GetScaleFactors(), cpu=not args.no_cpu)
+        mappoint = bench_mappoint_side(dev, d_kps, d_desc, d_n, cap, w, h, SCALE, cpu=not args.no_cpu)
     print(json.dumps({
         "metric": "orb_extract_frames_per_s", "value": value, "unit": "frames/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps,
@@ -527,7 +666,7 @@ def run_ours(args, rank, world, local_rank):
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": (LEVELS - 1 + 4 + (3 if stereo else 0)) * chunks * args.steps,
         "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "hamming_bf": hamming,
-        "window_match": window,
+        "window_match": window, "mappoint_side": mappoint,
     }))
     if dist is not None:
         dist.destroy_process_group()
