@@ -296,6 +296,19 @@ int orbm_search_by_bow_batch(const orbm_frames* A, const orbm_featvec* VA, const
                              int kf_kf, float nnratio, int check_ori, int* match12, int* match21,
                              int* nmatches, int* rounds, void* cuda_stream);
 
+/* ---- the same three for ONE problem with HOST arrays (what the C++ forwarders call) ---------
+ * orbm_search_by_bow: SearchByBoW (src/ORBmatcher.cc:552-832), feature vectors in CSR form (see orbm_featvec).
+ * orbm_project_points: Frame::isInFrustum for n map points of one frame (src/Frame.cc:288-345).
+ * orbm_distinctive_descriptor: MapPoint::ComputeDistinctiveDescriptors for one map point (src/MapPoint.cc:275-340). */
+int orbm_search_by_bow(const orbm_frame* A, const uint8_t* a_valid, int nn_a, const int* node_id_a, const int* node_off_a, const int* feat_a,
+                       const orbm_frame* B, const uint8_t* b_valid, int nn_b, const int* node_id_b, const int* node_off_b, const int* feat_b,
+                       int kf_kf, float nnratio, int check_ori, int* match12, int* nmatches, int device);
+int orbm_project_points(const float* Tcw, const float* K, float bf, float min_x, float max_x, float min_y, float max_y,
+                        float scale_factor, int nlevels, float viewing_cos_limit, int n, const float* xyz, const float* normal,
+                        const float* max_distance, const float* min_distance, uint8_t* in_view, float* proj_xyxr, int* level,
+                        float* view_cos, int device);
+int orbm_distinctive_descriptor(const uint8_t* desc, int n, const uint8_t* bad, int* best_idx, int* best_median, int device);
+
 #ifdef __cplusplus
 }
 #endif

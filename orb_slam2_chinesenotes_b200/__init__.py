@@ -120,6 +120,9 @@ def lib():
         L.orbm_distinctive_descriptors.argtypes = [vp, vp, i32, vp, vp, vp, vp]
         L.orbm_search_by_bow_batch.argtypes = [C.POINTER(OrbmFrames), C.POINTER(OrbmFeatVec), vp, C.POINTER(OrbmFrames), C.POINTER(OrbmFeatVec), vp,
                                                i32, f32, i32, vp, vp, vp, vp, vp]
+        L.orbm_search_by_bow.argtypes = [fp, vp, i32, vp, vp, vp, fp, vp, i32, vp, vp, vp, i32, f32, i32, vp, pi, i32]
+        L.orbm_project_points.argtypes = [vp, vp, f32, f32, f32, f32, f32, f32, i32, f32, i32] + [vp] * 8 + [i32]
+        L.orbm_distinctive_descriptor.argtypes = [vp, i32, vp, pi, pi, i32]
         L.orbm_stereo_matches.argtypes = [vp, i32, vp, i32, i32, vp, vp, i32, vp, vp, f32, f32, vp, vp, pi]
         _lib = L
     return _lib
@@ -399,6 +402,49 @@ class ORBmatcher:
         self._rc(lib().orbm_search_for_initialization(C.byref(f1), C.byref(f2), prev.ctypes.data, m12.ctypes.data, windowSize,
                  self.mfNNratio, int(self.mbCheckOrientation), C.byref(nm), self.device), "orbm_search_for_initialization")
         return nm.value, m12, prev
+
+
+def search_by_bow(A, fv_a, a_valid, B, fv_b, b_valid, kf_kf, nnratio, check_ori, device=0):
+    """orbm_search_by_bow: ORBmatcher::SearchByBoW (src/ORBmatcher.cc:552-832) for one pair with host arrays.  A, B:
+    FrameView; fv_*: (node_id, node_off, feat) int32 arrays; *_valid: uint8 per feature (b_valid None for the
+    KeyFrame/Frame overload).  Returns (nmatches, match12 [A.n])."""
+    (ia, oa, fa), (ib, ob, fb) = [tuple(_np(x, np.int32) for x in fv) for fv in (fv_a, fv_b)]
+    av, bv = _np(a_valid, np.uint8), _np(b_valid, np.uint8)
+    out = np.zeros(max(len(A.kps), 1), np.int32)
+    nm = C.c_int()
+    sa, sb = A.struct(), B.struct()
+    p = lambda a: None if a is None else a.ctypes.data
+    rc = lib().orbm_search_by_bow(C.byref(sa), p(av), len(ia), p(ia), p(oa), p(fa), C.byref(sb), p(bv), len(ib), p(ib), p(ob), p(fb),
+                                  int(kf_kf), float(np.float32(nnratio)), int(check_ori), p(out), C.byref(nm), device)
+    if rc:
+        raise OrbError(rc, "orbm_search_by_bow failed")
+    return nm.value, out[:len(A.kps)]
+
+
+def project_points(Tcw, K, bf, bounds, scale_factor, nlevels, xyz, normal, max_distance, min_distance, cos_limit=0.5, device=0):
+    """orbm_project_points: Frame::isInFrustum (src/Frame.cc:288-345) for n map points of one frame, host arrays.
+    Returns (in_view u8 [n], proj [n,3], level [n], view_cos [n]); entries of points not in view are zero."""
+    Tcw, K = _np(Tcw, np.float32), _np(K, np.float32)
+    xyz, normal, mx, mn = _np(xyz, np.float32), _np(normal, np.float32), _np(max_distance, np.float32), _np(min_distance, np.float32)
+    n = len(mx)
+    iv, proj, lv, vc = np.zeros(n, np.uint8), np.zeros((n, 3), np.float32), np.zeros(n, np.int32), np.zeros(n, np.float32)
+    rc = lib().orbm_project_points(Tcw.ctypes.data, K.ctypes.data, float(bf), *(float(b) for b in bounds), float(np.float32(scale_factor)),
+                                   nlevels, cos_limit, n, xyz.ctypes.data, normal.ctypes.data, mx.ctypes.data, mn.ctypes.data,
+                                   iv.ctypes.data, proj.ctypes.data, lv.ctypes.data, vc.ctypes.data, device)
+    if rc:
+        raise OrbError(rc, "orbm_project_points failed")
+    return iv, proj, lv, vc
+
+
+def distinctive_descriptor(desc, bad=None, device=0):
+    """orbm_distinctive_descriptor: MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:275-340) for one map
+    point's observations desc [n,32].  Returns (index or -1, median or -1)."""
+    desc, bad = _np(desc, np.uint8), _np(bad, np.uint8)
+    bi, bm = C.c_int(), C.c_int()
+    rc = lib().orbm_distinctive_descriptor(desc.ctypes.data, len(desc), None if bad is None else bad.ctypes.data, C.byref(bi), C.byref(bm), device)
+    if rc:
+        raise OrbError(rc, "orbm_distinctive_descriptor failed")
+    return bi.value, bm.value
 
 
 def window_search_best(F, uvr, min_level, max_level, qdesc, th_accept, check_ori=False, q_angle=None, q_obs=None,

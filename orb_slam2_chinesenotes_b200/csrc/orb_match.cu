@@ -820,4 +820,94 @@ int orbm_stereo_matches(orbx_ctx* ex_left, int frame_l, orbx_ctx* ex_right, int 
     return ORBX_OK;
 }
 
+
+// ---- single problems with HOST arrays over the device-resident kernels (what the C++ forwarders call)
+
+int orbm_search_by_bow(const orbm_frame* A, const uint8_t* a_valid, int nn_a, const int* node_id_a, const int* node_off_a, const int* feat_a,
+                       const orbm_frame* B, const uint8_t* b_valid, int nn_b, const int* node_id_b, const int* node_off_b, const int* feat_b,
+                       int kf_kf, float nnratio, int check_ori, int* match12, int* nmatches, int device)
+{
+    if (!A || !B || !a_valid || !match12 || !nmatches || nn_a < 0 || nn_b < 0 || A->n < 0 || B->n < 0) return ORBX_E_ARG;
+    if ((nn_a > 0 && (!node_id_a || !node_off_a || !feat_a)) || (nn_b > 0 && (!node_id_b || !node_off_b || !feat_b))) return ORBX_E_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return ORBX_E_CUDA; }
+    *nmatches = 0;
+    for (int i = 0; i < A->n; ++i) match12[i] = -1;
+    if (A->n == 0 || B->n == 0 || nn_a == 0 || nn_b == 0) return ORBX_OK;
+    Scratch S;
+    OneFrame OA, OB;
+    if (!one_frame(S, A, &OA) || !one_frame(S, B, &OB)) return S.ok ? ORBX_E_ARG : ORBX_E_CUDA;
+    OA.F.u_right = nullptr; OB.F.u_right = nullptr;
+    const int ta = node_off_a[nn_a], tb = node_off_b[nn_b];
+    if (ta < 0 || ta > A->n || tb < 0 || tb > B->n) return ORBX_E_ARG;
+    std::vector<int> fa((size_t)A->n, 0), fb((size_t)B->n, 0);
+    memcpy(fa.data(), feat_a, sizeof(int) * (size_t)ta);
+    memcpy(fb.data(), feat_b, sizeof(int) * (size_t)tb);
+    orbm_featvec VA, VB;
+    VA.node_id = S.up(node_id_a, (size_t)nn_a); VA.node_off = S.up(node_off_a, (size_t)nn_a + 1); VA.n_nodes = S.up(&nn_a, 1);
+    VA.feat = S.up(fa.data(), fa.size()); VA.node_stride = nn_a;
+    VB.node_id = S.up(node_id_b, (size_t)nn_b); VB.node_off = S.up(node_off_b, (size_t)nn_b + 1); VB.n_nodes = S.up(&nn_b, 1);
+    VB.feat = S.up(fb.data(), fb.size()); VB.node_stride = nn_b;
+    const uint8_t* d_av = S.up(a_valid, (size_t)A->n);
+    const uint8_t* d_bv = b_valid ? S.up(b_valid, (size_t)B->n) : nullptr;
+    int* d_m = (int*)S.alloc(sizeof(int) * (size_t)A->n);
+    int* d_nm = (int*)S.alloc(4);
+    if (!S.ok) return ORBX_E_CUDA;
+    const int rc = orbm_search_by_bow_batch(&OA.F, &VA, d_av, &OB.F, &VB, d_bv, kf_kf, nnratio, check_ori, d_m, nullptr, d_nm, nullptr, nullptr);
+    if (rc) return rc;
+    CKM(cudaMemcpy(match12, d_m, sizeof(int) * (size_t)A->n, cudaMemcpyDeviceToHost));
+    CKM(cudaMemcpy(nmatches, d_nm, 4, cudaMemcpyDeviceToHost));
+    return *nmatches < 0 ? ORBX_E_ARG : ORBX_OK;
+}
+
+int orbm_project_points(const float* Tcw, const float* K, float bf, float min_x, float max_x, float min_y, float max_y,
+                        float scale_factor, int nlevels, float viewing_cos_limit, int n, const float* xyz, const float* normal,
+                        const float* max_distance, const float* min_distance, uint8_t* in_view, float* proj_xyxr, int* level,
+                        float* view_cos, int device)
+{
+    if (!Tcw || !K || n < 0 || (n > 0 && (!xyz || !normal || !max_distance || !min_distance || !in_view || !proj_xyxr || !level || !view_cos))) return ORBX_E_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return ORBX_E_CUDA; }
+    if (n == 0) return ORBX_OK;
+    Scratch S;
+    const float* d_T = S.up(Tcw, 16);
+    const int* d_n = S.up(&n, 1);
+    const float* d_x = S.up(xyz, (size_t)n * 3); const float* d_nrm = S.up(normal, (size_t)n * 3);
+    const float* d_mx = S.up(max_distance, (size_t)n); const float* d_mn = S.up(min_distance, (size_t)n);
+    uint8_t* d_iv = (uint8_t*)S.alloc((size_t)n);
+    float* d_p = S.up(proj_xyxr, (size_t)n * 3);               // entries of points not in view keep the caller's values
+    int* d_l = S.up(level, (size_t)n);
+    float* d_vc = S.up(view_cos, (size_t)n);
+    if (!S.ok) return ORBX_E_CUDA;
+    const int rc = orbm_project_points_batch(1, d_T, K, bf, min_x, max_x, min_y, max_y, scale_factor, nlevels, viewing_cos_limit, d_n, n, 0,
+                                             d_x, d_nrm, d_mx, d_mn, d_iv, d_p, d_l, d_vc, nullptr, nullptr);
+    if (rc) return rc;
+    CKM(cudaMemcpy(in_view, d_iv, (size_t)n, cudaMemcpyDeviceToHost));
+    CKM(cudaMemcpy(proj_xyxr, d_p, sizeof(float) * (size_t)n * 3, cudaMemcpyDeviceToHost));
+    CKM(cudaMemcpy(level, d_l, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost));
+    CKM(cudaMemcpy(view_cos, d_vc, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost));
+    return ORBX_OK;
+}
+
+int orbm_distinctive_descriptor(const uint8_t* desc, int n, const uint8_t* bad, int* best_idx, int* best_median, int device)
+{
+    if (n < 0 || !best_idx || (n > 0 && !desc)) return ORBX_E_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return ORBX_E_CUDA; }
+    *best_idx = -1;
+    if (best_median) *best_median = -1;
+    if (n == 0) return ORBX_OK;
+    Scratch S;
+    const int off[2] = { 0, n };
+    const uint8_t* d_d = S.up(desc, (size_t)n * 32);
+    const uint8_t* d_b = bad ? S.up(bad, (size_t)n) : nullptr;
+    const int* d_o = S.up(off, 2);
+    int* d_r = (int*)S.alloc(8);
+    if (!S.ok) return ORBX_E_CUDA;
+    const int rc = orbm_distinctive_descriptors(d_d, d_o, 1, d_b, d_r, d_r + 1, nullptr);
+    if (rc) return rc;
+    int r[2];
+    CKM(cudaMemcpy(r, d_r, 8, cudaMemcpyDeviceToHost));
+    *best_idx = r[0];
+    if (best_median) *best_median = r[1];
+    return r[0] == -2 ? ORBX_E_ARG : ORBX_OK;
+}
+
 } // extern "C"

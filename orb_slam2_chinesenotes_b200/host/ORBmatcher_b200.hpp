@@ -17,6 +17,13 @@
 //   { return b200::SearchByProjection(Cur, pKF, sAlreadyFound, th, ORBdist, mbCheckOrientation); }   // src/ORBmatcher.cc:303
 //   int ORBmatcher::SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const vector<MapPoint*> &vpPoints, vector<MapPoint*> &vpMatched, int th)
 //   { return b200::SearchByProjection(pKF, Scw, vpPoints, vpMatched, th); }              // src/ORBmatcher.cc:434
+//   int ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame &F, vector<MapPoint*> &vpMapPointMatches)
+//   { return b200::SearchByBoW(pKF, F, vpMapPointMatches, mfNNratio, mbCheckOrientation); }          // src/ORBmatcher.cc:552
+//   int ORBmatcher::SearchByBoW(KeyFrame *pKF1, KeyFrame *pKF2, vector<MapPoint*> &vpMatches12)
+//   { return b200::SearchByBoW(pKF1, pKF2, vpMatches12, mfNNratio, mbCheckOrientation); }            // src/ORBmatcher.cc:700
+//   the isInFrustum loop of Tracking::SearchLocalPoints -> b200::IsInFrustum(F, vpPoints, 0.5f, inView)
+//   the distance-matrix / median part of MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:311-334)
+//   -> BestIdx = b200::DistinctiveDescriptor(vDescriptors)
 //   int ORBmatcher::DescriptorDistance(const cv::Mat &a, const cv::Mat &b)   stays on the CPU for single
 //   pairs (a 32-byte popcount); batches go through orbm_hamming_bf.
 //
@@ -30,6 +37,8 @@
 #include <map>
 #include <set>
 #include <stdexcept>
+#include <string>
+#include <type_traits>
 #include <vector>
 
 #include "orb_b200.h"
@@ -320,6 +329,120 @@ int SearchForInitialization(FrameT& F1, FrameT& F2, std::vector<Point2fT>& vbPre
           "orbm_search_for_initialization");
     for (size_t i = 0; i < k1.size(); ++i) { vnMatches12[i] = m12[i]; vbPrevMatched[i].x = prev[2 * i]; vbPrevMatched[i].y = prev[2 * i + 1]; }
     return nmatches;
+}
+
+// A DBoW2::FeatureVector (std::map<NodeId, std::vector<unsigned int>>) as the CSR arrays of orbm_featvec.
+template <class FeatVecT>
+inline void FlattenFeatureVector(const FeatVecT& fv, std::vector<int>& node_id, std::vector<int>& node_off, std::vector<int>& feat)
+{
+    node_id.clear(); node_off.assign(1, 0); feat.clear();
+    for (typename FeatVecT::const_iterator it = fv.begin(); it != fv.end(); ++it) {
+        node_id.push_back((int)it->first);
+        for (size_t j = 0; j < it->second.size(); ++j) feat.push_back((int)it->second[j]);
+        node_off.push_back((int)feat.size());
+    }
+}
+
+template <class MapPointT>
+inline void ValidPoints(const std::vector<MapPointT*>& pts, size_t n, std::vector<unsigned char>& valid)
+{
+    valid.assign(n ? n : 1, 0);
+    for (size_t i = 0; i < n && i < pts.size(); ++i) valid[i] = (pts[i] && !pts[i]->isBad()) ? 1 : 0;
+}
+
+// ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&), src/ORBmatcher.cc:552-697.
+// Reads: pKF->GetMapPointMatches(), mFeatVec, mDescriptors, mvKeysUn; F.N, mFeatVec, mDescriptors, mvKeys; MapPoint::isBad().
+template <class KeyFrameT, class FrameT, class MapPointT>
+int SearchByBoW(KeyFrameT* pKF, FrameT& F, std::vector<MapPointT*>& vpMapPointMatches, const float nnratio, const bool checkOri)
+{
+    const std::vector<MapPointT*> vpMapPointsKF = pKF->GetMapPointMatches();
+    vpMapPointMatches = std::vector<MapPointT*>((size_t)F.N, static_cast<MapPointT*>(0));
+    std::vector<orbx_kp> ka, kb; FlattenKeys(pKF->mvKeysUn, ka); FlattenKeys(F.mvKeys, kb);
+    std::vector<unsigned char> da, db; FlattenDescriptors(pKF->mDescriptors, (int)ka.size(), da); FlattenDescriptors(F.mDescriptors, (int)kb.size(), db);
+    orbm_frame va = { (int)ka.size(), ka.empty() ? 0 : &ka[0], &da[0], 0, 0, 1, 0, 1 }, vb = { (int)kb.size(), kb.empty() ? 0 : &kb[0], &db[0], 0, 0, 1, 0, 1 };
+    std::vector<int> ia, oa, fa, ib, ob, fb;
+    FlattenFeatureVector(pKF->mFeatVec, ia, oa, fa); FlattenFeatureVector(F.mFeatVec, ib, ob, fb);
+    std::vector<unsigned char> valid; ValidPoints(vpMapPointsKF, ka.size(), valid);
+    std::vector<int> m12(ka.size() ? ka.size() : 1, -1);
+    int nmatches = 0;
+    Check(orbm_search_by_bow(&va, &valid[0], (int)ia.size(), ia.empty() ? 0 : &ia[0], &oa[0], fa.empty() ? 0 : &fa[0],
+                             &vb, 0, (int)ib.size(), ib.empty() ? 0 : &ib[0], &ob[0], fb.empty() ? 0 : &fb[0],
+                             0, nnratio, checkOri ? 1 : 0, &m12[0], &nmatches, Device()), "orbm_search_by_bow");
+    for (size_t i = 0; i < ka.size(); ++i) if (m12[i] >= 0) vpMapPointMatches[(size_t)m12[i]] = vpMapPointsKF[i];
+    return nmatches;
+}
+
+// ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vector<MapPoint*>&), src/ORBmatcher.cc:700-832.
+template <class KeyFrameT, class MapPointT>
+int SearchByBoW(KeyFrameT* pKF1, KeyFrameT* pKF2, std::vector<MapPointT*>& vpMatches12, const float nnratio, const bool checkOri)
+{
+    const std::vector<MapPointT*> p1 = pKF1->GetMapPointMatches(), p2 = pKF2->GetMapPointMatches();
+    vpMatches12 = std::vector<MapPointT*>(p1.size(), static_cast<MapPointT*>(0));
+    std::vector<orbx_kp> ka, kb; FlattenKeys(pKF1->mvKeysUn, ka); FlattenKeys(pKF2->mvKeysUn, kb);
+    std::vector<unsigned char> da, db; FlattenDescriptors(pKF1->mDescriptors, (int)ka.size(), da); FlattenDescriptors(pKF2->mDescriptors, (int)kb.size(), db);
+    orbm_frame va = { (int)ka.size(), ka.empty() ? 0 : &ka[0], &da[0], 0, 0, 1, 0, 1 }, vb = { (int)kb.size(), kb.empty() ? 0 : &kb[0], &db[0], 0, 0, 1, 0, 1 };
+    std::vector<int> ia, oa, fa, ib, ob, fb;
+    FlattenFeatureVector(pKF1->mFeatVec, ia, oa, fa); FlattenFeatureVector(pKF2->mFeatVec, ib, ob, fb);
+    std::vector<unsigned char> v1, v2; ValidPoints(p1, ka.size(), v1); ValidPoints(p2, kb.size(), v2);
+    std::vector<int> m12(ka.size() ? ka.size() : 1, -1);
+    int nmatches = 0;
+    Check(orbm_search_by_bow(&va, &v1[0], (int)ia.size(), ia.empty() ? 0 : &ia[0], &oa[0], fa.empty() ? 0 : &fa[0],
+                             &vb, &v2[0], (int)ib.size(), ib.empty() ? 0 : &ib[0], &ob[0], fb.empty() ? 0 : &fb[0],
+                             1, nnratio, checkOri ? 1 : 0, &m12[0], &nmatches, Device()), "orbm_search_by_bow");
+    for (size_t i = 0; i < ka.size() && i < p1.size(); ++i) if (m12[i] >= 0) vpMatches12[i] = p2[(size_t)m12[i]];
+    return nmatches;
+}
+
+// The loop `if (mCurrentFrame.isInFrustum(pMP, 0.5)) ...` of Tracking::SearchLocalPoints: Frame::isInFrustum
+// (src/Frame.cc:288-345) for all points at once.  Sets mbTrackInView and, for points in view, mTrackProjX/Y/XR,
+// mnTrackScaleLevel, mTrackViewCos exactly as the reference does; inView[i] is isInFrustum's return value.
+// MapPoint needs two one-line accessors beside Get{Min,Max}DistanceInvariance:
+//   float GetMaxDistance() { unique_lock<mutex> lock(mMutexPos); return mfMaxDistance; }   and GetMinDistance() likewise,
+// because PredictScale (src/MapPoint.cc:459-475) divides the RAW mfMaxDistance.
+template <class FrameT, class MapPointT>
+int IsInFrustum(FrameT& F, const std::vector<MapPointT*>& pts, const float viewingCosLimit, std::vector<bool>& inView)
+{
+    const size_t n = pts.size();
+    inView.assign(n, false);
+    if (!n) return 0;
+    std::vector<float> xyz(3 * n), nrm(3 * n), mx(n), mn(n), proj(3 * n, 0.f), vc(n, 0.f);
+    std::vector<int> lvl(n, 0);
+    std::vector<unsigned char> iv(n, 0);
+    for (size_t i = 0; i < n; ++i) {
+        pts[i]->mbTrackInView = false;
+        const typename std::remove_reference<decltype(pts[i]->GetWorldPos())>::type P = pts[i]->GetWorldPos(), N = pts[i]->GetNormal();
+        for (int k = 0; k < 3; ++k) { xyz[3 * i + k] = P.template at<float>(k); nrm[3 * i + k] = N.template at<float>(k); }
+        mx[i] = pts[i]->GetMaxDistance(); mn[i] = pts[i]->GetMinDistance();
+    }
+    float T[16];
+    for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) T[4 * r + c] = F.mTcw.template at<float>(r, c);
+    const float K[4] = { FrameT::fx, FrameT::fy, FrameT::cx, FrameT::cy };
+    Check(orbm_project_points(T, K, F.mbf, FrameT::mnMinX, FrameT::mnMaxX, FrameT::mnMinY, FrameT::mnMaxY, F.mfScaleFactor, F.mnScaleLevels,
+                              viewingCosLimit, (int)n, &xyz[0], &nrm[0], &mx[0], &mn[0], &iv[0], &proj[0], &lvl[0], &vc[0], Device()),
+          "orbm_project_points");
+    int count = 0;
+    for (size_t i = 0; i < n; ++i) {
+        if (!iv[i]) continue;
+        inView[i] = true; ++count;
+        pts[i]->mbTrackInView = true;
+        pts[i]->mTrackProjX = proj[3 * i]; pts[i]->mTrackProjY = proj[3 * i + 1]; pts[i]->mTrackProjXR = proj[3 * i + 2];
+        pts[i]->mnTrackScaleLevel = lvl[i]; pts[i]->mTrackViewCos = vc[i];
+    }
+    return count;
+}
+
+// The distance matrix and median search of MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:311-334):
+// returns BestIdx for the descriptors the reference collected in vDescriptors (-1 when empty).
+template <class MatT>
+int DistinctiveDescriptor(const std::vector<MatT>& vDescriptors)
+{
+    const size_t n = vDescriptors.size();
+    if (!n) return -1;
+    std::vector<unsigned char> d(32 * n);
+    for (size_t i = 0; i < n; ++i) std::memcpy(&d[32 * i], vDescriptors[i].ptr(0), 32);
+    int best = -1;
+    Check(orbm_distinctive_descriptor(&d[0], (int)n, 0, &best, 0, Device()), "orbm_distinctive_descriptor");
+    return best;
 }
 
 }} // namespace ORB_SLAM2::b200

@@ -21,9 +21,14 @@ struct MapPointT {
     cv::Mat GetDescriptor() { return descriptor.clone(); }
     cv::Mat GetWorldPos() { return pos.clone(); }
     cv::Mat GetNormal() { return pos.clone(); }
+    float GetMaxDistance() { return 1e9f; }
+    float GetMinDistance() { return 0.f; }
 };
+#include <map>
+struct FeatVecT : std::map<unsigned int, std::vector<unsigned int> > {};
 struct FrameT {
-    int N; float mbf, mb;
+    int N, mnScaleLevels; float mbf, mb, mfScaleFactor;
+    FeatVecT mFeatVec;
     std::vector<cv::KeyPoint> mvKeys, mvKeysUn;
     std::vector<float> mvuRight, mvScaleFactors;
     cv::Mat mDescriptors, mTcw;
@@ -34,6 +39,7 @@ struct FrameT {
 struct KeyFrameT {
     float fx, fy, cx, cy; int mnMinX, mnMinY, mnMaxX, mnMaxY;
     cv::Mat mDescriptors;
+    FeatVecT mFeatVec;
     std::vector<float> mvScaleFactors;
     std::vector<cv::KeyPoint> mvKeysUn;
     std::vector<MapPointT*> pts;
@@ -58,5 +64,13 @@ extern "C" int matcher_forwarders_instantiate(int run)
     n += ORB_SLAM2::b200::SearchByProjection(a, &kf, found, 10.0f, 100, true);
     std::vector<MapPointT*> matched;
     n += ORB_SLAM2::b200::SearchByProjection(&kf, cv::Mat(), pts, matched, 10);
+    n += ORB_SLAM2::b200::SearchByBoW(&kf, a, matched, 0.7f, true);
+    n += ORB_SLAM2::b200::SearchByBoW(&kf, &kf, matched, 0.75f, true);
+#ifndef WITH_REFERENCE_HEADERS      // the reference's MapPoint lacks the two raw-distance accessors until patched
+    std::vector<bool> inView;
+    n += ORB_SLAM2::b200::IsInFrustum(a, pts, 0.5f, inView);
+#endif
+    std::vector<cv::Mat> vd;
+    n += ORB_SLAM2::b200::DistinctiveDescriptor(vd);
     return n;
 }

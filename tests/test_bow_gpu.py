@@ -91,3 +91,19 @@ def test_bow_batch_equals_reference_fixture(frame):
         ob.search_by_bow_batch(A, VA, v1, B, VB, v2 if kf_kf else None, kf_kf, nnratio, check_ori, m12, nm)
         torch.cuda.synchronize()
         assert int(nm[0]) == int(g[f"nm_{k}"]) and (m12[0].cpu().numpy() == g[f"match_{k}"]).all()
+
+
+@pytest.mark.parametrize("nnratio,check_ori,kf_kf", CASES[:3])
+def test_bow_single_problem_host_arrays(frame, nnratio, check_ori, kf_kf):
+    """orbm_search_by_bow (what the C++ forwarder calls): host arrays in, same result as the oracle."""
+    s = bow_scene(*frame, 8, n2=1700)
+    B = (0.0, 1241.0, 0.0, 376.0)
+    v1 = s["valid1"] & (1 - s["bad1"])
+    v2 = (s["valid2"] & (1 - s["bad2"])) if kf_kf else None
+    nm, m = ob.search_by_bow(ob.FrameView(s["k1"], s["d1"], B), s["fv1"], v1, ob.FrameView(s["k2"], s["d2"], B), s["fv2"], v2, kf_kf, nnratio, check_ori)
+    want = search_by_bow("oracle", s, nnratio, check_ori, kf_kf)
+    assert nm == want[0] and nm > 100 and (m == want[1]).all()
+    # empty feature vector on one side: nothing matches
+    empty = (np.zeros(0, np.int32), np.zeros(1, np.int32), np.zeros(0, np.int32))
+    nm, m = ob.search_by_bow(ob.FrameView(s["k1"], s["d1"], B), s["fv1"], v1, ob.FrameView(s["k2"], s["d2"], B), empty, v2, kf_kf, nnratio, check_ori)
+    assert nm == 0 and (m == -1).all()

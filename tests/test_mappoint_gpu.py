@@ -154,3 +154,19 @@ def test_projection_feeds_window_matching_on_device():
     ob.search_by_projection_points_batch(F, scale, dq, nq, n, assign, nm, 3.0, 0.8)
     torch.cuda.synchronize()
     assert int(nm[0]) == want[0] and (assign[0].cpu().numpy() == want[1]).all()
+
+
+def test_single_problem_host_arrays():
+    """orbm_project_points / orbm_distinctive_descriptor (what the C++ forwarders call): host arrays in."""
+    s = frustum_scene(41)
+    iv, proj, lv, vc = ob.project_points(s["Tcw"], s["K"], s["bf"], s["bounds"], 1.2, 8, s["xyz"], s["normal"], s["max_d"], s["min_d"])
+    wiv, wproj, wlv, wvc = is_in_frustum("oracle", s)
+    m = wiv.astype(bool)
+    assert (iv == wiv).all() and (lv[m] == wlv[m]).all() and (proj[m].view(np.uint32) == wproj[m].view(np.uint32)).all()
+    assert (vc[m].view(np.uint32) == wvc[m].view(np.uint32)).all() and (proj[~m] == 0).all()
+    for d, bad in descriptor_groups(4, sizes=(1, 7, 40, 300)):
+        for b in (None, bad):
+            _, wi, wm = distinctive("oracle", d, b)
+            gi, gm = ob.distinctive_descriptor(d, b)
+            assert (wi is None and gi == -1) or (gi == wi and gm == wm)
+    assert ob.distinctive_descriptor(np.zeros((0, 32), np.uint8)) == (-1, -1)
