@@ -107,7 +107,9 @@ __device__ __forceinline__ int mb_rot_bin(const float a1, const float a2)   // s
 // One query, one GROUP of MB_G lanes (a window holds a few candidates per grid column, far fewer than 32): the two
 // smallest (distance << 16 | position) keys among the candidates that are not taken, and whether a taken
 // candidate was skipped.  gmask = the lanes of the group; all four groups of a warp run this together.
-#define MB_G 8
+#ifndef MB_G
+#define MB_G 4
+#endif
 template <int MODE>
 __device__ __forceinline__ void query_top2(const MbParams& P, const WinQ& Q, const int q, const uint32_t (&qd)[8],
                                            const uint4* rec, const uint4* sdesc, const int* cell_start,
@@ -147,10 +149,15 @@ __device__ __forceinline__ void query_top2(const MbParams& P, const WinQ& Q, con
             }
         }
     }
-    k1 = __reduce_min_sync(gmask, a1);
+    // group reductions with xor shuffles (redux.sync with a different member mask per group is serialised per mask)
+    k1 = a1;
+#pragma unroll
+    for (int d = MB_G / 2; d > 0; d >>= 1) k1 = min(k1, __shfl_xor_sync(0xffffffffu, k1, d));
     if (a1 == k1) a1 = a2;                        // keys are unique (position) or "none"
-    k2 = __reduce_min_sync(gmask, a1);
-    skipped = __reduce_max_sync(gmask, (unsigned)(nb > 0)) != 0;
+    k2 = a1;
+#pragma unroll
+    for (int d = MB_G / 2; d > 0; d >>= 1) k2 = min(k2, __shfl_xor_sync(0xffffffffu, k2, d));
+    skipped = (__ballot_sync(0xffffffffu, nb > 0) & gmask) != 0;
     (void)MODE;
 }
 
@@ -164,7 +171,10 @@ __device__ long long g_clk[16];
 #define CLK(i)
 #endif
 
-template <int MODE>
+// LOC: where the sorted records / descriptors live -- 0: both in shared memory, 1: records in shared memory,
+// descriptors in the global workspace, 2: both global.  A template parameter so that the loads of the window walk
+// are LDS, not generic loads.
+template <int MODE, int LOC>
 __global__ void __launch_bounds__(MB_NT) k_match_fixpoint(const __grid_constant__ MbParams P)
 {
     extern __shared__ __align__(16) uint32_t smem[];
@@ -189,8 +199,10 @@ __global__ void __launch_bounds__(MB_NT) k_match_fixpoint(const __grid_constant_
     // sorted records and descriptors: shared memory when the problem fits (the window walk is a chain of dependent
     // loads, so their latency is what a query costs), else the global workspace
     uint4* const sm16 = (uint4*)(st_best + P.nq_max);
-    uint4* rec = P.rec_in_smem ? sm16 : P.rec + ko;
-    uint4* sdesc = P.desc_in_smem ? sm16 + (P.rec_in_smem ? P.sn_max : 0) : (uint4*)(P.sdesc + ko * 8);
+    uint4* rec; uint4* sdesc;
+    if (LOC == 0) { rec = sm16; sdesc = sm16 + P.sn_max; }
+    else if (LOC == 1) { rec = sm16; sdesc = (uint4*)(P.sdesc + ko * 8); }
+    else { rec = P.rec + ko; sdesc = (uint4*)(P.sdesc + ko * 8); }
 
     CLK(0);
     // ---- Frame::AssignFeaturesToGrid (src/Frame.cc:243-259): cell of every keypoint (round(), :414-415), sorted
@@ -423,6 +435,16 @@ size_t base_smem(int kp_stride, int nq_stride, int* sn_out, int* nq_out)
 }
 const size_t kSmemMax = 224 * 1024;
 
+template <int MODE, int LOC>
+cudaError_t launch_loc(const MbParams& P, int nprob, size_t smem, cudaStream_t st)
+{
+    cudaError_t e = cudaSuccess;
+    if (smem > 48 * 1024) e = cudaFuncSetAttribute(k_match_fixpoint<MODE, LOC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k_match_fixpoint<MODE, LOC><<<nprob, MB_NT, smem, st>>>(P);
+    return cudaGetLastError();
+}
+
 template <int MODE>
 int launch(MbParams& P, int nprob, cudaStream_t st)
 {
@@ -443,12 +465,8 @@ int launch(MbParams& P, int nprob, cudaStream_t st)
     if (cudaMallocAsync(&ws, ws_bytes, st) != cudaSuccess) { cudaGetLastError(); return ORBX_E_CUDA; }
     P.rec = (uint4*)ws;
     P.sdesc = (uint32_t*)((char*)ws + rec_bytes);
-    cudaError_t e = cudaSuccess;
-    if (smem > 48 * 1024) e = cudaFuncSetAttribute(k_match_fixpoint<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) {
-        k_match_fixpoint<MODE><<<nprob, MB_NT, smem, st>>>(P);
-        e = cudaGetLastError();
-    }
+    const cudaError_t e = P.desc_in_smem ? launch_loc<MODE, 0>(P, nprob, smem, st)
+                        : P.rec_in_smem ? launch_loc<MODE, 1>(P, nprob, smem, st) : launch_loc<MODE, 2>(P, nprob, smem, st);
     cudaFreeAsync(ws, st);
     if (e != cudaSuccess) { cudaGetLastError(); return ORBX_E_CUDA; }
     return ORBX_OK;

@@ -7,7 +7,7 @@
 // later ones (:603-604 / :747).  The order of the side-1 features is simply their POSITION in feat1, and the
 // candidates of one of them are one contiguous run of feat2, so the same fixpoint over "first claimant of each
 // candidate" as in orb_match_batch.cu applies: every claim blocks, blockers only ever move to earlier queries, and a
-// query is recomputed only when one of its two best candidates became blocked.  Groups of 8 lanes work on one
+// query is recomputed only when one of its two best candidates became blocked.  Groups of 4 lanes work on one
 // query each (a node holds a handful of features).
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -19,7 +19,9 @@
 #define TH_LOW 50        // src/ORBmatcher.cc:38
 #define HISTO_LENGTH 30  // :39
 #define BW_NT 512
-#define BW_G 8
+#ifndef BW_G
+#define BW_G 4
+#endif
 #define BW_MAX_KP 8192
 #define BW_NONE 0xffffffffu
 
@@ -44,6 +46,7 @@ __device__ __forceinline__ int bw_rot_bin(const float a1, const float a2)   // s
     return bin;
 }
 
+template <bool DSM>    // side-2 descriptors staged in shared memory (LDS in the candidate loop) or read from global memory
 __global__ void __launch_bounds__(BW_NT) k_bow_fixpoint(const __grid_constant__ BowParams P)
 {
     extern __shared__ __align__(16) uint32_t smem[];
@@ -67,7 +70,7 @@ __global__ void __launch_bounds__(BW_NT) k_bow_fixpoint(const __grid_constant__ 
     uint32_t* st_best = st_top + P.n1_max;                  // [n1_max] accepted position + 1 (0 = none); bin afterwards
     uint8_t* use2 = (uint8_t*)(st_best + P.n1_max);         // [n2_max] side-2 position may be matched
     uint4* sdesc = (uint4*)(use2 + P.n2_max);               // [n2_max][2] side-2 descriptors in position order (if they fit)
-    const bool dsm = P.desc_in_smem != 0;
+    const bool dsm = DSM;
 
     // ---- lockstep walk of the two maps (:576-: equal NodeIds; lower_bound otherwise) = intersection of the id lists
     for (int p = tid; p < t1; p += BW_NT) seg[p] = 0;
@@ -121,7 +124,6 @@ __global__ void __launch_bounds__(BW_NT) k_bow_fixpoint(const __grid_constant__ 
             }
             if (!__any_sync(0xffffffffu, go)) continue;
             const int sub = lane & (BW_G - 1), g0 = lane & ~(BW_G - 1);
-            const unsigned gmask = ((1u << BW_G) - 1u) << g0;
             for (int i = 0; i < BW_G; ++i) {
                 const int src = g0 + i, qq = base + src;
                 const int act = __shfl_sync(0xffffffffu, (int)go, src);
@@ -146,9 +148,14 @@ __global__ void __launch_bounds__(BW_NT) k_bow_fixpoint(const __grid_constant__ 
                         else if (key < a2) a2 = key;
                     }
                 }
-                const uint32_t k1 = __reduce_min_sync(gmask, a1);
+                // group reductions with xor shuffles (redux.sync with one member mask per group is serialised per mask)
+                uint32_t k1 = a1;
+#pragma unroll
+                for (int d = BW_G / 2; d > 0; d >>= 1) k1 = min(k1, __shfl_xor_sync(0xffffffffu, k1, d));
                 if (a1 == k1) a1 = a2;
-                const uint32_t k2 = __reduce_min_sync(gmask, a1);
+                uint32_t k2 = a1;
+#pragma unroll
+                for (int d = BW_G / 2; d > 0; d >>= 1) k2 = min(k2, __shfl_xor_sync(0xffffffffu, k2, d));
                 if (sub == 0 && act) {
                     int best = -1;
                     const int bestDist1 = k1 == BW_NONE ? 256 : (int)(k1 >> 16), bestDist2 = k2 == BW_NONE ? 256 : (int)(k2 >> 16);
@@ -265,10 +272,12 @@ extern "C" int orbm_search_by_bow_batch(const orbm_frames* A, const orbm_featvec
         P.desc_in_smem = smem + (size_t)P.n2_max * 32 <= smem_max;
         if (P.desc_in_smem) smem += (size_t)P.n2_max * 32;
         cudaError_t e = cudaSuccess;
-        if (smem > 48 * 1024) e = cudaFuncSetAttribute(k_bow_fixpoint, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) {
-            k_bow_fixpoint<<<A->nprob, BW_NT, smem, (cudaStream_t)cuda_stream>>>(P);
-            e = cudaGetLastError();
+        if (P.desc_in_smem) {
+            if (smem > 48 * 1024) e = cudaFuncSetAttribute(k_bow_fixpoint<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) { k_bow_fixpoint<true><<<A->nprob, BW_NT, smem, (cudaStream_t)cuda_stream>>>(P); e = cudaGetLastError(); }
+        } else {
+            if (smem > 48 * 1024) e = cudaFuncSetAttribute(k_bow_fixpoint<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) { k_bow_fixpoint<false><<<A->nprob, BW_NT, smem, (cudaStream_t)cuda_stream>>>(P); e = cudaGetLastError(); }
         }
         if (e != cudaSuccess) { cudaGetLastError(); rc = ORBX_E_CUDA; }
     }
