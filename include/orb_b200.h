@@ -135,6 +135,12 @@ int orbx_stage_ms(orbx_ctx* ctx, float* ms /*[ORBX_STAGE_COUNT]*/, int* launches
 int orbx_plan_describe(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST, int w, int h,
                        int* level_w, int* level_h, int* cells, int* quota, int* n_ini, int* cand_cap);
 
+/* Host-only: the largest n_out operator() can produce for one w x h image with these parameters (every level's
+ * DistributeOctTree returns at most max(N + 2, 4 * nIni) keypoints, src/ORBextractor.cc:617-766).  Negative
+ * orbx_status on bad parameters / unsupported shape.  Lets a caller size capacities -- and tell the batched
+ * matchers a tight bound (orbm_frames.max_n) -- without reading n_out back. */
+int orbx_max_keypoints(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST, int w, int h);
+
 /* ---- matcher -------------------------------------------------------------------- */
 
 /* ORBmatcher::DescriptorDistance (src/ORBmatcher.cc:46-63) over all pairs: for each of the nq
@@ -223,6 +229,9 @@ typedef struct {
     const int* n;            /* [nprob] keypoints per frame (<= min(kp_stride, 8192)) */
     int kp_stride;
     float min_x, max_x, min_y, max_y;   /* mnMinX..mnMaxY, shared by all frames */
+    int max_n;               /* 0, or a bound the caller guarantees for every n[p] (orbx_max_keypoints): the kernels
+                                size their shared memory by it instead of kp_stride; a frame that exceeds it gets
+                                nmatches = -1 */
 } orbm_frames;
 
 /* The map points of SearchByProjection(Frame&, const vector<MapPoint*>&, th): arrays [nprob][nq_stride]

@@ -33,7 +33,8 @@ class OrbmFrame(C.Structure):
 class OrbmFrames(C.Structure):
     """orbm_frames: a batch of device-resident frames in the layout orbx_extract_batch writes."""
     _fields_ = [("nprob", C.c_int), ("kps", C.c_void_p), ("desc", C.c_void_p), ("u_right", C.c_void_p), ("n", C.c_void_p),
-                ("kp_stride", C.c_int), ("min_x", C.c_float), ("max_x", C.c_float), ("min_y", C.c_float), ("max_y", C.c_float)]
+                ("kp_stride", C.c_int), ("min_x", C.c_float), ("max_x", C.c_float), ("min_y", C.c_float), ("max_y", C.c_float),
+                ("max_n", C.c_int)]
 
 
 class OrbmPoints(C.Structure):
@@ -108,6 +109,7 @@ def lib():
         L.orbx_profile.argtypes = [vp, i32]
         L.orbx_stage_ms.argtypes = [vp, vp, vp, i32]
         L.orbx_plan_describe.argtypes = [i32, f32, i32, i32, i32, i32, i32] + [vp] * 6
+        L.orbx_max_keypoints.argtypes = [i32, f32, i32, i32, i32, i32, i32]
         L.orbm_hamming_bf.argtypes = [vp, i32, vp, i32, i32, vp, vp, vp, i32]
         fp = C.POINTER(OrbmFrame)
         L.orbm_search_by_projection_points.argtypes = [fp, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, f32, f32, pi, i32]
@@ -468,11 +470,20 @@ def window_search_best(F, uvr, min_level, max_level, qdesc, th_accept, check_ori
     return nm.value, out
 
 
-def frames_batch(kps, desc, n, bounds, u_right=None):
+def frames_batch(kps, desc, n, bounds, u_right=None, max_n=0):
     """orbm_frames over CUDA tensors laid out as orbx_extract_batch leaves them: kps [P,cap] (28-byte records, any
-    dtype), desc [P,cap,32] uint8, n [P] int32, u_right [P,cap] float32 or None."""
+    dtype), desc [P,cap,32] uint8, n [P] int32, u_right [P,cap] float32 or None; max_n: a guaranteed bound on n
+    (max_keypoints(...)), 0 = cap."""
     nprob, cap = int(desc.shape[0]), int(desc.shape[1])
-    return OrbmFrames(nprob, _ptr(kps), _ptr(desc), _ptr(u_right), _ptr(n), cap, *(float(b) for b in bounds))
+    return OrbmFrames(nprob, _ptr(kps), _ptr(desc), _ptr(u_right), _ptr(n), cap, *(float(b) for b in bounds), int(max_n))
+
+
+def max_keypoints(nfeatures, scale_factor, nlevels, ini_th, min_th, w, h):
+    """orbx_max_keypoints: the largest keypoint count operator() can return for one w x h image (host only)."""
+    r = lib().orbx_max_keypoints(nfeatures, scale_factor, nlevels, ini_th, min_th, w, h)
+    if r < 0:
+        raise OrbError(-r, "unsupported shape" if -r == ORBX_E_SHAPE else "bad argument")
+    return r
 
 
 def search_by_projection_points_batch(frames, scale, q, nq, nq_stride, assign_out, nmatches, th, nnratio, init_assign=None,

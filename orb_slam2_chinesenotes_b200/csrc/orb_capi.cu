@@ -681,4 +681,17 @@ int orbx_plan_describe(int nfeatures, float scaleFactor, int nlevels, int iniThF
     return ORBX_OK;
 }
 
+// Upper bound on the keypoints operator() can return for one image of this shape: a level's DistributeOctTree list
+// never exceeds max(N + 2, 4 * nIni) nodes (src/ORBextractor.cc:617-766) and every node yields one keypoint.
+int orbx_max_keypoints(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST, int w, int h)
+{
+    OrbParams p;
+    if (orb_params_init(&p, nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST)) return -ORBX_E_ARG;
+    OrbPlan plan;
+    if (orb_plan_build(&p, w, h, &plan, nullptr)) return -ORBX_E_SHAPE;
+    int n = 0;
+    for (int l = 0; l < nlevels; ++l) n += plan.lv[l].quota + 2 > 4 * plan.lv[l].nIni ? plan.lv[l].quota + 2 : 4 * plan.lv[l].nIni;
+    return n;
+}
+
 } // extern "C"

@@ -484,6 +484,7 @@ bool one_frame(Scratch& S, const orbm_frame* F, OneFrame* O)
     O->F.n = O->d_n;
     O->F.kp_stride = F->n;
     O->F.min_x = F->min_x; O->F.max_x = F->max_x; O->F.min_y = F->min_y; O->F.max_y = F->max_y;
+    O->F.max_n = 0;
     return S.ok;
 }
 

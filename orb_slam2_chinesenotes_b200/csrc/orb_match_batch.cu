@@ -29,6 +29,7 @@
 #include <stdint.h>
 
 #include <climits>
+#include <cstdlib>
 
 #include "../../include/orb_b200.h"
 
@@ -46,7 +47,7 @@ enum { MODE_POINTS = 0, MODE_BEST = 1 };
 
 struct MbParams {
     // frames
-    const orbx_kp* kps; const uint32_t* desc; const float* u_right; const int* n; int kp_stride;
+    const orbx_kp* kps; const uint32_t* desc; const float* u_right; const int* n; int kp_stride, n_bound;
     float min_x, min_y, max_x, max_y, inv_w, inv_h;
     // queries
     const int* nq; int nq_stride;
@@ -106,7 +107,7 @@ __device__ __forceinline__ int mb_rot_bin(const float a1, const float a2)   // s
 
 // One query, one GROUP of MB_G lanes (a window holds a few candidates per grid column, far fewer than 32): the two
 // smallest (distance << 16 | position) keys among the candidates that are not taken, and whether a taken
-// candidate was skipped.  gmask = the lanes of the group; all four groups of a warp run this together.
+// candidate was skipped.  gmask = the lanes of the group; all groups of a warp run this together.
 #ifndef MB_G
 #define MB_G 4
 #endif
@@ -182,7 +183,7 @@ __global__ void __launch_bounds__(MB_NT) k_match_fixpoint(const __grid_constant_
     const int prob = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = MB_NT >> 5;
     const int n = P.n[prob], nq = P.nq[prob];
     int* const nm_out = P.nmatches + prob;
-    if (n < 0 || n > MB_MAX_KP || n > P.kp_stride || nq < 0 || nq > P.nq_stride) { if (tid == 0) *nm_out = -1; return; }
+    if (n < 0 || n > P.sn_max || n > P.kp_stride || nq < 0 || nq > P.nq_stride) { if (tid == 0) *nm_out = -1; return; }
     const size_t ko = (size_t)prob * P.kp_stride, qo = (size_t)prob * P.nq_stride;
     const orbx_kp* kps = P.kps + ko;
     const int* init = P.init ? P.init + ko : nullptr;
@@ -289,7 +290,7 @@ __global__ void __launch_bounds__(MB_NT) k_match_fixpoint(const __grid_constant_
                     myd0 = __ldg(qd); myd1 = __ldg(qd + 1);
                 } else if (st_best[q] & 0xffffu) { st_best[q] = 0; st_top[q] = MB_NONE; s_flag[par] = 1; }   // cannot happen: validity is fixed
             }
-            // four groups of 8 lanes, each working through the 8 queries its own lanes fetched
+            // groups of MB_G lanes, each working through the MB_G queries its own lanes fetched
             const bool go = need && myQ.valid;
             if (!__any_sync(0xffffffffu, go)) continue;
             const int sub = lane & (MB_G - 1), g0 = lane & ~(MB_G - 1);
@@ -452,12 +453,17 @@ int launch(MbParams& P, int nprob, cudaStream_t st)
     if (dev < 0 || device_of(P.assign_out) != dev || device_of(P.nmatches) != dev || device_of(P.qdesc) != dev) return ORBX_E_ARG;
     DevGuard g;
     if (cudaGetDevice(&g.prev) != cudaSuccess || cudaSetDevice(dev) != cudaSuccess) { cudaGetLastError(); return ORBX_E_CUDA; }
-    size_t smem = base_smem(P.kp_stride, P.nq_stride, &P.sn_max, &P.nq_max);
+    size_t smem = base_smem(P.n_bound, P.nq_stride, &P.sn_max, &P.nq_max);
     const size_t smem_max = kSmemMax;
     if (smem > smem_max) return ORBX_E_ARG;
     P.rec_in_smem = smem + (size_t)P.sn_max * 16 <= smem_max;
     if (P.rec_in_smem) smem += (size_t)P.sn_max * 16;
-    P.desc_in_smem = smem + (size_t)P.sn_max * 32 <= smem_max;
+    P.desc_in_smem = P.rec_in_smem && smem + (size_t)P.sn_max * 32 <= smem_max;
+    if (const char* e = getenv("ORB_MATCH_LOC")) {          // experiments only
+        const int loc = atoi(e);
+        if (loc >= 1) P.desc_in_smem = 0;
+        if (loc >= 2 && P.rec_in_smem) { P.rec_in_smem = 0; smem -= (size_t)P.sn_max * 16; }
+    }
     if (P.desc_in_smem) smem += (size_t)P.sn_max * 32;
     void* ws = nullptr;
     const size_t rec_bytes = P.rec_in_smem ? 0 : (size_t)nprob * P.kp_stride * sizeof(uint4);
@@ -477,6 +483,7 @@ bool fill_frames(MbParams& P, const orbm_frames* F)
     if (!F || F->nprob <= 0 || !F->kps || !F->desc || !F->n || F->kp_stride <= 0) return false;
     if (((uintptr_t)F->desc & 15) || ((uintptr_t)F->kps & 3)) return false;
     P.kps = F->kps; P.desc = (const uint32_t*)F->desc; P.u_right = F->u_right; P.n = F->n; P.kp_stride = F->kp_stride;
+    P.n_bound = (F->max_n > 0 && F->max_n < F->kp_stride) ? F->max_n : F->kp_stride;
     P.min_x = F->min_x; P.min_y = F->min_y; P.max_x = F->max_x; P.max_y = F->max_y;
     P.inv_w = (float)GRID_COLS / (F->max_x - F->min_x);     // src/Frame.cc:108
     P.inv_h = (float)GRID_ROWS / (F->max_y - F->min_y);     // :109

@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(BW_NT) k_bow_fixpoint(const __grid_constant__ 
     const int prob = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = BW_NT >> 5;
     const int n1 = P.A.n[prob], n2 = P.B.n[prob], nn1 = P.A.n_nodes[prob], nn2 = P.B.n_nodes[prob];
     int* const nm_out = P.nmatches + prob;
-    if (n1 < 0 || n1 > P.A.kp_stride || n1 > BW_MAX_KP || n2 < 0 || n2 > P.B.kp_stride || n2 > BW_MAX_KP ||
+    if (n1 < 0 || n1 > P.A.kp_stride || n1 > P.n1_max || n2 < 0 || n2 > P.B.kp_stride || n2 > P.n2_max ||
         nn1 < 0 || nn1 > P.A.node_stride || nn2 < 0 || nn2 > P.B.node_stride) { if (tid == 0) *nm_out = -1; return; }
     const size_t ka = (size_t)prob * P.A.kp_stride, kb = (size_t)prob * P.B.kp_stride;
     const int* id1 = P.A.node_id + (size_t)prob * P.A.node_stride; const int* off1 = P.A.node_off + (size_t)prob * (P.A.node_stride + 1);
@@ -262,8 +262,9 @@ extern "C" int orbm_search_by_bow_batch(const orbm_frames* A, const orbm_featvec
     if (cudaGetDevice(&prev) != cudaSuccess || cudaSetDevice(dev) != cudaSuccess) { cudaGetLastError(); return ORBX_E_CUDA; }
     P.nnratio = nnratio; P.check_ori = check_ori; P.strict = kf_kf ? 1 : 0;
     P.match12 = match12; P.match21 = match21; P.nmatches = nmatches; P.rounds = rounds;
-    P.n1_max = (A->kp_stride < BW_MAX_KP ? A->kp_stride : BW_MAX_KP) + 3 & ~3;
-    P.n2_max = (B->kp_stride < BW_MAX_KP ? B->kp_stride : BW_MAX_KP) + 15 & ~15;
+    const int b1 = (A->max_n > 0 && A->max_n < A->kp_stride) ? A->max_n : A->kp_stride, b2 = (B->max_n > 0 && B->max_n < B->kp_stride) ? B->max_n : B->kp_stride;
+    P.n1_max = (b1 < BW_MAX_KP ? b1 : BW_MAX_KP) + 3 & ~3;
+    P.n2_max = (b2 < BW_MAX_KP ? b2 : BW_MAX_KP) + 15 & ~15;
     size_t smem = (size_t)P.n2_max * 4 + (size_t)P.n1_max * 12 + (size_t)P.n2_max;
     const size_t smem_max = 224 * 1024;
     int rc = ORBX_OK;

@@ -75,3 +75,18 @@ def test_no_cpu_fallback(built_lib):
     assert e.value.code == ob.ORBX_E_CUDA
     with pytest.raises(ob.OrbError):
         ob.hamming_bf(np.zeros((4, 32), np.uint8), np.zeros((4, 32), np.uint8))
+
+
+def test_max_keypoints_bounds_the_reference_counts(built_lib):
+    """orbx_max_keypoints (host only) is an upper bound on what operator() returns: checked on the committed outputs of
+    the reference's own extractor."""
+    import os
+    import numpy as np
+    import orb_slam2_chinesenotes_b200 as ob
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    for name in ("tum", "kitti", "small"):
+        g = np.load(os.path.join(gdir, f"ref_extract_{name}.npz"))
+        bound = ob.max_keypoints(int(g["nfeatures"]), 1.2, 8, 20, 7, int(g["w"]), int(g["h"]))
+        assert len(g["kps"]) <= bound <= int(g["nfeatures"]) + 4 * 8 + 64, (name, len(g["kps"]), bound)
+    with pytest.raises(ob.OrbError):
+        ob.max_keypoints(1000, 1.2, 8, 20, 7, 20, 20)

@@ -163,6 +163,16 @@ def test_batch_rejects_oversized_problems(scene):
     bounds = (0.0, float(W), 0.0, float(H))
     pr = [dict(kps=scene["k2"][:100], desc=scene["d2"][:100])]
     F, keep = _frames(pr, bounds, 128, False)
+    # a bound the frames respect sizes the shared memory; one they exceed marks the problem
+    for max_n, ok in ((100, True), (64, False)):
+        Fb = ob.frames_batch(keep[0], keep[1], keep[2], bounds, None, max_n)
+        q0 = projected_queries(scene["k2"][:100], scene["d2"][:100], 10, 1)
+        dq0 = {k: _dev(q0[k][None]) for k in q0}
+        a0 = torch.zeros((1, 128), dtype=torch.int32, device="cuda")
+        n0 = torch.zeros(1, dtype=torch.int32, device="cuda")
+        ob.search_by_projection_points_batch(Fb, scene["scale"], dq0, _dev(np.int32([10])), 10, a0, n0, 3.0, 0.9)
+        torch.cuda.synchronize()
+        assert (int(n0[0]) >= 0) == ok
     keep[2].fill_(500)                                   # n > kp_stride
     q = projected_queries(scene["k2"][:100], scene["d2"][:100], 10, 1)
     dq = {k: _dev(q[k][None]) for k in q}
