@@ -507,6 +507,7 @@ def run_ours(args, rank, world, local_rank):
     dist = None
     if world > 1:
         import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # NCCL's banner must not share stdout with the JSON line
         dist.init_process_group("nccl", device_id=dev)
     w, h, nf, batch = WORKLOADS[args.workload]
     if args.batch:
