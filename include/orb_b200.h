@@ -259,6 +259,19 @@ typedef struct {
 int orbm_window_search_best_batch(const orbm_frames* F, const orbm_windows* Q, const int* init_obs, int* assign_out,
                                   int th_accept, int check_ori, int* nmatches, int* rounds, void* cuda_stream);
 
+/* ORBmatcher::SearchByProjection(Frame& cur, const Frame& last, th, bMono), src/ORBmatcher.cc:160-300, for nprob
+ * (current frame, last frame) pairs: the projection of the last frame's map points (:172-244) runs on the device too.
+ * Tcw_cur / Tcw_last [nprob][16] row-major poses; last-frame arrays [nprob][last_stride]: kps_last (octave, angle),
+ * last_mp (has a map point), last_outlier (mvbOutlier, may be NULL), last_xyz [.][3], last_mp_desc [.][32],
+ * last_mp_obs (Observations(), NULL = 1); n_last [nprob].  cur_init_obs / assign_out [nprob][cur->kp_stride] as in
+ * orbm_search_by_projection_frame.  K, scale: host.  Device pointers otherwise; only enqueues. */
+int orbm_search_by_projection_frame_batch(const orbm_frames* cur, const float* Tcw_cur, const float* Tcw_last, const float* K, float bf,
+                                          const float* scale, int nlevels, const int* n_last, int last_stride,
+                                          const orbx_kp* kps_last, const uint8_t* last_mp, const uint8_t* last_outlier,
+                                          const float* last_xyz, const uint8_t* last_mp_desc, const int* last_mp_obs,
+                                          const int* cur_init_obs, int* assign_out, float th, int bMono, int checkOri,
+                                          int* nmatches, void* cuda_stream);
+
 /* ---- map-point side of the matching path (device resident, only enqueue) ------------------
  * Frame::isInFrustum (src/Frame.cc:288-345, camera centre as Frame::UpdatePoseMatrices :280-285, level by
  * MapPoint::PredictScale src/MapPoint.cc:459-475) for every (frame, map point): the loop of

@@ -118,6 +118,7 @@ def lib():
         L.orbm_window_search_best.argtypes = [fp, i32] + [vp] * 11 + [i32, i32, pi, i32]
         L.orbm_search_by_projection_points_batch.argtypes = [C.POINTER(OrbmFrames), vp, i32, C.POINTER(OrbmPoints), vp, vp, f32, f32, vp, vp, vp]
         L.orbm_window_search_best_batch.argtypes = [C.POINTER(OrbmFrames), C.POINTER(OrbmWindows), vp, vp, i32, i32, vp, vp, vp]
+        L.orbm_search_by_projection_frame_batch.argtypes = [C.POINTER(OrbmFrames), vp, vp, vp, f32, vp, i32, vp, i32] + [vp] * 8 + [f32, i32, i32, vp, vp]
         L.orbm_project_points_batch.argtypes = [i32, vp, vp, f32, f32, f32, f32, f32, f32, i32, f32, vp, i32, i32] + [vp] * 9 + [vp]
         L.orbm_distinctive_descriptors.argtypes = [vp, vp, i32, vp, vp, vp, vp]
         L.orbm_search_by_bow_batch.argtypes = [C.POINTER(OrbmFrames), C.POINTER(OrbmFeatVec), vp, C.POINTER(OrbmFrames), C.POINTER(OrbmFeatVec), vp,
@@ -509,6 +510,19 @@ def window_search_best_batch(frames, q, nq, nq_stride, assign_out, nmatches, th_
                                              int(check_ori), _ptr(nmatches), _ptr(rounds), stream)
     if rc:
         raise OrbError(rc, "orbm_window_search_best_batch failed")
+
+
+def search_by_projection_frame_batch(cur, Tcw_cur, Tcw_last, K, bf, scale, n_last, last_stride, last, assign_out, nmatches, th, bMono,
+                                     check_ori, cur_init_obs=None, stream=None):
+    """orbm_search_by_projection_frame_batch (src/ORBmatcher.cc:160-300 for every (current, last) frame pair).  cur:
+    frames_batch(...); last: dict of CUDA tensors [P,last_stride(,..)] kps, has_mp, outlier (or None), xyz, mp_desc, mp_obs (or None)."""
+    K, scale = np.ascontiguousarray(K, np.float32), np.ascontiguousarray(scale, np.float32)
+    rc = lib().orbm_search_by_projection_frame_batch(C.byref(cur), _ptr(Tcw_cur), _ptr(Tcw_last), K.ctypes.data, float(bf), scale.ctypes.data,
+                                                     len(scale), _ptr(n_last), last_stride, _ptr(last["kps"]), _ptr(last["has_mp"]),
+                                                     _ptr(last.get("outlier")), _ptr(last["xyz"]), _ptr(last["mp_desc"]), _ptr(last.get("mp_obs")),
+                                                     _ptr(cur_init_obs), _ptr(assign_out), th, int(bMono), int(check_ori), _ptr(nmatches), stream)
+    if rc:
+        raise OrbError(rc, "orbm_search_by_projection_frame_batch failed")
 
 
 def project_points_batch(Tcw, K, bf, bounds, scale_factor, nlevels, nq, nq_stride, pts, out, cos_limit=0.5, points_shared=False,

@@ -138,6 +138,80 @@ __global__ void __launch_bounds__(256) k_project_points(const ProjParams P)
     }
 }
 
+// ------------------------------------------------------------------------------------------ motion-model projection
+// The per-point part of ORBmatcher::SearchByProjection(Frame& cur, const Frame& last, th, bMono), src/ORBmatcher.cc:172-244:
+// last-frame map points into the current image, search radius by the last keypoint's octave, level range by the
+// direction of motion.  Writes the orbm_windows arrays the best-candidate kernel reads.
+struct LastParams {
+    const float* Tcw_cur; const float* Tcw_last;      // [nprob][16]
+    float fx, fy, cx, cy, bf, mb, min_x, max_x, min_y, max_y, th;
+    int mono, nlevels;
+    float scale[32];
+    const int* n_last; int stride;
+    const orbx_kp* kps_last; const uint8_t* last_mp; const uint8_t* last_outlier; const float* last_xyz;
+    float* uvr; int* min_level; int* max_level; float* ur; float* er_max; uint8_t* valid; float* q_angle;
+};
+
+__global__ void __launch_bounds__(256) k_project_last_frame(const LastParams P)
+{
+    __shared__ float T[12], tlcz;
+    const int prob = blockIdx.y;
+    if (threadIdx.x < 12) T[threadIdx.x] = P.Tcw_cur[(size_t)prob * 16 + threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // twc = -Rcw.t() * tcw (:177), tlc = Rlw * twc + tlw (:181): cv::gemm order, products left to right
+        const float* L = P.Tcw_last + (size_t)prob * 16;
+        float twc[3];
+        for (int i = 0; i < 3; ++i) {
+            float s = __fmul_rn(-T[0 * 4 + i], T[3]);
+            s = __fadd_rn(s, __fmul_rn(-T[1 * 4 + i], T[7]));
+            s = __fadd_rn(s, __fmul_rn(-T[2 * 4 + i], T[11]));
+            twc[i] = s;
+        }
+        float s = __fmul_rn(L[8], twc[0]);
+        s = __fadd_rn(s, __fmul_rn(L[9], twc[1]));
+        s = __fadd_rn(s, __fmul_rn(L[10], twc[2]));
+        tlcz = __fadd_rn(s, L[11]);
+    }
+    __syncthreads();
+    const bool bForward = tlcz > P.mb && !P.mono, bBackward = -tlcz > P.mb && !P.mono;     // :184-185
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= min(P.n_last[prob], P.stride)) return;
+    const size_t o = (size_t)prob * P.stride + i;
+    const orbx_kp kp = P.kps_last[o];
+    P.q_angle[o] = kp.angle;
+    bool ok = P.last_mp[o] && !(P.last_outlier && P.last_outlier[o]);                       // :190-193
+    float u = 0, v = 0, invzc = 0;
+    if (ok) {
+        const float X = P.last_xyz[3 * o], Y = P.last_xyz[3 * o + 1], Z = P.last_xyz[3 * o + 2];
+        float pc[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            float s = __fmul_rn(T[4 * r], X);
+            s = __fadd_rn(s, __fmul_rn(T[4 * r + 1], Y));
+            s = __fadd_rn(s, __fmul_rn(T[4 * r + 2], Z));
+            pc[r] = __fadd_rn(s, T[4 * r + 3]);
+        }
+        invzc = (float)__ddiv_rn(1.0, (double)pc[2]);                                       // :199: 1.0 / float
+        ok = !(invzc < 0);
+        if (ok) {
+            u = __fadd_rn(__fmul_rn(__fmul_rn(P.fx, pc[0]), invzc), P.cx);
+            v = __fadd_rn(__fmul_rn(__fmul_rn(P.fy, pc[1]), invzc), P.cy);
+            ok = !(u < P.min_x || u > P.max_x) && !(v < P.min_y || v > P.max_y) && kp.octave >= 0 && kp.octave < P.nlevels;
+        }
+    }
+    P.valid[o] = ok ? 1 : 0;
+    if (!ok) { P.uvr[3 * o] = 0; P.uvr[3 * o + 1] = 0; P.uvr[3 * o + 2] = 0; P.min_level[o] = 0; P.max_level[o] = 0; P.ur[o] = 0; P.er_max[o] = 0; return; }
+    const int oct = kp.octave;
+    const float r = __fmul_rn(P.th, P.scale[oct]);                                           // :215
+    P.uvr[3 * o] = u; P.uvr[3 * o + 1] = v; P.uvr[3 * o + 2] = r;
+    if (bForward) { P.min_level[o] = oct; P.max_level[o] = -1; }                             // :219-224
+    else if (bBackward) { P.min_level[o] = 0; P.max_level[o] = oct; }
+    else { P.min_level[o] = oct - 1; P.max_level[o] = oct + 1; }
+    P.ur[o] = __fsub_rn(u, __fmul_rn(P.bf, invzc));                                          // :241-244
+    P.er_max[o] = r;
+}
+
 // ------------------------------------------------------------------------------------------ distinctive descriptor
 #define DD_NT 128
 #define DD_MAX 4096      // observations per map point the kernel handles
@@ -253,6 +327,50 @@ int orbm_project_points_batch(int nprob, const float* Tcw, const float* K, float
     k_project_points<<<dim3((nq_stride + 255) / 256, nprob), 256, 0, st>>>(P);
     if (cudaGetLastError() != cudaSuccess) return ORBX_E_CUDA;
     return ORBX_OK;
+}
+
+int orbm_search_by_projection_frame_batch(const orbm_frames* cur, const float* Tcw_cur, const float* Tcw_last, const float* K, float bf,
+                                          const float* scale, int nlevels, const int* n_last, int last_stride,
+                                          const orbx_kp* kps_last, const uint8_t* last_mp, const uint8_t* last_outlier,
+                                          const float* last_xyz, const uint8_t* last_mp_desc, const int* last_mp_obs,
+                                          const int* cur_init_obs, int* assign_out, float th, int bMono, int checkOri,
+                                          int* nmatches, void* cuda_stream)
+{
+    if (!cur || cur->nprob <= 0 || !Tcw_cur || !Tcw_last || !K || !scale || nlevels <= 0 || nlevels > 32 || !n_last || last_stride <= 0 ||
+        !kps_last || !last_mp || !last_xyz || !last_mp_desc || !assign_out || !nmatches)
+        return ORBX_E_ARG;
+    const int dev = dev_of(kps_last);
+    if (dev < 0 || dev_of(Tcw_cur) != dev || dev_of(Tcw_last) != dev || dev_of(last_xyz) != dev || dev_of(n_last) != dev) return ORBX_E_ARG;
+    DevScope g;
+    if (!g.enter(dev)) { cudaGetLastError(); return ORBX_E_CUDA; }
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const int nprob = cur->nprob;
+    const size_t nq = (size_t)nprob * last_stride;
+    // workspace: uvr (3 f), min/max level (2 i), ur, er_max, q_angle (3 f), valid (1 b)
+    const size_t bytes = nq * (3 + 2 + 3) * 4 + nq;
+    char* ws = nullptr;
+    if (cudaMallocAsync((void**)&ws, bytes + 64, st) != cudaSuccess) { cudaGetLastError(); return ORBX_E_CUDA; }
+    LastParams P;
+    P.Tcw_cur = Tcw_cur; P.Tcw_last = Tcw_last;
+    P.fx = K[0]; P.fy = K[1]; P.cx = K[2]; P.cy = K[3]; P.bf = bf; P.mb = bf / K[0];      // mb = mbf / fx, src/Frame.cc:121
+    P.min_x = cur->min_x; P.max_x = cur->max_x; P.min_y = cur->min_y; P.max_y = cur->max_y; P.th = th;
+    P.mono = bMono ? 1 : 0; P.nlevels = nlevels;
+    for (int i = 0; i < nlevels; ++i) P.scale[i] = scale[i];
+    P.n_last = n_last; P.stride = last_stride;
+    P.kps_last = kps_last; P.last_mp = last_mp; P.last_outlier = last_outlier; P.last_xyz = last_xyz;
+    P.uvr = (float*)ws; P.min_level = (int*)(P.uvr + 3 * nq); P.max_level = P.min_level + nq;
+    P.ur = (float*)(P.max_level + nq); P.er_max = P.ur + nq; P.q_angle = P.er_max + nq; P.valid = (uint8_t*)(P.q_angle + nq);
+    k_project_last_frame<<<dim3((last_stride + 255) / 256, nprob), 256, 0, st>>>(P);
+    int rc = cudaGetLastError() == cudaSuccess ? ORBX_OK : ORBX_E_CUDA;
+    if (rc == ORBX_OK) {
+        orbm_windows W;
+        W.nq = n_last; W.nq_stride = last_stride; W.uvr = P.uvr; W.min_level = P.min_level; W.max_level = P.max_level;
+        W.ur = cur->u_right ? P.ur : nullptr; W.er_max = cur->u_right ? P.er_max : nullptr;
+        W.valid = P.valid; W.qdesc = last_mp_desc; W.q_angle = P.q_angle; W.q_obs = last_mp_obs;
+        rc = orbm_window_search_best_batch(cur, &W, cur_init_obs, assign_out, 100 /* TH_HIGH, :256 */, checkOri, nmatches, nullptr, cuda_stream);
+    }
+    cudaFreeAsync(ws, st);
+    return rc;
 }
 
 int orbm_distinctive_descriptors(const uint8_t* desc, const int* offsets, int npoints, const uint8_t* bad,

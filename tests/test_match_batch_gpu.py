@@ -183,3 +183,46 @@ def test_batch_rejects_oversized_problems(scene):
     assert int(d_nm[0]) == -1
     with pytest.raises(ob.OrbError):
         ob.search_by_projection_points_batch(F, scene["scale"], {k: v.cpu() for k, v in dq.items()}, _dev(np.int32([10])), 10, d_assign, d_nm, 3.0, 0.9)
+
+
+@pytest.mark.parametrize("th,mono,check_ori", [(7.0, False, True), (15.0, True, True), (7.0, False, False)])
+def test_frame_to_frame_batch_equals_oracle(scene, th, mono, check_ori):
+    """SearchByProjection(cur, last) with the projection of the last frame's map points on the device too."""
+    import torch
+    from matcher_lib import two_view_scene
+    O = Matcher("oracle")
+    K = np.float32([718.856, 718.856, 607.1928, 185.2157])
+    bounds = (0.0, float(W), 0.0, float(H))
+    rng = np.random.default_rng(8)
+    probs = []
+    for seed, n_use in ((21, None), (22, 1500), (23, None)):
+        kps, desc = (scene["kps"], scene["desc"]) if n_use is None else (scene["kps"][:n_use], scene["desc"][:n_use])
+        cur, last, Tc, Tl = two_view_scene(kps, desc, W, H, seed, K)
+        if seed == 23:                                       # backward motion: the level range flips (:219-224)
+            Tc = Tc.copy(); Tc[2, 3] = 0.9
+        if mono:
+            cur = dict(cur); cur["u_right"] = None
+        init_obs = np.where(rng.random(len(cur["kps"])) < 0.05, rng.integers(0, 2, len(cur["kps"])), -1).astype(np.int32)
+        probs.append(dict(cur=cur, last=last, Tc=Tc, Tl=Tl, init=init_obs))
+    cap = 2100
+    fr = [dict(kps=p["cur"]["kps"], desc=p["cur"]["desc"], ur=p["cur"].get("u_right")) for p in probs]
+    F, keep = _frames(fr, bounds, cap, not mono)
+    d_last = dict(kps=_dev(np.stack([np.concatenate([p["last"]["kps"], np.zeros(cap - len(p["last"]["kps"]), KP_DTYPE)]) for p in probs])),
+                  has_mp=_dev(_pad([p["last"]["has_mp"] for p in probs], cap)), outlier=_dev(_pad([p["last"]["outlier"] for p in probs], cap)),
+                  xyz=_dev(_pad([p["last"]["xyz"] for p in probs], cap)), mp_desc=_dev(_pad([p["last"]["mp_desc"] for p in probs], cap)),
+                  mp_obs=_dev(_pad([p["last"]["mp_obs"] for p in probs], cap)))
+    d_Tc = _dev(np.stack([p["Tc"].reshape(16) for p in probs])); d_Tl = _dev(np.stack([p["Tl"].reshape(16) for p in probs]))
+    d_nl = _dev(np.int32([len(p["last"]["kps"]) for p in probs]))
+    for use_init in (False, True):
+        d_init = _dev(_pad([p["init"] for p in probs], cap, -1)) if use_init else None
+        d_assign = torch.full((len(probs), cap), -7, dtype=torch.int32, device="cuda")
+        d_nm = torch.zeros(len(probs), dtype=torch.int32, device="cuda")
+        ob.search_by_projection_frame_batch(F, d_Tc, d_Tl, K, 386.1448, scene["scale"], d_nl, cap, d_last, d_assign, d_nm, th, mono, check_ori, d_init)
+        torch.cuda.synchronize()
+        assign, nm = d_assign.cpu().numpy(), d_nm.cpu().numpy()
+        for i, p in enumerate(probs):
+            want = O.search_by_projection_frame(p["cur"], p["last"], p["Tc"], p["Tl"], K, 386.1448, scene["scale"], bounds, th, mono, 0.9, check_ori,
+                                                p["init"] if use_init else None)
+            n = len(p["cur"]["kps"])
+            assert nm[i] == want[0] and want[0] > 100, (i, nm[i], want[0])
+            assert (assign[i, :n] == want[1]).all()
