@@ -26,7 +26,9 @@
 // List size bound: a full pass runs only while size + 3*nToExpand <= N, so it ends with at most
 // N nodes (the very first pass: at most 4*nIni); a partial round stops at the first split that
 // reaches N, i.e. at most N+2.  plan.lv[l].kp_cap = max(N+3, 4*nIni).
+#ifndef OCT_NT
 #define OCT_NT 256
+#endif
 
 struct OctShared {
     short4* box[2];   // (ulx, urx, uly, bry)
