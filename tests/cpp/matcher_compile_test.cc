@@ -74,3 +74,136 @@ extern "C" int matcher_forwarders_instantiate(int run)
     n += ORB_SLAM2::b200::DistinctiveDescriptor(vd);
     return n;
 }
+
+#ifndef WITH_REFERENCE_HEADERS
+// ---- runtime entry points for pytest (GPU): objects of the stand-in types are filled from arrays and handed to the
+// forwarders exactly as the patched ORBmatcher.cc / Tracking.cc / MapPoint.cc would hand over the SLAM system's own.
+#include <cstring>
+namespace {
+struct Kp { float x, y, size, angle, response; int octave, class_id; };
+void fill_keys(std::vector<cv::KeyPoint>& v, const Kp* k, int n)
+{
+    v.resize(n);
+    for (int i = 0; i < n; ++i) v[i] = cv::KeyPoint(k[i].x, k[i].y, k[i].size, k[i].angle, k[i].response, k[i].octave, k[i].class_id);
+}
+void fill_desc(cv::Mat& m, const unsigned char* d, int n)
+{
+    m.create(n > 0 ? n : 1, 32, CV_8U);
+    if (n > 0) std::memcpy(m.data, d, (size_t)n * 32);
+}
+void fill_featvec(FeatVecT& fv, int nn, const int* id, const int* off, const int* feat)
+{
+    for (int k = 0; k < nn; ++k) for (int j = off[k]; j < off[k + 1]; ++j) fv[(unsigned)id[k]].push_back((unsigned)feat[j]);
+}
+} // namespace
+
+extern "C" {
+
+// ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&, th) through b200::SearchByProjection
+int fwd_search_by_projection_points(int n, const Kp* kps, const unsigned char* desc, const float* uright, const float* scale, int nlevels,
+                                    float minX, float maxX, float minY, float maxY, int nq, const float* proj, const int* level,
+                                    const float* view_cos, const unsigned char* in_view, const unsigned char* bad, const int* obs,
+                                    const unsigned char* qdesc, const int* init_assign, int* assign_out, float th, float nnratio)
+{
+    FrameT F;
+    F.N = n;
+    fill_keys(F.mvKeysUn, kps, n); F.mvKeys = F.mvKeysUn;
+    fill_desc(F.mDescriptors, desc, n);
+    F.mvuRight.assign(n, -1.f);
+    if (uright) F.mvuRight.assign(uright, uright + n);
+    F.mvScaleFactors.assign(scale, scale + nlevels);
+    FrameT::mnMinX = minX; FrameT::mnMaxX = maxX; FrameT::mnMinY = minY; FrameT::mnMaxY = maxY;
+    std::vector<MapPointT> store(nq > 0 ? nq : 1);
+    std::vector<MapPointT*> pts(nq);
+    for (int i = 0; i < nq; ++i) {
+        MapPointT& m = store[i];
+        m.mbTrackInView = in_view[i] != 0; m.bad = bad[i] != 0; m.mnTrackScaleLevel = level[i]; m.nObs = obs[i];
+        m.mTrackViewCos = view_cos[i]; m.mTrackProjX = proj[3 * i]; m.mTrackProjY = proj[3 * i + 1]; m.mTrackProjXR = proj[3 * i + 2];
+        fill_desc(m.descriptor, qdesc + 32 * (size_t)i, 1);
+        pts[i] = &m;
+    }
+    F.mvpMapPoints.assign(n, static_cast<MapPointT*>(0));
+    if (init_assign) for (int k = 0; k < n; ++k) if (init_assign[k] >= 0) F.mvpMapPoints[k] = &store[init_assign[k]];
+    const int nm = ORB_SLAM2::b200::SearchByProjection(F, pts, th, nnratio);
+    for (int k = 0; k < n; ++k) assign_out[k] = F.mvpMapPoints[k] ? (int)(F.mvpMapPoints[k] - &store[0]) : -1;
+    return nm;
+}
+
+// both ORBmatcher::SearchByBoW overloads through b200::SearchByBoW; match12 [n1] = feature of side 2 or -1
+int fwd_search_by_bow(int kf_kf, int n1, const Kp* k1, const unsigned char* d1, const unsigned char* has1, const unsigned char* bad1,
+                      int nn1, const int* id1, const int* off1, const int* f1,
+                      int n2, const Kp* k2, const unsigned char* d2, const unsigned char* has2, const unsigned char* bad2,
+                      int nn2, const int* id2, const int* off2, const int* f2, float nnratio, int check_ori, int* match12)
+{
+    KeyFrameT A, B;
+    std::vector<MapPointT> s1(n1 > 0 ? n1 : 1), s2(n2 > 0 ? n2 : 1);
+    fill_keys(A.mvKeysUn, k1, n1); fill_desc(A.mDescriptors, d1, n1); fill_featvec(A.mFeatVec, nn1, id1, off1, f1);
+    A.pts.assign(n1, static_cast<MapPointT*>(0));
+    for (int i = 0; i < n1; ++i) if (has1[i]) { s1[i].bad = bad1[i] != 0; A.pts[i] = &s1[i]; }
+    std::vector<MapPointT*> matches;
+    int nm;
+    for (int i = 0; i < n1; ++i) match12[i] = -1;
+    if (kf_kf) {
+        fill_keys(B.mvKeysUn, k2, n2); fill_desc(B.mDescriptors, d2, n2); fill_featvec(B.mFeatVec, nn2, id2, off2, f2);
+        B.pts.assign(n2, static_cast<MapPointT*>(0));
+        for (int i = 0; i < n2; ++i) if (has2[i]) { s2[i].bad = bad2[i] != 0; B.pts[i] = &s2[i]; }
+        nm = ORB_SLAM2::b200::SearchByBoW(&A, &B, matches, nnratio, check_ori != 0);
+        for (int i = 0; i < n1; ++i) if (matches[i]) match12[i] = (int)(matches[i] - &s2[0]);
+    } else {
+        FrameT F;
+        F.N = n2;
+        fill_keys(F.mvKeys, k2, n2); F.mvKeysUn = F.mvKeys; fill_desc(F.mDescriptors, d2, n2); fill_featvec(F.mFeatVec, nn2, id2, off2, f2);
+        nm = ORB_SLAM2::b200::SearchByBoW(&A, F, matches, nnratio, check_ori != 0);
+        for (int i = 0; i < n2; ++i) if (matches[i]) match12[(int)(matches[i] - &s1[0])] = i;   // vpMapPointMatches is per FRAME feature
+    }
+    return nm;
+}
+
+// the isInFrustum loop of Tracking::SearchLocalPoints through b200::IsInFrustum
+int fwd_is_in_frustum(const float* Tcw, const float* K, float bf, float minX, float maxX, float minY, float maxY, float scale_factor,
+                      int nlevels, float cos_limit, int n, const float* xyz, const float* normal, const float* max_d, const float* min_d,
+                      unsigned char* in_view, float* proj, int* level, float* view_cos)
+{
+    struct MP : MapPointT {
+        cv::Mat nrm; float mx, mn;
+        cv::Mat GetNormal() { return nrm.clone(); }
+        float GetMaxDistance() { return mx; }
+        float GetMinDistance() { return mn; }
+    };
+    FrameT F;
+    F.mTcw = cv::Mat(4, 4, CV_32F);
+    for (int i = 0; i < 16; ++i) F.mTcw.at<float>(i / 4, i % 4) = Tcw[i];
+    FrameT::fx = K[0]; FrameT::fy = K[1]; FrameT::cx = K[2]; FrameT::cy = K[3];
+    FrameT::mnMinX = minX; FrameT::mnMaxX = maxX; FrameT::mnMinY = minY; FrameT::mnMaxY = maxY;
+    F.mbf = bf; F.mfScaleFactor = scale_factor; F.mnScaleLevels = nlevels;
+    std::vector<MP> store(n > 0 ? n : 1);
+    std::vector<MP*> pts(n);
+    for (int i = 0; i < n; ++i) {
+        MP& m = store[i];
+        m.pos = cv::Mat(3, 1, CV_32F); m.nrm = cv::Mat(3, 1, CV_32F);
+        for (int k = 0; k < 3; ++k) { m.pos.at<float>(k) = xyz[3 * i + k]; m.nrm.at<float>(k) = normal[3 * i + k]; }
+        m.mx = max_d[i]; m.mn = min_d[i];
+        m.mbTrackInView = true; m.mTrackProjX = m.mTrackProjY = m.mTrackProjXR = m.mTrackViewCos = 0.f; m.mnTrackScaleLevel = 0;
+        pts[i] = &m;
+    }
+    std::vector<bool> iv;
+    const int cnt = ORB_SLAM2::b200::IsInFrustum(F, pts, cos_limit, iv);
+    for (int i = 0; i < n; ++i) {
+        in_view[i] = (iv[i] && store[i].mbTrackInView) ? 1 : 0;
+        if ((iv[i] ? 1 : 0) != (store[i].mbTrackInView ? 1 : 0)) return -1;
+        proj[3 * i] = store[i].mTrackProjX; proj[3 * i + 1] = store[i].mTrackProjY; proj[3 * i + 2] = store[i].mTrackProjXR;
+        level[i] = store[i].mnTrackScaleLevel; view_cos[i] = store[i].mTrackViewCos;
+    }
+    return cnt;
+}
+
+// the median search of MapPoint::ComputeDistinctiveDescriptors through b200::DistinctiveDescriptor
+int fwd_distinctive(const unsigned char* desc, int n)
+{
+    std::vector<cv::Mat> v(n);
+    for (int i = 0; i < n; ++i) fill_desc(v[i], desc + 32 * (size_t)i, 1);
+    return ORB_SLAM2::b200::DistinctiveDescriptor(v);
+}
+
+} // extern "C"
+#endif

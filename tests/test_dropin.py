@@ -79,3 +79,58 @@ def test_dropin_class_matches_oracle(dropin):
     assert dropin.dropin_call(ex, None, 0, 0, 0, kps.ctypes.data, desc.ctypes.data, 8) == -1   # empty image: outputs untouched
     dropin.dropin_destroy(ex)
     O.close()
+
+
+@pytest.mark.gpu
+def test_matcher_forwarders_run_like_the_patched_reference(dropin):
+    """host/ORBmatcher_b200.hpp at run time: Frame / KeyFrame / MapPoint objects (stand-in types with the reference's
+    member names) are filled from arrays, handed to the forwarders the way the patched ORBmatcher.cc, Tracking.cc and
+    MapPoint.cc would, and what the forwarders write back into the objects is compared with the oracle."""
+    from bow_lib import bow_scene, search_by_bow
+    from mappoint_lib import descriptor_groups, distinctive, frustum_scene, is_in_frustum
+    from matcher_lib import Matcher, extract_frame, perturbed_frame, projected_queries
+    M = C.CDLL(os.path.join(CPP, "_build", "libmatcher_fwd.so"))
+    vp, ci, cf = C.c_void_p, C.c_int, C.c_float
+    p = lambda a: None if a is None else a.ctypes.data
+    W, H = 1241, 376
+    bounds = (0.0, float(W), 0.0, float(H))
+    kps, desc, scale = extract_frame(W, H, 2000, 2)
+    k2, d2, _ = perturbed_frame(kps, desc, W, H, 11)
+    # SearchByProjection(Frame, MapPoints)
+    q = projected_queries(k2, d2, 1500, 5)
+    rng = np.random.default_rng(6)
+    n = len(k2)
+    ur = np.where(rng.random(n) < 0.5, k2["x"] - 20 * rng.random(n), -1).astype(np.float32)
+    init = np.where(rng.random(n) < 0.05, rng.integers(0, 1500, n), -1).astype(np.int32)
+    M.fwd_search_by_projection_points.argtypes = [ci, vp, vp, vp, vp, ci] + [cf] * 4 + [ci] + [vp] * 9 + [cf, cf]
+    for ia in (None, init):
+        out = np.zeros(n, np.int32)
+        nm = M.fwd_search_by_projection_points(n, p(k2), p(d2), p(ur), p(scale), len(scale), *bounds, 1500, p(q["proj"]), p(q["level"]),
+                                               p(q["view_cos"]), p(q["in_view"]), p(q["bad"]), p(q["obs"]), p(q["desc"]), p(ia), p(out), 3.0, 0.8)
+        want = Matcher("oracle").search_by_projection_points(k2, d2, ur, scale, bounds, q, 3.0, 0.8, ia)
+        assert nm == want[0] and nm > 300 and (out == want[1]).all()
+    # SearchByBoW x2
+    s = bow_scene(kps, desc, 8, n2=1700)
+    (id1, off1, f1), (id2, off2, f2) = s["fv1"], s["fv2"]
+    M.fwd_search_by_bow.argtypes = [ci] + [ci, vp, vp, vp, vp, ci, vp, vp, vp] * 2 + [cf, ci, vp]
+    for kf_kf in (0, 1):
+        m12 = np.zeros(len(s["k1"]), np.int32)
+        nm = M.fwd_search_by_bow(kf_kf, len(s["k1"]), p(s["k1"]), p(s["d1"]), p(s["valid1"]), p(s["bad1"]), len(id1), p(id1), p(off1), p(f1),
+                                 len(s["k2"]), p(s["k2"]), p(s["d2"]), p(s["valid2"]), p(s["bad2"]), len(id2), p(id2), p(off2), p(f2), 0.75, 1, p(m12))
+        want = search_by_bow("oracle", s, 0.75, True, bool(kf_kf))
+        assert nm == want[0] and nm > 100 and (m12 == want[1]).all()
+    # isInFrustum loop
+    fs = frustum_scene(3)
+    nf = len(fs["xyz"])
+    iv, proj, lv, vc = np.zeros(nf, np.uint8), np.zeros((nf, 3), np.float32), np.zeros(nf, np.int32), np.zeros(nf, np.float32)
+    M.fwd_is_in_frustum.argtypes = [vp, vp, cf] + [cf] * 4 + [cf, ci, cf, ci] + [vp] * 8
+    cnt = M.fwd_is_in_frustum(p(fs["Tcw"]), p(fs["K"]), float(fs["bf"]), *fs["bounds"], 1.2, 8, 0.5, nf, p(fs["xyz"]), p(fs["normal"]),
+                              p(fs["max_d"]), p(fs["min_d"]), p(iv), p(proj), p(lv), p(vc))
+    wiv, wproj, wlv, wvc = is_in_frustum("oracle", fs)
+    m = wiv.astype(bool)
+    assert cnt == wiv.sum() and (iv == wiv).all() and (lv[m] == wlv[m]).all()
+    assert (proj[m].view(np.uint32) == wproj[m].view(np.uint32)).all() and (vc[m].view(np.uint32) == wvc[m].view(np.uint32)).all()
+    # ComputeDistinctiveDescriptors' median search
+    M.fwd_distinctive.argtypes = [vp, ci]
+    for d, _ in descriptor_groups(2, sizes=(1, 5, 33, 120)):
+        assert M.fwd_distinctive(p(d), len(d)) == distinctive("oracle", d)[1]
