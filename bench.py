@@ -645,6 +645,9 @@ def run_ours(args, rank, world, local_rank):
     else:
         roof["achieved"] = None
         roof["frac"] = None
+    # what actually bounds the dominant kernel, from the committed ncu capture of this same command (not measured live)
+    roof["limiter"] = {"fast": "instruction issue: 2.75 of 4 warp instructions per clock and SM, ALU pipe 62 %, 177 instructions per pixel pair; "
+                               "DRAM traffic = algorithmic bytes (profiles/r01d_ncu_full_all_kernels.txt, r01d_ncu_full_extract_stalls.txt)"}.get(dom)
     roof["dense_stages"] = {s: {"GB/s": bytes_per_frame[s] * batch * args.steps / (stage_ms[s] * 1e-3) / 1e9,
                                 "frac": bytes_per_frame[s] * batch * args.steps / (stage_ms[s] * 1e-3) / 1e9 / peak}
                             for s in bytes_per_frame if stage_ms[s] > 0}
