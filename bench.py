@@ -38,6 +38,29 @@ STEREO = {"kitti_1241x376_nf2000"}
 CAM = dict(fx=718.856, fy=718.856, cx=607.1928, cy=185.2157, bf=386.1448, th_depth=35.0 * 386.1448 / 718.856)
 
 
+_STDOUT_FD = None
+
+
+def guard_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version banner does, whatever
+    NCCL_DEBUG_FILE says), so file descriptor 1 is pointed at stderr for the whole run and the JSON line is written to
+    the saved descriptor at the end."""
+    global _STDOUT_FD
+    if _STDOUT_FD is None:
+        sys.stdout.flush()
+        _STDOUT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    sys.stdout.flush()
+    if _STDOUT_FD is None:
+        os.write(1, line)
+    else:
+        os.write(_STDOUT_FD, line)
+
+
 def level_pixels(w, h):
     """Sum of level pixels P, last level p7."""
     import orb_slam2_chinesenotes_b200 as ob
@@ -225,7 +248,7 @@ def run_reference(args, rank, world):
     dt = time.perf_counter() - t0
     value = nsample * args.steps / dt
     sample = f"{nsample} frames per step ({min(nsample, 16)} distinct), {what}"
-    print(json.dumps({
+    emit(({
         "impl": "reference", "metric": "orb_extract_frames_per_s", "value": value, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
@@ -671,7 +694,7 @@ def run_ours(args, rank, world, local_rank):
     if world == 1 and stereo:
         window = bench_window_match(dev, d_kps, d_desc, d_n, cap, w, h, ex.GetScaleFactors(), cpu=not args.no_cpu)
         mappoint = bench_mappoint_side(dev, d_kps, d_desc, d_n, cap, w, h, SCALE, cpu=not args.no_cpu)
-    print(json.dumps({
+    emit(({
         "metric": "orb_extract_frames_per_s", "value": value, "unit": "frames/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
@@ -703,6 +726,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    guard_stdout()
     if args.impl == "reference":
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         run_reference(args, rank, world)
