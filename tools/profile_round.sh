@@ -1,5 +1,6 @@
 #!/bin/bash
-# Round-1 (session d) evidence: tests, bench lines, ncu launch list, ncu full-set capture of one chunk of every kernel.
+# Evidence of a round (run on the GPU box through gpurun; outputs under gpurun_out/, summaries are then written to
+# profiles/ with tools/launch_summary.py, ncu_summary.py, ncu_brief.py, ncu_traffic.py): tests, bench lines, ncu launch list, ncu full-set capture of one chunk of every kernel.
 set -x
 cd "$GRAFT_REPO_ROOT"
 python -m pytest tests -m gpu -x -q 2>&1 | tail -3 > gpurun_out/r01d_pytest_gpu.txt
@@ -10,5 +11,5 @@ python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r01d_smoke.txt 2
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:^k_ -s 84 -c 56 --csv --log-file gpurun_out/r01d_ncu_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/r01d_ncu_launches.log 2>&1
 # full set: one chunk (512 frames) of every extractor kernel = launches 0..13 of the first warm-up step
 ncu --set full --clock-control none --import-source on -k regex:^k_ -c 14 -o gpurun_out/r01d_prof_extract -f python bench.py --steps 1 --warmup 3 --no-cpu > gpurun_out/r01d_ncu_full.log 2>&1
-ORB_BENCH_PROFILE=1 ncu --set full --clock-control none --import-source on -k regex:"k_match_fixpoint|k_bow_fixpoint|k_distinctive|k_project_points|k_hamming_bf" -c 10 -o gpurun_out/r01d_prof_match -f python tools/scratch/match_once.py > gpurun_out/r01d_ncu_full_match.log 2>&1
+ORB_BENCH_PROFILE=1 ncu --set full --clock-control none --import-source on -k regex:"k_match_fixpoint|k_bow_fixpoint|k_distinctive|k_project_points|k_hamming_bf" -c 10 -o gpurun_out/r01d_prof_match -f python tools/match_once.py > gpurun_out/r01d_ncu_full_match.log 2>&1
 ls -la gpurun_out
