@@ -80,7 +80,10 @@ static inline __host__ __device__ int orb_fast_wpc(int ncs, int wc) { return (((
 // image words fetched per strip row (from the aligned address at or below the first pixel)
 static inline __host__ __device__ int orb_fast_rw(int ncs, int wc) { return ((ncs * wc + 15) >> 2) + 1; }
 // word offset of the second copy inside a tile row: the first value >= wpc that is 1 (mod 32) (bank spreading)
-static inline __host__ __device__ int orb_fast_ob(int wpc) { return ((wpc + 30) & ~31) + 1; }
+#ifndef ORB_FAST_OBX
+#define ORB_FAST_OBX 1      // copy B starts this many words past a multiple of 32 (odd: rows stay 8-byte aligned)
+#endif
+static inline __host__ __device__ int orb_fast_ob(int wpc) { return ((wpc + 30) & ~31) + ORB_FAST_OBX; }
 
 // packed candidate / level keypoint: x | y<<12 | score<<24, x,y in the border frame
 static inline __host__ __device__ uint32_t orb_pack(int x, int y, int s) { return (uint32_t)x | ((uint32_t)y << 12) | ((uint32_t)s << 24); }
