@@ -29,7 +29,6 @@
 #include <stdint.h>
 
 #include <climits>
-#include <cstdlib>
 
 #include "../../include/orb_b200.h"
 
@@ -459,11 +458,8 @@ int launch(MbParams& P, int nprob, cudaStream_t st)
     P.rec_in_smem = smem + (size_t)P.sn_max * 16 <= smem_max;
     if (P.rec_in_smem) smem += (size_t)P.sn_max * 16;
     P.desc_in_smem = P.rec_in_smem && smem + (size_t)P.sn_max * 32 <= smem_max;
-    if (const char* e = getenv("ORB_MATCH_LOC")) {          // experiments only
-        const int loc = atoi(e);
-        if (loc >= 1) P.desc_in_smem = 0;
-        if (loc >= 2 && P.rec_in_smem) { P.rec_in_smem = 0; smem -= (size_t)P.sn_max * 16; }
-    }
+    // (measured at 2000 x 2000: everything in shared memory 0.25 ms per 296 problems, descriptors in global memory
+    // 0.30 ms, records too 0.34 ms -- although the smaller footprints would let two blocks share an SM)
     if (P.desc_in_smem) smem += (size_t)P.sn_max * 32;
     void* ws = nullptr;
     const size_t rec_bytes = P.rec_in_smem ? 0 : (size_t)nprob * P.kp_stride * sizeof(uint4);
