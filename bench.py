@@ -284,16 +284,16 @@ def bench_hamming(dev, device_index, nq=2000, nt=2000, nprob=256, reps=5):
     dt = (time.perf_counter() - t0) / reps
     props = torch.cuda.get_device_properties(dev)
     sms = props.multi_processor_count
-    # The kernel compresses the 8 XOR words with a carry-save tree before POPC (4 POPC per pair), so the quarter-rate
-    # POPC pipe no longer bounds it; the ALU pipe does: 8 XOR + 14 LOP3 + ~4 for the best / second-best update per pair
-    # at the 1.95 warp instructions per clock and SM measured for LOP3 (profiles/r01_ubench_pipes.txt).
-    peak = sms * 32 * 1.95 * 1.965e9 / 26 / 1e9
+    # The kernel trades POPC work for LOP3 work with three carry-save adders (csrc/orb_match.cu k_hamming_bf): 5 POPC +
+    # 8 XOR + 6 LOP3 per pair instead of 8 POPC + 8 XOR, which balances the quarter-rate POPC pipe against the ALU pipe.
+    peak = sms * 16 * 1.965e9 / 5 / 1e9
     gp = nprob * nq * nt / dt / 1e9
     return {"value": gp, "unit": "Gpairs/s", "nq": nq, "nt": nt, "problems_per_launch": nprob, "ms_per_launch": dt * 1e3,
-            "bound": "integer pipe (ALU issue)", "peak": peak, "frac": gp / peak,
-            "peak_note": "SMs x 32 lanes x 1.95 LOP3-class instructions/clk x 1965 MHz / 26 ALU instructions per pair",
+            "bound": "integer pipes (POPC and ALU balanced)", "peak": peak, "frac": gp / peak,
+            "peak_note": "SMs x 16 POPC/clk x 1965 MHz / 5 POPC per pair; the ALU pipe (21 instructions per pair at 1.95 per "
+                         "clock and SM, profiles/r01_ubench_pipes.txt) allows 864",
             "plain_popc_peak": sms * 16 * 1.965e9 / 8 / 1e9,
-            "plain_popc_peak_note": "what 8 POPC per pair would allow (SMs x 16 POPC/clk x 1965 MHz / 8); 537 Gpairs/s measured in that form"}
+            "plain_popc_peak_note": "what 8 POPC per pair allow (SMs x 16 POPC/clk x 1965 MHz / 8); 537 Gpairs/s were measured in that form"}
 
 
 def warm_up(fn, seconds=0.3):

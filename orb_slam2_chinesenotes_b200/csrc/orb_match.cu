@@ -39,7 +39,7 @@
 
 // ------------------------------------------------------------------------------ brute force
 #ifndef ORB_BF_CSA
-#define ORB_BF_CSA 1  // brute force: carry-save compression before POPC (4 POPC per pair instead of 8)
+#define ORB_BF_CSA 2  // brute force: carry-save compression before POPC (0 = plain 8 POPC per pair; 1, 2, 3 see k_hamming_bf)
 #endif
 #define BF_NT 128     // threads per block = queries per block
 #define BF_TILE 128   // train descriptors per shared-memory tile
@@ -66,19 +66,29 @@ __global__ void __launch_bounds__(BF_NT) k_hamming_bf(const uint4* __restrict__ 
         for (int j = 0; j < m; ++j) {
             const uint4 b0 = s_t[2 * j], b1 = s_t[2 * j + 1];
 #if ORB_BF_CSA
-            // POPC issues at a quarter of the LOP3 rate and bounds the plain form (8 per pair).  A carry-save adder
-            // tree (Harley-Seal) first compresses the 8 XOR words into 4 words of weight 1, 2, 4, 8 with 14 LOP3, so
-            // a pair costs 4 POPC: popcount = popc(ones) + 2 popc(twos) + 4 popc(fours) + 8 popc(eights).
+            // POPC issues at a quarter of the LOP3 rate and bounds the plain form (8 per pair).  Carry-save adders
+            // (sum = x^y^z, carry = majority, one LOP3 each) compress three words of equal weight into two, so POPC
+            // work can be traded for LOP3 work until the two pipes are balanced:
+            //   ORB_BF_CSA = 1: two CSAs           -> 6 POPC + 4 LOP3
+            //   ORB_BF_CSA = 2: three CSAs         -> 5 POPC + 6 LOP3   (balanced on sm_100: POPC 0.5, LOP3 ~2 per clock and SM)
+            //   ORB_BF_CSA = 3: full Harley-Seal   -> 4 POPC + 14 LOP3
             const uint32_t x0 = a0.x ^ b0.x, x1 = a0.y ^ b0.y, x2 = a0.z ^ b0.z, x3 = a0.w ^ b0.w,
                            x4 = a1.x ^ b1.x, x5 = a1.y ^ b1.y, x6 = a1.z ^ b1.z, x7 = a1.w ^ b1.w;
             const uint32_t s1 = x0 ^ x1 ^ x2, c1 = (x0 & x1) | (x2 & (x0 | x1));
             const uint32_t s2 = x3 ^ x4 ^ x5, c2 = (x3 & x4) | (x5 & (x3 | x4));
+#if ORB_BF_CSA == 1
+            const int d = (__popc(s1) + __popc(s2)) + (__popc(x6) + __popc(x7)) + 2 * (__popc(c1) + __popc(c2));
+#elif ORB_BF_CSA == 2
+            const uint32_t s3 = s1 ^ s2 ^ x6, c3 = (s1 & s2) | (x6 & (s1 | s2));
+            const int d = (__popc(s3) + __popc(x7)) + 2 * (__popc(c1) + __popc(c2) + __popc(c3));
+#else
             const uint32_t s3 = s1 ^ s2 ^ x6, c3 = (s1 & s2) | (x6 & (s1 | s2));
             const uint32_t ones = s3 ^ x7, c4 = s3 & x7;
             const uint32_t t1 = c1 ^ c2 ^ c3, e1 = (c1 & c2) | (c3 & (c1 | c2));
             const uint32_t twos = t1 ^ c4, e2 = t1 & c4;
             const uint32_t fours = e1 ^ e2, eights = e1 & e2;
             const int d = __popc(ones) + 2 * __popc(twos) + 4 * __popc(fours) + 8 * __popc(eights);
+#endif
 #else
             const int d = __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
                           __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
