@@ -44,6 +44,8 @@
 #define BF_NT 128     // threads per block = queries per block
 #define BF_TILE 128   // train descriptors per shared-memory tile
 
+#define BF_KEY_SHIFT 22   // packed (distance << 22 | train index) keys: train sets below 2^22 descriptors
+template <bool PACKED>
 __global__ void __launch_bounds__(BF_NT) k_hamming_bf(const uint4* __restrict__ q, const int nq,
                                                      const uint4* __restrict__ t, const int nt,
                                                      int* __restrict__ best_idx, int* __restrict__ best_dist,
@@ -57,6 +59,7 @@ __global__ void __launch_bounds__(BF_NT) k_hamming_bf(const uint4* __restrict__ 
     uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0;
     if (qi < nq) { a0 = __ldg(qp + 2 * qi); a1 = __ldg(qp + 2 * qi + 1); }
     int bd = 256, bd2 = 256, bi = -1;   // initial values of src/ORBmatcher.cc:101-105
+    uint32_t k1 = 0xffffffffu, k2 = 0xffffffffu;
     for (int j0 = 0; j0 < nt; j0 += BF_TILE) {
         const int m = min(BF_TILE, nt - j0);
         __syncthreads();
@@ -71,6 +74,7 @@ __global__ void __launch_bounds__(BF_NT) k_hamming_bf(const uint4* __restrict__ 
             // work can be traded for LOP3 work until the two pipes are balanced:
             //   ORB_BF_CSA = 1: two CSAs           -> 6 POPC + 4 LOP3
             //   ORB_BF_CSA = 2: three CSAs         -> 5 POPC + 6 LOP3   (balanced on sm_100: POPC 0.5, LOP3 ~2 per clock and SM)
+            //   ORB_BF_CSA = 4: four CSAs          -> 4 POPC + 8 LOP3
             //   ORB_BF_CSA = 3: full Harley-Seal   -> 4 POPC + 14 LOP3
             const uint32_t x0 = a0.x ^ b0.x, x1 = a0.y ^ b0.y, x2 = a0.z ^ b0.z, x3 = a0.w ^ b0.w,
                            x4 = a1.x ^ b1.x, x5 = a1.y ^ b1.y, x6 = a1.z ^ b1.z, x7 = a1.w ^ b1.w;
@@ -81,6 +85,10 @@ __global__ void __launch_bounds__(BF_NT) k_hamming_bf(const uint4* __restrict__ 
 #elif ORB_BF_CSA == 2
             const uint32_t s3 = s1 ^ s2 ^ x6, c3 = (s1 & s2) | (x6 & (s1 | s2));
             const int d = (__popc(s3) + __popc(x7)) + 2 * (__popc(c1) + __popc(c2) + __popc(c3));
+#elif ORB_BF_CSA == 4
+            const uint32_t s3 = s1 ^ s2 ^ x6, c3 = (s1 & s2) | (x6 & (s1 | s2));
+            const uint32_t t1 = c1 ^ c2 ^ c3, e1 = (c1 & c2) | (c3 & (c1 | c2));
+            const int d = (__popc(s3) + __popc(x7)) + 2 * __popc(t1) + 4 * __popc(e1);
 #else
             const uint32_t s3 = s1 ^ s2 ^ x6, c3 = (s1 & s2) | (x6 & (s1 | s2));
             const uint32_t ones = s3 ^ x7, c4 = s3 & x7;
@@ -93,9 +101,23 @@ __global__ void __launch_bounds__(BF_NT) k_hamming_bf(const uint4* __restrict__ 
             const int d = __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
                           __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
 #endif
-            if (d < bd) { bd2 = bd; bd = d; bi = j0 + j; }
-            else if (d < bd2) bd2 = d;
+            if (PACKED) {
+                // the running best / second-best update of :129-141 (strict <, first wins) keeps the two smallest
+                // (distance, index) pairs; as one key per candidate that is three min/max (the pack is an IMAD on the
+                // FMA pipe)
+                const uint32_t key = (uint32_t)d * (1u << BF_KEY_SHIFT) + (uint32_t)(j0 + j);
+                k2 = min(k2, max(k1, key));
+                k1 = min(k1, key);
+            } else {
+                if (d < bd) { bd2 = bd; bd = d; bi = j0 + j; }
+                else if (d < bd2) bd2 = d;
+            }
         }
+    }
+    if (PACKED) {
+        // a candidate at distance 256 is never accepted (the initial bestDist is 256 and the test is strict)
+        if ((k1 >> BF_KEY_SHIFT) < 256u) { bd = (int)(k1 >> BF_KEY_SHIFT); bi = (int)(k1 & ((1u << BF_KEY_SHIFT) - 1u)); }
+        bd2 = min((int)(k2 >> BF_KEY_SHIFT), 256);
     }
     if (qi < nq) {
         const size_t o = (size_t)prob * nq + qi;
@@ -575,7 +597,10 @@ int orbm_hamming_bf(const uint8_t* q, int nq, const uint8_t* t, int nt, int npro
     if (h2) o2 = (int*)S.alloc(ob);
     if (!S.ok) return ORBX_E_CUDA;
     if (((uintptr_t)pq | (uintptr_t)pt) & 15) return ORBX_E_ARG; // descriptors are read as 128-bit words
-    k_hamming_bf<<<dim3((nq + BF_NT - 1) / BF_NT, nprob), BF_NT>>>((const uint4*)pq, nq, (const uint4*)pt, nt, o0, o1, o2);
+    if (nt < (1 << BF_KEY_SHIFT))
+        k_hamming_bf<true><<<dim3((nq + BF_NT - 1) / BF_NT, nprob), BF_NT>>>((const uint4*)pq, nq, (const uint4*)pt, nt, o0, o1, o2);
+    else
+        k_hamming_bf<false><<<dim3((nq + BF_NT - 1) / BF_NT, nprob), BF_NT>>>((const uint4*)pq, nq, (const uint4*)pt, nt, o0, o1, o2);
     CKM(cudaGetLastError());
     if (h0) CKM(cudaMemcpy(best_idx, o0, ob, cudaMemcpyDeviceToHost));
     if (h1) CKM(cudaMemcpy(best_dist, o1, ob, cudaMemcpyDeviceToHost));
