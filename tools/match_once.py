@@ -18,4 +18,6 @@ r = bench.bench_window_match(dev, d_kps, d_desc, d_n, cap, w, h, ex.GetScaleFact
 print({k: r[k] for k in ("value", "ms_per_launch")})
 m = bench.bench_mappoint_side(dev, d_kps, d_desc, d_n, cap, w, h, 1.2, reps=1, cpu=False)
 print({k: (v["value"], v["ms_per_launch"]) for k, v in m.items()})
+h = bench.bench_hamming(dev, 0, reps=1)
+print({k: h[k] for k in ("value", "ms_per_launch")})
 os._exit(0)
