@@ -22,7 +22,10 @@
 
 namespace {
 
-const int NSLOT = 3;
+#ifndef ORB_NSLOT
+#define ORB_NSLOT 3
+#endif
+const int NSLOT = ORB_NSLOT;
 
 struct DevBuf {
     void* p = nullptr;
