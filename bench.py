@@ -368,6 +368,18 @@ def bench_window_match(dev, d_kps, d_desc, d_n, cap, w, h, scale, nprob=512, nq=
            "nq": nq, "nt": float(n.float().mean().item()), "problems_per_launch": nprob, "ms_per_launch": ms,
            "queries_per_s": nprob * nq / (ms * 1e-3), "matches_per_problem": float(nm.mean()),
            "rounds_max": int(d_rounds.max().item()), "rounds_mean": float(d_rounds.float().mean().item()), "launches": 1}
+    # latency of ONE problem through the host-array entry point (what a real-time tracker calls once per frame)
+    n0 = int(n[0].item())
+    kp0 = np.ascontiguousarray(kps[0, :n0].cpu().numpy()).view(ob.KP_DTYPE).reshape(n0)
+    F1 = ob.FrameView(kp0, np.ascontiguousarray(desc[0, :n0].cpu().numpy()), bounds)
+    q1 = {k: np.ascontiguousarray(v[0].cpu().numpy()) for k, v in q.items()}
+    M1 = ob.ORBmatcher(nnratio, True)
+    for _ in range(5):
+        M1.SearchByProjection(F1, scale, q1, th)
+    t0 = time.perf_counter()
+    for _ in range(30):
+        M1.SearchByProjection(F1, scale, q1, th)
+    out["single_call_ms"] = 1e3 * (time.perf_counter() - t0) / 30
     if cpu:
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import oracle_lib

@@ -363,7 +363,7 @@ cudaError_t orb_launch_fast(const OrbPlan& plan, const OrbBatch& io, int batch, 
     if (plan.total_strips == 0) return cudaSuccess;
     const size_t smem = orb_fast_smem_bytes(plan);
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(k_fast_strips, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k_fast_strips, cudaFuncAttributeMaxDynamicSharedMemorySize, ORB_SMEM_OPTIN);   // a constant: the attribute is per-function state shared by all host threads (a per-launch value races)
         if (e != cudaSuccess) return e;
     }
     // Cell rows per block: whole strip columns once the batch alone fills the GPU several times over (the

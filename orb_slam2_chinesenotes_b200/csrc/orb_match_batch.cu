@@ -29,6 +29,8 @@
 #include <stdint.h>
 
 #include <climits>
+#include <cstdio>
+#include <cstdlib>
 
 #include "../../include/orb_b200.h"
 
@@ -439,7 +441,8 @@ template <int MODE, int LOC>
 cudaError_t launch_loc(const MbParams& P, int nprob, size_t smem, cudaStream_t st)
 {
     cudaError_t e = cudaSuccess;
-    if (smem > 48 * 1024) e = cudaFuncSetAttribute(k_match_fixpoint<MODE, LOC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // a constant: the attribute is per-function state shared by all host threads (a per-launch value races)
+    if (smem > 48 * 1024) e = cudaFuncSetAttribute(k_match_fixpoint<MODE, LOC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
     if (e != cudaSuccess) return e;
     k_match_fixpoint<MODE, LOC><<<nprob, MB_NT, smem, st>>>(P);
     return cudaGetLastError();
@@ -464,13 +467,14 @@ int launch(MbParams& P, int nprob, cudaStream_t st)
     void* ws = nullptr;
     const size_t rec_bytes = P.rec_in_smem ? 0 : (size_t)nprob * P.kp_stride * sizeof(uint4);
     const size_t ws_bytes = rec_bytes + (P.desc_in_smem ? 0 : (size_t)nprob * P.kp_stride * 32) + 16;
-    if (cudaMallocAsync(&ws, ws_bytes, st) != cudaSuccess) { cudaGetLastError(); return ORBX_E_CUDA; }
+    { const cudaError_t em = cudaMallocAsync(&ws, ws_bytes, st);
+      if (em != cudaSuccess) { if (getenv("ORB_B200_DEBUG")) fprintf(stderr, "orb_b200: cudaMallocAsync: %s\n", cudaGetErrorString(em)); cudaGetLastError(); return ORBX_E_CUDA; } }
     P.rec = (uint4*)ws;
     P.sdesc = (uint32_t*)((char*)ws + rec_bytes);
     const cudaError_t e = P.desc_in_smem ? launch_loc<MODE, 0>(P, nprob, smem, st)
                         : P.rec_in_smem ? launch_loc<MODE, 1>(P, nprob, smem, st) : launch_loc<MODE, 2>(P, nprob, smem, st);
     cudaFreeAsync(ws, st);
-    if (e != cudaSuccess) { cudaGetLastError(); return ORBX_E_CUDA; }
+    if (e != cudaSuccess) { if (getenv("ORB_B200_DEBUG")) fprintf(stderr, "orb_b200: k_match_fixpoint launch: %s\n", cudaGetErrorString(e)); cudaGetLastError(); return ORBX_E_CUDA; }
     return ORBX_OK;
 }
 

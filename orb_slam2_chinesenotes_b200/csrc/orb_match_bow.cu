@@ -274,10 +274,10 @@ extern "C" int orbm_search_by_bow_batch(const orbm_frames* A, const orbm_featvec
         if (P.desc_in_smem) smem += (size_t)P.n2_max * 32;
         cudaError_t e = cudaSuccess;
         if (P.desc_in_smem) {
-            if (smem > 48 * 1024) e = cudaFuncSetAttribute(k_bow_fixpoint<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (smem > 48 * 1024) e = cudaFuncSetAttribute(k_bow_fixpoint<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
             if (e == cudaSuccess) { k_bow_fixpoint<true><<<A->nprob, BW_NT, smem, (cudaStream_t)cuda_stream>>>(P); e = cudaGetLastError(); }
         } else {
-            if (smem > 48 * 1024) e = cudaFuncSetAttribute(k_bow_fixpoint<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (smem > 48 * 1024) e = cudaFuncSetAttribute(k_bow_fixpoint<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
             if (e == cudaSuccess) { k_bow_fixpoint<false><<<A->nprob, BW_NT, smem, (cudaStream_t)cuda_stream>>>(P); e = cudaGetLastError(); }
         }
         if (e != cudaSuccess) { cudaGetLastError(); rc = ORBX_E_CUDA; }

@@ -14,6 +14,7 @@
 #include <stdint.h>
 
 #define ORB_MAX_LEVELS 16
+#define ORB_SMEM_OPTIN (224 * 1024)   // dynamic shared memory a kernel opts in to (sm_100 allows 227 KB per block INCLUDING its static shared memory); set as a constant, never per launch
 #define ORB_EDGE 19          // EDGE_THRESHOLD, src/ORBextractor.cc:74
 #define ORB_HALF_PATCH 15    // HALF_PATCH_SIZE, :73
 #define ORB_PATCH 31         // PATCH_SIZE, :72

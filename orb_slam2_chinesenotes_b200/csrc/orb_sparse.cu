@@ -272,7 +272,7 @@ cudaError_t orb_launch_octree(const OrbPlan& plan, const OrbBatch& io, int batch
 {
     const size_t smem = orb_octree_smem_bytes(plan);
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, ORB_SMEM_OPTIN);   // a constant: the attribute is per-function state shared by all host threads (a per-launch value races)
         if (e != cudaSuccess) return e;
     }
     k_octree<<<dim3(plan.nlevels, batch), OCT_NT, smem, st>>>(plan, io);

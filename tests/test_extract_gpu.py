@@ -173,3 +173,36 @@ def test_full_size_batch_properties():
         assert (np.diff(k["octave"]) >= 0).all()               # appended level by level
         assert no >= nf and (k["response"] >= 7).all() and (k["angle"] >= 0).all() and (k["angle"] < 360).all()
     G.close(); O.close()
+
+
+def test_two_extractors_on_two_threads_with_different_shapes():
+    """Frame::ExtractORB runs the left and right extractor on two std::threads (src/Frame.cc:82-85); a SLAM process may
+    also hold extractors for different cameras.  Two contexts, two image shapes (different shared-memory footprints of
+    the same kernels), concurrent calls: same results as alone."""
+    import threading
+    jobs = [(640, 480, 1000, 1), (1241, 376, 2000, 2)]
+    want, errors = [], []
+    for w, h, nf, seed in jobs:
+        G = ob.ORBextractor(nf, 1.2, 8, 20, 7)
+        want.append(G(synth_frame(w, h, seed)))
+        G.close()
+
+    def work(i):
+        try:
+            w, h, nf, seed = jobs[i]
+            G = ob.ORBextractor(nf, 1.2, 8, 20, 7)
+            img = synth_frame(w, h, seed)
+            for _ in range(15):
+                k, d = G(img)
+                if not (same_kps(k, want[i][0]) and (d == want[i][1]).all()):
+                    errors.append("mismatch")
+            G.close()
+        except Exception as e:
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[:3]

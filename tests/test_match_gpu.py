@@ -269,3 +269,33 @@ def test_very_large_query_set_takes_the_list_path(scene):
     a = O.search_by_projection_points(k, d, None, scene["scale"], BOUNDS, q, 3.0, 0.9, None)
     b = ob.ORBmatcher(0.9, True).SearchByProjection(ob.FrameView(k, d, BOUNDS), scene["scale"], q, 3.0)
     assert a[0] == b[0] and a[0] > 100 and (a[1] == b[1]).all()
+
+
+def test_matcher_entry_points_are_reentrant(scene):
+    """The reference's tracking, mapping and loop-closing threads construct matchers concurrently: the
+    single-problem entry points keep their staging memory per thread.  Four threads, different problems, 20 calls each."""
+    import threading
+    O = Matcher("oracle")
+    F = ob.FrameView(scene["k2"], scene["d2"], BOUNDS)
+    jobs = []
+    for t in range(4):
+        q = projected_queries(scene["k2"], scene["d2"], 1200 + 100 * t, 50 + t)
+        jobs.append((q, O.search_by_projection_points(scene["k2"], scene["d2"], None, scene["scale"], BOUNDS, q, 3.0, 0.9, None)))
+    errors = []
+
+    def work(q, want):
+        try:
+            M = ob.ORBmatcher(0.9, True)
+            for _ in range(20):
+                nm, a = M.SearchByProjection(F, scene["scale"], q, 3.0)
+                if nm != want[0] or not (a == want[1]).all():
+                    errors.append(nm)
+        except Exception as e:                       # an exception in a thread must fail the test too
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=work, args=j) for j in jobs]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[:3]
