@@ -268,20 +268,20 @@ def bench_hamming(dev, device_index, nq=2000, nt=2000, nprob=256, reps=5):
     q = torch.randint(0, 256, (nprob, nq, 32), generator=g, device=dev, dtype=torch.uint8)
     t = torch.randint(0, 256, (nprob, nt, 32), generator=g, device=dev, dtype=torch.uint8)
     outs = [torch.zeros(nprob * nq, dtype=torch.int32, device=dev) for _ in range(3)]
-    L = ob.lib()
+    stream = torch.cuda.current_stream()
 
     def run():
-        rc = L.orbm_hamming_bf(q.data_ptr(), nq, t.data_ptr(), nt, nprob, outs[0].data_ptr(), outs[1].data_ptr(), outs[2].data_ptr(), device_index)
-        assert rc == 0
+        ob.hamming_bf_async(q, t, outs, nprob, stream.cuda_stream)
 
-    for _ in range(3):
-        run()
+    warm_up(run)
     torch.cuda.synchronize()
-    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
     for _ in range(reps):
-        run()                                      # the call synchronises the device itself
+        run()
+    e1.record(stream)
     torch.cuda.synchronize()
-    dt = (time.perf_counter() - t0) / reps
+    dt = e0.elapsed_time(e1) * 1e-3 / reps
     props = torch.cuda.get_device_properties(dev)
     sms = props.multi_processor_count
     # The kernel trades POPC work for LOP3 work with three carry-save adders (csrc/orb_match.cu k_hamming_bf): 5 POPC +

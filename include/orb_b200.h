@@ -151,6 +151,10 @@ int orbx_max_keypoints(int nfeatures, float scaleFactor, int nlevels, int iniThF
 int orbm_hamming_bf(const uint8_t* q, int nq, const uint8_t* t, int nt, int nprob,
                     int* best_idx, int* best_dist, int* second_dist, int device);
 
+/* The same with every pointer in DEVICE memory: only enqueues on cuda_stream (cudaStream_t, NULL = default stream). */
+int orbm_hamming_bf_async(const uint8_t* d_q, int nq, const uint8_t* d_t, int nt, int nprob,
+                          int* d_best_idx, int* d_best_dist, int* d_second_dist, void* cuda_stream);
+
 /* The Frame fields the window searches read (include/Frame.h:120-175): undistorted keypoints,
  * descriptors, right-image coordinates (NULL = monocular) and the image bounds mnMinX..mnMaxY.
  * The 64x48 grid of Frame::AssignFeaturesToGrid (src/Frame.cc:243-259) is rebuilt on the device. */

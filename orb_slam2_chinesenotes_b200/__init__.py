@@ -111,6 +111,7 @@ def lib():
         L.orbx_plan_describe.argtypes = [i32, f32, i32, i32, i32, i32, i32] + [vp] * 6
         L.orbx_max_keypoints.argtypes = [i32, f32, i32, i32, i32, i32, i32]
         L.orbm_hamming_bf.argtypes = [vp, i32, vp, i32, i32, vp, vp, vp, i32]
+        L.orbm_hamming_bf_async.argtypes = [vp, i32, vp, i32, i32, vp, vp, vp, vp]
         fp = C.POINTER(OrbmFrame)
         L.orbm_search_by_projection_points.argtypes = [fp, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, f32, f32, pi, i32]
         L.orbm_search_by_projection_frame.argtypes = [fp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, f32, vp, i32, vp, vp, f32, i32, i32, pi, i32]
@@ -591,3 +592,11 @@ def hamming_bf(queries, train, device=0, nprob=1):
     if rc:
         raise OrbError(rc, "orbm_hamming_bf failed")
     return tuple(outs)
+
+
+def hamming_bf_async(queries, train, outs, nprob=1, stream=None):
+    """orbm_hamming_bf_async: CUDA tensors in, results into the three int32 CUDA tensors `outs`; only enqueues."""
+    nq, nt = queries.shape[-2], train.shape[-2]
+    rc = lib().orbm_hamming_bf_async(_ptr(queries), nq, _ptr(train), nt, nprob, _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2]), stream)
+    if rc:
+        raise OrbError(rc, "orbm_hamming_bf_async failed")

@@ -680,6 +680,24 @@ int orbm_hamming_bf(const uint8_t* q, int nq, const uint8_t* t, int nt, int npro
     return ORBX_OK;
 }
 
+int orbm_hamming_bf_async(const uint8_t* d_q, int nq, const uint8_t* d_t, int nt, int nprob,
+                          int* d_best_idx, int* d_best_dist, int* d_second_dist, void* cuda_stream)
+{
+    if (!d_q || !d_t || !d_best_idx || !d_best_dist || !d_second_dist || nq <= 0 || nt < 0 || nprob <= 0) return ORBX_E_ARG;
+    if (!dev_ptr(d_q) || !dev_ptr(d_t) || !dev_ptr(d_best_idx) || !dev_ptr(d_best_dist) || !dev_ptr(d_second_dist)) return ORBX_E_ARG;
+    if (((uintptr_t)d_q | (uintptr_t)d_t) & 15) return ORBX_E_ARG;
+    cudaPointerAttributes a;
+    int prev = -1;
+    if (cudaPointerGetAttributes(&a, d_q) != cudaSuccess || cudaGetDevice(&prev) != cudaSuccess || cudaSetDevice(a.device) != cudaSuccess) { cudaGetLastError(); return ORBX_E_CUDA; }
+    const dim3 grid((nq + BF_NT - 1) / BF_NT, nprob);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    if (nt < (1 << BF_KEY_SHIFT)) k_hamming_bf<true><<<grid, BF_NT, 0, st>>>((const uint4*)d_q, nq, (const uint4*)d_t, nt, d_best_idx, d_best_dist, d_second_dist);
+    else k_hamming_bf<false><<<grid, BF_NT, 0, st>>>((const uint4*)d_q, nq, (const uint4*)d_t, nt, d_best_idx, d_best_dist, d_second_dist);
+    const cudaError_t e = cudaGetLastError();
+    cudaSetDevice(prev);
+    return e == cudaSuccess ? ORBX_OK : ORBX_E_CUDA;
+}
+
 int orbm_search_by_projection_points(const orbm_frame* F, const float* scale, int nlevels,
                                      int nq, const float* proj_xyxr, const int* level, const float* view_cos,
                                      const uint8_t* in_view, const uint8_t* bad, const int* observations,

@@ -40,6 +40,22 @@ def test_hamming_bf_matches_oracle(scene):
     assert ob.ORBmatcher.DescriptorDistance(q[0], t[0]) == int(np.unpackbits(q[0] ^ t[0]).sum())
 
 
+def test_hamming_bf_async_on_a_stream(scene):
+    import torch
+    rng = np.random.default_rng(4)
+    q = torch.from_numpy(rng.integers(0, 256, (3, 130, 32), dtype=np.uint8)).cuda()
+    t = torch.from_numpy(rng.integers(0, 256, (3, 200, 32), dtype=np.uint8)).cuda()
+    outs = [torch.zeros(3 * 130, dtype=torch.int32, device="cuda") for _ in range(3)]
+    st = torch.cuda.Stream()
+    st.wait_stream(torch.cuda.current_stream())
+    ob.hamming_bf_async(q, t, outs, nprob=3, stream=st.cuda_stream)
+    st.synchronize()
+    want = ob.hamming_bf(q.cpu().numpy(), t.cpu().numpy(), nprob=3)
+    assert all((o.cpu().numpy() == w).all() for o, w in zip(outs, want))
+    with pytest.raises(ob.OrbError):
+        ob.hamming_bf_async(q.cpu(), t, outs, nprob=3)
+
+
 def test_hamming_bf_batched_problems(scene):
     rng = np.random.default_rng(3)
     q = rng.integers(0, 256, (4, 300, 32), dtype=np.uint8)
