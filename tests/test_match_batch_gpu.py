@@ -226,3 +226,66 @@ def test_frame_to_frame_batch_equals_oracle(scene, th, mono, check_ori):
             n = len(p["cur"]["kps"])
             assert nm[i] == want[0] and want[0] > 100, (i, nm[i], want[0])
             assert (assign[i, :n] == want[1]).all()
+
+
+def _adversarial_problem(kind, rng):
+    """(kps, desc, queries) built to stress the order resolution and the grid."""
+    nlevels = 8
+    if kind == "pile":            # every keypoint and every query in one grid cell, a handful of distinct descriptors:
+        n, nq = 600, 900          # long chains of "taken by an earlier query" -> many fixpoint rounds
+        kp = np.zeros(n, KP_DTYPE)
+        kp["x"] = 300 + rng.integers(0, 6, n); kp["y"] = 150 + rng.integers(0, 4, n); kp["octave"] = rng.integers(0, 2, n)
+        base = rng.integers(0, 256, (5, 32), dtype=np.uint8)
+        de = base[rng.integers(0, 5, n)].copy(); de[:, 0] ^= rng.integers(0, 4, n).astype(np.uint8)
+        proj = np.stack([300 + rng.random(nq) * 6, 150 + rng.random(nq) * 4, 280 + rng.random(nq) * 6], 1).astype(np.float32)
+        q = dict(proj=proj, level=rng.integers(0, 2, nq).astype(np.int32), view_cos=np.full(nq, 0.9, np.float32),
+                 in_view=np.ones(nq, np.uint8), bad=np.zeros(nq, np.uint8), obs=(rng.random(nq) < 0.9).astype(np.int32),
+                 desc=base[rng.integers(0, 5, nq)].copy())
+    elif kind == "big":           # the largest frame the kernels take
+        n, nq = 8192, 8192
+        kp = np.zeros(n, KP_DTYPE)
+        kp["x"] = rng.random(n) * W; kp["y"] = rng.random(n) * H; kp["octave"] = rng.integers(0, nlevels, n)
+        de = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+        q = projected_queries(kp, de, nq, 3)
+    else:                         # "outside": a third of the keypoints lie outside the image bounds (not in the grid)
+        n, nq = 1500, 1500
+        kp = np.zeros(n, KP_DTYPE)
+        kp["x"] = rng.random(n) * (W + 600) - 300; kp["y"] = rng.random(n) * (H + 300) - 150; kp["octave"] = rng.integers(0, nlevels, n)
+        de = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+        q = projected_queries(kp, de, nq, 4)
+    return kp, de, q
+
+
+@pytest.mark.parametrize("kind", ["pile", "big", "outside"])
+def test_adversarial_problems_equal_oracle(scene, kind):
+    import torch
+    rng = np.random.default_rng(77)
+    bounds = (0.0, float(W), 0.0, float(H))
+    kp, de, q = _adversarial_problem(kind, rng)
+    n, nq = len(kp), len(q["level"])
+    want = Matcher("oracle").search_by_projection_points(kp, de, None, scene["scale"], bounds, q, 3.0, 0.9, None)
+    F, keep = _frames([dict(kps=kp, desc=de)], bounds, n, False)
+    dq = {k: _dev(q[k][None]) for k in q}
+    d_assign = torch.zeros((1, n), dtype=torch.int32, device="cuda")
+    d_nm = torch.zeros(1, dtype=torch.int32, device="cuda")
+    d_rounds = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ob.search_by_projection_points_batch(F, scene["scale"], dq, _dev(np.int32([nq])), nq, d_assign, d_nm, 3.0, 0.9, None, d_rounds)
+    torch.cuda.synchronize()
+    assert int(d_nm[0]) == want[0] and (d_assign[0].cpu().numpy() == want[1]).all(), (kind, int(d_nm[0]), want[0], int(d_rounds[0]))
+    if kind == "pile":
+        assert want[0] > 20 and int(d_rounds[0]) > 8          # the chain really was long
+    # the best-only mode on the same windows
+    uvr = np.ascontiguousarray(np.concatenate([q["proj"][:, :2], np.full((nq, 1), 9.0, np.float32)], 1))
+    qb = dict(uvr=uvr, min_level=np.maximum(q["level"] - 1, -1).astype(np.int32), max_level=(q["level"] + 1).astype(np.int32),
+              desc=q["desc"], q_angle=(rng.random(nq) * 360).astype(np.float32), q_obs=q["obs"])
+    O = oracle()
+    vp, ci, cf = C.c_void_p, C.c_int, C.c_float
+    O.orbo_window_search_best.argtypes = [ci, vp, vp, vp] + [cf] * 4 + [ci] + [vp] * 11 + [ci, ci]
+    ref_assign = np.zeros(n, np.int32)
+    p = lambda a: None if a is None else a.ctypes.data
+    wantb = O.orbo_window_search_best(n, p(kp), p(de), None, *bounds, nq, p(qb["uvr"]), p(qb["min_level"]), p(qb["max_level"]), None, None, None,
+                                      p(qb["desc"]), p(qb["q_angle"]), p(qb["q_obs"]), None, p(ref_assign), 100, 1)
+    dqb = {k: _dev(v[None]) for k, v in qb.items()}
+    ob.window_search_best_batch(F, dqb, _dev(np.int32([nq])), nq, d_assign, d_nm, 100, True, None, d_rounds)
+    torch.cuda.synchronize()
+    assert int(d_nm[0]) == wantb and (d_assign[0].cpu().numpy() == ref_assign).all(), (kind, int(d_nm[0]), wantb)
