@@ -276,6 +276,13 @@ int orbm_search_by_projection_frame_batch(const orbm_frames* cur, const float* T
                                           const int* cur_init_obs, int* assign_out, float th, int bMono, int checkOri,
                                           int* nmatches, void* cuda_stream);
 
+/* ORBmatcher::SearchForInitialization, src/ORBmatcher.cc:1055-1180, for nprob (F1, F2) pairs.  prev_matched
+ * [nprob][F1.kp_stride][2] = vbPrevMatched (window centres; updated in place like the reference does), matches12
+ * [nprob][F1.kp_stride] = vnMatches12, nmatches [nprob] the return value.  Frames with at most 8192 keypoints.
+ * rounds (or NULL): passes of the order resolution, negative when a problem fell back to the in-order walk. */
+int orbm_search_for_initialization_batch(const orbm_frames* F1, const orbm_frames* F2, float* prev_matched, int* matches12,
+                                         int windowSize, float nnratio, int checkOri, int* nmatches, int* rounds, void* cuda_stream);
+
 /* ---- map-point side of the matching path (device resident, only enqueue) ------------------
  * Frame::isInFrustum (src/Frame.cc:288-345, camera centre as Frame::UpdatePoseMatrices :280-285, level by
  * MapPoint::PredictScale src/MapPoint.cc:459-475) for every (frame, map point): the loop of

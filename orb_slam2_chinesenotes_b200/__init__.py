@@ -120,6 +120,7 @@ def lib():
         L.orbm_search_by_projection_points_batch.argtypes = [C.POINTER(OrbmFrames), vp, i32, C.POINTER(OrbmPoints), vp, vp, f32, f32, vp, vp, vp]
         L.orbm_window_search_best_batch.argtypes = [C.POINTER(OrbmFrames), C.POINTER(OrbmWindows), vp, vp, i32, i32, vp, vp, vp]
         L.orbm_search_by_projection_frame_batch.argtypes = [C.POINTER(OrbmFrames), vp, vp, vp, f32, vp, i32, vp, i32] + [vp] * 8 + [f32, i32, i32, vp, vp]
+        L.orbm_search_for_initialization_batch.argtypes = [C.POINTER(OrbmFrames), C.POINTER(OrbmFrames), vp, vp, i32, f32, i32, vp, vp, vp]
         L.orbm_project_points_batch.argtypes = [i32, vp, vp, f32, f32, f32, f32, f32, f32, i32, f32, vp, i32, i32] + [vp] * 9 + [vp]
         L.orbm_distinctive_descriptors.argtypes = [vp, vp, i32, vp, vp, vp, vp]
         L.orbm_search_by_bow_batch.argtypes = [C.POINTER(OrbmFrames), C.POINTER(OrbmFeatVec), vp, C.POINTER(OrbmFrames), C.POINTER(OrbmFeatVec), vp,
@@ -524,6 +525,15 @@ def search_by_projection_frame_batch(cur, Tcw_cur, Tcw_last, K, bf, scale, n_las
                                                      _ptr(cur_init_obs), _ptr(assign_out), th, int(bMono), int(check_ori), _ptr(nmatches), stream)
     if rc:
         raise OrbError(rc, "orbm_search_by_projection_frame_batch failed")
+
+
+def search_for_initialization_batch(F1, F2, prev_matched, matches12, nmatches, window, nnratio, check_ori, rounds=None, stream=None):
+    """orbm_search_for_initialization_batch (src/ORBmatcher.cc:1055-1180 for every (F1, F2) pair): F1, F2 frames_batch(...);
+    prev_matched [P,cap1,2] float32 (updated in place), matches12 [P,cap1] int32, nmatches [P] int32 CUDA tensors."""
+    rc = lib().orbm_search_for_initialization_batch(C.byref(F1), C.byref(F2), _ptr(prev_matched), _ptr(matches12), int(window),
+                                                    float(np.float32(nnratio)), int(check_ori), _ptr(nmatches), _ptr(rounds), stream)
+    if rc:
+        raise OrbError(rc, "orbm_search_for_initialization_batch failed")
 
 
 def project_points_batch(Tcw, K, bf, bounds, scale_factor, nlevels, nq, nq_stride, pts, out, cos_limit=0.5, points_shared=False,

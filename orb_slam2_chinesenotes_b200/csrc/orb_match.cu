@@ -888,6 +888,21 @@ int orbm_search_for_initialization(const orbm_frame* F1, const orbm_frame* F2, f
     for (int i = 0; i < n1; ++i) matches12[i] = -1;
     if (n1 == 0 || n2 == 0) return ORBX_OK;
     Scratch S;
+    if (n1 <= MAX_KP && orb_match_batch_fits(n2, n1)) {
+        // one launch of the block-per-problem kernel (orb_match_batch.cu k_init_fixpoint)
+        OneFrame O1, O2;
+        if (!one_frame(S, F1, &O1) || !one_frame(S, F2, &O2)) return S.ok ? ORBX_E_ARG : ORBX_E_CUDA;
+        float* d_prev = S.up(prev_matched, (size_t)n1 * 2);
+        int* d_m12 = (int*)S.alloc(sizeof(int) * (size_t)n1);
+        int* d_nm = (int*)S.alloc(4);
+        if (!S.ok || !S.flush()) return ORBX_E_CUDA;
+        const int rc = orbm_search_for_initialization_batch(&O1.F, &O2.F, d_prev, d_m12, windowSize, nnratio, checkOri, d_nm, nullptr, nullptr);
+        if (rc) return rc;
+        CKM(cudaMemcpy(matches12, d_m12, sizeof(int) * (size_t)n1, cudaMemcpyDeviceToHost));
+        CKM(cudaMemcpy(prev_matched, d_prev, sizeof(float) * (size_t)n1 * 2, cudaMemcpyDeviceToHost));
+        CKM(cudaMemcpy(nmatches, d_nm, 4, cudaMemcpyDeviceToHost));
+        return *nmatches < 0 ? ORBX_E_ARG : ORBX_OK;
+    }
     DevFrame D2;
     if (!make_frame(S, F2, &D2)) return S.ok ? ORBX_E_ARG : ORBX_E_CUDA;
     std::vector<WinQuery> hq((size_t)n1);

@@ -43,6 +43,8 @@
 #define MB_MAX_LEVELS 32
 #define MB_NT 1024
 #define MB_NONE 0xffffffffu
+#define MB_CL 6            // claimants per keypoint kept for the parallel rounds of SearchForInitialization
+#define TH_LOW 50         // src/ORBmatcher.cc:38
 
 enum { MODE_POINTS = 0, MODE_BEST = 1 };
 
@@ -70,6 +72,12 @@ struct MbParams {
     uint4* rec; uint32_t* sdesc;     // [nprob][kp_stride], [nprob][kp_stride][8]
     int sn_max, nq_max;              // shared-memory sizing
     int rec_in_smem, desc_in_smem;   // the sorted records / descriptors live in shared memory when they fit
+    // SearchForInitialization only
+    const orbx_kp* kps1;             // F1.mvKeysUn [nprob][nq_stride]
+    float* prev;                     // vbPrevMatched [nprob][nq_stride][2], updated in place
+    int* matches12;                  // vnMatches12 [nprob][nq_stride]
+    uint32_t* cl;                    // workspace [nprob][kp_stride][MB_CL]: claimants (query << 9 | distance) of every position
+    float window;
     int* rounds;                     // [nprob] or null: fixpoint rounds used (profiling / tests)
 };
 
@@ -112,10 +120,12 @@ __device__ __forceinline__ int mb_rot_bin(const float a1, const float a2)   // s
 #ifndef MB_G
 #define MB_G 4
 #endif
-template <int MODE>
-__device__ __forceinline__ void query_top2(const MbParams& P, const WinQ& Q, const int q, const uint32_t (&qd)[8],
+// taken(j): the candidate at position j is held by an earlier query (tested before the distance is computed);
+// beaten(j, dist): an earlier query matched it at a distance <= dist (SearchForInitialization only).
+template <typename Taken, typename Beaten>
+__device__ __forceinline__ void query_top2(const MbParams& P, const WinQ& Q, const uint32_t (&qd)[8],
                                            const uint4* rec, const uint4* sdesc, const int* cell_start,
-                                           const int* blk, const bool use_ur, const int sub, const unsigned gmask,
+                                           Taken taken, Beaten beaten, const bool use_ur, const int sub, const unsigned gmask,
                                            uint32_t& k1, uint32_t& k2, bool& skipped)
 {
     uint32_t a1 = MB_NONE, a2 = MB_NONE;
@@ -137,7 +147,7 @@ __device__ __forceinline__ void query_top2(const MbParams& P, const WinQ& Q, con
                     if (Q.max_level >= 0 && oct > Q.max_level) continue;
                 }
                 if (!(fabsf(__uint_as_float(r.x) - Q.u) < Q.r && fabsf(__uint_as_float(r.y) - Q.v) < Q.r)) continue;   // :402
-                if (blk[j] < q) { ++nb; continue; }                                   // src/ORBmatcher.cc:115-117 / :234-236
+                if (taken(j)) { ++nb; continue; }                                     // src/ORBmatcher.cc:115-117 / :234-236
                 if (use_ur) {
                     const float ur = __uint_as_float(r.w);
                     if (ur > 0 && fabsf(Q.ur - ur) > Q.er_max) continue;             // :119-124 / :238-244
@@ -145,6 +155,7 @@ __device__ __forceinline__ void query_top2(const MbParams& P, const WinQ& Q, con
                 const uint4 b0 = sdesc[2 * j], b1 = sdesc[2 * j + 1];
                 const uint32_t dist = __popc(qd[0] ^ b0.x) + __popc(qd[1] ^ b0.y) + __popc(qd[2] ^ b0.z) + __popc(qd[3] ^ b0.w) +
                                       __popc(qd[4] ^ b1.x) + __popc(qd[5] ^ b1.y) + __popc(qd[6] ^ b1.z) + __popc(qd[7] ^ b1.w);
+                if (beaten(j, (int)dist)) continue;                                   // :1094
                 const uint32_t key = (dist << 16) | (uint32_t)j;
                 if (key < a1) { a2 = a1; a1 = key; }
                 else if (key < a2) a2 = key;
@@ -160,7 +171,6 @@ __device__ __forceinline__ void query_top2(const MbParams& P, const WinQ& Q, con
 #pragma unroll
     for (int d = MB_G / 2; d > 0; d >>= 1) k2 = min(k2, __shfl_xor_sync(0xffffffffu, k2, d));
     skipped = (__ballot_sync(0xffffffffu, nb > 0) & gmask) != 0;
-    (void)MODE;
 }
 
 // The blocked-candidate order matters: in the reference the "taken" test comes BEFORE the right-image test, and
@@ -172,6 +182,42 @@ __device__ long long g_clk[16];
 #else
 #define CLK(i)
 #endif
+
+// Frame::AssignFeaturesToGrid (src/Frame.cc:243-259) for one frame, by the whole block: the cell of every keypoint
+// (round(), :414-415), keys = cell << 16 | index sorted in shared memory, cell_start[c] = first position of cell c
+// (cell_start[GRID_CELLS] = number of keypoints inside the grid).  Ends with a barrier.
+template <int NT>
+__device__ __forceinline__ void mb_sort_frame(const MbParams& P, const orbx_kp* kps, const int n, const int sn, uint32_t* keys, int* cell_start)
+{
+    const int tid = threadIdx.x;
+    for (int i = tid; i < sn; i += NT) {
+        uint32_t key = MB_NONE;
+        if (i < n) {
+            const int px = (int)roundf((kps[i].x - P.min_x) * P.inv_w);
+            const int py = (int)roundf((kps[i].y - P.min_y) * P.inv_h);
+            if (!(px < 0 || px >= GRID_COLS || py < 0 || py >= GRID_ROWS)) key = ((uint32_t)(px * GRID_ROWS + py) << 16) | (uint32_t)i;
+        }
+        keys[i] = key;
+    }
+    __syncthreads();
+    for (int k = 2; k <= sn; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < (sn >> 1); t += NT) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), ixj = i | j;
+                const uint32_t a = keys[i], b = keys[ixj];
+                if (((i & k) == 0) ? (a > b) : (a < b)) { keys[i] = b; keys[ixj] = a; }
+            }
+            __syncthreads();
+        }
+    for (int i = tid; i < sn; i += NT) {
+        const uint32_t key = keys[i];
+        const int c = key == MB_NONE ? GRID_CELLS : (int)(key >> 16);
+        const int cprev = i == 0 ? -1 : (keys[i - 1] == MB_NONE ? GRID_CELLS : (int)(keys[i - 1] >> 16));
+        for (int cc = cprev + 1; cc <= c; ++cc) cell_start[cc] = i;
+        if (i == sn - 1) for (int cc = c + 1; cc <= GRID_CELLS; ++cc) cell_start[cc] = sn;
+    }
+    __syncthreads();
+}
 
 // LOC: where the sorted records / descriptors live -- 0: both in shared memory, 1: records in shared memory,
 // descriptors in the global workspace, 2: both global.  A template parameter so that the loads of the window walk
@@ -207,35 +253,7 @@ __global__ void __launch_bounds__(MB_NT) k_match_fixpoint(const __grid_constant_
     else { rec = P.rec + ko; sdesc = (uint4*)(P.sdesc + ko * 8); }
 
     CLK(0);
-    // ---- Frame::AssignFeaturesToGrid (src/Frame.cc:243-259): cell of every keypoint (round(), :414-415), sorted
-    for (int i = tid; i < sn; i += MB_NT) {
-        uint32_t key = MB_NONE;
-        if (i < n) {
-            const int px = (int)roundf((kps[i].x - P.min_x) * P.inv_w);
-            const int py = (int)roundf((kps[i].y - P.min_y) * P.inv_h);
-            if (!(px < 0 || px >= GRID_COLS || py < 0 || py >= GRID_ROWS)) key = ((uint32_t)(px * GRID_ROWS + py) << 16) | (uint32_t)i;
-        }
-        keys[i] = key;
-    }
-    __syncthreads();
-    CLK(1);
-    for (int k = 2; k <= sn; k <<= 1)
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = tid; t < (sn >> 1); t += MB_NT) {
-                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), ixj = i | j;
-                const uint32_t a = keys[i], b = keys[ixj];
-                if (((i & k) == 0) ? (a > b) : (a < b)) { keys[i] = b; keys[ixj] = a; }
-            }
-            __syncthreads();
-        }
-    for (int i = tid; i < sn; i += MB_NT) {
-        const uint32_t key = keys[i];
-        const int c = key == MB_NONE ? GRID_CELLS : (int)(key >> 16);
-        const int cprev = i == 0 ? -1 : (keys[i - 1] == MB_NONE ? GRID_CELLS : (int)(keys[i - 1] >> 16));
-        for (int cc = cprev + 1; cc <= c; ++cc) cell_start[cc] = i;
-        if (i == sn - 1) for (int cc = c + 1; cc <= GRID_CELLS; ++cc) cell_start[cc] = sn;
-    }
-    __syncthreads();
+    mb_sort_frame<MB_NT>(P, kps, n, sn, keys, cell_start);
     const int nvalid = cell_start[GRID_CELLS];
     CLK(2);
     const bool use_ur = P.u_right != nullptr && (MODE == MODE_POINTS || P.f1 != nullptr);
@@ -311,7 +329,8 @@ __global__ void __launch_bounds__(MB_NT) k_match_fixpoint(const __grid_constant_
                 d[6] = __shfl_sync(0xffffffffu, myd1.z, src); d[7] = __shfl_sync(0xffffffffu, myd1.w, src);
                 uint32_t k1 = MB_NONE, k2 = MB_NONE;
                 bool skipped = false;
-                query_top2<MODE>(P, Q, qq, d, rec, sdesc, cell_start, blk, use_ur, sub, gmask, k1, k2, skipped);
+                query_top2(P, Q, d, rec, sdesc, cell_start, [&](const int j) { return blk[j] < qq; }, [](int, int) { return false; },
+                           use_ur, sub, gmask, k1, k2, skipped);
                 if (sub == 0 && Q.valid) {
                     int best = -1;
                     if (k1 != MB_NONE) {
@@ -410,6 +429,216 @@ __global__ void __launch_bounds__(MB_NT) k_match_fixpoint(const __grid_constant_
     }
     if (tid == 0) *nm_out = s_cnt[0] - s_cnt[1];
     CLK(12);
+}
+
+// ------------------------------------------------------------------------------------------ monocular initialisation
+// ORBmatcher::SearchForInitialization, src/ORBmatcher.cc:1055-1180, one block per (F1, F2) pair.  Queries = the level-0
+// keypoints of F1 in order; candidates = level-0 keypoints of F2 inside the window around vbPrevMatched.  A candidate is
+// skipped when an EARLIER query already matched it at a distance <= this one's (:1094); an accepted match replaces the
+// previous owner (:1115-1122).  The same fixpoint idea as above with a richer state: per F2 keypoint the list of its
+// claimants (query, distance).  "Beaten when query q runs" <=> some claimant q' < q has distance <= dist.  Every round
+// recomputes all queries against the lists of the previous round (after round r the first r decisions are final); a
+// keypoint with more than MB_CL claimants in some round switches the block to the plain in-order walk by one warp.
+template <int LOC>
+__global__ void __launch_bounds__(MB_NT) k_init_fixpoint(const __grid_constant__ MbParams P)
+{
+    extern __shared__ __align__(16) uint32_t smem[];
+    __shared__ int s_flag[3], s_cnt[2], s_sizes[HISTO_LENGTH], s_ind[3];
+    const int prob = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = MB_NT >> 5;
+    const int n = P.n[prob], nq = P.nq[prob];
+    int* const nm_out = P.nmatches + prob;
+    if (n < 0 || n > P.sn_max || n > P.kp_stride || nq < 0 || nq > P.nq_stride || nq > MB_MAX_KP) { if (tid == 0) *nm_out = -1; return; }
+    const size_t ko = (size_t)prob * P.kp_stride, qo = (size_t)prob * P.nq_stride;
+    const orbx_kp* kps = P.kps + ko;
+    const orbx_kp* kps1 = P.kps1 + qo;
+    float* prev = P.prev + 2 * qo;
+    int* matches12 = P.matches12 + qo;
+    uint32_t* cl = P.cl + ko * MB_CL;
+    int sn = 32; while (sn < n) sn <<= 1;
+    uint32_t* keys = smem;
+    int* cell_start = (int*)(smem + P.sn_max);
+    int* const cnt = cell_start + GRID_CELLS + 4;           // [sn_max] claimants of every position; last writer at the end
+    int* const md = cnt + P.sn_max;                         // [sn_max] vMatchedDistance of the in-order walk
+    uint32_t* st_dist = (uint32_t*)(md + P.sn_max);         // [nq_max] accepted distance (| bin << 16 at the end)
+    uint32_t* st_best = st_dist + P.nq_max;                 // [nq_max] accepted position + 1, 0 = none
+    uint4* const sm16 = (uint4*)(st_best + P.nq_max);
+    uint4* rec; uint4* sdesc;
+    if (LOC == 0) { rec = sm16; sdesc = sm16 + P.sn_max; }
+    else if (LOC == 1) { rec = sm16; sdesc = (uint4*)(P.sdesc + ko * 8); }
+    else { rec = P.rec + ko; sdesc = (uint4*)(P.sdesc + ko * 8); }
+
+    mb_sort_frame<MB_NT>(P, kps, n, sn, keys, cell_start);
+    const int nvalid = cell_start[GRID_CELLS];
+    for (int j = tid; j < nvalid; j += MB_NT) {
+        const int idx = (int)(keys[j] & 0xffffu);
+        const orbx_kp kp = kps[idx];
+        rec[j] = make_uint4(__float_as_uint(kp.x), __float_as_uint(kp.y), (uint32_t)(kp.octave & 0xff) | ((uint32_t)idx << 8), __float_as_uint(-1.0f));
+        cnt[j] = 0;
+    }
+    for (int t = tid; t < nvalid * 8; t += MB_NT) {
+        const int j = t >> 3, wd = t & 7;
+        ((uint32_t*)sdesc)[(size_t)j * 8 + wd] = P.desc[(ko + (keys[j] & 0xffffu)) * 8 + wd];
+    }
+    for (int q = tid; q < nq; q += MB_NT) { st_dist[q] = 0; st_best[q] = 0; }
+    if (tid == 0) { s_flag[0] = 0; s_flag[1] = 0; s_flag[2] = 0; s_cnt[0] = 0; s_cnt[1] = 0; }
+    if (tid < HISTO_LENGTH) s_sizes[tid] = 0;
+    __syncthreads();
+
+    auto load_q = [&](const int q) {                         // :1071-1080
+        WinQ Q;
+        const orbx_kp k1 = kps1[q];
+        Q.valid = !(k1.octave > 0);
+        Q.u = prev[2 * q]; Q.v = prev[2 * q + 1]; Q.r = P.window;
+        Q.min_level = k1.octave; Q.max_level = k1.octave;
+        Q.ur = 0.f; Q.er_max = 0.f;
+        return Q;
+    };
+    auto decide = [&](const int q, const uint32_t k1, const uint32_t k2) -> bool {      // :1107-1113; returns "changed"
+        uint32_t nb = 0, nd = 0;
+        if (k1 != MB_NONE) {
+            const int bestDist = (int)(k1 >> 16);
+            const float second = k2 == MB_NONE ? 2147483648.0f : (float)(int)(k2 >> 16);   // INT_MAX when there is none
+            if (bestDist <= TH_LOW && (float)bestDist < __fmul_rn(second, P.nnratio)) { nb = (k1 & 0xffffu) + 1; nd = (uint32_t)bestDist; }
+        }
+        const bool changed = st_best[q] != nb || st_dist[q] != nd;
+        st_best[q] = nb; st_dist[q] = nd;
+        return changed;
+    };
+
+    int round = 0;
+    bool in_order = false;
+    for (;; ++round) {
+        const int par = round & 1;
+        for (int base = warp * 32; base < nq; base += nwarps * 32) {
+            const int q = base + lane;
+            WinQ myQ;
+            myQ.valid = 0;
+            uint4 myd0 = make_uint4(0, 0, 0, 0), myd1 = myd0;
+            if (q < nq) {
+                myQ = load_q(q);
+                if (myQ.valid) { const uint4* qd = (const uint4*)(P.qdesc + (qo + q) * 8); myd0 = __ldg(qd); myd1 = __ldg(qd + 1); }
+            }
+            const bool go = myQ.valid != 0;
+            if (!__any_sync(0xffffffffu, go)) continue;
+            const int sub = lane & (MB_G - 1), g0 = lane & ~(MB_G - 1);
+            const unsigned gmask = ((1u << MB_G) - 1u) << g0;
+            for (int i = 0; i < MB_G; ++i) {
+                const int src = g0 + i, qq = base + src;
+                WinQ Q;
+                Q.valid = __shfl_sync(0xffffffffu, (int)go, src);
+                if (!__any_sync(0xffffffffu, Q.valid)) continue;
+                Q.u = __shfl_sync(0xffffffffu, myQ.u, src); Q.v = __shfl_sync(0xffffffffu, myQ.v, src); Q.r = P.window;
+                Q.ur = 0.f; Q.er_max = 0.f;
+                Q.min_level = __shfl_sync(0xffffffffu, myQ.min_level, src); Q.max_level = Q.min_level;
+                uint32_t d[8];
+                d[0] = __shfl_sync(0xffffffffu, myd0.x, src); d[1] = __shfl_sync(0xffffffffu, myd0.y, src);
+                d[2] = __shfl_sync(0xffffffffu, myd0.z, src); d[3] = __shfl_sync(0xffffffffu, myd0.w, src);
+                d[4] = __shfl_sync(0xffffffffu, myd1.x, src); d[5] = __shfl_sync(0xffffffffu, myd1.y, src);
+                d[6] = __shfl_sync(0xffffffffu, myd1.z, src); d[7] = __shfl_sync(0xffffffffu, myd1.w, src);
+                uint32_t k1 = MB_NONE, k2 = MB_NONE;
+                bool skipped = false;
+                query_top2(P, Q, d, rec, sdesc, cell_start, [](int) { return false; },
+                           [&](const int j, const int dist) {
+                               const int c = min(cnt[j], MB_CL);
+                               for (int e = 0; e < c; ++e) {
+                                   const uint32_t ent = cl[(size_t)j * MB_CL + e];
+                                   if ((int)(ent >> 9) < qq && (int)(ent & 0x1ffu) <= dist) return true;
+                               }
+                               return false;
+                           }, false, sub, gmask, k1, k2, skipped);
+                if (sub == 0 && Q.valid && decide(qq, k1, k2)) s_flag[par] = 1;
+            }
+        }
+        __syncthreads();
+        if (!s_flag[par]) break;
+        // claimant lists from the decisions
+        for (int j = tid; j < nvalid; j += MB_NT) cnt[j] = 0;
+        if (tid == 0) s_flag[par ^ 1] = 0;
+        __syncthreads();
+        for (int q = tid; q < nq; q += MB_NT) {
+            const int b = (int)st_best[q] - 1;
+            if (b < 0) continue;
+            const int e = atomicAdd(&cnt[b], 1);
+            if (e < MB_CL) cl[(size_t)b * MB_CL + e] = ((uint32_t)q << 9) | st_dist[q];
+            else s_flag[2] = 1;
+        }
+        __syncthreads();
+        if (s_flag[2] || round > nq) { in_order = true; break; }
+    }
+    if (in_order) {
+        // the reference's own order on one warp (group 0 works, the other lanes only take part in the shuffles)
+        for (int j = tid; j < nvalid; j += MB_NT) md[j] = INT_MAX;
+        for (int q = tid; q < nq; q += MB_NT) { st_dist[q] = 0; st_best[q] = 0; }
+        __syncthreads();
+        if (warp == 0) {
+            const int sub = lane & (MB_G - 1);
+            const unsigned gmask = ((1u << MB_G) - 1u) << (lane & ~(MB_G - 1));
+            for (int q = 0; q < nq; ++q) {
+                WinQ Q = load_q(q);
+                const bool valid = Q.valid != 0;
+                Q.valid = valid && lane < MB_G;
+                uint32_t d[8];
+#pragma unroll
+                for (int w = 0; w < 8; ++w) d[w] = __ldg(P.qdesc + (qo + q) * 8 + w);
+                uint32_t k1 = MB_NONE, k2 = MB_NONE;
+                bool skipped = false;
+                query_top2(P, Q, d, rec, sdesc, cell_start, [](int) { return false; }, [&](const int j, const int dist) { return md[j] <= dist; },
+                           false, sub, gmask, k1, k2, skipped);
+                if (lane == 0 && valid) { decide(q, k1, k2); if (st_best[q]) md[st_best[q] - 1] = (int)st_dist[q]; }
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+    }
+    if (P.rounds && tid == 0) P.rounds[prob] = in_order ? -(round + 1) : round + 1;
+
+    // ---- results: the owner of a keypoint is its last claimant; replaced queries keep their histogram entry (:1124-1134)
+    for (int j = tid; j < nvalid; j += MB_NT) cnt[j] = -1;
+    __syncthreads();
+    for (int q = tid; q < nq; q += MB_NT) {
+        const int b = (int)st_best[q] - 1;
+        if (b < 0) continue;
+        atomicMax(&cnt[b], q);
+        if (P.check_ori) {
+            const int bin = mb_rot_bin(kps1[q].angle, kps[rec[b].z >> 8 & 0x7fffffu].angle);
+            st_dist[q] |= (uint32_t)bin << 16;
+            atomicAdd(&s_sizes[bin], 1);
+        }
+    }
+    __syncthreads();
+    int owned = 0;
+    for (int j = tid; j < nvalid; j += MB_NT) owned += cnt[j] >= 0 ? 1 : 0;
+    if (owned) atomicAdd(&s_cnt[0], owned);
+    if (P.check_ori && tid == 0) {   // ComputeThreeMaxima, src/ORBmatcher.cc:1663-1707
+        int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
+        for (int i = 0; i < HISTO_LENGTH; ++i) {
+            const int sz = s_sizes[i];
+            if (sz > max1) { max3 = max2; max2 = max1; max1 = sz; ind3 = ind2; ind2 = ind1; ind1 = i; }
+            else if (sz > max2) { max3 = max2; max2 = sz; ind3 = ind2; ind2 = i; }
+            else if (sz > max3) { max3 = sz; ind3 = i; }
+        }
+        if ((float)max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+        else if ((float)max3 < 0.1f * (float)max1) ind3 = -1;
+        s_ind[0] = ind1; s_ind[1] = ind2; s_ind[2] = ind3;
+    }
+    __syncthreads();
+    int dec = 0;
+    for (int q = tid; q < nq; q += MB_NT) {
+        int m = -1;
+        const int b = (int)st_best[q] - 1;
+        if (b >= 0 && cnt[b] == q) {                                          // still the owner
+            m = (int)(rec[b].z >> 8 & 0x7fffffu);
+            if (P.check_ori) {
+                const int bin = (int)(st_dist[q] >> 16);
+                if (bin != s_ind[0] && bin != s_ind[1] && bin != s_ind[2]) { m = -1; ++dec; }     // :1163-1167
+            }
+        }
+        matches12[q] = m;
+        if (m >= 0) { prev[2 * q] = kps[m].x; prev[2 * q + 1] = kps[m].y; }  // :1175-1177
+    }
+    if (dec) atomicAdd(&s_cnt[1], dec);
+    __syncthreads();
+    if (tid == 0) *nm_out = s_cnt[0] - s_cnt[1];
 }
 
 // ================================================================================ host side
@@ -535,6 +764,51 @@ int orbm_window_search_best_batch(const orbm_frames* F, const orbm_windows* Q, c
     P.init = init_obs; P.assign_out = assign_out; P.nmatches = nmatches; P.rounds = rounds;
     P.th_accept = th_accept; P.check_ori = check_ori;
     return launch<MODE_BEST>(P, F->nprob, (cudaStream_t)cuda_stream);
+}
+
+int orbm_search_for_initialization_batch(const orbm_frames* F1, const orbm_frames* F2, float* prev_matched, int* matches12,
+                                         int windowSize, float nnratio, int checkOri, int* nmatches, int* rounds, void* cuda_stream)
+{
+    MbParams P = {};
+    if (!fill_frames(P, F2) || !F1 || F1->nprob != F2->nprob || !F1->kps || !F1->desc || !F1->n || F1->kp_stride <= 0 ||
+        ((uintptr_t)F1->desc & 15) || !prev_matched || !matches12 || !nmatches)
+        return ORBX_E_ARG;
+    const int nprob = F2->nprob;
+    P.u_right = nullptr;
+    P.nq = F1->n; P.nq_stride = F1->kp_stride; P.kps1 = F1->kps; P.qdesc = (const uint32_t*)F1->desc;
+    P.prev = prev_matched; P.matches12 = matches12; P.nmatches = nmatches; P.rounds = rounds;
+    P.window = (float)windowSize; P.nnratio = nnratio; P.check_ori = checkOri;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const int dev = device_of(P.kps);
+    if (dev < 0 || device_of(F1->kps) != dev || device_of(prev_matched) != dev || device_of(matches12) != dev || device_of(nmatches) != dev) return ORBX_E_ARG;
+    DevGuard g;
+    if (cudaGetDevice(&g.prev) != cudaSuccess || cudaSetDevice(dev) != cudaSuccess) { cudaGetLastError(); return ORBX_E_CUDA; }
+    size_t smem = base_smem(P.n_bound, P.nq_stride, &P.sn_max, &P.nq_max);
+    if (smem > kSmemMax || P.nq_stride > MB_MAX_KP) return ORBX_E_ARG;
+    P.rec_in_smem = smem + (size_t)P.sn_max * 16 <= kSmemMax;
+    if (P.rec_in_smem) smem += (size_t)P.sn_max * 16;
+    P.desc_in_smem = P.rec_in_smem && smem + (size_t)P.sn_max * 32 <= kSmemMax;
+    if (P.desc_in_smem) smem += (size_t)P.sn_max * 32;
+    const size_t rec_bytes = P.rec_in_smem ? 0 : (size_t)nprob * P.kp_stride * sizeof(uint4);
+    const size_t desc_bytes = P.desc_in_smem ? 0 : (size_t)nprob * P.kp_stride * 32;
+    const size_t cl_bytes = (size_t)nprob * P.kp_stride * MB_CL * 4;
+    char* ws = nullptr;
+    if (cudaMallocAsync((void**)&ws, rec_bytes + desc_bytes + cl_bytes + 16, st) != cudaSuccess) { cudaGetLastError(); return ORBX_E_CUDA; }
+    P.rec = (uint4*)ws; P.sdesc = (uint32_t*)(ws + rec_bytes); P.cl = (uint32_t*)(ws + rec_bytes + desc_bytes);
+    cudaError_t e = cudaSuccess;
+    if (P.desc_in_smem) {
+        if (smem > 48 * 1024) e = cudaFuncSetAttribute(k_init_fixpoint<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
+        if (e == cudaSuccess) { k_init_fixpoint<0><<<nprob, MB_NT, smem, st>>>(P); e = cudaGetLastError(); }
+    } else if (P.rec_in_smem) {
+        if (smem > 48 * 1024) e = cudaFuncSetAttribute(k_init_fixpoint<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
+        if (e == cudaSuccess) { k_init_fixpoint<1><<<nprob, MB_NT, smem, st>>>(P); e = cudaGetLastError(); }
+    } else {
+        if (smem > 48 * 1024) e = cudaFuncSetAttribute(k_init_fixpoint<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
+        if (e == cudaSuccess) { k_init_fixpoint<2><<<nprob, MB_NT, smem, st>>>(P); e = cudaGetLastError(); }
+    }
+    cudaFreeAsync(ws, st);
+    if (e != cudaSuccess) { cudaGetLastError(); return ORBX_E_CUDA; }
+    return ORBX_OK;
 }
 
 } // extern "C"

@@ -289,3 +289,44 @@ def test_adversarial_problems_equal_oracle(scene, kind):
     ob.window_search_best_batch(F, dqb, _dev(np.int32([nq])), nq, d_assign, d_nm, 100, True, None, d_rounds)
     torch.cuda.synchronize()
     assert int(d_nm[0]) == wantb and (d_assign[0].cpu().numpy() == ref_assign).all(), (kind, int(d_nm[0]), wantb)
+
+
+def test_search_for_initialization_batch_equals_oracle(scene):
+    """Monocular initialisation as a batch: ordinary frame pairs (parallel rounds), a pile of identical keypoints (more
+    claimants per keypoint than the rounds keep: in-order walk inside the kernel), empty sides."""
+    import torch
+    O = Matcher("oracle")
+    bounds = (0.0, float(W), 0.0, float(H))
+    rng = np.random.default_rng(31)
+    k1, d1, k2, d2 = scene["kps"], scene["desc"], scene["k2"], scene["d2"]
+    pile1 = np.zeros(300, KP_DTYPE); pile1["x"] = 200 + rng.integers(0, 5, 300); pile1["y"] = 100 + rng.integers(0, 5, 300)
+    pile2 = np.zeros(120, KP_DTYPE); pile2["x"] = 200 + rng.integers(0, 5, 120); pile2["y"] = 100 + rng.integers(0, 5, 120)
+    pile1["angle"] = rng.random(300) * 360; pile2["angle"] = rng.random(120) * 360
+    pd2 = rng.integers(0, 256, (120, 32), dtype=np.uint8)                     # distinct targets ...
+    pd1 = pd2[rng.integers(0, 40, 300)].copy()                                # ... 300 queries aimed at 40 of them
+    pd1[:, 0] ^= rng.integers(0, 256, 300).astype(np.uint8); pd1[:, 1] ^= rng.integers(0, 16, 300).astype(np.uint8)
+    probs = [dict(k1=k1, d1=d1, k2=k2, d2=d2, prev=np.stack([k1["x"], k1["y"]], 1)),
+             dict(k1=k2[:1500], d1=d2[:1500], k2=k1, d2=d1, prev=np.stack([k2["x"][:1500] + 10, k2["y"][:1500] - 5], 1).astype(np.float32)),
+             dict(k1=pile1, d1=pd1, k2=pile2, d2=pd2, prev=np.stack([pile1["x"], pile1["y"]], 1)),
+             dict(k1=k1[:0], d1=d1[:0], k2=k2, d2=d2, prev=np.zeros((0, 2), np.float32)),
+             dict(k1=k1[:200], d1=d1[:200], k2=k2[:0], d2=d2[:0], prev=np.stack([k1["x"][:200], k1["y"][:200]], 1))]
+    cap = 2100
+    FA, keepA = _frames([dict(kps=p["k1"], desc=p["d1"]) for p in probs], bounds, cap, False)
+    FB, keepB = _frames([dict(kps=p["k2"], desc=p["d2"]) for p in probs], bounds, cap, False)
+    for nnratio, check_ori, window in ((0.9, True, 100), (0.6, True, 50), (0.9, False, 100)):
+        d_prev = _dev(_pad([np.ascontiguousarray(p["prev"], np.float32) for p in probs], cap))
+        d_m12 = torch.full((len(probs), cap), -7, dtype=torch.int32, device="cuda")
+        d_nm = torch.zeros(len(probs), dtype=torch.int32, device="cuda")
+        d_rounds = torch.zeros(len(probs), dtype=torch.int32, device="cuda")
+        ob.search_for_initialization_batch(FA, FB, d_prev, d_m12, d_nm, window, nnratio, check_ori, d_rounds)
+        torch.cuda.synchronize()
+        m12, nm, prev, rounds = d_m12.cpu().numpy(), d_nm.cpu().numpy(), d_prev.cpu().numpy(), d_rounds.cpu().numpy()
+        for i, p in enumerate(probs):
+            n1 = len(p["k1"])
+            if n1 and len(p["k2"]):
+                want = O.search_for_initialization(p["k1"], p["d1"], p["k2"], p["d2"], scene["scale"], bounds, p["prev"], window, nnratio, check_ori)
+            else:
+                want = (0, np.full(n1, -1, np.int32), np.ascontiguousarray(p["prev"], np.float32))
+            assert nm[i] == want[0], (i, nm[i], want[0], rounds[i])
+            assert (m12[i, :n1] == want[1]).all() and (prev[i, :n1] == want[2]).all(), i
+        assert nm[0] > 50 and rounds[0] > 0 and nm[2] > 5 and rounds[2] < 0, (nm, rounds)   # pair 0 by parallel rounds, the pile in order
