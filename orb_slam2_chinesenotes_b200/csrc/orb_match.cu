@@ -1,17 +1,17 @@
 // orb_match.cu -- Hamming matching kernels (sm_100a) and their C entry points.
 //   k_hamming_bf        ORBmatcher::DescriptorDistance over all pairs, src/ORBmatcher.cc:46-63, with the
 //                       best / second-best bookkeeping of :129-141 (strict <, first wins)
-//   k_grid_build        Frame::AssignFeaturesToGrid / PosInGrid           src/Frame.cc:243-259, 412-422
-//   k_window_candidates Frame::GetFeaturesInArea + DescriptorDistance for every query (parallel part)
-//   k_resolve_*         the order-dependent part of the three window matchers, one warp per problem:
-//                       SearchByProjection(Frame, MapPoints)  src/ORBmatcher.cc:73-157
-//                       SearchByProjection(Frame, Frame)      src/ORBmatcher.cc:160-300
-//                       SearchForInitialization               src/ORBmatcher.cc:1055-1180
-//                       incl. the rotation histogram and ComputeThreeMaxima (:1663-1707)
+//   single-problem entry points with HOST arrays for every matcher: they stage the inputs in a per-thread
+//                       arena and run ONE problem through the block-per-problem kernels of orb_match_batch.cu /
+//                       orb_match_bow.cu / orb_mappoint.cu
+//   k_grid_build, k_window_candidates, k_resolve_points / k_resolve_frame
+//                       the candidate-list form of the window matchers (src/ORBmatcher.cc:73-157, :160-300 and
+//                       the other best-candidate overloads): only for query sets too large for the shared memory
+//                       of the block-per-problem kernel (more than ~23 000 queries)
 //   (Frame::ComputeStereoMatches, src/Frame.cc:513-699: kernels in orb_stereo.cu, entry point here)
-// 256-bit descriptors as 8 x u32; distance = 8 x (LOP3 xor + POPC).  Integer pipe only.
+// 256-bit descriptors as 8 x u32.  Integer pipes only.
 //
-// Why two phases: a query's candidate set and distances do not depend on other queries, but the
+// The candidate-list form, why two phases: a query's candidate set and distances do not depend on other queries, but the
 // reference skips candidates that an EARLIER query already claimed (:115-117, :234-236, :1094), so the
 // choice of the best candidate must follow query order.  Phase 1 lists, per query and in the
 // reference's candidate order (grid column, grid row, insertion), every candidate that passes the
@@ -371,67 +371,6 @@ __global__ void __launch_bounds__(32) k_resolve_frame(const DevFrame F, const in
         for (int d = 16; d > 0; d >>= 1) dec += __shfl_xor_sync(0xffffffffu, dec, d);
         nmatches -= dec;
     }
-    if (lane == 0) *nmatches_out = nmatches;
-}
-
-// ------------------------------------------------------------------------------ phase 2: monocular initialisation
-// src/ORBmatcher.cc:1071-1177.  Queries = F1 keypoints (all of them; octave > 0 are invalid).
-__global__ void __launch_bounds__(32) k_resolve_init(const DevFrame F2, const int n1, const WinQuery* __restrict__ queries,
-                                                    const uint32_t* __restrict__ list, const int* __restrict__ count, const int cap,
-                                                    const float* __restrict__ angle1, int* __restrict__ matched_dist /* [n2] */,
-                                                    int* __restrict__ matches21 /* [n2] */, int* __restrict__ matches12 /* [n1] */,
-                                                    const float nnratio, const int check_ori, int* __restrict__ hist_entry, int* __restrict__ hist_bin,
-                                                    float* __restrict__ prev_matched, int* __restrict__ nmatches_out)
-{
-    __shared__ int sizes[HISTO_LENGTH];
-    const int lane = threadIdx.x;
-    if (lane < HISTO_LENGTH) sizes[lane] = 0;
-    __syncwarp();
-    int nmatches = 0, nh = 0;
-    for (int i1 = 0; i1 < n1; ++i1) {
-        const int n = queries[i1].valid ? count[i1] : 0;
-        if (n == 0) continue;
-        const uint32_t* lst = list + (size_t)i1 * cap;
-        uint32_t k1, k2;
-        warp_top2(lst, n, lane, [&](int idx, int dist) { return !(matched_dist[idx] <= dist); }, k1, k2);   // :1094
-        if (k1 == 0xffffffffu) continue;
-        const int bestDist = (int)(k1 >> 20), bestIdx2 = (int)(lst[k1 & 0xfffffu] & 0xffffu);
-        // INT_MAX second distance when there is none: (float)INT_MAX * nnratio is huge, the test passes
-        const float second = k2 == 0xffffffffu ? 2147483648.0f : (float)(int)(k2 >> 20);
-        if (bestDist <= TH_LOW && (float)bestDist < __fmul_rn(second, nnratio)) {                // :1109-1112
-            __syncwarp();
-            const int old = matches21[bestIdx2];
-            if (old >= 0) --nmatches;                                                             // :1115-1119
-            __syncwarp();
-            if (lane == 0) {
-                if (old >= 0) matches12[old] = -1;
-                matches12[i1] = bestIdx2; matches21[bestIdx2] = i1; matched_dist[bestIdx2] = bestDist;
-                if (check_ori) {
-                    const int bin = rot_bin(angle1[i1], F2.kps[bestIdx2].angle);
-                    hist_entry[nh] = i1; hist_bin[nh] = bin; sizes[bin] += 1;
-                }
-            }
-            __syncwarp();
-            ++nmatches; ++nh;
-        }
-    }
-    if (check_ori) {
-        int i1, i2, i3;
-        three_maxima(sizes, i1, i2, i3);
-        int dec = 0;
-        for (int e = lane; e < nh; e += 32) {
-            const int b = hist_bin[e];
-            if (b != i1 && b != i2 && b != i3) {
-                const int idx1 = hist_entry[e];
-                if (matches12[idx1] >= 0) { matches12[idx1] = -1; ++dec; }                        // :1163-1167 (an index is pushed at most once)
-            }
-        }
-        for (int d = 16; d > 0; d >>= 1) dec += __shfl_xor_sync(0xffffffffu, dec, d);
-        nmatches -= dec;
-    }
-    __syncwarp();
-    for (int i = lane; i < n1; i += 32)                                                           // :1175-1177
-        if (matches12[i] >= 0) { prev_matched[2 * i] = F2.kps[matches12[i]].x; prev_matched[2 * i + 1] = F2.kps[matches12[i]].y; }
     if (lane == 0) *nmatches_out = nmatches;
 }
 
@@ -888,7 +827,7 @@ int orbm_search_for_initialization(const orbm_frame* F1, const orbm_frame* F2, f
     for (int i = 0; i < n1; ++i) matches12[i] = -1;
     if (n1 == 0 || n2 == 0) return ORBX_OK;
     Scratch S;
-    if (n1 <= MAX_KP && orb_match_batch_fits(n2, n1)) {
+    if (n1 <= MAX_KP && n2 <= MAX_KP && orb_match_batch_fits(n2, n1)) {   // always true up to 8192 x 8192
         // one launch of the block-per-problem kernel (orb_match_batch.cu k_init_fixpoint)
         OneFrame O1, O2;
         if (!one_frame(S, F1, &O1) || !one_frame(S, F2, &O2)) return S.ok ? ORBX_E_ARG : ORBX_E_CUDA;
@@ -903,39 +842,7 @@ int orbm_search_for_initialization(const orbm_frame* F1, const orbm_frame* F2, f
         CKM(cudaMemcpy(nmatches, d_nm, 4, cudaMemcpyDeviceToHost));
         return *nmatches < 0 ? ORBX_E_ARG : ORBX_OK;
     }
-    DevFrame D2;
-    if (!make_frame(S, F2, &D2)) return S.ok ? ORBX_E_ARG : ORBX_E_CUDA;
-    std::vector<WinQuery> hq((size_t)n1);
-    std::vector<float> h_angle((size_t)n1);
-    for (int i = 0; i < n1; ++i) {
-        WinQuery& Q = hq[(size_t)i];
-        h_angle[(size_t)i] = F1->kps[i].angle;
-        const int level1 = F1->kps[i].octave;
-        Q.valid = !(level1 > 0);                                                // :1075
-        Q.u = prev_matched[2 * i]; Q.v = prev_matched[2 * i + 1]; Q.r = (float)windowSize;
-        Q.min_level = level1; Q.max_level = level1; Q.ur = 0; Q.er_max = 3.0e38f;
-    }
-    DevFrame D2q = D2; D2q.u_right = nullptr;                                   // no right-image test in this matcher
-    WinQuery* dq; uint32_t* list; int* count; int cap;
-    int rc = run_candidates(S, D2q, hq, F1->desc, n1, &dq, &list, &count, &cap);
-    if (rc) return rc;
-    std::vector<int> h_md((size_t)n2, 2147483647), h_m21((size_t)n2, -1);
-    float* d_angle = S.up(h_angle.data(), (size_t)n1);
-    int* d_md = S.up(h_md.data(), (size_t)n2);
-    int* d_m21 = S.up(h_m21.data(), (size_t)n2);
-    int* d_m12 = S.up(matches12, (size_t)n1);
-    float* d_prev = S.up(prev_matched, (size_t)n1 * 2);
-    int* d_he = (int*)S.alloc(sizeof(int) * (size_t)n1);
-    int* d_hb = (int*)S.alloc(sizeof(int) * (size_t)n1);
-    int* d_nm = (int*)S.alloc(4);
-    if (!S.ok) return ORBX_E_CUDA;
-    if (!S.flush()) return ORBX_E_CUDA;
-    k_resolve_init<<<1, 32>>>(D2, n1, dq, list, count, cap, d_angle, d_md, d_m21, d_m12, nnratio, checkOri, d_he, d_hb, d_prev, d_nm);
-    CKM(cudaGetLastError());
-    CKM(cudaMemcpy(matches12, d_m12, sizeof(int) * (size_t)n1, cudaMemcpyDeviceToHost));
-    CKM(cudaMemcpy(prev_matched, d_prev, sizeof(float) * (size_t)n1 * 2, cudaMemcpyDeviceToHost));
-    CKM(cudaMemcpy(nmatches, d_nm, 4, cudaMemcpyDeviceToHost));
-    return ORBX_OK;
+    return ORBX_E_ARG;     // more than 8192 keypoints on a side
 }
 
 int orbm_stereo_matches(orbx_ctx* ex_left, int frame_l, orbx_ctx* ex_right, int frame_r,

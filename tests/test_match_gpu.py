@@ -315,3 +315,27 @@ def test_matcher_entry_points_are_reentrant(scene):
     for t in threads:
         t.join()
     assert not errors, errors[:3]
+
+
+def test_very_large_best_only_query_set_takes_the_list_path(scene):
+    """orbm_window_search_best with more queries than the block-per-problem kernel holds: candidate lists + in-order
+    resolve (k_window_candidates / k_resolve_frame), same results as the oracle."""
+    import ctypes as C
+    rng = np.random.default_rng(5)
+    k, d = scene["k2"][:500].copy(), scene["d2"][:500].copy()
+    n, nq = len(k), 30000
+    tgt = rng.integers(0, n, nq)
+    uvr = np.stack([k["x"][tgt] + rng.normal(0, 3, nq), k["y"][tgt] + rng.normal(0, 3, nq), rng.choice([4.0, 12.0], nq)], 1).astype(np.float32)
+    minl = np.full(nq, -1, np.int32); maxl = np.full(nq, -1, np.int32)
+    qd = d[tgt].copy(); qd[:, :2] ^= rng.integers(0, 256, (nq, 2), dtype=np.uint8)
+    q_angle = ((k["angle"][tgt] + rng.normal(0, 5, nq)) % 360).astype(np.float32)
+    q_obs = (rng.random(nq) < 0.5).astype(np.int32)
+    O = oracle()
+    vp, ci, cf = C.c_void_p, C.c_int, C.c_float
+    O.orbo_window_search_best.argtypes = [ci, vp, vp, vp] + [cf] * 4 + [ci] + [vp] * 11 + [ci, ci]
+    p = lambda a: None if a is None else a.ctypes.data
+    ref_assign = np.zeros(n, np.int32)
+    nm = O.orbo_window_search_best(n, p(k), p(d), None, *BOUNDS, nq, p(uvr), p(minl), p(maxl), None, None, None, p(qd), p(q_angle), p(q_obs), None,
+                                   p(ref_assign), 100, 1)
+    g_nm, g_assign = ob.window_search_best(ob.FrameView(k, d, BOUNDS), uvr, minl, maxl, qd, 100, True, q_angle=q_angle, q_obs=q_obs)
+    assert g_nm == nm and nm > 100 and (g_assign == ref_assign).all()
