@@ -701,6 +701,23 @@ def run_ours(args, rank, world, local_rank):
         v, kind, what = cpu_workload_frames_per_s(args.workload, sample, nf, cores)
         cpu = {"value": v, "unit": "frames/s", "cores": cores, "kind": kind,
                "sample": f"first {ns} frames of the step's batch, {what}"}
+    # ---- latency of ONE call with host buffers (what a real-time tracker sees per frame), rank 0 only
+    latency = None
+    if world == 1:
+        one = h_frames[:2].numpy()
+        for _ in range(5):
+            ex(one[0])
+        t0 = time.perf_counter()
+        for _ in range(30):
+            ex(one[0])
+        latency = {"extract_1_frame_ms": 1e3 * (time.perf_counter() - t0) / 30, "note": "operator() on one frame, host buffers, ctypes overhead included"}
+        if stereo:
+            for _ in range(3):
+                ex.extract_stereo_batch(one, CAM["bf"], CAM["fx"])
+            t0 = time.perf_counter()
+            for _ in range(30):
+                ex.extract_stereo_batch(one, CAM["bf"], CAM["fx"])
+            latency["stereo_pair_ms"] = 1e3 * (time.perf_counter() - t0) / 30
     chunk = args.chunk or 512                      # device-resident default of orb_capi.cu (the timed `value` path)
     chunks = (batch + chunk - 1) // chunk
     cfg_stereo = {}
@@ -724,7 +741,7 @@ def run_ours(args, rank, world, local_rank):
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": (LEVELS - 1 + 4 + (3 if stereo else 0)) * chunks * args.steps,
         "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "hamming_bf": hamming,
-        "window_match": window, "mappoint_side": mappoint,
+        "window_match": window, "mappoint_side": mappoint, "latency": latency,
     }))
     if dist is not None:
         dist.destroy_process_group()
