@@ -374,12 +374,13 @@ def bench_window_match(dev, d_kps, d_desc, d_n, cap, w, h, scale, nprob=512, nq=
     F1 = ob.FrameView(kp0, np.ascontiguousarray(desc[0, :n0].cpu().numpy()), bounds)
     q1 = {k: np.ascontiguousarray(v[0].cpu().numpy()) for k, v in q.items()}
     M1 = ob.ORBmatcher(nnratio, True)
-    for _ in range(5):
+    nrep = 1 if os.environ.get("ORB_BENCH_PROFILE") else 30            # under ncu: one launch
+    for _ in range(min(5, nrep)):
         M1.SearchByProjection(F1, scale, q1, th)
     t0 = time.perf_counter()
-    for _ in range(30):
+    for _ in range(nrep):
         M1.SearchByProjection(F1, scale, q1, th)
-    out["single_call_ms"] = 1e3 * (time.perf_counter() - t0) / 30
+    out["single_call_ms"] = 1e3 * (time.perf_counter() - t0) / nrep
     if cpu:
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import oracle_lib
