@@ -189,13 +189,26 @@ __device__ __forceinline__ void fast_strip_body(const OrbPlan& plan, const OrbBa
         if (gp < rgp) {
             const uint8_t* rowp = src + (size_t)(y0 + gp) * pitch + x0;
             uint32_t dst = (uint32_t)__cvta_generic_to_shared(raw + gp * RW + jp);
-            for (int r = gp; r < th; r += rgp, rowp += (size_t)rgp * pitch, dst += 4u * rgp * RW) {
+            if ((pitch & 3) == 0) {
+                // every row starts at the same offset inside its word (all pyramid levels, and level 0 when the caller's
+                // pitch is a multiple of 4): source word and byte count are set up once, the loop only steps
                 const uintptr_t a = (uintptr_t)rowp;
                 const int s = (int)(a & 3);
                 const uint8_t* q = (const uint8_t*)(a - s) + 4 * jp;
-                int n = 4;
-                if (!fetch_full) n = min(max(w - (x0 - s + 4 * jp), 0), 4);
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(q), "r"(n) : "memory");
+                const int n = fetch_full ? 4 : min(max(w - (x0 - s + 4 * jp), 0), 4);
+                const size_t qstep = (size_t)rgp * pitch;
+                const uint32_t dstep4 = 4u * rgp * RW;
+                for (int r = gp; r < th; r += rgp, q += qstep, dst += dstep4)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(q), "r"(n) : "memory");
+            } else {
+                for (int r = gp; r < th; r += rgp, rowp += (size_t)rgp * pitch, dst += 4u * rgp * RW) {
+                    const uintptr_t a = (uintptr_t)rowp;
+                    const int s = (int)(a & 3);
+                    const uint8_t* q = (const uint8_t*)(a - s) + 4 * jp;
+                    int n = 4;
+                    if (!fetch_full) n = min(max(w - (x0 - s + 4 * jp), 0), 4);
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(q), "r"(n) : "memory");
+                }
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
