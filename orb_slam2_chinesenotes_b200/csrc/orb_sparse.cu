@@ -355,7 +355,9 @@ __device__ __forceinline__ void orb_sincosf(const float y, float* sn, float* cs)
     *cs = orb_sincos_poly(xs, x2, neg, n ^ 1);
 }
 
-#define DESC_NT 256
+#ifndef DESC_NT
+#define DESC_NT 128
+#endif
 // One warp per output keypoint.  Lanes are the 31 columns of the orientation patch, then the
 // 32 descriptor bytes (16 rotated taps each).
 __global__ void __launch_bounds__(DESC_NT) k_describe(const __grid_constant__ OrbPlan plan, const OrbBatch io)
