@@ -35,7 +35,9 @@ __device__ __forceinline__ uint32_t dp2a_hi(const uint32_t a, const uint32_t b, 
 //           (a0,a1) pair as the 16-bit operand;
 //   vertical pass: consecutive destination rows share a source row four times out of five, so the two H rows
 //           live in registers and only the new one is computed; (b*h)>>16 is IMAD.HI with b pre-shifted.
-#define PYR_NT 128
+#ifndef PYR_NT
+#define PYR_NT 64        // measured per 1024 frames: 32 threads 1.82 ms, 64 1.60, 128 1.63, 256 2.00
+#endif
 #define PYR_TW 128
 #define PYR_TH 64
 
@@ -177,7 +179,9 @@ __global__ void __launch_bounds__(256) k_pyr_resize_generic(const __grid_constan
 //           four IDP.2A (two 16-bit sums x two 8-bit weights + accumulate, rounding constant folded in);
 //   store   one 32-bit word per lane and row.
 // (Column-then-row equals row-then-column: the sums are exact integers.)
-#define BLUR_NT 128
+#ifndef BLUR_NT
+#define BLUR_NT 32       // one warp per block; measured per 1024 frames: 32 threads 1.33 ms, 64 1.52, 128 1.54, 256 1.66
+#endif
 
 __global__ void __launch_bounds__(BLUR_NT) k_blur7(const __grid_constant__ OrbPlan plan, const OrbBatch io)
 {
