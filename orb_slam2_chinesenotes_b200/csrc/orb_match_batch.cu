@@ -41,7 +41,9 @@
 #define HISTO_LENGTH 30 // :39
 #define MB_MAX_KP 8192
 #define MB_MAX_LEVELS 32
+#ifndef MB_NT
 #define MB_NT 1024
+#endif
 #define MB_NONE 0xffffffffu
 #define MB_CL 6            // claimants per keypoint kept for the parallel rounds of SearchForInitialization
 #define TH_LOW 50         // src/ORBmatcher.cc:38

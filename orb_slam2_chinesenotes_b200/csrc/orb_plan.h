@@ -20,7 +20,9 @@
 #define ORB_PATCH 31         // PATCH_SIZE, :72
 #define ORB_BORDER0 16       // minBorderX = EDGE_THRESHOLD-3, :804
 #define ORB_MAX_DIM 4128     // candidate coordinates are packed in 12 bits (border frame)
+#ifndef ORB_FAST_STRIP
 #define ORB_FAST_STRIP 4     // cells per FAST block (orb_fast.cu); the block has 32 threads per cell
+#endif
 #define ORB_FAST_WC_STATIC 32    // widest cell handled with compile-time tile geometry
 #define ORB_FAST_WPC_STATIC (((ORB_FAST_STRIP * ORB_FAST_WC_STATIC + 9) / 2 + 2) & ~1)   // orb_fast_wpc(ORB_FAST_STRIP, 32)
 #define ORB_FAST_RW_STATIC (((ORB_FAST_STRIP * ORB_FAST_WC_STATIC + 15) >> 2) + 1)            // orb_fast_rw(ORB_FAST_STRIP, 32)
