@@ -40,6 +40,9 @@
 #define ORB_FAST_TPC 32      // threads per cell of the strip
 #endif
 #define FAST_NT (ORB_FAST_TPC * ORB_FAST_STRIP)
+#ifndef ORB_FAST_FULLCOL
+#define ORB_FAST_FULLCOL 64   // frames per launch from which a block walks a whole strip column
+#endif
 
 __device__ __forceinline__ uint32_t hmin2(const uint32_t a, const uint32_t b)
 {
@@ -384,7 +387,7 @@ cudaError_t orb_launch_fast(const OrbPlan& plan, const OrbBatch& io, int batch, 
     int maxrows = 1;
     for (int l = 0; l < plan.nlevels; ++l) if (plan.lv[l].ncy > maxrows) maxrows = plan.lv[l].ncy;
     FastGrid fg;
-    fg.rows_per_block = batch >= 64 ? maxrows : batch >= 16 ? 4 : 1;
+    fg.rows_per_block = batch >= ORB_FAST_FULLCOL ? maxrows : batch >= 16 ? 4 : 1;
     int n = 0;
     for (int l = 0; l < plan.nlevels; ++l) {
         fg.first[l] = n;

@@ -27,7 +27,9 @@
 #define ORB_FAST_WPC_STATIC (((ORB_FAST_STRIP * ORB_FAST_WC_STATIC + 9) / 2 + 2) & ~1)   // orb_fast_wpc(ORB_FAST_STRIP, 32)
 #define ORB_FAST_RW_STATIC (((ORB_FAST_STRIP * ORB_FAST_WC_STATIC + 15) >> 2) + 1)            // orb_fast_rw(ORB_FAST_STRIP, 32)
 #define ORB_BLUR_TW 120      // blur tile (orb_dense.cu): a warp makes 120 output pixels per row (30 lanes x 4 + 2 apron lanes)
+#ifndef ORB_BLUR_TH
 #define ORB_BLUR_TH 64       // ... and walks down this many rows
+#endif
 
 struct OrbLevel {
     int w, h;               // level image size
