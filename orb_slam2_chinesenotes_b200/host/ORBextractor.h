@@ -1,96 +1,67 @@
-// ORBextractor.h -- drop-in replacement of the reference's include/ORBextractor.h.
+// ORBextractor.h -- the class a SLAM build includes INSTEAD of the reference's include/ORBextractor.h.
 //
-// Same class, same public interface (constructor, operator(), Get* accessors, public
-// mvImagePyramid: reference include/ORBextractor.h:47-111); the bodies forward to the B200 library
-// through the C ABI of include/orb_b200.h.  A SLAM build replaces the reference's ORBextractor.h/.cc
-// with this pair and links liborb_b200.so; nothing else changes.
-// There is no CPU fallback: construction throws std::runtime_error when no CUDA device is usable.
+// The interface is the reference's (include/ORBextractor.h:47-111: constructor, operator(), the six Get*
+// accessors, the public mvImagePyramid) because Frame.cc and Tracking.cc are compiled against it unchanged; every
+// body forwards to liborb_b200.so through the C ABI of include/orb_b200.h (ORBextractor.cc next to this file).
+// INTEGRATION.md has the recipe.  No CPU fallback exists: the constructor throws std::runtime_error when no CUDA
+// device can be used.
 #ifndef ORBEXTRACTOR_H
 #define ORBEXTRACTOR_H
 
-#include <list>
 #include <vector>
+
 #include <opencv2/core/core.hpp>
 #include <opencv2/features2d/features2d.hpp>
 
-struct orbx_ctx;
+struct orbx_ctx;   // include/orb_b200.h
 
-namespace ORB_SLAM2
-{
+namespace ORB_SLAM2 {
 
-class ORBextractor
-{
+class ORBextractor {
 public:
+    enum { HARRIS_SCORE = 0, FAST_SCORE = 1 };
 
-    enum {HARRIS_SCORE=0, FAST_SCORE=1 };
-
-    ORBextractor(int nfeatures, float scaleFactor, int nlevels,
-                 int iniThFAST, int minThFAST);
-
+    ORBextractor(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST);
     ~ORBextractor();
 
-    // Compute the ORB features and descriptors on an image (mask is ignored, as in the reference).
-    void operator()( cv::InputArray image, cv::InputArray mask,
-      std::vector<cv::KeyPoint>& keypoints,
-      cv::OutputArray descriptors);
+    // Keypoints and 32-byte descriptors of an 8-bit single-channel image.  As in the reference the mask is ignored,
+    // an empty image leaves the outputs untouched and zero keypoints release the descriptor matrix.
+    void operator()(cv::InputArray image, cv::InputArray mask, std::vector<cv::KeyPoint>& keypoints, cv::OutputArray descriptors);
 
-    int inline GetLevels(){
-        return nlevels;}
+    // Pyramid geometry, copied out by every Frame constructor (src/Frame.cc:73-79).
+    int GetLevels() { return nlevels; }
+    float GetScaleFactor() { return (float)scaleFactor; }
+    std::vector<float> GetScaleFactors() { return mvScaleFactor; }
+    std::vector<float> GetInverseScaleFactors() { return mvInvScaleFactor; }
+    std::vector<float> GetScaleSigmaSquares() { return mvLevelSigma2; }
+    std::vector<float> GetInverseScaleSigmaSquares() { return mvInvLevelSigma2; }
 
-    float inline GetScaleFactor(){
-        return scaleFactor;}
-
-    std::vector<float> inline GetScaleFactors(){
-        return mvScaleFactor;
-    }
-
-    std::vector<float> inline GetInverseScaleFactors(){
-        return mvInvScaleFactor;
-    }
-
-    std::vector<float> inline GetScaleSigmaSquares(){
-        return mvLevelSigma2;
-    }
-
-    std::vector<float> inline GetInverseScaleSigmaSquares(){
-        return mvInvLevelSigma2;
-    }
-
-    // Filled after every call when pyramid download is on (default): level ROIs inside
-    // REFLECT_101-padded buffers, exactly what Frame::ComputeStereoMatches reads (src/Frame.cc:520,611-633).
+    // Levels of the last image as ROIs inside their REFLECT_101-padded buffers, which is how
+    // Frame::ComputeStereoMatches reads them (src/Frame.cc:520, 611-633).  Refreshed by operator() unless the
+    // download is switched off below.
     std::vector<cv::Mat> mvImagePyramid;
 
-    // --- additions (not in the reference) ---------------------------------------------------------
-    // CUDA ordinal for extractors constructed afterwards (default 0, or $ORB_B200_DEVICE).
-    static void SetDevice(int device);
-    // Skip the device->host copy of the pyramid (use orbm_stereo_matches on the device instead).
-    void SetPyramidDownload(bool on) { mbDownloadPyramid = on; }
-    // The C-ABI context (for orbm_stereo_matches and batched calls).
-    orbx_ctx* Context() { return mpCtx; }
+    // ---- not in the reference ------------------------------------------------------------------------------
+    static void SetDevice(int device);                      // CUDA ordinal of extractors built afterwards (default 0 or $ORB_B200_DEVICE)
+    void SetPyramidDownload(bool on) { mbDownloadPyramid = on; }   // off: the pyramid stays on the GPU (orbm_stereo_matches reads it there)
+    orbx_ctx* Context() { return mpCtx; }                   // the C-ABI context, for the batched / stereo entry points
 
 protected:
-
+    // the reference's members (include/ORBextractor.h:98-111); scaleFactor really is a double there
     int nfeatures;
     double scaleFactor;
-    int nlevels;
-    int iniThFAST;
-    int minThFAST;
-
+    int nlevels, iniThFAST, minThFAST;
     std::vector<int> mnFeaturesPerLevel;
-
-    std::vector<float> mvScaleFactor;
-    std::vector<float> mvInvScaleFactor;
-    std::vector<float> mvLevelSigma2;
-    std::vector<float> mvInvLevelSigma2;
+    std::vector<float> mvScaleFactor, mvInvScaleFactor, mvLevelSigma2, mvInvLevelSigma2;
 
     orbx_ctx* mpCtx;
     bool mbDownloadPyramid;
 
 private:
-    ORBextractor(const ORBextractor&);
+    ORBextractor(const ORBextractor&);              // one CUDA context per instance: not copyable
     ORBextractor& operator=(const ORBextractor&);
 };
 
-} //namespace ORB_SLAM
+}  // namespace ORB_SLAM2
 
 #endif
