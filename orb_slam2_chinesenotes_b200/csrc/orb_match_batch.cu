@@ -4,6 +4,7 @@
 //   MODE_POINTS  ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th)   src/ORBmatcher.cc:73-157
 //   MODE_BEST    the best-candidate-only overloads once the caller has projected its points
 //                (motion model :160-300, relocalisation :303-431, loop closing :434-549)
+//   k_init_fixpoint   ORBmatcher::SearchForInitialization                                :1055-1180
 //   + Frame::AssignFeaturesToGrid / GetFeaturesInArea (src/Frame.cc:243-259, 348-409) and the rotation
 //     histogram with ComputeThreeMaxima (src/ORBmatcher.cc:1663-1707)
 //
