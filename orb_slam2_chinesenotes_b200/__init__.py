@@ -13,7 +13,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "liborb_b200.so")
+LIB_PATH = os.environ.get("ORB_B200_LIB") or os.path.join(_HERE, "lib", "liborb_b200.so")   # override: a differently tuned build
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
 KP_DTYPE = np.dtype([("x", "f4"), ("y", "f4"), ("size", "f4"), ("angle", "f4"), ("response", "f4"),

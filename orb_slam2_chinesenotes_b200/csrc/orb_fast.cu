@@ -63,7 +63,7 @@ __device__ __forceinline__ uint32_t hmax2(const uint32_t a, const uint32_t b)
 // exact, because the operands are integers 0..255 held as fp16 denormals (multiples of 2^-24 below 2^-14:
 // sums and differences are representable, nothing rounds, f16 arithmetic keeps subnormals).
 #ifndef ORB_FAST_FMA
-#define ORB_FAST_FMA 3
+#define ORB_FAST_FMA 2      // bit 0: the 8 first-stage pairs, bit 1: the 8 lo/hi pairs on the FMA pipe; per 1024 frames: 0 5.24 ms, 1 5.03, 2 4.98, 3 5.09
 #endif
 #ifndef ORB_FAST_UNROLL
 #define ORB_FAST_UNROLL 2
