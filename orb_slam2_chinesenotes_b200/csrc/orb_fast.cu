@@ -2,22 +2,34 @@
 // Replaces the cell loop of ORBextractor::ComputeKeyPointsOctTree, src/ORBextractor.cc:826-875
 // (cv::FAST(cell, kps, iniThFAST, true), and again with minThFAST when that returns nothing).
 //
-// One block per STRIP: a run of up to ORB_FAST_STRIP horizontally adjacent 30-px cells of one
-// cell row.  The kernel is bound by the integer/min-max issue rate (tools/ubench_pipes.cu), so
-// it is organised around instructions per pixel:
-//   * the strip is staged into shared memory as one image (evaluated rectangle + 3-px ring
-//     apron), widened ONCE to 16 bits per pixel and stored TWICE: copy A holds pixel pairs that
-//     start on an even column, copy B pairs that start on an odd column.  Each of the 16 ring
-//     positions of a horizontally adjacent PIXEL PAIR is then one aligned 32-bit shared load of
-//     a ready-made 16x2 operand -- no funnel shifts or byte permutes in the scoring loop;
-//   * the score network works on the 16x2 operands with the full-rate 2-input half2 min/max
-//     (VHMNMX; the values 0..255 are positive fp16 denormals, whose order is the integer
-//     order), 47 operations per polarity (below) instead of the 80 of a sliding 3-input
-//     network, with no data-dependent branch;
-//   * a thread owns one pixel-pair column of the strip and walks down the rows, so index math
-//     is paid per column, not per pixel;
-//   * NMS reads a 16x2 score map with the same packing (3 rows x 3 words, column maxima,
-//     two permutes for the left/right neighbours, one carry-free packed compare).
+// Measured facts the design rests on (tools/ubench_fast.cu, profiles/r02_ubench_fast.txt): HMNMX2, the 3-input
+// VHMNMX, PRMT, LOP3, IADD3 (ALU pipe) and HADD2 / HFMA2 (FMA pipe) all issue at ~1.9 warp instructions per clock
+// and SM, a stream that mixes the two pipes tops out at ~2.9, so the kernel is bound by INSTRUCTIONS, mostly those
+// of the ALU pipe.  Everything here is organised to issue fewer of them per pixel:
+//
+//   * ONE WARP = ONE BAND: up to 64 evaluated columns (one or two 30-px cells) walked down their cell rows by a
+//     warp that shares nothing with any other warp -- no block barrier anywhere, only __syncwarp and the warp's
+//     own mbarrier.  A lane owns the pixel pair (2p, 2p+1) of the band, whatever cell each pixel lies in.
+//   * DATA PATH: lane r of the warp issues one bulk asynchronous copy (cp.async.bulk, the TMA unit) per image row
+//     of the next chunk into the warp's raw buffer and the warp's mbarrier counts the bytes; the copy of chunk
+//     k+1 is in flight while chunk k is scored.  Rows are fetched from the 16-byte aligned address at or below
+//     their first pixel, so any pitch and any level works (level 0 is the caller's image, untouched).
+//   * WIDENING on the LSU and FMA pipes: the raw bytes are re-read one by one (LDS.U8 has no alignment rule, so
+//     no funnel shifts) and paired with one IMAD each into the two 16-bit copies of the tile -- copy A holds the
+//     pixel pairs that start on an even tile column, copy B those that start on an odd one -- so every ring
+//     operand of a pixel pair is one aligned, bank-conflict-free 32-bit load (consecutive lanes, consecutive words).
+//   * the score network runs on the 16x2 operands with half2 min/max (the values 0..255 are positive fp16
+//     denormals, whose order is the integer order): 36 operations per polarity, the 3-input ones fused by ptxas
+//     into VHMNMX; min/max PAIRS of the same two operands can be moved to the idle FMA pipe (ORB_FAST_FMA);
+//   * the score is finished on the FMA pipe in signed fp16 arithmetic (exact: all values are integers below 2048
+//     in units of 2^-24), masked and biased by one HFMA2.RELU;
+//   * NMS needs no score map: the scores of the last three rows of the lane's column pair live in registers, the
+//     neighbouring columns come from two shuffles, cell and band borders are folded into the two PRMT selectors;
+//   * a survivor is RECORDED, not handled, in the row loop: of the four pixels of a lane's row pair at most one
+//     can be a strict 3x3 maximum, so one 16-bit code per row pair (sign = column, binade = row, value = score)
+//     goes to a per-warp stash with FMA-pipe arithmetic; survivor counts per column accumulate the same way;
+//   * per cell row the warp decides the cut-off of each cell (below), adds its total to the frame's candidate
+//     counter with ONE atomic and lets every lane write its own survivors.
 //
 // Score (OpenCV cornerScore<16>, threshold independent), d[k] = v - ring[k]:
 //     score = max( max_k min_{m<9} d[k+m], max_k min_{m<9} -d[k+m] ) - 1
@@ -27,7 +39,6 @@
 // Every 9-arc is an 8-arc starting at an EVEN position plus one of the two ring values next to
 // it, and min/max distribute over each other, so with F[j] = min(E[2j..2j+7]):
 //     M1 = max_j min( F[j], max(E[2j-1], E[2j+8]) )                     (indices mod 16)
-// F comes from pair minima B[j] = min(E[2j],E[2j+1]) by doubling: 8 + 8 + 8 ops, then 8 + 8 + 7.
 // A pixel is a FAST corner at threshold t iff score >= t.  NMS is the strict 3x3 maximum of the
 // score map INSIDE the cell (FAST runs on the cropped cell image, so neighbours outside the
 // cell's evaluated rectangle count as 0); both thresholds read the same map, hence the
@@ -35,52 +46,58 @@
 // reaches it, else minThFAST.
 #include "orb_device.cuh"
 #include "orb_launch.h"
+#include <cuda_fp16.h>
 
-#ifndef ORB_FAST_TPC
-#define ORB_FAST_TPC 32      // threads per cell of the strip
+#ifndef ORB_FAST_R
+#define ORB_FAST_R 16         // evaluated rows per chunk (even); the tile holds R + 6 rows
 #endif
-#define FAST_NT (ORB_FAST_TPC * ORB_FAST_STRIP)
+#ifndef ORB_FAST_WPB
+#define ORB_FAST_WPB 2        // warps (bands) per block; the warps of a block share nothing
+#endif
+#ifndef ORB_FAST_FMA
+#define ORB_FAST_FMA 0x00ffu  // bit j: first-stage pair j, bit 8+j: lo/hi pair j computed on the FMA pipe
+#endif
 #ifndef ORB_FAST_FULLCOL
-#define ORB_FAST_FULLCOL 64   // frames per launch from which a block walks a whole strip column
+#define ORB_FAST_FULLCOL 64   // frames per launch from which a warp walks a whole band column
+#endif
+#ifndef ORB_FAST_MINBLK
+#define ORB_FAST_MINBLK 10    // resident blocks per SM the register allocation must allow
 #endif
 
-__device__ __forceinline__ uint32_t hmin2(const uint32_t a, const uint32_t b)
-{
-    uint32_t d;
-    asm("min.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
-    return d;
-}
-__device__ __forceinline__ uint32_t hmax2(const uint32_t a, const uint32_t b)
-{
-    uint32_t d;
-    asm("max.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
-    return d;
-}
+constexpr int kR = ORB_FAST_R;
+constexpr int kTileRows = kR + 6;
+constexpr int kCopyW = 36;                 // 32-bit words per copy of a tile row (72 pixels)
+constexpr int kRS = 2 * kCopyW;            // tile row: [copy A][copy B]
+constexpr int kRawPitch = 96;              // bytes per raw row: 15 (alignment) + 70 pixels, rounded up to 16
+constexpr int kNT = 32 * ORB_FAST_WPB;
+static_assert(kR % 2 == 0 && kR >= 2, "chunks hold whole row pairs");
+static_assert(kTileRows <= 32, "one lane per tile row issues the bulk copy");
 
-// The min/max network is bound by the ALU pipe (HMNMX2 issues at half the warp rate), while the FMA pipe idles.
-// Where a min AND a max of the same two operands are needed, the pair is computed on the FMA pipe instead:
+__device__ __forceinline__ uint32_t hmin2(const uint32_t a, const uint32_t b) { uint32_t d; asm("min.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+__device__ __forceinline__ uint32_t hmax2(const uint32_t a, const uint32_t b) { uint32_t d; asm("max.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+__device__ __forceinline__ uint32_t hadd2(const uint32_t a, const uint32_t b) { uint32_t d; asm("add.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+__device__ __forceinline__ uint32_t hsub2(const uint32_t a, const uint32_t b) { uint32_t d; asm("sub.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+__device__ __forceinline__ uint32_t hmul2(const uint32_t a, const uint32_t b) { uint32_t d; asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+__device__ __forceinline__ uint32_t hfma2(const uint32_t a, const uint32_t b, const uint32_t c) { uint32_t d; asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+__device__ __forceinline__ uint32_t hfma2_relu(const uint32_t a, const uint32_t b, const uint32_t c) { uint32_t d; asm("fma.rn.relu.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+__device__ __forceinline__ uint32_t hsetgt2(const uint32_t a, const uint32_t b) { uint32_t d; asm("set.gt.f16x2.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }   // 1.0 / 0.0 per lane
+__device__ __forceinline__ uint32_t hsetge2(const uint32_t a, const uint32_t b) { uint32_t d; asm("set.ge.f16x2.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+
+// Where a min AND a max of the same two operands are needed, the pair can be computed on the FMA pipe:
 //     r = relu(a - b) (HFMA2.RELU: b * -1 + a),  max = b + r,  min = a - r            (HADD2)
 // exact, because the operands are integers 0..255 held as fp16 denormals (multiples of 2^-24 below 2^-14:
 // sums and differences are representable, nothing rounds, f16 arithmetic keeps subnormals).
-#ifndef ORB_FAST_FMA
-#define ORB_FAST_FMA 2      // bit 0: the 8 first-stage pairs, bit 1: the 8 lo/hi pairs on the FMA pipe; per 1024 frames: 0 5.24 ms, 1 5.03, 2 4.98, 3 5.09
-#endif
-#ifndef ORB_FAST_UNROLL
-#define ORB_FAST_UNROLL 2
-#endif
-constexpr int kFastUnroll = ORB_FAST_UNROLL;
-__device__ __forceinline__ void hminmax_fma(const uint32_t a, const uint32_t b, uint32_t& mn, uint32_t& mx)
-{
-    uint32_t r;
-    asm("fma.rn.relu.f16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(b), "r"(0xbc00bc00u), "r"(a));
-    asm("add.rn.f16x2 %0, %1, %2;" : "=r"(mx) : "r"(b), "r"(r));
-    asm("sub.rn.f16x2 %0, %1, %2;" : "=r"(mn) : "r"(a), "r"(r));
-}
 template <bool FMA>
 __device__ __forceinline__ void hminmax(const uint32_t a, const uint32_t b, uint32_t& mn, uint32_t& mx)
 {
-    if (FMA) hminmax_fma(a, b, mn, mx);
-    else { mn = hmin2(a, b); mx = hmax2(a, b); }
+    if (FMA) {
+        const uint32_t r = hfma2_relu(b, 0xbc00bc00u, a);
+        mx = hadd2(b, r);
+        mn = hsub2(a, r);
+    } else {
+        mn = hmin2(a, b);
+        mx = hmax2(a, b);
+    }
 }
 
 // packed (M1, M2) of a pixel pair from its 16 ring operands
@@ -88,7 +105,10 @@ __device__ __forceinline__ void fast_network(const uint32_t* E, uint32_t& M1, ui
 {
     uint32_t Bn[8], Bx[8], Qn[8], Qx[8], Y[8], Z[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) hminmax<(ORB_FAST_FMA & 1) != 0>(E[2 * j], E[2 * j + 1], Bn[j], Bx[j]);
+    for (int j = 0; j < 8; ++j) {
+        if ((ORB_FAST_FMA >> j) & 1u) hminmax<true>(E[2 * j], E[2 * j + 1], Bn[j], Bx[j]);
+        else hminmax<false>(E[2 * j], E[2 * j + 1], Bn[j], Bx[j]);
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) { Qn[j] = hmin2(Bn[j], Bn[(j + 1) & 7]); Qx[j] = hmax2(Bx[j], Bx[(j + 1) & 7]); }
 #pragma unroll
@@ -96,7 +116,8 @@ __device__ __forceinline__ void fast_network(const uint32_t* E, uint32_t& M1, ui
         const uint32_t Fn = hmin2(Qn[j], Qn[(j + 2) & 7]);                 // min E[2j .. 2j+7]
         const uint32_t Fx = hmax2(Qx[j], Qx[(j + 2) & 7]);                 // max E[2j .. 2j+7]
         uint32_t ln, lx;
-        hminmax<(ORB_FAST_FMA & 2) != 0>(E[(2 * j + 15) & 15], E[(2 * j + 8) & 15], ln, lx);
+        if ((ORB_FAST_FMA >> (8 + j)) & 1u) hminmax<true>(E[(2 * j + 15) & 15], E[(2 * j + 8) & 15], ln, lx);
+        else hminmax<false>(E[(2 * j + 15) & 15], E[(2 * j + 8) & 15], ln, lx);
         Y[j] = hmin2(Fn, lx);
         Z[j] = hmax2(Fx, ln);
     }
@@ -110,280 +131,323 @@ __device__ __forceinline__ int fast_div(const int n, const int d)
     return __float2int_rz(__fmul_rn((float)n + 0.5f, __frcp_rn((float)d)));
 }
 
-// Which (level, strip column, cell rows) a block works on: filled per launch (rows_per_block follows the batch
-// size: whole strip columns for big batches, single cell rows when few frames must fill the GPU).
+// ---- mbarrier + bulk copy (one barrier per warp, arrival count 1)
+__device__ __forceinline__ void mbar_init(const uint32_t bar, const uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(const uint32_t bar, const uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(const uint32_t bar, const uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "W_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra W_%=;\n\t}"
+        ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(const uint32_t dst, const void* src, const uint32_t bytes, const uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// Which (level, band group, cell rows) a block works on: filled per launch (rows_per_block follows the batch
+// size: whole band columns for big batches, single cell rows when few frames must fill the GPU).
 struct FastGrid {
     int first[ORB_MAX_LEVELS + 1];   // first block of each level; [nlevels] = total
     int rows_per_block;
 };
 
-// Geometry of a strip's shared-memory images.  STATIC: compile-time strides for cells up to
-// ORB_FAST_WC_STATIC wide (all offsets of the scoring loop become immediates); otherwise run-time.
-//   tile row  = [copy A: WPC words][pad][copy B: WPC words][1] of the strip as ONE image (cells are contiguous,
-//               so nothing is staged twice); copy A word j = strip columns (2j, 2j+1), copy B word j = columns
-//               (2j+1, 2j+2); strip column 0 = first column of the first cell image.  Copy B starts OB words
-//               into the row with OB = 1 (mod 32): a warp spans two cells, and when wCell is odd its second
-//               cell reads the other copy -- this offset puts the two half-warps on disjoint banks.
-//   score row = 1 + ncs * SP words, SP = np + 1: pixel pair p (evaluated columns 2p, 2p+1) of cell c at word
-//               c*SP + p + 1; word c*SP is the zero apron between cells
-// Pixel pair p of cell c has its ring window starting at strip column t = c*wCell + 2p.  For even t the odd
-// ring offsets dx are words of copy A and the even ones words of copy B; for odd t the roles swap.  Either
-// way the words are a[(3+dx)/2] (dx odd) and b[(2+dx)/2] (dx even) from two per-column base pointers.
-// Everything that depends only on the strip column is set up once; the block then walks down its cell rows.
-template <bool STATIC>
-__device__ __forceinline__ void fast_strip_body(const OrbPlan& plan, const OrbBatch& io, uint32_t* smem, int* s_ctr, int* s_any,
-                                                const int frame, const int l, const int sx, const int ci0, const int ci1)
+// Per-warp shared memory: [mbarrier, 16 B][tile: kTileRows x kRS words][raw: kTileRows x kRawPitch bytes][stash:
+// (slots + 1) x 32 codes of 16 bits].
+//   tile row  = [copy A: 36 words][copy B: 36 words]; tile column u = band column t + 3 (the 3-px ring apron on the
+//               left); copy A word j = tile columns (2j, 2j+1), copy B word j = columns (2j+1, 2j+2).  Lane p
+//               scores band columns (2p, 2p+1), i.e. tile columns (2p+3, 2p+4): ring offsets dx = -2, 0, +2 are
+//               words p, p+1, p+2 of copy B and dx = -3, -1, +1, +3 words p .. p+3 of copy A.
+//   stash     = one code per (row pair, lane): 0, or the stored score of the single surviving pixel of the lane's
+//               2 x 2 pixels, times 256 if it lies in the odd row of the pair, negated if in the odd column.
+//               With an odd cell width one lane has its two columns in different cells, where BOTH can hold a
+//               survivor: that lane's code covers its even column only and the uncombined 32-bit word goes to a
+//               second, one-word-per-row-pair stash.
+__host__ __device__ inline int fast_warp_bytes(const int stash_slots)
 {
-    const OrbLevel& L = plan.lv[l];
-    const int tid = threadIdx.x;
-    const int cj0 = sx * ORB_FAST_STRIP;
-    const int ncs = min(ORB_FAST_STRIP, L.ncx - cj0);
-    const int wc = L.wCell, hc = L.hCell, maxBX = L.w - ORB_BORDER0, maxBY = L.h - ORB_BORDER0;
-    const int np = (wc + 1) >> 1;                    // pixel pairs per cell row
-    const int WPC = STATIC ? ORB_FAST_WPC_STATIC : orb_fast_wpc(ncs, wc);
-    const int OB = orb_fast_ob(WPC), RS = OB + WPC + 1;         // even: rows stay 8-byte aligned
-    const int SP = np + 1, SRS = ncs * SP + 1;
-    uint32_t* tile = smem;                                            // (eh+6) x RS
-    uint32_t* score = smem + plan.fast_tile_words;                    // (eh+2) x SRS
-    uint32_t* surv = tile;                                            // NMS survivors (tile is dead by then)
-    uint16_t* surv_tag = (uint16_t*)(score + plan.fast_score_words);  // cell | isA << 15
-    uint32_t* raw = score + plan.fast_score_words + ((plan.fast_surv_max + 1) >> 1);   // (eh+6) x RW image words, as fetched
-    const int RW = STATIC ? ORB_FAST_RW_STATIC : orb_fast_rw(ncs, wc);
-
-    int pitch;
-    const uint8_t* src = orb_level_ptr(plan, io, frame, l, &pitch);
-    const int w = L.w;
-
-    // ---- this thread's pixel-pair column: col = c * np + p, row group g of rgc
-    const int ipr = ncs * np;
-    const int rgc = max(fast_div(FAST_NT, ipr), 1);
-    const int g = fast_div(tid, ipr), col = tid - g * ipr;
-    int nv = 0, c = 0, xb = 0, aofs = 0, ab = 0, sofs = 0;
-    if (g < rgc) {
-        c = fast_div(col, np);
-        const int p = col - c * np;
-        const int X = (cj0 + c) * wc;                                  // border-frame x of the cell image's first column
-        const int ew = min(wc, maxBX - 6 - (ORB_BORDER0 + X));         // evaluated width of this cell
-        nv = min(max(ew - 2 * p, 0), 2);                               // valid pixels of the pair
-        const int t = c * wc + 2 * p, odd = t & 1;
-        aofs = (odd ? OB : 0) + (t >> 1);
-        ab = (odd ? (t >> 1) + 1 : OB + (t >> 1)) - aofs;
-        sofs = c * SP + p + 1;
-        xb = X + 3 + 2 * p;
-    }
-    const uint32_t lanes = nv == 2 ? 0xffffffffu : 0x0000ffffu;
-    // stored score = score - (minTh - 1) where score >= minTh, else 0 (monotone, so NMS is unchanged)
-    const uint32_t bias = 0x00010001u * (uint32_t)(65536 - 257 - (plan.minTh - 1));
-    const int iniBias = plan.iniTh - plan.minTh + 1;                   // stored score of a corner at iniThFAST
-    // ---- this thread's staging column: 4-column group k, row group gs of rgs
-    const int ncolS = min(WPC >> 1, ((ncs * wc + 7) >> 2) + 1);        // columns 0 .. ncs*wc+7 are read
-    const int rgs = fast_div(FAST_NT, ncolS);
-    const int gs = fast_div(tid, ncolS), ks = tid - gs * ncolS;
-    const int x0 = ORB_BORDER0 + cj0 * wc;                             // level x of strip column 0
-    const int dstep = rgs * RS;
-    // ---- this thread's fetch column: image word jp of every rgp-th row.  Rows are fetched from the 4-byte
-    // aligned address at or below their first pixel; bytes past the image width are zero-filled.
-    const int rgp = fast_div(FAST_NT, RW);
-    const int gp = fast_div(tid, RW), jp = tid - gp * RW;
-    const bool fetch_full = x0 + 4 * jp + 8 <= w;
-
-    auto prefetch = [&](const int ci) {
-        const int y0 = ORB_BORDER0 + ci * hc, th = min(y0 + hc + 6, maxBY) - y0;
-        if (gp < rgp) {
-            const uint8_t* rowp = src + (size_t)(y0 + gp) * pitch + x0;
-            uint32_t dst = (uint32_t)__cvta_generic_to_shared(raw + gp * RW + jp);
-            if ((pitch & 3) == 0) {
-                // every row starts at the same offset inside its word (all pyramid levels, and level 0 when the caller's
-                // pitch is a multiple of 4): source word and byte count are set up once, the loop only steps
-                const uintptr_t a = (uintptr_t)rowp;
-                const int s = (int)(a & 3);
-                const uint8_t* q = (const uint8_t*)(a - s) + 4 * jp;
-                const int n = fetch_full ? 4 : min(max(w - (x0 - s + 4 * jp), 0), 4);
-                const size_t qstep = (size_t)rgp * pitch;
-                const uint32_t dstep4 = 4u * rgp * RW;
-                for (int r = gp; r < th; r += rgp, q += qstep, dst += dstep4)
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(q), "r"(n) : "memory");
-            } else {
-                for (int r = gp; r < th; r += rgp, rowp += (size_t)rgp * pitch, dst += 4u * rgp * RW) {
-                    const uintptr_t a = (uintptr_t)rowp;
-                    const int s = (int)(a & 3);
-                    const uint8_t* q = (const uint8_t*)(a - s) + 4 * jp;
-                    int n = 4;
-                    if (!fetch_full) n = min(max(w - (x0 - s + 4 * jp), 0), 4);
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(q), "r"(n) : "memory");
-                }
-            }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    prefetch(ci0);
-
-    for (int ci = ci0; ci < ci1; ++ci) {
-        const int y0 = ORB_BORDER0 + ci * hc, y1 = min(y0 + hc + 6, maxBY);
-        const int eh = y1 - y0 - 6;                  // evaluated rows y0+3 .. y1-4
-        if (eh <= 0) break;
-        const int th = eh + 6;
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncthreads();
-        // ---- staging: a thread owns a 4-column group and walks down the rows of the fetched image words
-        if (gs < rgs) {
-            uint32_t* dA = tile + 2 * ks + gs * RS;
-            const uint32_t* rq = raw + gs * RW + ks;
-            uint32_t s = (uint32_t)((uintptr_t)(src + (size_t)(y0 + gs) * pitch + x0) & 3);
-            const uint32_t sinc = (uint32_t)(rgs * pitch) & 3u;
-#pragma unroll 4
-            for (int r = gs; r < th; r += rgs, rq += rgs * RW, dA += dstep, s = (s + sinc) & 3u) {
-                const uint32_t q0 = rq[0], q1 = rq[1];
-                const uint32_t w0 = __funnelshift_r(q0, q1, 8 * s);          // columns 4k .. 4k+3
-                const uint32_t c4 = __byte_perm(q1, 0, 0x4440u | s);         // column 4k+4
-                *(uint2*)dA = make_uint2(__byte_perm(w0, 0, 0x4140), __byte_perm(w0, 0, 0x4342));
-                dA[OB] = __byte_perm(w0, 0, 0x4241);
-                dA[OB + 1] = __byte_perm(w0, c4, 0x5453);
-            }
-        }
-        {   // score map = 0 (aprons must be; interior is only written where non-zero)
-            uint4* z = (uint4*)score;
-            const int n4 = ((eh + 2) * SRS + 3) >> 2;
-            for (int i = tid; i < n4; i += FAST_NT) z[i] = make_uint4(0, 0, 0, 0);
-        }
-        if (tid < ORB_FAST_STRIP) s_any[tid] = 0;
-        if (tid < 4) s_ctr[tid] = 0;
-        __syncthreads();
-        if (ci + 1 < ci1) prefetch(ci + 1);                           // overlaps the scoring of this cell row
-
-        // ---- a thread owns a pixel-pair column of the strip and a contiguous run of rows [ya, yb)
-        const int chunk = fast_div(eh + rgc - 1, rgc);
-        const int ya = g * chunk, yb = min(eh, ya + chunk);
-        if (nv) {   // scores
-            const uint32_t* a = tile + aofs + ya * RS;                    // ring row dy = -3 of evaluated row ya
-            uint32_t* sc = score + sofs + (ya + 1) * SRS;
-#pragma unroll (kFastUnroll)
-            for (int ly = ya; ly < yb; ++ly, a += RS, sc += SRS) {
-                const uint32_t* b = a + ab;
-                uint32_t E[16];
-                E[0] = b[6 * RS + 1];    //  ( 0, 3)
-                E[1] = a[6 * RS + 2];    //  ( 1, 3)
-                E[2] = b[5 * RS + 2];    //  ( 2, 2)
-                E[3] = a[4 * RS + 3];    //  ( 3, 1)
-                E[4] = a[3 * RS + 3];    //  ( 3, 0)
-                E[5] = a[2 * RS + 3];    //  ( 3,-1)
-                E[6] = b[1 * RS + 2];    //  ( 2,-2)
-                E[7] = a[0 * RS + 2];    //  ( 1,-3)
-                E[8] = b[0 * RS + 1];    //  ( 0,-3)
-                E[9] = a[0 * RS + 1];    //  (-1,-3)
-                E[10] = b[1 * RS + 0];   //  (-2,-2)
-                E[11] = a[2 * RS + 0];   //  (-3,-1)
-                E[12] = a[3 * RS + 0];   //  (-3, 0)
-                E[13] = a[4 * RS + 0];   //  (-3, 1)
-                E[14] = b[5 * RS + 0];   //  (-2, 2)
-                E[15] = a[6 * RS + 1];   //  (-1, 3)
-                const uint32_t v = b[3 * RS + 1];
-                uint32_t M1, M2;
-                fast_network(E, M1, M2);
-                // per 16-bit lane, carry free: bright + 256 = M1 + (256 - v), dark + 256 = (v + 256) - M2
-                const uint32_t br = M1 + (0x01000100u - v), dk = (v + 0x01000100u) - M2;
-                const uint32_t t = hmax2(br, dk);                                   // score + 257
-                const uint32_t out = __viaddmax_s16x2_relu(t, bias, 0u) & lanes;    // max(score - minTh + 1, 0)
-                if (out) *sc = out;
-            }
-        }
-        __syncthreads();
-
-        // ---- strict 3x3 maximum inside each cell: rows slide through registers, 3 loads per pixel pair.
-        // The loop only records WHICH lanes survive (2 bits per row); the rare survivors are pushed afterwards.
-        if (nv) {
-            const uint32_t* sc = score + sofs + (ya + 1) * SRS;           // row of evaluated row ya
-            uint32_t u0 = sc[-SRS - 1], u1 = sc[-SRS], u2 = sc[-SRS + 1];
-            uint32_t m0 = sc[-1], m1 = sc[0], m2 = sc[1];
-            for (int yq = ya; yq < yb; yq += 32) {                        // 2 bits per row in a 64-bit mask
-                const int ye = min(yb, yq + 32);
-                unsigned long long kept = 0;
-#pragma unroll 3
-                for (int ly = yq; ly < ye; ++ly, sc += SRS) {
-                    const uint32_t d0 = sc[SRS - 1], d1 = sc[SRS], d2 = sc[SRS + 1];
-                    const uint32_t Lw = __vimax3_s16x2(u0, m0, d0), Rw = __vimax3_s16x2(u2, m2, d2);
-                    const uint32_t Uw = hmax2(u1, d1), Cw = hmax2(Uw, m1);
-                    // neighbours of (x | x+1): columns (x-1 | x) and (x+1 | x+2) over three rows, own column above/below
-                    const uint32_t nb = __vimax3_s16x2(__byte_perm(Lw, Cw, 0x5432), __byte_perm(Cw, Rw, 0x5432), Uw);
-                    // lane > neighbour maximum  <=>  bit 15 of (lane + 32768 - nb - 1); lanes stay in 0..65535, no borrow
-                    const uint32_t keep = ((m1 | 0x80008000u) - nb - 0x00010001u) & 0x80008000u;
-                    kept = (kept << 2) | ((keep >> 15) & 1u) | (keep >> 30);
-                    u0 = m0; u1 = m1; u2 = m2; m0 = d0; m1 = d1; m2 = d2;
-                }
-                // kept: row ye-1 in bits 0..1, row ye-2 in bits 2..3, ...; sc is now the row of evaluated row ye
-                while (kept) {
-                    const int bit = __ffsll((long long)kept) - 1;
-                    kept &= kept - 1;
-                    const int back = bit >> 1, hi = bit & 1;
-                    const int r = (int)((sc[-(back + 1) * SRS] >> (16 * hi)) & 0xffffu);
-                    const int slot = atomicAdd(&s_ctr[0], 1);
-                    // border-frame coordinates (src/ORBextractor.cc:868-869): cell-local + (j*wCell, i*hCell)
-                    surv[slot] = orb_pack(xb + hi, ye - 1 - back + 3 + ci * hc, r + plan.minTh - 1);
-                    const bool isA = r >= iniBias;
-                    surv_tag[slot] = (uint16_t)(c | (isA ? 0x8000 : 0));
-                    if (isA) s_any[c] = 1;
-                }
-            }
-        }
-        __syncthreads();
-        // ---- per-cell cut-off: keep the iniThFAST survivors, or all of them if the cell has none (:857-861)
-        const int nsurv = s_ctr[0];
-        int mykeep = 0;
-        for (int j = tid; j < nsurv; j += FAST_NT) {
-            const int t = surv_tag[j];
-            if ((t & 0x8000) || !s_any[t & 0x7fff]) ++mykeep;
-        }
-        if (mykeep) atomicAdd(&s_ctr[1], mykeep);
-        __syncthreads();
-        const int nkeep = s_ctr[1];
-        if (nkeep) {
-            if (tid == 0) s_ctr[3] = atomicAdd(&io.cand_count[frame * ORB_MAX_LEVELS + l], nkeep);
-            __syncthreads();
-            const int base = s_ctr[3];
-            uint32_t* out = io.cand + (size_t)frame * plan.cand_per_frame + L.cand_off;
-            for (int j = tid; j < nsurv; j += FAST_NT) {
-                const int t = surv_tag[j];
-                if ((t & 0x8000) || !s_any[t & 0x7fff]) {
-                    const int slot = base + atomicAdd(&s_ctr[2], 1);
-                    if (slot < L.cand_cap) out[slot] = surv[j];
-                }
-            }
-        }
-        __syncthreads();                                              // the next cell row reuses everything
-    }
+    return (16 + kTileRows * kRS * 4 + kTileRows * kRawPitch + (stash_slots + 1) * (64 + 4) + 15) & ~15;
 }
 
-__global__ void __launch_bounds__(FAST_NT) k_fast_strips(const __grid_constant__ OrbPlan plan, const OrbBatch io, const __grid_constant__ FastGrid fg)
+__global__ void __launch_bounds__(kNT, ORB_FAST_MINBLK) k_fast_bands(const __grid_constant__ OrbPlan plan, const OrbBatch io, const __grid_constant__ FastGrid fg)
 {
-    extern __shared__ __align__(16) uint32_t smem[];
-    __shared__ int s_ctr[4], s_any[ORB_FAST_STRIP];
+    extern __shared__ __align__(16) unsigned char fast_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int l = 0;
     while (l + 1 < plan.nlevels && (int)blockIdx.x >= fg.first[l + 1]) ++l;
+    const OrbLevel& L = plan.lv[l];
     const int idx = blockIdx.x - fg.first[l];
-    const int spr = plan.lv[l].spr;
-    const int rb = fast_div(idx, spr), sx = idx - rb * spr;
-    const int ci0 = rb * fg.rows_per_block, ci1 = min(plan.lv[l].ncy, ci0 + fg.rows_per_block);
-    if (plan.lv[l].wCell <= ORB_FAST_WC_STATIC)
-        fast_strip_body<true>(plan, io, smem, s_ctr, s_any, blockIdx.y, l, sx, ci0, ci1);
-    else
-        fast_strip_body<false>(plan, io, smem, s_ctr, s_any, blockIdx.y, l, sx, ci0, ci1);
+    const int bpr = (L.fbands + ORB_FAST_WPB - 1) / ORB_FAST_WPB;      // blocks per group of cell rows
+    const int rb = fast_div(idx, bpr);
+    const int band = (idx - rb * bpr) * ORB_FAST_WPB + warp;
+    if (band >= L.fbands) return;                                      // warps share nothing: no barrier follows
+    const int frame = blockIdx.y;
+    const int ci0 = rb * fg.rows_per_block, ci1 = min(L.ncy, ci0 + fg.rows_per_block);
+
+    unsigned char* wsm = fast_smem + (size_t)warp * fast_warp_bytes(plan.fast_stash_slots);
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(wsm);
+    uint32_t* tile = (uint32_t*)(wsm + 16);
+    unsigned char* raw = wsm + 16 + kTileRows * kRS * 4;
+    uint16_t* stash = (uint16_t*)(raw + kTileRows * kRawPitch);
+    uint32_t* stash2 = (uint32_t*)(stash + (plan.fast_stash_slots + 1) * 32);   // row pairs of the lane that straddles two cells
+    const uint32_t raw_s = (uint32_t)__cvta_generic_to_shared(raw);
+
+    // ---- band geometry (src/ORBextractor.cc:826-848): cells cj0 .. cj0+ncb-1 of every cell row
+    const int wc = L.wCell, hc = L.hCell, maxBX = L.w - ORB_BORDER0, maxBY = L.h - ORB_BORDER0;
+    const int cpb = L.fcpb;                                            // cells per band: 2 while two cells fit 64 columns
+    const int cj0 = band * cpb, ncb = min(cpb, L.ncx - cj0);
+    const int X0 = cj0 * wc;                                           // border-frame x of the band's first cell image
+    // evaluated columns of the band: cells are contiguous, only the last cell of a level can be narrower
+    const int tw = min(ncb * wc, maxBX - 6 - (ORB_BORDER0 + X0));
+    const int npx = tw + 6;                                            // tile columns that must be valid
+    int pitch;
+    const uint8_t* src = orb_level_ptr(plan, io, frame, l, &pitch);
+    src += ORB_BORDER0 + X0;                                           // level address of tile column 0, row 0
+
+    // ---- this lane's pixel pair: band columns t0 = 2 * lane (lo half) and t0 + 1 (hi half)
+    const int t0 = 2 * lane;
+    const bool vlo = t0 < tw, vhi = t0 + 1 < tw;
+    const int clo = (cpb > 1 && t0 >= wc) ? 1 : 0, chi = (cpb > 1 && t0 + 1 >= wc) ? 1 : 0;   // cell of each half
+    const uint32_t lm = (vlo ? 0x00003c00u : 0u) | (vhi ? 0x3c000000u : 0u);   // 1.0 in the valid halves
+    const bool straddle = clo != chi;                                          // at most one lane of the warp
+    const unsigned short foldk = straddle ? 0x0000u : 0xbc00u;                 // code = lo + foldk * hi
+    // NMS neighbours: (left of lo | left of hi) = (Lw.hi | Cw.lo), (right of lo | right of hi) = (Cw.hi | Rw.lo);
+    // a neighbour in another cell, outside the band or in another warp reads byte 1 of the first operand, the
+    // high byte of a score below 256, i.e. zero
+    const bool lo_first = t0 == 0 || (cpb > 1 && t0 == wc);
+    const bool hi_first = cpb > 1 && t0 + 1 == wc;
+    const bool lo_last = (cpb > 1 && t0 == wc - 1) || t0 == tw - 1;
+    const bool hi_last = (cpb > 1 && t0 + 1 == wc - 1) || t0 + 1 >= tw - 1 || lane == 31;
+    const uint32_t selL = (lo_first ? 0x0011u : 0x0032u) | (hi_first ? 0x1100u : 0x5400u);
+    const uint32_t selR = (lo_last ? 0x0011u : 0x0032u) | (hi_last ? 0x1100u : 0x5400u);
+    const uint32_t bias = 0x80008000u | (0x00010001u * (uint32_t)plan.minTh);            // -minTh * 2^-24 per half
+    const int iniBias = plan.iniTh - plan.minTh + 1;                                      // stored score of a corner at iniThFAST
+    const uint32_t iniV = 0x00010001u * (uint32_t)min(max(iniBias, 1), 1023);          // every survivor is >= 1
+    const uint32_t* po = tile + lane;                // odd ring offsets: words po[0..3] = dx -3, -1, +1, +3
+    const uint32_t* pb = tile + kCopyW + lane;       // even ring offsets: words pb[0..2] = dx -2, 0, +2
+    // widening: lane = (sub-row, 8-column group); 27 lanes work on 3 tile rows per pass
+    const int wsub = lane / 9, wk = lane - 9 * wsub;
+    const uint32_t pitch15 = (uint32_t)pitch & 15u;
+
+    if (lane == 0) mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+
+    // Issue the bulk copies of tile rows [0, trows) whose first image row is y: lane r fetches row r from the
+    // 16-byte aligned address at or below its first pixel; the bytes stay inside the image row (the band starts
+    // at column >= 16 and its last tile column lies >= 16 pixels before the row's end).
+    auto fetch = [&](const int y, const int trows) {
+        uint32_t bytes = 0;
+        const uint8_t* q = nullptr;
+        if (lane < trows) {
+            const uint8_t* rowp = src + (size_t)(y + lane) * pitch;
+            const uint32_t s = (uint32_t)((uintptr_t)rowp & 15u);
+            q = rowp - s;
+            bytes = (s + (uint32_t)npx + 15u) & ~15u;
+        }
+        const uint32_t total = __reduce_add_sync(0xffffffffu, bytes);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the raw rows were read through the generic proxy
+        if (lane == 0) mbar_expect_tx(bar, total);
+        __syncwarp();
+        if (lane < trows) bulk_g2s(raw_s + lane * kRawPitch, q, bytes, bar);
+    };
+
+    // chunk schedule of a cell row: evaluated rows [ya, yb) of the cell; returns false when the cell row is empty
+    uint32_t parity = 0;
+    {
+        const int y0 = ORB_BORDER0 + ci0 * hc, eh = min(y0 + hc + 6, maxBY) - y0 - 6;
+        if (ci0 < ci1 && eh > 0) fetch(y0, min(eh, kR) + 6);
+    }
+
+    for (int ci = ci0; ci < ci1; ++ci) {
+        const int y0 = ORB_BORDER0 + ci * hc;
+        const int eh = min(y0 + hc + 6, maxBY) - y0 - 6;               // evaluated rows y0+3 .. y0+3+eh-1
+        if (eh <= 0) break;
+        uint32_t u = 0, m = 0, carry = 0;                              // scores of the two rows above; even-row survivors
+        uint32_t cntAll = 0, cntA = 0;                                 // survivors / survivors at iniThFAST per column (fp16 counts)
+
+        for (int ya = 0; ya < eh; ya += kR) {
+            const int nr = min(eh - ya, kR), trows = nr + 6;
+            mbar_wait(bar, parity);
+            parity ^= 1u;
+            // ---- widen: raw bytes -> copies A and B
+            {
+                const uint32_t s0 = (uint32_t)((uintptr_t)(src + (size_t)(y0 + ya) * pitch) & 15u);
+                if (wsub < 3) {
+                    uint32_t s = (s0 + (uint32_t)wsub * pitch15) & 15u;
+                    const uint32_t sstep = (3u * pitch15) & 15u;
+                    const unsigned char* rp = raw + wsub * kRawPitch + 8 * wk;
+                    uint32_t* dst = tile + wsub * kRS + 4 * wk;
+                    for (int r = wsub; r < trows; r += 3, rp += 3 * kRawPitch, dst += 3 * kRS, s = (s + sstep) & 15u) {
+                        uint32_t b[9];
+#pragma unroll
+                        for (int i = 0; i < 9; ++i) b[i] = rp[s + i];         // LDS.U8: no alignment rule, no funnel shift
+                        uint32_t A[4], B[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            asm("mad.lo.u32 %0, %1, 65536, %2;" : "=r"(A[i]) : "r"(b[2 * i + 1]), "r"(b[2 * i]));
+                            asm("mad.lo.u32 %0, %1, 65536, %2;" : "=r"(B[i]) : "r"(b[2 * i + 2]), "r"(b[2 * i + 1]));
+                        }
+                        *(uint4*)dst = make_uint4(A[0], A[1], A[2], A[3]);
+                        *(uint4*)(dst + kCopyW) = make_uint4(B[0], B[1], B[2], B[3]);
+                    }
+                }
+            }
+            __syncwarp();
+            // ---- the raw buffer is free: fetch the next chunk (of this cell row or of the next one)
+            {
+                int ny = -1, nt = 0;
+                if (ya + kR < eh) { ny = y0 + ya + kR; nt = min(eh - ya - kR, kR) + 6; }
+                else if (ci + 1 < ci1) {
+                    const int y1 = y0 + hc, eh1 = min(y1 + hc + 6, maxBY) - y1 - 6;
+                    if (eh1 > 0) { ny = y1; nt = min(eh1, kR) + 6; }
+                }
+                if (ny >= 0) fetch(ny, nt);
+            }
+            // ---- scores, NMS of the row above, survivor record; rows ya .. ya+nr-1, two per step
+            const uint32_t* a = po;
+            const uint32_t* b = pb;
+            uint16_t* st = stash + ((ya >> 1) * 32 + lane);            // slot of rows (ya-2, ya-1) = index ya/2; slot index is shifted by one, slot 0 is a dummy
+            auto score = [&](const uint32_t* a, const uint32_t* b) -> uint32_t {
+                uint32_t E[16];
+                E[0] = b[6 * kRS + 1];    //  ( 0, 3)
+                E[1] = a[6 * kRS + 2];    //  ( 1, 3)
+                E[2] = b[5 * kRS + 2];    //  ( 2, 2)
+                E[3] = a[4 * kRS + 3];    //  ( 3, 1)
+                E[4] = a[3 * kRS + 3];    //  ( 3, 0)
+                E[5] = a[2 * kRS + 3];    //  ( 3,-1)
+                E[6] = b[1 * kRS + 2];    //  ( 2,-2)
+                E[7] = a[0 * kRS + 2];    //  ( 1,-3)
+                E[8] = b[0 * kRS + 1];    //  ( 0,-3)
+                E[9] = a[0 * kRS + 1];    //  (-1,-3)
+                E[10] = b[1 * kRS + 0];   //  (-2,-2)
+                E[11] = a[2 * kRS + 0];   //  (-3,-1)
+                E[12] = a[3 * kRS + 0];   //  (-3, 0)
+                E[13] = a[4 * kRS + 0];   //  (-3, 1)
+                E[14] = b[5 * kRS + 0];   //  (-2, 2)
+                E[15] = a[6 * kRS + 1];   //  (-1, 3)
+                const uint32_t v = b[3 * kRS + 1];
+                uint32_t M1, M2;
+                fast_network(E, M1, M2);
+                const uint32_t t = hmax2(hsub2(M1, v), hsub2(v, M2));     // score + 1, signed
+                return hfma2_relu(t, lm, bias);                           // max(score - minTh + 1, 0); 0 in the invalid halves
+            };
+            // strict 3x3 maximum of row mm between rows uu and dd: mm where it survives, else 0
+            auto nms = [&](const uint32_t uu, const uint32_t mm, const uint32_t dd) -> uint32_t {
+                const uint32_t Uw = hmax2(uu, dd), Cw = hmax2(Uw, mm);
+                const uint32_t Lw = __shfl_up_sync(0xffffffffu, Cw, 1), Rw = __shfl_down_sync(0xffffffffu, Cw, 1);
+                const uint32_t nb = hmax2(hmax2(__byte_perm(Lw, Cw, selL), __byte_perm(Cw, Rw, selR)), Uw);
+                const uint32_t g = hsetgt2(mm, nb);
+                cntAll = hadd2(cntAll, g);
+                const uint32_t s = hmul2(mm, g);
+                cntA = hadd2(cntA, hsetge2(s, iniV));
+                return s;
+            };
+            // code of a row pair: even-row survivor se, odd-row survivor so
+            auto record = [&](uint16_t* slot, const uint32_t se, const uint32_t so) {
+                const uint32_t w = hfma2(so, 0x5c005c00u, se);            // se + 256 * so: at most one of the four halves is non-zero (one per half in the straddling lane)
+                uint16_t c;
+                asm("{ .reg .b16 lo, hi; mov.b32 {lo, hi}, %1; fma.rn.f16 %0, hi, %2, lo; }" : "=h"(c) : "r"(w), "h"(foldk));
+                *slot = c;
+                if (straddle) stash2[(slot - stash) >> 5] = w;
+            };
+            int r = 0;
+#pragma unroll 1
+            for (; r + 2 <= nr; r += 2, a += 2 * kRS, b += 2 * kRS, st += 32) {
+                const uint32_t d0 = score(a, b);
+                const uint32_t d1 = score(a + kRS, b + kRS);
+                const uint32_t so = nms(u, m, d0);                        // survivors of the odd row above d0
+                record(st, carry, so);
+                carry = nms(m, d0, d1);                                   // survivors of the even row d0
+                u = d0; m = d1;
+            }
+            if (r < nr) {                                                 // single last row (even index): only at the end of a cell row
+                const uint32_t d0 = score(a, b);
+                const uint32_t so = nms(u, m, d0);
+                record(st, carry, so);
+                st += 32;
+                carry = 0;
+                u = m; m = d0;
+                // the row below is outside the cell: finish now, this row is the even row of its pair
+                const uint32_t se = nms(u, m, 0u);
+                record(st, se, 0u);
+            } else if (ya + kR >= eh) {                                   // the cell row ended on an odd row
+                const uint32_t so = nms(u, m, 0u);
+                record(st, carry, so);
+            }
+        }
+        __syncwarp();
+
+        // ---- per-cell cut-off (:857-861), one atomic per cell row and band, every lane writes its own survivors
+        const int nslots = (eh + 1) >> 1;
+        // survivors of iniThFAST per cell; the fp16 counts are exact (at most one per row pair and column)
+        const bool aLo = (cntA & 0x7fffu) != 0, aHi = (cntA >> 16 & 0x7fffu) != 0;
+        const uint32_t any0 = __ballot_sync(0xffffffffu, (aLo && clo == 0) || (aHi && chi == 0));
+        const uint32_t any1 = __ballot_sync(0xffffffffu, (aLo && clo == 1) || (aHi && chi == 1));
+        const bool iniLo = clo ? any1 != 0 : any0 != 0, iniHi = chi ? any1 != 0 : any0 != 0;   // cut-off of each half's cell
+        const int nAllLo = __half2int_rn(__ushort_as_half((unsigned short)(cntAll & 0xffffu))), nAllHi = __half2int_rn(__ushort_as_half((unsigned short)(cntAll >> 16)));
+        const int nALo = __half2int_rn(__ushort_as_half((unsigned short)(cntA & 0xffffu))), nAHi = __half2int_rn(__ushort_as_half((unsigned short)(cntA >> 16)));
+        const int mine = (iniLo ? nALo : nAllLo) + (iniHi ? nAHi : nAllHi);
+        int incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&io.cand_count[frame * ORB_MAX_LEVELS + l], total);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            int slot = base + incl - mine;
+            uint32_t* out = io.cand + (size_t)frame * plan.cand_per_frame + L.cand_off;
+            const uint16_t* sp = stash + 32 + lane;
+            uint32_t mask = 0;                                          // this lane's row pairs that hold a survivor
+            if (mine) for (int j = 0; j < nslots; ++j) if (sp[32 * j] & 0x7fffu) mask |= 1u << j;
+            uint32_t mask2 = 0;                                         // the odd column of the straddling lane
+            if (mine && straddle) for (int j = 0; j < nslots; ++j) if (stash2[j + 1] >> 16) mask2 |= 1u << j;
+            while (mask | mask2) {
+                const bool second = mask == 0;
+                const uint32_t mm = second ? mask2 : mask;
+                const int j = __ffs((int)mm) - 1;
+                if (second) mask2 &= mask2 - 1; else mask &= mask - 1;
+                const uint32_t c = second ? (stash2[j + 1] >> 16) | 0x8000u : sp[32 * j];
+                const int hi = (int)(c >> 15);
+                const int n = __float2int_rn(__half2float(__ushort_as_half((unsigned short)(c & 0x7fffu))) * 16777216.0f);
+                const int odd = n >= 256 ? 1 : 0;
+                const int sc = odd ? n >> 8 : n;
+                if (sc >= iniBias || !(hi ? iniHi : iniLo)) {
+                    // border-frame coordinates (src/ORBextractor.cc:868-869): cell-local + (j*wCell, i*hCell)
+                    if (slot < L.cand_cap) out[slot] = orb_pack(X0 + t0 + hi + 3, ci * hc + 2 * j + odd + 3, sc + plan.minTh - 1);
+                    ++slot;
+                }
+            }
+        }
+        __syncwarp();                                                   // the next cell row reuses the stash
+    }
 }
 
 size_t orb_fast_smem_bytes(const OrbPlan& plan)
 {
-    return ((size_t)plan.fast_tile_words + plan.fast_score_words + ((plan.fast_surv_max + 1) >> 1) + plan.fast_raw_words) * 4 + 32;
+    return (size_t)ORB_FAST_WPB * fast_warp_bytes(plan.fast_stash_slots);
 }
 
 cudaError_t orb_launch_fast(const OrbPlan& plan, const OrbBatch& io, int batch, cudaStream_t st)
 {
-    if (plan.total_strips == 0) return cudaSuccess;
+    if (plan.total_cells == 0) return cudaSuccess;
     const size_t smem = orb_fast_smem_bytes(plan);
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(k_fast_strips, cudaFuncAttributeMaxDynamicSharedMemorySize, ORB_SMEM_OPTIN);   // a constant: the attribute is per-function state shared by all host threads (a per-launch value races)
+        cudaError_t e = cudaFuncSetAttribute(k_fast_bands, cudaFuncAttributeMaxDynamicSharedMemorySize, ORB_SMEM_OPTIN);   // a constant: the attribute is per-function state shared by all host threads (a per-launch value races)
         if (e != cudaSuccess) return e;
     }
-    // Cell rows per block: whole strip columns once the batch alone fills the GPU several times over (the
-    // per-column setup is then paid once per column), single cell rows for a few frames (latency).
+    // Cell rows per block: whole band columns once the batch alone fills the GPU several times over (the
+    // per-band setup is then paid once per column), single cell rows for a few frames (latency).
     int maxrows = 1;
     for (int l = 0; l < plan.nlevels; ++l) if (plan.lv[l].ncy > maxrows) maxrows = plan.lv[l].ncy;
     FastGrid fg;
@@ -391,10 +455,11 @@ cudaError_t orb_launch_fast(const OrbPlan& plan, const OrbBatch& io, int batch, 
     int n = 0;
     for (int l = 0; l < plan.nlevels; ++l) {
         fg.first[l] = n;
-        n += plan.lv[l].spr * ((plan.lv[l].ncy + fg.rows_per_block - 1) / fg.rows_per_block);
+        const int bpr = (plan.lv[l].fbands + ORB_FAST_WPB - 1) / ORB_FAST_WPB;
+        n += bpr * ((plan.lv[l].ncy + fg.rows_per_block - 1) / fg.rows_per_block);
     }
     for (int l = plan.nlevels; l <= ORB_MAX_LEVELS; ++l) fg.first[l] = n;
     if (n == 0) return cudaSuccess;
-    k_fast_strips<<<dim3(n, batch), FAST_NT, smem, st>>>(plan, io, fg);
+    k_fast_bands<<<dim3(n, batch), kNT, smem, st>>>(plan, io, fg);
     return cudaGetLastError();
 }

@@ -81,7 +81,7 @@ int orb_plan_build(const OrbParams* p, int w, int h, OrbPlan* plan, std::vector<
     for (int i = 0; i <= ORB_HALF_PATCH; ++i) plan->umax[i] = p->umax[i];
     if ((long long)w * h >= (1 << 24)) return 1;
     uint32_t pyr = 0, blur = 0;
-    int cells = 0, strips = 0, tiles = 0, cand = 0, kp = 0;
+    int cells = 0, tiles = 0, cand = 0, kp = 0;
     const float Wcell = 30.f;                                              // src/ORBextractor.cc:799
     for (int l = 0; l < p->nlevels; ++l) {
         OrbLevel& L = plan->lv[l];
@@ -115,29 +115,18 @@ int orb_plan_build(const OrbParams* p, int w, int h, OrbPlan* plan, std::vector<
                     int x0 = ORB_BORDER0 + j * L.wCell, x1 = x0 + L.wCell + 6; if (x1 > maxBorderX) x1 = maxBorderX;
                     int ew = x1 - x0 - 6; if (ew < 0) ew = 0;
                     cap += ((ew + 1) / 2) * ((eh + 1) / 2);                // strict 3x3 maxima cannot be denser
-                    if (ew * eh > plan->fast_eval_max) plan->fast_eval_max = ew * eh;
                 }
             }
-            // orb_fast.cu: a block takes a run of up to ORB_FAST_STRIP cells of one cell row, staged as two
-            // 16-bit copies of the strip image, plus a 16-bit score map with a zero apron per cell
-            const int ncs = L.ncx < ORB_FAST_STRIP ? L.ncx : ORB_FAST_STRIP;
-            const int np = (L.wCell + 1) / 2;
-            const int wpc = L.wCell <= ORB_FAST_WC_STATIC ? ORB_FAST_WPC_STATIC : orb_fast_wpc(ncs, L.wCell);
-            const int rs = orb_fast_ob(wpc) + wpc + 1;
-            const int tile = ((L.hCell + 6) * rs + 3) & ~3, score = ((L.hCell + 2) * (ncs * (np + 1) + 1) + 3) & ~3;
-            const int surv = ncs * np * ((L.hCell + 1) / 2);
-            if (tile > plan->fast_tile_words) plan->fast_tile_words = tile;
-            if (score > plan->fast_score_words) plan->fast_score_words = score;
-            if (surv > plan->fast_surv_max) plan->fast_surv_max = surv;
-            const int rawW = (L.hCell + 6) * (L.wCell <= ORB_FAST_WC_STATIC ? ORB_FAST_RW_STATIC : orb_fast_rw(ncs, L.wCell));
-            if (rawW > plan->fast_raw_words) plan->fast_raw_words = rawW;
-            if (surv > tile || ncs * np > 32 * ORB_FAST_STRIP || rs >= 1024) return 1;  // survivors reuse the tile; table / offset widths
+            // orb_fast.cu: a warp takes a band of one or two cells (at most ORB_FAST_BAND evaluated columns) and
+            // keeps one 16-bit code per row pair and lane; the slot mask of a lane is 32 bits wide
+            if (L.wCell > ORB_FAST_BAND || L.hCell > 64) return 1;
+            if ((L.hCell + 1) / 2 > plan->fast_stash_slots) plan->fast_stash_slots = (L.hCell + 1) / 2;
             // order key (cell, y-in-cell, x-in-cell) must fit 24 bits
             if ((long long)L.ncx * L.ncy * L.wCell * L.hCell >= (1 << 24)) return 1;
         }
         L.cell_first = cells; cells += L.ncx * L.ncy;
-        L.spr = (L.ncx + ORB_FAST_STRIP - 1) / ORB_FAST_STRIP;
-        L.strip_first = strips; strips += L.spr * L.ncy;
+        L.fcpb = 2 * L.wCell <= ORB_FAST_BAND ? 2 : 1;
+        L.fbands = (L.ncx + L.fcpb - 1) / L.fcpb;
         L.quota = p->per_level[l];
         L.cand_off = cand; L.cand_cap = cap; cand += (cap + 31) / 32 * 32;
         // list size never exceeds max(N+2, 4*nIni) (see orb_octree.cuh); keep a little slack
@@ -155,7 +144,7 @@ int orb_plan_build(const OrbParams* p, int w, int h, OrbPlan* plan, std::vector<
         L.blur_tiles_y = (L.h + ORB_BLUR_TH - 1) / ORB_BLUR_TH;
         L.blur_tile_first = tiles; tiles += L.blur_tiles_x * L.blur_tiles_y;
     }
-    plan->total_cells = cells; plan->total_strips = strips; plan->total_blur_tiles = tiles;
+    plan->total_cells = cells; plan->total_blur_tiles = tiles;
     plan->cand_per_frame = cand; plan->kp_per_frame = kp;
     plan->pyr_bytes = align_up(pyr + 64, 256); plan->blur_bytes = align_up(blur + 64, 256);
     return 0;

@@ -20,12 +20,7 @@
 #define ORB_PATCH 31         // PATCH_SIZE, :72
 #define ORB_BORDER0 16       // minBorderX = EDGE_THRESHOLD-3, :804
 #define ORB_MAX_DIM 4128     // candidate coordinates are packed in 12 bits (border frame)
-#ifndef ORB_FAST_STRIP
-#define ORB_FAST_STRIP 4     // cells per FAST block (orb_fast.cu); the block has 32 threads per cell
-#endif
-#define ORB_FAST_WC_STATIC 32    // widest cell handled with compile-time tile geometry
-#define ORB_FAST_WPC_STATIC (((ORB_FAST_STRIP * ORB_FAST_WC_STATIC + 9) / 2 + 2) & ~1)   // orb_fast_wpc(ORB_FAST_STRIP, 32)
-#define ORB_FAST_RW_STATIC (((ORB_FAST_STRIP * ORB_FAST_WC_STATIC + 15) >> 2) + 1)            // orb_fast_rw(ORB_FAST_STRIP, 32)
+#define ORB_FAST_BAND 64     // evaluated columns a FAST warp covers (orb_fast.cu): 32 lanes x 2 pixels
 #define ORB_BLUR_TW 120      // blur tile (orb_dense.cu): a warp makes 120 output pixels per row (30 lanes x 4 + 2 apron lanes)
 #ifndef ORB_BLUR_TH
 #define ORB_BLUR_TH 64       // ... and walks down this many rows
@@ -40,8 +35,8 @@ struct OrbLevel {
     int wCell, hCell;       // reference cell size
     int ncx, ncy;           // processed cell columns / rows
     int cell_first;         // index of this level's first cell in the all-level cell list
-    int spr;                // FAST strips (runs of up to ORB_FAST_STRIP cells) per cell row
-    int strip_first;        // index of this level's first strip in the all-level strip list
+    int fcpb;               // FAST: cells per band (2 while two cells fit ORB_FAST_BAND columns, else 1)
+    int fbands;             // FAST: bands per cell row
     // quadtree
     int W, H;               // maxBorder-minBorder extents = w-32, h-32
     int nIni;               // number of root nodes
@@ -67,28 +62,12 @@ struct OrbPlan {
     int cand_per_frame;     // candidate entries per frame (sum of cand_cap)
     int kp_per_frame;       // level-keypoint entries per frame (sum of kp_cap)
     int max_nodes;          // largest kp_cap: quadtree shared-memory sizing
-    int total_strips;       // sum of FAST strips over levels
-    int fast_tile_words;    // largest FAST strip tile (both copies) in 32-bit words, multiple of 4
-    int fast_eval_max;      // largest evaluated area of a cell (pixels)
-    int fast_score_words;   // largest strip score map in 32-bit words, multiple of 4
-    int fast_surv_max;      // largest possible number of NMS survivors in a strip
-    int fast_raw_words;     // largest fetched strip image in 32-bit words
+    int fast_stash_slots;   // FAST: row pairs of the tallest cell (survivor stash of a warp)
     int umax[ORB_HALF_PATCH + 1]; // row half-widths of the orientation patch
     uint32_t pyr_bytes;     // bytes of one frame's pyramid block (levels 1..)
     uint32_t blur_bytes;    // bytes of one frame's blur block (levels 0..)
     OrbLevel lv[ORB_MAX_LEVELS];
 };
-
-// FAST strip tile (orb_fast.cu): 32-bit words per row of ONE of the two 16-bit copies of a strip of ncs
-// cells of width wc.  Strip columns 0 .. ncs*wc+7 are read; a word holds two columns; even count.
-static inline __host__ __device__ int orb_fast_wpc(int ncs, int wc) { return (((ncs * wc + 8 + 1) >> 1) + 1 + 1) & ~1; }
-// image words fetched per strip row (from the aligned address at or below the first pixel)
-static inline __host__ __device__ int orb_fast_rw(int ncs, int wc) { return ((ncs * wc + 15) >> 2) + 1; }
-// word offset of the second copy inside a tile row: the first value >= wpc that is 1 (mod 32) (bank spreading)
-#ifndef ORB_FAST_OBX
-#define ORB_FAST_OBX 1      // copy B starts this many words past a multiple of 32 (odd: rows stay 8-byte aligned)
-#endif
-static inline __host__ __device__ int orb_fast_ob(int wpc) { return ((wpc + 30) & ~31) + ORB_FAST_OBX; }
 
 // packed candidate / level keypoint: x | y<<12 | score<<24, x,y in the border frame
 static inline __host__ __device__ uint32_t orb_pack(int x, int y, int s) { return (uint32_t)x | ((uint32_t)y << 12) | ((uint32_t)s << 24); }
