@@ -25,9 +25,10 @@
 //     in units of 2^-24), masked and biased by one HFMA2.RELU;
 //   * NMS needs no score map: the scores of the last three rows of the lane's column pair live in registers, the
 //     neighbouring columns come from two shuffles, cell and band borders are folded into the two PRMT selectors;
-//   * a survivor is RECORDED, not handled, in the row loop: of the four pixels of a lane's row pair at most one
-//     can be a strict 3x3 maximum, so one 16-bit code per row pair (sign = column, binade = row, value = score)
-//     goes to a per-warp stash with FMA-pipe arithmetic; survivor counts per column accumulate the same way;
+//   * a survivor is RECORDED, not handled, in the row loop: a column of a row pair holds at most one strict 3x3
+//     maximum, so one word per row pair and lane (per 16-bit half: the stored score, times 256 if it lies in the
+//     odd row) goes to a per-warp stash with one IMAD and one store; survivor counts per column accumulate on
+//     the FMA pipe as fp16 numbers;
 //   * per cell row the warp decides the cut-off of each cell (below), adds its total to the frame's candidate
 //     counter with ONE atomic and lets every lane write its own survivors.
 //
@@ -168,14 +169,13 @@ struct FastGrid {
 //               left); copy A word j = tile columns (2j, 2j+1), copy B word j = columns (2j+1, 2j+2).  Lane p
 //               scores band columns (2p, 2p+1), i.e. tile columns (2p+3, 2p+4): ring offsets dx = -2, 0, +2 are
 //               words p, p+1, p+2 of copy B and dx = -3, -1, +1, +3 words p .. p+3 of copy A.
-//   stash     = one code per (row pair, lane): 0, or the stored score of the single surviving pixel of the lane's
-//               2 x 2 pixels, times 256 if it lies in the odd row of the pair, negated if in the odd column.
-//               With an odd cell width one lane has its two columns in different cells, where BOTH can hold a
-//               survivor: that lane's code covers its even column only and the uncombined 32-bit word goes to a
-//               second, one-word-per-row-pair stash.
+//   stash     = one word per (row pair, lane): per 16-bit half (column) 0, or the stored score of the surviving
+//               pixel of that column, times 256 if it lies in the odd row of the pair.  The two pixels of a column
+//               are neighbours, so a half never holds two survivors; the two halves of a lane can both hold one
+//               only where the lane straddles two cells (odd cell width).
 __host__ __device__ inline int fast_warp_bytes(const int stash_slots)
 {
-    return (16 + kTileRows * kRS * 4 + kTileRows * kRawPitch + (stash_slots + 1) * (64 + 4) + 15) & ~15;
+    return (16 + kTileRows * kRS * 4 + kTileRows * kRawPitch + (stash_slots + 1) * 128 + 15) & ~15;
 }
 
 __global__ void __launch_bounds__(kNT, ORB_FAST_MINBLK) k_fast_bands(const __grid_constant__ OrbPlan plan, const OrbBatch io, const __grid_constant__ FastGrid fg)
@@ -197,8 +197,7 @@ __global__ void __launch_bounds__(kNT, ORB_FAST_MINBLK) k_fast_bands(const __gri
     const uint32_t bar = (uint32_t)__cvta_generic_to_shared(wsm);
     uint32_t* tile = (uint32_t*)(wsm + 16);
     unsigned char* raw = wsm + 16 + kTileRows * kRS * 4;
-    uint16_t* stash = (uint16_t*)(raw + kTileRows * kRawPitch);
-    uint32_t* stash2 = (uint32_t*)(stash + (plan.fast_stash_slots + 1) * 32);   // row pairs of the lane that straddles two cells
+    uint32_t* stash = (uint32_t*)(raw + kTileRows * kRawPitch) + lane;         // this lane's column of the stash; slot 0 is a dummy
     const uint32_t raw_s = (uint32_t)__cvta_generic_to_shared(raw);
 
     // ---- band geometry (src/ORBextractor.cc:826-848): cells cj0 .. cj0+ncb-1 of every cell row
@@ -218,8 +217,6 @@ __global__ void __launch_bounds__(kNT, ORB_FAST_MINBLK) k_fast_bands(const __gri
     const bool vlo = t0 < tw, vhi = t0 + 1 < tw;
     const int clo = (cpb > 1 && t0 >= wc) ? 1 : 0, chi = (cpb > 1 && t0 + 1 >= wc) ? 1 : 0;   // cell of each half
     const uint32_t lm = (vlo ? 0x00003c00u : 0u) | (vhi ? 0x3c000000u : 0u);   // 1.0 in the valid halves
-    const bool straddle = clo != chi;                                          // at most one lane of the warp
-    const unsigned short foldk = straddle ? 0x0000u : 0xbc00u;                 // code = lo + foldk * hi
     // NMS neighbours: (left of lo | left of hi) = (Lw.hi | Cw.lo), (right of lo | right of hi) = (Cw.hi | Rw.lo);
     // a neighbour in another cell, outside the band or in another warp reads byte 1 of the first operand, the
     // high byte of a score below 256, i.e. zero
@@ -233,7 +230,7 @@ __global__ void __launch_bounds__(kNT, ORB_FAST_MINBLK) k_fast_bands(const __gri
     const int iniBias = plan.iniTh - plan.minTh + 1;                                      // stored score of a corner at iniThFAST
     const uint32_t iniV = 0x00010001u * (uint32_t)min(max(iniBias, 1), 1023);          // every survivor is >= 1
     const uint32_t* po = tile + lane;                // odd ring offsets: words po[0..3] = dx -3, -1, +1, +3
-    const uint32_t* pb = tile + kCopyW + lane;       // even ring offsets: words pb[0..2] = dx -2, 0, +2
+                                                     // even ring offsets: words po[kCopyW .. kCopyW+2] = dx -2, 0, +2
     // widening: lane = (sub-row, 8-column group); 27 lanes work on 3 tile rows per pass
     const int wsub = lane / 9, wk = lane - 9 * wsub;
     const uint32_t pitch15 = (uint32_t)pitch & 15u;
@@ -274,6 +271,7 @@ __global__ void __launch_bounds__(kNT, ORB_FAST_MINBLK) k_fast_bands(const __gri
         if (eh <= 0) break;
         uint32_t u = 0, m = 0, carry = 0;                              // scores of the two rows above; even-row survivors
         uint32_t cntAll = 0, cntA = 0;                                 // survivors / survivors at iniThFAST per column (fp16 counts)
+        uint32_t smask = 0, sbit = 1;                                  // stash slots (index, i.e. row pair + 1) of this lane that hold a survivor
 
         for (int ya = 0; ya < eh; ya += kR) {
             const int nr = min(eh - ya, kR), trows = nr + 6;
@@ -314,9 +312,7 @@ __global__ void __launch_bounds__(kNT, ORB_FAST_MINBLK) k_fast_bands(const __gri
                 if (ny >= 0) fetch(ny, nt);
             }
             // ---- scores, NMS of the row above, survivor record; rows ya .. ya+nr-1, two per step
-            const uint32_t* a = po;
-            const uint32_t* b = pb;
-            uint16_t* st = stash + ((ya >> 1) * 32 + lane);            // slot of rows (ya-2, ya-1) = index ya/2; slot index is shifted by one, slot 0 is a dummy
+            uint32_t* st = stash + (ya >> 1) * 32;                     // rows (ya-2, ya-1) = slot index ya/2: indices are shifted by one
             auto score = [&](const uint32_t* a, const uint32_t* b) -> uint32_t {
                 uint32_t E[16];
                 E[0] = b[6 * kRS + 1];    //  ( 0, 3)
@@ -352,33 +348,33 @@ __global__ void __launch_bounds__(kNT, ORB_FAST_MINBLK) k_fast_bands(const __gri
                 cntA = hadd2(cntA, hsetge2(s, iniV));
                 return s;
             };
-            // code of a row pair: even-row survivor se, odd-row survivor so
-            auto record = [&](uint16_t* slot, const uint32_t se, const uint32_t so) {
-                const uint32_t w = hfma2(so, 0x5c005c00u, se);            // se + 256 * so: at most one of the four halves is non-zero (one per half in the straddling lane)
-                uint16_t c;
-                asm("{ .reg .b16 lo, hi; mov.b32 {lo, hi}, %1; fma.rn.f16 %0, hi, %2, lo; }" : "=h"(c) : "r"(w), "h"(foldk));
-                *slot = c;
-                if (straddle) stash2[(slot - stash) >> 5] = w;
+            // word of a row pair: even-row survivors se, odd-row survivors so (scores are fp16 denormals: the bits are the integers)
+            auto record = [&](uint32_t* slot, const uint32_t se, const uint32_t so) {
+                uint32_t w;
+                asm("mad.lo.u32 %0, %1, 256, %2;" : "=r"(w) : "r"(so), "r"(se));
+                *slot = w;
+                if (w) smask |= sbit;
+                sbit += sbit;
             };
             int r = 0;
 #pragma unroll 1
-            for (; r + 2 <= nr; r += 2, a += 2 * kRS, b += 2 * kRS, st += 32) {
-                const uint32_t d0 = score(a, b);
-                const uint32_t d1 = score(a + kRS, b + kRS);
+            for (; r + 2 <= nr; r += 2, st += 32) {
+                const uint32_t* a = po + r * kRS;
+                const uint32_t d0 = score(a, a + kCopyW);
+                const uint32_t d1 = score(a + kRS, a + kRS + kCopyW);
                 const uint32_t so = nms(u, m, d0);                        // survivors of the odd row above d0
                 record(st, carry, so);
                 carry = nms(m, d0, d1);                                   // survivors of the even row d0
                 u = d0; m = d1;
             }
             if (r < nr) {                                                 // single last row (even index): only at the end of a cell row
-                const uint32_t d0 = score(a, b);
+                const uint32_t* a = po + r * kRS;
+                const uint32_t d0 = score(a, a + kCopyW);
                 const uint32_t so = nms(u, m, d0);
                 record(st, carry, so);
                 st += 32;
-                carry = 0;
-                u = m; m = d0;
                 // the row below is outside the cell: finish now, this row is the even row of its pair
-                const uint32_t se = nms(u, m, 0u);
+                const uint32_t se = nms(m, d0, 0u);
                 record(st, se, 0u);
             } else if (ya + kR >= eh) {                                   // the cell row ended on an odd row
                 const uint32_t so = nms(u, m, 0u);
@@ -388,7 +384,6 @@ __global__ void __launch_bounds__(kNT, ORB_FAST_MINBLK) k_fast_bands(const __gri
         __syncwarp();
 
         // ---- per-cell cut-off (:857-861), one atomic per cell row and band, every lane writes its own survivors
-        const int nslots = (eh + 1) >> 1;
         // survivors of iniThFAST per cell; the fp16 counts are exact (at most one per row pair and column)
         const bool aLo = (cntA & 0x7fffu) != 0, aHi = (cntA >> 16 & 0x7fffu) != 0;
         const uint32_t any0 = __ballot_sync(0xffffffffu, (aLo && clo == 0) || (aHi && chi == 0));
@@ -405,28 +400,29 @@ __global__ void __launch_bounds__(kNT, ORB_FAST_MINBLK) k_fast_bands(const __gri
             int base = 0;
             if (lane == 0) base = atomicAdd(&io.cand_count[frame * ORB_MAX_LEVELS + l], total);
             base = __shfl_sync(0xffffffffu, base, 0);
-            int slot = base + incl - mine;
+            const int slot = base + incl - mine;
             uint32_t* out = io.cand + (size_t)frame * plan.cand_per_frame + L.cand_off;
-            const uint16_t* sp = stash + 32 + lane;
-            uint32_t mask = 0;                                          // this lane's row pairs that hold a survivor
-            if (mine) for (int j = 0; j < nslots; ++j) if (sp[32 * j] & 0x7fffu) mask |= 1u << j;
-            uint32_t mask2 = 0;                                         // the odd column of the straddling lane
-            if (mine && straddle) for (int j = 0; j < nslots; ++j) if (stash2[j + 1] >> 16) mask2 |= 1u << j;
-            while (mask | mask2) {
-                const bool second = mask == 0;
-                const uint32_t mm = second ? mask2 : mask;
-                const int j = __ffs((int)mm) - 1;
-                if (second) mask2 &= mask2 - 1; else mask &= mask - 1;
-                const uint32_t c = second ? (stash2[j + 1] >> 16) | 0x8000u : sp[32 * j];
-                const int hi = (int)(c >> 15);
-                const int n = __float2int_rn(__half2float(__ushort_as_half((unsigned short)(c & 0x7fffu))) * 16777216.0f);
-                const int odd = n >= 256 ? 1 : 0;
-                const int sc = odd ? n >> 8 : n;
+            uint32_t* outp = out + slot;
+            const int room = L.cand_cap - slot;                         // entries this lane may still write (the capacity is a proven bound)
+            int wrote = 0;
+            const int xb = X0 + t0 + 3, yb = ci * hc + 3 - 2, sb = plan.minTh - 1;   // slot index i holds rows 2i-2, 2i-1
+            auto emit = [&](const uint32_t v, const int hi, const int i) {
+                const int odd = v > 255u ? 1 : 0;
+                const int sc = (int)(odd ? v >> 8 : v);
                 if (sc >= iniBias || !(hi ? iniHi : iniLo)) {
                     // border-frame coordinates (src/ORBextractor.cc:868-869): cell-local + (j*wCell, i*hCell)
-                    if (slot < L.cand_cap) out[slot] = orb_pack(X0 + t0 + hi + 3, ci * hc + 2 * j + odd + 3, sc + plan.minTh - 1);
-                    ++slot;
+                    if (wrote < room) outp[wrote] = orb_pack(xb + hi, yb + 2 * i + odd, sc + sb);
+                    ++wrote;
                 }
+            };
+            while (smask) {
+                const int i = __ffs((int)smask) - 1;
+                smask &= smask - 1;
+                const uint32_t w = stash[32 * i];
+                const uint32_t lo = w & 0xffffu;
+                const int hi = lo == 0u ? 1 : 0;
+                emit(hi ? w >> 16 : lo, hi, i);
+                if (lo != 0u && (w >> 16) != 0u) emit(w >> 16, 1, i);  // both halves: only the lane that straddles two cells
             }
         }
         __syncwarp();                                                   // the next cell row reuses the stash

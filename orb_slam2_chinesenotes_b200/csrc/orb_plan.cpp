@@ -118,8 +118,8 @@ int orb_plan_build(const OrbParams* p, int w, int h, OrbPlan* plan, std::vector<
                 }
             }
             // orb_fast.cu: a warp takes a band of one or two cells (at most ORB_FAST_BAND evaluated columns) and
-            // keeps one 16-bit code per row pair and lane; the slot mask of a lane is 32 bits wide
-            if (L.wCell > ORB_FAST_BAND || L.hCell > 64) return 1;
+            // keeps one word per row pair and lane; the slot mask of a lane is 32 bits wide (31 row pairs + a dummy)
+            if (L.wCell > ORB_FAST_BAND || L.hCell > 62) return 1;
             if ((L.hCell + 1) / 2 > plan->fast_stash_slots) plan->fast_stash_slots = (L.hCell + 1) / 2;
             // order key (cell, y-in-cell, x-in-cell) must fit 24 bits
             if ((long long)L.ncx * L.ncy * L.wCell * L.hCell >= (1 << 24)) return 1;
