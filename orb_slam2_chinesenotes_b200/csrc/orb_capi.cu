@@ -47,6 +47,7 @@ struct Slot {
     DevBuf img_stage, pyr, blur, cand, node_of, counts, lkp, out_kps, out_desc, out_n;
     DevBuf st_sad, st_sorted, st_rows, out_ur, out_depth, out_ns;   // stereo: scratch and staged mvuRight / mvDepth / counts
     int frames = 0;                       // frames the work buffers are sized for
+    OrbFastMaps fmaps;                    // FAST's tensor maps for the batch layout last seen in this slot
     cudaEvent_t h2d_done = nullptr, compute_done = nullptr, d2h_done = nullptr;
     cudaStream_t aux = nullptr;            // the blur runs here, beside FAST + quadtree (both only need the pyramid)
     cudaEvent_t pyr_done = nullptr, blur_done = nullptr;
@@ -245,7 +246,7 @@ int enqueue_chunk(orbx_ctx* c, Slot& s, cudaStream_t st, const uint8_t* d_img, s
     CU(c, cudaMemsetAsync(io.cand_count, 0, (size_t)frames * ORB_MAX_LEVELS * 4, st));
     { StageScope t(c, ORBX_STAGE_PYRAMID, st); CU(c, orb_launch_pyramid(P, io, frames, st)); }
     if (c->profile) {
-        { StageScope t(c, ORBX_STAGE_FAST, st); CU(c, orb_launch_fast(P, io, frames, st)); }
+        { StageScope t(c, ORBX_STAGE_FAST, st); CU(c, orb_launch_fast(P, io, frames, st, &s.fmaps)); }
         { StageScope t(c, ORBX_STAGE_BLUR, st); CU(c, orb_launch_blur(P, io, frames, st)); }
         { StageScope t(c, ORBX_STAGE_OCTREE, st); CU(c, orb_launch_octree(P, io, frames, st)); }
     } else {
@@ -253,7 +254,7 @@ int enqueue_chunk(orbx_ctx* c, Slot& s, cudaStream_t st, const uint8_t* d_img, s
         CU(c, cudaStreamWaitEvent(s.aux, s.pyr_done, 0));
         CU(c, orb_launch_blur(P, io, frames, s.aux));
         CU(c, cudaEventRecord(s.blur_done, s.aux));
-        CU(c, orb_launch_fast(P, io, frames, st));
+        CU(c, orb_launch_fast(P, io, frames, st, &s.fmaps));
         CU(c, orb_launch_octree(P, io, frames, st));
         CU(c, cudaStreamWaitEvent(st, s.blur_done, 0));
     }

@@ -10,10 +10,12 @@
 //   * ONE WARP = ONE BAND: up to 64 evaluated columns (one or two 30-px cells) walked down their cell rows by a
 //     warp that shares nothing with any other warp -- no block barrier anywhere, only __syncwarp and the warp's
 //     own mbarrier.  A lane owns the pixel pair (2p, 2p+1) of the band, whatever cell each pixel lies in.
-//   * DATA PATH: lane r of the warp issues one bulk asynchronous copy (cp.async.bulk, the TMA unit) per image row
-//     of the next chunk into the warp's raw buffer and the warp's mbarrier counts the bytes; the copy of chunk
-//     k+1 is in flight while chunk k is scored.  Rows are fetched from the 16-byte aligned address at or below
-//     their first pixel, so any pitch and any level works (level 0 is the caller's image, untouched).
+//   * DATA PATH: the TMA unit.  Where the level's layout is 16-byte aligned (every pyramid level; level 0 when the
+//     caller's base, pitch and frame stride allow) ONE tensor-map copy (cp.async.bulk.tensor.3d: x, y, frame)
+//     brings the whole chunk, starting at the 16-byte aligned column at or below its first pixel; otherwise lane r of the warp issues one bulk copy
+//     (cp.async.bulk) for image row r from the 16-byte aligned address at or below its first pixel, so any pitch
+//     works (level 0 is the caller's image, untouched).  The warp's mbarrier counts the bytes; the copy of chunk
+//     k+1 is in flight while chunk k is scored.
 //   * WIDENING on the LSU and FMA pipes: the raw bytes are re-read one by one (LDS.U8 has no alignment rule, so
 //     no funnel shifts) and paired with one IMAD each into the two 16-bit copies of the tile -- copy A holds the
 //     pixel pairs that start on an even tile column, copy B those that start on an odd one -- so every ring
@@ -47,7 +49,9 @@
 // reaches it, else minThFAST.
 #include "orb_device.cuh"
 #include "orb_launch.h"
+#include <cuda.h>
 #include <cuda_fp16.h>
+#include <cstring>
 
 #ifndef ORB_FAST_R
 #define ORB_FAST_R 16         // evaluated rows per chunk (even); the tile holds R + 6 rows
@@ -69,7 +73,9 @@ constexpr int kR = ORB_FAST_R;
 constexpr int kTileRows = kR + 6;
 constexpr int kCopyW = 36;                 // 32-bit words per copy of a tile row (72 pixels)
 constexpr int kRS = 2 * kCopyW;            // tile row: [copy A][copy B]
-constexpr int kRawPitch = 96;              // bytes per raw row: 15 (alignment) + 70 pixels, rounded up to 16
+constexpr int kRawPitch = 96;              // bytes per raw row, row-by-row copies: 15 (alignment) + 70 pixels, rounded up to 16
+constexpr int kBoxW = kRawPitch;           // tensor-map copies: the box starts at the 16-byte aligned column at or below the first pixel (measured: the TMA
+                                           // unit raises an illegal-instruction fault on an innermost coordinate that is not a multiple of 16 bytes)
 constexpr int kNT = 32 * ORB_FAST_WPB;
 static_assert(kR % 2 == 0 && kR >= 2, "chunks hold whole row pairs");
 static_assert(kTileRows <= 32, "one lane per tile row issues the bulk copy");
@@ -156,15 +162,24 @@ __device__ __forceinline__ void bulk_g2s(const uint32_t dst, const void* src, co
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
+__device__ __forceinline__ void tensor_g2s(const uint32_t dst, const void* map, const int x, const int y, const int z, const uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(z), "r"(bar) : "memory");
+}
+
+struct alignas(64) FastMapsArg { unsigned char map[ORB_MAX_LEVELS][128]; };
+
 // Which (level, band group, cell rows) a block works on: filled per launch (rows_per_block follows the batch
 // size: whole band columns for big batches, single cell rows when few frames must fill the GPU).
 struct FastGrid {
     int first[ORB_MAX_LEVELS + 1];   // first block of each level; [nlevels] = total
     int rows_per_block;
+    unsigned tensor_levels;          // bit l: level l is fetched through its tensor map
 };
 
-// Per-warp shared memory: [mbarrier, 16 B][tile: kTileRows x kRS words][raw: kTileRows x kRawPitch bytes][stash:
-// (slots + 1) x 32 codes of 16 bits].
+// Per-warp shared memory: [raw: kTileRows x kRawPitch bytes, 128-byte aligned (tensor-map copies demand it)][tile:
+// kTileRows x kRS words][stash: (slots + 1) x 32 words][mbarrier].
 //   tile row  = [copy A: 36 words][copy B: 36 words]; tile column u = band column t + 3 (the 3-px ring apron on the
 //               left); copy A word j = tile columns (2j, 2j+1), copy B word j = columns (2j+1, 2j+2).  Lane p
 //               scores band columns (2p, 2p+1), i.e. tile columns (2p+3, 2p+4): ring offsets dx = -2, 0, +2 are
@@ -175,12 +190,13 @@ struct FastGrid {
 //               only where the lane straddles two cells (odd cell width).
 __host__ __device__ inline int fast_warp_bytes(const int stash_slots)
 {
-    return (16 + kTileRows * kRS * 4 + kTileRows * kRawPitch + (stash_slots + 1) * 128 + 15) & ~15;
+    return (((kTileRows * kRawPitch + 127) & ~127) + kTileRows * kRS * 4 + (stash_slots + 1) * 128 + 16 + 127) & ~127;
 }
 
-__global__ void __launch_bounds__(kNT, ORB_FAST_MINBLK) k_fast_bands(const __grid_constant__ OrbPlan plan, const OrbBatch io, const __grid_constant__ FastGrid fg)
+__global__ void __launch_bounds__(kNT, ORB_FAST_MINBLK) k_fast_bands(const __grid_constant__ OrbPlan plan, const OrbBatch io, const __grid_constant__ FastGrid fg,
+                                                                      const __grid_constant__ FastMapsArg maps)
 {
-    extern __shared__ __align__(16) unsigned char fast_smem[];
+    extern __shared__ __align__(128) unsigned char fast_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int l = 0;
     while (l + 1 < plan.nlevels && (int)blockIdx.x >= fg.first[l + 1]) ++l;
@@ -194,10 +210,10 @@ __global__ void __launch_bounds__(kNT, ORB_FAST_MINBLK) k_fast_bands(const __gri
     const int ci0 = rb * fg.rows_per_block, ci1 = min(L.ncy, ci0 + fg.rows_per_block);
 
     unsigned char* wsm = fast_smem + (size_t)warp * fast_warp_bytes(plan.fast_stash_slots);
-    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(wsm);
-    uint32_t* tile = (uint32_t*)(wsm + 16);
-    unsigned char* raw = wsm + 16 + kTileRows * kRS * 4;
-    uint32_t* stash = (uint32_t*)(raw + kTileRows * kRawPitch) + lane;         // this lane's column of the stash; slot 0 is a dummy
+    unsigned char* raw = wsm;
+    uint32_t* tile = (uint32_t*)(wsm + ((kTileRows * kRawPitch + 127) & ~127));
+    uint32_t* stash = tile + kTileRows * kRS + lane;                           // this lane's column of the stash; slot 0 is a dummy
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(tile + kTileRows * kRS + (plan.fast_stash_slots + 1) * 32);
     const uint32_t raw_s = (uint32_t)__cvta_generic_to_shared(raw);
 
     // ---- band geometry (src/ORBextractor.cc:826-848): cells cj0 .. cj0+ncb-1 of every cell row
@@ -211,6 +227,9 @@ __global__ void __launch_bounds__(kNT, ORB_FAST_MINBLK) k_fast_bands(const __gri
     int pitch;
     const uint8_t* src = orb_level_ptr(plan, io, frame, l, &pitch);
     src += ORB_BORDER0 + X0;                                           // level address of tile column 0, row 0
+    const bool tensor = (fg.tensor_levels >> l) & 1u;                  // one tensor-map copy per chunk; else one bulk copy per row
+    const void* tmap = maps.map[l];
+    const int tx0 = (ORB_BORDER0 + X0) & ~15;                          // first column of the tensor box
 
     // ---- this lane's pixel pair: band columns t0 = 2 * lane (lo half) and t0 + 1 (hi half)
     const int t0 = 2 * lane;
@@ -233,7 +252,7 @@ __global__ void __launch_bounds__(kNT, ORB_FAST_MINBLK) k_fast_bands(const __gri
                                                      // even ring offsets: words po[kCopyW .. kCopyW+2] = dx -2, 0, +2
     // widening: lane = (sub-row, 8-column group); 27 lanes work on 3 tile rows per pass
     const int wsub = lane / 9, wk = lane - 9 * wsub;
-    const uint32_t pitch15 = (uint32_t)pitch & 15u;
+    const uint32_t pitch15 = tensor ? 0u : (uint32_t)pitch & 15u;
 
     if (lane == 0) mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -243,6 +262,15 @@ __global__ void __launch_bounds__(kNT, ORB_FAST_MINBLK) k_fast_bands(const __gri
     // 16-byte aligned address at or below its first pixel; the bytes stay inside the image row (the band starts
     // at column >= 16 and its last tile column lies >= 16 pixels before the row's end).
     auto fetch = [&](const int y, const int trows) {
+        if (tensor) {
+            // the whole box (kTileRows rows, zero filled outside the image) always arrives
+            if (lane == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the raw rows were read through the generic proxy
+                mbar_expect_tx(bar, kBoxW * kTileRows);
+                tensor_g2s(raw_s, tmap, tx0, y, frame, bar);
+            }
+            return;
+        }
         uint32_t bytes = 0;
         const uint8_t* q = nullptr;
         if (lane < trows) {
@@ -279,7 +307,7 @@ __global__ void __launch_bounds__(kNT, ORB_FAST_MINBLK) k_fast_bands(const __gri
             parity ^= 1u;
             // ---- widen: raw bytes -> copies A and B
             {
-                const uint32_t s0 = (uint32_t)((uintptr_t)(src + (size_t)(y0 + ya) * pitch) & 15u);
+                const uint32_t s0 = tensor ? (uint32_t)(ORB_BORDER0 + X0 - tx0) : (uint32_t)((uintptr_t)(src + (size_t)(y0 + ya) * pitch) & 15u);
                 if (wsub < 3) {
                     uint32_t s = (s0 + (uint32_t)wsub * pitch15) & 15u;
                     const uint32_t sstep = (3u * pitch15) & 15u;
@@ -434,7 +462,53 @@ size_t orb_fast_smem_bytes(const OrbPlan& plan)
     return (size_t)ORB_FAST_WPB * fast_warp_bytes(plan.fast_stash_slots);
 }
 
-cudaError_t orb_launch_fast(const OrbPlan& plan, const OrbBatch& io, int batch, cudaStream_t st)
+// ---- host: tensor maps.  cuTensorMapEncodeTiled comes from the driver (no link dependency on libcuda).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &p, 12000, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) { cudaGetLastError(); return nullptr; }
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
+// u8 tensor (x, y, frame) of one level; false when the layout is not 16-byte aligned
+static bool encode_level(unsigned char* out, const void* base, int w, int h, int pitch, size_t frame_stride, int frames)
+{
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn || ((uintptr_t)base & 15u) || (pitch & 15) || (frame_stride & 15u) || pitch < w) return false;
+    const cuuint64_t dims[3] = { (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)frames };
+    const cuuint64_t strides[2] = { (cuuint64_t)pitch, (cuuint64_t)(frames > 1 ? frame_stride : (size_t)pitch * h + 16 & ~(size_t)15) };
+    const cuuint32_t box[3] = { (cuuint32_t)kBoxW, (cuuint32_t)kTileRows, 1u };
+    const cuuint32_t estr[3] = { 1u, 1u, 1u };
+    alignas(64) CUtensorMap m;
+    if (fn(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return false;
+    static_assert(sizeof(CUtensorMap) == 128, "descriptor size");
+    memcpy(out, &m, 128);
+    return true;
+}
+
+static void fast_maps_update(const OrbPlan& plan, const OrbBatch& io, int batch, OrbFastMaps* M)
+{
+    if (M->key_img0 == io.img0 && M->key_pyr == io.pyr && M->key_stride == io.img0_stride && M->key_pitch == io.img0_pitch && M->key_batch == batch &&
+        M->key_w == plan.w && M->key_h == plan.h && M->key_levels == plan.nlevels) return;
+    M->use = 0;
+    for (int l = 0; l < plan.nlevels; ++l) {
+        const OrbLevel& L = plan.lv[l];
+        const bool ok = l == 0 ? encode_level(M->map[0], io.img0, L.w, L.h, io.img0_pitch, io.img0_stride, batch)
+                               : encode_level(M->map[l], io.pyr + L.img_off, L.w, L.h, L.pitch, plan.pyr_bytes, batch);
+        if (ok) M->use |= 1u << l;
+    }
+    M->key_img0 = io.img0; M->key_pyr = io.pyr; M->key_stride = io.img0_stride; M->key_pitch = io.img0_pitch; M->key_batch = batch;
+    M->key_w = plan.w; M->key_h = plan.h; M->key_levels = plan.nlevels;
+}
+
+cudaError_t orb_launch_fast(const OrbPlan& plan, const OrbBatch& io, int batch, cudaStream_t st, OrbFastMaps* maps)
 {
     if (plan.total_cells == 0) return cudaSuccess;
     const size_t smem = orb_fast_smem_bytes(plan);
@@ -456,6 +530,11 @@ cudaError_t orb_launch_fast(const OrbPlan& plan, const OrbBatch& io, int batch, 
     }
     for (int l = plan.nlevels; l <= ORB_MAX_LEVELS; ++l) fg.first[l] = n;
     if (n == 0) return cudaSuccess;
-    k_fast_bands<<<dim3(n, batch), kNT, smem, st>>>(plan, io, fg);
+    OrbFastMaps local;                                       // callers without a cache: encoded per launch
+    if (!maps) maps = &local;
+    fast_maps_update(plan, io, batch, maps);
+    fg.tensor_levels = maps->use;
+    static_assert(sizeof(FastMapsArg) == sizeof(maps->map), "descriptor block");
+    k_fast_bands<<<dim3(n, batch), kNT, smem, st>>>(plan, io, fg, *reinterpret_cast<const FastMapsArg*>(maps->map));
     return cudaGetLastError();
 }

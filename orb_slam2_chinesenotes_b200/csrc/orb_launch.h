@@ -9,7 +9,16 @@ size_t orb_fast_smem_bytes(const OrbPlan& plan);
 size_t orb_octree_smem_bytes(const OrbPlan& plan);
 cudaError_t orb_launch_pyramid(const OrbPlan& plan, const OrbBatch& io, int batch, cudaStream_t st);
 cudaError_t orb_launch_blur(const OrbPlan& plan, const OrbBatch& io, int batch, cudaStream_t st);
-cudaError_t orb_launch_fast(const OrbPlan& plan, const OrbBatch& io, int batch, cudaStream_t st);
+// FAST fetches its tiles with one tensor-map TMA copy per chunk wherever the level's base address, row pitch and
+// frame stride are multiples of 16 bytes (all pyramid levels; level 0 when the caller's layout allows).  The
+// descriptors of one batch layout are cached here (one per extractor slot) and only re-encoded when it changes.
+struct alignas(64) OrbFastMaps {
+    unsigned char map[ORB_MAX_LEVELS][128];   // CUtensorMap per level
+    unsigned use = 0;                          // bit l: level l has a valid descriptor
+    const void* key_img0 = nullptr; const void* key_pyr = nullptr;
+    size_t key_stride = 0; int key_pitch = 0, key_batch = 0, key_w = 0, key_h = 0, key_levels = 0;
+};
+cudaError_t orb_launch_fast(const OrbPlan& plan, const OrbBatch& io, int batch, cudaStream_t st, OrbFastMaps* maps = nullptr);
 cudaError_t orb_launch_octree(const OrbPlan& plan, const OrbBatch& io, int batch, cudaStream_t st);
 cudaError_t orb_launch_describe(const OrbPlan& plan, const OrbBatch& io, int batch, cudaStream_t st);
 cudaError_t orb_launch_border(const uint8_t* src, int w, int h, int spitch, uint8_t* dst, int dpitch, int b, cudaStream_t st);
