@@ -54,19 +54,22 @@
 #include <cstring>
 
 #ifndef ORB_FAST_R
-#define ORB_FAST_R 16         // evaluated rows per chunk (even); the tile holds R + 6 rows
+#define ORB_FAST_R 16         // evaluated rows per chunk (even); the tile holds R + 6 rows (per 512 frames: 10 rows 2.12 ms, 12 1.99, 14 2.02, 16 1.99, 20 2.06, 24 2.14)
 #endif
 #ifndef ORB_FAST_WPB
-#define ORB_FAST_WPB 2        // warps (bands) per block; the warps of a block share nothing
+#define ORB_FAST_WPB 1        // warps (bands) per block; the warps of a block share nothing (per 512 frames: 1 warp 1.99 ms, 2 warps 2.07, 4 warps 2.06)
 #endif
 #ifndef ORB_FAST_FMA
 #define ORB_FAST_FMA 0x00ffu  // bit j: first-stage pair j, bit 8+j: lo/hi pair j computed on the FMA pipe
 #endif
 #ifndef ORB_FAST_FULLCOL
-#define ORB_FAST_FULLCOL 64   // frames per launch from which a warp walks a whole band column
+#define ORB_FAST_FULLCOL 256  // frames per launch from which a warp walks a whole band column
+#endif
+#ifndef ORB_FAST_MIDROWS
+#define ORB_FAST_MIDROWS 2    // cell rows per warp for 16 .. ORB_FAST_FULLCOL-1 frames (64 frames: 2 rows 0.27 ms, 4 rows 0.29, whole columns 0.35)
 #endif
 #ifndef ORB_FAST_MINBLK
-#define ORB_FAST_MINBLK 10    // resident blocks per SM the register allocation must allow
+#define ORB_FAST_MINBLK 16    // resident blocks per SM the register allocation must allow
 #endif
 
 constexpr int kR = ORB_FAST_R;
@@ -309,14 +312,10 @@ __global__ void __launch_bounds__(kNT, ORB_FAST_MINBLK) k_fast_bands(const __gri
             {
                 const uint32_t s0 = tensor ? (uint32_t)(ORB_BORDER0 + X0 - tx0) : (uint32_t)((uintptr_t)(src + (size_t)(y0 + ya) * pitch) & 15u);
                 if (wsub < 3) {
-                    uint32_t s = (s0 + (uint32_t)wsub * pitch15) & 15u;
-                    const uint32_t sstep = (3u * pitch15) & 15u;
-                    const unsigned char* rp = raw + wsub * kRawPitch + 8 * wk;
-                    uint32_t* dst = tile + wsub * kRS + 4 * wk;
-                    for (int r = wsub; r < trows; r += 3, rp += 3 * kRawPitch, dst += 3 * kRS, s = (s + sstep) & 15u) {
+                    auto widen_row = [&](const unsigned char* rq, uint32_t* dst) {
                         uint32_t b[9];
 #pragma unroll
-                        for (int i = 0; i < 9; ++i) b[i] = rp[s + i];         // LDS.U8: no alignment rule, no funnel shift
+                        for (int i = 0; i < 9; ++i) b[i] = rq[i];             // LDS.U8: no alignment rule, no funnel shift
                         uint32_t A[4], B[4];
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
@@ -325,6 +324,16 @@ __global__ void __launch_bounds__(kNT, ORB_FAST_MINBLK) k_fast_bands(const __gri
                         }
                         *(uint4*)dst = make_uint4(A[0], A[1], A[2], A[3]);
                         *(uint4*)(dst + kCopyW) = make_uint4(B[0], B[1], B[2], B[3]);
+                    };
+                    const unsigned char* rp = raw + wsub * kRawPitch + 8 * wk;
+                    uint32_t* dst = tile + wsub * kRS + 4 * wk;
+                    if (pitch15 == 0) {                                        // every row starts at the same offset inside its 16 bytes
+                        rp += s0;
+                        for (int r = wsub; r < trows; r += 3, rp += 3 * kRawPitch, dst += 3 * kRS) widen_row(rp, dst);
+                    } else {
+                        uint32_t s = (s0 + (uint32_t)wsub * pitch15) & 15u;
+                        const uint32_t sstep = (3u * pitch15) & 15u;
+                        for (int r = wsub; r < trows; r += 3, rp += 3 * kRawPitch, dst += 3 * kRS, s = (s + sstep) & 15u) widen_row(rp + s, dst);
                     }
                 }
             }
@@ -521,7 +530,7 @@ cudaError_t orb_launch_fast(const OrbPlan& plan, const OrbBatch& io, int batch, 
     int maxrows = 1;
     for (int l = 0; l < plan.nlevels; ++l) if (plan.lv[l].ncy > maxrows) maxrows = plan.lv[l].ncy;
     FastGrid fg;
-    fg.rows_per_block = batch >= ORB_FAST_FULLCOL ? maxrows : batch >= 16 ? 4 : 1;
+    fg.rows_per_block = batch >= ORB_FAST_FULLCOL ? maxrows : batch >= 16 ? ORB_FAST_MIDROWS : 1;
     int n = 0;
     for (int l = 0; l < plan.nlevels; ++l) {
         fg.first[l] = n;
