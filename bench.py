@@ -94,22 +94,28 @@ def measured_traffic(kernel, frames_per_launch):
         return None
 
 
-def synth_batch_torch(batch, w, h, seed, device):
-    """Synthetic frames on the GPU: smoothed noise, mean 128 / std 48, low-contrast bottom band,
-    hard-edged rectangles (the recipe of tests/synth.py, generated with torch for speed)."""
+GEN_BLOCK = 32   # frames are generated in blocks of 32 whose random streams depend on the GLOBAL block index only
+
+
+def synth_frames_torch(first, count, w, h, seed, device):
+    """Synthetic frames [first, first+count) of the endless sequence `seed`: smoothed noise, mean 128 / std 48,
+    low-contrast bottom band, hard-edged rectangles (the recipe of tests/synth.py, generated with torch for speed).
+    A frame depends only on (seed, its global index), so any rank / any arm can produce any block of the sequence;
+    `first` must be a multiple of GEN_BLOCK."""
     import torch
     import torch.nn.functional as F
-    g = torch.Generator(device=device).manual_seed(seed)
-    out = torch.empty((batch, h, w), dtype=torch.uint8, device=device)
+    assert first % GEN_BLOCK == 0
+    out = torch.empty((count, h, w), dtype=torch.uint8, device=device)
     sigma, r = 2.5, 8
     x = torch.arange(-r, r + 1, device=device, dtype=torch.float32)
     k = torch.exp(-0.5 * (x / sigma) ** 2)
     k = k / k.sum()
-    rng = np.random.default_rng(seed)
-    step = 32
-    for b0 in range(0, batch, step):
-        nb = min(step, batch - b0)
-        n = torch.randint(0, 256, (nb, 1, h, w), generator=g, device=device, dtype=torch.uint8).float()
+    for b0 in range(0, count, GEN_BLOCK):
+        nb = min(GEN_BLOCK, count - b0)
+        blk = (first + b0) // GEN_BLOCK
+        g = torch.Generator(device=device).manual_seed(seed * 1000003 + blk)
+        rng = np.random.default_rng([seed, blk])
+        n = torch.randint(0, 256, (GEN_BLOCK, 1, h, w), generator=g, device=device, dtype=torch.uint8)[:nb].float()
         n = F.conv2d(F.pad(n, (r, r, 0, 0), mode="reflect"), k.view(1, 1, 1, -1))
         n = F.conv2d(F.pad(n, (0, 0, r, r), mode="reflect"), k.view(1, 1, -1, 1))
         n = n[:, 0]
@@ -125,23 +131,36 @@ def synth_batch_torch(batch, w, h, seed, device):
     return out
 
 
-def stereo_right_torch(left, seed):
-    """Right images for a batch of left images (tests/synth.py stereo_pair): every block of 16..63 rows is the left
-    block shifted by its own disparity of 5..60 px, plus +-2 grey levels of noise."""
+def stereo_right_torch(left, first, seed):
+    """Right images for left images [first, first+len) (tests/synth.py stereo_pair): every block of 16..63 rows is the
+    left block shifted by its own disparity of 5..60 px, plus +-2 grey levels of noise; depends on (seed, index) only."""
     import torch
     b, h, w = left.shape
-    rng = np.random.default_rng(seed + 7919)
     right = torch.empty_like(left)
     for i in range(b):
+        rng = np.random.default_rng([seed + 7919, first + i])
         y = 0
         while y < h:
             bh, d = int(rng.integers(16, 64)), int(rng.integers(5, 61))
             right[i, y:y + bh, :w - d] = left[i, y:y + bh, d:]
             right[i, y:y + bh, w - d:] = left[i, y:y + bh, w - d - 1:w - d]
             y += bh
-    g = torch.Generator(device=left.device).manual_seed(seed + 1)
-    noise = torch.randint(-2, 3, right.shape, generator=g, device=left.device, dtype=torch.int16)
-    return (right.to(torch.int16) + noise).clamp_(0, 255).to(torch.uint8)
+        g = torch.Generator(device=left.device).manual_seed((seed + 1) * 1000003 + first + i)
+        noise = torch.randint(-2, 3, (h, w), generator=g, device=left.device, dtype=torch.int16)
+        right[i] = (right[i].to(torch.int16) + noise).clamp_(0, 255).to(torch.uint8)
+    return right
+
+
+def workload_frames(workload, first, count, device):
+    """Frames [first, first+count) of a workload's input sequence (stereo workloads: L0,R0,L1,R1,...; first and count even)."""
+    import torch
+    w, h, _, _ = WORKLOADS[workload]
+    seed = 2000 + sorted(WORKLOADS).index(workload)
+    if workload in STEREO:
+        assert first % 2 == 0 and count % 2 == 0 and (first // 2) % GEN_BLOCK == 0
+        left = synth_frames_torch(first // 2, count // 2, w, h, seed, device)
+        return torch.stack([left, stereo_right_torch(left, first // 2, seed)], dim=1).reshape(count, h, w).contiguous()
+    return synth_frames_torch(first, count, w, h, seed, device)
 
 
 class ClockSampler:
@@ -219,40 +238,55 @@ def cpu_stereo_frames_per_s(frames_np, nfeatures, threads):
 
 
 def cpu_workload_frames_per_s(workload, frames_np, nfeatures, cores):
-    """(frames/s, kind, what ran) of the CPU implementation of one bench workload."""
+    """(frames/s, kind, what ran, keypoints found) of the CPU implementation of one bench workload."""
     if workload in STEREO:
         r = cpu_stereo_frames_per_s(frames_np, nfeatures, cores)
         if r is not None:
-            return r[0], "reference", f"stereo Frame constructor, {max(cores // 2, 1)} frames in flight x 2 extractor threads"
-    v, kind, _ = cpu_frames_per_s(frames_np, nfeatures, cores)
-    return v, kind, f"{cores} threads, one extractor per thread" + (" (extraction only)" if workload in STEREO else "")
+            return r[0], "reference", f"stereo Frame constructor, {max(cores // 2, 1)} frames in flight x 2 extractor threads", r[1]
+    v, kind, tot = cpu_frames_per_s(frames_np, nfeatures, cores)
+    return v, kind, f"{cores} threads, one extractor per thread" + (" (extraction only)" if workload in STEREO else ""), tot
+
+
+def workload_config(workload, batch, world, scaling):
+    """The `config` object of a JSON line: what is measured, nothing that was measured (both arms print the same one)."""
+    w, h, nf, _ = WORKLOADS[workload]
+    cfg = {"workload": workload, "w": w, "h": h, "nfeatures": nf, "levels": LEVELS, "scale_factor": SCALE, "ini_th": INI_TH, "min_th": MIN_TH,
+           "frames_per_step_per_gpu": batch if scaling == "weak" else batch // max(world, 1), "frames_per_step": batch * world if scaling == "weak" else batch,
+           "l2": "inputs larger than L2 (%.0f MB per step and GPU)" % ((batch if scaling == "weak" else batch // max(world, 1)) * w * h / 1e6)}
+    if workload in STEREO:
+        cfg["stereo"] = "frames are rectified pairs L0,R0,L1,R1,...: left/right extraction + Frame::ComputeStereoMatches per pair"
+    return cfg
 
 
 def run_reference(args, rank, world):
+    """The reference's own CPU code (oracle/_ref: the unmodified sources) on a bounded sample of the workload: the FIRST
+    frames of the very sequence the CUDA arm extracts (same generator, same seeds), all host cores."""
     if rank != 0:
         return
-    from synth import stereo_pair, synth_frame  # numpy generators of the parity tests (no torch / CUDA needed)
-    w, h, nf, _ = WORKLOADS[args.workload]
+    import torch
+    w, h, nf, batch = WORKLOADS[args.workload]
+    if args.batch:
+        batch = args.batch
     cores = os.cpu_count() or 1
-    nsample = int(min(256, max(16, 4 * cores)))
-    if args.workload in STEREO:
-        frames = np.stack([im for i in range(min(nsample, 16) // 2) for im in stereo_pair(w, h, 2000 + i)])
-    else:
-        frames = np.stack([synth_frame(w, h, 2000 + i) for i in range(min(nsample, 16))])
-    frames = np.concatenate([frames] * ((nsample + len(frames) - 1) // len(frames)))[:nsample]
+    nsample = 64 if args.workload in STEREO else int(min(256, max(16, 4 * cores))) // GEN_BLOCK * GEN_BLOCK or GEN_BLOCK
+    nsample = min(nsample, batch)
+    dev = torch.device("cuda", 0) if torch.cuda.is_available() else torch.device("cpu")   # the generator's random streams are per device type
+    frames = np.ascontiguousarray(workload_frames(args.workload, 0, nsample, dev).cpu().numpy())
     for _ in range(args.warmup):
         cpu_workload_frames_per_s(args.workload, frames[:max(2, cores & ~1)], nf, cores)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        v, kind, what = cpu_workload_frames_per_s(args.workload, frames, nf, cores)
+        v, kind, what, total_kp = cpu_workload_frames_per_s(args.workload, frames, nf, cores)
     dt = time.perf_counter() - t0
     value = nsample * args.steps / dt
-    sample = f"{nsample} frames per step ({min(nsample, 16)} distinct), {what}"
+    sample = f"first {nsample} frames of the workload's sequence per step (generated on {dev.type}), {what}"
     emit(({
         "impl": "reference", "metric": "orb_extract_frames_per_s", "value": value, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": args.workload, "w": w, "h": h, "nfeatures": nf, "levels": LEVELS},
+        "config": workload_config(args.workload, batch, max(args.gpus, 1), "weak"),
+        "stats": ({"depth_points_per_pair": total_kp / (nsample // 2)} if args.workload in STEREO and kind == "reference"
+                  else {"keypoints_per_frame": total_kp / nsample}),
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -539,37 +573,98 @@ def bench_mappoint_side(dev, d_kps, d_desc, d_n, cap, w, h, scale_factor, reps=4
 
 
 # ------------------------------------------------------------------------------------------ our arm
-def run_ours(args, rank, world, local_rank):
+def kernel_limits():
+    """What bounds each kernel according to the committed ncu capture of this round (profiles/r02_kernel_limits.json,
+    written by tools/ncu_limits.py from an `ncu --set full` report): issue rate, pipe utilisation, instructions per unit."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_kernel_limits.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
+def oracle_parity(workload, frames_np, first, got, stereo_got=None):
+    """Compare extraction results of frames `frames_np` with the CPU checker (oracle/, the C restatement pinned to the
+    reference): every keypoint field, every descriptor byte, and for stereo pairs uRight / depth bit patterns.
+    `got` = (kps [f,cap] structured, desc [f,cap,32], n [f]); stereo_got = (ur [p,cap], depth [p,cap], ns [p]).
+    Raises SystemExit on the first difference: a number from a wrong result is not a number."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    _, _, nf, _ = WORKLOADS[workload]
+    kps, desc, n = got
+    O = [oracle_lib.OracleExtractor(nf, SCALE, LEVELS, INI_TH, MIN_TH) for _ in range(2)]
+    L = oracle_lib.oracle()
+    checked = 0
+    for i in range(len(frames_np)):
+        m, k_o, d_o = O[i & 1].extract(frames_np[i])
+        if m != int(n[i]):
+            raise SystemExit(f"bench.py: PARITY FAILURE frame {first + i}: {int(n[i])} keypoints, the checker has {m}")
+        k_g = kps[i, :m]
+        for f in k_o.dtype.names:
+            if not (k_o[f].view(np.uint32) == k_g[f].view(np.uint32)).all():
+                raise SystemExit(f"bench.py: PARITY FAILURE frame {first + i}: keypoint field {f}")
+        if not (d_o == desc[i, :m]).all():
+            raise SystemExit(f"bench.py: PARITY FAILURE frame {first + i}: descriptors")
+        if stereo_got is not None and (i & 1):
+            ur, dep, ns = stereo_got
+            pl = i // 2
+            nl = int(n[i - 1])
+            kl, dl = np.ascontiguousarray(kps[i - 1, :nl]), np.ascontiguousarray(desc[i - 1, :nl])
+            our, odep = np.zeros(nl, np.float32), np.zeros(nl, np.float32)
+            L.orbo_stereo_matches.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                              C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+            kr, dr = np.ascontiguousarray(k_o), np.ascontiguousarray(d_o)
+            nd = L.orbo_stereo_matches(O[0].h, O[1].h, nl, kl.ctypes.data, dl.ctypes.data, m, kr.ctypes.data, dr.ctypes.data,
+                                       CAM["bf"], CAM["fx"], our.ctypes.data, odep.ctypes.data)
+            if nd != int(ns[pl]) or not (ur[pl, :nl].view(np.uint32) == our.view(np.uint32)).all() or \
+               not (dep[pl, :nl].view(np.uint32) == odep.view(np.uint32)).all():
+                raise SystemExit(f"bench.py: PARITY FAILURE pair {(first + i) // 2}: mvuRight / mvDepth")
+        checked += 1
+    for o in O:
+        o.close()
+    return checked
+
+
+def frame_crcs(kps, desc, n):
+    """CRC32 of every frame's result (the valid keypoint records followed by their descriptors)."""
+    import zlib
+    out = np.zeros(len(n), np.int64)
+    for i in range(len(n)):
+        m = int(n[i])
+        out[i] = zlib.crc32(desc[i, :m].tobytes(), zlib.crc32(kps[i, :m].tobytes()))
+    return out
+
+
+def measure_workload(workload, batch_total, scaling, rank, world, local_rank, dist, args, cpu, chunk=0):
+    """One workload on this rank's GPU: device-resident throughput, per-stage times, end to end with pinned host
+    buffers, parity against the CPU checker, roofline of the dominant stage.  scaling "weak": every rank extracts
+    `batch_total` frames of its own; "strong": ONE batch of `batch_total` frames is split over the ranks
+    (shard.frame_block) and the per-frame CRCs of all ranks are checked against rank 0's single-GPU result;
+    "single": rank 0 alone.  Returns the result dict on rank 0, None elsewhere."""
     import torch
     import orb_slam2_chinesenotes_b200 as ob
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback for the product path)")
-    torch.cuda.set_device(local_rank)
+    from orb_slam2_chinesenotes_b200.shard import frame_block
     dev = torch.device("cuda", local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # NCCL's banner must not share stdout with the JSON line
-        dist.init_process_group("nccl", device_id=dev)
-    w, h, nf, batch = WORKLOADS[args.workload]
-    if args.batch:
-        batch = args.batch
-    ex = ob.ORBextractor(nf, SCALE, LEVELS, INI_TH, MIN_TH, device=local_rank)
-    if args.chunk:
-        ex.set_chunk(args.chunk)
-    cap = ex.default_capacity()
-    stereo = args.workload in STEREO
-    if stereo:
-        batch += batch % 2
-        left = synth_batch_torch(batch // 2, w, h, 1000 * 2 + rank * 100003, dev)
-        frames = torch.stack([left, stereo_right_torch(left, 1000 * 2 + rank * 100003)], dim=1).reshape(batch, h, w).contiguous()
-        del left
+    w, h, nf, _ = WORKLOADS[workload]
+    stereo = workload in STEREO
+    if scaling == "single" and rank != 0:
+        return None
+    nranks = 1 if scaling == "single" else world
+    if scaling == "strong":
+        first, stop = frame_block(batch_total, rank, nranks)
+        batch = stop - first
     else:
-        frames = synth_batch_torch(batch, w, h, 1000 * 2 + rank * 100003, dev)
+        first, batch = rank * batch_total, batch_total
+    sync_ranks = dist is not None and nranks > 1
+    ex = ob.ORBextractor(nf, SCALE, LEVELS, INI_TH, MIN_TH, device=local_rank)
+    if chunk:
+        ex.set_chunk(chunk)
+    cap = ex.default_capacity()
+    frames = workload_frames(workload, first, batch, dev)
     pairs = batch // 2
-    d_ur = torch.full((pairs, cap), -1.0, dtype=torch.float32, device=dev)
-    d_dep = torch.full((pairs, cap), -1.0, dtype=torch.float32, device=dev)
-    d_ns = torch.zeros(pairs, dtype=torch.int32, device=dev)
+    d_ur = torch.full((max(pairs, 1), cap), -1.0, dtype=torch.float32, device=dev)
+    d_dep = torch.full((max(pairs, 1), cap), -1.0, dtype=torch.float32, device=dev)
+    d_ns = torch.zeros(max(pairs, 1), dtype=torch.int32, device=dev)
     d_kps = torch.zeros((batch, cap, 7), dtype=torch.float32, device=dev)
     d_desc = torch.zeros((batch, cap, 32), dtype=torch.uint8, device=dev)
     d_n = torch.zeros(batch, dtype=torch.int32, device=dev)
@@ -588,10 +683,11 @@ def run_ours(args, rank, world, local_rank):
 
     def barrier():
         torch.cuda.synchronize()
-        if dist is not None:
+        if sync_ranks:
             dist.barrier()
             torch.cuda.synchronize()
 
+    steps = args.steps
     for _ in range(max(args.warmup, 3)):
         step_device()
     barrier()
@@ -601,7 +697,7 @@ def run_ours(args, rank, world, local_rank):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(stream)
-    for _ in range(args.steps):
+    for _ in range(steps):
         step_device()
     e1.record(stream)
     barrier()
@@ -610,16 +706,19 @@ def run_ours(args, rank, world, local_rank):
     # launch; the library then keeps all kernels on the one stream, so an event pair brackets one stage
     ex.profile(True)
     ex.stage_ms(reset=True)
-    for _ in range(args.steps):
+    for _ in range(steps):
         step_device()
     barrier()
     stage_ms, stage_cnt = ex.stage_ms(reset=True)
     ex.profile(False)
     nk = d_n.cpu().numpy()
-    assert (nk > 0).all() and (nk <= cap).all(), "extraction produced no keypoints / overflowed"
+    if not ((nk > 0).all() and (nk <= cap).all()):
+        raise SystemExit("bench.py: extraction produced no keypoints / overflowed")
     ns_dev = d_ns.cpu().numpy()
+    n_depth = 0
     if stereo:
-        assert (ns_dev > 0).all(), "stereo matching found nothing"
+        if not (ns_dev > 0).all():
+            raise SystemExit("bench.py: stereo matching found nothing")
         n_depth = int((d_dep > 0).sum().item())
 
     # ---- end to end through the C ABI with HOST buffers (pinned): H2D + kernels + D2H per step
@@ -628,9 +727,35 @@ def run_ours(args, rank, world, local_rank):
     h_kps = torch.empty((batch, cap, 7), dtype=torch.float32).pin_memory()
     h_desc = torch.empty((batch, cap, 32), dtype=torch.uint8).pin_memory()
     h_n = torch.empty(batch, dtype=torch.int32).pin_memory()
-    h_ur = torch.empty((pairs, cap), dtype=torch.float32).pin_memory()
-    h_dep = torch.empty((pairs, cap), dtype=torch.float32).pin_memory()
-    h_ns = torch.empty(pairs, dtype=torch.int32).pin_memory()
+    h_ur = torch.empty((max(pairs, 1), cap), dtype=torch.float32).pin_memory()
+    h_dep = torch.empty((max(pairs, 1), cap), dtype=torch.float32).pin_memory()
+    h_ns = torch.empty(max(pairs, 1), dtype=torch.int32).pin_memory()
+    h2d_bytes = batch * w * h
+    d2h_bytes = batch * (cap * 60 + 4) + (pairs * (cap * 8 + 4) if stereo else 0)
+
+    # what the copies alone cost on this box: the step's host->device and device->host bytes on two streams, all ranks
+    # at once, nothing else running (the ceiling of any end-to-end number)
+    s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    stage_in = torch.empty_like(frames)
+
+    def copies():
+        with torch.cuda.stream(s_in):
+            stage_in.copy_(h_frames, non_blocking=True)
+        with torch.cuda.stream(s_out):
+            h_kps.copy_(d_kps, non_blocking=True)
+            h_desc.copy_(d_desc, non_blocking=True)
+            if stereo:
+                h_ur.copy_(d_ur, non_blocking=True)
+                h_dep.copy_(d_dep, non_blocking=True)
+
+    copies()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        copies()
+    barrier()
+    ms_copy = 1e3 * (time.perf_counter() - t0)
+    del stage_in
 
     def step_host():
         if stereo:
@@ -642,66 +767,204 @@ def run_ours(args, rank, world, local_rank):
     step_host()
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         step_host()
     barrier()
     ms_e2e = 1e3 * (time.perf_counter() - t0)
     clocks = sampler.stop()
-    assert (h_n.numpy() == nk).all(), "host-buffer path and device-resident path disagree"
-    if stereo:
-        assert (h_ns.numpy() == ns_dev).all(), "stereo: host-buffer path and device-resident path disagree"
+
+    # ---- the results that were timed are the reference's results: first and last frames of the batch, both paths
+    kp_dt = ob.KP_DTYPE
+    hk = h_kps.numpy().view(np.uint8).reshape(batch, cap, 28).view(kp_dt).reshape(batch, cap)
+    hd, hn = h_desc.numpy(), h_n.numpy()
+    if not (hn == nk).all() or (stereo and not (h_ns.numpy()[:pairs] == ns_dev[:pairs]).all()):
+        raise SystemExit("bench.py: host-buffer path and device-resident path disagree")
+    ncheck = min(batch, 4 if not stereo else 4)
+    idx = list(range(ncheck)) + [i for i in range(batch - ncheck, batch) if i >= ncheck]
+    blocks = [(0, ncheck)] + ([(batch - ncheck, batch)] if batch - ncheck >= ncheck else [])
+    checked = 0
+    for lo, hi in blocks:
+        fr = np.ascontiguousarray(frames[lo:hi].cpu().numpy())
+        dk = d_kps[lo:hi].cpu().numpy().view(np.uint8).reshape(hi - lo, cap, 28).view(kp_dt).reshape(hi - lo, cap)
+        sg_d = sg_h = None
+        if stereo:
+            sg_d = (d_ur[lo // 2:hi // 2].cpu().numpy(), d_dep[lo // 2:hi // 2].cpu().numpy(), ns_dev[lo // 2:hi // 2])
+            sg_h = (h_ur.numpy()[lo // 2:hi // 2], h_dep.numpy()[lo // 2:hi // 2], h_ns.numpy()[lo // 2:hi // 2])
+        checked += oracle_parity(workload, fr, first + lo, (dk, d_desc[lo:hi].cpu().numpy(), nk[lo:hi]), sg_d)
+        oracle_parity(workload, fr, first + lo, (hk[lo:hi], hd[lo:hi], hn[lo:hi]), sg_h)
+    parity = {"frames_checked_against_cpu_checker": checked, "paths": ["device resident", "host buffers"],
+              "fields": "all keypoint fields (bit patterns), descriptors" + (", mvuRight / mvDepth bits, match counts" if stereo else ""),
+              "which": f"first and last {ncheck} frames of each rank's batch", "result": "identical"}
+
+    # ---- strong scaling: the sharded batch equals the single-GPU batch (CRC32 per frame, gathered over NCCL)
+    crc_check = None
+    if scaling == "strong":
+        mine = torch.from_numpy(frame_crcs(hk, hd, hn)).to(dev)
+        if sync_ranks:
+            sizes = [frame_block(batch_total, r, nranks) for r in range(nranks)]
+            maxb = max(b - a for a, b in sizes)
+            pad = torch.zeros(maxb, dtype=torch.int64, device=dev)
+            pad[:batch] = mine
+            gathered = [torch.zeros(maxb, dtype=torch.int64, device=dev) for _ in range(nranks)]
+            dist.all_gather(gathered, pad)
+            allcrc = torch.cat([g[:b - a] for g, (a, b) in zip(gathered, sizes)]).cpu().numpy()
+        else:
+            allcrc = mine.cpu().numpy()
+        if rank == 0:
+            # rank 0 extracts the WHOLE batch on its own GPU (device resident, in pieces) and compares
+            want = np.zeros(batch_total, np.int64)
+            piece = max(batch, 1)
+            for p0 in range(0, batch_total, piece):
+                pn = min(piece, batch_total - p0)
+                if p0 == first and pn == batch:
+                    fr = frames
+                else:
+                    fr = workload_frames(workload, p0, pn, dev)
+                ex.extract_batch_raw(fr, h * w, pn, w, h, w, d_kps, d_desc, cap, d_n, asynchronous=True)
+                torch.cuda.synchronize()
+                pk = d_kps[:pn].cpu().numpy().view(np.uint8).reshape(pn, cap, 28).view(kp_dt).reshape(pn, cap)
+                want[p0:p0 + pn] = frame_crcs(pk, d_desc[:pn].cpu().numpy(), d_n[:pn].cpu().numpy())
+                del fr
+            if not (want == allcrc).all():
+                raise SystemExit(f"bench.py: SHARDING FAILURE: {int((want != allcrc).sum())} of {batch_total} frames differ from the single-GPU result")
+            crc_check = {"frames": batch_total, "ranks": nranks, "result": "per-frame CRC32 (keypoints + descriptors) of the sharded batch = single-GPU batch"}
 
     # ---- max over ranks
-    if dist is not None:
-        t = torch.tensor([ms_dev, ms_e2e], device=dev, dtype=torch.float64)
+    total_kp = float(nk.sum())
+    if sync_ranks:
+        t = torch.tensor([ms_dev, ms_e2e, ms_copy], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_dev, ms_e2e = float(t[0]), float(t[1])
-        kp = torch.tensor([float(nk.sum())], device=dev, dtype=torch.float64)
+        ms_dev, ms_e2e, ms_copy = float(t[0]), float(t[1]), float(t[2])
+        kp = torch.tensor([total_kp, float(n_depth)], device=dev, dtype=torch.float64)
         dist.all_reduce(kp)
-        total_kp = float(kp[0])
-    else:
-        total_kp = float(nk.sum())
+        total_kp, n_depth = float(kp[0]), float(kp[1])
+    torch.cuda.set_stream(torch.cuda.default_stream(dev))
     if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
-        return
-    total_frames = batch * world * args.steps
-    value = total_frames / (ms_dev * 1e-3)
-    e2e_value = total_frames / (ms_e2e * 1e-3)
+        ex.close()
+        return None
+    frames_all = batch_total * nranks if scaling == "weak" else batch_total
+    value = frames_all * steps / (ms_dev * 1e-3)
+    e2e_value = frames_all * steps / (ms_e2e * 1e-3)
     # ---- roofline of the dominant kernel (stage times measured above with CUDA events on the stream)
     bytes_per_frame = algorithmic_bytes(w, h)
-    dom = max(("pyramid", "fast", "blur", "octree", "describe", "stereo"), key=lambda s: stage_ms[s])
+    dom = max(("pyramid", "fast", "blur", "octree", "describe", "stereo"), key=lambda s_: stage_ms[s_])
     peak, peak_src = measured_peak()
     roof = {"bound": "hbm", "kernel": dom, "peak": peak, "unit": "GB/s", "peak_source": peak_src, "traffic": None,
             "stage_timing": "second pass of the same steps, kernels serialised on one stream, CUDA events around each launch",
-            "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()}}
+            "stage_ms_per_step": {k: v / steps for k, v in stage_ms.items()}}
     if dom in bytes_per_frame:
         launches = max(stage_cnt[dom], 1)
-        frames_per_launch = batch * args.steps / launches
+        frames_per_launch = batch * steps / launches
         dur_s = stage_ms[dom] * 1e-3 / launches
         roof["achieved"] = bytes_per_frame[dom] * frames_per_launch / dur_s / 1e9
         roof["frac"] = roof["achieved"] / peak
         roof["algorithmic_bytes_per_frame"] = bytes_per_frame[dom]
         roof["algorithmic_bytes_per_launch"] = bytes_per_frame[dom] * frames_per_launch
-        roof["traffic"] = measured_traffic(dom, frames_per_launch)
+        roof["traffic"] = measured_traffic(dom, frames_per_launch) if workload == "kitti_1241x376_nf2000" else None
     else:
         roof["achieved"] = None
         roof["frac"] = None
-    # what actually bounds the dominant kernel, from the committed ncu capture of this same command (not measured live)
-    roof["limiter"] = {"fast": "instruction issue: 2.75 of 4 warp instructions per clock and SM, ALU pipe 62 %, 177 instructions per pixel pair; "
-                               "DRAM traffic = algorithmic bytes (profiles/r01d_ncu_full_all_kernels.txt, r01d_ncu_full_extract_stalls.txt)"}.get(dom)
-    roof["dense_stages"] = {s: {"GB/s": bytes_per_frame[s] * batch * args.steps / (stage_ms[s] * 1e-3) / 1e9,
-                                "frac": bytes_per_frame[s] * batch * args.steps / (stage_ms[s] * 1e-3) / 1e9 / peak}
-                            for s in bytes_per_frame if stage_ms[s] > 0}
+    # what actually bounds the dominant kernel: from the committed ncu capture of this round (not measured live)
+    lim = kernel_limits().get(dom)
+    if lim:
+        roof["limiter"] = lim
+        roof["issue_frac"] = lim.get("issue_frac")
+        roof["binding"] = lim.get("binding")
+    roof["dense_stages"] = {s_: {"GB/s": bytes_per_frame[s_] * batch * steps / (stage_ms[s_] * 1e-3) / 1e9,
+                                 "frac": bytes_per_frame[s_] * batch * steps / (stage_ms[s_] * 1e-3) / 1e9 / peak}
+                            for s_ in bytes_per_frame if stage_ms[s_] > 0}
     # ---- CPU baseline on a bounded sample of the same frames (rank 0, N=1 only)
-    cpu = None
-    if world == 1 and not args.no_cpu:
+    cpu_base = None
+    if cpu:
         cores = os.cpu_count() or 1
-        ns = int(min(batch, max(16, 4 * cores))) & ~1
+        ns = int(min(batch, max(16, 4 * cores))) & ~1 or batch
         sample = frames[:ns].cpu().numpy()
-        v, kind, what = cpu_workload_frames_per_s(args.workload, sample, nf, cores)
-        cpu = {"value": v, "unit": "frames/s", "cores": cores, "kind": kind,
-               "sample": f"first {ns} frames of the step's batch, {what}"}
+        v, kind, what, _ = cpu_workload_frames_per_s(workload, sample, nf, cores)
+        cpu_base = {"value": v, "unit": "frames/s", "cores": cores, "kind": kind,
+                    "sample": f"first {ns} frames of the step's batch, {what}"}
+    chunk_dev = chunk or 512                      # device-resident default of orb_capi.cu (the timed `value` path)
+    chunks = (batch + chunk_dev - 1) // chunk_dev
+    stats = {"keypoints_per_frame": total_kp / frames_all}
+    if stereo:
+        stats["depth_points_per_pair"] = n_depth / (frames_all / 2)
+    res = {
+        "value": value, "unit": "frames/s", "ms_per_step": ms_dev / steps, "scaling": "weak" if scaling == "single" else scaling,
+        "n_gpus": nranks, "config": workload_config(workload, batch_total, nranks, "weak" if scaling != "strong" else "strong"), "stats": stats,
+        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                "ms_per_step": ms_e2e / steps, "copy_ceiling_frames_per_s": frames_all * steps / (ms_copy * 1e-3),
+                "copy_ceiling_note": "the step's pinned host->device and device->host copies alone, two streams, all ranks at once (max over ranks)"},
+        "gpu_launches": ex.launches_per_chunk(stereo) * chunks * steps,
+        "roofline": roof, "cpu_baseline": cpu_base, "clocks": clocks, "parity": parity,
+    }
+    if crc_check:
+        res["sharding_check"] = crc_check
+    res["_keep"] = (ex, d_kps, d_desc, d_n, cap, h_frames, frames)
+    return res
+
+
+def pin_rank_to_cores(local_rank, world):
+    """One rank per GPU on one host: give every rank its own slice of the host cores so the staging threads of
+    eight ranks do not migrate over each other (all GPUs of these boxes hang off NUMA node 0)."""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        per = len(cores) // world
+        if world > 1 and per >= 2:
+            os.sched_setaffinity(0, set(cores[local_rank * per:(local_rank + 1) * per]))
+            return per
+    except Exception:
+        pass
+    return None
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import orb_slam2_chinesenotes_b200 as ob
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    pinned = pin_rank_to_cores(local_rank, world)
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # NCCL's banner must not share stdout with the JSON line
+        dist.init_process_group("nccl", device_id=dev)
+    w, h, nf, batch = WORKLOADS[args.workload]
+    if args.batch:
+        batch = args.batch
+    stereo = args.workload in STEREO
+    if stereo:
+        batch += batch % 2
+    cpu = world == 1 and not args.no_cpu
+    main = measure_workload(args.workload, batch, args.scaling, rank, world, local_rank, dist, args, cpu, args.chunk)
+
+    # ---- the other BASELINE.json configs in the same line (default run only): configs[0] one 640x480 frame, configs[2]
+    # EuRoC x256 on one GPU, configs[4] 4096 HD frames sharded over all ranks (strong scaling)
+    others = []
+    if not args.only_main and args.workload == "kitti_1241x376_nf2000" and args.scaling == "weak" and not args.batch:
+        for name, b, sc in (("tum_640x480_nf1000", GEN_BLOCK, "single"), ("euroc_752x480_nf1200", 256, "single"),
+                            ("hd_1920x1080_nf4000", args.hd_batch, "strong")):
+            sub = argparse.Namespace(**vars(args))
+            sub.steps, sub.warmup = min(args.steps, 3), 3
+            r = measure_workload(name, b, sc, rank, world, local_rank, dist, sub, cpu and rank == 0)
+            if r is not None:
+                ex1, _, _, _, _, h_fr, _ = r.pop("_keep")
+                if name == "tum_640x480_nf1000":      # configs[0]: ONE frame through operator(), host buffers
+                    one = h_fr[0].numpy()
+                    for _ in range(5):
+                        ex1(one)
+                    t0 = time.perf_counter()
+                    for _ in range(30):
+                        ex1(one)
+                    r["latency"] = {"extract_1_frame_ms": 1e3 * (time.perf_counter() - t0) / 30,
+                                    "note": "configs[0]: operator() on one 640x480 frame, nfeatures 1000, host buffers, ctypes overhead included"}
+                ex1.close()
+                others.append(r)
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    ex, d_kps, d_desc, d_n, cap, h_frames, frames = main.pop("_keep")
     # ---- latency of ONE call with host buffers (what a real-time tracker sees per frame), rank 0 only
     latency = None
     if world == 1:
@@ -719,31 +982,19 @@ def run_ours(args, rank, world, local_rank):
             for _ in range(30):
                 ex.extract_stereo_batch(one, CAM["bf"], CAM["fx"])
             latency["stereo_pair_ms"] = 1e3 * (time.perf_counter() - t0) / 30
-    chunk = args.chunk or 512                      # device-resident default of orb_capi.cu (the timed `value` path)
-    chunks = (batch + chunk - 1) // chunk
-    cfg_stereo = {}
-    if stereo:
-        cfg_stereo = {"stereo": "frames are rectified pairs L0,R0,L1,R1,...: left/right extraction + Frame::ComputeStereoMatches per pair",
-                      "pairs_per_step_per_gpu": pairs, "depth_points_per_pair": n_depth / pairs}
     hamming = bench_hamming(dev, local_rank) if world == 1 else None
     window = mappoint = None
     if world == 1 and stereo:
         window = bench_window_match(dev, d_kps, d_desc, d_n, cap, w, h, ex.GetScaleFactors(), cpu=not args.no_cpu)
         mappoint = bench_mappoint_side(dev, d_kps, d_desc, d_n, cap, w, h, SCALE, cpu=not args.no_cpu)
-    emit(({
-        "metric": "orb_extract_frames_per_s", "value": value, "unit": "frames/s", "n_gpus": world,
-        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": args.workload, "w": w, "h": h, "nfeatures": nf, "levels": LEVELS,
-                   "frames_per_step_per_gpu": batch, "l2": "inputs larger than L2 (%.0f MB per step)" % (batch * w * h / 1e6),
-                   "keypoints_per_frame": total_kp / (batch * world), **cfg_stereo},
-        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": batch * w * h,
-                "d2h_bytes_per_step": batch * (cap * 60 + 4) + (pairs * (cap * 8 + 4) if stereo else 0),
-                "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": (LEVELS - 1 + 4 + (3 if stereo else 0)) * chunks * args.steps,
-        "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "hamming_bf": hamming,
-        "window_match": window, "mappoint_side": mappoint, "latency": latency,
-    }))
+    line = {"metric": "orb_extract_frames_per_s", "value": main.pop("value"), "unit": main.pop("unit"), "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": main.pop("ms_per_step"),
+            "higher_is_better": True, "scaling": main.pop("scaling"), "vs_baseline": None, "dtype": "u8", "data": "synthetic"}
+    main.pop("n_gpus")
+    line.update(main)
+    line.update({"hamming_bf": hamming, "window_match": window, "mappoint_side": mappoint, "latency": latency,
+                 "other_workloads": others, "host_cores_per_rank": pinned})
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
@@ -758,6 +1009,10 @@ def main():
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--chunk", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: every rank extracts --batch frames; strong: ONE batch of --batch frames is sharded over the ranks")
+    ap.add_argument("--only-main", action="store_true", help="skip the other BASELINE configs (other_workloads)")
+    ap.add_argument("--hd-batch", type=int, default=4096, help="frames of the configs[4] strong-scaling workload")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -141,6 +141,11 @@ int orbx_plan_describe(int nfeatures, float scaleFactor, int nlevels, int iniThF
  * matchers a tight bound (orbm_frames.max_n) -- without reading n_out back. */
 int orbx_max_keypoints(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST, int w, int h);
 
+/* Kernels of this library one chunk of frames launches for the context's current shape (pyramid levels, FAST, blur,
+ * quadtree, describe, plus the three stereo kernels when `stereo`): what bench.py reports as gpu_launches.  Negative
+ * ORBX_E_EMPTY when no shape has been seen yet. */
+int orbx_launches_per_chunk(orbx_ctx* ctx, int stereo);
+
 /* ---- matcher -------------------------------------------------------------------- */
 
 /* ORBmatcher::DescriptorDistance (src/ORBmatcher.cc:46-63) over all pairs: for each of the nq
@@ -169,7 +174,8 @@ typedef struct {
 /* ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th), src/ORBmatcher.cc:73-157.
  * Map points as arrays [nq]: mTrackProjX/Y/XR (3 floats each), mnTrackScaleLevel, mTrackViewCos,
  * mbTrackInView, isBad(), Observations(), GetDescriptor().  init_assign [n] (or NULL): index of the map
- * point already attached to a keypoint, -1 if none.  assign_out [n]: F.mvpMapPoints afterwards.
+ * point already attached to a keypoint, -1 if none.  assign_out [n]: F.mvpMapPoints afterwards (may be NULL when the
+ * frame has no keypoints, as may init_assign: the call then returns 0 matches like the reference on a black image).
  * scale = F.mvScaleFactors.  All pointers are HOST memory.  *nmatches = the function's return value. */
 int orbm_search_by_projection_points(const orbm_frame* F, const float* scale, int nlevels,
                                      int nq, const float* proj_xyxr, const int* level, const float* view_cos,

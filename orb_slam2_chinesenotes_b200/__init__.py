@@ -110,6 +110,7 @@ def lib():
         L.orbx_stage_ms.argtypes = [vp, vp, vp, i32]
         L.orbx_plan_describe.argtypes = [i32, f32, i32, i32, i32, i32, i32] + [vp] * 6
         L.orbx_max_keypoints.argtypes = [i32, f32, i32, i32, i32, i32, i32]
+        L.orbx_launches_per_chunk.argtypes = [vp, i32]
         L.orbm_hamming_bf.argtypes = [vp, i32, vp, i32, i32, vp, vp, vp, i32]
         L.orbm_hamming_bf_async.argtypes = [vp, i32, vp, i32, i32, vp, vp, vp, vp]
         fp = C.POINTER(OrbmFrame)
@@ -224,7 +225,7 @@ class ORBextractor:
         if image.size == 0:
             return None, None
         assert image.dtype == np.uint8 and image.ndim == 2, "CV_8UC1 expected (src/ORBextractor.cc:1091)"
-        if not image.flags.c_contiguous and image.strides[1] != 1:
+        if image.strides[1] != 1 or image.strides[0] < image.shape[1]:   # also views with a negative / overlapping row stride
             image = np.ascontiguousarray(image)
         cap = capacity or self.default_capacity()
         kps = np.zeros(cap, KP_DTYPE)
@@ -316,6 +317,13 @@ class ORBextractor:
 
     def level_keypoints(self, level, frame=0):
         return self._packed(self._L.orbx_debug_level_keypoints, level, frame)
+
+    def launches_per_chunk(self, stereo=False):
+        """Kernels one chunk of frames launches for the shape last seen (orbx_launches_per_chunk)."""
+        r = self._L.orbx_launches_per_chunk(self._h, int(stereo))
+        if r < 0:
+            raise OrbError(-r, "orbx_launches_per_chunk")
+        return r
 
     def profile(self, enable=True):
         self._check(self._L.orbx_profile(self._h, int(enable)))

@@ -687,6 +687,13 @@ int orbx_plan_describe(int nfeatures, float scaleFactor, int nlevels, int iniThF
 
 // Upper bound on the keypoints operator() can return for one image of this shape: a level's DistributeOctTree list
 // never exceeds max(N + 2, 4 * nIni) nodes (src/ORBextractor.cc:617-766) and every node yields one keypoint.
+int orbx_launches_per_chunk(orbx_ctx* c, int stereo)
+{
+    if (!c) return -ORBX_E_ARG;
+    if (c->plan.nlevels <= 0 || c->plan.w <= 0) return -ORBX_E_EMPTY;
+    return orb_pyramid_launch_count(c->plan) + 4 + (stereo ? 3 : 0);
+}
+
 int orbx_max_keypoints(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST, int w, int h)
 {
     OrbParams p;

@@ -291,6 +291,8 @@ cudaError_t orb_launch_pyramid(const OrbPlan& plan, const OrbBatch& io, int batc
     return cudaGetLastError();
 }
 
+int orb_pyramid_launch_count(const OrbPlan& plan) { return plan.nlevels - 1; }   // one launch per level: a level is resized from the ROUNDED level above
+
 cudaError_t orb_launch_blur(const OrbPlan& plan, const OrbBatch& io, int batch, cudaStream_t st)
 {
     k_blur7<<<dim3((plan.total_blur_tiles + BLUR_NT / 32 - 1) / (BLUR_NT / 32), batch), BLUR_NT, 0, st>>>(plan, io);

@@ -8,6 +8,7 @@ struct OrbBatch;
 size_t orb_fast_smem_bytes(const OrbPlan& plan);
 size_t orb_octree_smem_bytes(const OrbPlan& plan);
 cudaError_t orb_launch_pyramid(const OrbPlan& plan, const OrbBatch& io, int batch, cudaStream_t st);
+int orb_pyramid_launch_count(const OrbPlan& plan);   // kernels orb_launch_pyramid launches
 cudaError_t orb_launch_blur(const OrbPlan& plan, const OrbBatch& io, int batch, cudaStream_t st);
 // FAST fetches its tiles with one tensor-map TMA copy per chunk wherever the level's base address, row pitch and
 // frame stride are multiples of 16 bytes (all pyramid levels; level 0 when the caller's layout allows).  The

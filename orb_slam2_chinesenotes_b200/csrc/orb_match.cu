@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(32) k_resolve_points(const DevFrame F, const i
         if (n == 0) continue;
         const uint32_t* lst = list + (size_t)q * cap;
         uint32_t k1, k2;
-        warp_top2(lst, n, lane, [&](int idx, int) { const int a = assign[idx]; return !(a >= 0 && observations[a] > 0); }, k1, k2);   // :115-117
+        warp_top2(lst, n, lane, [&](int idx, int) { const int a = assign[idx]; return !(a >= 0 && a < nq && observations[a] > 0); }, k1, k2);   // :115-117
         if (k1 == 0xffffffffu) continue;
         const int bestDist = (int)(k1 >> 20), bestIdx = (int)(lst[k1 & 0xfffffu] & 0xffffu);
         if (bestDist <= TH_HIGH) {
@@ -400,6 +400,7 @@ static void report_cuda(cudaError_t e, const char* what, int line)
 struct ArenaBlock { char* dev = nullptr; char* pin = nullptr; size_t cap = 0, used = 0, flushed = 0; };
 struct ThreadArena {
     int device = -1;
+    bool inflight = false;              // flush() queued host-to-device copies that no synchronisation has covered yet
     std::vector<ArenaBlock> up, scratch;
     void release()
     {
@@ -419,6 +420,9 @@ struct Scratch {
         int dev = -1;
         if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); ok = false; return; }
         if (dev != t_arena.device) { t_arena.release(); t_arena.device = dev; }
+        // an entry point that failed after flush() may have left copies from the pinned twins in flight: they must land
+        // before the bytes are reused (every successful call ends synchronised, the wait is then free)
+        if (t_arena.inflight) { if (cudaStreamSynchronize(0) != cudaSuccess) cudaGetLastError(); t_arena.inflight = false; }
         for (ArenaBlock& b : t_arena.up) b.used = b.flushed = 0;
         for (ArenaBlock& b : t_arena.scratch) b.used = 0;
     }
@@ -462,6 +466,7 @@ struct Scratch {
             if (b.used > b.flushed) {
                 { const cudaError_t e_ = cudaMemcpyAsync(b.dev + b.flushed, b.pin + b.flushed, b.used - b.flushed, cudaMemcpyHostToDevice, 0); if (e_ != cudaSuccess) { report_cuda(e_, "flush", __LINE__); cudaGetLastError(); ok = false; return false; } }
                 b.flushed = b.used;
+                t_arena.inflight = true;
             }
         return ok;
     }
@@ -643,7 +648,7 @@ int orbm_search_by_projection_points(const orbm_frame* F, const float* scale, in
                                      const uint8_t* qdesc, const int* init_assign, int* assign_out,
                                      float th, float nnratio, int* nmatches, int device)
 {
-    if (!F || !scale || nq < 0 || !assign_out || !nmatches || (nq > 0 && (!proj_xyxr || !level || !view_cos || !in_view || !bad || !observations || !qdesc)))
+    if (!F || !scale || nq < 0 || (F->n > 0 && !assign_out) || !nmatches || (nq > 0 && (!proj_xyxr || !level || !view_cos || !in_view || !bad || !observations || !qdesc)))
         return ORBX_E_ARG;
     if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return ORBX_E_CUDA; }
     *nmatches = 0;
@@ -709,7 +714,7 @@ int orbm_search_by_projection_frame(const orbm_frame* cur, int n_last, const orb
                                     const float* scale, int nlevels, const int* cur_init_obs, int* assign_out,
                                     float th, int bMono, int checkOri, int* nmatches, int device)
 {
-    if (!cur || n_last < 0 || !assign_out || !nmatches || !Tcw_cur || !Tcw_last || !K || !scale ||
+    if (!cur || n_last < 0 || (cur->n > 0 && !assign_out) || !nmatches || !Tcw_cur || !Tcw_last || !K || !scale ||
         (n_last > 0 && (!kps_last || !last_mp || !last_xyz || !last_mp_desc))) return ORBX_E_ARG;
     if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return ORBX_E_CUDA; }
     *nmatches = 0;
@@ -783,7 +788,7 @@ int orbm_window_search_best(const orbm_frame* F, int nq, const float* uvr, const
                             const float* q_angle, const int* q_obs, const int* init_obs, int* assign_out,
                             int th_accept, int check_ori, int* nmatches, int device)
 {
-    if (!F || nq < 0 || !assign_out || !nmatches || (nq > 0 && (!uvr || !min_level || !max_level || !qdesc))) return ORBX_E_ARG;
+    if (!F || nq < 0 || (F->n > 0 && !assign_out) || !nmatches || (nq > 0 && (!uvr || !min_level || !max_level || !qdesc))) return ORBX_E_ARG;
     if (check_ori && nq > 0 && !q_angle) return ORBX_E_ARG;
     if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return ORBX_E_CUDA; }
     *nmatches = 0;
@@ -855,9 +860,11 @@ int orbm_stereo_matches(orbx_ctx* ex_left, int frame_l, orbx_ctx* ex_right, int 
     OrbStereoView V;
     memset(&V, 0, sizeof(V));
     int dev_l = 0, dev_r = 0;
+    int wr[ORB_MAX_LEVELS], hr[ORB_MAX_LEVELS], nlr = 0;
     if (orb_ctx_levels(ex_left, frame_l, V.l, V.lpitch, V.w, V.h, V.scale, V.inv_scale, &V.nlevels, &dev_l) ||
-        orb_ctx_levels(ex_right, frame_r, V.r, V.rpitch, nullptr, nullptr, nullptr, nullptr, nullptr, &dev_r) || dev_l != dev_r)
+        orb_ctx_levels(ex_right, frame_r, V.r, V.rpitch, wr, hr, nullptr, nullptr, &nlr, &dev_r) || dev_l != dev_r || nlr != V.nlevels)
         return ORBX_E_ARG;
+    for (int l = 0; l < V.nlevels; ++l) if (wr[l] != V.w[l] || hr[l] != V.h[l]) return ORBX_E_ARG;   // both extractors must have seen the same shape
     if (cudaSetDevice(dev_l) != cudaSuccess) { cudaGetLastError(); return ORBX_E_CUDA; }
     if (nmatched) *nmatched = 0;
     for (int i = 0; i < nl; ++i) { u_right[i] = -1.0f; depth[i] = -1.0f; }

@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(MB_NT) k_match_fixpoint(const __grid_constant_
         uint32_t taken = 0;
         if (init) {
             const int a = init[idx];
-            if (MODE == MODE_POINTS) taken = (a >= 0 && qobs[a] > 0) ? 1u : 0u;   // attached point with Observations() > 0
+            if (MODE == MODE_POINTS) taken = (a >= 0 && a < nq && qobs[a] > 0) ? 1u : 0u;   // attached point with Observations() > 0 (an index outside the query set counts as free)
             else taken = a > 0 ? 1u : 0u;
         }
         rec[j] = make_uint4(__float_as_uint(kp.x), __float_as_uint(kp.y), (uint32_t)(kp.octave & 0xff) | ((uint32_t)idx << 8) | (taken << 31),

@@ -47,6 +47,10 @@ namespace ORB_SLAM2 { namespace b200 {
 
 inline int& Device() { static int d = 0; return d; }
 
+// &v[0] of an empty vector is undefined: a frame without keypoints (a black image) must reach the C ABI as n = 0, null
+template <class T> inline T* Ptr(std::vector<T>& v) { return v.empty() ? (T*)0 : &v[0]; }
+template <class T> inline const T* Ptr(const std::vector<T>& v) { return v.empty() ? (const T*)0 : &v[0]; }
+
 template <class KeyPointT>
 inline void FlattenKeys(const std::vector<KeyPointT>& keys, std::vector<orbx_kp>& out)
 {
@@ -120,8 +124,8 @@ int SearchByProjection(FrameT& F, const std::vector<MapPointT*>& vpMapPoints, co
     }
     std::vector<int> assign(kps.size(), -1);
     int nmatches = 0;
-    Check(orbm_search_by_projection_points(&view, &F.mvScaleFactors[0], (int)F.mvScaleFactors.size(), (int)n, &proj[0], &level[0], &viewCos[0],
-                                           &inView[0], &bad[0], &obs[0], &qdesc[0], &init[0], kps.empty() ? 0 : &assign[0], th, nnratio,
+    Check(orbm_search_by_projection_points(&view, &F.mvScaleFactors[0], (int)F.mvScaleFactors.size(), (int)n, Ptr(proj), Ptr(level), Ptr(viewCos),
+                                           Ptr(inView), Ptr(bad), Ptr(obs), &qdesc[0], Ptr(init), Ptr(assign), th, nnratio,
                                            &nmatches, Device()), "orbm_search_by_projection_points");
     for (size_t k = 0; k < kps.size(); ++k) if (assign[k] >= 0) F.mvpMapPoints[k] = pts[(size_t)assign[k]];
     return nmatches;
@@ -157,8 +161,8 @@ int SearchByProjection(FrameT& Cur, const FrameT& Last, const float th, const bo
     for (size_t k = 0; k < kps.size(); ++k) if (Cur.mvpMapPoints[k]) initObs[k] = Cur.mvpMapPoints[k]->Observations();
     int nmatches = 0;
     Check(orbm_search_by_projection_frame(&view, nl, lk.empty() ? 0 : &lk[0], &hasMp[0], &outlier[0], &xyz[0], &mdesc[0], &mobs[0], Tc, Tl, K, Cur.mbf,
-                                          &Cur.mvScaleFactors[0], (int)Cur.mvScaleFactors.size(), kps.empty() ? 0 : &initObs[0],
-                                          kps.empty() ? 0 : &assign[0], th, bMono ? 1 : 0, checkOri ? 1 : 0, &nmatches, Device()),
+                                          &Cur.mvScaleFactors[0], (int)Cur.mvScaleFactors.size(), Ptr(initObs),
+                                          Ptr(assign), th, bMono ? 1 : 0, checkOri ? 1 : 0, &nmatches, Device()),
           "orbm_search_by_projection_frame");
     for (size_t k = 0; k < kps.size(); ++k) {
         if (assign[k] >= 0) Cur.mvpMapPoints[k] = Last.mvpMapPoints[(size_t)assign[k]];
@@ -222,7 +226,7 @@ int SearchByProjection(FrameT& Cur, KeyFrameT* pKF, const std::set<MapPointT*>& 
     for (size_t k = 0; k < kps.size(); ++k) if (Cur.mvpMapPoints[k]) initObs[k] = 1;   // any attached point blocks (:373-374)
     int nmatches = 0;
     Check(orbm_window_search_best(&view, (int)nq, &uvr[0], &minl[0], &maxl[0], 0, 0, &valid[0], &qdesc[0], &qangle[0], 0,
-                                  kps.empty() ? 0 : &initObs[0], kps.empty() ? 0 : &assign[0], ORBdist, checkOri ? 1 : 0, &nmatches, Device()),
+                                  Ptr(initObs), Ptr(assign), ORBdist, checkOri ? 1 : 0, &nmatches, Device()),
           "orbm_window_search_best");
     for (size_t k = 0; k < kps.size(); ++k) {
         if (assign[k] >= 0) Cur.mvpMapPoints[k] = vpMPs[(size_t)assign[k]];
@@ -306,7 +310,7 @@ int SearchByProjection(KeyFrameT* pKF, const MatT& Scw, const std::vector<MapPoi
     for (size_t k = 0; k < kps.size(); ++k) if (vpMatched[k]) initObs[k] = 1;
     int nmatches = 0;
     Check(orbm_window_search_best(&view, (int)nq, &uvr[0], &minl[0], &maxl[0], 0, 0, &valid[0], &qdesc[0], 0, 0,
-                                  kps.empty() ? 0 : &initObs[0], kps.empty() ? 0 : &assign[0], TH_LOW, 0, &nmatches, Device()),
+                                  Ptr(initObs), Ptr(assign), TH_LOW, 0, &nmatches, Device()),
           "orbm_window_search_best");
     for (size_t k = 0; k < kps.size(); ++k) if (assign[k] >= 0) vpMatched[k] = vpPoints[(size_t)assign[k]];
     return nmatches;

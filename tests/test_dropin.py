@@ -109,6 +109,11 @@ def test_matcher_forwarders_run_like_the_patched_reference(dropin):
                                                p(q["view_cos"]), p(q["in_view"]), p(q["bad"]), p(q["obs"]), p(q["desc"]), p(ia), p(out), 3.0, 0.8)
         want = Matcher("oracle").search_by_projection_points(k2, d2, ur, scale, bounds, q, 3.0, 0.8, ia)
         assert nm == want[0] and nm > 300 and (out == want[1]).all()
+    # a frame without keypoints (a black image): the reference returns 0 matches and tracking goes on to "lost"; the
+    # forwarder must do the same, not throw (the C ABI accepts assign_out = NULL when the frame is empty)
+    nm = M.fwd_search_by_projection_points(0, None, None, None, p(scale), len(scale), *bounds, 1500, p(q["proj"]), p(q["level"]),
+                                           p(q["view_cos"]), p(q["in_view"]), p(q["bad"]), p(q["obs"]), p(q["desc"]), None, None, 3.0, 0.8)
+    assert nm == 0
     # SearchByBoW x2
     s = bow_scene(kps, desc, 8, n2=1700)
     (id1, off1, f1), (id2, off2, f2) = s["fv1"], s["fv2"]
