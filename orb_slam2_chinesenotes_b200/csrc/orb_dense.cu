@@ -38,6 +38,10 @@ __device__ __forceinline__ uint32_t dp2a_hi(const uint32_t a, const uint32_t b, 
 #ifndef PYR_NT
 #define PYR_NT 64        // measured per 1024 frames: 32 threads 1.82 ms, 64 1.60, 128 1.63, 256 2.00
 #endif
+// Measured dead end (round 2): keeping the raw words of the next 2..4 source rows in flight in a register ring (loads issued
+// two to three destination rows ahead of the funnel shift that needs them) costs 16 more registers and the ring's moves:
+// 1.02 / 1.11 / 1.15 ms per 512 frames for 2 / 3 / 4 rows ahead against 0.78 ms for this version, whose loads are hidden
+// by the 36 resident warps per SM instead.
 #define PYR_TW 128
 #define PYR_TH 64
 
