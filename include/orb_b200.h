@@ -64,6 +64,29 @@ int orbx_shape_supported(const orbx_ctx* ctx, int w, int h);
 int orbx_extract(orbx_ctx* ctx, const uint8_t* img, int w, int h, size_t pitch,
                  orbx_kp* kps, uint8_t* desc, int capacity, int* n_out);
 
+/* What Frame::ExtractORB (src/Frame.cc:262-268) needs from ONE call, at the lowest latency: operator() for one host
+ * image plus, if with_pyramid, mvImagePyramid (include/ORBextractor.h:86: every level as a view inside its
+ * REFLECT_101-padded buffer, src/ORBextractor.cc:1157-1178, which Frame::ComputeStereoMatches reads, src/Frame.cc:520,
+ * 611-633).  The image goes up through a pinned staging buffer (or straight from the caller's buffer when that is
+ * pinned), the whole pipeline replays as one CUDA graph, and keypoints, descriptors and all padded levels come back
+ * with it into context-owned pinned host memory: everything in `out` points INTO the context and stays valid until
+ * the next call on it, like the reference's mvImagePyramid.  orbx_extract() on a single host image takes the same
+ * path and copies the n records out. */
+#define ORBX_MAX_LEVELS 16
+typedef struct {
+    int n;                                   /* keypoints found */
+    const orbx_kp* kps;                      /* [n] */
+    const uint8_t* desc;                     /* [n][32] */
+    int nlevels;                             /* 0 unless with_pyramid */
+    const uint8_t* level[ORBX_MAX_LEVELS];   /* first pixel of level l INSIDE its padded buffer (19 px border all round) */
+    int level_w[ORBX_MAX_LEVELS], level_h[ORBX_MAX_LEVELS];
+    size_t level_pitch[ORBX_MAX_LEVELS];
+} orbx_frame_out;
+int orbx_extract_frame(orbx_ctx* ctx, const uint8_t* image, int w, int h, size_t pitch, int with_pyramid, orbx_frame_out* out);
+/* Host-side microseconds of the last single-call invocation: {copy into the pinned staging buffer, cudaGraphLaunch,
+ * wait until the results are back}.  Development aid (tools/latency_once.py). */
+int orbx_debug_last_call_us(const orbx_ctx* ctx, double* us3);
+
 /* The same over a batch of equally sized frames: frame f starts at imgs + f*frame_stride.
  * Outputs are [batch][cap_per_frame] / [batch][cap_per_frame][32] / [batch].  This is the
  * call Frame::ExtractORB (src/Frame.cc:262-268) would make once per camera per frame;

@@ -55,6 +55,12 @@ class OrbmFeatVec(C.Structure):
     _fields_ = [("node_id", C.c_void_p), ("node_off", C.c_void_p), ("n_nodes", C.c_void_p), ("feat", C.c_void_p), ("node_stride", C.c_int)]
 
 
+class _FrameOut(C.Structure):
+    """orbx_frame_out (include/orb_b200.h)."""
+    _fields_ = [("n", C.c_int), ("kps", C.c_void_p), ("desc", C.c_void_p), ("nlevels", C.c_int), ("level", C.c_void_p * 16),
+                ("level_w", C.c_int * 16), ("level_h", C.c_int * 16), ("level_pitch", C.c_size_t * 16)]
+
+
 class OrbError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"orb_b200 status {code}: {msg}")
@@ -111,6 +117,8 @@ def lib():
         L.orbx_plan_describe.argtypes = [i32, f32, i32, i32, i32, i32, i32] + [vp] * 6
         L.orbx_max_keypoints.argtypes = [i32, f32, i32, i32, i32, i32, i32]
         L.orbx_launches_per_chunk.argtypes = [vp, i32]
+        L.orbx_extract_frame.argtypes = [vp, vp, i32, i32, sz, i32, vp]
+        L.orbx_debug_last_call_us.argtypes = [vp, vp]
         L.orbm_hamming_bf.argtypes = [vp, i32, vp, i32, i32, vp, vp, vp, i32]
         L.orbm_hamming_bf_async.argtypes = [vp, i32, vp, i32, i32, vp, vp, vp, vp]
         fp = C.POINTER(OrbmFrame)
@@ -165,6 +173,7 @@ class ORBextractor:
     def __init__(self, nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, device=0):
         self._L = lib()
         self._h = C.c_void_p()
+        self._profiling = False
         self.nfeatures, self.nlevels = int(nfeatures), int(nlevels)
         rc = self._L.orbx_create(C.byref(self._h), nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, device)
         if rc:
@@ -227,11 +236,22 @@ class ORBextractor:
         assert image.dtype == np.uint8 and image.ndim == 2, "CV_8UC1 expected (src/ORBextractor.cc:1091)"
         if image.strides[1] != 1 or image.strides[0] < image.shape[1]:   # also views with a negative / overlapping row stride
             image = np.ascontiguousarray(image)
+        h, w = image.shape
+        if capacity is None and not self._profiling:
+            # orbx_extract_frame: the single-call CUDA graph; the results are copied out of the context's pinned memory
+            out = _FrameOut()
+            self._check(self._L.orbx_extract_frame(self._h, image.ctypes.data, w, h, image.strides[0], 0, C.byref(out)))
+            k = out.n
+            kps = np.empty(k, KP_DTYPE)
+            desc = np.empty((k, 32), np.uint8)
+            if k:
+                C.memmove(kps.ctypes.data, out.kps, k * 28)
+                C.memmove(desc.ctypes.data, out.desc, k * 32)
+            return kps, desc
         cap = capacity or self.default_capacity()
         kps = np.zeros(cap, KP_DTYPE)
         desc = np.zeros((cap, 32), np.uint8)
         n = np.zeros(1, np.int32)
-        h, w = image.shape
         self._check(self._L.orbx_extract(self._h, image.ctypes.data, w, h, image.strides[0], kps.ctypes.data,
                                          desc.ctypes.data, cap, n.ctypes.data))
         k = int(n[0])
@@ -326,6 +346,7 @@ class ORBextractor:
         return r
 
     def profile(self, enable=True):
+        self._profiling = bool(enable)
         self._check(self._L.orbx_profile(self._h, int(enable)))
 
     def stage_ms(self, reset=True):

@@ -11,6 +11,7 @@
 // is enabled (orbx_profile) everything runs on the one stream so the CUDA events bracket kernels.
 #include <cstdarg>
 #include <cstdio>
+#include <chrono>
 #include <cstring>
 #include <new>
 #include <string>
@@ -42,6 +43,21 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
 };
 
+struct PinBuf {     // pinned host memory
+    void* p = nullptr;
+    size_t bytes = 0;
+    cudaError_t reserve(size_t n)
+    {
+        if (n <= bytes) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; bytes = 0;
+        cudaError_t e = cudaHostAlloc(&p, n, cudaHostAllocDefault);
+        if (e == cudaSuccess) bytes = n;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; bytes = 0; }
+};
+
 // One set of per-chunk device buffers.
 struct Slot {
     DevBuf img_stage, pyr, blur, cand, node_of, counts, lkp, out_kps, out_desc, out_n;
@@ -51,6 +67,9 @@ struct Slot {
     cudaEvent_t h2d_done = nullptr, compute_done = nullptr, d2h_done = nullptr;
     cudaStream_t aux = nullptr;            // the blur runs here, beside FAST + quadtree (both only need the pyramid)
     cudaEvent_t pyr_done = nullptr, blur_done = nullptr;
+    // a handful of frames (latency): FAST + quadtree of level l run on their own stream as soon as level l exists
+    cudaStream_t lvl[ORB_MAX_LEVELS] = { nullptr };
+    cudaEvent_t lvl_ready[ORB_MAX_LEVELS] = { nullptr }, lvl_done[ORB_MAX_LEVELS] = { nullptr };
     bool used = false;
     void release()
     {
@@ -65,6 +84,32 @@ struct Slot {
 struct StereoReq {
     float bf, fx;
     float* u_right; float* depth; int* n_stereo;
+};
+
+// The single-call path (one frame or one stereo pair from host memory): everything one call does -- the upload, every
+// kernel, the download of the results and of the padded pyramid -- is ONE instantiated CUDA graph over fixed buffers.
+struct FramePath {
+    cudaGraphExec_t exec = nullptr;
+    // what the graph was captured for
+    int w = 0, h = 0, pitch = 0, frames = 0, cap = 0, nlevels = 0;
+    bool stereo = false, pyr = false;
+    float bf = 0.f, fx = 0.f;
+    cudaStream_t stream = nullptr;
+    cudaGraphNode_t in_node = nullptr;     // the host->device copy of the frames
+    const void* in_src = nullptr;          // its current source: h_in, or the caller's own buffer when that is pinned
+    PinBuf h_in, h_kps, h_desc, h_n, h_ur, h_dep, h_ns, h_pad;
+    DevBuf d_in, d_kps, d_desc, d_n, d_ur, d_dep, d_ns, d_pad;
+    OrbBorderJob job;
+    double last_us[3] = { 0, 0, 0 };       // host time of the last call: staging copy, graph launch, wait for the results
+    void release()
+    {
+        if (exec) cudaGraphExecDestroy(exec);
+        exec = nullptr;
+        PinBuf* hb[] = { &h_in, &h_kps, &h_desc, &h_n, &h_ur, &h_dep, &h_ns, &h_pad };
+        for (PinBuf* x : hb) x->release();
+        DevBuf* db[] = { &d_in, &d_kps, &d_desc, &d_n, &d_ur, &d_dep, &d_ns, &d_pad };
+        for (DevBuf* x : db) x->release();
+    }
 };
 
 struct StageTimer {
@@ -92,7 +137,8 @@ struct orbx_ctx {
     bool have_plan = false;
     OrbPlan plan;
     DevBuf taps, border_tmp;
-    Slot slot[NSLOT];
+    Slot slot[NSLOT + 1];                  // the last one belongs to the single-call path
+    FramePath fp;
 
     // what is resident from the last call (for orbx_pyramid_level / stage taps)
     int last_slot = -1, last_first = 0, last_count = 0;
@@ -134,7 +180,10 @@ int sync_all(orbx_ctx* c)
     CU(c, cudaStreamSynchronize(c->h2d_stream));
     CU(c, cudaStreamSynchronize(c->stream));
     for (cudaStream_t x : c->xstream) CU(c, cudaStreamSynchronize(x));
-    for (Slot& s : c->slot) CU(c, cudaStreamSynchronize(s.aux));
+    for (Slot& s : c->slot) {
+        CU(c, cudaStreamSynchronize(s.aux));
+        for (cudaStream_t x : s.lvl) if (x) CU(c, cudaStreamSynchronize(x));
+    }
     CU(c, cudaStreamSynchronize(c->d2h_stream));
     return ORBX_OK;
 }
@@ -153,6 +202,7 @@ int ensure_plan(orbx_ctx* c, int w, int h)
     c->have_plan = true;
     for (Slot& s : c->slot) s.frames = 0;   // work buffers are re-sized lazily (reserve only grows)
     c->last_slot = -1; c->last_count = 0;
+    if (c->fp.exec) { cudaGraphExecDestroy(c->fp.exec); c->fp.exec = nullptr; }   // captured for the old shape
     return ORBX_OK;
 }
 
@@ -228,6 +278,17 @@ void collect_timers(orbx_ctx* c)
     c->pending.clear();
 }
 
+int ensure_level_streams(orbx_ctx* c, Slot& s, int nlevels)
+{
+    for (int l = 0; l < nlevels; ++l)
+        if (!s.lvl[l]) {
+            CU(c, cudaStreamCreateWithFlags(&s.lvl[l], cudaStreamNonBlocking));
+            CU(c, cudaEventCreateWithFlags(&s.lvl_ready[l], cudaEventDisableTiming));
+            CU(c, cudaEventCreateWithFlags(&s.lvl_done[l], cudaEventDisableTiming));
+        }
+    return ORBX_OK;
+}
+
 // Enqueue the whole extractor for `frames` frames whose level-0 images are device resident.
 int enqueue_chunk(orbx_ctx* c, Slot& s, cudaStream_t st, const uint8_t* d_img, size_t frame_stride, int pitch, int frames,
                   orbx_kp* d_kps, uint8_t* d_desc, int* d_n, int cap,
@@ -244,7 +305,26 @@ int enqueue_chunk(orbx_ctx* c, Slot& s, cudaStream_t st, const uint8_t* d_img, s
     io.kps = d_kps; io.desc = d_desc; io.n_out = d_n; io.cap = cap;
     io.taps = (const OrbTap*)c->taps.p;
     CU(c, cudaMemsetAsync(io.cand_count, 0, (size_t)frames * ORB_MAX_LEVELS * 4, st));
-    { StageScope t(c, ORBX_STAGE_PYRAMID, st); CU(c, orb_launch_pyramid(P, io, frames, st)); }
+    // A handful of frames (latency): the quadtree of one level is the longest single piece of the call and needs only
+    // that level, so FAST + quadtree of level l start on their own stream as soon as level l exists (level 0: at once),
+    // beside the rest of the pyramid, the blur and the other levels.
+    const bool split = !c->profile && frames <= 2 && P.nlevels > 1;
+    if (split) {
+        int rc = ensure_level_streams(c, s, P.nlevels);
+        if (rc) return rc;
+        fast_maps_prepare(P, io, frames, &s.fmaps);      // once, not per level
+        for (int l = 0; l < P.nlevels; ++l) {
+            if (l > 0) CU(c, orb_launch_pyramid_level(P, io, frames, l, st));
+            CU(c, cudaEventRecord(s.lvl_ready[l], st));
+            CU(c, cudaStreamWaitEvent(s.lvl[l], s.lvl_ready[l], 0));
+            CU(c, orb_launch_fast(P, io, frames, s.lvl[l], &s.fmaps, l, l + 1));
+            CU(c, orb_launch_octree(P, io, frames, s.lvl[l], l, l + 1));
+            CU(c, cudaEventRecord(s.lvl_done[l], s.lvl[l]));
+        }
+    } else {
+        StageScope t(c, ORBX_STAGE_PYRAMID, st);
+        CU(c, orb_launch_pyramid(P, io, frames, st));
+    }
     if (c->profile) {
         { StageScope t(c, ORBX_STAGE_FAST, st); CU(c, orb_launch_fast(P, io, frames, st, &s.fmaps)); }
         { StageScope t(c, ORBX_STAGE_BLUR, st); CU(c, orb_launch_blur(P, io, frames, st)); }
@@ -254,9 +334,12 @@ int enqueue_chunk(orbx_ctx* c, Slot& s, cudaStream_t st, const uint8_t* d_img, s
         CU(c, cudaStreamWaitEvent(s.aux, s.pyr_done, 0));
         CU(c, orb_launch_blur(P, io, frames, s.aux));
         CU(c, cudaEventRecord(s.blur_done, s.aux));
-        CU(c, orb_launch_fast(P, io, frames, st, &s.fmaps));
-        CU(c, orb_launch_octree(P, io, frames, st));
+        if (!split) {
+            CU(c, orb_launch_fast(P, io, frames, st, &s.fmaps));
+            CU(c, orb_launch_octree(P, io, frames, st));
+        }
         CU(c, cudaStreamWaitEvent(st, s.blur_done, 0));
+        if (split) for (int l = 0; l < P.nlevels; ++l) CU(c, cudaStreamWaitEvent(st, s.lvl_done[l], 0));
     }
     { StageScope t(c, ORBX_STAGE_DESCRIBE, st); CU(c, orb_launch_describe(P, io, frames, st)); }
     if (sr) {
@@ -396,6 +479,159 @@ int run_batch(orbx_ctx* c, const uint8_t* imgs, size_t frame_stride, int batch, 
     return ORBX_OK;
 }
 
+// ---- single-call path ------------------------------------------------------------------------------------------
+bool is_pinned_host(const void* p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+// Capture the graph of one call: frames (1, or 2 = a stereo pair) of w x h with row pitch `pitch`.
+int frame_path_build(orbx_ctx* c, int w, int h, int pitch, int frames, const StereoReq* sr, bool pyr)
+{
+    FramePath& F = c->fp;
+    const OrbPlan& P = c->plan;
+    if (F.exec) { cudaGraphExecDestroy(F.exec); F.exec = nullptr; }
+    int cap = 0;
+    for (int l = 0; l < P.nlevels; ++l) cap += P.lv[l].kp_cap;           // no frame can return more (orbx_max_keypoints)
+    Slot& s = c->slot[NSLOT];
+    int rc = ensure_slot(c, s, frames, cap, false, 0, false, sr != nullptr);
+    if (rc) return rc;
+    rc = sync_all(c);
+    if (rc) return rc;
+    const size_t in_bytes = (size_t)frames * pitch * h;
+    CU(c, F.h_in.reserve(in_bytes)); CU(c, F.d_in.reserve(in_bytes + 256));
+    CU(c, F.h_kps.reserve((size_t)frames * cap * sizeof(orbx_kp))); CU(c, F.d_kps.reserve((size_t)frames * cap * sizeof(orbx_kp)));
+    CU(c, F.h_desc.reserve((size_t)frames * cap * 32)); CU(c, F.d_desc.reserve((size_t)frames * cap * 32));
+    CU(c, F.h_n.reserve(64)); CU(c, F.d_n.reserve(64));
+    if (sr) {
+        CU(c, F.h_ur.reserve((size_t)cap * 4)); CU(c, F.d_ur.reserve((size_t)cap * 4));
+        CU(c, F.h_dep.reserve((size_t)cap * 4)); CU(c, F.d_dep.reserve((size_t)cap * 4));
+        CU(c, F.h_ns.reserve(64)); CU(c, F.d_ns.reserve(64));
+    }
+    size_t pad = 0;
+    for (int l = 0; l < P.nlevels; ++l) {
+        F.job.off[l] = (uint32_t)pad;
+        F.job.pitch[l] = (P.lv[l].w + 2 * ORB_EDGE + 15) & ~15;
+        pad += ((size_t)F.job.pitch[l] * (P.lv[l].h + 2 * ORB_EDGE) + 255) & ~(size_t)255;
+    }
+    F.job.frame_bytes = pad;
+    if (pyr) { CU(c, F.h_pad.reserve(pad * frames)); CU(c, F.d_pad.reserve(pad * frames)); }
+
+    rc = ensure_level_streams(c, s, P.nlevels);          // nothing may be created while the stream is capturing
+    if (rc) return rc;
+    cudaStream_t st = c->stream;
+    CU(c, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    cudaGraph_t graph = nullptr;
+    int erc = ORBX_OK;
+    do {
+        if (cudaMemcpyAsync(F.d_in.p, F.h_in.p, in_bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) { erc = ORBX_E_CUDA; break; }
+        StereoReq dsr;
+        if (sr) { dsr = *sr; dsr.u_right = (float*)F.d_ur.p; dsr.depth = (float*)F.d_dep.p; dsr.n_stereo = (int*)F.d_ns.p; }
+        erc = enqueue_chunk(c, s, st, (const uint8_t*)F.d_in.p, (size_t)pitch * h, pitch, frames, (orbx_kp*)F.d_kps.p, (uint8_t*)F.d_desc.p,
+                            (int*)F.d_n.p, cap, sr ? &dsr : nullptr, sr ? (float*)F.d_ur.p : nullptr, sr ? (float*)F.d_dep.p : nullptr, sr ? (int*)F.d_ns.p : nullptr);
+        if (erc) break;
+        bool ok = true;
+        if (pyr) {
+            // the padded levels leave on the copy stream as soon as the pyramid exists, beside FAST / quadtree / descriptors
+            OrbBatch io;
+            memset(&io, 0, sizeof(io));
+            io.img0 = (const uint8_t*)F.d_in.p; io.img0_stride = (size_t)pitch * h; io.img0_pitch = pitch; io.pyr = (uint8_t*)s.pyr.p;
+            ok = ok && cudaStreamWaitEvent(c->d2h_stream, s.pyr_done, 0) == cudaSuccess;
+            ok = ok && orb_launch_border_levels(P, io, F.job, (uint8_t*)F.d_pad.p, frames, c->d2h_stream) == cudaSuccess;
+            ok = ok && cudaMemcpyAsync(F.h_pad.p, F.d_pad.p, pad * frames, cudaMemcpyDeviceToHost, c->d2h_stream) == cudaSuccess;
+            ok = ok && cudaEventRecord(s.d2h_done, c->d2h_stream) == cudaSuccess;
+        }
+        ok = ok && cudaMemcpyAsync(F.h_n.p, F.d_n.p, (size_t)frames * 4, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+        ok = ok && cudaMemcpyAsync(F.h_kps.p, F.d_kps.p, (size_t)frames * cap * sizeof(orbx_kp), cudaMemcpyDeviceToHost, st) == cudaSuccess;
+        ok = ok && cudaMemcpyAsync(F.h_desc.p, F.d_desc.p, (size_t)frames * cap * 32, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+        if (sr) {
+            ok = ok && cudaMemcpyAsync(F.h_ur.p, F.d_ur.p, (size_t)cap * 4, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+            ok = ok && cudaMemcpyAsync(F.h_dep.p, F.d_dep.p, (size_t)cap * 4, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+            ok = ok && cudaMemcpyAsync(F.h_ns.p, F.d_ns.p, 4, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+        }
+        if (pyr) ok = ok && cudaStreamWaitEvent(st, s.d2h_done, 0) == cudaSuccess;
+        if (!ok) erc = ORBX_E_CUDA;
+    } while (0);
+    const cudaError_t ec = cudaStreamEndCapture(st, &graph);
+    if (erc || ec != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        return fail(c, ORBX_E_CUDA, "single-call graph capture failed (%s)", cudaGetErrorString(ec));
+    }
+    // the node that uploads the frames: its source is re-pointed at the caller's buffer when that is pinned
+    F.in_node = nullptr;
+    size_t nn = 0;
+    cudaGraphGetNodes(graph, nullptr, &nn);
+    std::vector<cudaGraphNode_t> nodes(nn);
+    cudaGraphGetNodes(graph, nodes.data(), &nn);
+    for (cudaGraphNode_t nd : nodes) {
+        cudaGraphNodeType t;
+        if (cudaGraphNodeGetType(nd, &t) != cudaSuccess || t != cudaGraphNodeTypeMemcpy) continue;
+        cudaMemcpy3DParms mp;
+        if (cudaGraphMemcpyNodeGetParams(nd, &mp) == cudaSuccess && mp.dstPtr.ptr == F.d_in.p) { F.in_node = nd; break; }
+    }
+    const cudaError_t ei = cudaGraphInstantiate(&F.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ei != cudaSuccess) { F.exec = nullptr; return fail(c, ORBX_E_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ei)); }
+    F.w = w; F.h = h; F.pitch = pitch; F.frames = frames; F.cap = cap; F.nlevels = P.nlevels; F.stereo = sr != nullptr; F.pyr = pyr;
+    F.bf = sr ? sr->bf : 0.f; F.fx = sr ? sr->fx : 0.f; F.stream = st; F.in_src = F.h_in.p;
+    return ORBX_OK;
+}
+
+// One frame (or one pair) from HOST memory through the graph; the results are left in the path's pinned buffers.
+int frame_path_run(orbx_ctx* c, const uint8_t* imgs, size_t frame_stride, int frames, int w, int h, size_t pitch, const StereoReq* sr, bool pyr)
+{
+    CU(c, cudaSetDevice(c->device));
+    int rc = ensure_plan(c, w, h);
+    if (rc) return rc;
+    FramePath& F = c->fp;
+    const bool fit = F.exec && F.w == w && F.h == h && F.pitch == (int)pitch && F.frames == frames && F.stereo == (sr != nullptr) &&
+                     (F.pyr || !pyr) && F.stream == c->stream && (!sr || (F.bf == sr->bf && F.fx == sr->fx));
+    if (!fit) {
+        rc = frame_path_build(c, w, h, (int)pitch, frames, sr, pyr || F.pyr);
+        if (rc) return rc;
+    }
+    const size_t fbytes = pitch * (size_t)h, in_bytes = (size_t)frames * fbytes;
+    const void* src = F.h_in.p;
+    const std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    if (F.in_node && (frames == 1 || frame_stride == fbytes) && is_pinned_host(imgs) && is_pinned_host(imgs + in_bytes - 1)) src = imgs;
+    else for (int f = 0; f < frames; ++f) memcpy((uint8_t*)F.h_in.p + (size_t)f * fbytes, imgs + (size_t)f * frame_stride, pitch * (size_t)(h - 1) + (size_t)w);
+    if (src != F.in_src) {
+        CU(c, cudaGraphExecMemcpyNodeSetParams1D(F.exec, F.in_node, F.d_in.p, src, in_bytes, cudaMemcpyHostToDevice));
+        F.in_src = src;
+    }
+    const std::chrono::steady_clock::time_point t1 = std::chrono::steady_clock::now();
+    CU(c, cudaGraphLaunch(F.exec, c->stream));
+    const std::chrono::steady_clock::time_point t2 = std::chrono::steady_clock::now();
+    CU(c, cudaStreamSynchronize(c->stream));
+    const std::chrono::steady_clock::time_point t3 = std::chrono::steady_clock::now();
+    F.last_us[0] = std::chrono::duration<double, std::micro>(t1 - t0).count();
+    F.last_us[1] = std::chrono::duration<double, std::micro>(t2 - t1).count();
+    F.last_us[2] = std::chrono::duration<double, std::micro>(t3 - t2).count();
+    c->last_slot = NSLOT; c->last_first = 0; c->last_count = frames;
+    c->last_img0 = (const uint8_t*)F.d_in.p; c->last_img0_stride = fbytes; c->last_img0_pitch = (int)pitch;
+    return ORBX_OK;
+}
+
+// Copy the first min(n, cap) records of frame f from the path's pinned buffers to the caller's (host) arrays.
+int frame_path_copy_out(orbx_ctx* c, int f, orbx_kp* kps, uint8_t* desc, int cap, int* n_out)
+{
+    const FramePath& F = c->fp;
+    const int n = ((const int*)F.h_n.p)[f];
+    *n_out = n;
+    const int m = n < cap ? n : cap;
+    memcpy(kps, (const orbx_kp*)F.h_kps.p + (size_t)f * F.cap, (size_t)m * sizeof(orbx_kp));
+    memcpy(desc, (const uint8_t*)F.h_desc.p + (size_t)f * F.cap * 32, (size_t)m * 32);
+    return n > cap ? fail(c, ORBX_E_CAPACITY, "frame %d: %d keypoints > capacity %d", f, n, cap) : ORBX_OK;
+}
+
+bool all_host(const void* a, const void* b, const void* d, const void* e)
+{
+    return !is_device_ptr(a) && !is_device_ptr(b) && !is_device_ptr(d) && !is_device_ptr(e);
+}
+
 int resident_frame(orbx_ctx* c, int frame, int level)
 {
     if (!c || !c->have_plan || c->last_count == 0 || c->last_slot < 0) return -1;
@@ -464,6 +700,7 @@ int orbx_create(orbx_ctx** out, int nfeatures, float scaleFactor, int nlevels, i
              cudaEventCreateWithFlags(&s.d2h_done, cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&s.pyr_done, cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&s.blur_done, cudaEventDisableTiming) == cudaSuccess &&
+
              cudaStreamCreateWithFlags(&s.aux, cudaStreamNonBlocking) == cudaSuccess;
     if (!ok) { cudaGetLastError(); delete c; return ORBX_E_CUDA; }
     c->stream = c->own_stream;
@@ -485,8 +722,14 @@ void orbx_destroy(orbx_ctx* c)
         if (s.d2h_done) cudaEventDestroy(s.d2h_done);
         if (s.pyr_done) cudaEventDestroy(s.pyr_done);
         if (s.blur_done) cudaEventDestroy(s.blur_done);
+        for (int l = 0; l < ORB_MAX_LEVELS; ++l) {
+            if (s.lvl_ready[l]) cudaEventDestroy(s.lvl_ready[l]);
+            if (s.lvl_done[l]) cudaEventDestroy(s.lvl_done[l]);
+            if (s.lvl[l]) cudaStreamDestroy(s.lvl[l]);
+        }
         if (s.aux) cudaStreamDestroy(s.aux);
     }
+    c->fp.release();
     c->taps.release(); c->border_tmp.release();
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
@@ -521,7 +764,41 @@ int orbx_shape_supported(const orbx_ctx* c, int w, int h)
 
 int orbx_extract(orbx_ctx* c, const uint8_t* img, int w, int h, size_t pitch, orbx_kp* kps, uint8_t* desc, int capacity, int* n_out)
 {
+    // one host image: the single-call graph (stage timing needs the launch-by-launch path)
+    if (c && !c->profile && img && w > 0 && h > 0 && pitch >= (size_t)w && capacity > 0 && kps && desc && n_out && all_host(img, kps, desc, n_out)) {
+        const int rc = frame_path_run(c, img, pitch * (size_t)h, 1, w, h, pitch, nullptr, false);
+        return rc ? rc : frame_path_copy_out(c, 0, kps, desc, capacity, n_out);
+    }
     return run_batch(c, img, pitch * (size_t)(h > 0 ? h : 0), 1, w, h, pitch, kps, desc, capacity, n_out, false);
+}
+
+int orbx_debug_last_call_us(const orbx_ctx* c, double* us3)
+{
+    if (!c || !us3) return ORBX_E_ARG;
+    for (int i = 0; i < 3; ++i) us3[i] = c->fp.last_us[i];
+    return ORBX_OK;
+}
+
+int orbx_extract_frame(orbx_ctx* c, const uint8_t* image, int w, int h, size_t pitch, int with_pyramid, orbx_frame_out* out)
+{
+    if (!c || !out) return ORBX_E_ARG;
+    if (!image || w <= 0 || h <= 0) return fail(c, ORBX_E_EMPTY, "empty image");
+    if (pitch < (size_t)w || is_device_ptr(image)) return fail(c, ORBX_E_ARG, "bad argument (a host image is expected)");
+    const int rc = frame_path_run(c, image, pitch * (size_t)h, 1, w, h, pitch, nullptr, with_pyramid != 0);
+    if (rc) return rc;
+    const FramePath& F = c->fp;
+    memset(out, 0, sizeof(*out));
+    out->n = ((const int*)F.h_n.p)[0];
+    out->kps = (const orbx_kp*)F.h_kps.p;
+    out->desc = (const uint8_t*)F.h_desc.p;
+    if (with_pyramid) {
+        out->nlevels = c->plan.nlevels;
+        for (int l = 0; l < c->plan.nlevels; ++l) {
+            out->level_w[l] = c->plan.lv[l].w; out->level_h[l] = c->plan.lv[l].h; out->level_pitch[l] = (size_t)F.job.pitch[l];
+            out->level[l] = (const uint8_t*)F.h_pad.p + F.job.off[l] + (size_t)ORB_EDGE * F.job.pitch[l] + ORB_EDGE;
+        }
+    }
+    return ORBX_OK;
 }
 
 int orbx_extract_batch(orbx_ctx* c, const uint8_t* imgs, size_t frame_stride, int batch, int w, int h, size_t pitch,
@@ -541,6 +818,21 @@ int orbx_extract_stereo_batch(orbx_ctx* c, const uint8_t* imgs, size_t frame_str
                               float* u_right, float* depth, int* n_stereo)
 {
     const StereoReq sr = { bf, fx, u_right, depth, n_stereo };
+    // one host pair: the single-call graph
+    if (c && !c->profile && pairs == 1 && imgs && w > 0 && h > 0 && pitch >= (size_t)w && cap_per_frame > 0 && cap_per_frame <= 65535 && kps && desc && n_out &&
+        u_right && depth && n_stereo && fx > 0.f && frame_stride >= pitch * (size_t)(h - 1) + (size_t)w && all_host(imgs, kps, desc, n_out) && all_host(u_right, depth, n_stereo, n_stereo)) {
+        int rc = frame_path_run(c, imgs, frame_stride, 2, w, h, pitch, &sr, false);
+        if (rc) return rc;
+        rc = frame_path_copy_out(c, 0, kps, desc, cap_per_frame, n_out);
+        const int rc1 = frame_path_copy_out(c, 1, kps + cap_per_frame, desc + (size_t)cap_per_frame * 32, cap_per_frame, n_out + 1);
+        const FramePath& F = c->fp;
+        const int m = n_out[0] < cap_per_frame ? n_out[0] : cap_per_frame;
+        for (int i = 0; i < cap_per_frame; ++i) { u_right[i] = -1.0f; depth[i] = -1.0f; }
+        memcpy(u_right, F.h_ur.p, (size_t)m * 4);
+        memcpy(depth, F.h_dep.p, (size_t)m * 4);
+        n_stereo[0] = ((const int*)F.h_ns.p)[0];
+        return rc ? rc : rc1;
+    }
     return run_batch(c, imgs, frame_stride, 2 * pairs, w, h, pitch, kps, desc, cap_per_frame, n_out, false, &sr);
 }
 

@@ -271,28 +271,61 @@ __global__ void k_border(const uint8_t* __restrict__ src, int w, int h, int spit
     dst[(size_t)y * dpitch + x] = src[(size_t)orb_refl101(y - b, h) * spitch + orb_refl101(x - b, w)];
 }
 
+// All levels of `frames` frames at once (the single-call path: one launch, one device-to-host copy): level l of frame f
+// goes to dst + f * job.frame_bytes + job.off[l] with row pitch job.pitch[l]; one thread writes 4 adjacent bytes.
+__global__ void __launch_bounds__(256) k_border_levels(const __grid_constant__ OrbPlan plan, const OrbBatch io, const __grid_constant__ OrbBorderJob job, uint8_t* __restrict__ dst)
+{
+    const int l = blockIdx.z % plan.nlevels, frame = blockIdx.z / plan.nlevels;
+    const OrbLevel& L = plan.lv[l];
+    const int b = ORB_EDGE, bw = L.w + 2 * b, bh = L.h + 2 * b;
+    const int x4 = 4 * (blockIdx.x * blockDim.x + threadIdx.x), y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x4 >= bw || y >= bh) return;
+    int spitch;
+    const uint8_t* src = orb_level_ptr(plan, io, frame, l, &spitch);
+    const uint8_t* row = src + (size_t)orb_refl101(y - b, L.h) * spitch;
+    uint32_t v = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v |= (uint32_t)__ldg(row + orb_refl101(min(x4 + i, bw - 1) - b, L.w)) << (8 * i);
+    *(uint32_t*)(dst + (size_t)frame * job.frame_bytes + job.off[l] + (size_t)y * job.pitch[l] + x4) = v;   // pitch is a multiple of 4, the tail bytes are padding
+}
+
+cudaError_t orb_launch_border_levels(const OrbPlan& plan, const OrbBatch& io, const OrbBorderJob& job, uint8_t* dst, int frames, cudaStream_t st)
+{
+    const int bw = plan.lv[0].w + 2 * ORB_EDGE, bh = plan.lv[0].h + 2 * ORB_EDGE;
+    dim3 blk(32, 8), grd(((bw + 3) / 4 + 31) / 32, (bh + 7) / 8, plan.nlevels * frames);
+    k_border_levels<<<grd, blk, 0, st>>>(plan, io, job, dst);
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------ launchers
+cudaError_t orb_launch_pyramid_level(const OrbPlan& plan, const OrbBatch& io, int batch, int l, cudaStream_t st)
+{
+    const OrbLevel& D = plan.lv[l];
+    const OrbLevel& S = plan.lv[l - 1];
+    // the walker needs the 4 destination pixels of a lane to span at most 7 source pixels
+    const bool walker = 4LL * S.w <= 5LL * D.w && S.w >= 12;
+    if (walker) {
+        // rows per warp: as many as still leave every SM a few dozen warps (each row waits for its loads)
+        int th = PYR_TH, tiles;
+        for (;; th >>= 1) {
+            tiles = ((D.w + PYR_TW - 1) / PYR_TW) * ((D.h + th - 1) / th);
+            if (th <= 8 || (long long)tiles * batch >= 148LL * 64) break;
+        }
+        k_pyr_resize<<<dim3((tiles + PYR_NT / 32 - 1) / (PYR_NT / 32), 1, batch), PYR_NT, 0, st>>>(plan, io, l, th);
+    } else {
+        dim3 blk(32, 8), grd((D.pitch / 4 + 31) / 32, (D.h + 7) / 8, batch);
+        k_pyr_resize_generic<<<grd, blk, 0, st>>>(plan, io, l);
+    }
+    return cudaGetLastError();
+}
+
 cudaError_t orb_launch_pyramid(const OrbPlan& plan, const OrbBatch& io, int batch, cudaStream_t st)
 {
     for (int l = 1; l < plan.nlevels; ++l) {
-        const OrbLevel& D = plan.lv[l];
-        const OrbLevel& S = plan.lv[l - 1];
-        // the walker needs the 4 destination pixels of a lane to span at most 7 source pixels
-        const bool walker = 4LL * S.w <= 5LL * D.w && S.w >= 12;
-        if (walker) {
-            // rows per warp: as many as still leave every SM a few dozen warps (each row waits for its loads)
-            int th = PYR_TH, tiles;
-            for (;; th >>= 1) {
-                tiles = ((D.w + PYR_TW - 1) / PYR_TW) * ((D.h + th - 1) / th);
-                if (th <= 8 || (long long)tiles * batch >= 148LL * 64) break;
-            }
-            k_pyr_resize<<<dim3((tiles + PYR_NT / 32 - 1) / (PYR_NT / 32), 1, batch), PYR_NT, 0, st>>>(plan, io, l, th);
-        } else {
-            dim3 blk(32, 8), grd((D.pitch / 4 + 31) / 32, (D.h + 7) / 8, batch);
-            k_pyr_resize_generic<<<grd, blk, 0, st>>>(plan, io, l);
-        }
+        const cudaError_t e = orb_launch_pyramid_level(plan, io, batch, l, st);
+        if (e != cudaSuccess) return e;
     }
-    return cudaGetLastError();
+    return cudaSuccess;
 }
 
 int orb_pyramid_launch_count(const OrbPlan& plan) { return plan.nlevels - 1; }   // one launch per level: a level is resized from the ROUNDED level above

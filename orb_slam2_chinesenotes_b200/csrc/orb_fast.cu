@@ -517,8 +517,11 @@ static void fast_maps_update(const OrbPlan& plan, const OrbBatch& io, int batch,
     M->key_w = plan.w; M->key_h = plan.h; M->key_levels = plan.nlevels;
 }
 
-cudaError_t orb_launch_fast(const OrbPlan& plan, const OrbBatch& io, int batch, cudaStream_t st, OrbFastMaps* maps)
+void fast_maps_prepare(const OrbPlan& plan, const OrbBatch& io, int batch, OrbFastMaps* maps) { fast_maps_update(plan, io, batch, maps); }
+
+cudaError_t orb_launch_fast(const OrbPlan& plan, const OrbBatch& io, int batch, cudaStream_t st, OrbFastMaps* maps, int level_lo, int level_hi)
 {
+    if (level_hi > plan.nlevels) level_hi = plan.nlevels;
     if (plan.total_cells == 0) return cudaSuccess;
     const size_t smem = orb_fast_smem_bytes(plan);
     if (smem > 48 * 1024) {
@@ -534,6 +537,7 @@ cudaError_t orb_launch_fast(const OrbPlan& plan, const OrbBatch& io, int batch, 
     int n = 0;
     for (int l = 0; l < plan.nlevels; ++l) {
         fg.first[l] = n;
+        if (l < level_lo || l >= level_hi) continue;          // levels outside the range get no blocks
         const int bpr = (plan.lv[l].fbands + ORB_FAST_WPB - 1) / ORB_FAST_WPB;
         n += bpr * ((plan.lv[l].ncy + fg.rows_per_block - 1) / fg.rows_per_block);
     }

@@ -401,6 +401,7 @@ struct ArenaBlock { char* dev = nullptr; char* pin = nullptr; size_t cap = 0, us
 struct ThreadArena {
     int device = -1;
     bool inflight = false;              // flush() queued host-to-device copies that no synchronisation has covered yet
+    cudaEvent_t flushed_ev = nullptr;   // recorded behind the last of them
     std::vector<ArenaBlock> up, scratch;
     void release()
     {
@@ -422,7 +423,7 @@ struct Scratch {
         if (dev != t_arena.device) { t_arena.release(); t_arena.device = dev; }
         // an entry point that failed after flush() may have left copies from the pinned twins in flight: they must land
         // before the bytes are reused (every successful call ends synchronised, the wait is then free)
-        if (t_arena.inflight) { if (cudaStreamSynchronize(0) != cudaSuccess) cudaGetLastError(); t_arena.inflight = false; }
+        if (t_arena.inflight) { if (cudaEventSynchronize(t_arena.flushed_ev) != cudaSuccess) cudaGetLastError(); t_arena.inflight = false; }
         for (ArenaBlock& b : t_arena.up) b.used = b.flushed = 0;
         for (ArenaBlock& b : t_arena.scratch) b.used = 0;
     }
@@ -466,7 +467,8 @@ struct Scratch {
             if (b.used > b.flushed) {
                 { const cudaError_t e_ = cudaMemcpyAsync(b.dev + b.flushed, b.pin + b.flushed, b.used - b.flushed, cudaMemcpyHostToDevice, 0); if (e_ != cudaSuccess) { report_cuda(e_, "flush", __LINE__); cudaGetLastError(); ok = false; return false; } }
                 b.flushed = b.used;
-                t_arena.inflight = true;
+                if (!t_arena.flushed_ev && cudaEventCreateWithFlags(&t_arena.flushed_ev, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); t_arena.flushed_ev = nullptr; }
+                if (t_arena.flushed_ev && cudaEventRecord(t_arena.flushed_ev, 0) == cudaSuccess) t_arena.inflight = true;
             }
         return ok;
     }

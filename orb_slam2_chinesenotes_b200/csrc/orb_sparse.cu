@@ -26,8 +26,14 @@
 // List size bound: a full pass runs only while size + 3*nToExpand <= N, so it ends with at most
 // N nodes (the very first pass: at most 4*nIni); a partial round stops at the first split that
 // reaches N, i.e. at most N+2.  plan.lv[l].kp_cap = max(N+3, 4*nIni).
-#ifndef OCT_NT
-#define OCT_NT 256
+#ifndef ORB_OCT_NT
+#define ORB_OCT_NT 256         // threads per block for batches (throughput: 128 / 256 / 512 / 1024 threads = 1.21 / 0.89 / 1.08 / 2.28 ms per 1024 frames)
+#endif
+#ifndef ORB_OCT_NT_SMALL
+#define ORB_OCT_NT_SMALL 1024  // ... and for a handful of frames, where one block per level is all the parallelism there is (latency)
+#endif
+#ifndef ORB_OCT_SMALL_BATCH
+#define ORB_OCT_SMALL_BATCH 8
 #endif
 
 struct OctShared {
@@ -48,13 +54,14 @@ __device__ __forceinline__ int oct_child(const short4 b, const int x, const int 
     return (x < midx ? 0 : 1) + (y < midy ? 0 : 2);  // n1,n2,n3,n4 (:467-484)
 }
 
-__global__ void __launch_bounds__(OCT_NT) k_octree(const __grid_constant__ OrbPlan plan, const OrbBatch io)
+template <int OCT_NT>
+__global__ void __launch_bounds__(OCT_NT) k_octree(const __grid_constant__ OrbPlan plan, const OrbBatch io, const int level_lo)
 {
     extern __shared__ __align__(16) unsigned char oct_smem[];
     __shared__ int s_scratch[OCT_NT / 32];
     __shared__ int s_nexp, s_m, s_L;
 
-    const int l = blockIdx.x, frame = blockIdx.y, tid = threadIdx.x;
+    const int l = blockIdx.x + level_lo, frame = blockIdx.y, tid = threadIdx.x;
     const OrbLevel& LV = plan.lv[l];
     const int cap = (plan.max_nodes + 31) & ~31;
     int sortn = 32; while (sortn < cap) sortn <<= 1;
@@ -268,14 +275,20 @@ size_t orb_octree_smem_bytes(const OrbPlan& plan)
     return cap * (8 * 2 + 4 * 2 + 16 + 4 * 3) + sortn * 8 + 64;
 }
 
-cudaError_t orb_launch_octree(const OrbPlan& plan, const OrbBatch& io, int batch, cudaStream_t st)
+cudaError_t orb_launch_octree(const OrbPlan& plan, const OrbBatch& io, int batch, cudaStream_t st, int level_lo, int level_hi)
 {
+    if (level_hi > plan.nlevels) level_hi = plan.nlevels;
+    if (level_lo >= level_hi) return cudaSuccess;
     const size_t smem = orb_octree_smem_bytes(plan);
+    const bool small = batch <= ORB_OCT_SMALL_BATCH;
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, ORB_SMEM_OPTIN);   // a constant: the attribute is per-function state shared by all host threads (a per-launch value races)
+        // a constant: the attribute is per-function state shared by all host threads (a per-launch value races)
+        cudaError_t e = small ? cudaFuncSetAttribute(k_octree<ORB_OCT_NT_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, ORB_SMEM_OPTIN)
+                              : cudaFuncSetAttribute(k_octree<ORB_OCT_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, ORB_SMEM_OPTIN);
         if (e != cudaSuccess) return e;
     }
-    k_octree<<<dim3(plan.nlevels, batch), OCT_NT, smem, st>>>(plan, io);
+    if (small) k_octree<ORB_OCT_NT_SMALL><<<dim3(level_hi - level_lo, batch), ORB_OCT_NT_SMALL, smem, st>>>(plan, io, level_lo);
+    else k_octree<ORB_OCT_NT><<<dim3(level_hi - level_lo, batch), ORB_OCT_NT, smem, st>>>(plan, io, level_lo);
     return cudaGetLastError();
 }
 

@@ -55,23 +55,13 @@ void ORBextractor::operator()( cv::InputArray _image, cv::InputArray /*_mask*/, 
     cv::Mat image = _image.getMat();
     assert(image.type() == CV_8UC1 );
 
-    // DistributeOctTree keeps at least its quota per level and at most a few more: start with
-    // nfeatures plus slack and grow on the (rare) capacity status.
-    int capacity = nfeatures + 4*nlevels + 64;
-    std::vector<orbx_kp> kps;
-    std::vector<unsigned char> desc;
-    int n = 0;
-    for(;;)
-    {
-        kps.resize(capacity);
-        desc.resize((size_t)capacity*32);
-        const int rc = orbx_extract(mpCtx, image.data, image.cols, image.rows, (size_t)image.step,
-                                    &kps[0], &desc[0], capacity, &n);
-        if(rc == ORBX_OK)
-            break;
-        if(rc == ORBX_E_CAPACITY) { capacity = n + 64; continue; }
+    // One call: upload, every kernel and the download of keypoints, descriptors and (if wanted) all padded pyramid
+    // levels replay as one CUDA graph; `out` points into pinned memory owned by the context (include/orb_b200.h).
+    orbx_frame_out out;
+    const int rc = orbx_extract_frame(mpCtx, image.data, image.cols, image.rows, (size_t)image.step, mbDownloadPyramid ? 1 : 0, &out);
+    if(rc != ORBX_OK)
         throw std::runtime_error(std::string("ORBextractor(B200): ") + orbx_last_error(mpCtx));
-    }
+    const int n = out.n;
 
     if( n == 0 )
         _descriptors.release();
@@ -79,27 +69,31 @@ void ORBextractor::operator()( cv::InputArray _image, cv::InputArray /*_mask*/, 
     {
         _descriptors.create(n, 32, CV_8U);
         cv::Mat descriptors = _descriptors.getMat();
-        for(int i=0; i<n; i++)
-            std::memcpy(descriptors.ptr(i), &desc[(size_t)i*32], 32);
+        if(descriptors.isContinuous())
+            std::memcpy(descriptors.ptr(0), out.desc, (size_t)n*32);
+        else
+            for(int i=0; i<n; i++)
+                std::memcpy(descriptors.ptr(i), out.desc + (size_t)i*32, 32);
     }
 
     _keypoints.clear();
     _keypoints.reserve(n);
     for(int i=0; i<n; i++)
-        _keypoints.push_back(cv::KeyPoint(kps[i].x, kps[i].y, kps[i].size, kps[i].angle, kps[i].response,
-                                          kps[i].octave, kps[i].class_id));
+        _keypoints.push_back(cv::KeyPoint(out.kps[i].x, out.kps[i].y, out.kps[i].size, out.kps[i].angle, out.kps[i].response,
+                                          out.kps[i].octave, out.kps[i].class_id));
 
     if(mbDownloadPyramid)
     {
+        // As in the reference (src/ORBextractor.cc:1157-1178) mvImagePyramid[level] is a view inside its REFLECT_101-padded
+        // buffer.  The buffers live in the context's pinned memory and are overwritten by the next operator() call on this
+        // extractor -- which is when the reference replaces them too.
         const int EDGE_THRESHOLD = 19;
         for(int level=0; level<nlevels; ++level)
         {
-            int w=0, h=0;
-            orbx_pyramid_level(mpCtx, 0, level, 1, NULL, 0, &w, &h);
-            cv::Mat temp(h, w, CV_8UC1);
-            if(orbx_pyramid_level(mpCtx, 0, level, 1, temp.data, (size_t)temp.step, NULL, NULL) != ORBX_OK)
-                throw std::runtime_error(std::string("ORBextractor(B200): ") + orbx_last_error(mpCtx));
-            mvImagePyramid[level] = temp(cv::Rect(EDGE_THRESHOLD, EDGE_THRESHOLD, w-2*EDGE_THRESHOLD, h-2*EDGE_THRESHOLD));
+            const int w = out.level_w[level], h = out.level_h[level];
+            unsigned char* padded = const_cast<unsigned char*>(out.level[level]) - (size_t)EDGE_THRESHOLD*out.level_pitch[level] - EDGE_THRESHOLD;
+            cv::Mat temp(h + 2*EDGE_THRESHOLD, w + 2*EDGE_THRESHOLD, CV_8UC1, padded, out.level_pitch[level]);
+            mvImagePyramid[level] = temp(cv::Rect(EDGE_THRESHOLD, EDGE_THRESHOLD, w, h));
         }
     }
 }

@@ -4,6 +4,7 @@
 // for OpenCV in this image (test infrastructure; a SLAM build uses the real OpenCV).
 #include "ORBextractor.h"
 
+#include <chrono>
 #include <cstring>
 
 struct Kp { float x, y, size, angle, response; int octave, class_id; };
@@ -43,6 +44,23 @@ int dropin_call(void* h, const unsigned char* img, int w, int hgt, size_t step, 
         std::memcpy(desc + (size_t)i * 32, descriptors.ptr(i), 32);
     }
     return n;
+}
+
+// Wall-clock milliseconds per (*extractor)(image, Mat(), keypoints, descriptors) call, measured inside C++ (no ctypes in
+// the loop): what Frame::ExtractORB costs, mvImagePyramid included when the download is on.
+double dropin_time_ms(void* h, const unsigned char* img, int w, int hgt, size_t step, int reps, int with_pyramid)
+{
+    ORB_SLAM2::ORBextractor* e = static_cast<ORB_SLAM2::ORBextractor*>(h);
+    e->SetPyramidDownload(with_pyramid != 0);
+    cv::Mat image(hgt, w, CV_8UC1, (void*)img, step);
+    std::vector<cv::KeyPoint> keys;
+    cv::Mat descriptors;
+    for (int i = 0; i < 5; ++i) (*e)(image, cv::Mat(), keys, descriptors);
+    const std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    for (int i = 0; i < reps; ++i) (*e)(image, cv::Mat(), keys, descriptors);
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() / reps;
+    e->SetPyramidDownload(true);
+    return keys.empty() ? -1.0 : ms;
 }
 
 // mvImagePyramid[level]: ROI size and, like Frame.cc does, pixels addressed relative to the ROI (the
