@@ -902,6 +902,34 @@ def measure_workload(workload, batch_total, scaling, rank, world, local_rank, di
     return res
 
 
+def dropin_latency(image, nf):
+    """Milliseconds per call of the C++ drop-in class ORB_SLAM2::ORBextractor (host/ORBextractor.{h,cc}) timed INSIDE C++
+    by tests/cpp/dropin_harness.cc, i.e. what Frame::ExtractORB (src/Frame.cc:262-268) costs, mvImagePyramid included.
+    The class needs OpenCV's cv::Mat / cv::KeyPoint types to compile; this image has no OpenCV C++, so the harness is
+    built against the container-only stand-in the tests use (oracle/cvshim: types, no arithmetic on this path)."""
+    cpp = os.path.join(ROOT, "tests", "cpp")
+    try:
+        if subprocess.run(["make", "-C", cpp, "all"], capture_output=True).returncode != 0:
+            return {}
+        D = C.CDLL(os.path.join(cpp, "_build", "libdropin.so"))
+        D.dropin_create.restype = C.c_void_p
+        D.dropin_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+        D.dropin_destroy.argtypes = [C.c_void_p]
+        D.dropin_time_ms.restype = C.c_double
+        D.dropin_time_ms.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int]
+        hd = D.dropin_create(nf, SCALE, LEVELS, INI_TH, MIN_TH)
+        img = np.array(image)                          # pageable memory, as a cv::Mat from an image decoder would be
+        h, w = img.shape
+        out = {"dropin_operator_ms": D.dropin_time_ms(hd, img.ctypes.data, w, h, img.strides[0], 50, 1),
+               "dropin_operator_no_pyramid_ms": D.dropin_time_ms(hd, img.ctypes.data, w, h, img.strides[0], 50, 0),
+               "dropin_note": "ORB_SLAM2::ORBextractor::operator() of host/ORBextractor.cc timed inside C++ (tests/cpp/dropin_harness.cc), pageable image, "
+                              "keypoint vector + descriptor Mat + all 8 REFLECT_101-padded mvImagePyramid levels filled"}
+        D.dropin_destroy(hd)
+        return out
+    except Exception as e:                             # no compiler on the box: the ctypes numbers above still stand
+        return {"dropin_note": f"not measured: {e}"}
+
+
 def pin_rank_to_cores(local_rank, world):
     """One rank per GPU on one host: give every rank its own slice of the host cores so the staging threads of
     eight ranks do not migrate over each other (all GPUs of these boxes hang off NUMA node 0)."""
@@ -982,6 +1010,7 @@ def run_ours(args, rank, world, local_rank):
             for _ in range(30):
                 ex.extract_stereo_batch(one, CAM["bf"], CAM["fx"])
             latency["stereo_pair_ms"] = 1e3 * (time.perf_counter() - t0) / 30
+        latency.update(dropin_latency(one[0], nf))
     hamming = bench_hamming(dev, local_rank) if world == 1 else None
     window = mappoint = None
     if world == 1 and stereo:

@@ -371,6 +371,16 @@ int orbm_project_points(const float* Tcw, const float* K, float bf, float min_x,
                         float* view_cos, int device);
 int orbm_distinctive_descriptor(const uint8_t* desc, int n, const uint8_t* bad, int* best_idx, int* best_median, int device);
 
+/* ---- test taps -------------------------------------------------------------------- */
+/* ORBmatcher::ComputeThreeMaxima (src/ORBmatcher.cc:1663-1707) as the matcher kernels run it: sizes [n][30] bin
+ * counts (host) -> ind [n][3]. */
+int orbm_debug_three_maxima(const int* sizes, int n, int* ind, int device);
+/* Frame::GetFeaturesInArea (src/Frame.cc:348-409) on the device grid: for query q the keypoint indices inside the
+ * window (xyr[3q], xyr[3q+1]) +- xyr[3q+2] at levels [min_level[q], max_level[q]] (-1 = open), IN THE REFERENCE'S ORDER
+ * (grid column, grid row, insertion), idx_out [nq][cap], count_out [nq].  Host pointers. */
+int orbm_debug_features_in_area(const orbm_frame* F, int nq, const float* xyr, const int* min_level, const int* max_level,
+                                int cap, int* idx_out, int* count_out, int device);
+
 #ifdef __cplusplus
 }
 #endif

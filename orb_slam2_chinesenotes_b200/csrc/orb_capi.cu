@@ -17,6 +17,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>   // header-only; a no-op unless a profiler is attached
+
 #include "orb_device.cuh"
 #include "orb_launch.h"
 #include "orb_stereo.h"
@@ -258,13 +260,17 @@ cudaEvent_t get_event(orbx_ctx* c)
     return e;
 }
 
+// One stage of a chunk: an NVTX range around its launches (shows up in Nsight Systems / ncu --nvtx; free when no tool
+// is attached) and, while stage timing is on, a CUDA event pair around them.
+const char* const kStageName[ORBX_STAGE_COUNT] = { "orb:pyramid", "orb:fast", "orb:blur", "orb:quadtree", "orb:describe", "orb:stereo" };
 struct StageScope {
     orbx_ctx* c; StageTimer t; bool on; cudaStream_t st;
     StageScope(orbx_ctx* ctx, int stage, cudaStream_t stream) : c(ctx), on(ctx->profile), st(stream)
     {
+        nvtxRangePushA(stage >= 0 && stage < ORBX_STAGE_COUNT ? kStageName[stage] : "orb");
         if (on) { t.stage = stage; t.ev[0] = get_event(c); t.ev[1] = get_event(c); cudaEventRecord(t.ev[0], st); }
     }
-    ~StageScope() { if (on) { cudaEventRecord(t.ev[1], st); c->pending.push_back(t); } }
+    ~StageScope() { if (on) { cudaEventRecord(t.ev[1], st); c->pending.push_back(t); } nvtxRangePop(); }
 };
 
 void collect_timers(orbx_ctx* c)
@@ -332,11 +338,11 @@ int enqueue_chunk(orbx_ctx* c, Slot& s, cudaStream_t st, const uint8_t* d_img, s
     } else {
         CU(c, cudaEventRecord(s.pyr_done, st));
         CU(c, cudaStreamWaitEvent(s.aux, s.pyr_done, 0));
-        CU(c, orb_launch_blur(P, io, frames, s.aux));
+        { StageScope t(c, ORBX_STAGE_BLUR, s.aux); CU(c, orb_launch_blur(P, io, frames, s.aux)); }
         CU(c, cudaEventRecord(s.blur_done, s.aux));
         if (!split) {
-            CU(c, orb_launch_fast(P, io, frames, st, &s.fmaps));
-            CU(c, orb_launch_octree(P, io, frames, st));
+            { StageScope t(c, ORBX_STAGE_FAST, st); CU(c, orb_launch_fast(P, io, frames, st, &s.fmaps)); }
+            { StageScope t(c, ORBX_STAGE_OCTREE, st); CU(c, orb_launch_octree(P, io, frames, st)); }
         }
         CU(c, cudaStreamWaitEvent(st, s.blur_done, 0));
         if (split) for (int l = 0; l < P.nlevels; ++l) CU(c, cudaStreamWaitEvent(st, s.lvl_done[l], 0));

@@ -36,7 +36,7 @@
 #define GRID_CELLS (GRID_COLS * GRID_ROWS)
 #define TH_HIGH 100     // src/ORBmatcher.cc:37
 #define TH_LOW 50       // :38
-#define HISTO_LENGTH 30 // :39
+#include "orb_match_common.cuh"   // HISTO_LENGTH, orb_three_maxima
 #define MAX_KP 8192     // keypoints per frame the grid kernel sorts in shared memory
 
 // ------------------------------------------------------------------------------ brute force
@@ -268,19 +268,13 @@ __device__ __forceinline__ void warp_top2(const uint32_t* lst, const int n, cons
     }
 }
 
-// ComputeThreeMaxima, src/ORBmatcher.cc:1663-1707 (every lane computes the same result)
-__device__ __forceinline__ void three_maxima(const int* sizes, int& ind1, int& ind2, int& ind3)
+__global__ void k_debug_three_maxima(const int* __restrict__ sizes, const int n, int* __restrict__ ind)
 {
-    int max1 = 0, max2 = 0, max3 = 0;
-    ind1 = ind2 = ind3 = -1;
-    for (int i = 0; i < HISTO_LENGTH; ++i) {
-        const int s = sizes[i];
-        if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
-        else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
-        else if (s > max3) { max3 = s; ind3 = i; }
-    }
-    if ((float)max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
-    else if ((float)max3 < 0.1f * (float)max1) ind3 = -1;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int a, b, c;
+    orb_three_maxima(sizes + (size_t)i * HISTO_LENGTH, a, b, c);
+    ind[3 * i] = a; ind[3 * i + 1] = b; ind[3 * i + 2] = c;
 }
 
 // rotation-histogram bin, src/ORBmatcher.cc:263-268 (factor = 1.0f/HISTO_LENGTH, as in the reference)
@@ -361,7 +355,7 @@ __global__ void __launch_bounds__(32) k_resolve_frame(const DevFrame F, const in
     }
     if (check_ori) {
         int i1, i2, i3;
-        three_maxima(sizes, i1, i2, i3);
+        orb_three_maxima(sizes, i1, i2, i3);
         // every entry of a rejected bin clears its keypoint and decrements, duplicates included (:286-296)
         int dec = 0;
         for (int e = lane; e < nh; e += 32) {
@@ -990,6 +984,58 @@ int orbm_distinctive_descriptor(const uint8_t* desc, int n, const uint8_t* bad, 
     *best_idx = r[0];
     if (best_median) *best_median = r[1];
     return r[0] == -2 ? ORBX_E_ARG : ORBX_OK;
+}
+
+
+// ---- test taps (tests/test_match_gpu.py): the pieces of the matchers that otherwise only show through match indices
+int orbm_debug_three_maxima(const int* sizes, int n, int* ind, int device)
+{
+    if (!sizes || !ind || n < 0) return ORBX_E_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return ORBX_E_CUDA; }
+    if (n == 0) return ORBX_OK;
+    Scratch S;
+    const int* d_sizes = S.up(sizes, (size_t)n * HISTO_LENGTH);
+    int* d_ind = (int*)S.alloc(sizeof(int) * 3 * (size_t)n);
+    if (!S.ok || !S.flush()) return ORBX_E_CUDA;
+    k_debug_three_maxima<<<(n + 127) / 128, 128>>>(d_sizes, n, d_ind);
+    CKM(cudaGetLastError());
+    CKM(cudaMemcpy(ind, d_ind, sizeof(int) * 3 * (size_t)n, cudaMemcpyDeviceToHost));
+    return ORBX_OK;
+}
+
+int orbm_debug_features_in_area(const orbm_frame* F, int nq, const float* xyr, const int* min_level, const int* max_level,
+                                int cap, int* idx_out, int* count_out, int device)
+{
+    if (!F || nq < 0 || cap <= 0 || !idx_out || !count_out || (nq > 0 && (!xyr || !min_level || !max_level))) return ORBX_E_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return ORBX_E_CUDA; }
+    for (int q = 0; q < nq; ++q) count_out[q] = 0;
+    if (nq == 0 || F->n == 0) return ORBX_OK;
+    Scratch S;
+    DevFrame D;
+    if (!make_frame(S, F, &D)) return S.ok ? ORBX_E_ARG : ORBX_E_CUDA;
+    std::vector<WinQuery> hq((size_t)nq);
+    for (int q = 0; q < nq; ++q) {
+        WinQuery w;
+        w.u = xyr[3 * q]; w.v = xyr[3 * q + 1]; w.r = xyr[3 * q + 2];
+        w.min_level = min_level[q]; w.max_level = max_level[q]; w.ur = 0.f; w.er_max = 0.f; w.valid = 1;
+        hq[(size_t)q] = w;
+    }
+    std::vector<uint32_t> zero((size_t)nq * 8, 0u);
+    const WinQuery* dq = S.up(hq.data(), (size_t)nq);
+    const uint32_t* dd = S.up(zero.data(), (size_t)nq * 8);
+    uint32_t* list = (uint32_t*)S.alloc(sizeof(uint32_t) * (size_t)nq * cap);
+    int* count = (int*)S.alloc(sizeof(int) * (size_t)nq);
+    if (!S.ok || !S.flush()) return ORBX_E_CUDA;
+    int sn = 32; while (sn < D.n) sn <<= 1;
+    k_grid_build<<<1, 1024, sizeof(uint32_t) * (size_t)sn>>>(D);
+    k_window_candidates<<<(nq + 7) / 8, 256>>>(D, dq, dd, nq, list, count, cap);
+    CKM(cudaGetLastError());
+    std::vector<uint32_t> hl((size_t)nq * cap);
+    CKM(cudaMemcpy(hl.data(), list, sizeof(uint32_t) * hl.size(), cudaMemcpyDeviceToHost));
+    CKM(cudaMemcpy(count_out, count, sizeof(int) * (size_t)nq, cudaMemcpyDeviceToHost));
+    for (int q = 0; q < nq; ++q)
+        for (int k = 0; k < count_out[q] && k < cap; ++k) idx_out[(size_t)q * cap + k] = (int)(hl[(size_t)q * cap + k] & 0xffffu);
+    return ORBX_OK;
 }
 
 } // extern "C"

@@ -39,7 +39,7 @@
 #define GRID_ROWS 48    // FRAME_GRID_ROWS, include/Frame.h:37
 #define GRID_CELLS (GRID_COLS * GRID_ROWS)
 #define TH_HIGH 100     // src/ORBmatcher.cc:37
-#define HISTO_LENGTH 30 // :39
+#include "orb_match_common.cuh"   // HISTO_LENGTH, orb_three_maxima
 #define MB_MAX_KP 8192
 #define MB_MAX_LEVELS 32
 #ifndef MB_NT
@@ -402,15 +402,8 @@ __global__ void __launch_bounds__(MB_NT) k_match_fixpoint(const __grid_constant_
     __syncthreads();
     if (MODE == MODE_BEST && P.check_ori) {
         if (tid == 0) {   // ComputeThreeMaxima, src/ORBmatcher.cc:1663-1707
-            int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
-            for (int i = 0; i < HISTO_LENGTH; ++i) {
-                const int s = s_sizes[i];
-                if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
-                else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
-                else if (s > max3) { max3 = s; ind3 = i; }
-            }
-            if ((float)max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
-            else if ((float)max3 < 0.1f * (float)max1) ind3 = -1;
+            int ind1, ind2, ind3;
+            orb_three_maxima(s_sizes, ind1, ind2, ind3);
             s_ind[0] = ind1; s_ind[1] = ind2; s_ind[2] = ind3;
         }
         __syncthreads();
@@ -613,15 +606,8 @@ __global__ void __launch_bounds__(MB_NT) k_init_fixpoint(const __grid_constant__
     for (int j = tid; j < nvalid; j += MB_NT) owned += cnt[j] >= 0 ? 1 : 0;
     if (owned) atomicAdd(&s_cnt[0], owned);
     if (P.check_ori && tid == 0) {   // ComputeThreeMaxima, src/ORBmatcher.cc:1663-1707
-        int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
-        for (int i = 0; i < HISTO_LENGTH; ++i) {
-            const int sz = s_sizes[i];
-            if (sz > max1) { max3 = max2; max2 = max1; max1 = sz; ind3 = ind2; ind2 = ind1; ind1 = i; }
-            else if (sz > max2) { max3 = max2; max2 = sz; ind3 = ind2; ind2 = i; }
-            else if (sz > max3) { max3 = sz; ind3 = i; }
-        }
-        if ((float)max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
-        else if ((float)max3 < 0.1f * (float)max1) ind3 = -1;
+        int ind1, ind2, ind3;
+        orb_three_maxima(s_sizes, ind1, ind2, ind3);
         s_ind[0] = ind1; s_ind[1] = ind2; s_ind[2] = ind3;
     }
     __syncthreads();

@@ -17,7 +17,7 @@
 #include "../../include/orb_b200.h"
 
 #define TH_LOW 50        // src/ORBmatcher.cc:38
-#define HISTO_LENGTH 30  // :39
+#include "orb_match_common.cuh"   // HISTO_LENGTH, orb_three_maxima
 #define BW_NT 512
 #ifndef BW_G
 #define BW_G 4
@@ -198,15 +198,8 @@ __global__ void __launch_bounds__(BW_NT) k_bow_fixpoint(const __grid_constant__ 
     if (mine) atomicAdd(&s_cnt[0], mine);
     __syncthreads();
     if (P.check_ori && tid == 0) {   // ComputeThreeMaxima, src/ORBmatcher.cc:1663-1707
-        int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
-        for (int i = 0; i < HISTO_LENGTH; ++i) {
-            const int s = s_sizes[i];
-            if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
-            else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
-            else if (s > max3) { max3 = s; ind3 = i; }
-        }
-        if ((float)max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
-        else if ((float)max3 < 0.1f * (float)max1) ind3 = -1;
+        int ind1, ind2, ind3;
+            orb_three_maxima(s_sizes, ind1, ind2, ind3);
         s_ind[0] = ind1; s_ind[1] = ind2; s_ind[2] = ind3;
     }
     __syncthreads();

@@ -339,3 +339,68 @@ def test_very_large_best_only_query_set_takes_the_list_path(scene):
                                    p(ref_assign), 100, 1)
     g_nm, g_assign = ob.window_search_best(ob.FrameView(k, d, BOUNDS), uvr, minl, maxl, qd, 100, True, q_angle=q_angle, q_obs=q_obs)
     assert g_nm == nm and nm > 100 and (g_assign == ref_assign).all()
+
+
+def test_three_maxima_on_random_histograms():
+    """a16, ORBmatcher::ComputeThreeMaxima (src/ORBmatcher.cc:1663-1707) as the matcher kernels run it (one shared device
+    function): random bin counts incl. ties, empty histograms and the 10 % cut, against a direct restatement."""
+    import ctypes as C
+    rng = np.random.default_rng(16)
+    n = 4000
+    sizes = rng.integers(0, 40, (n, 30)).astype(np.int32)
+    sizes[:200] = rng.integers(0, 3, (200, 30))                  # many ties
+    sizes[200:300] = 0                                          # empty
+    sizes[300:600] = (rng.random((300, 30)) < 0.1) * rng.integers(1, 200, (300, 30))   # sparse: the 10 % rule bites
+    sizes[600:700, :] = 7                                       # all equal
+    ind = np.zeros((n, 3), np.int32)
+    L = ob.lib()
+    L.orbm_debug_three_maxima.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    assert L.orbm_debug_three_maxima(sizes.ctypes.data, n, ind.ctypes.data, 0) == 0
+
+    def three(s):
+        m1 = m2 = m3 = 0
+        i1 = i2 = i3 = -1
+        for i, v in enumerate(s):
+            if v > m1:
+                m3, m2, m1, i3, i2, i1 = m2, m1, v, i2, i1, i
+            elif v > m2:
+                m3, m2, i3, i2 = m2, v, i2, i
+            elif v > m3:
+                m3, i3 = v, i
+        if np.float32(m2) < np.float32(0.1) * np.float32(m1):
+            i2 = i3 = -1
+        elif np.float32(m3) < np.float32(0.1) * np.float32(m1):
+            i3 = -1
+        return i1, i2, i3
+
+    want = np.array([three(s.tolist()) for s in sizes], np.int32)
+    assert (ind == want).all()
+
+
+def test_device_grid_returns_candidates_in_reference_order(scene):
+    """a17, Frame::AssignFeaturesToGrid + GetFeaturesInArea (src/Frame.cc:243-259, 348-422) on the device grid: the
+    candidate LIST of a window -- not just the match it leads to -- equals the oracle's, element by element (grid
+    column, grid row, insertion order), with and without level bounds, incl. windows hanging over the image border."""
+    import ctypes as C
+    kps, desc = scene["k2"], scene["d2"]
+    rng = np.random.default_rng(17)
+    nq = 600
+    xyr = np.stack([rng.uniform(-30, W + 30, nq), rng.uniform(-30, H + 30, nq), rng.choice([3.0, 7.5, 15.0, 40.0, 100.0], nq)], 1).astype(np.float32)
+    lo = rng.choice([-1, 0, 1, 3], nq).astype(np.int32)
+    hi = np.where(rng.random(nq) < 0.5, -1, lo + rng.integers(0, 4, nq)).astype(np.int32)
+    hi = np.where((lo < 0) & (hi >= 0), hi + 1, hi).astype(np.int32)
+    cap = len(kps)
+    idx = np.zeros((nq, cap), np.int32)
+    cnt = np.zeros(nq, np.int32)
+    F = ob.FrameView(kps, desc, BOUNDS)
+    L = ob.lib()
+    L.orbm_debug_features_in_area.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    st = F.struct()
+    assert L.orbm_debug_features_in_area(C.byref(st), nq, xyr.ctypes.data, lo.ctypes.data, hi.ctypes.data, cap, idx.ctypes.data, cnt.ctypes.data, 0) == 0
+    M = Matcher("oracle")
+    nonempty = 0
+    for q in range(nq):
+        want = M.features_in_area(kps, scene["scale"], BOUNDS, float(xyr[q, 0]), float(xyr[q, 1]), float(xyr[q, 2]), int(lo[q]), int(hi[q]))
+        assert cnt[q] == len(want) and (idx[q, :cnt[q]] == want).all(), q
+        nonempty += len(want) > 1
+    assert nonempty > 200
