@@ -373,6 +373,11 @@ __device__ __forceinline__ void orb_sincosf(const float y, float* sn, float* cs)
 #endif
 // One warp per output keypoint.  Lanes are the 31 columns of the orientation patch, then the
 // 32 descriptor bytes (16 rotated taps each).
+// Measured dead end (round 2): issuing fastAtan2 + the FP64 sincos once per keypoint instead of in all 32 lanes -- a
+// block takes 8..32 keypoints in three phases (moments per warp / one LANE per keypoint for angle, sin, cos / descriptor
+// per warp, two block barriers) -- removes ~70 of ~420 instructions per keypoint but measures 1.17..1.45 ms per 512
+// frames against 0.99 ms for this version (72 instead of 39 registers, phases that wait for each other): the kernel
+// follows the uncoalesced tap gathers, not the issue rate.
 __global__ void __launch_bounds__(DESC_NT) k_describe(const __grid_constant__ OrbPlan plan, const OrbBatch io)
 {
     const int frame = blockIdx.y, lane = threadIdx.x & 31;
