@@ -67,8 +67,7 @@ int orbx_extract(orbx_ctx* ctx, const uint8_t* img, int w, int h, size_t pitch,
 /* What Frame::ExtractORB (src/Frame.cc:262-268) needs from ONE call, at the lowest latency: operator() for one host
  * image plus, if with_pyramid, mvImagePyramid (include/ORBextractor.h:86: every level as a view inside its
  * REFLECT_101-padded buffer, src/ORBextractor.cc:1157-1178, which Frame::ComputeStereoMatches reads, src/Frame.cc:520,
- * 611-633).  The image goes up through a pinned staging buffer (or straight from the caller's buffer when that is
- * pinned), the whole pipeline replays as one CUDA graph, and keypoints, descriptors and all padded levels come back
+ * 611-633).  The image goes up through a pinned staging buffer, the whole pipeline replays as one CUDA graph, and keypoints, descriptors and all padded levels come back
  * with it into context-owned pinned host memory: everything in `out` points INTO the context and stays valid until
  * the next call on it, like the reference's mvImagePyramid.  orbx_extract() on a single host image takes the same
  * path and copies the n records out. */

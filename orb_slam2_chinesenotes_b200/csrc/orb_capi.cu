@@ -97,8 +97,6 @@ struct FramePath {
     bool stereo = false, pyr = false;
     float bf = 0.f, fx = 0.f;
     cudaStream_t stream = nullptr;
-    cudaGraphNode_t in_node = nullptr;     // the host->device copy of the frames
-    const void* in_src = nullptr;          // its current source: h_in, or the caller's own buffer when that is pinned
     PinBuf h_in, h_kps, h_desc, h_n, h_ur, h_dep, h_ns, h_pad;
     DevBuf d_in, d_kps, d_desc, d_n, d_ur, d_dep, d_ns, d_pad;
     OrbBorderJob job;
@@ -486,13 +484,6 @@ int run_batch(orbx_ctx* c, const uint8_t* imgs, size_t frame_stride, int batch, 
 }
 
 // ---- single-call path ------------------------------------------------------------------------------------------
-bool is_pinned_host(const void* p)
-{
-    cudaPointerAttributes a;
-    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
-    return a.type == cudaMemoryTypeHost;
-}
-
 // Capture the graph of one call: frames (1, or 2 = a stereo pair) of w x h with row pitch `pitch`.
 int frame_path_build(orbx_ctx* c, int w, int h, int pitch, int frames, const StereoReq* sr, bool pyr)
 {
@@ -566,23 +557,11 @@ int frame_path_build(orbx_ctx* c, int w, int h, int pitch, int frames, const Ste
         cudaGetLastError();
         return fail(c, ORBX_E_CUDA, "single-call graph capture failed (%s)", cudaGetErrorString(ec));
     }
-    // the node that uploads the frames: its source is re-pointed at the caller's buffer when that is pinned
-    F.in_node = nullptr;
-    size_t nn = 0;
-    cudaGraphGetNodes(graph, nullptr, &nn);
-    std::vector<cudaGraphNode_t> nodes(nn);
-    cudaGraphGetNodes(graph, nodes.data(), &nn);
-    for (cudaGraphNode_t nd : nodes) {
-        cudaGraphNodeType t;
-        if (cudaGraphNodeGetType(nd, &t) != cudaSuccess || t != cudaGraphNodeTypeMemcpy) continue;
-        cudaMemcpy3DParms mp;
-        if (cudaGraphMemcpyNodeGetParams(nd, &mp) == cudaSuccess && mp.dstPtr.ptr == F.d_in.p) { F.in_node = nd; break; }
-    }
     const cudaError_t ei = cudaGraphInstantiate(&F.exec, graph, 0);
     cudaGraphDestroy(graph);
     if (ei != cudaSuccess) { F.exec = nullptr; return fail(c, ORBX_E_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ei)); }
     F.w = w; F.h = h; F.pitch = pitch; F.frames = frames; F.cap = cap; F.nlevels = P.nlevels; F.stereo = sr != nullptr; F.pyr = pyr;
-    F.bf = sr ? sr->bf : 0.f; F.fx = sr ? sr->fx : 0.f; F.stream = st; F.in_src = F.h_in.p;
+    F.bf = sr ? sr->bf : 0.f; F.fx = sr ? sr->fx : 0.f; F.stream = st;
     return ORBX_OK;
 }
 
@@ -599,15 +578,12 @@ int frame_path_run(orbx_ctx* c, const uint8_t* imgs, size_t frame_stride, int fr
         rc = frame_path_build(c, w, h, (int)pitch, frames, sr, pyr || F.pyr);
         if (rc) return rc;
     }
-    const size_t fbytes = pitch * (size_t)h, in_bytes = (size_t)frames * fbytes;
-    const void* src = F.h_in.p;
+    const size_t fbytes = pitch * (size_t)h;
+    // The frames always go through the path's own pinned buffer (13 us for a 1241x376 frame).  Re-pointing the graph's
+    // upload node at a caller buffer that is itself pinned was tried: cudaGraphExecMemcpyNodeSetParams1D rejects a
+    // source registered by someone else (torch's pinned allocator) with cudaErrorInvalidValue.
     const std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
-    if (F.in_node && (frames == 1 || frame_stride == fbytes) && is_pinned_host(imgs) && is_pinned_host(imgs + in_bytes - 1)) src = imgs;
-    else for (int f = 0; f < frames; ++f) memcpy((uint8_t*)F.h_in.p + (size_t)f * fbytes, imgs + (size_t)f * frame_stride, pitch * (size_t)(h - 1) + (size_t)w);
-    if (src != F.in_src) {
-        CU(c, cudaGraphExecMemcpyNodeSetParams1D(F.exec, F.in_node, F.d_in.p, src, in_bytes, cudaMemcpyHostToDevice));
-        F.in_src = src;
-    }
+    for (int f = 0; f < frames; ++f) memcpy((uint8_t*)F.h_in.p + (size_t)f * fbytes, imgs + (size_t)f * frame_stride, pitch * (size_t)(h - 1) + (size_t)w);
     const std::chrono::steady_clock::time_point t1 = std::chrono::steady_clock::now();
     CU(c, cudaGraphLaunch(F.exec, c->stream));
     const std::chrono::steady_clock::time_point t2 = std::chrono::steady_clock::now();

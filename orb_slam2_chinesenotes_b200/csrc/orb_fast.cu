@@ -12,10 +12,10 @@
 //     own mbarrier.  A lane owns the pixel pair (2p, 2p+1) of the band, whatever cell each pixel lies in.
 //   * DATA PATH: the TMA unit.  Where the level's layout is 16-byte aligned (every pyramid level; level 0 when the
 //     caller's base, pitch and frame stride allow) ONE tensor-map copy (cp.async.bulk.tensor.3d: x, y, frame)
-//     brings the whole chunk, starting at the 16-byte aligned column at or below its first pixel; otherwise lane r of the warp issues one bulk copy
-//     (cp.async.bulk) for image row r from the 16-byte aligned address at or below its first pixel, so any pitch
-//     works (level 0 is the caller's image, untouched).  The warp's mbarrier counts the bytes; the copy of chunk
-//     k+1 is in flight while chunk k is scored.
+//     brings the whole chunk, starting at the 16-byte aligned column at or below its first pixel, and the warp's
+//     mbarrier counts the bytes; otherwise (level 0 of a caller with an odd pitch, where every row starts at another
+//     offset inside its 16 bytes, so that no TMA form fits) lane j copies the aligned word j of every row with
+//     cp.async.  Either way the copy of chunk k+1 is in flight while chunk k is scored.
 //   * WIDENING on the LSU and FMA pipes: the raw bytes are re-read one by one (LDS.U8 has no alignment rule, so
 //     no funnel shifts) and paired with one IMAD each into the two 16-bit copies of the tile -- copy A holds the
 //     pixel pairs that start on an even tile column, copy B those that start on an odd one -- so every ring
@@ -65,6 +65,9 @@
 #ifndef ORB_FAST_FULLCOL
 #define ORB_FAST_FULLCOL 256  // frames per launch from which a warp walks a whole band column
 #endif
+#ifndef ORB_FAST_UNROLL
+#define ORB_FAST_UNROLL 2     // row pairs per trip of the scoring loop (per 512 frames: 1 pair 1.963 ms, 2 pairs 1.931)
+#endif
 #ifndef ORB_FAST_MIDROWS
 #define ORB_FAST_MIDROWS 2    // cell rows per warp for 16 .. ORB_FAST_FULLCOL-1 frames (64 frames: 2 rows 0.27 ms, 4 rows 0.29, whole columns 0.35)
 #endif
@@ -72,6 +75,7 @@
 #define ORB_FAST_MINBLK 16    // resident blocks per SM the register allocation must allow
 #endif
 
+constexpr int kFastUnroll = ORB_FAST_UNROLL;
 constexpr int kR = ORB_FAST_R;
 constexpr int kTileRows = kR + 6;
 constexpr int kCopyW = 36;                 // 32-bit words per copy of a tile row (72 pixels)
@@ -159,12 +163,6 @@ __device__ __forceinline__ void mbar_wait(const uint32_t bar, const uint32_t par
         "@!p bra W_%=;\n\t}"
         ::"r"(bar), "r"(parity) : "memory");
 }
-__device__ __forceinline__ void bulk_g2s(const uint32_t dst, const void* src, const uint32_t bytes, const uint32_t bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-
 __device__ __forceinline__ void tensor_g2s(const uint32_t dst, const void* map, const int x, const int y, const int z, const uint32_t bar)
 {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
@@ -226,7 +224,6 @@ __global__ void __launch_bounds__(kNT, ORB_FAST_MINBLK) k_fast_bands(const __gri
     const int X0 = cj0 * wc;                                           // border-frame x of the band's first cell image
     // evaluated columns of the band: cells are contiguous, only the last cell of a level can be narrower
     const int tw = min(ncb * wc, maxBX - 6 - (ORB_BORDER0 + X0));
-    const int npx = tw + 6;                                            // tile columns that must be valid
     int pitch;
     const uint8_t* src = orb_level_ptr(plan, io, frame, l, &pitch);
     src += ORB_BORDER0 + X0;                                           // level address of tile column 0, row 0
@@ -255,7 +252,7 @@ __global__ void __launch_bounds__(kNT, ORB_FAST_MINBLK) k_fast_bands(const __gri
                                                      // even ring offsets: words po[kCopyW .. kCopyW+2] = dx -2, 0, +2
     // widening: lane = (sub-row, 8-column group); 27 lanes work on 3 tile rows per pass
     const int wsub = lane / 9, wk = lane - 9 * wsub;
-    const uint32_t pitch15 = tensor ? 0u : (uint32_t)pitch & 15u;
+    const uint32_t pitch15 = tensor ? 0u : (uint32_t)pitch & 3u;   // how the offset of a row inside its aligned word moves from row to row
 
     if (lane == 0) mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -274,19 +271,20 @@ __global__ void __launch_bounds__(kNT, ORB_FAST_MINBLK) k_fast_bands(const __gri
             }
             return;
         }
-        uint32_t bytes = 0;
-        const uint8_t* q = nullptr;
-        if (lane < trows) {
-            const uint8_t* rowp = src + (size_t)(y + lane) * pitch;
-            const uint32_t s = (uint32_t)((uintptr_t)rowp & 15u);
-            q = rowp - s;
-            bytes = (s + (uint32_t)npx + 15u) & ~15u;
+        // Layouts that are not 16-byte aligned (level 0 of a caller with an odd pitch): no TMA form fits, because every
+        // row starts at a different offset inside its 16 bytes.  Lane j copies the aligned 32-bit word j of every row
+        // with cp.async (19 words cover the 3 + 70 + 3 bytes a row can need); the widening reads from byte (row & 3).
+        // (One bulk copy per row, issued by lane r, was the first version: ptxas serialises the 22 per-lane UBLKCP
+        // through an ELECT loop of ~10 instructions each, 7 % of the kernel's instructions.)
+        if (lane < 19) {
+            const uint8_t* rowp = src + (size_t)y * pitch;
+            uint32_t dst = raw_s + 4u * lane;
+            for (int r = 0; r < trows; ++r, rowp += pitch, dst += kRawPitch) {
+                const uint8_t* q = (const uint8_t*)((uintptr_t)rowp & ~(uintptr_t)3) + 4 * lane;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(q) : "memory");
+            }
         }
-        const uint32_t total = __reduce_add_sync(0xffffffffu, bytes);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the raw rows were read through the generic proxy
-        if (lane == 0) mbar_expect_tx(bar, total);
-        __syncwarp();
-        if (lane < trows) bulk_g2s(raw_s + lane * kRawPitch, q, bytes, bar);
+        asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
     // chunk schedule of a cell row: evaluated rows [ya, yb) of the cell; returns false when the cell row is empty
@@ -302,15 +300,15 @@ __global__ void __launch_bounds__(kNT, ORB_FAST_MINBLK) k_fast_bands(const __gri
         if (eh <= 0) break;
         uint32_t u = 0, m = 0, carry = 0;                              // scores of the two rows above; even-row survivors
         uint32_t cntAll = 0, cntA = 0;                                 // survivors / survivors at iniThFAST per column (fp16 counts)
-        uint32_t smask = 0, sbit = 1;                                  // stash slots (index, i.e. row pair + 1) of this lane that hold a survivor
+        uint32_t smask = 0;                                            // one bit per record of this cell row (newest in bit 0): the slot holds a survivor
 
         for (int ya = 0; ya < eh; ya += kR) {
             const int nr = min(eh - ya, kR), trows = nr + 6;
-            mbar_wait(bar, parity);
-            parity ^= 1u;
+            if (tensor) { mbar_wait(bar, parity); parity ^= 1u; }
+            else { asm volatile("cp.async.wait_group 0;" ::: "memory"); __syncwarp(); }
             // ---- widen: raw bytes -> copies A and B
             {
-                const uint32_t s0 = tensor ? (uint32_t)(ORB_BORDER0 + X0 - tx0) : (uint32_t)((uintptr_t)(src + (size_t)(y0 + ya) * pitch) & 15u);
+                const uint32_t s0 = tensor ? (uint32_t)(ORB_BORDER0 + X0 - tx0) : (uint32_t)((uintptr_t)(src + (size_t)(y0 + ya) * pitch) & 3u);
                 if (wsub < 3) {
                     auto widen_row = [&](const unsigned char* rq, uint32_t* dst) {
                         uint32_t b[9];
@@ -331,9 +329,9 @@ __global__ void __launch_bounds__(kNT, ORB_FAST_MINBLK) k_fast_bands(const __gri
                         rp += s0;
                         for (int r = wsub; r < trows; r += 3, rp += 3 * kRawPitch, dst += 3 * kRS) widen_row(rp, dst);
                     } else {
-                        uint32_t s = (s0 + (uint32_t)wsub * pitch15) & 15u;
-                        const uint32_t sstep = (3u * pitch15) & 15u;
-                        for (int r = wsub; r < trows; r += 3, rp += 3 * kRawPitch, dst += 3 * kRS, s = (s + sstep) & 15u) widen_row(rp + s, dst);
+                        uint32_t s = (s0 + (uint32_t)wsub * pitch15) & 3u;
+                        const uint32_t sstep = (3u * pitch15) & 3u;
+                        for (int r = wsub; r < trows; r += 3, rp += 3 * kRawPitch, dst += 3 * kRS, s = (s + sstep) & 3u) widen_row(rp + s, dst);
                     }
                 }
             }
@@ -390,11 +388,10 @@ __global__ void __launch_bounds__(kNT, ORB_FAST_MINBLK) k_fast_bands(const __gri
                 uint32_t w;
                 asm("mad.lo.u32 %0, %1, 256, %2;" : "=r"(w) : "r"(so), "r"(se));
                 *slot = w;
-                if (w) smask |= sbit;
-                sbit += sbit;
+                smask = smask * 2u + min(w, 1u);                       // newest record in bit 0: one VIMNMX + one IMAD
             };
             int r = 0;
-#pragma unroll 1
+#pragma unroll (kFastUnroll)
             for (; r + 2 <= nr; r += 2, st += 32) {
                 const uint32_t* a = po + r * kRS;
                 const uint32_t d0 = score(a, a + kCopyW);
@@ -452,8 +449,9 @@ __global__ void __launch_bounds__(kNT, ORB_FAST_MINBLK) k_fast_bands(const __gri
                     ++wrote;
                 }
             };
+            const int nrec = ((eh + 1) >> 1) + 1;                      // records written: the dummy slot 0 and one per row pair
             while (smask) {
-                const int i = __ffs((int)smask) - 1;
+                const int i = nrec - __ffs((int)smask);                // bit b is the record written b steps before the last
                 smask &= smask - 1;
                 const uint32_t w = stash[32 * i];
                 const uint32_t lo = w & 0xffffu;
