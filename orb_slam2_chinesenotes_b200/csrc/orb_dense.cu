@@ -30,110 +30,151 @@ __device__ __forceinline__ uint32_t dp2a_hi(const uint32_t a, const uint32_t b, 
 // No shared memory and no barriers: a WARP owns a column of 128 destination pixels (lane = 4
 // adjacent pixels) and walks down PYR_TH destination rows.
 //   horizontal pass of ONE source row: the lane's 8 taps lie in 8 consecutive source bytes (scale <= 1.25);
-//           they are fetched as aligned words, funnel-shifted to the lane's first tap, permuted into two
-//           (p0,p0+1,p1,p1+1) byte quads (selectors fixed per lane), and each H is one IDP.2A with the
-//           (a0,a1) pair as the 16-bit operand;
-//   vertical pass: consecutive destination rows share a source row four times out of five, so the two H rows
-//           live in registers and only the new one is computed; (b*h)>>16 is IMAD.HI with b pre-shifted.
+//           they are fetched as aligned words (one source row AHEAD of their use), funnel-shifted to the lane's first
+//           tap, permuted into two (p0,p0+1,p1,p1+1) byte quads (selectors fixed per lane), and each H is one IDP.2A
+//           with the (a0,a1) pair as the 16-bit operand;
+//   vertical pass: the walk goes over SOURCE rows r: H(r) is computed exactly once, and the destination row whose
+//           upper tap is r-1 (at most one, the vertical scale is >= 1) is emitted from H(r-1), H(r) -- no routing of
+//           rows to register slots, one warp-uniform compare per source row.  H is kept as H & ~15 and the row weights
+//           are pre-shifted by 12, so ((H >> 4) * b) >> 16 is one IMAD.HI and the sum of both rows + 2 is two.
 #ifndef PYR_NT
-#define PYR_NT 64        // measured per 1024 frames: 32 threads 1.82 ms, 64 1.60, 128 1.63, 256 2.00
+#define PYR_NT 64
 #endif
-// Measured dead end (round 2): keeping the raw words of the next 2..4 source rows in flight in a register ring (loads issued
-// two to three destination rows ahead of the funnel shift that needs them) costs 16 more registers and the ring's moves:
-// 1.02 / 1.11 / 1.15 ms per 512 frames for 2 / 3 / 4 rows ahead against 0.78 ms for this version, whose loads are hidden
-// by the 36 resident warps per SM instead.
 #define PYR_TW 128
 #define PYR_TH 64
 
-__device__ __forceinline__ uint32_t mad_hi(const uint32_t a, const uint32_t b, const uint32_t c)
+// Everything a launch needs about its level, as plain kernel parameters (constant bank, fixed offsets).
+struct PyrJob {
+    const uint8_t* src; size_t src_stride; int spitch;      // source level: first frame, bytes between frames / rows
+    uint8_t* dst; size_t dst_stride; int dpitch;            // destination level
+    int sw, sh, dw, dh;
+    const int2* xtab;                                       // OrbTap table of the x axis
+    const int4* ytab;                                       // y axis: { source row, c0 << 12, c1 << 12, - }
+    int th, tiles_x, tiles_y;                               // destination rows per warp, warp tiles per frame
+};
+
+#ifndef PYR_STAGES
+#define PYR_STAGES 4     // source rows in flight per warp
+#endif
+__device__ __forceinline__ void cp_async4(const uint32_t dst, const void* src)
 {
-    uint32_t d;
-    asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    return d;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4_zfill(const uint32_t dst, const void* src, const uint32_t src_bytes)   // src_bytes 0: nothing is read
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" :: "r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
 
-__global__ void __launch_bounds__(PYR_NT) k_pyr_resize(const __grid_constant__ OrbPlan plan, const OrbBatch io, const int l, const int th)
+// The row walk of one lane.  The kernel waits on memory latency, not on instruction issue (ncu: long scoreboard), and
+// registers spent on prefetching cost resident warps, so the source rows travel through a small shared-memory ring
+// instead: each lane posts the three aligned words of its own taps with cp.async (LDGSTS) PYR_STAGES rows ahead and reads
+// them back when the row's turn comes -- lane-private slots, no barrier, only cp.async.wait_group.
+// ALLFAST: no lane of the warp touches the right edge of the source.  Otherwise words that start behind the row's last
+// pixel are zero-filled instead of read (they only ever meet the zero weight of the clamped tap).
+template <bool ALLFAST>
+__device__ __forceinline__ void pyr_walk(const PyrJob& J, uint32_t (*ring)[3][32], const int frame, const int lane, const int d0, const int sx0, const bool live,
+                                         const uint32_t (&C)[4], const uint32_t selA, const uint32_t selB, const int yb, const int ye)
+{
+    const int sh = J.sh, spitch = J.spitch, dpitch = J.dpitch;
+    const int room = J.sw - sx0;                                           // source bytes from the lane's first tap to the row end
+    int4 ty = __ldg(&J.ytab[yb]);                                          // taps of the next destination row to emit
+    const int r_last = min(__ldg(&J.ytab[ye - 1]).x + 1, sh - 1);
+    int r = ty.x;
+    const uint8_t* a = J.src + (size_t)frame * J.src_stride + (size_t)r * spitch + sx0;   // the lane's first tap in the row being POSTED
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(&ring[0][0][lane]);
+    auto post = [&](const int slot, const bool on) {                        // one commit group per row, empty once the rows are used up
+        if (on) {
+            const uint8_t* q = (const uint8_t*)((uintptr_t)a & ~(uintptr_t)3);
+            const uint32_t d = ring_s + (uint32_t)slot * (3 * 32 * 4);
+            if (ALLFAST) { cp_async4(d, q); cp_async4(d + 128, q + 4); cp_async4(d + 256, q + 8); }
+            else {
+                const int al = (int)((uintptr_t)a & 3);
+                cp_async4(d, q);
+                cp_async4_zfill(d + 128, q + 4, 4 - al < room ? 4u : 0u);
+                cp_async4_zfill(d + 256, q + 8, 8 - al < room ? 4u : 0u);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        a += spitch;
+    };
+#pragma unroll
+    for (int s = 0; s < PYR_STAGES; ++s) post(s, r + s <= r_last);
+    const uint32_t back = (uint32_t)(PYR_STAGES * spitch);                 // `a` runs this far ahead of the row being consumed
+    uint8_t* __restrict__ out = J.dst + (size_t)frame * J.dst_stride + (size_t)yb * dpitch + d0;
+    int y = yb;
+    // destination row y from the H rows of its two taps; the weights arrive pre-shifted by 12
+    auto emit = [&](const uint32_t* __restrict__ H0, const uint32_t b0, const uint32_t* __restrict__ H1, const uint32_t b1) {
+        uint32_t v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = __umulhi(H0[j], b0) + __umulhi(H1[j], b1) + 2u;
+        // (v0 | v1 << 16) >> 2 leaks two bits of v1 into bits 14-15, which the byte selection below skips
+        const uint32_t px = __byte_perm(__byte_perm(v[0], v[1], 0x5410) >> 2, __byte_perm(v[2], v[3], 0x5410) >> 2, 0x6420);
+        if (live) *(uint32_t*)out = px;
+        out += dpitch;
+        ++y;
+        if (y < ye) ty = __ldg(&J.ytab[y]); else ty.x = -2;               // -2: no source row ends it
+    };
+    // one source row: H(r) into Hn; emits the destination row whose taps are (r-1, r).  Returns true after the last source
+    // row, when the rows of the bottom clamp (upper tap sh-1, lower weight 0) are emitted as well.
+    auto advance = [&](const int slot, uint32_t* __restrict__ Hn, const uint32_t* __restrict__ Ho) -> bool {
+        asm volatile("cp.async.wait_group %0;" :: "n"(PYR_STAGES - 1) : "memory");
+        const uint32_t q0 = ring[slot][0][lane], q1 = ring[slot][1][lane], q2 = ring[slot][2][lane];
+        const uint32_t sft = ((uint32_t)(uintptr_t)a - back) << 3;        // SHF.W takes the amount modulo 32
+        const uint32_t w0 = __funnelshift_r(q0, q1, sft), w1 = __funnelshift_r(q1, q2, sft);
+        const uint32_t A = __byte_perm(w0, w1, selA), B = __byte_perm(w0, w1, selB);
+        post(slot, r + PYR_STAGES <= r_last);                              // after the words have been consumed
+        Hn[0] = dp2a_lo(C[0], A, 0u) & 0xfffffff0u;
+        Hn[1] = dp2a_hi(C[1], A, 0u) & 0xfffffff0u;
+        Hn[2] = dp2a_lo(C[2], B, 0u) & 0xfffffff0u;
+        Hn[3] = dp2a_hi(C[3], B, 0u) & 0xfffffff0u;
+        if (ty.x == r - 1) emit(Ho, (uint32_t)ty.y, Hn, (uint32_t)ty.z);
+        if (r == r_last) {
+            while (y < ye) emit(Hn, (uint32_t)ty.y, Hn, 0u);
+            return true;
+        }
+        ++r;
+        return false;
+    };
+    uint32_t HA[4] = { 0u, 0u, 0u, 0u }, HB[4] = { 0u, 0u, 0u, 0u };
+    static_assert(PYR_STAGES % 2 == 0, "the slot walk below pairs the H registers with the slots");
+    for (;;) {
+#pragma unroll
+        for (int s = 0; s < PYR_STAGES; s += 2) {
+            if (advance(s, HA, HB)) return;
+            if (advance(s + 1, HB, HA)) return;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(PYR_NT) k_pyr_resize(const __grid_constant__ PyrJob J)
 {
     const int frame = blockIdx.z, lane = threadIdx.x & 31;
-    const OrbLevel& D = plan.lv[l];
-    const OrbLevel& S = plan.lv[l - 1];
-    const int tiles_x = (D.w + PYR_TW - 1) / PYR_TW, tiles_y = (D.h + th - 1) / th;
+    const int sw = J.sw, dw = J.dw;
     const int wt = blockIdx.x * (PYR_NT / 32) + (threadIdx.x >> 5);
-    if (wt >= tiles_x * tiles_y) return;
-    const int tyi = __float2int_rz(__fmul_rn((float)wt + 0.5f, __frcp_rn((float)tiles_x)));
-    const int d0 = (wt - tyi * tiles_x) * PYR_TW + 4 * lane;              // first destination column of the lane
-    const int yb = tyi * th, ye = min(yb + th, D.h);
-    int spitch;
-    const uint8_t* __restrict__ src = orb_level_ptr(plan, io, frame, l - 1, &spitch);
-    const int2* __restrict__ xtab = (const int2*)io.taps + D.xtab;
-    const int2* __restrict__ ytab = (const int2*)io.taps + D.ytab;
-    const int sw = S.w, sh = S.h, dw = D.w, dpitch = D.pitch;
-    if (d0 >= dw) return;                                                  // no warp-wide operation below
+    if (wt >= J.tiles_x * J.tiles_y) return;
+    const int tyi = __float2int_rz(__fmul_rn((float)wt + 0.5f, __frcp_rn((float)J.tiles_x)));
+    const int d0 = (wt - tyi * J.tiles_x) * PYR_TW + 4 * lane;            // first destination column of the lane
+    const int yb = tyi * J.th, ye = min(yb + J.th, J.dh);
+    const bool live = d0 < dw;                                             // lanes right of the level walk along on column 0 and store nothing
+    const int dc = live ? d0 : 0;
     // ---- column setup: taps of the 4 destination pixels relative to the first one
     uint32_t C[4];
     int rel[4];
-    const int2 t0 = __ldg(&xtab[min(d0, dw - 1)]);
+    const int2 t0 = __ldg(&J.xtab[min(dc, dw - 1)]);
     const int sx0 = t0.x;
     C[0] = (uint32_t)t0.y; rel[0] = 0;
 #pragma unroll
     for (int j = 1; j < 4; ++j) {
-        const int2 t = __ldg(&xtab[min(d0 + j, dw - 1)]);
+        const int2 t = __ldg(&J.xtab[min(dc + j, dw - 1)]);
         C[j] = (uint32_t)t.y; rel[j] = min(t.x - sx0, 6);
     }
     const uint32_t selA = (uint32_t)(rel[0] | ((rel[0] + 1) << 4) | (rel[1] << 8) | ((rel[1] + 1) << 12));
     const uint32_t selB = (uint32_t)(rel[2] | ((rel[2] + 1) << 4) | (rel[3] << 8) | ((rel[3] + 1) << 12));
-    // bytes sx0 .. sx0+7 are fetched through three aligned words; lanes that would run past the row's last
-    // pixel (right edge) gather clamped bytes instead
+    // bytes sx0 .. sx0+7 are fetched through three aligned words
+    __shared__ uint32_t ring[PYR_NT / 32][PYR_STAGES][3][32];
     const bool fast = sx0 + 12 <= sw;
-    auto hrow = [&](const int r, uint32_t* H) {
-        const uint8_t* row = src + (size_t)r * spitch;
-        uint32_t w0, w1;
-        if (fast) {
-            const uintptr_t a = (uintptr_t)(row + sx0);
-            const uint32_t sft = 8u * (uint32_t)(a & 3);
-            const uint32_t* q = (const uint32_t*)(a & ~(uintptr_t)3);
-            const uint32_t q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
-            w0 = __funnelshift_r(q0, q1, sft);
-            w1 = __funnelshift_r(q1, q2, sft);
-        } else {
-            uint32_t b[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) b[i] = __ldg(row + min(sx0 + i, sw - 1));
-            w0 = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
-            w1 = b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24);
-        }
-        const uint32_t A = __byte_perm(w0, w1, selA), B = __byte_perm(w0, w1, selB);
-        // kept as (H >> 4) << 16, so that ((H >> 4) * b) >> 16 is one IMAD.HI
-        H[0] = (dp2a_lo(C[0], A, 0u) << 12) & 0xffff0000u;
-        H[1] = (dp2a_hi(C[1], A, 0u) << 12) & 0xffff0000u;
-        H[2] = (dp2a_lo(C[2], B, 0u) << 12) & 0xffff0000u;
-        H[3] = (dp2a_hi(C[3], B, 0u) << 12) & 0xffff0000u;
-    };
-    uint8_t* __restrict__ out = io.pyr + (size_t)frame * plan.pyr_bytes + D.img_off + (size_t)yb * dpitch + d0;
-    // Two register slots X, Y hold the H rows rX, rY.  A destination row needs source rows r0 and r1 = r0+1; one
-    // of them is usually already in a slot, so the WEIGHTS are routed to the slots instead of moving the data.
-    // (At the bottom clamp r1 == r0 the weight of r1 is 0, so whatever the other slot holds contributes 0.)
-    uint32_t HX[4], HY[4];
-    int rX = -1, rY = -1;
-    int2 ty = __ldg(&ytab[yb]);
-    for (int y = yb; y < ye; ++y, out += dpitch) {
-        const int r0 = ty.x, r1 = min(r0 + 1, sh - 1);
-        const uint32_t b0 = (uint32_t)ty.y & 0xffffu, b1 = (uint32_t)ty.y >> 16;
-        if (y + 1 < ye) ty = __ldg(&ytab[y + 1]);
-        uint32_t wX, wY;
-        if (r0 == rY) {
-            wY = b0; wX = b1;
-            if (rX != r1) { hrow(r1, HX); rX = r1; }
-        } else {
-            if (r0 != rX) { hrow(r0, HX); rX = r0; }
-            wX = b0; wY = b1;
-            if (rY != r1) { hrow(r1, HY); rY = r1; }
-        }
-        uint32_t v[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = (__umulhi(HX[j], wX) + __umulhi(HY[j], wY) + 2u) >> 2;
-        *(uint32_t*)out = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
-    }
+    if (__all_sync(0xffffffffu, fast)) pyr_walk<true>(J, ring[threadIdx.x >> 5], frame, lane, d0, sx0, live, C, selA, selB, yb, ye);
+    else pyr_walk<false>(J, ring[threadIdx.x >> 5], frame, lane, d0, sx0, live, C, selA, selB, yb, ye);
 }
 
 // Generic fallback (any scale factor): one thread = 4 destination pixels straight from global.
@@ -303,7 +344,8 @@ cudaError_t orb_launch_pyramid_level(const OrbPlan& plan, const OrbBatch& io, in
     const OrbLevel& D = plan.lv[l];
     const OrbLevel& S = plan.lv[l - 1];
     // the walker needs the 4 destination pixels of a lane to span at most 7 source pixels
-    const bool walker = 4LL * S.w <= 5LL * D.w && S.w >= 12;
+    // ... and every source row to end at most one destination row (no upsampling)
+    const bool walker = 4LL * S.w <= 5LL * D.w && S.w >= 12 && S.h >= D.h;
     if (walker) {
         // rows per warp: as many as still leave every SM a few dozen warps (each row waits for its loads)
         int th = PYR_TH, tiles;
@@ -311,7 +353,14 @@ cudaError_t orb_launch_pyramid_level(const OrbPlan& plan, const OrbBatch& io, in
             tiles = ((D.w + PYR_TW - 1) / PYR_TW) * ((D.h + th - 1) / th);
             if (th <= 8 || (long long)tiles * batch >= 148LL * 64) break;
         }
-        k_pyr_resize<<<dim3((tiles + PYR_NT / 32 - 1) / (PYR_NT / 32), 1, batch), PYR_NT, 0, st>>>(plan, io, l, th);
+        PyrJob J;
+        if (l == 1) { J.src = io.img0; J.src_stride = io.img0_stride; J.spitch = io.img0_pitch; }
+        else { J.src = io.pyr + S.img_off; J.src_stride = plan.pyr_bytes; J.spitch = S.pitch; }
+        J.dst = io.pyr + D.img_off; J.dst_stride = plan.pyr_bytes; J.dpitch = D.pitch;
+        J.sw = S.w; J.sh = S.h; J.dw = D.w; J.dh = D.h;
+        J.xtab = (const int2*)io.taps + D.xtab; J.ytab = (const int4*)(io.taps + D.ytab4);
+        J.th = th; J.tiles_x = (D.w + PYR_TW - 1) / PYR_TW; J.tiles_y = (D.h + th - 1) / th;
+        k_pyr_resize<<<dim3((tiles + PYR_NT / 32 - 1) / (PYR_NT / 32), 1, batch), PYR_NT, 0, st>>>(J);
     } else {
         dim3 blk(32, 8), grd((D.pitch / 4 + 31) / 32, (D.h + 7) / 8, batch);
         k_pyr_resize_generic<<<grd, blk, 0, st>>>(plan, io, l);

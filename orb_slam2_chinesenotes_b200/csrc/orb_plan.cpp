@@ -139,6 +139,14 @@ int orb_plan_build(const OrbParams* p, int w, int h, OrbPlan* plan, std::vector<
         if (l > 0 && taps) {
             L.xtab = (int)taps->size(); axis_table(plan->lv[l - 1].w, L.w, taps);
             L.ytab = (int)taps->size(); axis_table(plan->lv[l - 1].h, L.h, taps);
+            // the same rows again for the pyramid walker: 16-byte entries { source row, c0 << 12, c1 << 12, 0 }
+            if (taps->size() & 1) taps->push_back(OrbTap{ 0, 0u });
+            L.ytab4 = (int)taps->size();
+            for (int d = 0; d < L.h; ++d) {
+                const OrbTap t = (*taps)[(size_t)L.ytab + d];
+                taps->push_back(OrbTap{ t.ofs, (t.c01 & 0xffffu) << 12 });
+                taps->push_back(OrbTap{ (int)((t.c01 >> 16) << 12), 0u });
+            }
         }
         L.blur_tiles_x = (L.w + ORB_BLUR_TW - 1) / ORB_BLUR_TW;
         L.blur_tiles_y = (L.h + ORB_BLUR_TH - 1) / ORB_BLUR_TH;

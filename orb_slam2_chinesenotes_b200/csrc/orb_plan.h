@@ -49,6 +49,7 @@ struct OrbLevel {
     float size;             // KeyPoint::size = (int)(31*scale)
     // resize tables (entries into the table buffer): for level >= 1, from level-1 to this level
     int xtab, ytab;
+    int ytab4;              // the y table again as 16-byte entries { source row, c0 << 12, c1 << 12, 0 } (even index)
     // blur tiles
     int blur_tiles_x, blur_tiles_y, blur_tile_first;
 };
