@@ -228,25 +228,24 @@ __global__ void __launch_bounds__(256) k_pyr_resize_generic(const __grid_constan
 #define BLUR_NT 32       // one warp per block; measured per 1024 frames: 32 threads 1.33 ms, 64 1.52, 128 1.54, 256 1.66
 #endif
 
-__global__ void __launch_bounds__(BLUR_NT) k_blur7(const __grid_constant__ OrbPlan plan, const OrbBatch io)
+// Filter taps as bytes for IDP.2A (.lo uses bytes 0-1, .hi bytes 2-3) and the rounding constant, handed over as kernel
+// parameters so that they are constant-bank operands of the instructions (as literals they are re-materialised into
+// uniform registers in every row of the loop).
+struct BlurTaps { uint32_t w0, w1, w2, w3, rnd; };
+
+// The row walk of one warp.  Like the pyramid, the kernel waits on memory before it runs out of issue slots, so the rows
+// travel through a per-warp shared-memory ring filled by cp.async seven rows ahead (lane-private slots, no barrier) and the
+// prefetch costs no registers.  Every lane fetches the one or two aligned words that hold its four pixels -- for the lanes at
+// the level's left / right edge the four REFLECT_101 columns, which span at most four bytes as well -- and one PRMT whose
+// selector is (column offsets + the row's misalignment) puts them in order: no lane takes a different path.
+// ONEWORD: every row of the level starts on a 4-byte boundary and no lane of the warp is an edge lane, so the four
+// pixels ARE one aligned word.
+template <bool ONEWORD>
+__device__ __forceinline__ void blur_walk(const BlurTaps& T, uint32_t (*ring)[2][32], const int lane, const uint8_t* __restrict__ src, const int pitch, const int w, const int h,
+                                          uint8_t* __restrict__ out, const int opitch, const int x, const int yb, const int ye, const bool writer)
 {
-    const int frame = blockIdx.y, lane = threadIdx.x & 31;
-    const int wt = blockIdx.x * (BLUR_NT / 32) + (threadIdx.x >> 5);       // this warp's tile within the frame
-    if (wt >= plan.total_blur_tiles) return;
-    int l = 0;
-    while (l + 1 < plan.nlevels && wt >= plan.lv[l + 1].blur_tile_first) ++l;
-    const OrbLevel& L = plan.lv[l];
-    const int t = wt - L.blur_tile_first;
-    const int tyi = __float2int_rz(__fmul_rn((float)t + 0.5f, __frcp_rn((float)L.blur_tiles_x)));
-    const int tx0 = (t - tyi * L.blur_tiles_x) * ORB_BLUR_TW, yb = tyi * ORB_BLUR_TH;
-    int pitch;
-    const uint8_t* __restrict__ src = orb_level_ptr(plan, io, frame, l, &pitch);
-    const int w = L.w, h = L.h;
-    const int ye = min(yb + ORB_BLUR_TH, h);
-    // columns: lane owns pixels x .. x+3.  Columns more than 3 px outside the image only feed outputs that are
-    // never stored, so indices are clamped to [-3, w+2] first and ONE reflection is enough (w >= 4 holds here).
-    const int x = tx0 - 4 + 4 * lane;
-    const bool fast = x >= 0 && x + 7 < w;
+    // columns more than 3 px outside the image only feed outputs that are never stored, so indices are clamped to
+    // [-3, w+2] first and ONE reflection is enough (w >= 4 holds here)
     int xr[4];
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
@@ -254,38 +253,66 @@ __global__ void __launch_bounds__(BLUR_NT) k_blur7(const __grid_constant__ OrbPl
         i = i < 0 ? -i : i;
         xr[b] = i >= w ? 2 * (w - 1) - i : i;
     }
-    auto load_row = [&](int y) -> uint32_t {                              // y in [-3, h+2]
+    const int xmin = min(min(xr[0], xr[1]), min(xr[2], xr[3])), xmax = max(max(xr[0], xr[1]), max(xr[2], xr[3]));
+    const uint32_t sel0 = (uint32_t)((xr[0] - xmin) | ((xr[1] - xmin) << 4) | ((xr[2] - xmin) << 8) | ((xr[3] - xmin) << 12));
+    const int span = xmax - xmin + 1;                                      // <= 4
+    const int h2 = 2 * (h - 1);
+    const uint8_t* const col = src + xmin;
+    auto row_ptr = [&](int y) -> const uint8_t* {                          // y in [-3, h+2]
         y = abs(y);
-        y = min(y, 2 * (h - 1) - y);
-        const uint8_t* row = src + (size_t)y * pitch;
-        if (fast) return orb_ld_u32_unaligned(row + x);
-        return (uint32_t)__ldg(row + xr[0]) | ((uint32_t)__ldg(row + xr[1]) << 8) | ((uint32_t)__ldg(row + xr[2]) << 16) |
-               ((uint32_t)__ldg(row + xr[3]) << 24);
+        y = min(y, h2 - y);
+        return col + (size_t)(unsigned)y * (unsigned)pitch;
     };
-    // weights as bytes for IDP.2A: .lo uses bytes 0-1, .hi bytes 2-3
-    const uint32_t W0 = 0x30221200u, W1 = 0x12223038u, W2 = 0x38302212u, W3 = 0x00122230u;
-    uint8_t* __restrict__ out = io.blur + (size_t)frame * plan.blur_bytes + L.blur_off + (size_t)yb * L.pitch + x;
-    const bool writer = lane >= 1 && lane <= ORB_BLUR_TW / 4 && x < w;
-
-    uint32_t lo[7], hi[7], raw[7];
+    auto load_row = [&](const int y) -> uint32_t {                         // direct loads: the rows above the first output row
+        const uint8_t* p = row_ptr(y);
+        if (ONEWORD) return __ldg((const uint32_t*)p);
+        const int al = (int)((uintptr_t)p & 3);
+        const uint32_t* q = (const uint32_t*)(p - al);
+        const uint32_t w0 = __ldg(q), w1 = al + span > 4 ? __ldg(q + 1) : 0u;
+        return __byte_perm(w0, w1, sel0 + 0x1111u * (uint32_t)al);
+    };
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(&ring[0][0][lane]);
+    auto post = [&](const int slot, const int y, const bool on) {          // one commit group per row, empty once the rows are used up
+        if (on) {
+            const uint8_t* p = row_ptr(y);
+            const uint32_t d = ring_s + (uint32_t)slot * (2 * 32 * 4);
+            if (ONEWORD) cp_async4(d, p);
+            else {
+                const int al = (int)((uintptr_t)p & 3);
+                cp_async4(d, p - al);
+                cp_async4_zfill(d + 128, p - al + 4, al + span > 4 ? 4u : 0u);   // never reads a word that starts behind the lane's last pixel
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto take = [&](const int slot, const int y) -> uint32_t {             // row y out of the ring
+        asm volatile("cp.async.wait_group 6;" ::: "memory");
+        if (ONEWORD) return ring[slot][0][lane];
+        const uint32_t al = (uint32_t)(uintptr_t)row_ptr(y) & 3u;
+        return __byte_perm(ring[slot][0][lane], ring[slot][1][lane], sel0 + 0x1111u * al);
+    };
+    const uint32_t W0 = T.w0, W1 = T.w1, W2 = T.w2, W3 = T.w3, RND = T.rnd;
+    const int ylast = ye + 2;                                              // last row any output of this tile reads
+#pragma unroll
+    for (int i = 0; i < 7; ++i) post(i, yb + 3 + i, yb + 3 + i <= ylast);  // rows yb+3 .. yb+9
+    uint32_t lo[7], hi[7];
 #pragma unroll
     for (int i = 0; i < 6; ++i) {                                          // rows yb-3 .. yb+2
         const uint32_t v = load_row(yb - 3 + i);
         lo[i] = __byte_perm(v, 0, 0x4140);
         hi[i] = __byte_perm(v, 0, 0x4342);
     }
-#pragma unroll
-    for (int i = 0; i < 7; ++i) raw[i] = yb + 3 + i <= ye + 2 ? load_row(yb + 3 + i) : 0u;   // rows yb+3 .. yb+9
     for (int y7 = yb; y7 < ye; y7 += 7) {
 #pragma unroll
         for (int u = 0; u < 7; ++u) {
             const int y = y7 + u;
             if (y >= ye) break;
 #define SL(i) ((u + (i)) % 7)
-            // row y-3+i sits in slot SL(i); the new row y+3 was fetched 7 iterations ago
-            lo[SL(6)] = __byte_perm(raw[u], 0, 0x4140);
-            hi[SL(6)] = __byte_perm(raw[u], 0, 0x4342);
-            if (y + 10 <= ye + 2) raw[u] = load_row(y + 10);
+            // row y-3+i sits in slot SL(i); the new row y+3 was posted 7 iterations ago
+            const uint32_t v = take(u, y + 3);
+            post(u, y + 10, y + 10 <= ylast);
+            lo[SL(6)] = __byte_perm(v, 0, 0x4140);
+            hi[SL(6)] = __byte_perm(v, 0, 0x4342);
             const uint32_t vlo = 18u * (lo[SL(0)] + lo[SL(6)]) + 34u * (lo[SL(1)] + lo[SL(5)]) + 48u * (lo[SL(2)] + lo[SL(4)]) + 56u * lo[SL(3)];
             const uint32_t vhi = 18u * (hi[SL(0)] + hi[SL(6)]) + 34u * (hi[SL(1)] + hi[SL(5)]) + 48u * (hi[SL(2)] + hi[SL(4)]) + 56u * hi[SL(3)];
 #undef SL
@@ -293,14 +320,38 @@ __global__ void __launch_bounds__(BLUR_NT) k_blur7(const __grid_constant__ OrbPl
             const uint32_t llo = __shfl_up_sync(0xffffffffu, vlo, 1), lhi = __shfl_up_sync(0xffffffffu, vhi, 1);
             const uint32_t rlo = __shfl_down_sync(0xffffffffu, vlo, 1), rhi = __shfl_down_sync(0xffffffffu, vhi, 1);
             // out(x+j) = 18 s[j-3] + 34 s[j-2] + 48 s[j-1] + 56 s[j] + 48 s[j+1] + 34 s[j+2] + 18 s[j+3] + 2^15
-            const uint32_t o0 = dp2a_hi(vhi, W1, dp2a_lo(vlo, W1, dp2a_hi(lhi, W0, dp2a_lo(llo, W0, 32768u))));
-            const uint32_t o1 = dp2a_hi(rlo, W3, dp2a_lo(vhi, W3, dp2a_hi(vlo, W2, dp2a_lo(lhi, W2, 32768u))));
-            const uint32_t o2 = dp2a_hi(rlo, W1, dp2a_lo(vhi, W1, dp2a_hi(vlo, W0, dp2a_lo(lhi, W0, 32768u))));
-            const uint32_t o3 = dp2a_hi(rhi, W3, dp2a_lo(rlo, W3, dp2a_hi(vhi, W2, dp2a_lo(vlo, W2, 32768u))));
+            const uint32_t o0 = dp2a_hi(vhi, W1, dp2a_lo(vlo, W1, dp2a_hi(lhi, W0, dp2a_lo(llo, W0, RND))));
+            const uint32_t o1 = dp2a_hi(rlo, W3, dp2a_lo(vhi, W3, dp2a_hi(vlo, W2, dp2a_lo(lhi, W2, RND))));
+            const uint32_t o2 = dp2a_hi(rlo, W1, dp2a_lo(vhi, W1, dp2a_hi(vlo, W0, dp2a_lo(lhi, W0, RND))));
+            const uint32_t o3 = dp2a_hi(rhi, W3, dp2a_lo(rlo, W3, dp2a_hi(vhi, W2, dp2a_lo(vlo, W2, RND))));
             if (writer) *(uint32_t*)out = __byte_perm(__byte_perm(o0, o1, 0x0062), __byte_perm(o2, o3, 0x0062), 0x5410);
-            out += L.pitch;
+            out += opitch;
         }
     }
+}
+
+__global__ void __launch_bounds__(BLUR_NT) k_blur7(const __grid_constant__ OrbPlan plan, const OrbBatch io, const BlurTaps T)
+{
+    __shared__ uint32_t ring[BLUR_NT / 32][7][2][32];
+    const int frame = blockIdx.y, lane = threadIdx.x & 31;
+    const int wt = blockIdx.x * (BLUR_NT / 32) + (threadIdx.x >> 5);       // this warp's tile within the frame
+    if (wt >= plan.total_blur_tiles) return;
+    int l = 0;
+    while (l + 1 < plan.nlevels && wt >= plan.lv[l + 1].blur_tile_first) ++l;
+    const int w = plan.lv[l].w, h = plan.lv[l].h, opitch = plan.lv[l].pitch, btx = plan.lv[l].blur_tiles_x;
+    const int t = wt - plan.lv[l].blur_tile_first;
+    const int tyi = __float2int_rz(__fmul_rn((float)t + 0.5f, __frcp_rn((float)btx)));
+    const int tx0 = (t - tyi * btx) * ORB_BLUR_TW, yb = tyi * ORB_BLUR_TH;
+    int pitch;
+    const uint8_t* __restrict__ src = orb_level_ptr(plan, io, frame, l, &pitch);
+    const int ye = min(yb + ORB_BLUR_TH, h);
+    const int x = tx0 - 4 + 4 * lane;                                      // lane owns pixels x .. x+3
+    uint8_t* __restrict__ out = io.blur + (size_t)frame * plan.blur_bytes + plan.lv[l].blur_off + (size_t)yb * opitch + x;
+    const bool writer = lane >= 1 && lane <= ORB_BLUR_TW / 4 && x < w;
+    const bool inner = __all_sync(0xffffffffu, x >= 0 && x + 3 < w);       // no lane reflects a column
+    const bool aligned = ((((uintptr_t)src) | (unsigned)pitch) & 3) == 0;  // x is a multiple of 4
+    if (inner && aligned) blur_walk<true>(T, ring[threadIdx.x >> 5], lane, src, pitch, w, h, out, opitch, x, yb, ye, writer);
+    else blur_walk<false>(T, ring[threadIdx.x >> 5], lane, src, pitch, w, h, out, opitch, x, yb, ye, writer);
 }
 
 // ------------------------------------------------------------------------------ border
@@ -381,7 +432,8 @@ int orb_pyramid_launch_count(const OrbPlan& plan) { return plan.nlevels - 1; }  
 
 cudaError_t orb_launch_blur(const OrbPlan& plan, const OrbBatch& io, int batch, cudaStream_t st)
 {
-    k_blur7<<<dim3((plan.total_blur_tiles + BLUR_NT / 32 - 1) / (BLUR_NT / 32), batch), BLUR_NT, 0, st>>>(plan, io);
+    const BlurTaps T = { 0x30221200u, 0x12223038u, 0x38302212u, 0x00122230u, 32768u };
+    k_blur7<<<dim3((plan.total_blur_tiles + BLUR_NT / 32 - 1) / (BLUR_NT / 32), batch), BLUR_NT, 0, st>>>(plan, io, T);
     return cudaGetLastError();
 }
 
