@@ -397,12 +397,27 @@ int run_batch(orbx_ctx* c, const uint8_t* imgs, size_t frame_stride, int batch, 
     const int want = piped ? c->chunk : c->chunk_resident;
     int chunk = batch < want ? batch : want;
     if (sr && chunk % 2) chunk = chunk > 1 ? chunk - 1 : 2;      // a pair never straddles two chunks
-    const int nchunks = (batch + chunk - 1) / chunk;
+    // Chunk schedule.  On the piped path the first chunk's upload and the last chunk's kernels + download have nothing to
+    // overlap with, so the batch starts and ends with smaller chunks (chunk/4, chunk/2, chunk ... chunk, chunk/2, chunk/4)
+    // when it is long enough (ORB_TAPER=0 switches it off).
+    std::vector<int> sched;
+    {
+        static const bool taper_on = []{ const char* e = getenv("ORB_TAPER"); return !(e && e[0] == '0'); }();
+        int left = batch;
+        const int q = (chunk / 4) & ~1, hlf = (chunk / 2) & ~1;
+        const bool taper = taper_on && piped && q >= 2 && batch >= 6 * chunk;
+        int tail[2] = { 0, 0 };
+        if (taper) { sched.push_back(q); sched.push_back(hlf); left -= q + hlf; tail[0] = hlf; tail[1] = q; left -= hlf + q; }
+        while (left > 0) { const int nfc = left < chunk ? left : chunk; sched.push_back(nfc); left -= nfc; }
+        if (taper) { sched.push_back(tail[0]); sched.push_back(tail[1]); }
+    }
+    const int nchunks = (int)sched.size();
     const int nslot = nchunks < NSLOT ? nchunks : NSLOT;
     // Chunks alternate between compute streams only on the piped path (small chunks: one chunk's latency-bound sparse
     // kernels share the SMs with the next chunk's dense ones).  Device-resident chunks are large; running two of
     // them side by side measured slower than back to back (6.84 vs 6.40 ms per 512 frames in chunks of 256).
-    const bool multi = nslot > 1 && !c->profile && piped;
+    static const bool force_multi = []{ const char* e = getenv("ORB_FORCE_MULTI"); return e && e[0] == '1'; }();   // experiment knob
+    const bool multi = nslot > 1 && !c->profile && (piped || force_multi);
     const size_t in_frame_bytes = pitch * (size_t)h;
     const size_t frame_copy_bytes = pitch * (size_t)(h - 1) + (size_t)w;   // never read past the last row's pixels
     for (int s = 0; s < nslot; ++s) {
@@ -413,9 +428,8 @@ int run_batch(orbx_ctx* c, const uint8_t* imgs, size_t frame_stride, int batch, 
         CU(c, cudaEventRecord(c->fork_ev, c->stream));
         for (int k = 1; k < nslot; ++k) CU(c, cudaStreamWaitEvent(c->xstream[k - 1], c->fork_ev, 0));
     }
-    for (int i = 0; i < nchunks; ++i) {
-        const int f0 = i * chunk;
-        const int nf = batch - f0 < chunk ? batch - f0 : chunk;
+    for (int i = 0, f0 = 0; i < nchunks; f0 += sched[i], ++i) {
+        const int nf = sched[i];
         Slot& s = c->slot[i % nslot];
         cudaStream_t st = multi && i % nslot ? c->xstream[i % nslot - 1] : c->stream;
         const uint8_t* d_img; size_t d_stride;

@@ -41,6 +41,9 @@ __device__ __forceinline__ uint32_t dp2a_hi(const uint32_t a, const uint32_t b, 
 #define PYR_NT 64
 #endif
 #define PYR_TW 128
+#ifndef PYR_MIN_WARPS
+#define PYR_MIN_WARPS 64   // warps per SM a launch should at least have before its tiles get taller
+#endif
 #define PYR_TH 64
 
 // Everything a launch needs about its level, as plain kernel parameters (constant bank, fixed offsets).
@@ -402,7 +405,7 @@ cudaError_t orb_launch_pyramid_level(const OrbPlan& plan, const OrbBatch& io, in
         int th = PYR_TH, tiles;
         for (;; th >>= 1) {
             tiles = ((D.w + PYR_TW - 1) / PYR_TW) * ((D.h + th - 1) / th);
-            if (th <= 8 || (long long)tiles * batch >= 148LL * 64) break;
+            if (th <= 8 || (long long)tiles * batch >= 148LL * PYR_MIN_WARPS) break;
         }
         PyrJob J;
         if (l == 1) { J.src = io.img0; J.src_stride = io.img0_stride; J.spitch = io.img0_pitch; }

@@ -32,6 +32,12 @@
 #ifndef ORB_OCT_NT_SMALL
 #define ORB_OCT_NT_SMALL 1024  // ... and for a handful of frames, where one block per level is all the parallelism there is (latency)
 #endif
+#ifndef ORB_OCT_NT_MID
+#define ORB_OCT_NT_MID 512     // ... and for launches whose blocks fit the GPU in one wave (148 SMs x 4 blocks of 512 threads)
+#endif
+#ifndef ORB_OCT_MID_BLOCKS
+#define ORB_OCT_MID_BLOCKS 592
+#endif
 #ifndef ORB_OCT_SMALL_BATCH
 #define ORB_OCT_SMALL_BATCH 8
 #endif
@@ -281,6 +287,17 @@ cudaError_t orb_launch_octree(const OrbPlan& plan, const OrbBatch& io, int batch
     if (level_lo >= level_hi) return cudaSuccess;
     const size_t smem = orb_octree_smem_bytes(plan);
     const bool small = batch <= ORB_OCT_SMALL_BATCH;
+    // a chunk of the host-buffer pipeline (64 frames): the blocks of all levels are resident at once, so the launch lasts as
+    // long as its slowest block; twice the threads per block shorten that
+    const bool mid = !small && (long long)batch * (level_hi - level_lo) <= ORB_OCT_MID_BLOCKS;
+    if (mid) {
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(k_octree<ORB_OCT_NT_MID>, cudaFuncAttributeMaxDynamicSharedMemorySize, ORB_SMEM_OPTIN);
+            if (e != cudaSuccess) return e;
+        }
+        k_octree<ORB_OCT_NT_MID><<<dim3(level_hi - level_lo, batch), ORB_OCT_NT_MID, smem, st>>>(plan, io, level_lo);
+        return cudaGetLastError();
+    }
     if (smem > 48 * 1024) {
         // a constant: the attribute is per-function state shared by all host threads (a per-launch value races)
         cudaError_t e = small ? cudaFuncSetAttribute(k_octree<ORB_OCT_NT_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, ORB_SMEM_OPTIN)
