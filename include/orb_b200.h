@@ -193,6 +193,22 @@ typedef struct {
     float min_x, max_x, min_y, max_y;
 } orbm_frame;
 
+/* A Frame kept on the device.  Tracking runs two to four searches on the same Frame (src/Tracking.cc: TrackWithMotionModel,
+ * TrackReferenceKeyFrame, SearchLocalPoints, Relocalization), and its mvKeysUn / mDescriptors / mvuRight never change after
+ * the constructor (src/Frame.cc:58-174), so they can be uploaded once: orbm_frame_upload copies them into device memory,
+ * orbm_frame_view fills an orbm_frame whose kps / desc / u_right are DEVICE pointers (bounds as given at upload; the caller
+ * may null u_right in its copy of the view to search monocularly), and EVERY single-problem search below
+ * (orbm_search_by_projection_points / _frame, orbm_window_search_best, orbm_search_for_initialization, orbm_search_by_bow,
+ * orbm_debug_features_in_area) accepts such a view in place of one with host pointers and skips the upload; it is also a
+ * valid one-problem input of the *_batch entry points (kps / desc / u_right with kp_stride = n).  Frames with n = 0 are
+ * allowed (the view then holds null pointers).  orbm_frame_release frees the device memory; the handle must outlive
+ * every search that uses its view. */
+typedef struct orbm_frame_handle orbm_frame_handle;
+int orbm_frame_upload(const orbm_frame* F, int device, orbm_frame_handle** handle);
+int orbm_frame_view(const orbm_frame_handle* handle, orbm_frame* view);
+int orbm_frame_device(const orbm_frame_handle* handle);
+void orbm_frame_release(orbm_frame_handle* handle);
+
 /* ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th), src/ORBmatcher.cc:73-157.
  * Map points as arrays [nq]: mTrackProjX/Y/XR (3 floats each), mnTrackScaleLevel, mTrackViewCos,
  * mbTrackInView, isBad(), Observations(), GetDescriptor().  init_assign [n] (or NULL): index of the map

@@ -78,11 +78,13 @@ public:
 
 class KeyFrame {
 public:
-    KeyFrame() : N(0), fx(0), fy(0), cx(0), cy(0), invfx(0), invfy(0), mbf(0), mb(0), mThDepth(0), mnId(0),
+    KeyFrame() : N(0), fx(0), fy(0), cx(0), cy(0), invfx(0), invfy(0), mbf(0), mb(0), mThDepth(0), mnId(0), mnFrameId(0), mTimeStamp(0),
                  mnMinX(0), mnMinY(0), mnMaxX(0), mnMaxY(0), mfGridElementWidthInv(0), mfGridElementHeightInv(0) {}
     int N;
     float fx, fy, cx, cy, invfx, invfy, mbf, mb, mThDepth;
     long unsigned int mnId;
+    long unsigned int mnFrameId;      // include/KeyFrame.h:126: id of the Frame the key frame was made from
+    double mTimeStamp;                // include/KeyFrame.h:128
     std::vector<cv::KeyPoint> mvKeys, mvKeysUn;
     std::vector<float> mvuRight, mvDepth;
     cv::Mat mDescriptors;

@@ -376,6 +376,44 @@ class FrameView:
                          None if self.u_right is None else self.u_right.ctypes.data, *self.bounds)
 
 
+class ResidentFrame(FrameView):
+    """A FrameView whose keypoints / descriptors / mvuRight were uploaded once (orbm_frame_upload): every search that takes
+    a FrameView takes this instead and skips the upload -- Tracking runs two to four searches per Frame."""
+
+    def __init__(self, kps, desc, bounds, u_right=None, device=0):
+        super().__init__(kps, desc, bounds, u_right)
+        self._h = C.c_void_p()
+        L = lib()
+        L.orbm_frame_upload.argtypes = [C.POINTER(OrbmFrame), C.c_int, C.POINTER(C.c_void_p)]
+        L.orbm_frame_view.argtypes = [C.c_void_p, C.POINTER(OrbmFrame)]
+        L.orbm_frame_release.argtypes = [C.c_void_p]
+        L.orbm_frame_release.restype = None
+        host = FrameView.struct(self)
+        rc = L.orbm_frame_upload(C.byref(host), device, C.byref(self._h))
+        if rc:
+            raise OrbError(rc, "orbm_frame_upload failed")
+
+    def struct(self, with_right=True):
+        v = OrbmFrame()
+        rc = lib().orbm_frame_view(self._h, C.byref(v))
+        if rc:
+            raise OrbError(rc, "orbm_frame_view failed")
+        if not with_right:
+            v.u_right = None
+        return v
+
+    def close(self):
+        if self._h:
+            lib().orbm_frame_release(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class ORBmatcher:
     """ORB_SLAM2::ORBmatcher (include/ORBmatcher.h:43-100): the Hamming searches of the hot path."""
     TH_LOW, TH_HIGH, HISTO_LENGTH = 50, 100, 30   # src/ORBmatcher.cc:37-39

@@ -399,10 +399,10 @@ int run_batch(orbx_ctx* c, const uint8_t* imgs, size_t frame_stride, int batch, 
     if (sr && chunk % 2) chunk = chunk > 1 ? chunk - 1 : 2;      // a pair never straddles two chunks
     // Chunk schedule.  On the piped path the first chunk's upload and the last chunk's kernels + download have nothing to
     // overlap with, so the batch starts and ends with smaller chunks (chunk/4, chunk/2, chunk ... chunk, chunk/2, chunk/4)
-    // when it is long enough (ORB_TAPER=0 switches it off).
+    // when ORB_TAPER=1 asks for it (measured: 80.9 k against 81.5 k frames/s end to end, so off by default).
     std::vector<int> sched;
     {
-        static const bool taper_on = []{ const char* e = getenv("ORB_TAPER"); return !(e && e[0] == '0'); }();
+        static const bool taper_on = []{ const char* e = getenv("ORB_TAPER"); return e && e[0] == '1'; }();
         int left = batch;
         const int q = (chunk / 4) & ~1, hlf = (chunk / 2) & ~1;
         const bool taper = taper_on && piped && q >= 2 && batch >= 6 * chunk;

@@ -19,6 +19,7 @@
 // reference's running best/second-best update equals "the two smallest by (distance, position)", so a
 // warp reduces 32 candidates at a time.
 #include <cuda_runtime.h>
+#include <new>
 #include <stdint.h>
 
 #include <cmath>
@@ -472,9 +473,10 @@ bool make_frame(Scratch& S, const orbm_frame* F, DevFrame* D)
 {
     if (!F || F->n < 0 || F->n > MAX_KP || (F->n > 0 && (!F->kps || !F->desc))) return false;
     D->n = F->n;
-    D->kps = S.up(F->kps, (size_t)F->n);
-    D->desc = (const uint32_t*)S.up(F->desc, (size_t)F->n * 32);
-    D->u_right = F->u_right ? S.up(F->u_right, (size_t)F->n) : nullptr;
+    // a frame that is already on the device (orbm_frame_upload / orbm_frame_view) is used where it lies
+    D->kps = dev_ptr(F->kps) ? F->kps : S.up(F->kps, (size_t)F->n);
+    D->desc = (const uint32_t*)(dev_ptr(F->desc) ? F->desc : S.up(F->desc, (size_t)F->n * 32));
+    D->u_right = F->u_right ? (dev_ptr(F->u_right) ? F->u_right : S.up(F->u_right, (size_t)F->n)) : nullptr;
     D->min_x = F->min_x; D->min_y = F->min_y;
     D->inv_w = (float)GRID_COLS / (F->max_x - F->min_x);     // src/Frame.cc:108
     D->inv_h = (float)GRID_ROWS / (F->max_y - F->min_y);     // :109
@@ -524,6 +526,19 @@ int resolve_best(Scratch& S, const DevFrame& D, int nq, const WinQuery* dq, cons
 }
 } // namespace
 
+// assign_out [n] and the match count come back in ONE copy (d_assign has n + 1 entries, the count last): a synchronous
+// device-to-host copy costs ~10 us whatever its size
+static int fetch_assign(const int* d_assign, int n, int* assign_out, int* nmatches)
+{
+    thread_local std::vector<int> tmp;
+    tmp.resize((size_t)n + 1);
+    const cudaError_t e = cudaMemcpy(tmp.data(), d_assign, sizeof(int) * ((size_t)n + 1), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { report_cuda(e, "fetch_assign", __LINE__); cudaGetLastError(); return ORBX_E_CUDA; }
+    memcpy(assign_out, tmp.data(), sizeof(int) * (size_t)n);
+    *nmatches = tmp[(size_t)n];
+    return ORBX_OK;
+}
+
 bool orb_match_batch_fits(int kp_stride, int nq_stride);   // orb_match_batch.cu
 
 namespace {
@@ -537,9 +552,10 @@ bool one_frame(Scratch& S, const orbm_frame* F, OneFrame* O)
 {
     if (!F || F->n <= 0 || F->n > MAX_KP || !F->kps || !F->desc) return false;
     O->F.nprob = 1;
-    O->F.kps = S.up(F->kps, (size_t)F->n);
-    O->F.desc = S.up(F->desc, (size_t)F->n * 32);
-    O->F.u_right = F->u_right ? S.up(F->u_right, (size_t)F->n) : nullptr;
+    // a frame that is already on the device (orbm_frame_upload / orbm_frame_view) is used where it lies
+    O->F.kps = dev_ptr(F->kps) ? F->kps : S.up(F->kps, (size_t)F->n);
+    O->F.desc = dev_ptr(F->desc) ? F->desc : S.up(F->desc, (size_t)F->n * 32);
+    O->F.u_right = F->u_right ? (dev_ptr(F->u_right) ? F->u_right : S.up(F->u_right, (size_t)F->n)) : nullptr;
     O->d_n = S.up(&F->n, 1);
     O->F.n = O->d_n;
     O->F.kp_stride = F->n;
@@ -575,20 +591,76 @@ int best_via_batch(Scratch& S, const orbm_frame* F, bool use_ur, const std::vect
     W.q_angle = h_angle ? S.up(h_angle, (size_t)nq) : nullptr;
     W.q_obs = h_qobs ? S.up(h_qobs, (size_t)nq) : nullptr;
     int* d_init = h_init_obs ? S.up(h_init_obs, (size_t)n) : nullptr;
-    int* d_assign = (int*)S.alloc(sizeof(int) * (size_t)n);
-    int* d_nm = (int*)S.alloc(4);
+    int* d_assign = (int*)S.alloc(sizeof(int) * ((size_t)n + 1));
+    int* d_nm = d_assign ? d_assign + n : nullptr;
     if (!S.ok) return ORBX_E_CUDA;
     if (!use_ur) O.F.u_right = nullptr;
     if (!S.flush()) return ORBX_E_CUDA;
     const int rc = orbm_window_search_best_batch(&O.F, &W, d_init, d_assign, th_accept, check_ori, d_nm, nullptr, nullptr);
     if (rc) return rc;
-    CKM(cudaMemcpy(assign_out, d_assign, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost));
-    CKM(cudaMemcpy(nmatches, d_nm, 4, cudaMemcpyDeviceToHost));
-    return ORBX_OK;
+    return fetch_assign(d_assign, n, assign_out, nmatches);
 }
 } // namespace
 
 extern "C" {
+
+// ---- frame handles: a Frame's keypoints / descriptors / mvuRight uploaded once, reused by every search of that frame
+struct orbm_frame_handle {
+    int device, n;
+    char* block;             // one allocation: kps | desc | u_right
+    const orbx_kp* kps; const uint8_t* desc; const float* u_right;
+    float min_x, max_x, min_y, max_y;
+};
+
+int orbm_frame_upload(const orbm_frame* F, int device, orbm_frame_handle** handle)
+{
+    if (!handle) return ORBX_E_ARG;
+    *handle = nullptr;
+    if (!F || F->n < 0 || F->n > MAX_KP || (F->n > 0 && (!F->kps || !F->desc))) return ORBX_E_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return ORBX_E_CUDA; }
+    orbm_frame_handle* H = new (std::nothrow) orbm_frame_handle();
+    if (!H) return ORBX_E_CUDA;
+    H->device = device; H->n = F->n; H->block = nullptr; H->kps = nullptr; H->desc = nullptr; H->u_right = nullptr;
+    H->min_x = F->min_x; H->max_x = F->max_x; H->min_y = F->min_y; H->max_y = F->max_y;
+    if (F->n > 0) {
+        const size_t n = (size_t)F->n;
+        const size_t o_desc = (n * sizeof(orbx_kp) + 255) & ~(size_t)255, o_ur = o_desc + ((n * 32 + 255) & ~(size_t)255);
+        const size_t bytes = o_ur + (F->u_right ? n * 4 : 0);
+        if (cudaMalloc((void**)&H->block, bytes) != cudaSuccess) { cudaGetLastError(); delete H; return ORBX_E_CUDA; }
+        // pageable sources: cudaMemcpy returns once the bytes are staged, so the caller's vectors may go away at once
+        bool ok = cudaMemcpy(H->block, F->kps, n * sizeof(orbx_kp), cudaMemcpyDefault) == cudaSuccess &&
+                  cudaMemcpy(H->block + o_desc, F->desc, n * 32, cudaMemcpyDefault) == cudaSuccess &&
+                  (!F->u_right || cudaMemcpy(H->block + o_ur, F->u_right, n * 4, cudaMemcpyDefault) == cudaSuccess);
+        if (!ok) { cudaGetLastError(); cudaFree(H->block); delete H; return ORBX_E_CUDA; }
+        H->kps = (const orbx_kp*)H->block; H->desc = (const uint8_t*)(H->block + o_desc);
+        H->u_right = F->u_right ? (const float*)(H->block + o_ur) : nullptr;
+    }
+    *handle = H;
+    return ORBX_OK;
+}
+
+int orbm_frame_view(const orbm_frame_handle* H, orbm_frame* view)
+{
+    if (!H || !view) return ORBX_E_ARG;
+    view->n = H->n; view->kps = H->kps; view->desc = H->desc; view->u_right = H->u_right;
+    view->min_x = H->min_x; view->max_x = H->max_x; view->min_y = H->min_y; view->max_y = H->max_y;
+    return ORBX_OK;
+}
+
+int orbm_frame_device(const orbm_frame_handle* H) { return H ? H->device : -1; }
+
+void orbm_frame_release(orbm_frame_handle* H)
+{
+    if (!H) return;
+    if (H->block) {
+        int prev = -1;
+        const bool sw = cudaGetDevice(&prev) == cudaSuccess && prev != H->device && cudaSetDevice(H->device) == cudaSuccess;
+        cudaFree(H->block);
+        if (sw) cudaSetDevice(prev);
+        cudaGetLastError();
+    }
+    delete H;
+}
 
 int orbm_hamming_bf(const uint8_t* q, int nq, const uint8_t* t, int nt, int nprob,
                     int* best_idx, int* best_dist, int* second_dist, int device)
@@ -662,15 +734,13 @@ int orbm_search_by_projection_points(const orbm_frame* F, const float* scale, in
         Qp.in_view = S.up(in_view, (size_t)nq); Qp.bad = S.up(bad, (size_t)nq); Qp.observations = S.up(observations, (size_t)nq);
         Qp.qdesc = S.up(qdesc, (size_t)nq * 32);
         int* d_init = init_assign ? S.up(init_assign, (size_t)F->n) : nullptr;
-        int* d_assign = (int*)S.alloc(sizeof(int) * (size_t)F->n);
-        int* d_nm = (int*)S.alloc(4);
+        int* d_assign = (int*)S.alloc(sizeof(int) * ((size_t)F->n + 1));
+        int* d_nm = d_assign ? d_assign + F->n : nullptr;
         if (!S.ok) return ORBX_E_CUDA;
         if (!S.flush()) return ORBX_E_CUDA;
         const int rc = orbm_search_by_projection_points_batch(&O.F, scale, nlevels, &Qp, d_init, d_assign, th, nnratio, d_nm, nullptr, nullptr);
         if (rc) return rc;
-        CKM(cudaMemcpy(assign_out, d_assign, sizeof(int) * (size_t)F->n, cudaMemcpyDeviceToHost));
-        CKM(cudaMemcpy(nmatches, d_nm, 4, cudaMemcpyDeviceToHost));
-        return ORBX_OK;
+        return fetch_assign(d_assign, F->n, assign_out, nmatches);
     }
     DevFrame D;
     if (!make_frame(S, F, &D)) return S.ok ? ORBX_E_ARG : ORBX_E_CUDA;

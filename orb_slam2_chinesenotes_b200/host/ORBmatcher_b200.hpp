@@ -39,6 +39,7 @@
 #include <stdexcept>
 #include <string>
 #include <type_traits>
+#include <unordered_map>
 #include <vector>
 
 #include "orb_b200.h"
@@ -68,21 +69,97 @@ inline void FlattenDescriptors(const MatT& m, int n, std::vector<unsigned char>&
     for (int i = 0; i < n; ++i) std::memcpy(&out[(size_t)i * 32], m.ptr(i), 32);
 }
 
-template <class FrameT>
-inline orbm_frame View(const FrameT& F, const std::vector<orbx_kp>& kps, const std::vector<unsigned char>& desc, bool withRight)
-{
-    orbm_frame v;
-    v.n = (int)kps.size();
-    v.kps = kps.empty() ? 0 : &kps[0];
-    v.desc = &desc[0];
-    v.u_right = (withRight && !F.mvuRight.empty()) ? &F.mvuRight[0] : 0;
-    v.min_x = FrameT::mnMinX; v.max_x = FrameT::mnMaxX; v.min_y = FrameT::mnMinY; v.max_y = FrameT::mnMaxY;
-    return v;
-}
-
 inline void Check(int rc, const char* what)
 {
     if (rc != ORBX_OK) throw std::runtime_error(std::string(what) + " failed (B200 matcher, no CPU fallback)");
+}
+
+// ---- frames kept on the device --------------------------------------------------------------------------------
+// Tracking runs two to four searches on the same Frame (TrackWithMotionModel / TrackReferenceKeyFrame, then
+// SearchLocalPoints, Relocalization's retries), and a Frame's mvKeysUn, mDescriptors and mvuRight never change after its
+// constructor (src/Frame.cc:58-174), nor do a KeyFrame's (they are copies of its Frame's, src/KeyFrame.cc:31-45).  So the
+// forwarders upload them once (orbm_frame_upload) and every later search of that Frame or KeyFrame reuses the device copy:
+// a small per-THREAD cache (Tracking, LocalMapping and LoopClosing run on their own threads) keyed by the frame id --
+// Frame::mnId, which a KeyFrame carries as mnFrameId, so a KeyFrame finds the entry its Frame made -- with the keypoint
+// count and the time stamp as a guard, least recently used entry dropped first.  Frame::nNextId restarts at 0 in
+// Tracking::Reset (src/Tracking.cc:1517): call b200::ResidentFrames::Local().Clear() there.
+class ResidentFrames {
+public:
+    enum { kCapacity = 8 };
+    static ResidentFrames& Local() { static thread_local ResidentFrames c; return c; }
+    ~ResidentFrames() { Clear(); }
+    void Clear()
+    {
+        for (size_t i = 0; i < e_.size(); ++i) orbm_frame_release(e_[i].h);
+        e_.clear();
+    }
+    size_t Size() const { return e_.size(); }
+    unsigned long Uploads() const { return uploads_; }
+
+    // The device-resident view of (keys, descriptors, uRight); uRight may be null.  Bounds are the caller's.
+    template <class KeyPointT, class MatT>
+    orbm_frame Get(unsigned long id, double stamp, const std::vector<KeyPointT>& keys, const MatT& descriptors, const std::vector<float>* uRight,
+                   float minX, float maxX, float minY, float maxY)
+    {
+        const int n = (int)keys.size();
+        const bool wantRight = uRight && !uRight->empty();
+        Entry* hit = 0;
+        for (size_t i = 0; i < e_.size(); ++i)
+            if (e_[i].id == id && e_[i].n == n && e_[i].stamp == stamp && e_[i].device == Device() && (e_[i].right || !wantRight)) { hit = &e_[i]; break; }
+        if (!hit) {
+            std::vector<orbx_kp> kps; FlattenKeys(keys, kps);
+            std::vector<unsigned char> desc; FlattenDescriptors(descriptors, n, desc);
+            orbm_frame host;
+            host.n = n; host.kps = Ptr(kps); host.desc = &desc[0]; host.u_right = wantRight ? &(*uRight)[0] : 0;
+            host.min_x = minX; host.max_x = maxX; host.min_y = minY; host.max_y = maxY;
+            Entry e;
+            e.id = id; e.n = n; e.stamp = stamp; e.device = Device(); e.right = wantRight; e.use = 0; e.h = 0;
+            Check(orbm_frame_upload(&host, Device(), &e.h), "orbm_frame_upload");
+            ++uploads_;
+            // an entry of the same frame without right coordinates is superseded; else the least recently used one goes
+            size_t victim = e_.size();
+            for (size_t i = 0; i < e_.size(); ++i) if (e_[i].id == id && e_[i].n == n && e_[i].stamp == stamp && e_[i].device == e.device) victim = i;
+            if (victim == e_.size() && e_.size() >= (size_t)kCapacity) {
+                victim = 0;
+                for (size_t i = 1; i < e_.size(); ++i) if (e_[i].use < e_[victim].use) victim = i;
+            }
+            if (victim < e_.size()) { orbm_frame_release(e_[victim].h); e_[victim] = e; hit = &e_[victim]; }
+            else { e_.push_back(e); hit = &e_.back(); }
+        }
+        hit->use = ++tick_;
+        orbm_frame v;
+        Check(orbm_frame_view(hit->h, &v), "orbm_frame_view");
+        if (!wantRight) v.u_right = 0;
+        v.min_x = minX; v.max_x = maxX; v.min_y = minY; v.max_y = maxY;
+        return v;
+    }
+
+private:
+    struct Entry { unsigned long id; int n; double stamp; int device; bool right; unsigned long use; orbm_frame_handle* h; };
+    ResidentFrames() : tick_(0), uploads_(0) {}
+    ResidentFrames(const ResidentFrames&);
+    ResidentFrames& operator=(const ResidentFrames&);
+    std::vector<Entry> e_;
+    unsigned long tick_, uploads_;
+};
+
+// A Frame's mvKeysUn / mDescriptors (/ mvuRight when withRight) on the device.  Reads F.mnId, F.mTimeStamp.
+template <class FrameT>
+inline orbm_frame Resident(const FrameT& F, bool withRight)
+{
+    return ResidentFrames::Local().Get((unsigned long)F.mnId, (double)F.mTimeStamp, F.mvKeysUn, F.mDescriptors, withRight ? &F.mvuRight : 0,
+                                       FrameT::mnMinX, FrameT::mnMaxX, FrameT::mnMinY, FrameT::mnMaxY);
+}
+// A KeyFrame's mvKeysUn / mDescriptors on the device (the entry of the Frame it was made from, if still cached).  Reads
+// pKF->mnFrameId, mTimeStamp.  `grid`: with the key frame's own image bounds (the window searches), else the 0..1 dummy
+// bounds of the searches that use no grid (SearchByBoW).
+template <class KeyFrameT>
+inline orbm_frame ResidentKF(const KeyFrameT* pKF, bool grid)
+{
+    if (grid)
+        return ResidentFrames::Local().Get((unsigned long)pKF->mnFrameId, (double)pKF->mTimeStamp, pKF->mvKeysUn, pKF->mDescriptors, 0,
+                                           (float)pKF->mnMinX, (float)pKF->mnMaxX, (float)pKF->mnMinY, (float)pKF->mnMaxY);
+    return ResidentFrames::Local().Get((unsigned long)pKF->mnFrameId, (double)pKF->mTimeStamp, pKF->mvKeysUn, pKF->mDescriptors, 0, 0.f, 1.f, 0.f, 1.f);
 }
 
 // ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th), src/ORBmatcher.cc:73-157.
@@ -91,20 +168,22 @@ inline void Check(int rc, const char* what)
 template <class FrameT, class MapPointT>
 int SearchByProjection(FrameT& F, const std::vector<MapPointT*>& vpMapPoints, const float th, const float nnratio)
 {
-    std::vector<orbx_kp> kps; FlattenKeys(F.mvKeysUn, kps);
-    std::vector<unsigned char> desc; FlattenDescriptors(F.mDescriptors, (int)kps.size(), desc);
-    const orbm_frame view = View(F, kps, desc, true);
+    const orbm_frame view = Resident(F, true);
+    const size_t nk = F.mvKeysUn.size();
     // map points already attached to the frame but not in the list still block their keypoint when
     // Observations()>0 (:115-117): they ride along as extra, never-queried entries
     std::vector<MapPointT*> pts(vpMapPoints.begin(), vpMapPoints.end());
-    std::map<MapPointT*, int> index;
-    for (size_t i = 0; i < pts.size(); ++i) index.insert(std::make_pair(pts[i], (int)i));
     const int nq = (int)pts.size();
-    std::vector<int> init(kps.size(), -1);
-    for (size_t k = 0; k < kps.size(); ++k) {
+    std::vector<int> init(nk, -1);
+    std::unordered_map<MapPointT*, int> index;                      // built only when some keypoint has a point attached
+    for (size_t k = 0; k < nk; ++k) {
         MapPointT* p = F.mvpMapPoints[k];
         if (!p) continue;
-        typename std::map<MapPointT*, int>::iterator it = index.find(p);
+        if (index.empty()) {
+            index.reserve(2 * pts.size() + nk);
+            for (size_t i = 0; i < pts.size(); ++i) index.insert(std::make_pair(pts[i], (int)i));   // first occurrence wins, as with std::map
+        }
+        typename std::unordered_map<MapPointT*, int>::iterator it = index.find(p);
         if (it == index.end()) { it = index.insert(std::make_pair(p, (int)pts.size())).first; pts.push_back(p); }
         init[k] = it->second;
     }
@@ -122,12 +201,12 @@ int SearchByProjection(FrameT& F, const std::vector<MapPointT*>& vpMapPoints, co
         proj[3 * i] = p->mTrackProjX; proj[3 * i + 1] = p->mTrackProjY; proj[3 * i + 2] = p->mTrackProjXR;
         if (inView[i] && !bad[i]) std::memcpy(&qdesc[32 * i], p->GetDescriptor().ptr(0), 32);
     }
-    std::vector<int> assign(kps.size(), -1);
+    std::vector<int> assign(nk, -1);
     int nmatches = 0;
     Check(orbm_search_by_projection_points(&view, &F.mvScaleFactors[0], (int)F.mvScaleFactors.size(), (int)n, Ptr(proj), Ptr(level), Ptr(viewCos),
                                            Ptr(inView), Ptr(bad), Ptr(obs), &qdesc[0], Ptr(init), Ptr(assign), th, nnratio,
                                            &nmatches, Device()), "orbm_search_by_projection_points");
-    for (size_t k = 0; k < kps.size(); ++k) if (assign[k] >= 0) F.mvpMapPoints[k] = pts[(size_t)assign[k]];
+    for (size_t k = 0; k < nk; ++k) if (assign[k] >= 0) F.mvpMapPoints[k] = pts[(size_t)assign[k]];
     return nmatches;
 }
 
@@ -137,9 +216,8 @@ int SearchByProjection(FrameT& F, const std::vector<MapPointT*>& vpMapPoints, co
 template <class FrameT>
 int SearchByProjection(FrameT& Cur, const FrameT& Last, const float th, const bool bMono, const bool checkOri)
 {
-    std::vector<orbx_kp> kps; FlattenKeys(Cur.mvKeysUn, kps);
-    std::vector<unsigned char> desc; FlattenDescriptors(Cur.mDescriptors, (int)kps.size(), desc);
-    const orbm_frame view = View(Cur, kps, desc, true);
+    const orbm_frame view = Resident(Cur, true);
+    const size_t nk = Cur.mvKeysUn.size();
     const int nl = Last.N;
     std::vector<orbx_kp> lk; FlattenKeys(Last.mvKeysUn, lk);
     for (int i = 0; i < nl; ++i) lk[(size_t)i].octave = Last.mvKeys[(size_t)i].octave;   // :211 uses mvKeys for the octave
@@ -157,14 +235,14 @@ int SearchByProjection(FrameT& Cur, const FrameT& Last, const float th, const bo
     float Tc[16], Tl[16];
     for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) { Tc[4 * r + c] = Cur.mTcw.template at<float>(r, c); Tl[4 * r + c] = Last.mTcw.template at<float>(r, c); }
     const float K[4] = { FrameT::fx, FrameT::fy, FrameT::cx, FrameT::cy };
-    std::vector<int> initObs(kps.size(), -1), assign(kps.size(), -1);
-    for (size_t k = 0; k < kps.size(); ++k) if (Cur.mvpMapPoints[k]) initObs[k] = Cur.mvpMapPoints[k]->Observations();
+    std::vector<int> initObs(nk, -1), assign(nk, -1);
+    for (size_t k = 0; k < nk; ++k) if (Cur.mvpMapPoints[k]) initObs[k] = Cur.mvpMapPoints[k]->Observations();
     int nmatches = 0;
     Check(orbm_search_by_projection_frame(&view, nl, lk.empty() ? 0 : &lk[0], &hasMp[0], &outlier[0], &xyz[0], &mdesc[0], &mobs[0], Tc, Tl, K, Cur.mbf,
                                           &Cur.mvScaleFactors[0], (int)Cur.mvScaleFactors.size(), Ptr(initObs),
                                           Ptr(assign), th, bMono ? 1 : 0, checkOri ? 1 : 0, &nmatches, Device()),
           "orbm_search_by_projection_frame");
-    for (size_t k = 0; k < kps.size(); ++k) {
+    for (size_t k = 0; k < nk; ++k) {
         if (assign[k] >= 0) Cur.mvpMapPoints[k] = Last.mvpMapPoints[(size_t)assign[k]];
         else if (assign[k] == -1) Cur.mvpMapPoints[k] = 0;
     }
@@ -179,9 +257,8 @@ template <class FrameT, class KeyFrameT, class MapPointT>
 int SearchByProjection(FrameT& Cur, KeyFrameT* pKF, const std::set<MapPointT*>& sAlreadyFound, const float th, const int ORBdist,
                        const bool checkOri)
 {
-    std::vector<orbx_kp> kps; FlattenKeys(Cur.mvKeysUn, kps);
-    std::vector<unsigned char> desc; FlattenDescriptors(Cur.mDescriptors, (int)kps.size(), desc);
-    const orbm_frame view = View(Cur, kps, desc, false);
+    const orbm_frame view = Resident(Cur, false);
+    const size_t nk = Cur.mvKeysUn.size();
     float T[16];
     for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) T[4 * r + c] = Cur.mTcw.template at<float>(r, c);
     float Ow[3];
@@ -222,13 +299,13 @@ int SearchByProjection(FrameT& Cur, KeyFrameT* pKF, const std::set<MapPointT*>& 
         qangle[i] = pKF->mvKeysUn[i].angle;
         std::memcpy(&qdesc[32 * i], pMP->GetDescriptor().ptr(0), 32);
     }
-    std::vector<int> initObs(kps.size(), -1), assign(kps.size(), -1);
-    for (size_t k = 0; k < kps.size(); ++k) if (Cur.mvpMapPoints[k]) initObs[k] = 1;   // any attached point blocks (:373-374)
+    std::vector<int> initObs(nk, -1), assign(nk, -1);
+    for (size_t k = 0; k < nk; ++k) if (Cur.mvpMapPoints[k]) initObs[k] = 1;   // any attached point blocks (:373-374)
     int nmatches = 0;
     Check(orbm_window_search_best(&view, (int)nq, &uvr[0], &minl[0], &maxl[0], 0, 0, &valid[0], &qdesc[0], &qangle[0], 0,
                                   Ptr(initObs), Ptr(assign), ORBdist, checkOri ? 1 : 0, &nmatches, Device()),
           "orbm_window_search_best");
-    for (size_t k = 0; k < kps.size(); ++k) {
+    for (size_t k = 0; k < nk; ++k) {
         if (assign[k] >= 0) Cur.mvpMapPoints[k] = vpMPs[(size_t)assign[k]];
         else if (assign[k] == -1) Cur.mvpMapPoints[k] = 0;
     }
@@ -247,11 +324,8 @@ template <class KeyFrameT, class MatT, class MapPointT>
 int SearchByProjection(KeyFrameT* pKF, const MatT& Scw, const std::vector<MapPointT*>& vpPoints, std::vector<MapPointT*>& vpMatched, int th)
 {
     const int TH_LOW = 50;                                                               // src/ORBmatcher.cc:38
-    std::vector<orbx_kp> kps; FlattenKeys(pKF->mvKeysUn, kps);
-    std::vector<unsigned char> desc; FlattenDescriptors(pKF->mDescriptors, (int)kps.size(), desc);
-    orbm_frame view;
-    view.n = (int)kps.size(); view.kps = kps.empty() ? 0 : &kps[0]; view.desc = &desc[0]; view.u_right = 0;
-    view.min_x = (float)pKF->mnMinX; view.max_x = (float)pKF->mnMaxX; view.min_y = (float)pKF->mnMinY; view.max_y = (float)pKF->mnMaxY;
+    const orbm_frame view = ResidentKF(pKF, true);
+    const size_t nk = pKF->mvKeysUn.size();
     const float fx = pKF->fx, fy = pKF->fy, cx = pKF->cx, cy = pKF->cy;
     float S[12];
     for (int r = 0; r < 3; ++r) for (int c = 0; c < 4; ++c) S[4 * r + c] = Scw.template at<float>(r, c);
@@ -306,13 +380,13 @@ int SearchByProjection(KeyFrameT* pKF, const MatT& Scw, const std::vector<MapPoi
         minl[i] = lvl - 1; maxl[i] = lvl; valid[i] = 1;
         std::memcpy(&qdesc[32 * i], pMP->GetDescriptor().ptr(0), 32);
     }
-    std::vector<int> initObs(kps.size(), -1), assign(kps.size(), -1);
-    for (size_t k = 0; k < kps.size(); ++k) if (vpMatched[k]) initObs[k] = 1;
+    std::vector<int> initObs(nk, -1), assign(nk, -1);
+    for (size_t k = 0; k < nk; ++k) if (vpMatched[k]) initObs[k] = 1;
     int nmatches = 0;
     Check(orbm_window_search_best(&view, (int)nq, &uvr[0], &minl[0], &maxl[0], 0, 0, &valid[0], &qdesc[0], 0, 0,
                                   Ptr(initObs), Ptr(assign), TH_LOW, 0, &nmatches, Device()),
           "orbm_window_search_best");
-    for (size_t k = 0; k < kps.size(); ++k) if (assign[k] >= 0) vpMatched[k] = vpPoints[(size_t)assign[k]];
+    for (size_t k = 0; k < nk; ++k) if (assign[k] >= 0) vpMatched[k] = vpPoints[(size_t)assign[k]];
     return nmatches;
 }
 
@@ -321,17 +395,16 @@ template <class FrameT, class Point2fT>
 int SearchForInitialization(FrameT& F1, FrameT& F2, std::vector<Point2fT>& vbPrevMatched, std::vector<int>& vnMatches12,
                             int windowSize, const float nnratio, const bool checkOri)
 {
-    std::vector<orbx_kp> k1, k2; FlattenKeys(F1.mvKeysUn, k1); FlattenKeys(F2.mvKeysUn, k2);
-    std::vector<unsigned char> d1, d2; FlattenDescriptors(F1.mDescriptors, (int)k1.size(), d1); FlattenDescriptors(F2.mDescriptors, (int)k2.size(), d2);
-    const orbm_frame v1 = View(F1, k1, d1, false), v2 = View(F2, k2, d2, false);
-    std::vector<float> prev(2 * (k1.size() ? k1.size() : 1), 0.f);
-    for (size_t i = 0; i < k1.size(); ++i) { prev[2 * i] = vbPrevMatched[i].x; prev[2 * i + 1] = vbPrevMatched[i].y; }
-    vnMatches12.assign(k1.size(), -1);
+    const orbm_frame v1 = Resident(F1, false), v2 = Resident(F2, false);
+    const size_t n1 = F1.mvKeysUn.size();
+    std::vector<float> prev(2 * (n1 ? n1 : 1), 0.f);
+    for (size_t i = 0; i < n1; ++i) { prev[2 * i] = vbPrevMatched[i].x; prev[2 * i + 1] = vbPrevMatched[i].y; }
+    vnMatches12.assign(n1, -1);
     int nmatches = 0;
-    std::vector<int> m12(k1.size() ? k1.size() : 1, -1);
+    std::vector<int> m12(n1 ? n1 : 1, -1);
     Check(orbm_search_for_initialization(&v1, &v2, &prev[0], &m12[0], windowSize, nnratio, checkOri ? 1 : 0, &nmatches, Device()),
           "orbm_search_for_initialization");
-    for (size_t i = 0; i < k1.size(); ++i) { vnMatches12[i] = m12[i]; vbPrevMatched[i].x = prev[2 * i]; vbPrevMatched[i].y = prev[2 * i + 1]; }
+    for (size_t i = 0; i < n1; ++i) { vnMatches12[i] = m12[i]; vbPrevMatched[i].x = prev[2 * i]; vbPrevMatched[i].y = prev[2 * i + 1]; }
     return nmatches;
 }
 
@@ -361,18 +434,20 @@ int SearchByBoW(KeyFrameT* pKF, FrameT& F, std::vector<MapPointT*>& vpMapPointMa
 {
     const std::vector<MapPointT*> vpMapPointsKF = pKF->GetMapPointMatches();
     vpMapPointMatches = std::vector<MapPointT*>((size_t)F.N, static_cast<MapPointT*>(0));
-    std::vector<orbx_kp> ka, kb; FlattenKeys(pKF->mvKeysUn, ka); FlattenKeys(F.mvKeys, kb);
-    std::vector<unsigned char> da, db; FlattenDescriptors(pKF->mDescriptors, (int)ka.size(), da); FlattenDescriptors(F.mDescriptors, (int)kb.size(), db);
-    orbm_frame va = { (int)ka.size(), ka.empty() ? 0 : &ka[0], &da[0], 0, 0, 1, 0, 1 }, vb = { (int)kb.size(), kb.empty() ? 0 : &kb[0], &db[0], 0, 0, 1, 0, 1 };
+    // (the reference reads F.mvKeys here, :655, but only its angle, which UndistortKeyPoints leaves as it is, src/Frame.cc:425-466)
+    const orbm_frame va = ResidentKF(pKF, false);
+    orbm_frame vb = Resident(F, false);
+    vb.min_x = 0.f; vb.max_x = 1.f; vb.min_y = 0.f; vb.max_y = 1.f;
+    const size_t na = pKF->mvKeysUn.size();
     std::vector<int> ia, oa, fa, ib, ob, fb;
     FlattenFeatureVector(pKF->mFeatVec, ia, oa, fa); FlattenFeatureVector(F.mFeatVec, ib, ob, fb);
-    std::vector<unsigned char> valid; ValidPoints(vpMapPointsKF, ka.size(), valid);
-    std::vector<int> m12(ka.size() ? ka.size() : 1, -1);
+    std::vector<unsigned char> valid; ValidPoints(vpMapPointsKF, na, valid);
+    std::vector<int> m12(na ? na : 1, -1);
     int nmatches = 0;
     Check(orbm_search_by_bow(&va, &valid[0], (int)ia.size(), ia.empty() ? 0 : &ia[0], &oa[0], fa.empty() ? 0 : &fa[0],
                              &vb, 0, (int)ib.size(), ib.empty() ? 0 : &ib[0], &ob[0], fb.empty() ? 0 : &fb[0],
                              0, nnratio, checkOri ? 1 : 0, &m12[0], &nmatches, Device()), "orbm_search_by_bow");
-    for (size_t i = 0; i < ka.size(); ++i) if (m12[i] >= 0) vpMapPointMatches[(size_t)m12[i]] = vpMapPointsKF[i];
+    for (size_t i = 0; i < na; ++i) if (m12[i] >= 0) vpMapPointMatches[(size_t)m12[i]] = vpMapPointsKF[i];
     return nmatches;
 }
 
@@ -382,18 +457,17 @@ int SearchByBoW(KeyFrameT* pKF1, KeyFrameT* pKF2, std::vector<MapPointT*>& vpMat
 {
     const std::vector<MapPointT*> p1 = pKF1->GetMapPointMatches(), p2 = pKF2->GetMapPointMatches();
     vpMatches12 = std::vector<MapPointT*>(p1.size(), static_cast<MapPointT*>(0));
-    std::vector<orbx_kp> ka, kb; FlattenKeys(pKF1->mvKeysUn, ka); FlattenKeys(pKF2->mvKeysUn, kb);
-    std::vector<unsigned char> da, db; FlattenDescriptors(pKF1->mDescriptors, (int)ka.size(), da); FlattenDescriptors(pKF2->mDescriptors, (int)kb.size(), db);
-    orbm_frame va = { (int)ka.size(), ka.empty() ? 0 : &ka[0], &da[0], 0, 0, 1, 0, 1 }, vb = { (int)kb.size(), kb.empty() ? 0 : &kb[0], &db[0], 0, 0, 1, 0, 1 };
+    const orbm_frame va = ResidentKF(pKF1, false), vb = ResidentKF(pKF2, false);
+    const size_t na = pKF1->mvKeysUn.size(), nb = pKF2->mvKeysUn.size();
     std::vector<int> ia, oa, fa, ib, ob, fb;
     FlattenFeatureVector(pKF1->mFeatVec, ia, oa, fa); FlattenFeatureVector(pKF2->mFeatVec, ib, ob, fb);
-    std::vector<unsigned char> v1, v2; ValidPoints(p1, ka.size(), v1); ValidPoints(p2, kb.size(), v2);
-    std::vector<int> m12(ka.size() ? ka.size() : 1, -1);
+    std::vector<unsigned char> v1, v2; ValidPoints(p1, na, v1); ValidPoints(p2, nb, v2);
+    std::vector<int> m12(na ? na : 1, -1);
     int nmatches = 0;
     Check(orbm_search_by_bow(&va, &v1[0], (int)ia.size(), ia.empty() ? 0 : &ia[0], &oa[0], fa.empty() ? 0 : &fa[0],
                              &vb, &v2[0], (int)ib.size(), ib.empty() ? 0 : &ib[0], &ob[0], fb.empty() ? 0 : &fb[0],
                              1, nnratio, checkOri ? 1 : 0, &m12[0], &nmatches, Device()), "orbm_search_by_bow");
-    for (size_t i = 0; i < ka.size() && i < p1.size(); ++i) if (m12[i] >= 0) vpMatches12[i] = p2[(size_t)m12[i]];
+    for (size_t i = 0; i < na && i < p1.size(); ++i) if (m12[i] >= 0) vpMatches12[i] = p2[(size_t)m12[i]];
     return nmatches;
 }
 

@@ -26,7 +26,10 @@ struct MapPointT {
 };
 #include <map>
 struct FeatVecT : std::map<unsigned int, std::vector<unsigned int> > {};
+static unsigned long NextFrameId() { static unsigned long n = 0; return n++; }   // Frame::nNextId++ (src/Frame.cc:213)
 struct FrameT {
+    long unsigned int mnId; double mTimeStamp;                                     // include/Frame.h:120,131
+    FrameT() : mnId(NextFrameId()), mTimeStamp(0.0) {}
     int N, mnScaleLevels; float mbf, mb, mfScaleFactor;
     FeatVecT mFeatVec;
     std::vector<cv::KeyPoint> mvKeys, mvKeysUn;
@@ -37,6 +40,8 @@ struct FrameT {
     static float fx, fy, cx, cy, mnMinX, mnMaxX, mnMinY, mnMaxY;
 };
 struct KeyFrameT {
+    long unsigned int mnFrameId; double mTimeStamp;                                // include/KeyFrame.h:128,130: the id of the Frame it was made from
+    KeyFrameT() : mnFrameId(NextFrameId()), mTimeStamp(0.0) {}
     float fx, fy, cx, cy; int mnMinX, mnMinY, mnMaxX, mnMaxY;
     cv::Mat mDescriptors;
     FeatVecT mFeatVec;
@@ -78,6 +83,7 @@ extern "C" int matcher_forwarders_instantiate(int run)
 #ifndef WITH_REFERENCE_HEADERS
 // ---- runtime entry points for pytest (GPU): objects of the stand-in types are filled from arrays and handed to the
 // forwarders exactly as the patched ORBmatcher.cc / Tracking.cc / MapPoint.cc would hand over the SLAM system's own.
+#include <chrono>
 #include <cstring>
 namespace {
 struct Kp { float x, y, size, angle, response; int octave, class_id; };
@@ -127,6 +133,43 @@ int fwd_search_by_projection_points(int n, const Kp* kps, const unsigned char* d
     const int nm = ORB_SLAM2::b200::SearchByProjection(F, pts, th, nnratio);
     for (int k = 0; k < n; ++k) assign_out[k] = F.mvpMapPoints[k] ? (int)(F.mvpMapPoints[k] - &store[0]) : -1;
     return nm;
+}
+
+// One Frame, `calls` searches: how many uploads the forwarders' device-side frame cache needed (1 when it works) and
+// whether every call returned the same matches; seconds[0] / seconds[1] = host time of the first call / mean of the rest.
+int fwd_resident_reuse(int calls, int n, const Kp* kps, const unsigned char* desc, const float* scale, int nlevels,
+                       float minX, float maxX, float minY, float maxY, int nq, const float* proj, const int* level,
+                       const float* view_cos, const unsigned char* qdesc, int* nmatches_out, double* seconds)
+{
+    FrameT F;
+    F.N = n;
+    fill_keys(F.mvKeysUn, kps, n); F.mvKeys = F.mvKeysUn;
+    fill_desc(F.mDescriptors, desc, n);
+    F.mvuRight.assign(n, -1.f);
+    F.mvScaleFactors.assign(scale, scale + nlevels);
+    FrameT::mnMinX = minX; FrameT::mnMaxX = maxX; FrameT::mnMinY = minY; FrameT::mnMaxY = maxY;
+    std::vector<MapPointT> store(nq > 0 ? nq : 1);
+    std::vector<MapPointT*> pts(nq);
+    for (int i = 0; i < nq; ++i) {
+        MapPointT& m = store[i];
+        m.mbTrackInView = true; m.bad = false; m.mnTrackScaleLevel = level[i]; m.nObs = 1;
+        m.mTrackViewCos = view_cos[i]; m.mTrackProjX = proj[3 * i]; m.mTrackProjY = proj[3 * i + 1]; m.mTrackProjXR = proj[3 * i + 2];
+        fill_desc(m.descriptor, qdesc + 32 * (size_t)i, 1);
+        pts[i] = &m;
+    }
+    ORB_SLAM2::b200::ResidentFrames& cache = ORB_SLAM2::b200::ResidentFrames::Local();
+    const unsigned long before = cache.Uploads();
+    int first = -1, same = 1;
+    seconds[0] = seconds[1] = 0.0;
+    for (int c = 0; c < calls; ++c) {
+        F.mvpMapPoints.assign(n, static_cast<MapPointT*>(0));
+        const std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+        const int nm = ORB_SLAM2::b200::SearchByProjection(F, pts, 3.0f, 0.8f);
+        const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        if (c == 0) { first = nm; seconds[0] = dt; } else { seconds[1] += dt / (calls - 1); if (nm != first) same = 0; }
+    }
+    *nmatches_out = first;
+    return same ? (int)(cache.Uploads() - before) : -1;
 }
 
 // both ORBmatcher::SearchByBoW overloads through b200::SearchByBoW; match12 [n1] = feature of side 2 or -1

@@ -139,3 +139,26 @@ def test_matcher_forwarders_run_like_the_patched_reference(dropin):
     M.fwd_distinctive.argtypes = [vp, ci]
     for d, _ in descriptor_groups(2, sizes=(1, 5, 33, 120)):
         assert M.fwd_distinctive(p(d), len(d)) == distinctive("oracle", d)[1]
+
+
+@pytest.mark.gpu
+def test_matcher_forwarders_keep_a_frame_on_the_device(dropin):
+    """The forwarders upload a Frame once (b200::ResidentFrames, keyed by Frame::mnId) and every further search of that
+    Frame reuses the device copy: one upload for five SearchByProjection calls, identical results, and the CPU checker's."""
+    from matcher_lib import Matcher, extract_frame, perturbed_frame, projected_queries
+    M = C.CDLL(os.path.join(CPP, "_build", "libmatcher_fwd.so"))
+    vp, ci, cf = C.c_void_p, C.c_int, C.c_float
+    p = lambda a: a.ctypes.data
+    W, H = 1241, 376
+    bounds = (0.0, float(W), 0.0, float(H))
+    kps, desc, scale = extract_frame(W, H, 2000, 2)
+    k2, d2, _ = perturbed_frame(kps, desc, W, H, 11)
+    q = projected_queries(k2, d2, 1500, 5)
+    q["in_view"][:] = 1; q["bad"][:] = 0; q["obs"][:] = 1
+    nm, secs = C.c_int(), (C.c_double * 2)()
+    M.fwd_resident_reuse.argtypes = [ci, ci, vp, vp, vp, ci] + [cf] * 4 + [ci] + [vp] * 6
+    uploads = M.fwd_resident_reuse(5, len(k2), p(k2), p(d2), p(scale), len(scale), *bounds, 1500, p(q["proj"]), p(q["level"]),
+                                   p(q["view_cos"]), p(q["desc"]), C.addressof(nm), C.addressof(secs))
+    want = Matcher("oracle").search_by_projection_points(k2, d2, np.full(len(k2), -1, np.float32), scale, bounds, q, 3.0, 0.8, None)
+    assert uploads == 1 and nm.value == want[0] and nm.value > 300
+    print(f"SearchByProjection through the forwarder: first call {secs[0] * 1e3:.3f} ms, later calls {secs[1] * 1e3:.3f} ms")

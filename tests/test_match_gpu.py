@@ -404,3 +404,46 @@ def test_device_grid_returns_candidates_in_reference_order(scene):
         assert cnt[q] == len(want) and (idx[q, :cnt[q]] == want).all(), q
         nonempty += len(want) > 1
     assert nonempty > 200
+
+
+def test_resident_frame_gives_the_same_results_as_host_frames(scene):
+    """orbm_frame_upload / orbm_frame_view: a Frame uploaded once serves every search of that Frame (Tracking runs two to
+    four per Frame) with results identical to the host-pointer path and to the CPU checker; mono views of a stereo frame
+    (u_right nulled in the caller's copy of the view), an empty frame and repeated use of one handle are covered."""
+    O = Matcher("oracle")
+    rng = np.random.default_rng(6)
+    n = len(scene["k2"])
+    ur = np.where(rng.random(n) < 0.5, scene["k2"]["x"] - 20 * rng.random(n), -1).astype(np.float32)
+    R = ob.ResidentFrame(scene["k2"], scene["d2"], BOUNDS, ur)
+    H = ob.FrameView(scene["k2"], scene["d2"], BOUNDS, ur)
+    M = ob.ORBmatcher(0.8, True)
+    # 1. SearchByProjection(Frame, MapPoints), twice on the same handle with different query sets
+    for seed, th in ((5, 3.0), (9, 5.0)):
+        q = projected_queries(scene["k2"], scene["d2"], 2000, seed)
+        a = O.search_by_projection_points(scene["k2"], scene["d2"], ur, scene["scale"], BOUNDS, q, th, 0.8, None)
+        b = M.SearchByProjection(R, scene["scale"], q, th)
+        c = M.SearchByProjection(H, scene["scale"], q, th)
+        assert a[0] == b[0] == c[0] and a[0] > 300 and (a[1] == b[1]).all() and (b[1] == c[1]).all()
+    # 2. the best-candidate-only search on the same handle (relocalisation / loop closing shape: no right coordinates)
+    k, d = scene["k2"], scene["d2"]
+    nq = 1200
+    pick = rng.integers(0, n, nq)
+    uvr = np.stack([k["x"][pick] + rng.normal(0, 2, nq), k["y"][pick] + rng.normal(0, 2, nq), np.full(nq, 12.0)], 1).astype(np.float32)
+    minl = np.maximum(k["octave"][pick] - 1, 0).astype(np.int32)
+    maxl = (k["octave"][pick] + 1).astype(np.int32)
+    qd = d[pick].copy()
+    g1 = ob.window_search_best(R, uvr, minl, maxl, qd, 100, False)
+    g2 = ob.window_search_best(H, uvr, minl, maxl, qd, 100, False)
+    assert g1[0] == g2[0] and g1[0] > 200 and (g1[1] == g2[1]).all()
+    # 3. SearchForInitialization with both frames resident
+    prev = np.stack([scene["kps"]["x"], scene["kps"]["y"]], 1)
+    R1 = ob.ResidentFrame(scene["kps"], scene["desc"], BOUNDS)
+    a = O.search_for_initialization(scene["kps"], scene["desc"], scene["k2"], scene["d2"], scene["scale"], BOUNDS, prev, 100, 0.9, True)
+    b = ob.ORBmatcher(0.9, True).SearchForInitialization(R1, ob.ResidentFrame(scene["k2"], scene["d2"], BOUNDS), prev, 100)
+    assert a[0] == b[0] and (a[1] == b[1]).all() and (a[2] == b[2]).all()
+    # 4. an empty frame can be uploaded and searched (0 matches, as the reference on a black image)
+    R0 = ob.ResidentFrame(np.zeros(0, KP_DTYPE), np.zeros((0, 32), np.uint8), BOUNDS)
+    q = projected_queries(scene["k2"], scene["d2"], 50, 5)
+    assert M.SearchByProjection(R0, scene["scale"], q, 3.0)[0] == 0
+    for r in (R, R1, R0):
+        r.close()
