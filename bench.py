@@ -415,6 +415,17 @@ def bench_window_match(dev, d_kps, d_desc, d_n, cap, w, h, scale, nprob=512, nq=
     for _ in range(nrep):
         M1.SearchByProjection(F1, scale, q1, th)
     out["single_call_ms"] = 1e3 * (time.perf_counter() - t0) / nrep
+    # the same with the Frame already on the device (orbm_frame_upload): the 2nd .. 4th search Tracking runs on a Frame
+    R1 = ob.ResidentFrame(F1.kps, F1.desc, bounds)
+    for _ in range(min(5, nrep)):
+        res_r = M1.SearchByProjection(R1, scale, q1, th)
+    t0 = time.perf_counter()
+    for _ in range(nrep):
+        res_r = M1.SearchByProjection(R1, scale, q1, th)
+    out["single_call_resident_frame_ms"] = 1e3 * (time.perf_counter() - t0) / nrep
+    res_h = M1.SearchByProjection(F1, scale, q1, th)
+    assert res_r[0] == res_h[0] and (res_r[1] == res_h[1]).all(), "resident-frame search differs from the host-frame search"
+    R1.close()
     if cpu:
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import oracle_lib

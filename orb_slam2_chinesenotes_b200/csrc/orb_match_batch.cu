@@ -317,16 +317,31 @@ __global__ void __launch_bounds__(MB_NT) k_match_fixpoint(const __grid_constant_
                     myd0 = __ldg(qd); myd1 = __ldg(qd + 1);
                 } else if (st_best[q] & 0xffffu) { st_best[q] = 0; st_top[q] = MB_NONE; s_flag[par] = 1; }   // cannot happen: validity is fixed
             }
-            // groups of MB_G lanes, each working through the MB_G queries its own lanes fetched
+            // groups of MB_G lanes; the queries of this pass that need work are dealt to the groups in turn (the i-th of them
+            // to group i % (32 / MB_G)), so that after round 0, when only a few of the 32 do, the warp makes one or two trips
+            // instead of MB_G nearly empty ones
             const bool go = need && myQ.valid;
-            if (!__any_sync(0xffffffffu, go)) continue;
+            const unsigned gomask = __ballot_sync(0xffffffffu, go);
+            if (!gomask) continue;
+            const int ngo = __popc(gomask);
             const int sub = lane & (MB_G - 1), g0 = lane & ~(MB_G - 1);
             const unsigned gmask = ((1u << MB_G) - 1u) << g0;
-            for (int i = 0; i < MB_G; ++i) {
-                const int src = g0 + i, qq = base + src;
+            for (int i0 = 0; i0 < ngo; i0 += 32 / MB_G) {
+                // lane of this group's query = position of the k-th set bit of gomask (binary search with popc; __fns is a loop)
+                int k = i0 + lane / MB_G, src = 0;
+                const bool have = k < ngo;
+                {
+                    unsigned m = gomask;
+                    int c = __popc(m & 0xffffu); if (k >= c) { k -= c; src += 16; m >>= 16; }
+                    c = __popc(m & 0xffu);       if (k >= c) { k -= c; src += 8; m >>= 8; }
+                    c = __popc(m & 0xfu);        if (k >= c) { k -= c; src += 4; m >>= 4; }
+                    c = __popc(m & 0x3u);        if (k >= c) { k -= c; src += 2; m >>= 2; }
+                    c = (int)(m & 1u);           if (k >= c) src += 1;
+                }
+                if (!have) src = 0;
+                const int qq = base + src;
                 WinQ Q;
-                Q.valid = __shfl_sync(0xffffffffu, (int)go, src);
-                if (!__any_sync(0xffffffffu, Q.valid)) continue;
+                Q.valid = have;
                 Q.u = __shfl_sync(0xffffffffu, myQ.u, src); Q.v = __shfl_sync(0xffffffffu, myQ.v, src); Q.r = __shfl_sync(0xffffffffu, myQ.r, src);
                 Q.ur = __shfl_sync(0xffffffffu, myQ.ur, src); Q.er_max = __shfl_sync(0xffffffffu, myQ.er_max, src);
                 Q.min_level = __shfl_sync(0xffffffffu, myQ.min_level, src); Q.max_level = __shfl_sync(0xffffffffu, myQ.max_level, src);

@@ -42,6 +42,14 @@ t0 = time.perf_counter()
 for _ in range(50):
     nm, a = M.SearchByProjection(F, scale, q, 3.0)
 t_m = (time.perf_counter() - t0) / 50
+R = ob.ResidentFrame(kps, desc, bounds)
+for _ in range(5):
+    M.SearchByProjection(R, scale, q, 3.0)
+t0 = time.perf_counter()
+for _ in range(50):
+    nm_r, a_r = M.SearchByProjection(R, scale, q, 3.0)
+t_mr = (time.perf_counter() - t0) / 50
+assert nm_r == nm and (a_r == a).all()
 O = OracleExtractor(nf)
 t0 = time.perf_counter(); O.extract(img); t_cpu_ex = time.perf_counter() - t0
 Mo = Matcher("oracle")
@@ -62,5 +70,5 @@ hd = D.dropin_create(nf, 1.2, 8, 20, 7)
 t_drop_pyr = D.dropin_time_ms(hd, img.ctypes.data, w, h, img.strides[0], 50, 1)
 t_drop = D.dropin_time_ms(hd, img.ctypes.data, w, h, img.strides[0], 50, 0)
 print({"dropin_operator_ms": t_drop_pyr, "dropin_operator_no_pyramid_ms": t_drop})
-print({"extract_1_frame_ms": t_ex * 1e3, "stereo_pair_ms": t_st * 1e3, "search_by_projection_ms": t_m * 1e3,
+print({"extract_1_frame_ms": t_ex * 1e3, "stereo_pair_ms": t_st * 1e3, "search_by_projection_ms": t_m * 1e3, "search_by_projection_resident_frame_ms": t_mr * 1e3,
        "cpu_extract_1_frame_ms": t_cpu_ex * 1e3, "cpu_search_by_projection_ms": t_cpu_m * 1e3, "nmatches": nm})
