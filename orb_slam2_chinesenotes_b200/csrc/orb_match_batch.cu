@@ -32,6 +32,7 @@
 // that order doubles as the tie-break of the reference's running best/second-best ("two smallest by
 // (distance, position)").
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 #include <stdint.h>
 
 #include <climits>
@@ -230,15 +231,29 @@ __device__ __forceinline__ void mb_sort_frame(const MbParams& P, const orbx_kp* 
 // LOC: where the sorted records / descriptors live -- 0: both in shared memory, 1: records in shared memory,
 // descriptors in the global workspace, 2: both global.  A template parameter so that the loads of the window walk
 // are LDS, not generic loads.
-template <int MODE, int LOC>
+// CL: blocks per problem.  1: many problems per launch, one block each.  MB_CLUSTER (LOC 0 only): ONE problem spread over a
+// thread-block cluster -- what a tracker's single SearchByProjection call is, where one block leaves 147 SMs idle while it
+// walks 2000 windows.  Every block of the cluster sorts its own copy of the frame (redundant, but parallel); the queries are
+// dealt to the warps of all blocks (32 / MB_G per warp and pass, i.e. one per lane group); a query's state lives in the
+// shared memory of the block that owns it and the others read it over distributed shared memory when they rebuild their
+// copy of the blocker array; two cluster barriers per round; block 0 collects the decisions and writes the results.
+#ifndef MB_CLUSTER
+#define MB_CLUSTER 8
+#endif
+template <int MODE, int LOC, int CL>
 __global__ void __launch_bounds__(MB_NT) k_match_fixpoint(const __grid_constant__ MbParams P)
 {
+    namespace cg = cooperative_groups;
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ int s_flag[3], s_cnt[2], s_sizes[HISTO_LENGTH], s_ind[3];
-    const int prob = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = MB_NT >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = MB_NT >> 5;
+    const int prob = blockIdx.x / CL, crank = CL > 1 ? (int)cg::this_cluster().block_rank() : 0;
+    constexpr int QW = CL > 1 ? 32 / MB_G : 32;            // queries a warp takes per pass
+    const int gw = crank * nwarps + warp, gwn = CL * nwarps;
+    auto owner = [&](const int q) { return ((q / QW) % gwn) / nwarps; };   // cluster rank of the block that holds query q's state
     const int n = P.n[prob], nq = P.nq[prob];
     int* const nm_out = P.nmatches + prob;
-    if (n < 0 || n > P.sn_max || n > P.kp_stride || nq < 0 || nq > P.nq_stride) { if (tid == 0) *nm_out = -1; return; }
+    if (n < 0 || n > P.sn_max || n > P.kp_stride || nq < 0 || nq > P.nq_stride) { if (tid == 0 && crank == 0) *nm_out = -1; return; }
     const size_t ko = (size_t)prob * P.kp_stride, qo = (size_t)prob * P.nq_stride;
     const orbx_kp* kps = P.kps + ko;
     const int* init = P.init ? P.init + ko : nullptr;
@@ -294,10 +309,10 @@ __global__ void __launch_bounds__(MB_NT) k_match_fixpoint(const __grid_constant_
     for (;; ++round) {
         const int par = round & 1;
         const bool unblocked = round > 0 && s_flag[2] != 0;     // some keypoint became free again in the last rebuild
-        for (int base = warp * 32; base < nq; base += nwarps * 32) {
+        for (int base = gw * QW; base < nq; base += gwn * QW) {
             const int q = base + lane;
             bool need = false;
-            if (q < nq) {
+            if (lane < QW && q < nq) {
                 if (round == 0) need = true;
                 else {
                     const uint32_t top = st_top[q], sb = st_best[q];
@@ -375,9 +390,17 @@ __global__ void __launch_bounds__(MB_NT) k_match_fixpoint(const __grid_constant_
                 }
             }
         }
-        __syncthreads();
+        bool changed;
+        if (CL > 1) {
+            cg::this_cluster().sync();                       // every block's decisions of this round are in place
+            changed = false;
+#pragma unroll
+            for (int r = 0; r < CL; ++r) changed |= cg::this_cluster().map_shared_rank(s_flag, r)[par] != 0;
+        } else {
+            __syncthreads();
+            changed = s_flag[par] != 0;
+        }
         if (round < 8) CLK(4 + round);
-        const bool changed = s_flag[par] != 0;
         if (!changed) break;
         // blocker[] from the decisions, into the other buffer; a keypoint whose blocker moved to a LATER query (or
         // went away) is the only thing that can change the result of a query that skipped taken candidates
@@ -386,7 +409,8 @@ __global__ void __launch_bounds__(MB_NT) k_match_fixpoint(const __grid_constant_
         if (tid == 0) { s_flag[par ^ 1] = 0; s_flag[2] = 0; }
         __syncthreads();
         for (int q = tid; q < nq; q += MB_NT) {
-            const int b = (int)(st_best[q] & 0xffffu) - 1;
+            const uint32_t sb = CL > 1 ? cg::this_cluster().map_shared_rank(st_best, owner(q))[q] : st_best[q];
+            const int b = (int)(sb & 0xffffu) - 1;
             if (b >= 0 && (qobs ? qobs[q] : 1) > 0) atomicMin(&nblk[b], q);
         }
         __syncthreads();
@@ -394,7 +418,18 @@ __global__ void __launch_bounds__(MB_NT) k_match_fixpoint(const __grid_constant_
         for (int j = tid; j < nvalid; j += MB_NT) freed |= nblk[j] > blk[j];
         if (freed) s_flag[2] = 1;
         blk = nblk;
-        __syncthreads();
+        if (CL > 1) cg::this_cluster().sync();               // nobody still reads the decisions the next round overwrites
+        else __syncthreads();
+    }
+    if (CL > 1) {
+        // block 0 collects every query's decision and finishes alone; the others stay until it has read them
+        if (crank == 0)
+            for (int q = tid; q < nq; q += MB_NT) {
+                const int o = owner(q);
+                if (o != 0) st_best[q] = cg::this_cluster().map_shared_rank(st_best, o)[q];
+            }
+        cg::this_cluster().sync();
+        if (crank != 0) return;
     }
     if (P.rounds && tid == 0) P.rounds[prob] = round + 1;
 
@@ -679,10 +714,27 @@ template <int MODE, int LOC>
 cudaError_t launch_loc(const MbParams& P, int nprob, size_t smem, cudaStream_t st)
 {
     cudaError_t e = cudaSuccess;
-    // a constant: the attribute is per-function state shared by all host threads (a per-launch value races)
-    if (smem > 48 * 1024) e = cudaFuncSetAttribute(k_match_fixpoint<MODE, LOC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
+    // a handful of problems with everything in shared memory: one thread-block cluster per problem
+    static const bool cluster_on = []{ const char* v = getenv("ORB_MATCH_CLUSTER"); return !(v && v[0] == '0'); }();
+    if (LOC == 0 && MB_CLUSTER > 1 && cluster_on && nprob * MB_CLUSTER <= 144) {
+        // a constant: the attribute is per-function state shared by all host threads (a per-launch value races)
+        e = cudaFuncSetAttribute(k_match_fixpoint<MODE, 0, MB_CLUSTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
+        if (e == cudaSuccess) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)(nprob * MB_CLUSTER)); cfg.blockDim = dim3(MB_NT); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = MB_CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            e = cudaLaunchKernelEx(&cfg, k_match_fixpoint<MODE, 0, MB_CLUSTER>, P);
+            if (e == cudaSuccess) return cudaSuccess;
+        }
+        cudaGetLastError();                                  // the cluster could not be placed: one block per problem instead
+        e = cudaSuccess;
+    }
+    if (smem > 48 * 1024) e = cudaFuncSetAttribute(k_match_fixpoint<MODE, LOC, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
     if (e != cudaSuccess) return e;
-    k_match_fixpoint<MODE, LOC><<<nprob, MB_NT, smem, st>>>(P);
+    k_match_fixpoint<MODE, LOC, 1><<<nprob, MB_NT, smem, st>>>(P);
     return cudaGetLastError();
 }
 
