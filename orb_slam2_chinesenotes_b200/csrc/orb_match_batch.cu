@@ -193,21 +193,68 @@ __device__ long long g_clk[16];
 #endif
 
 // Frame::AssignFeaturesToGrid (src/Frame.cc:243-259) for one frame, by the whole block: the cell of every keypoint
-// (round(), :414-415), keys = cell << 16 | index sorted in shared memory, cell_start[c] = first position of cell c
-// (cell_start[GRID_CELLS] = number of keypoints inside the grid).  Ends with a barrier.
+// (round(), :414-415), keys = cell << 16 | index in the order (grid column, grid row, index), cell_start[c] = first
+// position of cell c (cell_start[GRID_CELLS] = number of keypoints inside the grid).  Ends with a barrier.
+// A counting sort -- cell histogram with shared-memory atomics, exclusive scan over the 3072 cells, scatter, and an
+// insertion sort inside every cell (a cell holds a handful of keypoints) -- with a dozen block barriers where the bitonic
+// sort of 2048 keys needs 66 (measured on one 2000-keypoint frame: 15.1 -> 5.4 us); a frame that crowds more than 32
+// keypoints into one cell takes the bitonic sort.  tmp: sn ints of scratch.
 template <int NT>
-__device__ __forceinline__ void mb_sort_frame(const MbParams& P, const orbx_kp* kps, const int n, const int sn, uint32_t* keys, int* cell_start)
+__device__ __forceinline__ void mb_sort_frame(const MbParams& P, const orbx_kp* kps, const int n, const int sn, uint32_t* keys, int* cell_start, int* tmp)
 {
-    const int tid = threadIdx.x;
-    for (int i = tid; i < sn; i += NT) {
-        uint32_t key = MB_NONE;
-        if (i < n) {
-            const int px = (int)roundf((kps[i].x - P.min_x) * P.inv_w);
-            const int py = (int)roundf((kps[i].y - P.min_y) * P.inv_h);
-            if (!(px < 0 || px >= GRID_COLS || py < 0 || py >= GRID_ROWS)) key = ((uint32_t)(px * GRID_ROWS + py) << 16) | (uint32_t)i;
-        }
-        keys[i] = key;
+    __shared__ int s_scan[NT / 32], s_crowded;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int c = tid; c <= GRID_CELLS; c += NT) cell_start[c] = 0;
+    if (tid == 0) s_crowded = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += NT) {
+        const int px = (int)roundf((kps[i].x - P.min_x) * P.inv_w);
+        const int py = (int)roundf((kps[i].y - P.min_y) * P.inv_h);
+        const int c = (px < 0 || px >= GRID_COLS || py < 0 || py >= GRID_ROWS) ? -1 : px * GRID_ROWS + py;
+        tmp[i] = c;
+        if (c >= 0 && atomicAdd(&cell_start[c], 1) >= 32) s_crowded = 1;
     }
+    __syncthreads();
+    if (!s_crowded) {
+        constexpr int IPT = (GRID_CELLS + NT) / NT;                       // cells per thread, GRID_CELLS + 1 entries in all
+        int v[IPT], sum = 0;
+#pragma unroll
+        for (int k = 0; k < IPT; ++k) { const int c = tid * IPT + k; v[k] = c <= GRID_CELLS ? cell_start[c] : 0; sum += v[k]; }
+        int inc = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+        if (lane == 31) s_scan[wid] = inc;
+        __syncthreads();
+        int run = inc - sum;
+        for (int w = 0; w < wid; ++w) run += s_scan[w];
+#pragma unroll
+        for (int k = 0; k < IPT; ++k) { const int c = tid * IPT + k; if (c <= GRID_CELLS) cell_start[c] = run; run += v[k]; }
+        __syncthreads();
+        // scatter with the start of each cell as its cursor: afterwards cell_start[c] is the END of cell c
+        for (int i = tid; i < n; i += NT) {
+            const int c = tmp[i];
+            if (c >= 0) keys[atomicAdd(&cell_start[c], 1)] = ((uint32_t)c << 16) | (uint32_t)i;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < IPT; ++k) { const int c = tid * IPT + k; v[k] = (c > 0 && c <= GRID_CELLS) ? cell_start[c - 1] : 0; }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < IPT; ++k) { const int c = tid * IPT + k; if (c <= GRID_CELLS) cell_start[c] = v[k]; }
+        __syncthreads();
+        for (int c = tid; c < GRID_CELLS; c += NT) {                       // insertion order inside the cell (:256)
+            const int s0 = cell_start[c], s1 = cell_start[c + 1];
+            for (int i = s0 + 1; i < s1; ++i) {
+                const uint32_t key = keys[i];
+                int j = i - 1;
+                while (j >= s0 && keys[j] > key) { keys[j + 1] = keys[j]; --j; }
+                keys[j + 1] = key;
+            }
+        }
+        __syncthreads();
+        return;
+    }
+    for (int i = tid; i < sn; i += NT) keys[i] = (i < n && tmp[i] >= 0) ? (((uint32_t)tmp[i] << 16) | (uint32_t)i) : MB_NONE;
     __syncthreads();
     for (int k = 2; k <= sn; k <<= 1)
         for (int j = k >> 1; j > 0; j >>= 1) {
@@ -276,7 +323,7 @@ __global__ void __launch_bounds__(MB_NT) k_match_fixpoint(const __grid_constant_
     else { rec = P.rec + ko; sdesc = (uint4*)(P.sdesc + ko * 8); }
 
     CLK(0);
-    mb_sort_frame<MB_NT>(P, kps, n, sn, keys, cell_start);
+    mb_sort_frame<MB_NT>(P, kps, n, sn, keys, cell_start, blk_a);
     const int nvalid = cell_start[GRID_CELLS];
     CLK(2);
     const bool use_ur = P.u_right != nullptr && (MODE == MODE_POINTS || P.f1 != nullptr);
@@ -518,7 +565,7 @@ __global__ void __launch_bounds__(MB_NT) k_init_fixpoint(const __grid_constant__
     else if (LOC == 1) { rec = sm16; sdesc = (uint4*)(P.sdesc + ko * 8); }
     else { rec = P.rec + ko; sdesc = (uint4*)(P.sdesc + ko * 8); }
 
-    mb_sort_frame<MB_NT>(P, kps, n, sn, keys, cell_start);
+    mb_sort_frame<MB_NT>(P, kps, n, sn, keys, cell_start, cnt);
     const int nvalid = cell_start[GRID_CELLS];
     for (int j = tid; j < nvalid; j += MB_NT) {
         const int idx = (int)(keys[j] & 0xffffu);

@@ -447,3 +447,22 @@ def test_resident_frame_gives_the_same_results_as_host_frames(scene):
     assert M.SearchByProjection(R0, scene["scale"], q, 3.0)[0] == 0
     for r in (R, R1, R0):
         r.close()
+
+
+def test_crowded_grid_cell(scene):
+    """The device grid is a counting sort with an insertion sort inside each cell; a frame that crowds more than 32 keypoints
+    into one cell takes the bitonic-sort path instead.  Both give the reference's candidate order: 150 keypoints moved into
+    one 19 x 8 px cell, queries aimed at them."""
+    O = Matcher("oracle")
+    k, d = scene["k2"].copy(), scene["d2"]
+    rng = np.random.default_rng(12)
+    n = len(k)
+    move = rng.choice(n, 150, replace=False)
+    k["x"][move] = 400.0 + rng.random(150).astype(np.float32) * 15.0
+    k["y"][move] = 200.0 + rng.random(150).astype(np.float32) * 6.0
+    q = projected_queries(k, d, 2000, 5)
+    F = ob.FrameView(k, d, BOUNDS)
+    for th in (1.0, 3.0):
+        a = O.search_by_projection_points(k, d, None, scene["scale"], BOUNDS, q, th, 0.9, None)
+        b = ob.ORBmatcher(0.9, True).SearchByProjection(F, scene["scale"], q, th)
+        assert a[0] == b[0] and a[0] > 200 and (a[1] == b[1]).all()
