@@ -25,6 +25,9 @@
 
 namespace {
 
+#ifndef ORB_NCOMP
+#define ORB_NCOMP 3      // compute streams the chunks of the piped path alternate between (<= ORB_NSLOT)
+#endif
 #ifndef ORB_NSLOT
 #define ORB_NSLOT 3
 #endif
@@ -39,8 +42,11 @@ struct DevBuf {
         if (p) cudaFree(p);
         p = nullptr; bytes = 0;
         cudaError_t e = cudaMalloc(&p, n);
-        if (e == cudaSuccess) bytes = n;
-        return e;
+        if (e != cudaSuccess) return e;
+        bytes = n;
+        // fresh device memory holds whatever its last owner left: entries of an output behind n_out are unspecified by
+        // contract, but they should not differ from run to run (a staged output is copied out whole)
+        return cudaMemset(p, 0, n);
     }
     void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
 };
@@ -127,11 +133,15 @@ struct orbx_ctx {
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
     cudaStream_t xstream[NSLOT - 1] = { nullptr };   // extra compute streams (slots 1..)
     cudaEvent_t fork_ev = nullptr, join_ev[NSLOT - 1] = { nullptr };
-    // Frames per internal pass.  With host buffers the chunks are what the copy / compute pipeline overlaps: 64 is the
-    // measured optimum (smaller: launch tails, larger: longer pipeline fill).  With everything device resident there
+    // Frames per internal pass.  With host buffers the chunks are what the copy / compute pipeline overlaps: smaller
+    // chunks cost launch tails (a 64-frame launch list takes 0.71 ms, an eighth of a 512-frame one 0.57 ms), larger ones a
+    // longer pipeline fill and drain; measured end to end with the round-2 kernels on 1024 KITTI frames per call:
+    // 64 / 96 / 128 / 160 frames = 82.6-84.4 / 85.3 / 86.1-86.4 / 83.0 k frames/s (with round 1's slower kernels 64 was the
+    // optimum: 74.4 against 72.0 k).  Slots and compute streams (ORB_NSLOT / ORB_NCOMP = 3/2, 3/1, 4/2, 6/3, 6/2, 8/4) all
+    // measure 80-86 k: the pipeline is not short of buffers.  With everything device resident there
     // is nothing to overlap and bigger launches are simply more efficient (1241x376: 6.66 ms per 512 frames in chunks
     // of 64, 6.03 ms as one chunk), so the chunk only bounds the work buffers (about 2.6 MB per frame at that shape).
-    int chunk = 64, chunk_resident = 512;
+    int chunk = 128, chunk_resident = 512;
     std::string err;
 
     bool have_plan = false;
@@ -424,14 +434,15 @@ int run_batch(orbx_ctx* c, const uint8_t* imgs, size_t frame_stride, int batch, 
         rc = ensure_slot(c, c->slot[s], chunk, cap, !in_dev, in_frame_bytes, stage_out, sr != nullptr);
         if (rc) return rc;
     }
+    const int ncomp = nslot < ORB_NCOMP ? nslot : ORB_NCOMP;   // slot s always runs on stream s % ncomp when ncomp divides nslot; else its events order it
     if (multi) {                                       // fork: the extra streams start after what is already queued
         CU(c, cudaEventRecord(c->fork_ev, c->stream));
-        for (int k = 1; k < nslot; ++k) CU(c, cudaStreamWaitEvent(c->xstream[k - 1], c->fork_ev, 0));
+        for (int k = 1; k < ncomp; ++k) CU(c, cudaStreamWaitEvent(c->xstream[k - 1], c->fork_ev, 0));
     }
     for (int i = 0, f0 = 0; i < nchunks; f0 += sched[i], ++i) {
         const int nf = sched[i];
         Slot& s = c->slot[i % nslot];
-        cudaStream_t st = multi && i % nslot ? c->xstream[i % nslot - 1] : c->stream;
+        cudaStream_t st = multi && i % ncomp ? c->xstream[i % ncomp - 1] : c->stream;
         const uint8_t* d_img; size_t d_stride;
         if (in_dev) { d_img = imgs + (size_t)f0 * frame_stride; d_stride = frame_stride; }
         else {
@@ -452,7 +463,7 @@ int run_batch(orbx_ctx* c, const uint8_t* imgs, size_t frame_stride, int batch, 
         uint8_t* dd = stage_out ? (uint8_t*)s.out_desc.p : desc + (size_t)f0 * cap * 32;
         int* dn = stage_out ? (int*)s.out_n.p : n_out + f0;
         if (stage_out && s.used) CU(c, cudaStreamWaitEvent(st, s.d2h_done, 0));   // output staging still being drained
-        if (!multi && !piped && nslot > 1 && s.used) CU(c, cudaStreamWaitEvent(st, s.compute_done, 0));
+        if (nslot > 1 && s.used && (!piped || multi)) CU(c, cudaStreamWaitEvent(st, s.compute_done, 0));   // the slot's work buffers may have served another stream
         float* dur = nullptr; float* ddep = nullptr; int* dns = nullptr;
         if (sr) {
             dur = stage_out ? (float*)s.out_ur.p : sr->u_right + (size_t)(f0 / 2) * cap;
@@ -483,7 +494,7 @@ int run_batch(orbx_ctx* c, const uint8_t* imgs, size_t frame_stride, int batch, 
         c->last_img0 = d_img; c->last_img0_stride = d_stride; c->last_img0_pitch = (int)pitch;
     }
     if (multi) {                                       // join: later work on the context's stream sees every chunk
-        for (int k = 1; k < nslot; ++k) {
+        for (int k = 1; k < ncomp; ++k) {
             CU(c, cudaEventRecord(c->join_ev[k - 1], c->xstream[k - 1]));
             CU(c, cudaStreamWaitEvent(c->stream, c->join_ev[k - 1], 0));
         }
