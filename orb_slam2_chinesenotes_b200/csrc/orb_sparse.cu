@@ -395,6 +395,13 @@ __device__ __forceinline__ void orb_sincosf(const float y, float* sn, float* cs)
 // per warp, two block barriers) -- removes ~70 of ~420 instructions per keypoint but measures 1.17..1.45 ms per 512
 // frames against 0.99 ms for this version (72 instead of 39 registers, phases that wait for each other): the kernel
 // follows the uncoalesced tap gathers, not the issue rate.
+// Measured dead end (round 2, second attempt, all inside one warp): a warp takes K = 1 / 2 / 4 / 8 consecutive keypoints,
+// computes their moments as an 8 x 4 grid of lanes over the patch (8 row words per lane, byte masks of the disc, two
+// IDP.4A per word: ~100 instead of ~290 instructions), runs fastAtan2 + sincos ONCE with keypoint k in lane k, then the K
+// descriptors: bit-exact, ~25 % fewer instructions per keypoint, and 1.19 / 1.59 / 1.46 / 1.40 ms per 512 frames against
+// 0.99 ms.  The word loads of the grid touch four image rows per instruction (more L1 sectors than the one-row byte loads
+// of the column walk), 72 registers halve the resident warps, and a warp that walks K keypoints in turn has one
+// keypoint's loads in flight where K warps had K: the kernel is bound by L1 sectors and load latency, not by issue.
 __global__ void __launch_bounds__(DESC_NT) k_describe(const __grid_constant__ OrbPlan plan, const OrbBatch io)
 {
     const int frame = blockIdx.y, lane = threadIdx.x & 31;
