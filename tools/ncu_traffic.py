@@ -14,7 +14,7 @@ rows = list(csv.reader(raw.splitlines()))
 hdr, units, data = rows[0], rows[1], rows[2:]
 col = {h: i for i, h in enumerate(hdr)}
 mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-stage = {"k_pyr_resize": "pyramid", "k_pyr_resize_generic": "pyramid", "k_fast_strips": "fast", "k_blur7": "blur",
+stage = {"k_pyr_resize": "pyramid", "k_pyr_resize_generic": "pyramid", "k_fast_strips": "fast", "k_fast_bands": "fast", "k_blur7": "blur",
          "k_octree": "octree", "k_describe": "describe", "k_stereo_rows": "stereo", "k_stereo_match": "stereo",
          "k_stereo_cut": "stereo"}
 tot = defaultdict(float)
