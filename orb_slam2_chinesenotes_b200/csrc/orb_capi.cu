@@ -135,13 +135,12 @@ struct orbx_ctx {
     cudaEvent_t fork_ev = nullptr, join_ev[NSLOT - 1] = { nullptr };
     // Frames per internal pass.  With host buffers the chunks are what the copy / compute pipeline overlaps: smaller
     // chunks cost launch tails (a 64-frame launch list takes 0.71 ms, an eighth of a 512-frame one 0.57 ms), larger ones a
-    // longer pipeline fill and drain; measured end to end with the round-2 kernels on 1024 KITTI frames per call:
-    // 64 / 96 / 128 / 160 frames = 82.6-84.4 / 85.3 / 86.1-86.4 / 83.0 k frames/s (with round 1's slower kernels 64 was the
-    // optimum: 74.4 against 72.0 k).  Slots and compute streams (ORB_NSLOT / ORB_NCOMP = 3/2, 3/1, 4/2, 6/3, 6/2, 8/4) all
-    // measure 80-86 k: the pipeline is not short of buffers.  With everything device resident there
-    // is nothing to overlap and bigger launches are simply more efficient (1241x376: 6.66 ms per 512 frames in chunks
-    // of 64, 6.03 ms as one chunk), so the chunk only bounds the work buffers (about 2.6 MB per frame at that shape).
-    int chunk = 128, chunk_resident = 512;
+    // longer pipeline fill and drain, so the size is chosen per call from the frame size and the batch (run_batch has the
+    // rule and the measurements) unless orbx_set_chunk fixed it.  Slots and compute streams (ORB_NSLOT / ORB_NCOMP = 3/2,
+    // 3/1, 4/2, 6/3, 6/2, 8/4) all measure 80-86 k frames/s on KITTI: the pipeline is not short of buffers.  With everything
+    // device resident there is nothing to overlap and bigger launches are simply more efficient (1241x376: 6.66 ms per 512
+    // frames in chunks of 64, 6.03 ms as one chunk), so the chunk only bounds the work buffers (about 2.6 MB per frame).
+    int chunk = 0, chunk_resident = 512;   // chunk 0: chosen per call (run_batch)
     std::string err;
 
     bool have_plan = false;
@@ -404,7 +403,15 @@ int run_batch(orbx_ctx* c, const uint8_t* imgs, size_t frame_stride, int batch, 
         return fail(c, ORBX_E_ARG, "async entry point needs device pointers");
     const bool stage_out = !(kps_dev && desc_dev && n_dev) || (sr && !(ur_dev && dep_dev && ns_dev));
     const bool piped = !in_dev || stage_out;           // any host buffer: rotate slots and overlap the copies
-    const int want = piped ? c->chunk : c->chunk_resident;
+    // piped chunks: at most 128 MB of frames (1920x1080: 64 frames) and at least four chunks per call when the batch allows,
+    // 16..128 frames; measured end to end: 1024 KITTI frames 64 / 96 / 128 / 160 = 82.6-84.4 / 85.3 / 86.1-86.4 / 83.0 k frames/s;
+    // 256 EuRoC frames 32 / 48 / 64 / 96 / 128 = 91.9 / 95.1 / 95.7 / 86.1 / 82.6 k; 1024 HD frames 32 / 64 / 128 / 256 = 22.3 /
+    // 24.0-24.3 / 22.7 / 20.5 k
+    int auto_chunk = (int)(((size_t)128 << 20) / (pitch * (size_t)h));
+    if (auto_chunk > batch / 4) auto_chunk = batch / 4;
+    auto_chunk = auto_chunk < 16 ? 16 : auto_chunk > 128 ? 128 : auto_chunk;
+    auto_chunk &= ~1;
+    const int want = piped ? (c->chunk > 0 ? c->chunk : auto_chunk) : c->chunk_resident;
     int chunk = batch < want ? batch : want;
     if (sr && chunk % 2) chunk = chunk > 1 ? chunk - 1 : 2;      // a pair never straddles two chunks
     // Chunk schedule.  On the piped path the first chunk's upload and the last chunk's kernels + download have nothing to

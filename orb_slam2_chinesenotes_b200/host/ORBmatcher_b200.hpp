@@ -82,7 +82,7 @@ inline void Check(int rc, const char* what)
 // a small per-THREAD cache (Tracking, LocalMapping and LoopClosing run on their own threads) keyed by the frame id --
 // Frame::mnId, which a KeyFrame carries as mnFrameId, so a KeyFrame finds the entry its Frame made -- with the keypoint
 // count and the time stamp as a guard, least recently used entry dropped first.  Frame::nNextId restarts at 0 in
-// Tracking::Reset (src/Tracking.cc:1517): call b200::ResidentFrames::Local().Clear() there.
+// Tracking::Reset (src/Tracking.cc:1636): call b200::ResidentFrames::Local().Clear() there.
 class ResidentFrames {
 public:
     enum { kCapacity = 8 };
