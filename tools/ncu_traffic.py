@@ -19,7 +19,7 @@ stage = {"k_pyr_resize": "pyramid", "k_pyr_resize_generic": "pyramid", "k_fast_s
          "k_stereo_cut": "stereo"}
 tot = defaultdict(float)
 for r in data:
-    name = r[col["Kernel Name"]].split("(")[0]
+    name = r[col["Kernel Name"]].split("(")[0].split("<")[0].replace("void ", "").strip()
     b = 0.0
     for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
         b += float(r[col[m]].replace(",", "")) * mult.get(units[col[m]], 1)
