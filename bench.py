@@ -782,6 +782,35 @@ def measure_workload(workload, batch_total, scaling, rank, world, local_rank, di
         step_host()
     barrier()
     ms_e2e = 1e3 * (time.perf_counter() - t0)
+    # the same steps SUBMITTED back to back (the _async entry points take pinned host buffers and only enqueue), one
+    # synchronisation at the end: what a stream of batches sees -- the next step's uploads run beside this step's last kernels
+    # and downloads.  Two sets of result buffers alternate, as a consumer of step k's results would need while step k+1 runs.
+    h2 = [torch.empty_like(t).pin_memory() for t in (h_kps, h_desc, h_n, h_ur, h_dep, h_ns)]
+    sets = [(h_kps, h_desc, h_n, h_ur, h_dep, h_ns), tuple(h2)]
+
+    def submit(i):
+        k_, d_, n_, u_, p_, s_ = sets[i % 2]
+        if stereo:
+            ex.extract_stereo_batch_raw(h_frames, h * w, pairs, w, h, w, k_, d_, cap, n_, CAM["bf"], CAM["fx"], u_, p_, s_, asynchronous=True)
+        else:
+            ex.extract_batch_raw(h_frames, h * w, batch, w, h, w, k_, d_, cap, n_, asynchronous=True)
+
+    keep_sync = [t.clone() for t in (h_n, h_ns)] + [h_desc[:4].clone(), h_kps[:4].clone()]
+    submit(0); submit(1)
+    ex.sync()
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        submit(i)
+    ex.sync()
+    barrier()
+    ms_pipe = 1e3 * (time.perf_counter() - t0)
+    m_ = int(keep_sync[0][:4].min())                    # entries behind n_out are unspecified: compare the valid ones
+    for k_, d_, n_, u_, p_, s_ in sets:                 # both buffer sets hold the synchronous call's results
+        if not ((n_ == keep_sync[0]).all() and (not stereo or (s_ == keep_sync[1]).all()) and (d_[:4, :m_] == keep_sync[2][:, :m_]).all()
+                and (k_[:4, :m_].contiguous().view(torch.uint8) == keep_sync[3][:, :m_].contiguous().view(torch.uint8)).all()):
+            raise SystemExit("bench.py: pipelined submissions and the synchronous call disagree")
+    del h2
     clocks = sampler.stop()
 
     # ---- the results that were timed are the reference's results: first and last frames of the batch, both paths
@@ -843,9 +872,9 @@ def measure_workload(workload, batch_total, scaling, rank, world, local_rank, di
     # ---- max over ranks
     total_kp = float(nk.sum())
     if sync_ranks:
-        t = torch.tensor([ms_dev, ms_e2e, ms_copy], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms_dev, ms_e2e, ms_copy, ms_pipe], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_dev, ms_e2e, ms_copy = float(t[0]), float(t[1]), float(t[2])
+        ms_dev, ms_e2e, ms_copy, ms_pipe = float(t[0]), float(t[1]), float(t[2]), float(t[3])
         kp = torch.tensor([total_kp, float(n_depth)], device=dev, dtype=torch.float64)
         dist.all_reduce(kp)
         total_kp, n_depth = float(kp[0]), float(kp[1])
@@ -903,7 +932,11 @@ def measure_workload(workload, batch_total, scaling, rank, world, local_rank, di
         "n_gpus": nranks, "config": workload_config(workload, batch_total, nranks, "weak" if scaling != "strong" else "strong"), "stats": stats,
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": ms_e2e / steps, "copy_ceiling_frames_per_s": frames_all * steps / (ms_copy * 1e-3),
-                "copy_ceiling_note": "the step's pinned host->device and device->host copies alone, two streams, all ranks at once (max over ranks)"},
+                "copy_ceiling_note": "the step's pinned host->device and device->host copies alone, two streams, all ranks at once (max over ranks)",
+                "note": "value: one synchronous call per step (the call returns when the step's results are on the host)",
+                "pipelined_submissions_frames_per_s": frames_all * steps / (ms_pipe * 1e-3),
+                "pipelined_note": "the same steps through the _async entry points with the same pinned host buffers (two alternating result sets), "
+                                  "one orbx_sync at the end: consecutive steps overlap; results compared with the synchronous call's"},
         "gpu_launches": ex.launches_per_chunk(stereo) * chunks * steps,
         "roofline": roof, "cpu_baseline": cpu_base, "clocks": clocks, "parity": parity,
     }

@@ -94,8 +94,11 @@ int orbx_extract_batch(orbx_ctx* ctx, const uint8_t* imgs, size_t frame_stride, 
                        int w, int h, size_t pitch, orbx_kp* kps, uint8_t* desc,
                        int cap_per_frame, int* n_out);
 
-/* As above with every pointer in DEVICE memory: only enqueues work on the context's stream
- * and returns; orbx_sync() waits.  n_out overflow is not reported here. */
+/* As above, but the call only enqueues its work (on the context's stream and, with host buffers, on its copy streams)
+ * and returns; orbx_sync() waits.  n_out overflow is not reported here.  With every pointer in DEVICE memory nothing is
+ * staged.  Host buffers (PINNED, or the copies block) are allowed too and must stay valid until orbx_sync(): several calls
+ * may be in flight, they complete in order, and the next call's uploads run beside the previous call's last kernels and
+ * downloads -- a stream of batches keeps the copy engines and the SMs busy across call boundaries. */
 int orbx_extract_batch_async(orbx_ctx* ctx, const uint8_t* d_imgs, size_t frame_stride, int batch,
                              int w, int h, size_t pitch, orbx_kp* d_kps, uint8_t* d_desc,
                              int cap_per_frame, int* d_n_out);
@@ -108,7 +111,7 @@ int orbx_sync(orbx_ctx* ctx);
  * u_right/depth [pairs][cap_per_frame] receive mvuRight/mvDepth of the LEFT keypoints (-1 = no match; entries
  * past n_out[2p] are not written), n_stereo [pairs] the number of matches before the median cut.  bf = mbf,
  * fx = K(0,0) (mb = bf/fx, :121).  Keypoints, descriptors and pyramids stay on the device between the two
- * steps.  Pointers host or device; the _async form takes device pointers only and just enqueues. */
+ * steps.  Pointers host or device; the _async form only enqueues (see orbx_extract_batch_async). */
 int orbx_extract_stereo_batch(orbx_ctx* ctx, const uint8_t* imgs, size_t frame_stride, int pairs,
                               int w, int h, size_t pitch, orbx_kp* kps, uint8_t* desc,
                               int cap_per_frame, int* n_out, float bf, float fx,

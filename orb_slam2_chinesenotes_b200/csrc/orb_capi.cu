@@ -399,8 +399,8 @@ int run_batch(orbx_ctx* c, const uint8_t* imgs, size_t frame_stride, int batch, 
     const bool in_dev = is_device_ptr(imgs);
     const bool kps_dev = is_device_ptr(kps), desc_dev = is_device_ptr(desc), n_dev = is_device_ptr(n_out);
     const bool ur_dev = sr && is_device_ptr(sr->u_right), dep_dev = sr && is_device_ptr(sr->depth), ns_dev = sr && is_device_ptr(sr->n_stereo);
-    if (async_only && !(in_dev && kps_dev && desc_dev && n_dev && (!sr || (ur_dev && dep_dev && ns_dev))))
-        return fail(c, ORBX_E_ARG, "async entry point needs device pointers");
+    // (the _async entry points take host buffers too: the call then only enqueues the copies and kernels of its chunks, and
+    // several calls in flight overlap -- the next call's uploads run beside this call's last kernels and downloads)
     const bool stage_out = !(kps_dev && desc_dev && n_dev) || (sr && !(ur_dev && dep_dev && ns_dev));
     const bool piped = !in_dev || stage_out;           // any host buffer: rotate slots and overlap the copies
     // piped chunks: at most 128 MB of frames (1920x1080: 64 frames) and at least four chunks per call when the batch allows,
@@ -506,7 +506,7 @@ int run_batch(orbx_ctx* c, const uint8_t* imgs, size_t frame_stride, int batch, 
             CU(c, cudaStreamWaitEvent(c->stream, c->join_ev[k - 1], 0));
         }
     }
-    if (async_only) { for (Slot& s : c->slot) s.used = false; return ORBX_OK; }
+    if (async_only) return ORBX_OK;                    // the slots' events keep ordering the next call against this one
     rc = sync_all(c);
     if (rc) return rc;
     for (Slot& s : c->slot) s.used = false;

@@ -206,3 +206,33 @@ def test_two_extractors_on_two_threads_with_different_shapes():
     for t in threads:
         t.join()
     assert not errors, errors[:3]
+
+
+@pytest.mark.gpu
+def test_async_submissions_with_host_buffers_overlap_and_agree():
+    """The _async entry points take (pinned) host buffers too: three batches submitted back to back without waiting, one
+    orbx_sync at the end; every batch's results equal the synchronous call's (frames differ per batch, so a mix-up of
+    staging slots between calls in flight would show)."""
+    import torch
+    w, h, nf, per = 640, 480, 1000, 40
+    ex = ob.ORBextractor(nf, 1.2, 8, 20, 7)
+    ex.set_chunk(16)                                                       # several chunks per call: the slots rotate across calls
+    cap = ex.default_capacity()
+    batches = [np.stack([synth_frame(w, h, 300 + 50 * b + i) for i in range(per)]) for b in range(3)]
+    want = [ex.extract_batch(fr) for fr in batches]
+    pin = lambda a: torch.from_numpy(a).pin_memory()
+    h_in = [pin(fr) for fr in batches]
+    outs = [(torch.zeros((per, cap, 7), dtype=torch.float32).pin_memory(), torch.zeros((per, cap, 32), dtype=torch.uint8).pin_memory(),
+             torch.zeros(per, dtype=torch.int32).pin_memory()) for _ in range(3)]
+    for b in range(3):
+        ex.extract_batch_raw(h_in[b], h * w, per, w, h, w, outs[b][0], outs[b][1], cap, outs[b][2], asynchronous=True)
+    ex.sync()
+    for b in range(3):
+        kps, desc, n = want[b]
+        gk = outs[b][0].numpy().view(np.uint8).reshape(per, cap, 28).view(ob.KP_DTYPE).reshape(per, cap)
+        gd, gn = outs[b][1].numpy(), outs[b][2].numpy()
+        assert (gn == n).all()
+        for f in range(per):
+            assert (gd[f, :n[f]] == desc[f, :n[f]]).all()
+            assert gk[f, :n[f]].tobytes() == kps[f, :n[f]].tobytes()
+    ex.close()
