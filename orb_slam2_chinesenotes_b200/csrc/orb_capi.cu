@@ -46,7 +46,10 @@ struct DevBuf {
         bytes = n;
         // fresh device memory holds whatever its last owner left: entries of an output behind n_out are unspecified by
         // contract, but they should not differ from run to run (a staged output is copied out whole)
-        return cudaMemset(p, 0, n);
+        // (the context's streams are non-blocking, i.e. NOT ordered against the default stream the memset runs on: wait for it
+        // here, once per allocation, or a kernel queued next could be overwritten by it)
+        e = cudaMemset(p, 0, n);
+        return e == cudaSuccess ? cudaStreamSynchronize(0) : e;
     }
     void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
 };

@@ -630,7 +630,8 @@ int orbm_frame_upload(const orbm_frame* F, int device, orbm_frame_handle** handl
         // pageable sources: cudaMemcpy returns once the bytes are staged, so the caller's vectors may go away at once
         bool ok = cudaMemcpy(H->block, F->kps, n * sizeof(orbx_kp), cudaMemcpyDefault) == cudaSuccess &&
                   cudaMemcpy(H->block + o_desc, F->desc, n * 32, cudaMemcpyDefault) == cudaSuccess &&
-                  (!F->u_right || cudaMemcpy(H->block + o_ur, F->u_right, n * 4, cudaMemcpyDefault) == cudaSuccess);
+                  (!F->u_right || cudaMemcpy(H->block + o_ur, F->u_right, n * 4, cudaMemcpyDefault) == cudaSuccess) &&
+                  cudaStreamSynchronize(0) == cudaSuccess;   // a copy from pageable memory may still be in flight when cudaMemcpy returns; the view may be used on any stream
         if (!ok) { cudaGetLastError(); cudaFree(H->block); delete H; return ORBX_E_CUDA; }
         H->kps = (const orbx_kp*)H->block; H->desc = (const uint8_t*)(H->block + o_desc);
         H->u_right = F->u_right ? (const float*)(H->block + o_ur) : nullptr;
