@@ -38,6 +38,9 @@
 #ifndef ORB_OCT_MID_BLOCKS
 #define ORB_OCT_MID_BLOCKS 592
 #endif
+#ifndef OCT_U
+#define OCT_U 4                // candidates a thread takes per trip of the two per-pass candidate loops
+#endif
 #ifndef ORB_OCT_SMALL_BATCH
 #define ORB_OCT_SMALL_BATCH 8
 #endif
@@ -126,13 +129,19 @@ __global__ void __launch_bounds__(OCT_NT) k_octree(const __grid_constant__ OrbPl
         for (int i = tid; i < 4 * L; i += OCT_NT) S.cc[i] = 0;
         if (tid == 0) { s_nexp = 0; s_m = 0; }
         __syncthreads();
-        for (int i = tid; i < n; i += OCT_NT) {
-            const int p = node[i] & 0xfff;
-            if (cnt[p] > 1) {
-                const uint32_t k = keys[i];
-                const int c = oct_child(box[p], ORB_PX(k), ORB_PY(k));
-                atomicAdd(&S.cc[4 * p + c], 1);
-                node[i] = (uint16_t)(p | (c << 12));
+        // (four candidates per trip, their loads issued together: the loop waits on global memory, not on arithmetic)
+        for (int i0 = tid; i0 < n; i0 += OCT_U * OCT_NT) {
+            int pv[OCT_U]; uint32_t kv[OCT_U];
+#pragma unroll
+            for (int u = 0; u < OCT_U; ++u) { const int i = i0 + u * OCT_NT; pv[u] = i < n ? (int)(node[i] & 0xfff) : -1; kv[u] = i < n ? keys[i] : 0u; }
+#pragma unroll
+            for (int u = 0; u < OCT_U; ++u) {
+                const int p = pv[u];
+                if (p >= 0 && cnt[p] > 1) {
+                    const int c = oct_child(box[p], ORB_PX(kv[u]), ORB_PY(kv[u]));
+                    atomicAdd(&S.cc[4 * p + c], 1);
+                    node[i0 + u * OCT_NT] = (uint16_t)(p | (c << 12));
+                }
             }
         }
         __syncthreads();
@@ -233,10 +242,17 @@ __global__ void __launch_bounds__(OCT_NT) k_octree(const __grid_constant__ OrbPl
         }
         __syncthreads();
         // E. move the keys
-        for (int i = tid; i < n; i += OCT_NT) {
-            const int v = node[i], p = v & 0xfff;
-            const int r = S.rk[p];
-            node[i] = (uint16_t)((r >= 0 && r < m) ? S.cc[4 * p + (v >> 12)] : S.keep[p]);
+        for (int i0 = tid; i0 < n; i0 += OCT_U * OCT_NT) {
+            int vv[OCT_U];
+#pragma unroll
+            for (int u = 0; u < OCT_U; ++u) { const int i = i0 + u * OCT_NT; vv[u] = i < n ? (int)node[i] : -1; }
+#pragma unroll
+            for (int u = 0; u < OCT_U; ++u) {
+                if (vv[u] < 0) continue;
+                const int v = vv[u], p = v & 0xfff;
+                const int r = S.rk[p];
+                node[i0 + u * OCT_NT] = (uint16_t)((r >= 0 && r < m) ? S.cc[4 * p + (v >> 12)] : S.keep[p]);
+            }
         }
         const int nToExpand = s_nexp;
         const int prevL = L;
