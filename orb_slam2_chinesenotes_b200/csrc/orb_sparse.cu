@@ -446,15 +446,19 @@ __global__ void __launch_bounds__(DESC_NT) k_describe(const __grid_constant__ Or
     const int u = lane - ORB_HALF_PATCH;
     int m10 = 0, m01 = 0;
     if (lane < ORB_PATCH) {
+        // rows +v and -v of a column are in or out of the disc together: one predicate, one 3-input add for the column sum
+        // and v * (below - above) for m01 per pair
         const int vmax = plan.umax[u < 0 ? -u : u];
-        const uint8_t* c = img + (size_t)(cy - ORB_HALF_PATCH) * pitch + cx + u;
-        int colsum = 0;
+        const uint8_t* pd = img + (size_t)cy * pitch + cx + u;
+        const uint8_t* pu = pd;
+        int colsum = __ldg(pd);
 #pragma unroll
-        for (int v = -ORB_HALF_PATCH; v <= ORB_HALF_PATCH; ++v, c += pitch) {
-            if ((v < 0 ? -v : v) <= vmax) {
-                const int val = __ldg(c);
-                colsum += val;
-                m01 += v * val;
+        for (int v = 1; v <= ORB_HALF_PATCH; ++v) {
+            pd += pitch; pu -= pitch;
+            if (v <= vmax) {
+                const int below = __ldg(pd), above = __ldg(pu);
+                colsum += below + above;
+                m01 += v * (below - above);
             }
         }
         m10 = u * colsum;
