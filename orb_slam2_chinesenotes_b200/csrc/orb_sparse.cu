@@ -331,15 +331,6 @@ cudaError_t orb_launch_octree(const OrbPlan& plan, const OrbBatch& io, int batch
 __device__ __align__(32) const signed char d_pattern[1024] = {
 #include "orb_pattern.inc"
 };
-// The same points in 16 spatially compact groups of 32 (tools/gen_pattern.py): entry [group][lane] = x | y << 8 | index << 16.
-// The 32 taps a warp fetches with one load instruction then lie in ~9 32-byte sectors whatever the angle, where the
-// reference's order (lane = descriptor byte) scatters them over ~22; the values find their descriptor bit through shared memory.
-__device__ __align__(16) const uint32_t d_pattern_tiles[512] = {
-#include "orb_pattern_tiles.inc"
-};
-#ifndef DESC_TILED
-#define DESC_TILED 1
-#endif
 
 // cv::fastAtan2 (scalar path of OpenCV's atanImpl<float>), degrees; every operation rounds to
 // float on its own (the file is compiled with -fmad=false; the intrinsics say so explicitly).
@@ -430,12 +421,6 @@ __device__ __forceinline__ void orb_sincosf(const float y, float* sn, float* cs)
 __global__ void __launch_bounds__(DESC_NT) k_describe(const __grid_constant__ OrbPlan plan, const OrbBatch io)
 {
     const int frame = blockIdx.y, lane = threadIdx.x & 31;
-#if DESC_TILED
-    __shared__ uint32_t s_tab[512];                                    // the grouped pattern, once per block
-    __shared__ __align__(16) uint8_t s_val[DESC_NT / 32][512];         // per warp: the 512 sampled values in the reference's order
-    for (int i = threadIdx.x; i < 512; i += DESC_NT) s_tab[i] = d_pattern_tiles[i];
-    __syncthreads();                                                   // (before any warp leaves)
-#endif
     const int s = blockIdx.x * (DESC_NT / 32) + (threadIdx.x >> 5);   // output slot within the frame
     // level of slot s: prefix over the per-level keypoint counts (operator() appends level by level, :1118-1148)
     int cnt = lane < plan.nlevels ? io.lkp_count[frame * ORB_MAX_LEVELS + lane] : 0;
@@ -491,36 +476,10 @@ __global__ void __launch_bounds__(DESC_NT) k_describe(const __grid_constant__ Or
     orb_sincosf(__fmul_rn(angle, factorPI), &b, &a);                   // a = cos, b = sin (:125)
     int blur_pitch = L.pitch;
     const uint8_t* bc = io.blur + (size_t)frame * plan.blur_bytes + L.blur_off + (size_t)cy * blur_pitch + cx;
-    int val = 0;
-#if DESC_TILED
-    // 16 loads of 32 neighbouring taps each; every value goes to its place in the reference's order ...
-    uint8_t* vals = s_val[threadIdx.x >> 5];
-#pragma unroll
-    for (int t = 0; t < 16; ++t) {
-        const uint32_t e = s_tab[t * 32 + lane];
-        const float px = (float)(signed char)(e & 0xffu), py = (float)(signed char)((e >> 8) & 0xffu);
-        // GET_VALUE (:132-134): row = cvRound(x*b + y*a), col = cvRound(x*a - y*b)
-        const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a)));
-        const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b)));
-        vals[e >> 16] = __ldg(bc + r0 * blur_pitch + c0);
-    }
-    __syncwarp();
-    // ... where lane = descriptor byte finds its 16 values as four words of two (t0, t1) byte pairs: t0 < t1 per 16-bit half
-    // is the missing bit 8 of (256 + t0) - t1
-    {
-        const uint4 w4 = *(const uint4*)(vals + 16 * lane);
-        const uint32_t w[4] = { w4.x, w4.y, w4.z, w4.w };
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const uint32_t d = ((w[k] & 0x00ff00ffu) | 0x01000100u) - ((w[k] >> 8) & 0x00ff00ffu);
-            const uint32_t lt = ~d & 0x01000100u;
-            val |= (int)(((lt >> 8) | (lt >> 23)) & 3u) << (2 * k);
-        }
-    }
-#else
     __align__(16) signed char pat[32];                                  // 16 points = 8 pairs per byte
     ((int4*)pat)[0] = __ldg((const int4*)(d_pattern + lane * 32));
     ((int4*)pat)[1] = __ldg((const int4*)(d_pattern + lane * 32) + 1);
+    int val = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const float px = (float)pat[4 * j], py = (float)pat[4 * j + 1];
@@ -533,7 +492,6 @@ __global__ void __launch_bounds__(DESC_NT) k_describe(const __grid_constant__ Or
         const int t0 = __ldg(bc + r0 * blur_pitch + c0), t1 = __ldg(bc + r1 * blur_pitch + c1);
         val |= (t0 < t1) << j;
     }
-#endif
     io.desc[((size_t)frame * io.cap + s) * 32 + lane] = (uint8_t)val;
 
     // ---- keypoint record (:892-896, :1140-1146): 7 lanes write the 7 fields
