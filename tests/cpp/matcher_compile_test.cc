@@ -172,6 +172,33 @@ int fwd_resident_reuse(int calls, int n, const Kp* kps, const unsigned char* des
     return same ? (int)(cache.Uploads() - before) : -1;
 }
 
+// b200::ResidentFrames bookkeeping: `frames` small Frames are made resident one after the other (capacity 8, least recently
+// used entry dropped), then the first one is asked for again (evicted: one more upload) and the last one (still there: none).
+// Returns uploads_total * 100 + entries held, or -1 if a view does not describe its frame.
+int fwd_resident_cache_lru(int frames, int n, const Kp* kps, const unsigned char* desc)
+{
+    ORB_SLAM2::b200::ResidentFrames& cache = ORB_SLAM2::b200::ResidentFrames::Local();
+    cache.Clear();
+    const unsigned long before = cache.Uploads();
+    std::vector<FrameT> F(frames);
+    for (int f = 0; f < frames; ++f) {
+        F[f].N = n - f;                                                     // different keypoint counts
+        fill_keys(F[f].mvKeysUn, kps, n - f); F[f].mvKeys = F[f].mvKeysUn;
+        fill_desc(F[f].mDescriptors, desc, n - f);
+        F[f].mvuRight.assign(n - f, -1.f);
+        const orbm_frame v = ORB_SLAM2::b200::Resident(F[f], f % 2 == 0);
+        if (v.n != n - f || !v.kps || !v.desc || (f % 2 == 0) != (v.u_right != 0)) return -1;
+    }
+    const orbm_frame first = ORB_SLAM2::b200::Resident(F[0], true), last = ORB_SLAM2::b200::Resident(F[frames - 1], false);
+    if (first.n != n || last.n != n - (frames - 1)) return -1;
+    // a frame cached without right coordinates is uploaded again when they are asked for, and then serves both kinds of view
+    const orbm_frame odd = ORB_SLAM2::b200::Resident(F[frames - 1], true), odd2 = ORB_SLAM2::b200::Resident(F[frames - 1], false);
+    if (!odd.u_right || odd2.u_right) return -1;
+    const int r = (int)(cache.Uploads() - before) * 100 + (int)cache.Size();
+    cache.Clear();
+    return r;
+}
+
 // both ORBmatcher::SearchByBoW overloads through b200::SearchByBoW; match12 [n1] = feature of side 2 or -1
 int fwd_search_by_bow(int kf_kf, int n1, const Kp* k1, const unsigned char* d1, const unsigned char* has1, const unsigned char* bad1,
                       int nn1, const int* id1, const int* off1, const int* f1,

@@ -162,3 +162,18 @@ def test_matcher_forwarders_keep_a_frame_on_the_device(dropin):
     want = Matcher("oracle").search_by_projection_points(k2, d2, np.full(len(k2), -1, np.float32), scale, bounds, q, 3.0, 0.8, None)
     assert uploads == 1 and nm.value == want[0] and nm.value > 300
     print(f"SearchByProjection through the forwarder: first call {secs[0] * 1e3:.3f} ms, later calls {secs[1] * 1e3:.3f} ms")
+
+
+@pytest.mark.gpu
+def test_resident_frame_cache_bookkeeping(dropin):
+    """b200::ResidentFrames: capacity 8 with least-recently-used eviction, one entry per frame, an entry without right
+    coordinates superseded when they are needed."""
+    from matcher_lib import extract_frame
+    M = C.CDLL(os.path.join(CPP, "_build", "libmatcher_fwd.so"))
+    kps, desc, _ = extract_frame(640, 480, 500, 3)
+    M.fwd_resident_cache_lru.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    frames = 10
+    r = M.fwd_resident_cache_lru(frames, len(kps), kps.ctypes.data, desc.ctypes.data)
+    # 10 uploads, + 1 for the evicted first frame, + 0 for the last frame (a hit), + 1 when the last frame (cached without
+    # right coordinates: index 9 is odd) is asked for with them; 8 entries held
+    assert r == (frames + 1 + 1) * 100 + 8, r
