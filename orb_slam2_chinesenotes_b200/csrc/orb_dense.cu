@@ -59,9 +59,27 @@ struct PyrJob {
 #ifndef PYR_STAGES
 #define PYR_STAGES 4     // source rows in flight per warp
 #endif
+#ifndef PYR_LD64
+#define PYR_LD64 1       // 1: a lane's window travels as two 8-byte words (four MIO instructions per source row), 0: as three 4-byte words (six)
+#endif
+#if PYR_LD64
+typedef uint2 PyrSlot;
+#define PYR_WORDS 2
+#else
+typedef uint32_t PyrSlot;
+#define PYR_WORDS 3
+#endif
 __device__ __forceinline__ void cp_async4(const uint32_t dst, const void* src)
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(const uint32_t dst, const void* src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8_zfill(const uint32_t dst, const void* src, const uint32_t src_bytes)   // the rest of the 8 bytes is zero-filled
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" :: "r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async4_zfill(const uint32_t dst, const void* src, const uint32_t src_bytes)   // src_bytes 0: nothing is read
 {
@@ -75,7 +93,7 @@ __device__ __forceinline__ void cp_async4_zfill(const uint32_t dst, const void* 
 // ALLFAST: no lane of the warp touches the right edge of the source.  Otherwise words that start behind the row's last
 // pixel are zero-filled instead of read (they only ever meet the zero weight of the clamped tap).
 template <bool ALLFAST>
-__device__ __forceinline__ void pyr_walk(const PyrJob& J, uint32_t (*ring)[3][32], const int frame, const int lane, const int d0, const int sx0, const bool live,
+__device__ __forceinline__ void pyr_walk(const PyrJob& J, PyrSlot (*ring)[PYR_WORDS][32], const int frame, const int lane, const int d0, const int sx0, const bool live,
                                          const uint32_t (&C)[4], const uint32_t selA, const uint32_t selB, const int yb, const int ye)
 {
     const int sh = J.sh, spitch = J.spitch, dpitch = J.dpitch;
@@ -87,6 +105,17 @@ __device__ __forceinline__ void pyr_walk(const PyrJob& J, uint32_t (*ring)[3][32
     const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(&ring[0][0][lane]);
     auto post = [&](const int slot, const bool on) {                        // one commit group per row, empty once the rows are used up
         if (on) {
+#if PYR_LD64
+            // the 8 tap bytes lie in the 16 bytes from the 8-byte boundary at or below the first one
+            const uint8_t* q = (const uint8_t*)((uintptr_t)a & ~(uintptr_t)7);
+            const uint32_t d = ring_s + (uint32_t)slot * (2 * 32 * 8);
+            if (ALLFAST) { cp_async8(d, q); cp_async8(d + 256, q + 8); }
+            else {
+                const int al = (int)((uintptr_t)a & 7);
+                cp_async8_zfill(d, q, (uint32_t)min(al + room, 8));         // starts at or before the first tap; only what the row still holds
+                cp_async8_zfill(d + 256, q + 8, (uint32_t)min(max(room - (8 - al), 0), 8));
+            }
+#else
             const uint8_t* q = (const uint8_t*)((uintptr_t)a & ~(uintptr_t)3);
             const uint32_t d = ring_s + (uint32_t)slot * (3 * 32 * 4);
             if (ALLFAST) { cp_async4(d, q); cp_async4(d + 128, q + 4); cp_async4(d + 256, q + 8); }
@@ -96,6 +125,7 @@ __device__ __forceinline__ void pyr_walk(const PyrJob& J, uint32_t (*ring)[3][32
                 cp_async4_zfill(d + 128, q + 4, 4 - al < room ? 4u : 0u);
                 cp_async4_zfill(d + 256, q + 8, 8 - al < room ? 4u : 0u);
             }
+#endif
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
         a += spitch;
@@ -121,8 +151,16 @@ __device__ __forceinline__ void pyr_walk(const PyrJob& J, uint32_t (*ring)[3][32
     // row, when the rows of the bottom clamp (upper tap sh-1, lower weight 0) are emitted as well.
     auto advance = [&](const int slot, uint32_t* __restrict__ Hn, const uint32_t* __restrict__ Ho) -> bool {
         asm volatile("cp.async.wait_group %0;" :: "n"(PYR_STAGES - 1) : "memory");
+#if PYR_LD64
+        const uint2 lo = ring[slot][0][lane], hi = ring[slot][1][lane];
+        const uint32_t ac = (uint32_t)(uintptr_t)a - back;                 // low address bits of the row being consumed
+        const bool up = (ac & 4u) != 0;                                     // the window starts in the second word
+        const uint32_t q0 = up ? lo.y : lo.x, q1 = up ? hi.x : lo.y, q2 = up ? hi.y : hi.x;
+        const uint32_t sft = ac << 3;                                       // SHF.W takes the amount modulo 32
+#else
         const uint32_t q0 = ring[slot][0][lane], q1 = ring[slot][1][lane], q2 = ring[slot][2][lane];
         const uint32_t sft = ((uint32_t)(uintptr_t)a - back) << 3;        // SHF.W takes the amount modulo 32
+#endif
         const uint32_t w0 = __funnelshift_r(q0, q1, sft), w1 = __funnelshift_r(q1, q2, sft);
         const uint32_t A = __byte_perm(w0, w1, selA), B = __byte_perm(w0, w1, selB);
         post(slot, r + PYR_STAGES <= r_last);                              // after the words have been consumed
@@ -174,8 +212,8 @@ __global__ void __launch_bounds__(PYR_NT) k_pyr_resize(const __grid_constant__ P
     const uint32_t selA = (uint32_t)(rel[0] | ((rel[0] + 1) << 4) | (rel[1] << 8) | ((rel[1] + 1) << 12));
     const uint32_t selB = (uint32_t)(rel[2] | ((rel[2] + 1) << 4) | (rel[3] << 8) | ((rel[3] + 1) << 12));
     // bytes sx0 .. sx0+7 are fetched through three aligned words
-    __shared__ uint32_t ring[PYR_NT / 32][PYR_STAGES][3][32];
-    const bool fast = sx0 + 12 <= sw;
+    __shared__ __align__(8) PyrSlot ring[PYR_NT / 32][PYR_STAGES][PYR_WORDS][32];
+    const bool fast = sx0 + (PYR_LD64 ? 16 : 12) <= sw;                    // the lane's whole fetch window lies inside the row
     if (__all_sync(0xffffffffu, fast)) pyr_walk<true>(J, ring[threadIdx.x >> 5], frame, lane, d0, sx0, live, C, selA, selB, yb, ye);
     else pyr_walk<false>(J, ring[threadIdx.x >> 5], frame, lane, d0, sx0, live, C, selA, selB, yb, ye);
 }
