@@ -236,3 +236,35 @@ def test_async_submissions_with_host_buffers_overlap_and_agree():
             assert (gd[f, :n[f]] == desc[f, :n[f]]).all()
             assert gk[f, :n[f]].tobytes() == kps[f, :n[f]].tobytes()
     ex.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("x0,pitch_pad", [(31, 0), (8, 5), (3, 1)])
+def test_device_resident_view_with_odd_offset_and_pitch(x0, pitch_pad):
+    """Frames that are a window of larger device images: base address, row pitch and frame stride with no alignment at all
+    (the pyramid and blur rings fetch aligned words around such rows; FAST falls back from its tensor-map copies)."""
+    import torch
+    w, h, nf, B = 640, 480, 1000, 3
+    Wb, Hb = w + 60 + pitch_pad, h + 20
+    big = np.stack([synth_frame(Wb, Hb, 700 + i) for i in range(B)])
+    y0 = 10
+    roi = np.ascontiguousarray(big[:, y0:y0 + h, x0:x0 + w])
+    O = OracleExtractor(nf)
+    want = [O.extract(roi[i]) for i in range(B)]
+    G = ob.ORBextractor(nf, 1.2, 8, 20, 7)
+    cap = G.default_capacity()
+    d_big = torch.from_numpy(big).cuda()
+    view = d_big[:, y0:y0 + h, x0:x0 + w]                                   # data_ptr() = first pixel of the window
+    d_k = torch.zeros((B, cap, 7), dtype=torch.float32, device="cuda")
+    d_d = torch.zeros((B, cap, 32), dtype=torch.uint8, device="cuda")
+    d_n = torch.zeros(B, dtype=torch.int32, device="cuda")
+    G.extract_batch_raw(view, Hb * Wb, B, w, h, Wb, d_k, d_d, cap, d_n, asynchronous=True)
+    G.sync()
+    n = d_n.cpu().numpy()
+    kps = d_k.cpu().numpy().view(np.uint8).reshape(B, cap, 28).view(ob.KP_DTYPE).reshape(B, cap)
+    desc = d_d.cpu().numpy()
+    for i in range(B):
+        no, k_o, d_o = want[i]
+        assert no == n[i]
+        assert same_kps(k_o, kps[i, :no]) and (d_o == desc[i, :no]).all(), i
+    G.close(); O.close()
