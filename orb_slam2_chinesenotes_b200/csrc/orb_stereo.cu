@@ -176,10 +176,8 @@ __global__ void __launch_bounds__(256) k_stereo_match(const __grid_constant__ Or
                 const int cR = sR[5 * 21 + 5 + i];
                 int s = 0;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int b = (int)sR[ro[k] + i] - cR;
-                    if (k < 3 || last) s += abs(a[k] - b);
-                }
+                for (int k = 0; k < 4; ++k)                                   // |(l - cL) - (r - cR)| = |(l - cL + cR) - r|
+                    if (k < 3 || last) s = (int)__sad(a[k] + cR, (int)sR[ro[k] + i], (unsigned)s);
                 s = __reduce_add_sync(0xffffffffu, s);
                 const float dist = (float)s;
                 if (dist < (float)bestDist) { bestDist = (int)dist; bestincR = i - L; }   // :641-645
