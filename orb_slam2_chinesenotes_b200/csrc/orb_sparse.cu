@@ -269,10 +269,12 @@ __global__ void __launch_bounds__(OCT_NT) k_octree(const __grid_constant__ OrbPl
     for (int p = tid; p < L; p += OCT_NT) best[p] = 0;
     __syncthreads();
     const int wc = LV.wCell, hc = LV.hCell;
+    // x / wCell and y / hCell by multiplication: floor(n / d) = (n * (2^20 / d + 1)) >> 20 for d <= 64 and n < 16384 (coordinates are < 4128)
+    const uint32_t mwc = (1u << 20) / (uint32_t)wc + 1u, mhc = (1u << 20) / (uint32_t)hc + 1u;
     for (int i = tid; i < n; i += OCT_NT) {
         const uint32_t k = keys[i];
         const int ax = ORB_PX(k) - 3, ay = ORB_PY(k) - 3;
-        const int cj = ax / wc, ci = ay / hc;
+        const int cj = (int)(((uint32_t)ax * mwc) >> 20), ci = (int)(((uint32_t)ay * mhc) >> 20);
         const uint32_t order = (uint32_t)(((ci * LV.ncx + cj) * hc + (ay - ci * hc)) * wc + (ax - cj * wc));
         atomicMax(&best[node[i] & 0xfff], ((uint32_t)ORB_PS(k) << 24) | (0xffffffu - order));
     }
@@ -281,7 +283,7 @@ __global__ void __launch_bounds__(OCT_NT) k_octree(const __grid_constant__ OrbPl
     for (int i = tid; i < n; i += OCT_NT) {
         const uint32_t k = keys[i];
         const int ax = ORB_PX(k) - 3, ay = ORB_PY(k) - 3;
-        const int cj = ax / wc, ci = ay / hc;
+        const int cj = (int)(((uint32_t)ax * mwc) >> 20), ci = (int)(((uint32_t)ay * mhc) >> 20);
         const uint32_t order = (uint32_t)(((ci * LV.ncx + cj) * hc + (ay - ci * hc)) * wc + (ax - cj * wc));
         const int p = node[i] & 0xfff;
         if (best[p] == (((uint32_t)ORB_PS(k) << 24) | (0xffffffu - order)) && p < LV.kp_cap) out[p] = k;
