@@ -323,6 +323,32 @@ int orbm_search_by_projection_frame_batch(const orbm_frames* cur, const float* T
                                           const int* cur_init_obs, int* assign_out, float th, int bMono, int checkOri,
                                           int* nmatches, void* cuda_stream);
 
+/* ---- order-free searches: ORBmatcher::Fuse and ORBmatcher::SearchBySim3 ------------------------------------------
+ * The search the reference runs for every projected map point in Fuse(KeyFrame*, const vector<MapPoint*>&, th)
+ * (src/ORBmatcher.cc:1364-1513), Fuse(KeyFrame*, cv::Mat Scw, const vector<MapPoint*>&, th, vpReplacePoint) (:1516-1633)
+ * and SearchBySim3 (:836-1052): among the keypoints KeyFrame::GetFeaturesInArea(u, v, radius) returns
+ * (src/KeyFrame.cc:637-676) at level[i] - 1 or level[i] (nPredictedLevel, :1436-1437 / :907-908 / :1593-1594) the one with
+ * the smallest descriptor distance, the first of them on ties.  With inv_sigma2 (= pKF->mvInvLevelSigma2, host, nlevels
+ * entries) the candidates must also pass Fuse's reprojection-error test (:1440-1469): (ex^2 + ey^2 + er^2) * inv_sigma2 <=
+ * 7.8 with er = ur[i] - mvuRight[k] when mvuRight[k] >= 0, (ex^2 + ey^2) * inv_sigma2 <= 5.99 otherwise.  No query depends
+ * on another one; what the reference does with a match afterwards (Replace / AddObservation / AddMapPoint, the mutual
+ * check of SearchBySim3) is the caller's (host/ORBmatcher_b200.hpp).
+ * best_idx [nq]: the keypoint, -1 when there is none or its distance exceeds th_accept (TH_LOW = 50 in Fuse, TH_HIGH = 100
+ * in SearchBySim3); best_dist [nq]: the smallest distance (256 without a candidate); *nfound: entries >= 0.
+ * uvr = u, v, radius per query; valid (or NULL) = 0 skips a query.  F's bounds are the KEY FRAME's (ints, include/KeyFrame.h:186-189). */
+int orbm_window_best_free(const orbm_frame* F, int nq, const float* uvr, const int* level, const float* ur, const uint8_t* valid,
+                          const uint8_t* qdesc, const float* inv_sigma2, int nlevels, int th_accept,
+                          int* best_idx, int* best_dist, int* nfound, int device);
+
+/* The same for nprob (key frame, point set) problems, device resident: arrays [nprob][nq_stride] (ur, valid may be NULL),
+ * best_idx / best_dist [nprob][nq_stride], nfound [nprob] (-1: a frame exceeds 8192 keypoints or a stride).  Only enqueues. */
+typedef struct {
+    const int* nq; int nq_stride;
+    const float* uvr; const int* level; const float* ur; const uint8_t* valid; const uint8_t* qdesc;
+} orbm_free_windows;
+int orbm_window_best_free_batch(const orbm_frames* F, const orbm_free_windows* Q, const float* inv_sigma2, int nlevels,
+                                int th_accept, int* best_idx, int* best_dist, int* nfound, void* cuda_stream);
+
 /* ORBmatcher::SearchForInitialization, src/ORBmatcher.cc:1055-1180, for nprob (F1, F2) pairs.  prev_matched
  * [nprob][F1.kp_stride][2] = vbPrevMatched (window centres; updated in place like the reference does), matches12
  * [nprob][F1.kp_stride] = vnMatches12, nmatches [nprob] the return value.  Frames with at most 8192 keypoints.

@@ -41,7 +41,7 @@ class MapPoint {
 public:
     MapPoint() : mTrackProjX(0), mTrackProjY(0), mTrackProjXR(0), mbTrackInView(false), mnTrackScaleLevel(0),
                  mTrackViewCos(0), mnTrackReferenceForFrame(0), mnLastFrameSeen(0), mnId(0), nObs(0), bad(false),
-                 maxDist(1e9f), minDist(0.f), maxDistRaw(0.f), realPredict(false) {}
+                 maxDist(1e9f), minDist(0.f), maxDistRaw(0.f), realPredict(false), replacedBy(NULL) {}
     // tracking variables read by ORBmatcher::SearchByProjection (src/ORBmatcher.cc:82-124)
     float mTrackProjX, mTrackProjY, mTrackProjXR;
     bool mbTrackInView;
@@ -68,10 +68,16 @@ public:
     bool realPredict;
     int PredictScale(const float& d, Frame* pF) { return realPredict ? PredictScaleReal(d, pF) : mnTrackScaleLevel; }
     int PredictScaleReal(const float& currentDist, Frame* pF);
-    int GetIndexInKeyFrame(KeyFrame*) { return -1; }
-    bool IsInKeyFrame(KeyFrame*) { return false; }
-    void Replace(MapPoint*) {}
-    void AddObservation(KeyFrame*, size_t) {}
+    // The observation bookkeeping that the loops of ORBmatcher::Fuse / SearchBySim3 can see (src/ORBmatcher.cc:1385, 1487-1502,
+    // 869-875): which key frames observe the point at which keypoint, and what MapPoint::AddObservation (src/MapPoint.cc:93-105)
+    // and MapPoint::Replace (:204-258) do to it.  Empty unless a harness fills it, so the other harnesses see the old
+    // "never in a key frame" behaviour.  Defined below, where KeyFrame is complete.
+    std::map<KeyFrame*, size_t> obs;
+    MapPoint* replacedBy;
+    int GetIndexInKeyFrame(KeyFrame* kf) { std::map<KeyFrame*, size_t>::iterator it = obs.find(kf); return it == obs.end() ? -1 : (int)it->second; }
+    bool IsInKeyFrame(KeyFrame* kf) { return obs.count(kf) != 0; }
+    inline void Replace(MapPoint* p);
+    inline void AddObservation(KeyFrame* kf, size_t idx);
     void IncreaseVisible(int = 1) {}
     void IncreaseFound(int = 1) {}
 };
@@ -130,6 +136,29 @@ public:
     cv::Mat GetPose() { return cv::Mat(); }
     bool isBad() { return false; }
 };
+
+// src/MapPoint.cc:93-105: a key frame is recorded once; a stereo observation counts twice
+inline void MapPoint::AddObservation(KeyFrame* kf, size_t idx)
+{
+    if (obs.count(kf)) return;
+    obs[kf] = idx;
+    nObs += (idx < kf->mvuRight.size() && kf->mvuRight[idx] >= 0) ? 2 : 1;
+}
+// src/MapPoint.cc:204-258: this point goes bad; every key frame that observed it now observes p at the same keypoint, unless
+// it observes p already, in which case the keypoint loses its point
+inline void MapPoint::Replace(MapPoint* p)
+{
+    if (p == this) return;
+    std::map<KeyFrame*, size_t> o = obs;
+    obs.clear();
+    bad = true;
+    replacedBy = p;
+    for (std::map<KeyFrame*, size_t>::iterator it = o.begin(); it != o.end(); ++it) {
+        KeyFrame* kf = it->first;
+        if (!p->IsInKeyFrame(kf)) { kf->mapPoints[it->second] = p; p->AddObservation(kf, it->second); }
+        else kf->mapPoints[it->second] = NULL;
+    }
+}
 
 // ORBVocabulary / Converter are only reached from Frame::ComputeBoW (src/Frame.cc:425-433)
 class ORBVocabulary {

@@ -120,6 +120,35 @@ int orbo_search_by_projection_sim3(int n, const orbo_kp* kps, const uint8_t* des
                                    const int* matched_in, int* assign_out, int th,
                                    float* uvr_out, int* minl_out, int* maxl_out, uint8_t* valid_out);
 
+/* order-free searches, orb_fuse_oracle.c: ORBmatcher::Fuse (src/ORBmatcher.cc:1364-1513, :1516-1633) and
+ * ORBmatcher::SearchBySim3 (:836-1052); map points are rows of plain arrays, -1 = NULL (see the file's header) */
+int orbo_window_best_free(int n, const orbo_kp* kps, const uint8_t* desc, const float* u_right,
+                          float minX, float maxX, float minY, float maxY,
+                          int nq, const float* uvr, const int* level, const float* ur, const uint8_t* valid, const uint8_t* qdesc,
+                          const float* inv_sigma2, int th_accept, int* best_idx, int* best_dist);
+int orbo_fuse(int n, const orbo_kp* kps, const uint8_t* desc, const float* u_right,
+              float minX, float maxX, float minY, float maxY, const float* scale, const float* inv_sigma2,
+              const float* K, float bf, const float* Rcw, const float* tcw, const float* Ow,
+              int npts, uint8_t* bad, const float* xyz, const float* normal, const uint8_t* mp_desc, const int* pred_level,
+              const float* min_dist, const float* max_dist, int* nobs, int* kf_idx, int* replaced_by,
+              int nlist, const int* list, int* kf_mp, float th,
+              float* uvr_out, int* level_out, float* ur_out, uint8_t* valid_out);
+int orbo_fuse_sim3(int n, const orbo_kp* kps, const uint8_t* desc, const float* u_right,
+                   float minX, float maxX, float minY, float maxY, const float* scale,
+                   const float* K, const float* Scw,
+                   int npts, uint8_t* bad, const float* xyz, const float* normal, const uint8_t* mp_desc, const int* pred_level,
+                   const float* min_dist, const float* max_dist, int* nobs, int* kf_idx,
+                   int nlist, const int* list, int* kf_mp, int* replace_out, float th,
+                   float* uvr_out, int* level_out, float* ur_out, uint8_t* valid_out);
+int orbo_search_by_sim3(int n1, const orbo_kp* kps1, const uint8_t* desc1, const int* mp1,
+                        int n2, const orbo_kp* kps2, const uint8_t* desc2, const int* mp2,
+                        float minX, float maxX, float minY, float maxY, const float* scale, const float* K,
+                        const float* R1w, const float* t1w, const float* R2w, const float* t2w, float s12, const float* R12, const float* t12,
+                        int npts, const uint8_t* bad, const float* xyz, const uint8_t* mp_desc, const int* pred_level,
+                        const float* min_dist, const float* max_dist, const int* idx_in_kf2,
+                        int* matches12, float th,
+                        float* uvr1_out, int* level1_out, uint8_t* valid1_out, float* uvr2_out, int* level2_out, uint8_t* valid2_out);
+
 /* Frame::ComputeStereoMatches, src/Frame.cc:513-699 */
 /* ORBmatcher::SearchByBoW, src/ORBmatcher.cc:552-697 (strict = 0, valid2 = NULL) and :700-832 (strict = 1). */
 int orbo_search_by_bow(int n1, const orbo_kp* kps1, const uint8_t* desc1, const uint8_t* valid1,

@@ -43,6 +43,12 @@ class OrbmPoints(C.Structure):
                 ("in_view", C.c_void_p), ("bad", C.c_void_p), ("observations", C.c_void_p), ("qdesc", C.c_void_p)]
 
 
+class OrbmFreeWindows(C.Structure):
+    """orbm_free_windows: device arrays [nprob][nq_stride] of the projected points of Fuse / SearchBySim3."""
+    _fields_ = [("nq", C.c_void_p), ("nq_stride", C.c_int), ("uvr", C.c_void_p), ("level", C.c_void_p), ("ur", C.c_void_p),
+                ("valid", C.c_void_p), ("qdesc", C.c_void_p)]
+
+
 class OrbmWindows(C.Structure):
     """orbm_windows: device arrays [nprob][nq_stride] of already projected best-only queries."""
     _fields_ = [("nq", C.c_void_p), ("nq_stride", C.c_int), ("uvr", C.c_void_p), ("min_level", C.c_void_p), ("max_level", C.c_void_p),
@@ -126,6 +132,8 @@ def lib():
         L.orbm_search_by_projection_frame.argtypes = [fp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, f32, vp, i32, vp, vp, f32, i32, i32, pi, i32]
         L.orbm_search_for_initialization.argtypes = [fp, fp, vp, vp, i32, f32, i32, pi, i32]
         L.orbm_window_search_best.argtypes = [fp, i32] + [vp] * 11 + [i32, i32, pi, i32]
+        L.orbm_window_best_free.argtypes = [fp, i32] + [vp] * 6 + [i32, i32, vp, vp, pi, i32]
+        L.orbm_window_best_free_batch.argtypes = [C.POINTER(OrbmFrames), C.POINTER(OrbmFreeWindows), vp, i32, i32, vp, vp, vp, vp]
         L.orbm_search_by_projection_points_batch.argtypes = [C.POINTER(OrbmFrames), vp, i32, C.POINTER(OrbmPoints), vp, vp, f32, f32, vp, vp, vp]
         L.orbm_window_search_best_batch.argtypes = [C.POINTER(OrbmFrames), C.POINTER(OrbmWindows), vp, vp, i32, i32, vp, vp, vp]
         L.orbm_search_by_projection_frame_batch.argtypes = [C.POINTER(OrbmFrames), vp, vp, vp, f32, vp, i32, vp, i32] + [vp] * 8 + [f32, i32, i32, vp, vp]
@@ -538,6 +546,36 @@ def window_search_best(F, uvr, min_level, max_level, qdesc, th_accept, check_ori
     if rc:
         raise OrbError(rc, "orbm_window_search_best failed")
     return nm.value, out
+
+
+def window_best_free(F, uvr, level, qdesc, th_accept, ur=None, valid=None, inv_sigma2=None, device=0):
+    """orbm_window_best_free: the search ORBmatcher::Fuse (src/ORBmatcher.cc:1364-1513, :1516-1633) and SearchBySim3
+    (:836-1052) run for every projected map point -- closest descriptor in the window at the predicted level or the one
+    below, optionally behind Fuse's chi-square test (inv_sigma2 = mvInvLevelSigma2, ur = projected right coordinates).
+    F: the KEY FRAME's keypoints with its (integer) image bounds.  Returns (nfound, best_idx [nq], best_dist [nq])."""
+    uvr, qdesc, level = _np(uvr, np.float32), _np(qdesc, np.uint8), _np(level, np.int32)
+    ur, va, s2 = _np(ur, np.float32), _np(valid, np.uint8), _np(inv_sigma2, np.float32)
+    nq = len(level)
+    bi, bd = np.zeros(nq, np.int32), np.zeros(nq, np.int32)
+    nf = C.c_int()
+    fs = F.struct()
+    p = lambda a: None if a is None else a.ctypes.data
+    rc = lib().orbm_window_best_free(C.byref(fs), nq, p(uvr), p(level), p(ur), p(va), p(qdesc), p(s2), 0 if s2 is None else len(s2),
+                                     int(th_accept), p(bi), p(bd), C.byref(nf), device)
+    if rc:
+        raise OrbError(rc, "orbm_window_best_free failed")
+    return nf.value, bi, bd
+
+
+def window_best_free_batch(frames, q, nq, nq_stride, best_idx, best_dist, nfound, th_accept, inv_sigma2=None, stream=None):
+    """orbm_window_best_free_batch.  q: dict of CUDA tensors uvr, level, desc and optionally ur, valid, each
+    [P,nq_stride(,3|32)]; best_idx / best_dist [P,nq_stride], nfound [P] int32 CUDA tensors.  Only enqueues."""
+    w = OrbmFreeWindows(_ptr(nq), nq_stride, _ptr(q["uvr"]), _ptr(q["level"]), _ptr(q.get("ur")), _ptr(q.get("valid")), _ptr(q["desc"]))
+    s2 = None if inv_sigma2 is None else np.ascontiguousarray(inv_sigma2, np.float32)
+    rc = lib().orbm_window_best_free_batch(C.byref(frames), C.byref(w), None if s2 is None else s2.ctypes.data, 0 if s2 is None else len(s2),
+                                           int(th_accept), _ptr(best_idx), _ptr(best_dist), _ptr(nfound), stream)
+    if rc:
+        raise OrbError(rc, "orbm_window_best_free_batch failed")
 
 
 def frames_batch(kps, desc, n, bounds, u_right=None, max_n=0):

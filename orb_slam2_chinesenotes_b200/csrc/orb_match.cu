@@ -889,6 +889,43 @@ int orbm_window_search_best(const orbm_frame* F, int nq, const float* uvr, const
     return resolve_best(S, D, nq, dq, list, count, cap, h_qobs.data(), h_angle.data(), h_obs.data(), assign_out, check_ori, th_accept, nmatches);
 }
 
+// One Fuse / SearchBySim3 search (orbm_window_best_free_batch with one problem): host arrays in, one launch, the two
+// result arrays and the count come back in one copy.
+int orbm_window_best_free(const orbm_frame* F, int nq, const float* uvr, const int* level, const float* ur, const uint8_t* valid,
+                          const uint8_t* qdesc, const float* inv_sigma2, int nlevels, int th_accept,
+                          int* best_idx, int* best_dist, int* nfound, int device)
+{
+    if (!F || nq < 0 || !nfound || (nq > 0 && (!uvr || !level || !qdesc || !best_idx || !best_dist))) return ORBX_E_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return ORBX_E_CUDA; }
+    *nfound = 0;
+    for (int i = 0; i < nq; ++i) { best_idx[i] = -1; best_dist[i] = 256; }
+    if (nq == 0 || F->n == 0) return ORBX_OK;
+    Scratch S;
+    OneFrame O;
+    if (!one_frame(S, F, &O)) return S.ok ? ORBX_E_ARG : ORBX_E_CUDA;
+    orbm_free_windows W;
+    int* d_nq = S.up(&nq, 1);
+    W.nq = d_nq; W.nq_stride = nq;
+    W.uvr = S.up(uvr, (size_t)nq * 3); W.level = S.up(level, (size_t)nq);
+    W.ur = ur ? S.up(ur, (size_t)nq) : nullptr;
+    W.valid = valid ? S.up(valid, (size_t)nq) : nullptr;
+    W.qdesc = S.up(qdesc, (size_t)nq * 32);
+    int* d_out = (int*)S.alloc(sizeof(int) * ((size_t)nq * 2 + 1));
+    if (!S.ok) return ORBX_E_CUDA;
+    if (!S.flush()) return ORBX_E_CUDA;
+    const int rc = orbm_window_best_free_batch(&O.F, &W, inv_sigma2, nlevels, th_accept, d_out, d_out + nq, d_out + 2 * (size_t)nq, nullptr);
+    if (rc) return rc;
+    thread_local std::vector<int> tmp;
+    tmp.resize((size_t)nq * 2 + 1);
+    const cudaError_t e = cudaMemcpy(tmp.data(), d_out, sizeof(int) * ((size_t)nq * 2 + 1), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { report_cuda(e, "orbm_window_best_free", __LINE__); cudaGetLastError(); return ORBX_E_CUDA; }
+    if (tmp[(size_t)nq * 2] < 0) return ORBX_E_ARG;          // more than 8192 keypoints
+    memcpy(best_idx, tmp.data(), sizeof(int) * (size_t)nq);
+    memcpy(best_dist, tmp.data() + nq, sizeof(int) * (size_t)nq);
+    *nfound = tmp[(size_t)nq * 2];
+    return ORBX_OK;
+}
+
 int orbm_search_for_initialization(const orbm_frame* F1, const orbm_frame* F2, float* prev_matched, int* matches12,
                                    int windowSize, float nnratio, int checkOri, int* nmatches, int device)
 {

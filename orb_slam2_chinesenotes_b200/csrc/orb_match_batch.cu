@@ -88,6 +88,9 @@ struct MbParams {
     uint32_t* cl;                    // workspace [nprob][kp_stride][MB_CL]: claimants (query << 9 | distance) of every position
     float window;
     int* rounds;                     // [nprob] or null: fixpoint rounds used (profiling / tests)
+    // order-free searches only (k_window_best_free)
+    int* best_dist;                  // [nprob][nq_stride]
+    int split, chi2;                 // blocks per problem; Fuse's reprojection-error test with scale[] = mvInvLevelSigma2
 };
 
 struct WinQ { float u, v, r, ur, er_max; int min_level, max_level, valid; };
@@ -732,6 +735,104 @@ __global__ void __launch_bounds__(MB_NT) k_init_fixpoint(const __grid_constant__
     if (tid == 0) *nm_out = s_cnt[0] - s_cnt[1];
 }
 
+// ------------------------------------------------------------------------------------------ order-free searches
+// The inner search that ORBmatcher::Fuse (src/ORBmatcher.cc:1364-1513 and :1516-1633) and ORBmatcher::SearchBySim3
+// (:836-1052) run for every projected map point: the closest descriptor among the keypoints KeyFrame::GetFeaturesInArea
+// (src/KeyFrame.cc:637-676) returns for the window, at the predicted level or the one below (:1436-1437, :907-908,
+// :1593-1594), first candidate on ties (strict <, :1478), accepted at TH_LOW (Fuse) or TH_HIGH (SearchBySim3).  Fuse(pKF,
+// vpMapPoints, th) also drops candidates whose reprojection error fails the chi-square test (:1440-1469): three degrees of
+// freedom (7.8) when the keypoint has a right coordinate (mvuRight >= 0), two (5.99) otherwise.
+// Unlike the searches above no query depends on another one -- what the reference does with a match (Replace,
+// AddObservation, the mutual check of SearchBySim3) happens after the search and stays with the caller -- so there is no
+// order to resolve: P.split blocks share a problem, each builds the position-ordered frame of k_match_fixpoint for itself
+// (redundant, but a single Fuse call then uses split SMs instead of one) and takes every split-th group of queries, 4 lanes
+// per query; per query the smallest (distance << 16 | position) key is the reference's answer.
+// LOC 0: records and descriptors in shared memory, 1: descriptors in the global workspace (frames above ~2700 keypoints).
+template <int LOC>
+__global__ void __launch_bounds__(MB_NT) k_window_best_free(const __grid_constant__ MbParams P)
+{
+    extern __shared__ __align__(16) uint32_t smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = MB_NT >> 5;
+    const int prob = blockIdx.x / P.split, part = blockIdx.x % P.split;
+    const int n = P.n[prob], nq = P.nq[prob];
+    if (n < 0 || n > P.sn_max || n > P.kp_stride || nq < 0 || nq > P.nq_stride) { if (tid == 0 && part == 0) P.nmatches[prob] = -1; return; }
+    const size_t ko = (size_t)prob * P.kp_stride, qo = (size_t)prob * P.nq_stride;
+    const orbx_kp* kps = P.kps + ko;
+    int sn = 32; while (sn < n) sn <<= 1;
+    uint32_t* keys = smem;                                  // [sn_max]
+    int* cell_start = (int*)(smem + P.sn_max);              // [GRID_CELLS + 1] (+3 pad)
+    int* tmp = cell_start + GRID_CELLS + 4;                 // [sn_max]
+    uint4* rec = (uint4*)(tmp + P.sn_max);                  // [sn_max]
+    uint4* sdesc = LOC == 0 ? rec + P.sn_max : (uint4*)(P.sdesc + ((size_t)blockIdx.x * P.kp_stride) * 8);
+    mb_sort_frame<MB_NT>(P, kps, n, sn, keys, cell_start, tmp);
+    const int nvalid = cell_start[GRID_CELLS];
+    for (int j = tid; j < nvalid; j += MB_NT) {
+        const int idx = (int)(keys[j] & 0xffffu);
+        const orbx_kp kp = kps[idx];
+        rec[j] = make_uint4(__float_as_uint(kp.x), __float_as_uint(kp.y), (uint32_t)(kp.octave & 0xff) | ((uint32_t)idx << 8),
+                            __float_as_uint(P.u_right ? P.u_right[ko + idx] : -1.0f));
+    }
+    for (int t = tid; t < nvalid * 8; t += MB_NT) {
+        const int j = t >> 3, wd = t & 7;
+        ((uint32_t*)sdesc)[(size_t)j * 8 + wd] = P.desc[(ko + (keys[j] & 0xffffu)) * 8 + wd];
+    }
+    __syncthreads();
+    constexpr int QW = 32 / MB_G;
+    const int sub = lane & (MB_G - 1);
+    int found = 0;
+    for (int base = (part * nwarps + warp) * QW; base < nq; base += P.split * nwarps * QW) {
+        const int q = base + lane / MB_G;
+        const bool live = q < nq && (!P.b0 || P.b0[qo + q]);
+        uint32_t best = MB_NONE;
+        if (live) {
+            const float u = P.f0[3 * (qo + q)], v = P.f0[3 * (qo + q) + 1], r = P.f0[3 * (qo + q) + 2];
+            const int level = P.i0[qo + q];
+            const float ur = P.f1 ? P.f1[qo + q] : 0.f;
+            const uint4 q0 = __ldg((const uint4*)(P.qdesc + (qo + q) * 8)), q1 = __ldg((const uint4*)(P.qdesc + (qo + q) * 8) + 1);
+            // src/KeyFrame.cc:642-656
+            const int nMinCellX = max(0, (int)floorf((u - P.min_x - r) * P.inv_w));
+            const int nMaxCellX = min(GRID_COLS - 1, (int)ceilf((u - P.min_x + r) * P.inv_w));
+            const int nMinCellY = max(0, (int)floorf((v - P.min_y - r) * P.inv_h));
+            const int nMaxCellY = min(GRID_ROWS - 1, (int)ceilf((v - P.min_y + r) * P.inv_h));
+            if (!(nMinCellX >= GRID_COLS || nMaxCellX < 0 || nMinCellY >= GRID_ROWS || nMaxCellY < 0))
+                for (int ix = nMinCellX; ix <= nMaxCellX; ++ix) {
+                    const int s0 = cell_start[ix * GRID_ROWS + nMinCellY], s1 = cell_start[ix * GRID_ROWS + nMaxCellY + 1];
+                    for (int j = s0 + sub; j < s1; j += MB_G) {
+                        const uint4 rc = rec[j];
+                        const int oct = (int)(rc.z & 0xffu);
+                        if (oct < level - 1 || oct > level) continue;                                        // :1436-1437
+                        const float ex = __fsub_rn(u, __uint_as_float(rc.x)), ey = __fsub_rn(v, __uint_as_float(rc.y));
+                        if (!(fabsf(ex) < r && fabsf(ey) < r)) continue;                                      // KeyFrame.cc:668
+                        if (P.chi2) {
+                            float e2 = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+                            const float kr = __uint_as_float(rc.w);
+                            if (kr >= 0) {                                                                    // :1442-1455
+                                const float er = __fsub_rn(ur, kr);
+                                e2 = __fadd_rn(e2, __fmul_rn(er, er));
+                                if ((double)__fmul_rn(e2, P.scale[oct]) > 7.8) continue;
+                            } else if ((double)__fmul_rn(e2, P.scale[oct]) > 5.99) continue;                  // :1457-1469
+                        }
+                        const uint4 b0 = sdesc[2 * j], b1 = sdesc[2 * j + 1];
+                        const uint32_t dist = __popc(q0.x ^ b0.x) + __popc(q0.y ^ b0.y) + __popc(q0.z ^ b0.z) + __popc(q0.w ^ b0.w) +
+                                              __popc(q1.x ^ b1.x) + __popc(q1.y ^ b1.y) + __popc(q1.z ^ b1.z) + __popc(q1.w ^ b1.w);
+                        best = min(best, (dist << 16) | (uint32_t)j);
+                    }
+                }
+        }
+#pragma unroll
+        for (int d = MB_G / 2; d > 0; d >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, d));
+        if (sub == 0 && q < nq) {
+            const int dist = best == MB_NONE ? 256 : (int)(best >> 16);
+            const bool ok = best != MB_NONE && dist <= P.th_accept;                                           // :1483 / :920 / :1607
+            P.assign_out[qo + q] = ok ? (int)(rec[best & 0xffffu].z >> 8) : -1;
+            P.best_dist[qo + q] = dist;
+            found += ok;
+        }
+    }
+    found = __reduce_add_sync(0xffffffffu, found);
+    if (lane == 0 && found) atomicAdd(P.nmatches + prob, found);
+}
+
 // ================================================================================ host side
 namespace {
 struct DevGuard {   // restores the caller's current device
@@ -872,6 +973,61 @@ int orbm_window_search_best_batch(const orbm_frames* F, const orbm_windows* Q, c
     P.init = init_obs; P.assign_out = assign_out; P.nmatches = nmatches; P.rounds = rounds;
     P.th_accept = th_accept; P.check_ori = check_ori;
     return launch<MODE_BEST>(P, F->nprob, (cudaStream_t)cuda_stream);
+}
+
+int orbm_window_best_free_batch(const orbm_frames* F, const orbm_free_windows* Q, const float* inv_sigma2, int nlevels,
+                                int th_accept, int* best_idx, int* best_dist, int* nfound, void* cuda_stream)
+{
+    MbParams P = {};
+    if (!fill_frames(P, F) || !Q || !Q->nq || Q->nq_stride <= 0 || !Q->uvr || !Q->level || !Q->qdesc || !best_idx || !best_dist || !nfound ||
+        (inv_sigma2 && (nlevels <= 0 || nlevels > MB_MAX_LEVELS)))
+        return ORBX_E_ARG;
+    if ((uintptr_t)Q->qdesc & 15) return ORBX_E_ARG;
+    const int nprob = F->nprob;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    P.nq = Q->nq; P.nq_stride = Q->nq_stride;
+    P.f0 = Q->uvr; P.i0 = Q->level; P.f1 = Q->ur; P.b0 = Q->valid; P.qdesc = (const uint32_t*)Q->qdesc;
+    P.assign_out = best_idx; P.best_dist = best_dist; P.nmatches = nfound; P.th_accept = th_accept;
+    P.chi2 = inv_sigma2 != nullptr;
+    // a keypoint's octave indexes the table: levels the caller did not supply get 0 (every error passes), as no
+    // keypoint of the key frame can lie there
+    for (int i = 0; i < MB_MAX_LEVELS; ++i) P.scale[i] = (inv_sigma2 && i < nlevels) ? inv_sigma2[i] : 0.f;
+    const int dev = device_of(P.kps);
+    if (dev < 0 || device_of(best_idx) != dev || device_of(best_dist) != dev || device_of(nfound) != dev || device_of(P.qdesc) != dev) return ORBX_E_ARG;
+    DevGuard g;
+    if (cudaGetDevice(&g.prev) != cudaSuccess || cudaSetDevice(dev) != cudaSuccess) { cudaGetLastError(); return ORBX_E_CUDA; }
+    int sn = 32; while (sn < P.n_bound && sn < MB_MAX_KP) sn <<= 1;
+    P.sn_max = sn;
+    size_t smem = ((size_t)sn * 2 + GRID_CELLS + 4) * 4 + (size_t)sn * 16;
+    const bool desc_in_smem = smem + (size_t)sn * 32 <= kSmemMax;
+    if (desc_in_smem) smem += (size_t)sn * 32;
+    if (smem > kSmemMax) return ORBX_E_ARG;
+    // blocks per problem: enough to cover the GPU when the launch holds a handful of problems, at most one block per
+    // trip of 256 queries
+    int split = 148 / nprob;
+    const int trips = (Q->nq_stride + MB_NT / MB_G - 1) / (MB_NT / MB_G);
+    if (split > trips) split = trips;
+    if (split > 16) split = 16;
+    if (split < 1) split = 1;
+    P.split = split;
+    void* ws = nullptr;
+    if (!desc_in_smem) {
+        if (cudaMallocAsync(&ws, (size_t)nprob * split * P.kp_stride * 32 + 16, st) != cudaSuccess) { cudaGetLastError(); return ORBX_E_CUDA; }
+        P.sdesc = (uint32_t*)ws;
+    }
+    cudaError_t e = cudaMemsetAsync(nfound, 0, sizeof(int) * (size_t)nprob, st);
+    if (e == cudaSuccess) {
+        if (desc_in_smem) {
+            if (smem > 48 * 1024) e = cudaFuncSetAttribute(k_window_best_free<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
+            if (e == cudaSuccess) { k_window_best_free<0><<<nprob * split, MB_NT, smem, st>>>(P); e = cudaGetLastError(); }
+        } else {
+            if (smem > 48 * 1024) e = cudaFuncSetAttribute(k_window_best_free<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
+            if (e == cudaSuccess) { k_window_best_free<1><<<nprob * split, MB_NT, smem, st>>>(P); e = cudaGetLastError(); }
+        }
+    }
+    if (ws) cudaFreeAsync(ws, st);
+    if (e != cudaSuccess) { if (getenv("ORB_B200_DEBUG")) fprintf(stderr, "orb_b200: k_window_best_free: %s\n", cudaGetErrorString(e)); cudaGetLastError(); return ORBX_E_CUDA; }
+    return ORBX_OK;
 }
 
 int orbm_search_for_initialization_batch(const orbm_frames* F1, const orbm_frames* F2, float* prev_matched, int* matches12,

@@ -6,6 +6,7 @@ ref_extract_*.npz    outputs of the reference's UNMODIFIED ORBextractor.cc (orac
                      built from /root/reference against oracle/cvshim + bump arena): pins the oracle
                      restatement and, through it, the CUDA path
 ref_match_*.npz      outputs of the reference's UNMODIFIED ORBmatcher.cc on mock frames
+ref_fuse.npz         the same for ORBmatcher::Fuse (both overloads) and ORBmatcher::SearchBySim3
 """
 import ctypes as C
 import os
@@ -147,8 +148,32 @@ def bow():
     np.savez_compressed(os.path.join(HERE, "ref_bow.npz"), **out)
 
 
+def fuse():
+    """Outputs of the reference's unmodified ORBmatcher::Fuse (both overloads, src/ORBmatcher.cc:1364-1633) and
+    ORBmatcher::SearchBySim3 (:836-1052) on the scenes of tests/fuse_lib.py (regenerated from seeds; results stored)."""
+    from fuse_lib import fuse_scene, run_fuse, run_search_by_sim3, sim3_pair_scene
+    from matcher_lib import extract_frame, perturbed_frame
+    from test_fuse_oracle import BF, BOUNDS, FUSE_CASES, H, K, NF, SIM3_CASES, W
+    kps, desc, scale = extract_frame(W, H, NF, 2)
+    k2, d2, _ = perturbed_frame(kps, desc, W, H, 11, shift=4, kmax=40)
+    inv_sigma2 = (np.float32(1.0) / (scale * scale)).astype(np.float32)
+    out = {}
+    for th, seed, sim3, stereo in FUSE_CASES:
+        s = fuse_scene(kps, desc, W, H, seed, K, BF, sim3)
+        nf, st, _ = run_fuse("ref", kps, desc, s, scale, inv_sigma2, BOUNDS, K, BF, th, sim3, stereo)
+        out[f"fuse_{seed}_n"] = nf
+        for k, v in st.items():
+            out[f"fuse_{seed}_{k}"] = v
+    for th, seed in SIM3_CASES:
+        s = sim3_pair_scene(kps, desc, k2, d2, W, H, seed, K)
+        nf, m12, _ = run_search_by_sim3("ref", kps, desc, k2, d2, s, scale, BOUNDS, K, th)
+        out[f"sim3_{seed}_n"] = nf
+        out[f"sim3_{seed}_m12"] = m12
+    np.savez_compressed(os.path.join(HERE, "ref_fuse.npz"), **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["primitives", "extractor", "matchers", "projection_overloads", "mappoint", "bow"]
+    which = sys.argv[1:] or ["primitives", "extractor", "matchers", "projection_overloads", "mappoint", "bow", "fuse"]
     for name in which:
         globals()[name]()
     print("golden fixtures written to", HERE)
