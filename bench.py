@@ -543,6 +543,33 @@ def bench_mappoint_side(dev, d_kps, d_desc, d_n, cap, w, h, scale_factor, reps=4
     pairs = float((sizes.double() ** 2).sum().item())
     out["distinctive"] = {"value": npnt / (ms * 1e-3), "unit": "map points/s", "points_per_launch": npnt, "observations": total,
                           "ms_per_launch": ms, "Gpairs_per_s": pairs / (ms * 1e-3) / 1e9}
+    # ---- fuse: the order-free search of ORBmatcher::Fuse (chi-square gate on) for nf key frames x 2000 projected points
+    nfz = min((d_kps.shape[0] // 2) // sms * sms or 1, 3 * sms)
+    kF, dF, nF = d_kps[0:2 * nfz:2].contiguous(), d_desc[0:2 * nfz:2].contiguous(), d_n[0:2 * nfz:2].contiguous()
+    nqf = 2000
+    tgt = (torch.rand((nfz, nqf), generator=g, device=dev) * nF[:, None]).long().clamp_(max=cap - 1)
+    kq = torch.gather(kF, 1, tgt[..., None].expand(-1, -1, 7))
+    lvl = kq[..., 5].contiguous().view(torch.int32).clone()
+    scale_t = torch.tensor([scale_factor ** i for i in range(LEVELS)], device=dev, dtype=torch.float32)
+    fq = dict(uvr=torch.stack([kq[..., 0] + 1.5 * torch.randn((nfz, nqf), generator=g, device=dev),
+                               kq[..., 1] + 1.5 * torch.randn((nfz, nqf), generator=g, device=dev),
+                               3.0 * scale_t[lvl.long().clamp_(0, LEVELS - 1)]], dim=2).contiguous(),
+              level=lvl, desc=torch.gather(dF, 1, tgt[..., None].expand(-1, -1, 32)).clone())
+    fq["desc"][:, :, :3] ^= torch.randint(0, 256, (nfz, nqf, 3), generator=g, device=dev, dtype=torch.uint8)
+    fq["ur"] = (fq["uvr"][..., 0] - 30 * torch.rand((nfz, nqf), generator=g, device=dev)).contiguous()
+    urF = torch.where(torch.rand((nfz, cap), generator=g, device=dev) < 0.5, kF[..., 0] - 30 * torch.rand((nfz, cap), generator=g, device=dev),
+                      torch.full((nfz, cap), -1.0, device=dev)).contiguous()
+    inv_sigma2 = (np.float32(1.0) / np.float32([np.float32(scale_factor) ** i for i in range(LEVELS)]) ** 2).astype(np.float32)
+    f_nq = torch.full((nfz,), nqf, dtype=torch.int32, device=dev)
+    f_bi = torch.zeros((nfz, nqf), dtype=torch.int32, device=dev)
+    f_bd = torch.zeros((nfz, nqf), dtype=torch.int32, device=dev)
+    f_nf = torch.zeros(nfz, dtype=torch.int32, device=dev)
+    max_n = ob.max_keypoints(WORKLOADS["kitti_1241x376_nf2000"][2], SCALE, LEVELS, INI_TH, MIN_TH, w, h)
+    FF = ob.frames_batch(kF, dF, nF, bounds, urF, max_n)
+    ms = timed(lambda: ob.window_best_free_batch(FF, fq, f_nq, nqf, f_bi, f_bd, f_nf, 50, inv_sigma2, stream.cuda_stream))
+    out["fuse"] = {"value": nfz / (ms * 1e-3), "unit": "problems/s", "what": "the search of ORBmatcher::Fuse(KeyFrame, MapPoints, th=3): 2000 projected "
+                   "points per key frame, chi-square gate, TH_LOW", "problems_per_launch": nfz, "points_per_problem": nqf, "ms_per_launch": ms,
+                   "points_per_s": nfz * nqf / (ms * 1e-3), "fused_per_problem": float(f_nf.float().mean().item())}
     if cpu:
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         from bow_lib import search_by_bow
@@ -572,6 +599,18 @@ def bench_mappoint_side(dev, d_kps, d_desc, d_n, cap, w, h, scale_factor, reps=4
         dt = (time.perf_counter() - t0) / 20
         assert want[0] == int(nm[0].item()) and (want[1] == m12[0, :n0].cpu().numpy()).all(), "SearchByBoW disagrees with the CPU checker"
         out["bow"]["cpu_baseline"] = {"value": 1.0 / dt, "unit": "problems/s", "cores": 1, "kind": "port", "sample": "problem 0, 20 repetitions, results compared"}
+        # fuse, problem 0
+        from fuse_lib import window_best_free_oracle
+        n0 = int(nF[0].item())
+        kp0 = tonp(kF[0, :n0]).view(oracle_lib.KP_DTYPE).reshape(n0)
+        q0 = dict(uvr=tonp(fq["uvr"][0]), level=tonp(fq["level"][0]), ur=tonp(fq["ur"][0]))
+        t0 = time.perf_counter()
+        for _ in range(5):
+            w_n, w_bi, w_bd = window_best_free_oracle(kp0, tonp(dF[0, :n0]), tonp(urF[0, :n0]), bounds, q0, tonp(fq["desc"][0]), inv_sigma2, 50)
+        dt = (time.perf_counter() - t0) / 5
+        assert w_n == int(f_nf[0].item()) and w_n > 100 and (w_bi == f_bi[0].cpu().numpy()).all() and (w_bd == f_bd[0].cpu().numpy()).all(), \
+            "the Fuse search disagrees with the CPU checker"
+        out["fuse"]["cpu_baseline"] = {"value": 1.0 / dt, "unit": "problems/s", "cores": 1, "kind": "port", "sample": "problem 0, 5 repetitions, results compared"}
         # distinctive, first 2000 points
         offh, obsh = off.cpu().numpy(), obs.cpu().numpy()
         t0 = time.perf_counter()

@@ -22,12 +22,11 @@
 
 /* best candidate of one window: KeyFrame::GetFeaturesInArea (src/KeyFrame.cc:637-676) + the candidate loop
  * (src/ORBmatcher.cc:1428-1481 with chi2, :1586-1604 / :900-918 without) */
-static int best_in_window(int n, const orbo_kp* kps, const uint8_t* desc, const float* u_right,
-                          float minX, float maxX, float minY, float maxY,
+static int best_in_window(const void* grid, int n, const orbo_kp* kps, const uint8_t* desc, const float* u_right,
                           float u, float v, float radius, int level, float ur, const uint8_t* qd,
                           const float* inv_sigma2, int* cand, int* best_dist_out)
 {
-    int nc = orbo_features_in_area(n, kps, minX, maxX, minY, maxY, u, v, radius, -1, -1, cand, n);
+    int nc = orbo_grid_query(grid, u, v, radius, -1, -1, cand, n);
     if (nc > n) nc = n;
     int bestDist = INT_MAX, bestIdx = -1;
     for (int c = 0; c < nc; ++c) {
@@ -59,16 +58,18 @@ int orbo_window_best_free(int n, const orbo_kp* kps, const uint8_t* desc, const 
                           const float* inv_sigma2, int th_accept, int* best_idx, int* best_dist)
 {
     int* cand = (int*)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
+    void* grid = orbo_grid_create(n, kps, minX, maxX, minY, maxY);
     int found = 0;
     for (int i = 0; i < nq; ++i) {
         best_idx[i] = -1; best_dist[i] = 256;
         if (valid && !valid[i]) continue;
         int d;
-        const int b = best_in_window(n, kps, desc, u_right, minX, maxX, minY, maxY, uvr[3 * i], uvr[3 * i + 1], uvr[3 * i + 2], level[i],
+        const int b = best_in_window(grid, n, kps, desc, u_right, uvr[3 * i], uvr[3 * i + 1], uvr[3 * i + 2], level[i],
                                      ur ? ur[i] : 0.f, qdesc + (size_t)i * 32, inv_sigma2, cand, &d);
         if (b >= 0) best_dist[i] = d;
         if (b >= 0 && d <= th_accept) { best_idx[i] = b; ++found; }
     }
+    orbo_grid_destroy(grid);
     free(cand);
     return found;
 }
@@ -122,6 +123,7 @@ static int fuse_body(int sim3, int n, const orbo_kp* kps, const uint8_t* desc, c
     const float fx = K[0], fy = K[1], cx = K[2], cy = K[3];
     const int iminX = (int)minX, imaxX = (int)maxX, iminY = (int)minY, imaxY = (int)maxY;   /* KeyFrame keeps int bounds */
     int* cand = (int*)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
+    void* grid = orbo_grid_create(n, kps, (float)iminX, maxX, (float)iminY, maxY);   /* the key frame's grid origin is its int bound */
     uint8_t* found0 = (uint8_t*)calloc((size_t)(npts > 0 ? npts : 1), 1);
     uint8_t* bad0 = (uint8_t*)malloc((size_t)(npts > 0 ? npts : 1));
     int* kfidx0 = (int*)malloc(sizeof(int) * (size_t)(npts > 0 ? npts : 1));
@@ -157,7 +159,7 @@ static int fuse_body(int sim3, int n, const orbo_kp* kps, const uint8_t* desc, c
         if (uvr_out && !skip_start) { uvr_out[3 * i] = u; uvr_out[3 * i + 1] = v; uvr_out[3 * i + 2] = radius; level_out[i] = lvl; ur_out[i] = ur; valid_out[i] = 1; }
         if (skip_now) continue;
         int bestDist;
-        const int bestIdx = best_in_window(n, kps, desc, u_right, (float)iminX, maxX, (float)iminY, maxY, u, v, radius, lvl, ur,
+        const int bestIdx = best_in_window(grid, n, kps, desc, u_right, u, v, radius, lvl, ur,
                                            mp_desc + (size_t)p * 32, sim3 ? NULL : inv_sigma2, cand, &bestDist);
         if (bestIdx >= 0 && bestDist <= 50) {                                                /* TH_LOW, :1483 / :1607 */
             const int inKF = kf_mp[bestIdx];
@@ -174,6 +176,7 @@ static int fuse_body(int sim3, int n, const orbo_kp* kps, const uint8_t* desc, c
             nFused++;
         }
     }
+    orbo_grid_destroy(grid);
     free(kfidx0); free(bad0); free(found0); free(cand);
     return nFused;
 }
@@ -240,6 +243,7 @@ static void sim3_direction(int nA, const int* mpA, const uint8_t* already, const
     const float fx = K[0], fy = K[1], cx = K[2], cy = K[3];
     const int iminX = (int)minX, imaxX = (int)maxX, iminY = (int)minY, imaxY = (int)maxY;
     int* cand = (int*)malloc(sizeof(int) * (size_t)(nB > 0 ? nB : 1));
+    void* grid = orbo_grid_create(nB, kpsB, (float)iminX, maxX, (float)iminY, maxY);
     for (int i = 0; i < nA; ++i) {
         match[i] = -1;
         if (uvr_out) { uvr_out[3 * i] = uvr_out[3 * i + 1] = uvr_out[3 * i + 2] = 0.f; level_out[i] = 0; valid_out[i] = 0; }
@@ -262,10 +266,11 @@ static void sim3_direction(int nA, const int* mpA, const uint8_t* already, const
         const float radius = th * scale[lvl];
         if (uvr_out) { uvr_out[3 * i] = u; uvr_out[3 * i + 1] = v; uvr_out[3 * i + 2] = radius; level_out[i] = lvl; valid_out[i] = 1; }
         int bestDist;
-        const int bestIdx = best_in_window(nB, kpsB, descB, NULL, (float)iminX, maxX, (float)iminY, maxY, u, v, radius, lvl, 0.f,
+        const int bestIdx = best_in_window(grid, nB, kpsB, descB, NULL, u, v, radius, lvl, 0.f,
                                            mp_desc + (size_t)p * 32, NULL, cand, &bestDist);
         if (bestIdx >= 0 && bestDist <= 100) match[i] = bestIdx;                             /* TH_HIGH, :920 / :971 */
     }
+    orbo_grid_destroy(grid);
     free(cand);
 }
 

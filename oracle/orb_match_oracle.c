@@ -100,6 +100,19 @@ int orbo_features_in_area(int n, const orbo_kp* kps, float minX, float maxX, flo
     return cnt;
 }
 
+/* The same grid kept across queries (a Frame / KeyFrame builds it once, src/Frame.cc:243-259): orb_fuse_oracle.c */
+void* orbo_grid_create(int n, const orbo_kp* kps, float minX, float maxX, float minY, float maxY)
+{
+    grid_t* g = (grid_t*)malloc(sizeof(grid_t));
+    grid_build(g, n, kps, minX, maxX, minY, maxY);
+    return g;
+}
+int orbo_grid_query(const void* g, float x, float y, float r, int minLevel, int maxLevel, int* out, int cap)
+{
+    return grid_query((const grid_t*)g, x, y, r, minLevel, maxLevel, out, cap);
+}
+void orbo_grid_destroy(void* g) { if (g) { grid_free((grid_t*)g); free(g); } }
+
 /* ComputeThreeMaxima, src/ORBmatcher.cc:1663-1707 */
 static void three_maxima(const int* sizes, int L, int* ind1, int* ind2, int* ind3)
 {

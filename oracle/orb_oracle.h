@@ -120,6 +120,11 @@ int orbo_search_by_projection_sim3(int n, const orbo_kp* kps, const uint8_t* des
                                    const int* matched_in, int* assign_out, int th,
                                    float* uvr_out, int* minl_out, int* maxl_out, uint8_t* valid_out);
 
+/* Frame::AssignFeaturesToGrid once, Frame / KeyFrame::GetFeaturesInArea many times */
+void* orbo_grid_create(int n, const orbo_kp* kps, float minX, float maxX, float minY, float maxY);
+int orbo_grid_query(const void* grid, float x, float y, float r, int minLevel, int maxLevel, int* out, int cap);
+void orbo_grid_destroy(void* grid);
+
 /* order-free searches, orb_fuse_oracle.c: ORBmatcher::Fuse (src/ORBmatcher.cc:1364-1513, :1516-1633) and
  * ORBmatcher::SearchBySim3 (:836-1052); map points are rows of plain arrays, -1 = NULL (see the file's header) */
 int orbo_window_best_free(int n, const orbo_kp* kps, const uint8_t* desc, const float* u_right,

@@ -21,6 +21,13 @@
 //   { return b200::SearchByBoW(pKF, F, vpMapPointMatches, mfNNratio, mbCheckOrientation); }          // src/ORBmatcher.cc:552
 //   int ORBmatcher::SearchByBoW(KeyFrame *pKF1, KeyFrame *pKF2, vector<MapPoint*> &vpMatches12)
 //   { return b200::SearchByBoW(pKF1, pKF2, vpMatches12, mfNNratio, mbCheckOrientation); }            // src/ORBmatcher.cc:700
+//   int ORBmatcher::Fuse(KeyFrame *pKF, const vector<MapPoint *> &vpMapPoints, const float th)
+//   { return b200::Fuse(pKF, vpMapPoints, th); }                                         // src/ORBmatcher.cc:1364
+//   int ORBmatcher::Fuse(KeyFrame *pKF, cv::Mat Scw, const vector<MapPoint *> &vpPoints, float th, vector<MapPoint *> &vpReplacePoint)
+//   { return b200::Fuse(pKF, Scw, vpPoints, th, vpReplacePoint); }                       // src/ORBmatcher.cc:1516
+//   int ORBmatcher::SearchBySim3(KeyFrame *pKF1, KeyFrame *pKF2, vector<MapPoint*> &vpMatches12, const float &s12,
+//                                const cv::Mat &R12, const cv::Mat &t12, const float th)
+//   { return b200::SearchBySim3(pKF1, pKF2, vpMatches12, s12, R12, t12, th); }           // src/ORBmatcher.cc:836
 //   the isInFrustum loop of Tracking::SearchLocalPoints -> b200::IsInFrustum(F, vpPoints, 0.5f, inView)
 //   the distance-matrix / median part of MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:311-334)
 //   -> BestIdx = b200::DistinctiveDescriptor(vDescriptors)
@@ -521,6 +528,249 @@ int DistinctiveDescriptor(const std::vector<MatT>& vDescriptors)
     int best = -1;
     Check(orbm_distinctive_descriptor(&d[0], (int)n, 0, &best, 0, Device()), "orbm_distinctive_descriptor");
     return best;
+}
+
+// ---- Fuse and SearchBySim3: searches whose queries do not depend on one another --------------------------------------
+// What the reference does per map point is (1) project, (2) find the closest descriptor in the window at the predicted level
+// or the one below, (3) update the map (Replace / AddObservation / AddMapPoint, or the mutual check of SearchBySim3).  Only
+// (3) reads state that earlier points changed, and it never feeds back into (2), so the forwarders project every point on the
+// host in the reference's arithmetic (matrix products accumulate in float, cv::norm and cv::Mat::dot in double), search all of
+// them in one device call (orbm_window_best_free) and then replay (3) in the reference's order with its tests re-evaluated
+// on the changing state.
+namespace detail {
+inline void MulAdd3(const float* R, const float* t, const float* x, float* out)      // R*x + t as cv::Mat computes it
+{
+    for (int r = 0; r < 3; ++r) {
+        float s = R[3 * r] * x[0];
+        s = s + R[3 * r + 1] * x[1];
+        s = s + R[3 * r + 2] * x[2];
+        out[r] = s + t[r];
+    }
+}
+template <class MatT> inline void Read3x3(const MatT& m, float* R) { for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) R[3 * r + c] = m.template at<float>(r, c); }
+template <class MatT> inline void Read3(const MatT& m, float* t) { for (int r = 0; r < 3; ++r) t[r] = m.template at<float>(r); }
+
+struct FreeQueries {
+    std::vector<float> uvr, ur;
+    std::vector<int> level;
+    std::vector<unsigned char> valid, desc;
+    explicit FreeQueries(size_t n) : uvr(3 * (n ? n : 1), 0.f), ur(n ? n : 1, 0.f), level(n ? n : 1, 0), valid(n ? n : 1, 0), desc(32 * (n ? n : 1), 0) {}
+};
+
+// Projection + gates of one candidate point of Fuse (src/ORBmatcher.cc:1388-1425 / :1546-1583); doubleInvZ: the Sim3 overload
+// divides 1.0 (double) by z, the pose overload 1 (int -> float).  Fills query i and returns true when the point reaches the search.
+template <class KeyFrameT, class MapPointT>
+inline bool FuseQuery(KeyFrameT* pKF, MapPointT* pMP, const float* R, const float* t, const float* Ow, float bf, float th, bool doubleInvZ,
+                      FreeQueries& Q, size_t i)
+{
+    float x[3], pc[3];
+    Read3(pMP->GetWorldPos(), x);
+    MulAdd3(R, t, x, pc);
+    if (pc[2] < 0.0f) return false;
+    const float invz = doubleInvZ ? (float)(1.0 / (double)pc[2]) : 1 / pc[2];
+    const float xn = pc[0] * invz, yn = pc[1] * invz;
+    const float u = pKF->fx * xn + pKF->cx, v = pKF->fy * yn + pKF->cy;
+    if (!(u >= pKF->mnMinX && u < pKF->mnMaxX && v >= pKF->mnMinY && v < pKF->mnMaxY)) return false;     // KeyFrame::IsInImage
+    float PO[3];
+    double acc = 0;
+    for (int r = 0; r < 3; ++r) { PO[r] = x[r] - Ow[r]; acc += (double)PO[r] * (double)PO[r]; }
+    const float dist3D = (float)std::sqrt(acc);
+    if (dist3D < pMP->GetMinDistanceInvariance() || dist3D > pMP->GetMaxDistanceInvariance()) return false;
+    float Pn[3];
+    Read3(pMP->GetNormal(), Pn);
+    double dn = 0;
+    for (int r = 0; r < 3; ++r) dn += (double)PO[r] * (double)Pn[r];
+    if (dn < 0.5 * dist3D) return false;
+    const int lvl = pMP->PredictScale(dist3D, pKF);
+    Q.uvr[3 * i] = u; Q.uvr[3 * i + 1] = v; Q.uvr[3 * i + 2] = th * pKF->mvScaleFactors[(size_t)lvl];
+    Q.ur[i] = u - bf * invz;
+    Q.level[i] = lvl; Q.valid[i] = 1;
+    std::memcpy(&Q.desc[32 * i], pMP->GetDescriptor().ptr(0), 32);
+    return true;
+}
+} // namespace detail
+
+// ORBmatcher::Fuse(KeyFrame* pKF, const vector<MapPoint*>& vpMapPoints, const float th), src/ORBmatcher.cc:1364-1513.
+// Reads pKF->GetRotation(), GetTranslation(), GetCameraCenter(), fx, fy, cx, cy, mbf, mnMinX..mnMaxY, mvKeysUn, mvuRight,
+// mDescriptors, mvScaleFactors, mvInvLevelSigma2, GetMapPoint(); MapPoint::isBad(), IsInKeyFrame(), GetWorldPos(),
+// GetNormal(), Get{Min,Max}DistanceInvariance(), PredictScale(), GetDescriptor(), Observations(); writes through
+// MapPoint::Replace(), AddObservation() and KeyFrame::AddMapPoint() exactly where the reference does.
+template <class KeyFrameT, class MapPointT>
+int Fuse(KeyFrameT* pKF, const std::vector<MapPointT*>& vpMapPoints, const float th)
+{
+    const int TH_LOW = 50;
+    float R[9], t[3], Ow[3];
+    detail::Read3x3(pKF->GetRotation(), R); detail::Read3(pKF->GetTranslation(), t); detail::Read3(pKF->GetCameraCenter(), Ow);
+    const size_t nq = vpMapPoints.size();
+    detail::FreeQueries Q(nq);
+    for (size_t i = 0; i < nq; ++i) {
+        MapPointT* pMP = vpMapPoints[i];
+        if (!pMP || pMP->isBad() || pMP->IsInKeyFrame(pKF)) continue;                   // :1383-1386 (re-tested below)
+        detail::FuseQuery(pKF, pMP, R, t, Ow, pKF->mbf, th, false, Q, i);
+    }
+    const orbm_frame view = ResidentFrames::Local().Get((unsigned long)pKF->mnFrameId, (double)pKF->mTimeStamp, pKF->mvKeysUn, pKF->mDescriptors,
+                                                        &pKF->mvuRight, (float)pKF->mnMinX, (float)pKF->mnMaxX, (float)pKF->mnMinY, (float)pKF->mnMaxY);
+    std::vector<int> best(nq ? nq : 1, -1), dist(nq ? nq : 1, 256);
+    int found = 0;
+    Check(orbm_window_best_free(&view, (int)nq, &Q.uvr[0], &Q.level[0], &Q.ur[0], &Q.valid[0], &Q.desc[0], Ptr(pKF->mvInvLevelSigma2),
+                                (int)pKF->mvInvLevelSigma2.size(), TH_LOW, &best[0], &dist[0], &found, Device()), "orbm_window_best_free");
+    int nFused = 0;
+    for (size_t i = 0; i < nq; ++i) {
+        MapPointT* pMP = vpMapPoints[i];
+        if (!pMP || !Q.valid[i] || best[i] < 0) continue;
+        if (pMP->isBad() || pMP->IsInKeyFrame(pKF)) continue;                           // state earlier points may have changed
+        MapPointT* pMPinKF = pKF->GetMapPoint((size_t)best[i]);
+        if (pMPinKF) {
+            if (!pMPinKF->isBad()) {                                                    // :1489-1495
+                if (pMPinKF->Observations() > pMP->Observations()) pMP->Replace(pMPinKF);
+                else pMPinKF->Replace(pMP);
+            }
+        } else {
+            pMP->AddObservation(pKF, (size_t)best[i]);                                  // :1500-1501
+            pKF->AddMapPoint(pMP, (size_t)best[i]);
+        }
+        nFused++;
+    }
+    return nFused;
+}
+
+// ORBmatcher::Fuse(KeyFrame* pKF, cv::Mat Scw, const vector<MapPoint*>& vpPoints, float th, vector<MapPoint*>& vpReplacePoint),
+// src/ORBmatcher.cc:1516-1633 (loop closing): pose from the Sim3, no chi-square test, points the key frame holds at the start
+// are skipped, a keypoint that holds a point already is reported in vpReplacePoint instead of replaced.
+template <class KeyFrameT, class MatT, class MapPointT>
+int Fuse(KeyFrameT* pKF, const MatT& Scw, const std::vector<MapPointT*>& vpPoints, float th, std::vector<MapPointT*>& vpReplacePoint)
+{
+    const int TH_LOW = 50;
+    float S[12];
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 4; ++c) S[4 * r + c] = Scw.template at<float>(r, c);
+    double d = 0;
+    for (int c = 0; c < 3; ++c) d += (double)S[c] * (double)S[c];
+    const float scw = (float)std::sqrt(d);                                              // :1525
+    const double inv = 1.0 / (double)scw;
+    float R[9], t[3], Ow[3];
+    for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c) R[3 * r + c] = (float)((double)S[4 * r + c] * inv);
+        t[r] = (float)((double)S[4 * r + 3] * inv);
+    }
+    for (int i = 0; i < 3; ++i) {                                                       // Ow = -Rcw.t()*tcw (:1528)
+        float s = (float)((double)R[i] * -1.0) * t[0];
+        s = s + (float)((double)R[3 + i] * -1.0) * t[1];
+        s = s + (float)((double)R[6 + i] * -1.0) * t[2];
+        Ow[i] = s;
+    }
+    const std::set<MapPointT*> spAlreadyFound = pKF->GetMapPoints();                    // :1531
+    const size_t nq = vpPoints.size();
+    detail::FreeQueries Q(nq);
+    for (size_t i = 0; i < nq; ++i) {
+        MapPointT* pMP = vpPoints[i];
+        if (pMP->isBad() || spAlreadyFound.count(pMP)) continue;
+        detail::FuseQuery(pKF, pMP, R, t, Ow, 0.f, th, true, Q, i);
+    }
+    const orbm_frame view = ResidentKF(pKF, true);
+    std::vector<int> best(nq ? nq : 1, -1), dist(nq ? nq : 1, 256);
+    int found = 0;
+    Check(orbm_window_best_free(&view, (int)nq, &Q.uvr[0], &Q.level[0], 0, &Q.valid[0], &Q.desc[0], 0, 0, TH_LOW, &best[0], &dist[0], &found,
+                                Device()), "orbm_window_best_free");
+    int nFused = 0;
+    for (size_t i = 0; i < nq; ++i) {
+        if (!Q.valid[i] || best[i] < 0) continue;
+        MapPointT* pMP = vpPoints[i];
+        if (pMP->isBad()) continue;
+        MapPointT* pMPinKF = pKF->GetMapPoint((size_t)best[i]);
+        if (pMPinKF) {
+            if (!pMPinKF->isBad()) vpReplacePoint[i] = pMPinKF;                         // :1612-1613
+        } else {
+            pMP->AddObservation(pKF, (size_t)best[i]);                                  // :1617-1618
+            pKF->AddMapPoint(pMP, (size_t)best[i]);
+        }
+        nFused++;
+    }
+    return nFused;
+}
+
+// ORBmatcher::SearchBySim3(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& vpMatches12, const float& s12, const cv::Mat& R12,
+// const cv::Mat& t12, const float th), src/ORBmatcher.cc:836-1052: the map points of each key frame moved through the similarity
+// into the other one and searched there (TH_HIGH), matches kept when both directions agree.
+template <class KeyFrameT, class MatT, class MapPointT>
+int SearchBySim3(KeyFrameT* pKF1, KeyFrameT* pKF2, std::vector<MapPointT*>& vpMatches12, const float& s12, const MatT& R12, const MatT& t12, const float th)
+{
+    const int TH_HIGH = 100;
+    float R1w[9], t1w[3], R2w[9], t2w[3], r12[9], T12[3], sR12[9], sR21[9], nsR21[9], t21[3];
+    detail::Read3x3(pKF1->GetRotation(), R1w); detail::Read3(pKF1->GetTranslation(), t1w);
+    detail::Read3x3(pKF2->GetRotation(), R2w); detail::Read3(pKF2->GetTranslation(), t2w);
+    detail::Read3x3(R12, r12); detail::Read3(t12, T12);
+    const double inv_s = 1.0 / (double)s12;
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) {
+            sR12[3 * r + c] = (float)((double)r12[3 * r + c] * (double)s12);            // :854
+            sR21[3 * r + c] = (float)((double)r12[3 * c + r] * inv_s);                  // :855
+            nsR21[3 * r + c] = (float)((double)sR21[3 * r + c] * -1.0);
+        }
+    for (int r = 0; r < 3; ++r) {                                                       // t21 = -sR21*t12 (:856)
+        float s = nsR21[3 * r] * T12[0];
+        s = s + nsR21[3 * r + 1] * T12[1];
+        s = s + nsR21[3 * r + 2] * T12[2];
+        t21[r] = s;
+    }
+    const std::vector<MapPointT*> vpMapPoints1 = pKF1->GetMapPointMatches();
+    const std::vector<MapPointT*> vpMapPoints2 = pKF2->GetMapPointMatches();
+    const int N1 = (int)vpMapPoints1.size(), N2 = (int)vpMapPoints2.size();
+    std::vector<bool> vbAlreadyMatched1((size_t)N1, false), vbAlreadyMatched2((size_t)N2, false);
+    for (int i = 0; i < N1; ++i) {                                                      // :864-877
+        MapPointT* pMP = vpMatches12[(size_t)i];
+        if (pMP) {
+            vbAlreadyMatched1[(size_t)i] = true;
+            const int idx2 = pMP->GetIndexInKeyFrame(pKF2);
+            if (idx2 >= 0 && idx2 < N2) vbAlreadyMatched2[(size_t)idx2] = true;
+        }
+    }
+    // one direction: points of A through (Raw, taw) into A's camera, through (sR, tt) into B's, searched in B
+    struct Dir {
+        static void Run(const std::vector<MapPointT*>& ptsA, const std::vector<bool>& already, const float* Raw, const float* taw, const float* sR,
+                        const float* tt, KeyFrameT* pKFB, const float* K, float th, int thAccept, std::vector<int>& match)
+        {
+            const size_t nA = ptsA.size();
+            detail::FreeQueries Q(nA);
+            for (size_t i = 0; i < nA; ++i) {
+                MapPointT* pMP = ptsA[i];
+                if (!pMP || already[i]) continue;
+                if (pMP->isBad()) continue;
+                float x[3], pa[3], pb[3];
+                detail::Read3(pMP->GetWorldPos(), x);
+                detail::MulAdd3(Raw, taw, x, pa);
+                detail::MulAdd3(sR, tt, pa, pb);
+                if (pb[2] < 0.0) continue;
+                const float invz = (float)(1.0 / (double)pb[2]);
+                const float xn = pb[0] * invz, yn = pb[1] * invz;
+                const float u = K[0] * xn + K[2], v = K[1] * yn + K[3];
+                if (!(u >= pKFB->mnMinX && u < pKFB->mnMaxX && v >= pKFB->mnMinY && v < pKFB->mnMaxY)) continue;
+                double acc = 0;
+                for (int r = 0; r < 3; ++r) acc += (double)pb[r] * (double)pb[r];
+                const float dist3D = (float)std::sqrt(acc);
+                if (dist3D < pMP->GetMinDistanceInvariance() || dist3D > pMP->GetMaxDistanceInvariance()) continue;
+                const int lvl = pMP->PredictScale(dist3D, pKFB);
+                Q.uvr[3 * i] = u; Q.uvr[3 * i + 1] = v; Q.uvr[3 * i + 2] = th * pKFB->mvScaleFactors[(size_t)lvl];
+                Q.level[i] = lvl; Q.valid[i] = 1;
+                std::memcpy(&Q.desc[32 * i], pMP->GetDescriptor().ptr(0), 32);
+            }
+            const orbm_frame view = ResidentKF(pKFB, true);
+            match.assign(nA ? nA : 1, -1);
+            std::vector<int> dist(nA ? nA : 1, 256);
+            int found = 0;
+            Check(orbm_window_best_free(&view, (int)nA, &Q.uvr[0], &Q.level[0], 0, &Q.valid[0], &Q.desc[0], 0, 0, thAccept, &match[0], &dist[0],
+                                        &found, Device()), "orbm_window_best_free");
+        }
+    };
+    const float K[4] = { pKF1->fx, pKF1->fy, pKF1->cx, pKF1->cy };                      // pKF1's intrinsics project in BOTH directions (:838-841)
+    std::vector<int> vnMatch1, vnMatch2;
+    Dir::Run(vpMapPoints1, vbAlreadyMatched1, R1w, t1w, sR21, t21, pKF2, K, th, TH_HIGH, vnMatch1);
+    Dir::Run(vpMapPoints2, vbAlreadyMatched2, R2w, t2w, sR12, T12, pKF1, K, th, TH_HIGH, vnMatch2);
+    int nFound = 0;
+    for (int i1 = 0; i1 < N1; ++i1) {                                                   // :1029-1042
+        const int idx2 = vnMatch1[(size_t)i1];
+        if (idx2 >= 0 && vnMatch2[(size_t)idx2] == i1) { vpMatches12[(size_t)i1] = vpMapPoints2[(size_t)idx2]; nFound++; }
+    }
+    return nFound;
 }
 
 }} // namespace ORB_SLAM2::b200

@@ -9,18 +9,29 @@ typedef ORB_SLAM2::MapPoint MapPointT;
 typedef ORB_SLAM2::KeyFrame KeyFrameT;
 #else
 #include "cvshim.hpp"
+#include <map>
+#include <set>
 #include <vector>
+struct KeyFrameT;
 struct MapPointT {
     bool mbTrackInView, bad; int mnTrackScaleLevel, nObs; float mTrackViewCos, mTrackProjX, mTrackProjY, mTrackProjXR;
-    cv::Mat descriptor, pos;
+    cv::Mat descriptor, pos, normalv;
+    float minD, maxD; bool haveRange;                         // zero-initialised by the vectors that hold the points: no range set
     bool isBad() { return bad; }
-    float GetMinDistanceInvariance() { return 0.f; }
-    float GetMaxDistanceInvariance() { return 1e9f; }
+    float GetMinDistanceInvariance() { return haveRange ? minD : 0.f; }
+    float GetMaxDistanceInvariance() { return haveRange ? maxD : 1e9f; }
+    // observation bookkeeping as the reference's MapPoint keeps it (src/MapPoint.cc:93-105, 204-258), for Fuse / SearchBySim3
+    std::map<KeyFrameT*, size_t> obs;
+    MapPointT* replacedBy;
+    bool IsInKeyFrame(KeyFrameT* kf) { return obs.count(kf) != 0; }
+    int GetIndexInKeyFrame(KeyFrameT* kf) { std::map<KeyFrameT*, size_t>::iterator it = obs.find(kf); return it == obs.end() ? -1 : (int)it->second; }
+    inline void AddObservation(KeyFrameT* kf, size_t idx);
+    inline void Replace(MapPointT* p);
     template <class F> int PredictScale(const float&, F*) { return mnTrackScaleLevel; }
     int Observations() { return nObs; }
     cv::Mat GetDescriptor() { return descriptor.clone(); }
     cv::Mat GetWorldPos() { return pos.clone(); }
-    cv::Mat GetNormal() { return pos.clone(); }
+    cv::Mat GetNormal() { return normalv.empty() ? pos.clone() : normalv.clone(); }
     float GetMaxDistance() { return 1e9f; }
     float GetMinDistance() { return 0.f; }
 };
@@ -42,14 +53,38 @@ struct FrameT {
 struct KeyFrameT {
     long unsigned int mnFrameId; double mTimeStamp;                                // include/KeyFrame.h:128,130: the id of the Frame it was made from
     KeyFrameT() : mnFrameId(NextFrameId()), mTimeStamp(0.0) {}
-    float fx, fy, cx, cy; int mnMinX, mnMinY, mnMaxX, mnMaxY;
-    cv::Mat mDescriptors;
+    float fx, fy, cx, cy, mbf; int mnMinX, mnMinY, mnMaxX, mnMaxY;
+    cv::Mat mDescriptors, Rcw, tcw, Ow;
     FeatVecT mFeatVec;
-    std::vector<float> mvScaleFactors;
+    std::vector<float> mvScaleFactors, mvInvLevelSigma2, mvuRight;
     std::vector<cv::KeyPoint> mvKeysUn;
     std::vector<MapPointT*> pts;
     std::vector<MapPointT*> GetMapPointMatches() { return pts; }
+    std::set<MapPointT*> GetMapPoints() { std::set<MapPointT*> s; for (size_t i = 0; i < pts.size(); ++i) if (pts[i] && !pts[i]->isBad()) s.insert(pts[i]); return s; }   // src/KeyFrame.cc:378-392
+    MapPointT* GetMapPoint(const size_t& i) { return pts[i]; }
+    void AddMapPoint(MapPointT* p, const size_t& i) { pts[i] = p; }
+    cv::Mat GetRotation() { return Rcw.clone(); }
+    cv::Mat GetTranslation() { return tcw.clone(); }
+    cv::Mat GetCameraCenter() { return Ow.clone(); }
 };
+inline void MapPointT::AddObservation(KeyFrameT* kf, size_t idx)
+{
+    if (obs.count(kf)) return;
+    obs[kf] = idx;
+    nObs += (idx < kf->mvuRight.size() && kf->mvuRight[idx] >= 0) ? 2 : 1;
+}
+inline void MapPointT::Replace(MapPointT* p)
+{
+    if (p == this) return;
+    std::map<KeyFrameT*, size_t> o = obs;
+    obs.clear();
+    bad = true;
+    replacedBy = p;
+    for (std::map<KeyFrameT*, size_t>::iterator it = o.begin(); it != o.end(); ++it) {
+        if (!p->IsInKeyFrame(it->first)) { it->first->pts[it->second] = p; p->AddObservation(it->first, it->second); }
+        else it->first->pts[it->second] = 0;
+    }
+}
 float FrameT::fx, FrameT::fy, FrameT::cx, FrameT::cy, FrameT::mnMinX, FrameT::mnMaxX, FrameT::mnMinY, FrameT::mnMaxY;
 #endif
 #include "ORBmatcher_b200.hpp"
@@ -71,6 +106,10 @@ extern "C" int matcher_forwarders_instantiate(int run)
     n += ORB_SLAM2::b200::SearchByProjection(&kf, cv::Mat(), pts, matched, 10);
     n += ORB_SLAM2::b200::SearchByBoW(&kf, a, matched, 0.7f, true);
     n += ORB_SLAM2::b200::SearchByBoW(&kf, &kf, matched, 0.75f, true);
+    n += ORB_SLAM2::b200::Fuse(&kf, pts, 3.0f);
+    n += ORB_SLAM2::b200::Fuse(&kf, cv::Mat(), pts, 4.0f, matched);
+    const float s12 = 1.f;
+    n += ORB_SLAM2::b200::SearchBySim3(&kf, &kf, matched, s12, cv::Mat(), cv::Mat(), 7.5f);
 #ifndef WITH_REFERENCE_HEADERS      // the reference's MapPoint lacks the two raw-distance accessors until patched
     std::vector<bool> inView;
     n += ORB_SLAM2::b200::IsInFrustum(a, pts, 0.5f, inView);
@@ -273,6 +312,104 @@ int fwd_distinctive(const unsigned char* desc, int n)
     std::vector<cv::Mat> v(n);
     for (int i = 0; i < n; ++i) fill_desc(v[i], desc + 32 * (size_t)i, 1);
     return ORB_SLAM2::b200::DistinctiveDescriptor(v);
+}
+
+// ORBmatcher::Fuse (both overloads) through b200::Fuse; the arrays and their meaning are those of oracle/ref_fuse_harness.cc
+namespace {
+cv::Mat mat_of(const float* v, int rows, int cols)
+{
+    cv::Mat m(rows, cols, CV_32F);
+    for (int r = 0; r < rows; ++r) for (int c = 0; c < cols; ++c) m.at<float>(r, c) = v[r * cols + c];
+    return m;
+}
+void fill_kf(KeyFrameT& KF, int n, const Kp* kps, const unsigned char* desc, const float* u_right, float minX, float maxX, float minY, float maxY,
+             const float* scale, const float* inv_sigma2, int nlevels, const float* K, float bf)
+{
+    fill_keys(KF.mvKeysUn, kps, n); fill_desc(KF.mDescriptors, desc, n);
+    KF.mvuRight.assign(n, -1.f);
+    if (u_right) KF.mvuRight.assign(u_right, u_right + n);
+    KF.mvScaleFactors.assign(scale, scale + nlevels);
+    if (inv_sigma2) KF.mvInvLevelSigma2.assign(inv_sigma2, inv_sigma2 + nlevels);
+    KF.fx = K[0]; KF.fy = K[1]; KF.cx = K[2]; KF.cy = K[3]; KF.mbf = bf;
+    KF.mnMinX = (int)minX; KF.mnMaxX = (int)maxX; KF.mnMinY = (int)minY; KF.mnMaxY = (int)maxY;
+    KF.pts.assign(n, static_cast<MapPointT*>(0));
+}
+void fill_points(std::vector<MapPointT>& mps, int npts, const unsigned char* bad, const float* xyz, const float* normal, const unsigned char* mp_desc,
+                 const int* pred_level, const float* min_dist, const float* max_dist, const int* nobs)
+{
+    for (int i = 0; i < npts; ++i) {
+        MapPointT& m = mps[i];
+        m.bad = bad[i] != 0;
+        m.pos = mat_of(xyz + 3 * i, 3, 1);
+        if (normal) m.normalv = mat_of(normal + 3 * i, 3, 1);
+        fill_desc(m.descriptor, mp_desc + 32 * (size_t)i, 1);
+        m.mnTrackScaleLevel = pred_level[i];
+        m.minD = min_dist[i]; m.maxD = max_dist[i]; m.haveRange = true;
+        m.nObs = nobs ? nobs[i] : 0;
+        m.replacedBy = 0;
+    }
+}
+} // namespace
+
+int fwd_fuse(int sim3, int n, const Kp* kps, const unsigned char* desc, const float* u_right,
+             float minX, float maxX, float minY, float maxY, const float* scale, const float* inv_sigma2, int nlevels,
+             const float* K, float bf, const float* Rcw, const float* tcw, const float* Ow, const float* Scw,
+             int npts, unsigned char* bad, const float* xyz, const float* normal, const unsigned char* mp_desc,
+             const int* pred_level, const float* min_dist, const float* max_dist, int* nobs, int* kf_idx, int* replaced_by,
+             int nlist, const int* list, int* kf_mp, int* replace_out, float th)
+{
+    KeyFrameT KF;
+    fill_kf(KF, n, kps, desc, u_right, minX, maxX, minY, maxY, scale, inv_sigma2, nlevels, K, bf);
+    if (!sim3) { KF.Rcw = mat_of(Rcw, 3, 3); KF.tcw = mat_of(tcw, 3, 1); KF.Ow = mat_of(Ow, 3, 1); }
+    std::vector<MapPointT> mps(npts > 0 ? npts : 1);
+    fill_points(mps, npts, bad, xyz, normal, mp_desc, pred_level, min_dist, max_dist, nobs);
+    for (int i = 0; i < npts; ++i) if (kf_idx[i] >= 0) mps[i].obs[&KF] = (size_t)kf_idx[i];
+    for (int k = 0; k < n; ++k) if (kf_mp[k] >= 0) KF.pts[k] = &mps[kf_mp[k]];
+    std::vector<MapPointT*> pts(nlist);
+    for (int i = 0; i < nlist; ++i) pts[i] = list[i] >= 0 ? &mps[list[i]] : static_cast<MapPointT*>(0);
+    int nf;
+    if (sim3) {
+        std::vector<MapPointT*> rep(nlist, static_cast<MapPointT*>(0));
+        nf = ORB_SLAM2::b200::Fuse(&KF, mat_of(Scw, 4, 4), pts, th, rep);
+        for (int i = 0; i < nlist; ++i) replace_out[i] = rep[i] ? (int)(rep[i] - &mps[0]) : -1;
+    } else {
+        nf = ORB_SLAM2::b200::Fuse(&KF, pts, th);
+    }
+    for (int i = 0; i < npts; ++i) {
+        bad[i] = mps[i].bad ? 1 : 0;
+        nobs[i] = mps[i].nObs;
+        kf_idx[i] = mps[i].GetIndexInKeyFrame(&KF);
+        replaced_by[i] = mps[i].replacedBy ? (int)(mps[i].replacedBy - &mps[0]) : -1;
+    }
+    for (int k = 0; k < n; ++k) kf_mp[k] = KF.pts[k] ? (int)(KF.pts[k] - &mps[0]) : -1;
+    ORB_SLAM2::b200::ResidentFrames::Local().Clear();
+    return nf;
+}
+
+// ORBmatcher::SearchBySim3 through b200::SearchBySim3 (arrays as in oracle/ref_fuse_harness.cc)
+int fwd_search_by_sim3(int n1, const Kp* kps1, const unsigned char* desc1, const int* mp1,
+                       int n2, const Kp* kps2, const unsigned char* desc2, const int* mp2,
+                       float minX, float maxX, float minY, float maxY, const float* scale, int nlevels, const float* K,
+                       const float* R1w, const float* t1w, const float* R2w, const float* t2w, float s12, const float* R12, const float* t12,
+                       int npts, const unsigned char* bad, const float* xyz, const unsigned char* mp_desc, const int* pred_level,
+                       const float* min_dist, const float* max_dist, const int* idx_in_kf2, int* matches12, float th)
+{
+    KeyFrameT KF1, KF2;
+    fill_kf(KF1, n1, kps1, desc1, 0, minX, maxX, minY, maxY, scale, 0, nlevels, K, 0.f);
+    fill_kf(KF2, n2, kps2, desc2, 0, minX, maxX, minY, maxY, scale, 0, nlevels, K, 0.f);
+    KF1.Rcw = mat_of(R1w, 3, 3); KF1.tcw = mat_of(t1w, 3, 1);
+    KF2.Rcw = mat_of(R2w, 3, 3); KF2.tcw = mat_of(t2w, 3, 1);
+    std::vector<MapPointT> mps(npts > 0 ? npts : 1);
+    fill_points(mps, npts, bad, xyz, 0, mp_desc, pred_level, min_dist, max_dist, 0);
+    for (int i = 0; i < npts; ++i) if (idx_in_kf2[i] >= 0) mps[i].obs[&KF2] = (size_t)idx_in_kf2[i];
+    for (int k = 0; k < n1; ++k) if (mp1[k] >= 0) KF1.pts[k] = &mps[mp1[k]];
+    for (int k = 0; k < n2; ++k) if (mp2[k] >= 0) KF2.pts[k] = &mps[mp2[k]];
+    std::vector<MapPointT*> m12(n1, static_cast<MapPointT*>(0));
+    for (int k = 0; k < n1; ++k) if (matches12[k] >= 0) m12[k] = &mps[matches12[k]];
+    const int nf = ORB_SLAM2::b200::SearchBySim3(&KF1, &KF2, m12, s12, mat_of(R12, 3, 3), mat_of(t12, 3, 1), th);
+    for (int k = 0; k < n1; ++k) matches12[k] = m12[k] ? (int)(m12[k] - &mps[0]) : -1;
+    ORB_SLAM2::b200::ResidentFrames::Local().Clear();
+    return nf;
 }
 
 } // extern "C"

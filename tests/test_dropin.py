@@ -177,3 +177,43 @@ def test_resident_frame_cache_bookkeeping(dropin):
     # 10 uploads, + 1 for the evicted first frame, + 0 for the last frame (a hit), + 1 when the last frame (cached without
     # right coordinates: index 9 is odd) is asked for with them; 8 entries held
     assert r == (frames + 1 + 1) * 100 + 8, r
+
+
+@pytest.mark.gpu
+def test_fuse_and_sim3_forwarders_run_like_the_patched_reference(dropin):
+    """b200::Fuse (both overloads) and b200::SearchBySim3 at run time: KeyFrame / MapPoint stand-ins (the reference's member
+    names, its Replace / AddObservation bookkeeping) are filled from arrays and handed to the forwarders the way the patched
+    ORBmatcher.cc would; what they leave in the objects is compared with the CPU checker's sequential loop."""
+    from fuse_lib import fuse_scene, run_fuse, run_search_by_sim3, same_state, sim3_pair_scene
+    from matcher_lib import extract_frame, perturbed_frame
+    from test_fuse_oracle import BF, BOUNDS, FUSE_CASES, K, SIM3_CASES
+    M = C.CDLL(os.path.join(CPP, "_build", "libmatcher_fwd.so"))
+    vp, ci, cf = C.c_void_p, C.c_int, C.c_float
+    p = lambda a: None if a is None else a.ctypes.data
+    W, H = 1241, 376
+    kps, desc, scale = extract_frame(W, H, 2000, 2)
+    k2, d2, _ = perturbed_frame(kps, desc, W, H, 11, shift=4, kmax=40)
+    inv_sigma2 = (np.float32(1.0) / (scale * scale)).astype(np.float32)
+    Kf = np.asarray(K, np.float32)
+    M.fwd_fuse.argtypes = [ci, ci, vp, vp, vp] + [cf] * 4 + [vp, vp, ci, vp, cf, vp, vp, vp, vp, ci] + [vp] * 10 + [ci, vp, vp, vp, cf]
+    for th, seed, sim3, stereo in FUSE_CASES:
+        s = fuse_scene(kps, desc, W, H, seed, K, BF, sim3)
+        want_n, want, _ = run_fuse("oracle", kps, desc, s, scale, inv_sigma2, BOUNDS, K, BF, th, sim3, stereo)
+        bad, nobs, kf_idx, kf_mp = s["bad"].copy(), s["nobs"].copy(), s["kf_idx"].copy(), s["kf_mp"].copy()
+        replaced_by, replace = np.full(s["npts"], -1, np.int32), np.full(len(s["list"]), -1, np.int32)
+        ur = s["u_right"] if stereo else None
+        nf = M.fwd_fuse(int(sim3), len(kps), p(kps), p(desc), p(ur), *BOUNDS, p(scale), p(inv_sigma2), len(scale), p(Kf), BF, p(s["R"]), p(s["t"]),
+                        p(s["Ow"]), p(s["Scw"]), s["npts"], p(bad), p(s["xyz"]), p(s["normal"]), p(s["mp_desc"]), p(s["level"]), p(s["min_dist"]),
+                        p(s["max_dist"]), p(nobs), p(kf_idx), p(replaced_by), len(s["list"]), p(s["list"]), p(kf_mp), p(replace), th)
+        got = dict(bad=bad, nobs=nobs, kf_idx=kf_idx, kf_mp=kf_mp)
+        got["replace" if sim3 else "replaced_by"] = replace if sim3 else replaced_by
+        assert nf == want_n and nf > 300 and same_state(got, want), (th, seed, sim3, stereo)
+    M.fwd_search_by_sim3.argtypes = [ci, vp, vp, vp, ci, vp, vp, vp] + [cf] * 4 + [vp, ci] + [vp] * 5 + [cf, vp, vp, ci] + [vp] * 8 + [cf]
+    for th, seed in SIM3_CASES:
+        s = sim3_pair_scene(kps, desc, k2, d2, W, H, seed, K)
+        want_n, want_m12, _ = run_search_by_sim3("oracle", kps, desc, k2, d2, s, scale, BOUNDS, K, th)
+        m12 = s["m12"].copy()
+        nf = M.fwd_search_by_sim3(len(kps), p(kps), p(desc), p(s["mp1"]), len(k2), p(k2), p(d2), p(s["mp2"]), *BOUNDS, p(scale), len(scale), p(Kf),
+                                  p(s["R1"]), p(s["t1"]), p(s["R2"]), p(s["t2"]), s["s12"], p(s["R12"]), p(s["t12"]), s["npts"], p(s["bad"]),
+                                  p(s["xyz"]), p(s["mp_desc"]), p(s["level"]), p(s["min_dist"]), p(s["max_dist"]), p(s["idx_in_kf2"]), p(m12), th)
+        assert nf == want_n and nf > 200 and (m12 == want_m12).all()

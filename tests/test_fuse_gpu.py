@@ -149,7 +149,7 @@ def test_batch_of_problems_equals_oracle(scene, chi2, bounds):
         assert (bi[i, :nq] == o_bi).all() and (bd[i, :nq] == o_bd).all(), i
         assert (bi[i, nq:] == -7).all()                           # nothing written behind a problem's queries
         total += o_n
-    assert total > 3000
+    assert total > 1500
 
 
 def test_degenerate_inputs(scene):
