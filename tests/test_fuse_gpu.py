@@ -163,6 +163,6 @@ def test_degenerate_inputs(scene):
     assert n == 0 and len(bi) == 0
     n, bi, bd = ob.window_best_free(F, q["uvr"], q["level"], qd, 50, valid=np.zeros(40, np.uint8))
     assert n == 0 and (bi == -1).all() and (bd == 256).all()
-    n, bi, bd = ob.window_best_free(F, q["uvr"], q["level"], qd, -1)              # nothing passes the threshold; distances still reported
+    n, bi, bd = ob.window_best_free(F, q["uvr"], q["level"], qd, -1, valid=q["valid"])   # nothing passes the threshold; distances still reported
     o_n, o_bi, o_bd = window_best_free_oracle(scene["kps"], scene["desc"], None, BOUNDS, q, qd, None, -1)
     assert n == 0 and (bi == -1).all() and (bd == o_bd).all() and (bd < 256).any()
