@@ -402,6 +402,20 @@ int orbm_search_by_bow_batch(const orbm_frames* A, const orbm_featvec* VA, const
                              int kf_kf, float nnratio, int check_ori, int* match12, int* match21,
                              int* nmatches, int* rounds, void* cuda_stream);
 
+/* ORBmatcher::SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, cv::Mat F12, vector<pair<size_t,size_t>>&, bOnlyStereo),
+ * src/ORBmatcher.cc:1183-1361 with CheckDistEpipolarLine (:1636-1650), for nprob key-frame pairs: features of shared
+ * vocabulary nodes (orbm_featvec, as SearchByBoW), a_valid / b_valid [nprob][kp_stride] = the feature has NO map point yet
+ * (and a right coordinate when bOnlyStereo); A->u_right / B->u_right = mvuRight of the key frames (NULL = monocular);
+ * F12 [nprob][9] row-major, epipole [nprob][2] = (ex, ey) of :1190-1196 (device); scale = pKF2->mvScaleFactors, sigma2 =
+ * pKF2->mvLevelSigma2 (host, nlevels).  A candidate must be within TH_LOW, off the epipole (:1272-1279) and on the epipolar
+ * line; of equally close ones the last wins; like the reference (which tests vbMatched2 but never sets it) no feature blocks
+ * another.  match12 [nprob][A.kp_stride] = vMatches12 (vMatchedPairs = its entries >= 0 in index order), nmatches [nprob]
+ * the return value (-1: sizes exceed 8192 or the strides).  Only enqueues. */
+int orbm_search_for_triangulation_batch(const orbm_frames* A, const orbm_featvec* VA, const uint8_t* a_valid,
+                                        const orbm_frames* B, const orbm_featvec* VB, const uint8_t* b_valid,
+                                        const float* F12, const float* epipole, const float* scale, const float* sigma2, int nlevels,
+                                        int check_ori, int* match12, int* nmatches, void* cuda_stream);
+
 /* ---- the same three for ONE problem with HOST arrays (what the C++ forwarders call) ---------
  * orbm_search_by_bow: SearchByBoW (src/ORBmatcher.cc:552-832), feature vectors in CSR form (see orbm_featvec).
  * orbm_project_points: Frame::isInFrustum for n map points of one frame (src/Frame.cc:288-345).
@@ -409,6 +423,12 @@ int orbm_search_by_bow_batch(const orbm_frames* A, const orbm_featvec* VA, const
 int orbm_search_by_bow(const orbm_frame* A, const uint8_t* a_valid, int nn_a, const int* node_id_a, const int* node_off_a, const int* feat_a,
                        const orbm_frame* B, const uint8_t* b_valid, int nn_b, const int* node_id_b, const int* node_off_b, const int* feat_b,
                        int kf_kf, float nnratio, int check_ori, int* match12, int* nmatches, int device);
+/* orbm_search_for_triangulation: SearchForTriangulation for one key-frame pair (host arrays; A->u_right / B->u_right = mvuRight
+ * or NULL; frames may be resident views) */
+int orbm_search_for_triangulation(const orbm_frame* A, const uint8_t* a_valid, int nn_a, const int* node_id_a, const int* node_off_a, const int* feat_a,
+                                  const orbm_frame* B, const uint8_t* b_valid, int nn_b, const int* node_id_b, const int* node_off_b, const int* feat_b,
+                                  const float* F12, const float* epipole, const float* scale, const float* sigma2, int nlevels,
+                                  int check_ori, int* match12, int* nmatches, int device);
 int orbm_project_points(const float* Tcw, const float* K, float bf, float min_x, float max_x, float min_y, float max_y,
                         float scale_factor, int nlevels, float viewing_cos_limit, int n, const float* xyz, const float* normal,
                         const float* max_distance, const float* min_distance, uint8_t* in_view, float* proj_xyxr, int* level,

@@ -524,3 +524,83 @@ int orbo_search_by_bow(int n1, const orbo_kp* kps1, const uint8_t* desc1, const 
     free(matched2);
     return nmatches;
 }
+
+/* ORBmatcher::SearchForTriangulation, src/ORBmatcher.cc:1183-1361, with CheckDistEpipolarLine (:1636-1650).
+ * has_mp1 / has_mp2: the key frame's feature already has a map point (pKF->GetMapPoint(idx) != NULL); u_right1 / u_right2 =
+ * mvuRight (NULL = monocular: every entry negative); F12 row-major 3x3; epipole = (ex, ey) of :1195-1196 (the caller projects
+ * KF1's camera centre into KF2); scale = pKF2->mvScaleFactors, sigma2 = pKF2->mvLevelSigma2.  A candidate replaces the
+ * running best when its distance is <= the best so far (:1248: `dist>bestDist` continues), i.e. the LAST of equally close
+ * candidates that pass the epipolar tests wins.  The reference declares vbMatched2 (:1205) and tests it (:1254) but never sets
+ * it, so no feature of key frame 1 depends on another one.  match12 [n1] = vMatches12 (vMatchedPairs lists its entries >= 0
+ * in order). */
+int orbo_search_for_triangulation(int n1, const orbo_kp* kps1, const uint8_t* desc1, const uint8_t* has_mp1, const float* u_right1,
+                                  int nn1, const int* node_id1, const int* node_off1, const int* feat1,
+                                  int n2, const orbo_kp* kps2, const uint8_t* desc2, const uint8_t* has_mp2, const float* u_right2,
+                                  int nn2, const int* node_id2, const int* node_off2, const int* feat2,
+                                  const float* F12, const float* epipole, const float* scale, const float* sigma2,
+                                  int onlyStereo, int checkOri, int* match12)
+{
+    int nmatches = 0;
+    uint8_t* matched2 = (uint8_t*)calloc((size_t)(n2 > 0 ? n2 : 1), 1);
+    ivec hist[HISTO_LENGTH];
+    memset(hist, 0, sizeof(hist));
+    for (int i = 0; i < n1; ++i) match12[i] = -1;
+    const float ex = epipole[0], ey = epipole[1];
+    int a = 0, b = 0;
+    while (a < nn1 && b < nn2) {
+        if (node_id1[a] == node_id2[b]) {
+            for (int p1 = node_off1[a]; p1 < node_off1[a + 1]; ++p1) {
+                const int idx1 = feat1[p1];
+                if (has_mp1[idx1]) continue;                                                    /* :1222-1225 */
+                const int bStereo1 = u_right1 && u_right1[idx1] >= 0;
+                if (onlyStereo && !bStereo1) continue;
+                const orbo_kp* kp1 = &kps1[idx1];
+                /* epipolar line of kp1 in image 2, :1640-1642 */
+                const float la = kp1->x * F12[0] + kp1->y * F12[3] + F12[6];
+                const float lb = kp1->x * F12[1] + kp1->y * F12[4] + F12[7];
+                const float lc = kp1->x * F12[2] + kp1->y * F12[5] + F12[8];
+                int bestDist = TH_LOW, bestIdx2 = -1;
+                for (int p2 = node_off2[b]; p2 < node_off2[b + 1]; ++p2) {
+                    const int idx2 = feat2[p2];
+                    if (matched2[idx2] || has_mp2[idx2]) continue;                              /* :1245-1246 */
+                    const int bStereo2 = u_right2 && u_right2[idx2] >= 0;
+                    if (onlyStereo && !bStereo2) continue;
+                    const int dist = orbo_descriptor_distance(desc1 + (size_t)idx1 * 32, desc2 + (size_t)idx2 * 32);
+                    if (dist > TH_LOW || dist > bestDist) continue;
+                    const orbo_kp* kp2 = &kps2[idx2];
+                    if (!bStereo1 && !bStereo2) {                                               /* too close to the epipole, :1263-1269 */
+                        const float distex = ex - kp2->x, distey = ey - kp2->y;
+                        if (distex * distex + distey * distey < 100 * scale[kp2->octave]) continue;
+                    }
+                    const float num = la * kp2->x + lb * kp2->y + lc;                           /* CheckDistEpipolarLine */
+                    const float den = la * la + lb * lb;
+                    if (den == 0) continue;
+                    const float dsqr = num * num / den;
+                    if (dsqr < 3.84 * sigma2[kp2->octave]) { bestIdx2 = idx2; bestDist = dist; }
+                }
+                if (bestIdx2 >= 0) {
+                    match12[idx1] = bestIdx2;      /* vbMatched2 is NOT set here (:1289-1292): several idx1 may share an idx2 */
+                    nmatches++;
+                    if (checkOri) ivec_push(&hist[rot_bin(kp1->angle, kps2[bestIdx2].angle)], idx1);
+                }
+            }
+            ++a; ++b;
+        } else if (node_id1[a] < node_id2[b]) {
+            while (a < nn1 && node_id1[a] < node_id2[b]) ++a;
+        } else {
+            while (b < nn2 && node_id2[b] < node_id1[a]) ++b;
+        }
+    }
+    if (checkOri) {
+        int sizes[HISTO_LENGTH], i1, i2, i3;
+        for (int i = 0; i < HISTO_LENGTH; ++i) sizes[i] = hist[i].n;
+        three_maxima(sizes, HISTO_LENGTH, &i1, &i2, &i3);
+        for (int i = 0; i < HISTO_LENGTH; ++i) {
+            if (i == i1 || i == i2 || i == i3) continue;
+            for (int j = 0; j < hist[i].n; ++j) { match12[hist[i].v[j]] = -1; nmatches--; }
+        }
+    }
+    for (int i = 0; i < HISTO_LENGTH; ++i) free(hist[i].v);
+    free(matched2);
+    return nmatches;
+}

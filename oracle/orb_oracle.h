@@ -162,6 +162,14 @@ int orbo_search_by_bow(int n1, const orbo_kp* kps1, const uint8_t* desc1, const 
                        int nn2, const int* node_id2, const int* node_off2, const int* feat2,
                        float nnratio, int checkOri, int strict, int* match12, int* match21);
 
+/* ORBmatcher::SearchForTriangulation, src/ORBmatcher.cc:1183-1361 (+ CheckDistEpipolarLine :1636-1650) */
+int orbo_search_for_triangulation(int n1, const orbo_kp* kps1, const uint8_t* desc1, const uint8_t* has_mp1, const float* u_right1,
+                                  int nn1, const int* node_id1, const int* node_off1, const int* feat1,
+                                  int n2, const orbo_kp* kps2, const uint8_t* desc2, const uint8_t* has_mp2, const float* u_right2,
+                                  int nn2, const int* node_id2, const int* node_off2, const int* feat2,
+                                  const float* F12, const float* epipole, const float* scale, const float* sigma2,
+                                  int onlyStereo, int checkOri, int* match12);
+
 /* map-point side, orb_mappoint_oracle.c */
 int orbo_distinctive_descriptor(const uint8_t* desc, int n, const uint8_t* bad, int* median_out);
 int orbo_predict_scale(float max_distance, float current_dist, float log_scale_factor, int nlevels);

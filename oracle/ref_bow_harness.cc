@@ -102,3 +102,44 @@ int orbref_search_by_bow_kf_kf(int n1, const RefKp* kps1, const unsigned char* d
 }
 
 } // extern "C"
+
+// ORBmatcher::SearchForTriangulation(KeyFrame*, KeyFrame*, cv::Mat F12, vector<pair<size_t,size_t>>&, bOnlyStereo),
+// src/ORBmatcher.cc:1183-1361.  pose2 = R2w (9) | t2w (3) of key frame 2, Cw = key frame 1's camera centre, K2 = fx, fy, cx, cy
+// of key frame 2 (the epipole is computed inside, :1190-1196); match12 [n1] = matched feature of key frame 2 or -1.
+extern "C" int orbref_search_for_triangulation(int n1, const RefKp* kps1, const unsigned char* desc1, const unsigned char* has_mp1, const float* u_right1,
+                                               int nn1, const int* node_id1, const int* node_off1, const int* feat1,
+                                               int n2, const RefKp* kps2, const unsigned char* desc2, const unsigned char* has_mp2, const float* u_right2,
+                                               int nn2, const int* node_id2, const int* node_off2, const int* feat2,
+                                               const float* F12, const float* Cw, const float* pose2, const float* K2,
+                                               const float* scale, const float* sigma2, int nlevels, int only_stereo, int check_ori, int* match12)
+{
+    ref_arena::Scope scope;
+    int nm;
+    {
+        std::vector<MapPoint> store1, store2;
+        KeyFrame K1, KB;
+        fill_kf(K1, n1, kps1, desc1, has_mp1, NULL, store1);
+        fill_kf(KB, n2, kps2, desc2, has_mp2, NULL, store2);
+        fill_featvec(K1.mFeatVec, nn1, node_id1, node_off1, feat1);
+        fill_featvec(KB.mFeatVec, nn2, node_id2, node_off2, feat2);
+        K1.mvuRight.assign(n1, -1.0f); KB.mvuRight.assign(n2, -1.0f);
+        if (u_right1) K1.mvuRight.assign(u_right1, u_right1 + n1);
+        if (u_right2) KB.mvuRight.assign(u_right2, u_right2 + n2);
+        KB.mvScaleFactors.assign(scale, scale + nlevels);
+        KB.mvLevelSigma2.assign(sigma2, sigma2 + nlevels);
+        KB.fx = K2[0]; KB.fy = K2[1]; KB.cx = K2[2]; KB.cy = K2[3];
+        K1.Ow.create(3, 1, CV_32F); KB.R.create(3, 3, CV_32F); KB.t.create(3, 1, CV_32F);
+        for (int r = 0; r < 3; ++r) {
+            K1.Ow.at<float>(r) = Cw[r]; KB.t.at<float>(r) = pose2[9 + r];
+            for (int c = 0; c < 3; ++c) KB.R.at<float>(r, c) = pose2[3 * r + c];
+        }
+        cv::Mat F(3, 3, CV_32F);
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) F.at<float>(r, c) = F12[3 * r + c];
+        std::vector<std::pair<size_t, size_t> > pairs;
+        ORBmatcher matcher(0.6f, check_ori != 0);
+        nm = matcher.SearchForTriangulation(&K1, &KB, F, pairs, only_stereo != 0);
+        for (int i = 0; i < n1; ++i) match12[i] = -1;
+        for (size_t k = 0; k < pairs.size(); ++k) match12[pairs[k].first] = (int)pairs[k].second;
+    }
+    return nm;
+}

@@ -143,6 +143,9 @@ def lib():
         L.orbm_search_by_bow_batch.argtypes = [C.POINTER(OrbmFrames), C.POINTER(OrbmFeatVec), vp, C.POINTER(OrbmFrames), C.POINTER(OrbmFeatVec), vp,
                                                i32, f32, i32, vp, vp, vp, vp, vp]
         L.orbm_search_by_bow.argtypes = [fp, vp, i32, vp, vp, vp, fp, vp, i32, vp, vp, vp, i32, f32, i32, vp, pi, i32]
+        L.orbm_search_for_triangulation.argtypes = [fp, vp, i32, vp, vp, vp, fp, vp, i32, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, pi, i32]
+        L.orbm_search_for_triangulation_batch.argtypes = [C.POINTER(OrbmFrames), C.POINTER(OrbmFeatVec), vp, C.POINTER(OrbmFrames), C.POINTER(OrbmFeatVec), vp,
+                                                          vp, vp, vp, vp, i32, i32, vp, vp, vp]
         L.orbm_project_points.argtypes = [vp, vp, f32, f32, f32, f32, f32, f32, i32, f32, i32] + [vp] * 8 + [i32]
         L.orbm_distinctive_descriptor.argtypes = [vp, i32, vp, pi, pi, i32]
         L.orbm_stereo_matches.argtypes = [vp, i32, vp, i32, i32, vp, vp, i32, vp, vp, f32, f32, vp, vp, pi]
@@ -501,6 +504,24 @@ def search_by_bow(A, fv_a, a_valid, B, fv_b, b_valid, kf_kf, nnratio, check_ori,
     return nm.value, out[:len(A.kps)]
 
 
+def search_for_triangulation(A, fv_a, a_valid, B, fv_b, b_valid, F12, epipole, scale, sigma2, check_ori, device=0):
+    """orbm_search_for_triangulation: ORBmatcher::SearchForTriangulation (src/ORBmatcher.cc:1183-1361) for one key-frame pair
+    with host arrays.  A, B: FrameView (u_right = mvuRight or None); *_valid: the feature has no map point yet (and is a stereo
+    one when bOnlyStereo); F12 3x3, epipole (ex, ey), scale / sigma2 = pKF2's tables.  Returns (nmatches, match12 [A.n])."""
+    (ia, oa, fa), (ib, ob, fb) = [tuple(_np(x, np.int32) for x in fv) for fv in (fv_a, fv_b)]
+    av, bv = _np(a_valid, np.uint8), _np(b_valid, np.uint8)
+    F12, epipole, scale, sigma2 = _np(F12, np.float32), _np(epipole, np.float32), _np(scale, np.float32), _np(sigma2, np.float32)
+    out = np.zeros(max(len(A.kps), 1), np.int32)
+    nm = C.c_int()
+    sa, sb = A.struct(), B.struct()
+    p = lambda a: None if a is None else a.ctypes.data
+    rc = lib().orbm_search_for_triangulation(C.byref(sa), p(av), len(ia), p(ia), p(oa), p(fa), C.byref(sb), p(bv), len(ib), p(ib), p(ob), p(fb),
+                                             p(F12), p(epipole), p(scale), p(sigma2), len(scale), int(check_ori), p(out), C.byref(nm), device)
+    if rc:
+        raise OrbError(rc, "orbm_search_for_triangulation failed")
+    return nm.value, out[:len(A.kps)]
+
+
 def project_points(Tcw, K, bf, bounds, scale_factor, nlevels, xyz, normal, max_distance, min_distance, cos_limit=0.5, device=0):
     """orbm_project_points: Frame::isInFrustum (src/Frame.cc:288-345) for n map points of one frame, host arrays.
     Returns (in_view u8 [n], proj [n,3], level [n], view_cos [n]); entries of points not in view are zero."""
@@ -675,6 +696,19 @@ def search_by_bow_batch(A, VA, a_valid, B, VB, b_valid, kf_kf, nnratio, check_or
                                         _ptr(rounds), stream)
     if rc:
         raise OrbError(rc, "orbm_search_by_bow_batch failed")
+
+
+def search_for_triangulation_batch(A, VA, a_valid, B, VB, b_valid, F12, epipole, scale, sigma2, check_ori, match12, nmatches, stream=None):
+    """orbm_search_for_triangulation_batch (src/ORBmatcher.cc:1183-1361 for every key-frame pair).  A, B: frames_batch(...) with
+    u_right = mvuRight (or None); VA, VB as in search_by_bow_batch; F12 [P,9], epipole [P,2] CUDA float32 tensors; scale, sigma2 host."""
+    fa = OrbmFeatVec(_ptr(VA[0]), _ptr(VA[1]), _ptr(VA[2]), _ptr(VA[3]), int(VA[0].shape[1]))
+    fb = OrbmFeatVec(_ptr(VB[0]), _ptr(VB[1]), _ptr(VB[2]), _ptr(VB[3]), int(VB[0].shape[1]))
+    scale, sigma2 = np.ascontiguousarray(scale, np.float32), np.ascontiguousarray(sigma2, np.float32)
+    rc = lib().orbm_search_for_triangulation_batch(C.byref(A), C.byref(fa), _ptr(a_valid), C.byref(B), C.byref(fb), _ptr(b_valid), _ptr(F12),
+                                                   _ptr(epipole), scale.ctypes.data, sigma2.ctypes.data, len(scale), int(check_ori),
+                                                   _ptr(match12), _ptr(nmatches), stream)
+    if rc:
+        raise OrbError(rc, "orbm_search_for_triangulation_batch failed")
 
 
 def stereo_matches(ex_left, ex_right, kps_l, desc_l, kps_r, desc_r, bf, fx, frame_l=0, frame_r=0):

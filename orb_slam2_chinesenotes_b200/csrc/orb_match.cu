@@ -1041,6 +1041,49 @@ int orbm_search_by_bow(const orbm_frame* A, const uint8_t* a_valid, int nn_a, co
     return *nmatches < 0 ? ORBX_E_ARG : ORBX_OK;
 }
 
+// ORBmatcher::SearchForTriangulation for one key-frame pair with HOST arrays (orbm_search_for_triangulation_batch with one problem)
+int orbm_search_for_triangulation(const orbm_frame* A, const uint8_t* a_valid, int nn_a, const int* node_id_a, const int* node_off_a, const int* feat_a,
+                                  const orbm_frame* B, const uint8_t* b_valid, int nn_b, const int* node_id_b, const int* node_off_b, const int* feat_b,
+                                  const float* F12, const float* epipole, const float* scale, const float* sigma2, int nlevels,
+                                  int check_ori, int* match12, int* nmatches, int device)
+{
+    if (!A || !B || !a_valid || !b_valid || !match12 || !nmatches || nn_a < 0 || nn_b < 0 || A->n < 0 || B->n < 0 || !F12 || !epipole || !scale ||
+        !sigma2 || nlevels <= 0 || nlevels > 32)
+        return ORBX_E_ARG;
+    if ((nn_a > 0 && (!node_id_a || !node_off_a || !feat_a)) || (nn_b > 0 && (!node_id_b || !node_off_b || !feat_b))) return ORBX_E_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return ORBX_E_CUDA; }
+    *nmatches = 0;
+    for (int i = 0; i < A->n; ++i) match12[i] = -1;
+    if (A->n == 0 || B->n == 0 || nn_a == 0 || nn_b == 0) return ORBX_OK;
+    Scratch S;
+    OneFrame OA, OB;
+    if (!one_frame(S, A, &OA) || !one_frame(S, B, &OB)) return S.ok ? ORBX_E_ARG : ORBX_E_CUDA;
+    const int ta = node_off_a[nn_a], tb = node_off_b[nn_b];
+    if (ta < 0 || ta > A->n || tb < 0 || tb > B->n) return ORBX_E_ARG;
+    std::vector<int> fa((size_t)A->n, 0), fb((size_t)B->n, 0);
+    memcpy(fa.data(), feat_a, sizeof(int) * (size_t)ta);
+    memcpy(fb.data(), feat_b, sizeof(int) * (size_t)tb);
+    orbm_featvec VA, VB;
+    VA.node_id = S.up(node_id_a, (size_t)nn_a); VA.node_off = S.up(node_off_a, (size_t)nn_a + 1); VA.n_nodes = S.up(&nn_a, 1);
+    VA.feat = S.up(fa.data(), fa.size()); VA.node_stride = nn_a;
+    VB.node_id = S.up(node_id_b, (size_t)nn_b); VB.node_off = S.up(node_off_b, (size_t)nn_b + 1); VB.n_nodes = S.up(&nn_b, 1);
+    VB.feat = S.up(fb.data(), fb.size()); VB.node_stride = nn_b;
+    const uint8_t* d_av = S.up(a_valid, (size_t)A->n);
+    const uint8_t* d_bv = S.up(b_valid, (size_t)B->n);
+    float fe[12];
+    memcpy(fe, F12, sizeof(float) * 9); fe[9] = epipole[0]; fe[10] = epipole[1]; fe[11] = 0.f;
+    const float* d_fe = S.up(fe, 12);
+    int* d_m = (int*)S.alloc(sizeof(int) * ((size_t)A->n + 1));
+    if (!S.ok) return ORBX_E_CUDA;
+    if (!S.flush()) return ORBX_E_CUDA;
+    const int rc = orbm_search_for_triangulation_batch(&OA.F, &VA, d_av, &OB.F, &VB, d_bv, d_fe, d_fe + 9, scale, sigma2, nlevels, check_ori,
+                                                       d_m, d_m + A->n, nullptr);
+    if (rc) return rc;
+    const int rf = fetch_assign(d_m, A->n, match12, nmatches);
+    if (rf) return rf;
+    return *nmatches < 0 ? ORBX_E_ARG : ORBX_OK;
+}
+
 int orbm_project_points(const float* Tcw, const float* K, float bf, float min_x, float max_x, float min_y, float max_y,
                         float scale_factor, int nlevels, float viewing_cos_limit, int n, const float* xyz, const float* normal,
                         const float* max_distance, const float* min_distance, uint8_t* in_view, float* proj_xyxr, int* level,

@@ -1,6 +1,7 @@
 // orb_match_bow.cu -- vocabulary-guided matching, batched and device resident (sm_100a):
 //   ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&)      src/ORBmatcher.cc:552-697
 //   ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vector<MapPoint*>&)   src/ORBmatcher.cc:700-832
+//   ORBmatcher::SearchForTriangulation(KeyFrame*, KeyFrame*, F12, pairs, bOnlyStereo)   src/ORBmatcher.cc:1183-1361  (TRI)
 // One thread block per (side 1, side 2) problem.  DBoW2::FeatureVector (a std::map NodeId -> feature indices) arrives
 // in CSR form: node_id ascending, node_off, feat.  The reference walks the two maps in lockstep and, inside a shared
 // node, takes side-1 features in order; a side-2 feature that an earlier side-1 feature matched is skipped by the
@@ -35,6 +36,10 @@ struct BowParams {
     float nnratio; int check_ori, strict;
     int* match12; int* match21; int* nmatches; int* rounds;
     int n1_max, n2_max, desc_in_smem;
+    // SearchForTriangulation only
+    const float* ur1; const float* ur2;     // mvuRight of the two key frames [nprob][kp_stride] (NULL = monocular)
+    const float* F12; const float* epipole; // [nprob][9] row-major, [nprob][2]
+    float scale[32], sigma2[32];            // pKF2->mvScaleFactors, mvLevelSigma2
 };
 
 __device__ __forceinline__ int bw_rot_bin(const float a1, const float a2)   // src/ORBmatcher.cc:627-633
@@ -46,7 +51,13 @@ __device__ __forceinline__ int bw_rot_bin(const float a1, const float a2)   // s
     return bin;
 }
 
-template <bool DSM>    // side-2 descriptors staged in shared memory (LDS in the candidate loop) or read from global memory
+// TRI = ORBmatcher::SearchForTriangulation: the same walk over shared vocabulary nodes, but (1) a candidate must lie within
+// TH_LOW, away from the epipole when neither feature is a stereo one (:1272-1279) and on the epipolar line of the side-1
+// feature (CheckDistEpipolarLine, :1636-1650); (2) of equally close candidates the LAST one wins (`dist>bestDist` continues,
+// :1260); (3) the reference tests vbMatched2 (:1254) but never sets it, so NO feature depends on another one: one round, no
+// blockers, several side-1 features may end up with the same side-2 feature.  The keypoints of the few candidates that pass
+// the distance test are read from global memory.
+template <bool DSM, bool TRI>    // DSM: side-2 descriptors staged in shared memory (LDS in the candidate loop) or read from global memory
 __global__ void __launch_bounds__(BW_NT) k_bow_fixpoint(const __grid_constant__ BowParams P)
 {
     extern __shared__ __align__(16) uint32_t smem[];
@@ -108,10 +119,20 @@ __global__ void __launch_bounds__(BW_NT) k_bow_fixpoint(const __grid_constant__ 
             bool go = false;
             uint32_t myseg = 0;
             uint4 myd0 = make_uint4(0, 0, 0, 0), myd1 = myd0;
+            float myla = 0.f, mylb = 0.f, mylc = 0.f;
+            int myst1 = 0;
             if (q < t1) {
                 myseg = seg[q];
                 const int idx1 = feat1[q];
-                go = myseg != 0 && idx1 >= 0 && idx1 < n1 && P.A.valid[ka + idx1];             // :587-590 / :733-736
+                go = myseg != 0 && idx1 >= 0 && idx1 < n1 && P.A.valid[ka + idx1];             // :587-590 / :733-736 / :1222-1232
+                if (TRI && go) {
+                    const float* F = P.F12 + (size_t)prob * 9;
+                    const float x1 = P.A.kps[ka + idx1].x, y1 = P.A.kps[ka + idx1].y;
+                    myla = __fadd_rn(__fadd_rn(__fmul_rn(x1, F[0]), __fmul_rn(y1, F[3])), F[6]);   // :1640-1642
+                    mylb = __fadd_rn(__fadd_rn(__fmul_rn(x1, F[1]), __fmul_rn(y1, F[4])), F[7]);
+                    mylc = __fadd_rn(__fadd_rn(__fmul_rn(x1, F[2]), __fmul_rn(y1, F[5])), F[8]);
+                    myst1 = P.ur1 && P.ur1[ka + idx1] >= 0;
+                }
                 if (go && round > 0) {
                     const uint32_t top = st_top[q];
                     const uint32_t p1 = top & 0xffffu, p2 = top >> 16;
@@ -133,17 +154,40 @@ __global__ void __launch_bounds__(BW_NT) k_bow_fixpoint(const __grid_constant__ 
                                d2 = __shfl_sync(0xffffffffu, myd0.z, src), d3 = __shfl_sync(0xffffffffu, myd0.w, src),
                                d4 = __shfl_sync(0xffffffffu, myd1.x, src), d5 = __shfl_sync(0xffffffffu, myd1.y, src),
                                d6 = __shfl_sync(0xffffffffu, myd1.z, src), d7 = __shfl_sync(0xffffffffu, myd1.w, src);
+                float la = 0.f, lb = 0.f, lc = 0.f, ex = 0.f, ey = 0.f;
+                int st1 = 0;
+                if (TRI) {
+                    la = __shfl_sync(0xffffffffu, myla, src); lb = __shfl_sync(0xffffffffu, mylb, src); lc = __shfl_sync(0xffffffffu, mylc, src);
+                    st1 = __shfl_sync(0xffffffffu, myst1, src);
+                    ex = P.epipole[2 * prob]; ey = P.epipole[2 * prob + 1];
+                }
                 uint32_t a1 = BW_NONE, a2 = BW_NONE;
                 if (act) {
                     const int c1 = (int)(sg >> 16);
                     for (int j = (int)(sg & 0xffffu) + sub; j < c1; j += BW_G) {
-                        if (!use2[j] || blk[j] < qq) continue;                                  // :603-604 / :747-751
+                        if (!use2[j] || (!TRI && blk[j] < qq)) continue;                        // :603-604 / :747-751 / :1254-1262
                         uint4 b0, b1;
                         if (dsm) { b0 = sdesc[2 * j]; b1 = sdesc[2 * j + 1]; }
                         else { const uint4* b = (const uint4*)(P.B.desc + (kb + feat2[j]) * 8); b0 = __ldg(b); b1 = __ldg(b + 1); }
                         const uint32_t dist = __popc(d0 ^ b0.x) + __popc(d1 ^ b0.y) + __popc(d2 ^ b0.z) + __popc(d3 ^ b0.w) +
                                               __popc(d4 ^ b1.x) + __popc(d5 ^ b1.y) + __popc(d6 ^ b1.z) + __popc(d7 ^ b1.w);
-                        const uint32_t key = (dist << 16) | (uint32_t)j;
+                        uint32_t key = (dist << 16) | (uint32_t)j;
+                        if (TRI) {
+                            if (dist > TH_LOW) continue;                                        // :1268
+                            const int idx2 = feat2[j];
+                            const orbx_kp k2 = P.B.kps[kb + idx2];
+                            const int oct2 = k2.octave & 31;
+                            if (!st1 && !(P.ur2 && P.ur2[kb + idx2] >= 0)) {                     // :1272-1279
+                                const float dex = __fsub_rn(ex, k2.x), dey = __fsub_rn(ey, k2.y);
+                                if (__fadd_rn(__fmul_rn(dex, dex), __fmul_rn(dey, dey)) < __fmul_rn(100.0f, P.scale[oct2])) continue;
+                            }
+                            const float num = __fadd_rn(__fadd_rn(__fmul_rn(la, k2.x), __fmul_rn(lb, k2.y)), lc);   // :1644-1649
+                            const float den = __fadd_rn(__fmul_rn(la, la), __fmul_rn(lb, lb));
+                            if (den == 0) continue;
+                            const float dsqr = __fdiv_rn(__fmul_rn(num, num), den);
+                            if (!((double)dsqr < 3.84 * (double)P.sigma2[oct2])) continue;
+                            key = (dist << 16) | (0xffffu - (uint32_t)j);                       // ties: the last candidate
+                        }
                         if (key < a1) { a2 = a1; a1 = key; }
                         else if (key < a2) a2 = key;
                     }
@@ -159,9 +203,10 @@ __global__ void __launch_bounds__(BW_NT) k_bow_fixpoint(const __grid_constant__ 
                 if (sub == 0 && act) {
                     int best = -1;
                     const int bestDist1 = k1 == BW_NONE ? 256 : (int)(k1 >> 16), bestDist2 = k2 == BW_NONE ? 256 : (int)(k2 >> 16);
-                    if ((P.strict ? bestDist1 < TH_LOW : bestDist1 <= TH_LOW) &&                                  // :618 / :768
-                        (float)bestDist1 < __fmul_rn(P.nnratio, (float)bestDist2)) best = (int)(k1 & 0xffffu);    // :620 / :770
-                    if (st_best[qq] != (uint32_t)(best + 1)) s_flag[par] = 1;
+                    if (TRI) { if (k1 != BW_NONE) best = (int)(0xffffu - (k1 & 0xffffu)); }                       // :1288
+                    else if ((P.strict ? bestDist1 < TH_LOW : bestDist1 <= TH_LOW) &&                             // :618 / :768
+                             (float)bestDist1 < __fmul_rn(P.nnratio, (float)bestDist2)) best = (int)(k1 & 0xffffu);   // :620 / :770
+                    if (!TRI && st_best[qq] != (uint32_t)(best + 1)) s_flag[par] = 1;
                     st_best[qq] = (uint32_t)(best + 1);
                     st_top[qq] = (k1 == BW_NONE ? 0xffffu : (k1 & 0xffffu)) | ((k2 == BW_NONE ? 0xffffu : (k2 & 0xffffu)) << 16);
                 }
@@ -240,21 +285,15 @@ bool fill_side(BowSide& S, const orbm_frames* F, const orbm_featvec* V, const ui
 }
 } // namespace
 
-extern "C" int orbm_search_by_bow_batch(const orbm_frames* A, const orbm_featvec* VA, const uint8_t* a_valid,
-                                        const orbm_frames* B, const orbm_featvec* VB, const uint8_t* b_valid,
-                                        int kf_kf, float nnratio, int check_ori, int* match12, int* match21,
-                                        int* nmatches, int* rounds, void* cuda_stream)
+namespace {
+template <bool TRI>
+int launch_bow(BowParams& P, const orbm_frames* A, const orbm_frames* B, const void* const* same_device, int n_same, cudaStream_t st)
 {
-    BowParams P = {};
-    if (!fill_side(P.A, A, VA, a_valid) || !fill_side(P.B, B, VB, b_valid) || !a_valid || !match12 || !nmatches || A->nprob <= 0 || A->nprob != B->nprob)
-        return ORBX_E_ARG;
     const int dev = dev_of(A->kps);
-    if (dev < 0 || dev_of(B->kps) != dev || dev_of(match12) != dev || dev_of(nmatches) != dev || dev_of(VA->feat) != dev || dev_of(VB->feat) != dev)
-        return ORBX_E_ARG;
+    if (dev < 0) return ORBX_E_ARG;
+    for (int i = 0; i < n_same; ++i) if (dev_of(same_device[i]) != dev) return ORBX_E_ARG;
     int prev = -1;
     if (cudaGetDevice(&prev) != cudaSuccess || cudaSetDevice(dev) != cudaSuccess) { cudaGetLastError(); return ORBX_E_CUDA; }
-    P.nnratio = nnratio; P.check_ori = check_ori; P.strict = kf_kf ? 1 : 0;
-    P.match12 = match12; P.match21 = match21; P.nmatches = nmatches; P.rounds = rounds;
     const int b1 = (A->max_n > 0 && A->max_n < A->kp_stride) ? A->max_n : A->kp_stride, b2 = (B->max_n > 0 && B->max_n < B->kp_stride) ? B->max_n : B->kp_stride;
     P.n1_max = (b1 < BW_MAX_KP ? b1 : BW_MAX_KP) + 3 & ~3;
     P.n2_max = (b2 < BW_MAX_KP ? b2 : BW_MAX_KP) + 15 & ~15;
@@ -267,14 +306,46 @@ extern "C" int orbm_search_by_bow_batch(const orbm_frames* A, const orbm_featvec
         if (P.desc_in_smem) smem += (size_t)P.n2_max * 32;
         cudaError_t e = cudaSuccess;
         if (P.desc_in_smem) {
-            if (smem > 48 * 1024) e = cudaFuncSetAttribute(k_bow_fixpoint<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
-            if (e == cudaSuccess) { k_bow_fixpoint<true><<<A->nprob, BW_NT, smem, (cudaStream_t)cuda_stream>>>(P); e = cudaGetLastError(); }
+            if (smem > 48 * 1024) e = cudaFuncSetAttribute(k_bow_fixpoint<true, TRI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
+            if (e == cudaSuccess) { k_bow_fixpoint<true, TRI><<<A->nprob, BW_NT, smem, st>>>(P); e = cudaGetLastError(); }
         } else {
-            if (smem > 48 * 1024) e = cudaFuncSetAttribute(k_bow_fixpoint<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
-            if (e == cudaSuccess) { k_bow_fixpoint<false><<<A->nprob, BW_NT, smem, (cudaStream_t)cuda_stream>>>(P); e = cudaGetLastError(); }
+            if (smem > 48 * 1024) e = cudaFuncSetAttribute(k_bow_fixpoint<false, TRI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
+            if (e == cudaSuccess) { k_bow_fixpoint<false, TRI><<<A->nprob, BW_NT, smem, st>>>(P); e = cudaGetLastError(); }
         }
         if (e != cudaSuccess) { cudaGetLastError(); rc = ORBX_E_CUDA; }
     }
     cudaSetDevice(prev);
     return rc;
+}
+} // namespace
+
+extern "C" int orbm_search_by_bow_batch(const orbm_frames* A, const orbm_featvec* VA, const uint8_t* a_valid,
+                                        const orbm_frames* B, const orbm_featvec* VB, const uint8_t* b_valid,
+                                        int kf_kf, float nnratio, int check_ori, int* match12, int* match21,
+                                        int* nmatches, int* rounds, void* cuda_stream)
+{
+    BowParams P = {};
+    if (!fill_side(P.A, A, VA, a_valid) || !fill_side(P.B, B, VB, b_valid) || !a_valid || !match12 || !nmatches || A->nprob <= 0 || A->nprob != B->nprob)
+        return ORBX_E_ARG;
+    P.nnratio = nnratio; P.check_ori = check_ori; P.strict = kf_kf ? 1 : 0;
+    P.match12 = match12; P.match21 = match21; P.nmatches = nmatches; P.rounds = rounds;
+    const void* same[] = { B->kps, match12, nmatches, VA->feat, VB->feat };
+    return launch_bow<false>(P, A, B, same, 5, (cudaStream_t)cuda_stream);
+}
+
+extern "C" int orbm_search_for_triangulation_batch(const orbm_frames* A, const orbm_featvec* VA, const uint8_t* a_valid,
+                                                   const orbm_frames* B, const orbm_featvec* VB, const uint8_t* b_valid,
+                                                   const float* F12, const float* epipole, const float* scale, const float* sigma2, int nlevels,
+                                                   int check_ori, int* match12, int* nmatches, void* cuda_stream)
+{
+    BowParams P = {};
+    if (!fill_side(P.A, A, VA, a_valid) || !fill_side(P.B, B, VB, b_valid) || !a_valid || !b_valid || !match12 || !nmatches || A->nprob <= 0 ||
+        A->nprob != B->nprob || !F12 || !epipole || !scale || !sigma2 || nlevels <= 0 || nlevels > 32)
+        return ORBX_E_ARG;
+    P.check_ori = check_ori;
+    P.match12 = match12; P.match21 = nullptr; P.nmatches = nmatches; P.rounds = nullptr;
+    P.ur1 = A->u_right; P.ur2 = B->u_right; P.F12 = F12; P.epipole = epipole;
+    for (int i = 0; i < 32; ++i) { P.scale[i] = i < nlevels ? scale[i] : 0.f; P.sigma2[i] = i < nlevels ? sigma2[i] : 0.f; }
+    const void* same[] = { B->kps, match12, nmatches, VA->feat, VB->feat, F12, epipole };
+    return launch_bow<true>(P, A, B, same, 7, (cudaStream_t)cuda_stream);
 }

@@ -28,6 +28,9 @@
 //   int ORBmatcher::SearchBySim3(KeyFrame *pKF1, KeyFrame *pKF2, vector<MapPoint*> &vpMatches12, const float &s12,
 //                                const cv::Mat &R12, const cv::Mat &t12, const float th)
 //   { return b200::SearchBySim3(pKF1, pKF2, vpMatches12, s12, R12, t12, th); }           // src/ORBmatcher.cc:836
+//   int ORBmatcher::SearchForTriangulation(KeyFrame *pKF1, KeyFrame *pKF2, cv::Mat F12,
+//                                          vector<pair<size_t, size_t> > &vMatchedPairs, const bool bOnlyStereo)
+//   { return b200::SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo, mbCheckOrientation); }   // src/ORBmatcher.cc:1183
 //   the isInFrustum loop of Tracking::SearchLocalPoints -> b200::IsInFrustum(F, vpPoints, 0.5f, inView)
 //   the distance-matrix / median part of MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:311-334)
 //   -> BestIdx = b200::DistinctiveDescriptor(vDescriptors)
@@ -47,6 +50,7 @@
 #include <string>
 #include <type_traits>
 #include <unordered_map>
+#include <utility>
 #include <vector>
 
 #include "orb_b200.h"
@@ -771,6 +775,49 @@ int SearchBySim3(KeyFrameT* pKF1, KeyFrameT* pKF2, std::vector<MapPointT*>& vpMa
         if (idx2 >= 0 && vnMatch2[(size_t)idx2] == i1) { vpMatches12[(size_t)i1] = vpMapPoints2[(size_t)idx2]; nFound++; }
     }
     return nFound;
+}
+
+// ORBmatcher::SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, cv::Mat F12, vector<pair<size_t,size_t>>& vMatchedPairs,
+// const bool bOnlyStereo), src/ORBmatcher.cc:1183-1361.  The epipole (:1190-1196) is computed here in the reference's
+// arithmetic; the walk over shared vocabulary nodes, the distance / epipole / epipolar-line tests and the rotation histogram
+// run on the GPU (orbm_search_for_triangulation).  Reads pKF->mFeatVec, GetMapPointMatches(), mvuRight, mvKeysUn, mDescriptors,
+// GetCameraCenter() (pKF1), GetRotation(), GetTranslation(), fx, fy, cx, cy, mvScaleFactors, mvLevelSigma2 (pKF2).
+template <class KeyFrameT, class MatT>
+int SearchForTriangulation(KeyFrameT* pKF1, KeyFrameT* pKF2, const MatT& F12, std::vector<std::pair<size_t, size_t> >& vMatchedPairs,
+                           const bool bOnlyStereo, const bool checkOri)
+{
+    float Cw[3], R2w[9], t2w[3], C2[3], F[9];
+    detail::Read3(pKF1->GetCameraCenter(), Cw); detail::Read3x3(pKF2->GetRotation(), R2w); detail::Read3(pKF2->GetTranslation(), t2w);
+    detail::MulAdd3(R2w, t2w, Cw, C2);                                                  // C2 = R2w*Cw + t2w
+    const float invz = 1.0f / C2[2];
+    float epipole[2];
+    epipole[0] = pKF2->fx * C2[0] * invz + pKF2->cx;
+    epipole[1] = pKF2->fy * C2[1] * invz + pKF2->cy;
+    detail::Read3x3(F12, F);
+    const size_t na = pKF1->mvKeysUn.size(), nb = pKF2->mvKeysUn.size();
+    std::vector<unsigned char> v1(na ? na : 1, 0), v2(nb ? nb : 1, 0);
+    {
+        const auto p1 = pKF1->GetMapPointMatches();
+        const auto p2 = pKF2->GetMapPointMatches();
+        for (size_t i = 0; i < na; ++i) v1[i] = (!(i < p1.size() && p1[i]) && (!bOnlyStereo || pKF1->mvuRight[i] >= 0)) ? 1 : 0;   // :1222-1232
+        for (size_t i = 0; i < nb; ++i) v2[i] = (!(i < p2.size() && p2[i]) && (!bOnlyStereo || pKF2->mvuRight[i] >= 0)) ? 1 : 0;   // :1254-1262
+    }
+    const orbm_frame va = ResidentFrames::Local().Get((unsigned long)pKF1->mnFrameId, (double)pKF1->mTimeStamp, pKF1->mvKeysUn, pKF1->mDescriptors,
+                                                      &pKF1->mvuRight, 0.f, 1.f, 0.f, 1.f);
+    const orbm_frame vb = ResidentFrames::Local().Get((unsigned long)pKF2->mnFrameId, (double)pKF2->mTimeStamp, pKF2->mvKeysUn, pKF2->mDescriptors,
+                                                      &pKF2->mvuRight, 0.f, 1.f, 0.f, 1.f);
+    std::vector<int> ia, oa, fa, ib, ob, fb;
+    FlattenFeatureVector(pKF1->mFeatVec, ia, oa, fa); FlattenFeatureVector(pKF2->mFeatVec, ib, ob, fb);
+    std::vector<int> m12(na ? na : 1, -1);
+    int nmatches = 0;
+    Check(orbm_search_for_triangulation(&va, &v1[0], (int)ia.size(), ia.empty() ? 0 : &ia[0], &oa[0], fa.empty() ? 0 : &fa[0],
+                                        &vb, &v2[0], (int)ib.size(), ib.empty() ? 0 : &ib[0], &ob[0], fb.empty() ? 0 : &fb[0],
+                                        F, epipole, Ptr(pKF2->mvScaleFactors), Ptr(pKF2->mvLevelSigma2), (int)pKF2->mvScaleFactors.size(),
+                                        checkOri ? 1 : 0, &m12[0], &nmatches, Device()), "orbm_search_for_triangulation");
+    vMatchedPairs.clear();
+    vMatchedPairs.reserve((size_t)(nmatches > 0 ? nmatches : 0));
+    for (size_t i = 0; i < na; ++i) if (m12[i] >= 0) vMatchedPairs.push_back(std::make_pair(i, (size_t)m12[i]));   // :1350-1356
+    return nmatches;
 }
 
 }} // namespace ORB_SLAM2::b200

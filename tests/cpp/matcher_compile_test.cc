@@ -56,7 +56,7 @@ struct KeyFrameT {
     float fx, fy, cx, cy, mbf; int mnMinX, mnMinY, mnMaxX, mnMaxY;
     cv::Mat mDescriptors, Rcw, tcw, Ow;
     FeatVecT mFeatVec;
-    std::vector<float> mvScaleFactors, mvInvLevelSigma2, mvuRight;
+    std::vector<float> mvScaleFactors, mvInvLevelSigma2, mvLevelSigma2, mvuRight;
     std::vector<cv::KeyPoint> mvKeysUn;
     std::vector<MapPointT*> pts;
     std::vector<MapPointT*> GetMapPointMatches() { return pts; }
@@ -110,6 +110,8 @@ extern "C" int matcher_forwarders_instantiate(int run)
     n += ORB_SLAM2::b200::Fuse(&kf, cv::Mat(), pts, 4.0f, matched);
     const float s12 = 1.f;
     n += ORB_SLAM2::b200::SearchBySim3(&kf, &kf, matched, s12, cv::Mat(), cv::Mat(), 7.5f);
+    std::vector<std::pair<size_t, size_t> > pairs;
+    n += ORB_SLAM2::b200::SearchForTriangulation(&kf, &kf, cv::Mat(), pairs, false, true);
 #ifndef WITH_REFERENCE_HEADERS      // the reference's MapPoint lacks the two raw-distance accessors until patched
     std::vector<bool> inView;
     n += ORB_SLAM2::b200::IsInFrustum(a, pts, 0.5f, inView);
@@ -410,6 +412,35 @@ int fwd_search_by_sim3(int n1, const Kp* kps1, const unsigned char* desc1, const
     for (int k = 0; k < n1; ++k) matches12[k] = m12[k] ? (int)(m12[k] - &mps[0]) : -1;
     ORB_SLAM2::b200::ResidentFrames::Local().Clear();
     return nf;
+}
+
+// ORBmatcher::SearchForTriangulation through b200::SearchForTriangulation (arrays as in oracle/ref_bow_harness.cc)
+int fwd_search_for_triangulation(int n1, const Kp* kps1, const unsigned char* desc1, const unsigned char* has_mp1, const float* u_right1,
+                                 int nn1, const int* node_id1, const int* node_off1, const int* feat1,
+                                 int n2, const Kp* kps2, const unsigned char* desc2, const unsigned char* has_mp2, const float* u_right2,
+                                 int nn2, const int* node_id2, const int* node_off2, const int* feat2,
+                                 const float* F12, const float* Cw, const float* pose2, const float* K2,
+                                 const float* scale, const float* sigma2, int nlevels, int only_stereo, int check_ori, int* match12)
+{
+    KeyFrameT A, B;
+    std::vector<MapPointT> s1(n1 > 0 ? n1 : 1), s2(n2 > 0 ? n2 : 1);
+    fill_keys(A.mvKeysUn, kps1, n1); fill_desc(A.mDescriptors, desc1, n1); fill_featvec(A.mFeatVec, nn1, node_id1, node_off1, feat1);
+    fill_keys(B.mvKeysUn, kps2, n2); fill_desc(B.mDescriptors, desc2, n2); fill_featvec(B.mFeatVec, nn2, node_id2, node_off2, feat2);
+    A.pts.assign(n1, static_cast<MapPointT*>(0)); B.pts.assign(n2, static_cast<MapPointT*>(0));
+    for (int i = 0; i < n1; ++i) if (has_mp1[i]) A.pts[i] = &s1[i];
+    for (int i = 0; i < n2; ++i) if (has_mp2[i]) B.pts[i] = &s2[i];
+    A.mvuRight.assign(n1, -1.f); B.mvuRight.assign(n2, -1.f);
+    if (u_right1) A.mvuRight.assign(u_right1, u_right1 + n1);
+    if (u_right2) B.mvuRight.assign(u_right2, u_right2 + n2);
+    B.mvScaleFactors.assign(scale, scale + nlevels); B.mvLevelSigma2.assign(sigma2, sigma2 + nlevels);
+    B.fx = K2[0]; B.fy = K2[1]; B.cx = K2[2]; B.cy = K2[3];
+    A.Ow = mat_of(Cw, 3, 1); B.Rcw = mat_of(pose2, 3, 3); B.tcw = mat_of(pose2 + 9, 3, 1);
+    std::vector<std::pair<size_t, size_t> > pairs;
+    const int nm = ORB_SLAM2::b200::SearchForTriangulation(&A, &B, mat_of(F12, 3, 3), pairs, only_stereo != 0, check_ori != 0);
+    for (int i = 0; i < n1; ++i) match12[i] = -1;
+    for (size_t k = 0; k < pairs.size(); ++k) match12[pairs[k].first] = (int)pairs[k].second;
+    ORB_SLAM2::b200::ResidentFrames::Local().Clear();
+    return nm;
 }
 
 } // extern "C"

@@ -172,8 +172,25 @@ def fuse():
     np.savez_compressed(os.path.join(HERE, "ref_fuse.npz"), **out)
 
 
+def triang():
+    """Outputs of the reference's unmodified ORBmatcher::SearchForTriangulation (src/ORBmatcher.cc:1183-1361) on the scenes of
+    tests/triang_lib.py (regenerated from seeds; results stored)."""
+    from matcher_lib import extract_frame
+    from test_triang_oracle import CASES, H, K, NF, W
+    from triang_lib import search_for_triangulation, triang_scene
+    kps, desc, scale = extract_frame(W, H, NF, 2)
+    sigma2 = (scale * scale).astype(np.float32)
+    out = {}
+    for seed, only_stereo, check_ori, mono, n2 in CASES:
+        s = triang_scene(kps, desc, W, H, seed, K, scale, n2)
+        nm, m12 = search_for_triangulation("ref", s, K, scale, sigma2, only_stereo, check_ori, mono)
+        out[f"triang_{seed}_n"] = nm
+        out[f"triang_{seed}_m12"] = m12
+    np.savez_compressed(os.path.join(HERE, "ref_triang.npz"), **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["primitives", "extractor", "matchers", "projection_overloads", "mappoint", "bow", "fuse"]
+    which = sys.argv[1:] or ["primitives", "extractor", "matchers", "projection_overloads", "mappoint", "bow", "fuse", "triang"]
     for name in which:
         globals()[name]()
     print("golden fixtures written to", HERE)

@@ -217,3 +217,32 @@ def test_fuse_and_sim3_forwarders_run_like_the_patched_reference(dropin):
                                   p(s["R1"]), p(s["t1"]), p(s["R2"]), p(s["t2"]), s["s12"], p(s["R12"]), p(s["t12"]), s["npts"], p(s["bad"]),
                                   p(s["xyz"]), p(s["mp_desc"]), p(s["level"]), p(s["min_dist"]), p(s["max_dist"]), p(s["idx_in_kf2"]), p(m12), th)
         assert nf == want_n and nf > 200 and (m12 == want_m12).all()
+
+
+@pytest.mark.gpu
+def test_triangulation_forwarder_runs_like_the_patched_reference(dropin):
+    """b200::SearchForTriangulation at run time: key-frame stand-ins filled from arrays, the epipole computed by the forwarder,
+    vMatchedPairs compared with the CPU checker."""
+    from matcher_lib import extract_frame
+    from test_triang_oracle import CASES, K
+    from triang_lib import search_for_triangulation, triang_scene
+    M = C.CDLL(os.path.join(CPP, "_build", "libmatcher_fwd.so"))
+    vp, ci = C.c_void_p, C.c_int
+    p = lambda a: None if a is None else a.ctypes.data
+    W, H = 1241, 376
+    kps, desc, scale = extract_frame(W, H, 2000, 2)
+    sigma2 = (scale * scale).astype(np.float32)
+    Kf = np.asarray(K, np.float32)
+    side = [ci, vp, vp, vp, vp, ci, vp, vp, vp]
+    M.fwd_search_for_triangulation.argtypes = side * 2 + [vp, vp, vp, vp, vp, vp, ci, ci, ci, vp]
+    for seed, only_stereo, check_ori, mono, n2 in CASES:
+        s = triang_scene(kps, desc, W, H, seed, K, scale, n2)
+        want = search_for_triangulation("oracle", s, K, scale, sigma2, only_stereo, check_ori, mono)
+        (id1, off1, f1), (id2, off2, f2) = s["fv1"], s["fv2"]
+        ur1, ur2 = (None, None) if mono else (s["ur1"], s["ur2"])
+        out = np.zeros(len(s["k1"]), np.int32)
+        nm = M.fwd_search_for_triangulation(len(s["k1"]), p(s["k1"]), p(s["d1"]), p(s["has1"]), p(ur1), len(id1), p(id1), p(off1), p(f1),
+                                            len(s["k2"]), p(s["k2"]), p(s["d2"]), p(s["has2"]), p(ur2), len(id2), p(id2), p(off2), p(f2),
+                                            p(s["F12"]), p(s["Cw"]), p(s["pose2"]), p(Kf), p(scale), p(sigma2), len(scale), int(only_stereo),
+                                            int(check_ori), p(out))
+        assert nm == want[0] and nm > 40 and (out == want[1]).all(), (seed, only_stereo, check_ori, mono)
