@@ -527,6 +527,22 @@ def bench_mappoint_side(dev, d_kps, d_desc, d_n, cap, w, h, scale_factor, reps=4
     out["bow"] = {"value": nb / (ms * 1e-3), "unit": "problems/s", "what": "SearchByBoW(KeyFrame, KeyFrame), nnratio 0.75, 256 nodes",
                   "problems_per_launch": nb, "ms_per_launch": ms, "matches_per_problem": float(nm.float().mean().item()),
                   "rounds_max": int(rounds.max().item())}
+    # ---- triangulation: SearchForTriangulation on the same key-frame pairs (side B = side A's features seen again: same keypoints,
+    # noisy descriptors, so the epipolar line of a feature passes through its twin), half of the features stereo ones
+    F12 = torch.tensor([0, 0, 0, 0, 0, -1, 0, 1, 0], dtype=torch.float32, device=dev).repeat(nb, 1).contiguous()
+    epi = torch.tensor([0.55 * w, 0.45 * h], dtype=torch.float32, device=dev).repeat(nb, 1).contiguous()
+    urA = torch.where(torch.rand((nb, cap), generator=g, device=dev) < 0.5, kA[..., 0] - 20.0, torch.full((nb, cap), -1.0, device=dev)).contiguous()
+    urB = torch.where(torch.rand((nb, cap), generator=g, device=dev) < 0.5, kA[..., 0] - 20.0, torch.full((nb, cap), -1.0, device=dev)).contiguous()
+    tvA = (torch.rand((nb, cap), generator=g, device=dev) < 0.7).to(torch.uint8).contiguous()      # features without a map point yet
+    tvB = (torch.rand((nb, cap), generator=g, device=dev) < 0.7).to(torch.uint8).contiguous()
+    t_scale = np.float32([np.float32(scale_factor) ** i for i in range(LEVELS)])
+    t_sigma2 = (t_scale * t_scale).astype(np.float32)
+    TA, TB = ob.frames_batch(kA, dA, nA, bounds, urA, max_n), ob.frames_batch(kB, dB, nB, bounds, urB, max_n)
+    t12 = torch.zeros((nb, cap), dtype=torch.int32, device=dev)
+    tnm = torch.zeros(nb, dtype=torch.int32, device=dev)
+    ms = timed(lambda: ob.search_for_triangulation_batch(TA, VA, tvA, TB, VB, tvB, F12, epi, t_scale, t_sigma2, True, t12, tnm, stream.cuda_stream))
+    out["triangulation"] = {"value": nb / (ms * 1e-3), "unit": "problems/s", "what": "SearchForTriangulation(KeyFrame, KeyFrame), 256 nodes, "
+                            "rotation check on", "problems_per_launch": nb, "ms_per_launch": ms, "matches_per_problem": float(tnm.float().mean().item())}
     # ---- distinctive descriptors
     npnt = 65536
     sizes = torch.randint(2, 34, (npnt,), generator=g, device=dev, dtype=torch.int32)
@@ -599,6 +615,23 @@ def bench_mappoint_side(dev, d_kps, d_desc, d_n, cap, w, h, scale_factor, reps=4
         dt = (time.perf_counter() - t0) / 20
         assert want[0] == int(nm[0].item()) and (want[1] == m12[0, :n0].cpu().numpy()).all(), "SearchByBoW disagrees with the CPU checker"
         out["bow"]["cpu_baseline"] = {"value": 1.0 / dt, "unit": "problems/s", "cores": 1, "kind": "port", "sample": "problem 0, 20 repetitions, results compared"}
+        # triangulation, problem 0
+        O = oracle_lib.oracle()
+        vpp, cii = C.c_void_p, C.c_int
+        O.orbo_search_for_triangulation.argtypes = [cii, vpp, vpp, vpp, vpp, cii, vpp, vpp, vpp] * 2 + [vpp, vpp, vpp, vpp, cii, cii, vpp]
+        tA = dict(kp=kp0, d=tonp(dA[0, :n0]), has=(1 - tonp(tvA[0, :n0])).astype(np.uint8), ur=tonp(urA[0, :n0]), fv=fv(VA))
+        tB = dict(kp=kp0, d=tonp(dB[0, :n0]), has=(1 - tonp(tvB[0, :n0])).astype(np.uint8), ur=tonp(urB[0, :n0]), fv=fv(VB))
+        f0, e0 = tonp(F12[0]), tonp(epi[0])
+        w12 = np.zeros(n0, np.int32)
+        pp = lambda a: a.ctypes.data
+        t0 = time.perf_counter()
+        for _ in range(20):
+            w_nm = O.orbo_search_for_triangulation(n0, pp(tA["kp"]), pp(tA["d"]), pp(tA["has"]), pp(tA["ur"]), len(tA["fv"][0]), pp(tA["fv"][0]), pp(tA["fv"][1]), pp(tA["fv"][2]),
+                                                   n0, pp(tB["kp"]), pp(tB["d"]), pp(tB["has"]), pp(tB["ur"]), len(tB["fv"][0]), pp(tB["fv"][0]), pp(tB["fv"][1]), pp(tB["fv"][2]),
+                                                   pp(f0), pp(e0), pp(t_scale), pp(t_sigma2), 0, 1, pp(w12))
+        dt = (time.perf_counter() - t0) / 20
+        assert w_nm == int(tnm[0].item()) and w_nm > 100 and (w12 == t12[0, :n0].cpu().numpy()).all(), "SearchForTriangulation disagrees with the CPU checker"
+        out["triangulation"]["cpu_baseline"] = {"value": 1.0 / dt, "unit": "problems/s", "cores": 1, "kind": "port", "sample": "problem 0, 20 repetitions, results compared"}
         # fuse, problem 0
         from fuse_lib import window_best_free_oracle
         n0 = int(nF[0].item())
