@@ -435,6 +435,24 @@ int orbm_project_points(const float* Tcw, const float* K, float bf, float min_x,
                         float* view_cos, int device);
 int orbm_distinctive_descriptor(const uint8_t* desc, int n, const uint8_t* bad, int* best_idx, int* best_median, int device);
 
+/* ---- the per-keypoint steps of the monocular / RGB-D Frame constructors (src/Frame.cc:127-240), device resident --------
+ * A stereo frame stays on the GPU from extraction to depth (orbx_extract_stereo_batch); these two do the same for the other
+ * two constructors: every pointer except K / dist_coef is DEVICE memory laid out as orbx_extract_batch leaves it
+ * (kps [batch][cap_per_frame], n [batch]); the calls only enqueue on cuda_stream.
+ * orbx_undistort_keypoints_batch: Frame::UndistortKeyPoints (src/Frame.cc:436-468), i.e. cv::undistortPoints(mat, mat, mK,
+ * mDistCoef, cv::Mat(), mK) on every keypoint: K = fx, fy, cx, cy (host); dist_coef = mDistCoef (host; 0, 4, 5, 8 or 12
+ * entries k1 k2 p1 p2 [k3 [k4 k5 k6 [s1..s4]]]); with dist_coef[0] == 0 the keypoints are copied (:438-442).  In place
+ * (d_kps_un == d_kps) is allowed.
+ * orbx_stereo_from_rgbd_batch: Frame::ComputeStereoFromRGBD (src/Frame.cc:702-727): depth image of frame f (float32, already
+ * scaled by mDepthMapFactor, src/Tracking.cc:257-258) at d_depth + f * depth_frame_stride bytes, rows depth_pitch bytes apart,
+ * read at the DISTORTED keypoint; d_kps_un (NULL = d_kps) supplies the undistorted x of :720.  d_u_right / d_depth_out
+ * [batch][cap_per_frame] = mvuRight / mvDepth (-1 without depth and behind n[f]); a keypoint outside the image reads as no depth. */
+int orbx_undistort_keypoints_batch(const orbx_kp* d_kps, orbx_kp* d_kps_un, const int* d_n, int cap_per_frame, int batch,
+                                   const float* K, const float* dist_coef, int n_dist, void* cuda_stream);
+int orbx_stereo_from_rgbd_batch(const orbx_kp* d_kps, const orbx_kp* d_kps_un, const int* d_n, int cap_per_frame, int batch,
+                                const float* d_depth, size_t depth_pitch, size_t depth_frame_stride, int w, int h, float bf,
+                                float* d_u_right, float* d_depth_out, void* cuda_stream);
+
 /* ---- test taps -------------------------------------------------------------------- */
 /* ORBmatcher::ComputeThreeMaxima (src/ORBmatcher.cc:1663-1707) as the matcher kernels run it: sizes [n][30] bin
  * counts (host) -> ind [n][3]. */

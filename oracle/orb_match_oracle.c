@@ -604,3 +604,45 @@ int orbo_search_for_triangulation(int n1, const orbo_kp* kps1, const uint8_t* de
     free(matched2);
     return nmatches;
 }
+
+/* Frame::UndistortKeyPoints, src/Frame.cc:436-468: cv::undistortPoints(mat, mat, mK, mDistCoef, cv::Mat(), mK) restated from
+ * OpenCV 4.13 (third-party arithmetic, not under /root/reference; pinned against cv2 4.13.0 live and against
+ * tests/golden/cv2_undistort.npz by tests/test_frame_steps.py): double arithmetic, normalise, five iterations of the inverse
+ * distortion model (TermCriteria(MAX_ITER, 5, 0.01): the count only), project with the new camera matrix, narrow to float.
+ * K = fx, fy, cx, cy; dist = k1 k2 p1 p2 [k3 [k4 k5 k6 [s1 s2 s3 s4]]].  Only pt.x / pt.y change. */
+void orbo_undistort_keypoints(int n, const orbo_kp* kps, const float* K, const float* dist, int n_dist, orbo_kp* out)
+{
+    if (n_dist == 0 || dist[0] == 0.0f) { for (int i = 0; i < n; ++i) out[i] = kps[i]; return; }   /* :438-442 */
+    double k[12] = { 0 };
+    for (int i = 0; i < n_dist && i < 12; ++i) k[i] = (double)dist[i];
+    const double fx = K[0], fy = K[1], cx = K[2], cy = K[3], ifx = 1.0 / fx, ify = 1.0 / fy;
+    for (int i = 0; i < n; ++i) {
+        double x = ((double)kps[i].x - cx) * ifx, y = ((double)kps[i].y - cy) * ify;
+        const double x0 = x, y0 = y;
+        for (int j = 0; j < 5; ++j) {
+            const double r2 = x * x + y * y;
+            const double icdist = (1 + ((k[7] * r2 + k[6]) * r2 + k[5]) * r2) / (1 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2);
+            if (icdist < 0) { x = x0; y = y0; break; }
+            const double deltaX = 2 * k[2] * x * y + k[3] * (r2 + 2 * x * x) + k[8] * r2 + k[9] * r2 * r2;
+            const double deltaY = k[2] * (r2 + 2 * y * y) + 2 * k[3] * x * y + k[10] * r2 + k[11] * r2 * r2;
+            x = (x0 - deltaX) * icdist;
+            y = (y0 - deltaY) * icdist;
+        }
+        out[i] = kps[i];
+        out[i].x = (float)(fx * x + cx);
+        out[i].y = (float)(fy * y + cy);
+    }
+}
+
+/* Frame::ComputeStereoFromRGBD, src/Frame.cc:702-727.  depth: h x w floats, row-major. */
+void orbo_stereo_from_rgbd(int n, const orbo_kp* kps, const orbo_kp* kps_un, const float* depth, int w, int h, float bf,
+                           float* u_right, float* depth_out)
+{
+    for (int i = 0; i < n; ++i) {
+        u_right[i] = -1.0f; depth_out[i] = -1.0f;
+        const int v = (int)kps[i].y, u = (int)kps[i].x;      /* imDepth.at<float>(v, u) with float arguments */
+        if (u < 0 || u >= w || v < 0 || v >= h) continue;    /* (the reference would read out of bounds) */
+        const float d = depth[(size_t)v * (size_t)w + (size_t)u];
+        if (d > 0) { depth_out[i] = d; u_right[i] = kps_un[i].x - bf / d; }
+    }
+}

@@ -170,6 +170,11 @@ int orbo_search_for_triangulation(int n1, const orbo_kp* kps1, const uint8_t* de
                                   const float* F12, const float* epipole, const float* scale, const float* sigma2,
                                   int onlyStereo, int checkOri, int* match12);
 
+/* Frame::UndistortKeyPoints (src/Frame.cc:436-468, cv::undistortPoints of OpenCV 4.13) and Frame::ComputeStereoFromRGBD (:702-727) */
+void orbo_undistort_keypoints(int n, const orbo_kp* kps, const float* K, const float* dist, int n_dist, orbo_kp* out);
+void orbo_stereo_from_rgbd(int n, const orbo_kp* kps, const orbo_kp* kps_un, const float* depth, int w, int h, float bf,
+                           float* u_right, float* depth_out);
+
 /* map-point side, orb_mappoint_oracle.c */
 int orbo_distinctive_descriptor(const uint8_t* desc, int n, const uint8_t* bad, int* median_out);
 int orbo_predict_scale(float max_distance, float current_dist, float log_scale_factor, int nlevels);

@@ -309,4 +309,27 @@ double orbref_stereo_bench(int nfeatures, float scaleFactor, int nlevels, int in
     return dt;
 }
 
+// Frame::ComputeStereoFromRGBD (src/Frame.cc:702-727) on a frame built from arrays: kps = mvKeys (distorted), kps_un =
+// mvKeysUn, depth = the h x w float image.  u_right / depth_out [n] receive mvuRight / mvDepth.
+int orbref_stereo_from_rgbd(int n, const RefKp* kps, const RefKp* kps_un, const float* depth, int w, int h, float bf,
+                            float* u_right, float* depth_out)
+{
+    ref_arena::Scope scope;
+    {
+        Frame F;
+        F.N = n;
+        F.mvKeys.resize(n); F.mvKeysUn.resize(n);
+        for (int i = 0; i < n; ++i) {
+            F.mvKeys[i] = cv::KeyPoint(kps[i].x, kps[i].y, kps[i].size, kps[i].angle, kps[i].response, kps[i].octave, kps[i].class_id);
+            F.mvKeysUn[i] = cv::KeyPoint(kps_un[i].x, kps_un[i].y, kps_un[i].size, kps_un[i].angle, kps_un[i].response, kps_un[i].octave, kps_un[i].class_id);
+        }
+        F.mbf = bf;
+        cv::Mat D(h, w, CV_32F);
+        for (int r = 0; r < h; ++r) std::memcpy(D.ptr(r), depth + (size_t)r * w, sizeof(float) * (size_t)w);
+        F.ComputeStereoFromRGBD(D);
+        for (int i = 0; i < n; ++i) { u_right[i] = F.mvuRight[i]; depth_out[i] = F.mvDepth[i]; }
+    }
+    return 0;
+}
+
 } // extern "C"

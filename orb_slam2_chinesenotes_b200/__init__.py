@@ -133,6 +133,8 @@ def lib():
         L.orbm_search_for_initialization.argtypes = [fp, fp, vp, vp, i32, f32, i32, pi, i32]
         L.orbm_window_search_best.argtypes = [fp, i32] + [vp] * 11 + [i32, i32, pi, i32]
         L.orbm_window_best_free.argtypes = [fp, i32] + [vp] * 6 + [i32, i32, vp, vp, pi, i32]
+        L.orbx_undistort_keypoints_batch.argtypes = [vp, vp, vp, i32, i32, vp, vp, i32, vp]
+        L.orbx_stereo_from_rgbd_batch.argtypes = [vp, vp, vp, i32, i32, vp, C.c_size_t, C.c_size_t, i32, i32, f32, vp, vp, vp]
         L.orbm_window_best_free_batch.argtypes = [C.POINTER(OrbmFrames), C.POINTER(OrbmFreeWindows), vp, i32, i32, vp, vp, vp, vp]
         L.orbm_search_by_projection_points_batch.argtypes = [C.POINTER(OrbmFrames), vp, i32, C.POINTER(OrbmPoints), vp, vp, f32, f32, vp, vp, vp]
         L.orbm_window_search_best_batch.argtypes = [C.POINTER(OrbmFrames), C.POINTER(OrbmWindows), vp, vp, i32, i32, vp, vp, vp]
@@ -597,6 +599,28 @@ def window_best_free_batch(frames, q, nq, nq_stride, best_idx, best_dist, nfound
                                            int(th_accept), _ptr(best_idx), _ptr(best_dist), _ptr(nfound), stream)
     if rc:
         raise OrbError(rc, "orbm_window_best_free_batch failed")
+
+
+def undistort_keypoints_batch(kps, kps_un, n, K, dist_coef, stream=None):
+    """orbx_undistort_keypoints_batch: Frame::UndistortKeyPoints (src/Frame.cc:436-468) for every frame of a batch.  kps,
+    kps_un: CUDA tensors [P,cap] of 28-byte records (kps_un may be kps), n [P] int32; K = fx, fy, cx, cy and dist_coef host."""
+    K = np.ascontiguousarray(K, np.float32)
+    d = np.ascontiguousarray(dist_coef, np.float32).ravel()
+    rc = lib().orbx_undistort_keypoints_batch(_ptr(kps), _ptr(kps_un), _ptr(n), int(kps.shape[1]), int(kps.shape[0]), K.ctypes.data,
+                                              d.ctypes.data if len(d) else None, len(d), stream)
+    if rc:
+        raise OrbError(rc, "orbx_undistort_keypoints_batch failed")
+
+
+def stereo_from_rgbd_batch(kps, kps_un, n, depth, bf, u_right, depth_out, stream=None):
+    """orbx_stereo_from_rgbd_batch: Frame::ComputeStereoFromRGBD (src/Frame.cc:702-727).  depth: CUDA float32 tensor [P,h,w]
+    (any row / frame stride); kps_un may be None (= kps); u_right, depth_out: CUDA float32 [P,cap]."""
+    P, h, w = (int(x) for x in depth.shape)
+    es = depth.element_size()
+    rc = lib().orbx_stereo_from_rgbd_batch(_ptr(kps), _ptr(kps_un), _ptr(n), int(kps.shape[1]), P, _ptr(depth), depth.stride(1) * es,
+                                           depth.stride(0) * es, w, h, float(np.float32(bf)), _ptr(u_right), _ptr(depth_out), stream)
+    if rc:
+        raise OrbError(rc, "orbx_stereo_from_rgbd_batch failed")
 
 
 def frames_batch(kps, desc, n, bounds, u_right=None, max_n=0):

@@ -189,8 +189,34 @@ def triang():
     np.savez_compressed(os.path.join(HERE, "ref_triang.npz"), **out)
 
 
+def frame_steps():
+    """cv2.undistortPoints (OpenCV 4.13) on the keypoints / cameras of tests/test_frame_steps.py, and the reference's unmodified
+    Frame::ComputeStereoFromRGBD on its RGB-D scene."""
+    import ctypes as C
+    import cv2
+    from oracle_lib import ref
+    from test_frame_steps import CAMS, depth_image, keypoints, undistort_oracle
+    assert cv2.__version__.startswith("4.13"), cv2.__version__
+    out = {}
+    k = keypoints(11)
+    for name, (K, D) in CAMS.items():
+        Km = np.float32([[K[0], 0, K[2]], [0, K[1], K[3]], [0, 0, 1]])
+        w = cv2.undistortPoints(np.stack([k["x"], k["y"]], 1).reshape(-1, 1, 2), Km, np.float32(D), None, Km).reshape(-1, 2)
+        out[name] = np.stack([k["x"], k["y"]], 1) if D[0] == 0.0 else w
+    k = keypoints(4)
+    k["x"], k["y"] = np.clip(k["x"], 0, 639.9), np.clip(k["y"], 0, 479.9)
+    ku = undistort_oracle(k, *CAMS["tum1"])
+    d = depth_image(4)
+    ur, dz = np.zeros(len(k), np.float32), np.zeros(len(k), np.float32)
+    L = ref()
+    L.orbref_stereo_from_rgbd.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p]
+    L.orbref_stereo_from_rgbd(len(k), k.ctypes.data, ku.ctypes.data, d.ctypes.data, 640, 480, 40.0, ur.ctypes.data, dz.ctypes.data)
+    out["rgbd_ur"], out["rgbd_depth"] = ur, dz
+    np.savez_compressed(os.path.join(HERE, "cv2_undistort.npz"), **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["primitives", "extractor", "matchers", "projection_overloads", "mappoint", "bow", "fuse", "triang"]
+    which = sys.argv[1:] or ["primitives", "extractor", "matchers", "projection_overloads", "mappoint", "bow", "fuse", "triang", "frame_steps"]
     for name in which:
         globals()[name]()
     print("golden fixtures written to", HERE)
