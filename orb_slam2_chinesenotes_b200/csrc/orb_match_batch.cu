@@ -780,15 +780,32 @@ __global__ void __launch_bounds__(MB_NT) k_window_best_free(const __grid_constan
     constexpr int QW = 32 / MB_G;
     const int sub = lane & (MB_G - 1);
     int found = 0;
-    for (int base = (part * nwarps + warp) * QW; base < nq; base += P.split * nwarps * QW) {
+    // a group's query data (a dozen words from global memory) is fetched one trip ahead of the window walk that uses it
+    struct QD { float u, v, r, ur; int level; bool live; uint4 q0, q1; };
+    auto fetch = [&](const int q) {
+        QD d;
+        d.live = q < nq && (!P.b0 || P.b0[qo + q]);
+        d.u = d.v = d.r = d.ur = 0.f; d.level = 0; d.q0 = d.q1 = make_uint4(0, 0, 0, 0);
+        if (d.live) {
+            d.u = P.f0[3 * (qo + q)]; d.v = P.f0[3 * (qo + q) + 1]; d.r = P.f0[3 * (qo + q) + 2];
+            d.level = P.i0[qo + q];
+            d.ur = P.f1 ? P.f1[qo + q] : 0.f;
+            d.q0 = __ldg((const uint4*)(P.qdesc + (qo + q) * 8)); d.q1 = __ldg((const uint4*)(P.qdesc + (qo + q) * 8) + 1);
+        }
+        return d;
+    };
+    const int step = P.split * nwarps * QW;
+    int base = (part * nwarps + warp) * QW;
+    QD nxt = fetch(base + lane / MB_G);
+    for (; base < nq; base += step) {
         const int q = base + lane / MB_G;
-        const bool live = q < nq && (!P.b0 || P.b0[qo + q]);
+        const QD cur = nxt;
+        nxt = fetch(q + step);
+        const float u = cur.u, v = cur.v, r = cur.r, ur = cur.ur;
+        const int level = cur.level;
+        const uint4 q0 = cur.q0, q1 = cur.q1;
         uint32_t best = MB_NONE;
-        if (live) {
-            const float u = P.f0[3 * (qo + q)], v = P.f0[3 * (qo + q) + 1], r = P.f0[3 * (qo + q) + 2];
-            const int level = P.i0[qo + q];
-            const float ur = P.f1 ? P.f1[qo + q] : 0.f;
-            const uint4 q0 = __ldg((const uint4*)(P.qdesc + (qo + q) * 8)), q1 = __ldg((const uint4*)(P.qdesc + (qo + q) * 8) + 1);
+        if (cur.live) {
             // src/KeyFrame.cc:642-656
             const int nMinCellX = max(0, (int)floorf((u - P.min_x - r) * P.inv_w));
             const int nMaxCellX = min(GRID_COLS - 1, (int)ceilf((u - P.min_x + r) * P.inv_w));
