@@ -435,7 +435,9 @@ int run_batch(orbx_ctx* c, const uint8_t* imgs, size_t frame_stride, int batch, 
     const int nslot = nchunks < NSLOT ? nchunks : NSLOT;
     // Chunks alternate between compute streams only on the piped path (small chunks: one chunk's latency-bound sparse
     // kernels share the SMs with the next chunk's dense ones).  Device-resident chunks are large; running two of
-    // them side by side measured slower than back to back (6.84 vs 6.40 ms per 512 frames in chunks of 256).
+    // them side by side measured slower than back to back (6.84 vs 6.40 ms per 512 frames in chunks of 256; again with the
+    // round-2 kernels, 1024 frames: 512-frame chunks 105.0 k frames/s back to back vs 88.8 k on two streams, 256: 100.1 vs 90.6 k,
+    // 128: 95.3 vs 88.1 k -- tools/multi_stream_exp.sh).
     static const bool force_multi = []{ const char* e = getenv("ORB_FORCE_MULTI"); return e && e[0] == '1'; }();   // experiment knob
     const bool multi = nslot > 1 && !c->profile && (piped || force_multi);
     const size_t in_frame_bytes = pitch * (size_t)h;
