@@ -24,6 +24,13 @@
 // the one or two among the 32 they own, costs two more block barriers and a pass over the queries per round and
 // measures 0.45-0.49 ms per 444 problems against 0.405 ms: the later rounds are cheap already, the time is in the grid
 // sort and round 0.
+// Measured dead end (round 2, last session): a "two-speed" window walk -- every lane runs ahead over its share of the window's
+// candidates (positions sub, sub + 4, ... of the concatenated column runs) with only the cheap tests (level, exact window, taken,
+// right coordinate) until one passes, then the lanes that hold one compute their distances together -- is bit-exact and 2.8x
+// SLOWER (0.97 vs 0.35 ms per 444 problems): the warp waits for its slowest scanner before EVERY distance step, so it pays the
+// sum over steps of the longest gap instead of the longest lane's total.  (Queueing the survivors per 4-lane group and computing
+// distances on full groups would bound that, but a scan step costs ~36 instructions against ~58 for the plain iteration, the
+// distance part being only ~30 of them: at the measured ~30 % pass rate it would save ~15 %.)
 //
 // Layout per problem (built once per launch in the block): keypoints sorted by (grid column, grid row, index) --
 // the order GetFeaturesInArea returns them in -- as 16-byte records {x, y, octave | index << 8 | taken << 31,
