@@ -644,6 +644,16 @@ def bench_mappoint_side(dev, d_kps, d_desc, d_n, cap, w, h, scale_factor, reps=4
         assert w_n == int(f_nf[0].item()) and w_n > 100 and (w_bi == f_bi[0].cpu().numpy()).all() and (w_bd == f_bd[0].cpu().numpy()).all(), \
             "the Fuse search disagrees with the CPU checker"
         out["fuse"]["cpu_baseline"] = {"value": 1.0 / dt, "unit": "problems/s", "cores": 1, "kind": "port", "sample": "problem 0, 5 repetitions, results compared"}
+        # one Fuse search through the host-array entry point (what LocalMapping::SearchInNeighbors calls per neighbour key frame)
+        F1 = ob.FrameView(kp0.view(ob.KP_DTYPE), tonp(dF[0, :n0]), bounds, tonp(urF[0, :n0]))
+        nrep = 1 if os.environ.get("ORB_BENCH_PROFILE") else 30
+        for _ in range(min(5, nrep)):
+            one = ob.window_best_free(F1, q0["uvr"], q0["level"], tonp(fq["desc"][0]), 50, ur=q0["ur"], inv_sigma2=inv_sigma2)
+        t0 = time.perf_counter()
+        for _ in range(nrep):
+            one = ob.window_best_free(F1, q0["uvr"], q0["level"], tonp(fq["desc"][0]), 50, ur=q0["ur"], inv_sigma2=inv_sigma2)
+        out["fuse"]["single_call_ms"] = 1e3 * (time.perf_counter() - t0) / nrep
+        assert one[0] == w_n and (one[1] == w_bi).all(), "single Fuse search differs from the batch"
         # distinctive, first 2000 points
         offh, obsh = off.cpu().numpy(), obs.cpu().numpy()
         t0 = time.perf_counter()
