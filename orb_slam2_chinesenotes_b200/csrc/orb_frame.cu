@@ -11,6 +11,7 @@
 #include <stdint.h>
 
 #include "../../include/orb_b200.h"
+#include "orb_match_common.cuh"   // ORB_CHECK
 
 namespace {
 struct UndistortParams {
@@ -60,6 +61,7 @@ __global__ void k_stereo_from_rgbd(const RgbdParams P)
         const orbx_kp kp = P.kps[o];
         const int v = (int)kp.y, u = (int)kp.x;                                   // imDepth.at<float>(v, u) with float arguments (:715)
         if (u >= 0 && u < P.w && v >= 0 && v < P.h) {
+            ORB_CHECK((size_t)v * P.pitch + (size_t)u * 4 + 4 <= (size_t)(P.h - 1) * P.pitch + (size_t)P.w * 4);
             const float d = *(const float*)((const char*)P.depth + (size_t)f * P.frame_stride + (size_t)v * P.pitch + (size_t)u * 4);
             if (d > 0) {
                 dz = d;

@@ -159,6 +159,7 @@ __device__ __forceinline__ void query_top2(const MbParams& P, const WinQ& Q, con
         for (int ix = nMinCellX; ix <= nMaxCellX; ++ix) {
             const int s0 = cell_start[ix * GRID_ROWS + nMinCellY], s1 = cell_start[ix * GRID_ROWS + nMaxCellY + 1];
             for (int j = s0 + sub; j < s1; j += MB_G) {
+                ORB_CHECK(j >= 0 && j < cell_start[GRID_CELLS]);
                 const uint4 r = rec[j];
                 const int oct = (int)(r.z & 0xffu);
                 if (check_levels) {
@@ -243,7 +244,7 @@ __device__ __forceinline__ void mb_sort_frame(const MbParams& P, const orbx_kp* 
         // scatter with the start of each cell as its cursor: afterwards cell_start[c] is the END of cell c
         for (int i = tid; i < n; i += NT) {
             const int c = tmp[i];
-            if (c >= 0) keys[atomicAdd(&cell_start[c], 1)] = ((uint32_t)c << 16) | (uint32_t)i;
+            if (c >= 0) { const int pos = atomicAdd(&cell_start[c], 1); ORB_CHECK(pos >= 0 && pos < sn && c < GRID_CELLS); keys[pos] = ((uint32_t)c << 16) | (uint32_t)i; }
         }
         __syncthreads();
 #pragma unroll
@@ -775,6 +776,7 @@ __global__ void __launch_bounds__(MB_NT) k_window_best_free(const __grid_constan
     const int nvalid = cell_start[GRID_CELLS];
     for (int j = tid; j < nvalid; j += MB_NT) {
         const int idx = (int)(keys[j] & 0xffffu);
+        ORB_CHECK(idx >= 0 && idx < n && j < P.sn_max);
         const orbx_kp kp = kps[idx];
         rec[j] = make_uint4(__float_as_uint(kp.x), __float_as_uint(kp.y), (uint32_t)(kp.octave & 0xff) | ((uint32_t)idx << 8),
                             __float_as_uint(P.u_right ? P.u_right[ko + idx] : -1.0f));
@@ -820,9 +822,12 @@ __global__ void __launch_bounds__(MB_NT) k_window_best_free(const __grid_constan
             const int nMaxCellY = min(GRID_ROWS - 1, (int)ceilf((v - P.min_y + r) * P.inv_h));
             if (!(nMinCellX >= GRID_COLS || nMaxCellX < 0 || nMinCellY >= GRID_ROWS || nMaxCellY < 0))
                 for (int ix = nMinCellX; ix <= nMaxCellX; ++ix) {
+                    ORB_CHECK(ix >= 0 && ix < GRID_COLS && nMinCellY >= 0 && nMaxCellY < GRID_ROWS);
                     const int s0 = cell_start[ix * GRID_ROWS + nMinCellY], s1 = cell_start[ix * GRID_ROWS + nMaxCellY + 1];
+                    ORB_CHECK(s0 >= 0 && s0 <= s1 && s1 <= nvalid);
                     for (int j = s0 + sub; j < s1; j += MB_G) {
                         const uint4 rc = rec[j];
+                        ORB_CHECK((int)(rc.z & 0xffu) < MB_MAX_LEVELS || !P.chi2);
                         const int oct = (int)(rc.z & 0xffu);
                         if (oct < level - 1 || oct > level) continue;                                        // :1436-1437
                         const float ex = __fsub_rn(u, __uint_as_float(rc.x)), ey = __fsub_rn(v, __uint_as_float(rc.y));
@@ -848,6 +853,8 @@ __global__ void __launch_bounds__(MB_NT) k_window_best_free(const __grid_constan
         if (sub == 0 && q < nq) {
             const int dist = best == MB_NONE ? 256 : (int)(best >> 16);
             const bool ok = best != MB_NONE && dist <= P.th_accept;                                           // :1483 / :920 / :1607
+            ORB_CHECK(best == MB_NONE || (int)(best & 0xffffu) < nvalid);
+            ORB_CHECK(!ok || (int)(rec[best & 0xffffu].z >> 8) < n);
             P.assign_out[qo + q] = ok ? (int)(rec[best & 0xffffu].z >> 8) : -1;
             P.best_dist[qo + q] = dist;
             found += ok;

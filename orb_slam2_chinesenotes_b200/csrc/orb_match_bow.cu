@@ -175,6 +175,7 @@ __global__ void __launch_bounds__(BW_NT) k_bow_fixpoint(const __grid_constant__ 
                         if (TRI) {
                             if (dist > TH_LOW) continue;                                        // :1268
                             const int idx2 = feat2[j];
+                            ORB_CHECK(j >= 0 && j < t2 && idx2 >= 0 && idx2 < n2);
                             const orbx_kp k2 = P.B.kps[kb + idx2];
                             const int oct2 = k2.octave & 31;
                             if (!st1 && !(P.ur2 && P.ur2[kb + idx2] >= 0)) {                     // :1272-1279
@@ -203,7 +204,7 @@ __global__ void __launch_bounds__(BW_NT) k_bow_fixpoint(const __grid_constant__ 
                 if (sub == 0 && act) {
                     int best = -1;
                     const int bestDist1 = k1 == BW_NONE ? 256 : (int)(k1 >> 16), bestDist2 = k2 == BW_NONE ? 256 : (int)(k2 >> 16);
-                    if (TRI) { if (k1 != BW_NONE) best = (int)(0xffffu - (k1 & 0xffffu)); }                       // :1288
+                    if (TRI) { if (k1 != BW_NONE) best = (int)(0xffffu - (k1 & 0xffffu)); ORB_CHECK(best < t2); }     // :1288
                     else if ((P.strict ? bestDist1 < TH_LOW : bestDist1 <= TH_LOW) &&                             // :618 / :768
                              (float)bestDist1 < __fmul_rn(P.nnratio, (float)bestDist2)) best = (int)(k1 & 0xffffu);   // :620 / :770
                     if (!TRI && st_best[qq] != (uint32_t)(best + 1)) s_flag[par] = 1;

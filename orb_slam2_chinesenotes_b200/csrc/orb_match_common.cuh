@@ -1,5 +1,15 @@
 // orb_match_common.cuh -- pieces shared by the matcher kernels (orb_match.cu, orb_match_batch.cu, orb_match_bow.cu).
 #pragma once
+#include <cstdio>
+
+// compute-sanitizer is closed on the GPU pool this was developed on, so the kernels added last carry their own index checks,
+// compiled in by -DORB_BOUNDS_CHECK (tools/build_checked.sh builds liborb_b200_checked.so; the GPU tests run against it with
+// ORB_B200_LIB): a failed check prints its location and traps, which fails the launch and the test.
+#ifdef ORB_BOUNDS_CHECK
+#define ORB_CHECK(cond) do { if (!(cond)) { printf("ORB_CHECK failed: %s (%s:%d) block %d thread %d\n", #cond, __FILE__, __LINE__, (int)blockIdx.x, (int)threadIdx.x); __trap(); } } while (0)
+#else
+#define ORB_CHECK(cond) do { } while (0)
+#endif
 
 #ifndef HISTO_LENGTH
 #define HISTO_LENGTH 30 // src/ORBmatcher.cc:39
