@@ -247,6 +247,26 @@ def cpu_workload_frames_per_s(workload, frames_np, nfeatures, cores):
     return v, kind, f"{cores} threads, one extractor per thread" + (" (extraction only)" if workload in STEREO else ""), tot
 
 
+def opencv_dense_frames_per_s(frames_np, cores):
+    """Informative only (never the reference arm): what REAL OpenCV (cv2, SIMD / IPP dispatch) needs for the dense stages of
+    ORBextractor::operator() alone -- pyramid, FAST per level, GaussianBlur per level -- one process per core
+    (tools/cv2_dense_baseline.py, run as a separate program: no fork of this CUDA process).  The reference arm runs the reference's
+    sources over oracle/cvshim, a scalar stand-in for OpenCV, so its frames/s understate what the reference reaches with the real
+    library; this line brackets it from the other side.  None when cv2 is missing or the helper fails."""
+    import tempfile
+    try:
+        with tempfile.TemporaryDirectory() as d:
+            path = os.path.join(d, "frames.npy")
+            np.save(path, np.ascontiguousarray(frames_np))
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "cv2_dense_baseline.py"), path, str(cores), str(LEVELS), str(SCALE), str(INI_TH)],
+                               capture_output=True, text=True, timeout=180)
+        if r.returncode != 0:
+            return None
+        return json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception:
+        return None
+
+
 def workload_config(workload, batch, world, scaling):
     """The `config` object of a JSON line: what is measured, nothing that was measured (both arms print the same one)."""
     w, h, nf, _ = WORKLOADS[workload]
@@ -1004,6 +1024,12 @@ def measure_workload(workload, batch_total, scaling, rank, world, local_rank, di
         v, kind, what, _ = cpu_workload_frames_per_s(workload, sample, nf, cores)
         cpu_base = {"value": v, "unit": "frames/s", "cores": cores, "kind": kind,
                     "sample": f"first {ns} frames of the step's batch, {what}"}
+        ocv = opencv_dense_frames_per_s(sample, cores)
+        if ocv is not None:
+            cpu_base["opencv_dense_stages_only"] = {"value": ocv["frames_per_s"], "unit": "frames/s", "cores": cores,
+                                                    "ms_per_frame_per_core": ocv["ms_per_frame_per_core"],
+                                                    "what": "cv2 (real OpenCV, SIMD) pyramid + FAST per level + GaussianBlur only, one thread per core, same "
+                                                            "frames; informative: brackets the reference arm, which runs over a scalar OpenCV stand-in"}
     chunk_dev = chunk or 512                      # device-resident default of orb_capi.cu (the timed `value` path)
     chunks = (batch + chunk_dev - 1) // chunk_dev
     stats = {"keypoints_per_frame": total_kp / frames_all}
