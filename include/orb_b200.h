@@ -349,6 +349,23 @@ typedef struct {
 int orbm_window_best_free_batch(const orbm_frames* F, const orbm_free_windows* Q, const float* inv_sigma2, int nlevels,
                                 int th_accept, int* best_idx, int* best_dist, int* nfound, void* cuda_stream);
 
+/* The per-point prologue of Fuse / SearchBySim3 on the device, so that projection -> orbm_window_best_free_batch never leaves
+ * the GPU: for every (key frame, map point) the projection and gates of ORBmatcher::Fuse (src/ORBmatcher.cc:1388-1426; the Sim3
+ * overload :1546-1584 is the same once the caller has decomposed Scw into R, t, Ow as :1524-1529 do) or, with sim3 != 0, of one
+ * direction of SearchBySim3 (:886-909 / :937-960), MapPoint::PredictScale(dist, KeyFrame*) (src/MapPoint.cc:442-457) and the
+ * search radius th * scale[level].  pose [nprob][24] (device): Fuse = Rcw (9, row-major), tcw (3), Ow (3), 9 unused; SearchBySim3 =
+ * R_a (9), t_a (3) of the key frame that owns the points, then sR (9), tt (3) of the similarity into the other one.  K = fx, fy,
+ * cx, cy and scale = mvScaleFactors (host); min_x..max_y = the TARGET key frame's (int) image bounds; scale_factor =
+ * mfScaleFactor.  Points as in orbm_project_points_batch (max_distance / min_distance = the RAW mfMaxDistance / mfMinDistance),
+ * normal may be NULL with sim3; skip (or NULL) [.][nq_stride]: 1 = the reference's loop skips the point before projecting it
+ * (NULL / isBad() / IsInKeyFrame / already found / already matched).  Outputs [nprob][nq_stride] in the layout of
+ * orbm_free_windows: uvr, level, ur (or NULL; u - bf * invz, :1402), valid.  Only enqueues. */
+int orbm_fuse_project_batch(int nprob, int sim3, const float* pose, const float* K, float bf, float min_x, float max_x, float min_y,
+                            float max_y, float scale_factor, const float* scale, int nlevels, float th,
+                            const int* nq, int nq_stride, int points_shared, const float* xyz, const float* normal,
+                            const float* max_distance, const float* min_distance, const uint8_t* skip,
+                            float* uvr, int* level, float* ur, uint8_t* valid, void* cuda_stream);
+
 /* ORBmatcher::SearchForInitialization, src/ORBmatcher.cc:1055-1180, for nprob (F1, F2) pairs.  prev_matched
  * [nprob][F1.kp_stride][2] = vbPrevMatched (window centres; updated in place like the reference does), matches12
  * [nprob][F1.kp_stride] = vnMatches12, nmatches [nprob] the return value.  Frames with at most 8192 keypoints.

@@ -325,3 +325,47 @@ int orbo_search_by_sim3(int n1, const orbo_kp* kps1, const uint8_t* desc1, const
     free(m2); free(m1); free(am2); free(am1);
     return nFound;
 }
+
+/* The per-point prologue alone (projection, gates, MapPoint::PredictScale(dist, KeyFrame*) src/MapPoint.cc:442-457, radius), i.e. the
+ * contract of the device's orbm_fuse_project_batch for one problem.  sim3 = 0: Fuse (src/ORBmatcher.cc:1388-1426, :1546-1584), pose =
+ * R(9) t(3) Ow(3); sim3 = 1: one direction of SearchBySim3 (:886-909 / :937-960), pose = R_a(9) t_a(3) sR(9) tt(3).  max_d / min_d = the
+ * RAW mfMaxDistance / mfMinDistance (the invariance factors 1.2 / 0.8 are applied here, src/MapPoint.cc:424-435).  Consistent with
+ * fuse_body / sim3_direction above (tests/test_fuse_oracle.py feeds this function's levels to them as the preset PredictScale and
+ * compares the queries), which are pinned against the reference. */
+void orbo_fuse_project(int sim3, const float* pose, const float* K, float bf, float minX, float maxX, float minY, float maxY,
+                       float scale_factor, const float* scale, int nlevels, float th,
+                       int n, const float* xyz, const float* normal, const float* max_d, const float* min_d, const uint8_t* skip,
+                       float* uvr, int* level, float* ur, uint8_t* valid)
+{
+    const float fx = K[0], fy = K[1], cx = K[2], cy = K[3];
+    const float logs = orbo_log_scale_factor(scale_factor);
+    for (int i = 0; i < n; ++i) {
+        uvr[3 * i] = uvr[3 * i + 1] = uvr[3 * i + 2] = 0.f; level[i] = 0; valid[i] = 0;
+        if (ur) ur[i] = 0.f;
+        if (skip && skip[i]) continue;
+        const float* x = xyz + 3 * i;
+        float pc[3];
+        project3(pose, pose + 9, x, pc);
+        if (sim3) { float pb[3]; project3(pose + 12, pose + 21, pc, pb); pc[0] = pb[0]; pc[1] = pb[1]; pc[2] = pb[2]; }
+        if (pc[2] < 0.0f) continue;
+        const float invz = 1 / pc[2];
+        const float xn = pc[0] * invz, yn = pc[1] * invz;
+        const float u = fx * xn + cx, v = fy * yn + cy;
+        if (!(u >= minX && u < maxX && v >= minY && v < maxY)) continue;
+        const float maxD = 1.2f * max_d[i], minD = 0.8f * min_d[i];
+        float d[3];
+        double acc = 0;
+        for (int r = 0; r < 3; ++r) { d[r] = sim3 ? pc[r] : x[r] - pose[12 + r]; acc += (double)d[r] * (double)d[r]; }
+        const float dist3D = (float)sqrt(acc);
+        if (dist3D < minD || dist3D > maxD) continue;
+        if (!sim3) {
+            double dn = 0;
+            for (int r = 0; r < 3; ++r) dn += (double)d[r] * (double)normal[3 * i + r];
+            if (dn < 0.5 * dist3D) continue;
+        }
+        const int lvl = orbo_predict_scale(max_d[i], dist3D, logs, nlevels);
+        uvr[3 * i] = u; uvr[3 * i + 1] = v; uvr[3 * i + 2] = th * scale[lvl];
+        level[i] = lvl; valid[i] = 1;
+        if (ur) ur[i] = u - bf * invz;
+    }
+}

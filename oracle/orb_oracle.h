@@ -154,6 +154,11 @@ int orbo_search_by_sim3(int n1, const orbo_kp* kps1, const uint8_t* desc1, const
                         int* matches12, float th,
                         float* uvr1_out, int* level1_out, uint8_t* valid1_out, float* uvr2_out, int* level2_out, uint8_t* valid2_out);
 
+void orbo_fuse_project(int sim3, const float* pose, const float* K, float bf, float minX, float maxX, float minY, float maxY,
+                       float scale_factor, const float* scale, int nlevels, float th,
+                       int n, const float* xyz, const float* normal, const float* max_d, const float* min_d, const uint8_t* skip,
+                       float* uvr, int* level, float* ur, uint8_t* valid);
+
 /* Frame::ComputeStereoMatches, src/Frame.cc:513-699 */
 /* ORBmatcher::SearchByBoW, src/ORBmatcher.cc:552-697 (strict = 0, valid2 = NULL) and :700-832 (strict = 1). */
 int orbo_search_by_bow(int n1, const orbo_kp* kps1, const uint8_t* desc1, const uint8_t* valid1,

@@ -133,6 +133,7 @@ def lib():
         L.orbm_search_for_initialization.argtypes = [fp, fp, vp, vp, i32, f32, i32, pi, i32]
         L.orbm_window_search_best.argtypes = [fp, i32] + [vp] * 11 + [i32, i32, pi, i32]
         L.orbm_window_best_free.argtypes = [fp, i32] + [vp] * 6 + [i32, i32, vp, vp, pi, i32]
+        L.orbm_fuse_project_batch.argtypes = [i32, i32, vp, vp, f32, f32, f32, f32, f32, f32, vp, i32, f32, vp, i32, i32] + [vp] * 9 + [vp]
         L.orbx_undistort_keypoints_batch.argtypes = [vp, vp, vp, i32, i32, vp, vp, i32, vp]
         L.orbx_stereo_from_rgbd_batch.argtypes = [vp, vp, vp, i32, i32, vp, C.c_size_t, C.c_size_t, i32, i32, f32, vp, vp, vp]
         L.orbm_window_best_free_batch.argtypes = [C.POINTER(OrbmFrames), C.POINTER(OrbmFreeWindows), vp, i32, i32, vp, vp, vp, vp]
@@ -621,6 +622,20 @@ def stereo_from_rgbd_batch(kps, kps_un, n, depth, bf, u_right, depth_out, stream
                                            depth.stride(0) * es, w, h, float(np.float32(bf)), _ptr(u_right), _ptr(depth_out), stream)
     if rc:
         raise OrbError(rc, "orbx_stereo_from_rgbd_batch failed")
+
+
+def fuse_project_batch(pose, K, bf, bounds, scale_factor, scale, th, nq, nq_stride, pts, out, sim3=False, points_shared=False, stream=None):
+    """orbm_fuse_project_batch: the projection / gates / PredictScale / radius prologue of ORBmatcher::Fuse (or, sim3, one direction
+    of SearchBySim3) for every (key frame, map point).  pose [P,24], nq [P] and pts = dict(xyz, normal (None with sim3), max_d,
+    min_d, skip (or absent)) are CUDA tensors; out = dict(uvr, level, ur (or absent), valid) CUDA tensors [P,nq_stride(,3)] -- the
+    arrays window_best_free_batch takes.  Only enqueues."""
+    K, scale = np.ascontiguousarray(K, np.float32), np.ascontiguousarray(scale, np.float32)
+    rc = lib().orbm_fuse_project_batch(int(pose.shape[0]), int(sim3), _ptr(pose), K.ctypes.data, float(np.float32(bf)), *(float(b) for b in bounds),
+                                       float(np.float32(scale_factor)), scale.ctypes.data, len(scale), float(np.float32(th)), _ptr(nq), nq_stride,
+                                       int(points_shared), _ptr(pts["xyz"]), _ptr(pts.get("normal")), _ptr(pts["max_d"]), _ptr(pts["min_d"]),
+                                       _ptr(pts.get("skip")), _ptr(out["uvr"]), _ptr(out["level"]), _ptr(out.get("ur")), _ptr(out["valid"]), stream)
+    if rc:
+        raise OrbError(rc, "orbm_fuse_project_batch failed")
 
 
 def frames_batch(kps, desc, n, bounds, u_right=None, max_n=0):

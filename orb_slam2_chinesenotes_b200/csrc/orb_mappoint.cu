@@ -284,6 +284,98 @@ __global__ void __launch_bounds__(DD_NT) k_distinctive(const uint4* __restrict__
 }
 
 // ================================================================================ host side
+// ------------------------------------------------------------------------------------------ projection for Fuse / SearchBySim3
+// The per-point prologue of ORBmatcher::Fuse (src/ORBmatcher.cc:1388-1426, :1546-1584) and of one direction of SearchBySim3
+// (:886-909 / :937-960) for every (key frame, map point): what orbm_window_best_free_batch searches, written in its layout, so
+// projection -> search stays on the GPU.  Differences from Frame::isInFrustum above, all kept: x = Pc.x * invz first, then
+// u = fx * x + cx (:1395-1399); KeyFrame::IsInImage with the key frame's int bounds (u >= min && u < max); the viewing-angle
+// test in double, PO.dot(Pn) < 0.5 * dist3D (:1420), and no such test in SearchBySim3, whose distance is the norm of the point in
+// the target camera (:899); MapPoint::PredictScale(dist, KeyFrame*) (src/MapPoint.cc:442-457) is the same arithmetic as the
+// Frame overload.  pose [nprob][24]: Fuse R(9) t(3) Ow(3); SearchBySim3 R_a(9) t_a(3) sR(9) tt(3) (p = sR * (R_a * x + t_a) + tt).
+struct FuseProjParams {
+    const float* pose; int sim3;
+    float fx, fy, cx, cy, bf, min_x, max_x, min_y, max_y, log_scale, th;
+    int nlevels;
+    float scale[32];
+    const int* nq; int nq_stride; size_t pt_stride;
+    const float* xyz; const float* normal; const float* max_d; const float* min_d; const uint8_t* skip;
+    float* uvr; int* level; float* ur; uint8_t* valid;
+};
+
+__global__ void __launch_bounds__(256) k_fuse_project(const FuseProjParams P)
+{
+    __shared__ float T[24];
+    const int prob = blockIdx.y;
+    if (threadIdx.x < 24) T[threadIdx.x] = P.pose[(size_t)prob * 24 + threadIdx.x];
+    __syncthreads();
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= P.nq_stride) return;
+    const size_t pi = (size_t)prob * P.pt_stride + q, oi = (size_t)prob * P.nq_stride + q;
+    bool ok = q < P.nq[prob] && !(P.skip && P.skip[pi]);
+    float u = 0.f, v = 0.f, r = 0.f, urv = 0.f;
+    int lvl = 0;
+    if (ok) {
+        const float X = P.xyz[3 * pi], Y = P.xyz[3 * pi + 1], Z = P.xyz[3 * pi + 2];
+        float Pc[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            float s = __fmul_rn(T[3 * k], X);
+            s = __fadd_rn(s, __fmul_rn(T[3 * k + 1], Y));
+            s = __fadd_rn(s, __fmul_rn(T[3 * k + 2], Z));
+            Pc[k] = __fadd_rn(s, T[9 + k]);
+        }
+        if (P.sim3) {                                                       // through the similarity into the other camera (:888 / :939)
+            float Pb[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                float s = __fmul_rn(T[12 + 3 * k], Pc[0]);
+                s = __fadd_rn(s, __fmul_rn(T[12 + 3 * k + 1], Pc[1]));
+                s = __fadd_rn(s, __fmul_rn(T[12 + 3 * k + 2], Pc[2]));
+                Pb[k] = __fadd_rn(s, T[21 + k]);
+            }
+            Pc[0] = Pb[0]; Pc[1] = Pb[1]; Pc[2] = Pb[2];
+        }
+        ok = !(Pc[2] < 0.0f);
+        float invz = 0.f, dist = 0.f;
+        if (ok) {
+            invz = __fdiv_rn(1.0f, Pc[2]);                                  // 1/z and (float)(1.0/z) are the same float
+            u = __fadd_rn(__fmul_rn(P.fx, __fmul_rn(Pc[0], invz)), P.cx);
+            v = __fadd_rn(__fmul_rn(P.fy, __fmul_rn(Pc[1], invz)), P.cy);
+            ok = u >= P.min_x && u < P.max_x && v >= P.min_y && v < P.max_y;                  // KeyFrame::IsInImage
+        }
+        if (ok) {
+            const float maxD = __fmul_rn(1.2f, P.max_d[pi]), minD = __fmul_rn(0.8f, P.min_d[pi]);   // src/MapPoint.cc:424-435
+            float d0, d1, d2;
+            if (P.sim3) { d0 = Pc[0]; d1 = Pc[1]; d2 = Pc[2]; }
+            else { d0 = __fsub_rn(X, T[12]); d1 = __fsub_rn(Y, T[13]); d2 = __fsub_rn(Z, T[14]); }   // PO = p3Dw - Ow
+            double s2 = __dmul_rn((double)d0, (double)d0);
+            s2 = __dadd_rn(s2, __dmul_rn((double)d1, (double)d1));
+            s2 = __dadd_rn(s2, __dmul_rn((double)d2, (double)d2));
+            dist = (float)__dsqrt_rn(s2);
+            ok = !(dist < minD || dist > maxD);
+            if (ok && !P.sim3) {
+                double dot = __dmul_rn((double)d0, (double)P.normal[3 * pi]);
+                dot = __dadd_rn(dot, __dmul_rn((double)d1, (double)P.normal[3 * pi + 1]));
+                dot = __dadd_rn(dot, __dmul_rn((double)d2, (double)P.normal[3 * pi + 2]));
+                ok = !(dot < __dmul_rn(0.5, (double)dist));                  // :1420
+            }
+        }
+        if (ok) {
+            const float ratio = __fdiv_rn(P.max_d[pi], dist);               // PredictScale, src/MapPoint.cc:442-457
+            int nScale = (int)ceilf(__fdiv_rn(glibc_logf(ratio), P.log_scale));
+            if (nScale < 0) nScale = 0;
+            else if (nScale >= P.nlevels) nScale = P.nlevels - 1;
+            lvl = nScale;
+            r = __fmul_rn(P.th, P.scale[lvl & 31]);
+            urv = __fsub_rn(u, __fmul_rn(P.bf, invz));
+        } else { u = 0.f; v = 0.f; }
+    }
+    P.uvr[3 * oi] = u; P.uvr[3 * oi + 1] = v; P.uvr[3 * oi + 2] = r;
+    P.level[oi] = lvl;
+    if (P.ur) P.ur[oi] = urv;
+    P.valid[oi] = ok ? 1 : 0;
+}
+
 namespace {
 int dev_of(const void* p)
 {
@@ -325,6 +417,34 @@ int orbm_project_points_batch(int nprob, const float* Tcw, const float* K, float
     P.in_view = in_view; P.proj = proj_xyxr; P.level = level; P.view_cos = view_cos; P.n_in_view = n_in_view;
     if (n_in_view && cudaMemsetAsync(n_in_view, 0, sizeof(int) * (size_t)nprob, st) != cudaSuccess) { cudaGetLastError(); return ORBX_E_CUDA; }
     k_project_points<<<dim3((nq_stride + 255) / 256, nprob), 256, 0, st>>>(P);
+    if (cudaGetLastError() != cudaSuccess) return ORBX_E_CUDA;
+    return ORBX_OK;
+}
+
+int orbm_fuse_project_batch(int nprob, int sim3, const float* pose, const float* K, float bf, float min_x, float max_x, float min_y,
+                            float max_y, float scale_factor, const float* scale, int nlevels, float th,
+                            const int* nq, int nq_stride, int points_shared, const float* xyz, const float* normal,
+                            const float* max_distance, const float* min_distance, const uint8_t* skip,
+                            float* uvr, int* level, float* ur, uint8_t* valid, void* cuda_stream)
+{
+    if (nprob <= 0 || !pose || !K || !scale || !nq || nq_stride <= 0 || nlevels <= 0 || nlevels > 32 || !xyz || (!sim3 && !normal) ||
+        !max_distance || !min_distance || !uvr || !level || !valid)
+        return ORBX_E_ARG;
+    const int dev = dev_of(xyz);
+    if (dev < 0 || dev_of(pose) != dev || dev_of(nq) != dev || dev_of(uvr) != dev || dev_of(level) != dev || dev_of(valid) != dev) return ORBX_E_ARG;
+    DevScope g;
+    if (!g.enter(dev)) { cudaGetLastError(); return ORBX_E_CUDA; }
+    FuseProjParams P = {};
+    P.pose = pose; P.sim3 = sim3 ? 1 : 0;
+    P.fx = K[0]; P.fy = K[1]; P.cx = K[2]; P.cy = K[3]; P.bf = bf;
+    P.min_x = min_x; P.max_x = max_x; P.min_y = min_y; P.max_y = max_y;
+    P.log_scale = logf(scale_factor);                       // mfLogScaleFactor, src/KeyFrame.cc:38 (copied from the Frame's host logf)
+    P.th = th; P.nlevels = nlevels;
+    for (int i = 0; i < 32; ++i) P.scale[i] = i < nlevels ? scale[i] : 0.f;
+    P.nq = nq; P.nq_stride = nq_stride; P.pt_stride = points_shared ? 0 : (size_t)nq_stride;
+    P.xyz = xyz; P.normal = normal; P.max_d = max_distance; P.min_d = min_distance; P.skip = skip;
+    P.uvr = uvr; P.level = level; P.ur = ur; P.valid = valid;
+    k_fuse_project<<<dim3((nq_stride + 255) / 256, nprob), 256, 0, (cudaStream_t)cuda_stream>>>(P);
     if (cudaGetLastError() != cudaSuccess) return ORBX_E_CUDA;
     return ORBX_OK;
 }

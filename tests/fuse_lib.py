@@ -264,3 +264,76 @@ def run_search_by_sim3(impl, k1, d1, k2, d2, s, scale, bounds, K, th):
     f.argtypes = base + tail + [vp] * 6
     nf = f(*head, *mid, p(q1["uvr"]), p(q1["level"]), p(q1["valid"]), p(q2["uvr"]), p(q2["level"]), p(q2["valid"]))
     return nf, m12, (q1, q2)
+
+
+# ------------------------------------------------------------------------------------------------ the projection prologue alone
+def fuse_project_oracle(sim3, pose24, K, bf, bounds, scale_factor, scale, th, xyz, normal, max_raw, min_raw, skip):
+    """orbo_fuse_project: (uvr, level, ur, valid) per point."""
+    n = len(max_raw)
+    uvr, lvl, ur, valid = np.zeros((n, 3), np.float32), np.zeros(n, np.int32), np.zeros(n, np.float32), np.zeros(n, np.uint8)
+    f = oracle().orbo_fuse_project
+    f.argtypes, f.restype = [ci, vp, vp] + [cf] * 6 + [vp, ci, cf, ci] + [vp] * 9, None
+    Kf = np.asarray(K, np.float32)
+    b = (float(int(bounds[0])), float(int(bounds[1])), float(int(bounds[2])), float(int(bounds[3])))
+    f(int(sim3), p(pose24), p(Kf), bf, *b, scale_factor, p(scale), len(scale), th, n, p(xyz), p(normal), p(max_raw), p(min_raw), p(skip),
+      p(uvr), p(lvl), p(ur), p(valid))
+    return dict(uvr=uvr, level=lvl, ur=ur, valid=valid)
+
+
+def decompose_sim3(Scw):
+    """R, t, Ow of src/ORBmatcher.cc:1524-1529 in the shim's arithmetic."""
+    d = np.float64(0)
+    for c in range(3):
+        d += np.float64(Scw[0, c]) * np.float64(Scw[0, c])
+    scw = np.float32(np.sqrt(d))
+    inv = np.float64(1.0) / np.float64(scw)
+    R = (Scw[:3, :3].astype(np.float64) * inv).astype(np.float32)
+    t = (Scw[:3, 3].astype(np.float64) * inv).astype(np.float32)
+    return np.ascontiguousarray(R), t, _camera_centre(R, t)
+
+
+def raw_distances(s, rng, lo=1.0, hi=3.5):
+    """mfMaxDistance / mfMinDistance for the points of a scene (the scenes above carry the INVARIANCE bounds the mocks return):
+    raw values around the true distances, and the scene's bounds replaced by 1.2 * max / 0.8 * min as MapPoint computes them."""
+    n = len(s["max_dist"])
+    max_raw = (s["max_dist"] / np.float32(1.6) * (lo + (hi - lo) * rng.random(n))).astype(np.float32)
+    min_raw = (max_raw / np.float32(1.2 ** 7) * np.where(rng.random(n) < 0.05, 8.0, 1.0)).astype(np.float32)
+    s2 = dict(s)
+    s2["max_dist"] = (np.float32(1.2) * max_raw).astype(np.float32)
+    s2["min_dist"] = (np.float32(0.8) * min_raw).astype(np.float32)
+    return s2, max_raw, min_raw
+
+
+def fuse_pose24(s, sim3):
+    R, t, Ow = decompose_sim3(s["Scw"]) if sim3 else (s["R"], s["t"], s["Ow"])
+    return np.ascontiguousarray(np.concatenate([R.ravel(), t, Ow, np.zeros(9, np.float32)]).astype(np.float32))
+
+
+def fuse_list_arrays(s, max_raw, min_raw, sim3):
+    """Per LIST ENTRY arrays for the projection: the entry's point (a NULL entry = skipped dummy) and the reference's skip test at
+    the start of the call (NULL, isBad(), IsInKeyFrame(pKF) / member of the already-found set)."""
+    lst = s["list"]
+    g = np.maximum(lst, 0)
+    found0 = np.zeros(s["npts"], bool)
+    found0[s["kf_mp"][s["kf_mp"] >= 0]] = True
+    skip = (lst < 0) | (s["bad"][g] != 0) | (found0[g] if sim3 else (s["kf_idx"][g] >= 0))
+    c = np.ascontiguousarray
+    return dict(xyz=c(s["xyz"][g]), normal=c(s["normal"][g]), max_d=c(max_raw[g]), min_d=c(min_raw[g]), skip=c(skip.astype(np.uint8)),
+                desc=c(s["mp_desc"][g]))
+
+
+def sim3_poses(s):
+    """pose24 of the two directions of SearchBySim3 in the reference's arithmetic (:854-856)."""
+    s12, R12, t12 = np.float32(s["s12"]), s["R12"], s["t12"]
+    inv_s = np.float64(1.0) / np.float64(s12)
+    sR12 = (R12.astype(np.float64) * np.float64(s12)).astype(np.float32)
+    sR21 = (R12.T.astype(np.float64) * inv_s).astype(np.float32)
+    ns = (sR21.astype(np.float64) * -1.0).astype(np.float32)
+    t21 = np.zeros(3, np.float32)
+    for r in range(3):
+        a = np.float32(ns[r, 0] * t12[0])
+        a = np.float32(a + np.float32(ns[r, 1] * t12[1]))
+        a = np.float32(a + np.float32(ns[r, 2] * t12[2]))
+        t21[r] = a
+    cat = lambda *a: np.ascontiguousarray(np.concatenate([np.asarray(x, np.float32).ravel() for x in a]))
+    return cat(s["R1"], s["t1"], sR21, t21), cat(s["R2"], s["t2"], sR12, t12)

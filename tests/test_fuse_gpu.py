@@ -166,3 +166,68 @@ def test_degenerate_inputs(scene):
     n, bi, bd = ob.window_best_free(F, q["uvr"], q["level"], qd, -1, valid=q["valid"])   # nothing passes the threshold; distances still reported
     o_n, o_bi, o_bd = window_best_free_oracle(scene["kps"], scene["desc"], None, BOUNDS, q, qd, None, -1)
     assert n == 0 and (bi == -1).all() and (bd == o_bd).all() and (bd < 256).any()
+
+
+@pytest.mark.parametrize("sim3", [False, True])
+def test_projection_then_search_stays_on_the_device(scene, sim3):
+    """orbm_fuse_project_batch -> orbm_window_best_free_batch for several (key frame, point set) problems without touching the host
+    in between: the projected queries equal the CPU restatement's bit for bit (real PredictScale arithmetic, both the Fuse gates
+    and one direction of SearchBySim3), and so does the search on them."""
+    import torch
+    from fuse_lib import (fuse_list_arrays, fuse_pose24, fuse_project_oracle, fuse_scene, raw_distances, sim3_pair_scene, sim3_poses)
+    kps, desc, scale = scene["kps"], scene["desc"], scene["scale"]
+    th = 7.5 if sim3 else 3.0
+    probs = []
+    for seed in (91, 92, 93):
+        if sim3:
+            s = sim3_pair_scene(kps, desc, scene["k2"], scene["d2"], W, H, seed, K)
+            rng = np.random.default_rng(seed)
+            max_raw = (3.0 + 60 * rng.random(s["npts"])).astype(np.float32)
+            min_raw = (max_raw / np.float32(1.2 ** 7)).astype(np.float32)
+            pose = sim3_poses(s)[0]                               # KF1's points searched in KF2
+            g = np.maximum(s["mp1"], 0)
+            A = dict(xyz=np.ascontiguousarray(s["xyz"][g]), normal=None, max_d=np.ascontiguousarray(max_raw[g]), min_d=np.ascontiguousarray(min_raw[g]),
+                     skip=((s["mp1"] < 0) | (s["m12"] >= 0) | (s["bad"][g] != 0)).astype(np.uint8), desc=np.ascontiguousarray(s["mp_desc"][g]))
+            probs.append(dict(pose=pose, A=A, tk=scene["k2"], td=scene["d2"], ur=None))
+        else:
+            s = fuse_scene(kps, desc, W, H, seed, K, BF, False)
+            s, max_raw, min_raw = raw_distances(s, np.random.default_rng(seed))
+            probs.append(dict(pose=fuse_pose24(s, False), A=fuse_list_arrays(s, max_raw, min_raw, False), tk=kps, td=desc, ur=s["u_right"]))
+    P = len(probs)
+    nqs = max(len(pr["A"]["max_d"]) for pr in probs) + 5
+    cap = max(len(pr["tk"]) for pr in probs) + 3
+    pts = dict(xyz=_dev(_pad([pr["A"]["xyz"] for pr in probs], nqs)), max_d=_dev(_pad([pr["A"]["max_d"] for pr in probs], nqs, 1)),
+               min_d=_dev(_pad([pr["A"]["min_d"] for pr in probs], nqs, 1)), skip=_dev(_pad([pr["A"]["skip"] for pr in probs], nqs, 1)))
+    if not sim3:
+        pts["normal"] = _dev(_pad([pr["A"]["normal"] for pr in probs], nqs))
+    d_pose = _dev(np.stack([pr["pose"] for pr in probs]))
+    d_nq = _dev(np.int32([len(pr["A"]["max_d"]) for pr in probs]))
+    out = dict(uvr=torch.full((P, nqs, 3), 7.0, device="cuda"), level=torch.full((P, nqs), 7, dtype=torch.int32, device="cuda"),
+               ur=torch.full((P, nqs), 7.0, device="cuda"), valid=torch.full((P, nqs), 7, dtype=torch.uint8, device="cuda"))
+    bf = 0.0 if sim3 else BF
+    ob.fuse_project_batch(d_pose, K, bf, BOUNDS, 1.2, scale, th, d_nq, nqs, pts, out, sim3=sim3)
+    tk = np.zeros((P, cap), KP_DTYPE)
+    for i, pr in enumerate(probs):
+        tk[i, :len(pr["tk"])] = pr["tk"]
+    d_k, d_d = _dev(tk), _dev(_pad([pr["td"] for pr in probs], cap))
+    d_n = _dev(np.int32([len(pr["tk"]) for pr in probs]))
+    d_ur = None if sim3 else _dev(_pad([pr["ur"] for pr in probs], cap, -1))
+    F = ob.frames_batch(d_k, d_d, d_n, BOUNDS, d_ur)
+    q = dict(uvr=out["uvr"], level=out["level"], ur=out["ur"], valid=out["valid"], desc=_dev(_pad([pr["A"]["desc"] for pr in probs], nqs)))
+    bi = torch.zeros((P, nqs), dtype=torch.int32, device="cuda")
+    bd = torch.zeros((P, nqs), dtype=torch.int32, device="cuda")
+    nf = torch.zeros(P, dtype=torch.int32, device="cuda")
+    ob.window_best_free_batch(F, q, d_nq, nqs, bi, bd, nf, 100 if sim3 else 50, inv_sigma2=None if sim3 else scene["inv_sigma2"])
+    torch.cuda.synchronize()
+    o = {k: v.cpu().numpy() for k, v in out.items()}
+    bi, bd, nf = bi.cpu().numpy(), bd.cpu().numpy(), nf.cpu().numpy()
+    for i, pr in enumerate(probs):
+        A, n = pr["A"], len(pr["A"]["max_d"])
+        w = fuse_project_oracle(sim3, pr["pose"], K, bf, BOUNDS, 1.2, scale, th, A["xyz"], A["normal"], A["max_d"], A["min_d"], A["skip"])
+        m = w["valid"].astype(bool)
+        assert (o["valid"][i, :n] == w["valid"]).all() and m.sum() > 500
+        assert (o["uvr"][i, :n][m].view(np.uint32) == w["uvr"][m].view(np.uint32)).all() and (o["level"][i, :n][m] == w["level"][m]).all()
+        assert (o["ur"][i, :n][m].view(np.uint32) == w["ur"][m].view(np.uint32)).all()
+        assert (o["valid"][i, n:] == 0).all()                       # entries behind a problem's points are written as invalid
+        want = window_best_free_oracle(pr["tk"], pr["td"], pr["ur"], BOUNDS, w, A["desc"], None if sim3 else scene["inv_sigma2"], 100 if sim3 else 50)
+        assert nf[i] == want[0] and want[0] > 100 and (bi[i, :n] == want[1]).all() and (bd[i, :n] == want[2]).all()

@@ -6,7 +6,8 @@ import os
 import numpy as np
 import pytest
 
-from fuse_lib import (fuse_scene, replay_fuse, run_fuse, run_search_by_sim3, same_state, sim3_pair_scene, window_best_free_oracle)
+from fuse_lib import (fuse_list_arrays, fuse_pose24, fuse_project_oracle, fuse_scene, raw_distances, replay_fuse, run_fuse, run_search_by_sim3,
+                      same_state, sim3_pair_scene, sim3_poses, window_best_free_oracle)
 from matcher_lib import extract_frame, perturbed_frame
 from oracle_lib import ref
 
@@ -82,3 +83,54 @@ def test_search_then_replay_equals_the_sequential_loop(scene, th, seed, sim3, st
     nf2, st2 = replay_fuse(s, q, bi, ur, sim3)
     assert nf2 == nf and same_state(st, st2)
     assert ((bd <= 50) == (bi >= 0)).all()
+
+
+def _same_queries(a, b, with_ur):
+    m = a["valid"].astype(bool)
+    ok = (a["valid"] == b["valid"]).all() and (a["uvr"][m].view(np.uint32) == b["uvr"][m].view(np.uint32)).all() and (a["level"][m] == b["level"][m]).all()
+    return ok and (not with_ur or (a["ur"][m].view(np.uint32) == b["ur"][m].view(np.uint32)).all())
+
+
+@pytest.mark.parametrize("th,seed,sim3,stereo", FUSE_CASES)
+def test_projection_prologue_is_the_loops_prologue(scene, th, seed, sim3, stereo):
+    """orbo_fuse_project (the contract of the device's orbm_fuse_project_batch, with the real PredictScale arithmetic) against the
+    queries the Fuse restatement -- pinned against the reference -- emits when its preset PredictScale returns the same levels."""
+    s = fuse_scene(scene["kps"], scene["desc"], W, H, seed, K, BF, sim3)
+    s, max_raw, min_raw = raw_distances(s, np.random.default_rng(seed))
+    L = fuse_list_arrays(s, max_raw, min_raw, sim3)
+    got = fuse_project_oracle(False, fuse_pose24(s, sim3), K, 0.0 if sim3 else BF, BOUNDS, 1.2, scene["scale"], th, L["xyz"], L["normal"], L["max_d"],
+                              L["min_d"], L["skip"])
+    lvl = s["level"].copy()
+    lvl[s["list"][got["valid"] == 1]] = got["level"][got["valid"] == 1]             # the preset PredictScale of the restatement
+    s["level"] = lvl
+    _, _, q = run_fuse("oracle", scene["kps"], scene["desc"], s, scene["scale"], scene["inv_sigma2"], BOUNDS, K, BF, th, sim3, stereo)
+    assert _same_queries(q, got, not sim3) and got["valid"].sum() > 500 and len(np.unique(got["level"][got["valid"] == 1])) >= 6
+
+
+@pytest.mark.parametrize("th,seed", SIM3_CASES)
+def test_sim3_projection_prologue(scene, th, seed):
+    k1, d1, k2, d2 = scene["kps"], scene["desc"], scene["k2"], scene["d2"]
+    s = sim3_pair_scene(k1, d1, k2, d2, W, H, seed, K)
+    rng = np.random.default_rng(seed)
+    max_raw = (3.0 + 60 * rng.random(s["npts"])).astype(np.float32)
+    min_raw = (max_raw / np.float32(1.2 ** 7)).astype(np.float32)
+    s["max_dist"], s["min_dist"] = (np.float32(1.2) * max_raw).astype(np.float32), (np.float32(0.8) * min_raw).astype(np.float32)
+    p1, p2 = sim3_poses(s)
+    am1 = s["m12"] >= 0
+    am2 = np.zeros(len(k2), bool)
+    idx2 = s["idx_in_kf2"][s["m12"][am1]]
+    am2[idx2[(idx2 >= 0) & (idx2 < len(k2))]] = True
+    outs = []
+    for pose, mp, am in ((p1, s["mp1"], am1), (p2, s["mp2"], am2)):
+        g = np.maximum(mp, 0)
+        skip = ((mp < 0) | am | (s["bad"][g] != 0)).astype(np.uint8)
+        outs.append(fuse_project_oracle(True, pose, K, 0.0, BOUNDS, 1.2, scene["scale"], th, np.ascontiguousarray(s["xyz"][g]), None,
+                                        np.ascontiguousarray(max_raw[g]), np.ascontiguousarray(min_raw[g]), skip))
+    lvl = s["level"].copy()
+    for o, mp in zip(outs, (s["mp1"], s["mp2"])):
+        v = o["valid"] == 1
+        lvl[mp[v]] = o["level"][v]
+    s["level"] = lvl
+    _, _, (q1, q2) = run_search_by_sim3("oracle", k1, d1, k2, d2, s, scene["scale"], BOUNDS, K, th)
+    assert _same_queries(q1, outs[0], False) and _same_queries(q2, outs[1], False)
+    assert outs[0]["valid"].sum() > 500 and outs[1]["valid"].sum() > 500
