@@ -26,7 +26,10 @@
 namespace {
 
 #ifndef ORB_NCOMP
-#define ORB_NCOMP 3      // compute streams the chunks of the piped path alternate between (<= ORB_NSLOT)
+#define ORB_NCOMP 2      // compute streams the chunks of the piped path alternate between (<= ORB_NSLOT).  Re-measured with the final
+                         // kernels (1024 KITTI frames from pinned host memory, alternating runs, tools/ncomp_exp.sh): 2 streams 88.4-88.5 k
+                         // frames/s per synchronous call and 99.1-99.2 k submitted; 3 streams 84.6-87.1 k / 91.6-98.3 k; 1 stream 82.0 k /
+                         // 91.4 k -- two chunks side by side hide each other's launch gaps, a third only takes cache and SM space
 #endif
 #ifndef ORB_NSLOT
 #define ORB_NSLOT 3
