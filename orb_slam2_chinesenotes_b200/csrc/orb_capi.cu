@@ -143,7 +143,8 @@ struct orbx_ctx {
     // chunks cost launch tails (a 64-frame launch list takes 0.71 ms, an eighth of a 512-frame one 0.57 ms), larger ones a
     // longer pipeline fill and drain, so the size is chosen per call from the frame size and the batch (run_batch has the
     // rule and the measurements) unless orbx_set_chunk fixed it.  Slots and compute streams (ORB_NSLOT / ORB_NCOMP = 3/2,
-    // 3/1, 4/2, 6/3, 6/2, 8/4) all measure 80-86 k frames/s on KITTI: the pipeline is not short of buffers.  With everything
+    // 3/1, 4/2, 6/3, 6/2, 8/4) all measured 80-86 k frames/s on KITTI before the last kernel changes: the pipeline is not short of
+    // buffers; with the final kernels two compute streams beat three and one (see ORB_NCOMP above).  With everything
     // device resident there is nothing to overlap and bigger launches are simply more efficient (1241x376: 6.66 ms per 512
     // frames in chunks of 64, 6.03 ms as one chunk), so the chunk only bounds the work buffers (about 2.6 MB per frame).
     int chunk = 0, chunk_resident = 512;   // chunk 0: chosen per call (run_batch)
