@@ -300,6 +300,13 @@ def run_reference(args, rank, world):
     dt = time.perf_counter() - t0
     value = nsample * args.steps / dt
     sample = f"first {nsample} frames of the workload's sequence per step (generated on {dev.type}), {what}"
+    base = {"value": value, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample}
+    ocv = opencv_dense_frames_per_s(frames, cores)          # after the timed region: informative bracket, see the function
+    if ocv is not None:
+        base["opencv_dense_stages_only"] = {"value": ocv["frames_per_s"], "unit": "frames/s", "cores": cores,
+                                            "ms_per_frame_per_core": ocv["ms_per_frame_per_core"],
+                                            "what": "cv2 (real OpenCV, SIMD) pyramid + FAST per level + GaussianBlur only, one process per core, same "
+                                                    "frames; informative: this arm runs the reference's sources over a scalar OpenCV stand-in"}
     emit(({
         "impl": "reference", "metric": "orb_extract_frames_per_s", "value": value, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
@@ -307,7 +314,7 @@ def run_reference(args, rank, world):
         "config": workload_config(args.workload, batch, max(args.gpus, 1), "weak"),
         "stats": ({"depth_points_per_pair": total_kp / (nsample // 2)} if args.workload in STEREO and kind == "reference"
                   else {"keypoints_per_frame": total_kp / nsample}),
-        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample},
+        "cpu_baseline": base,
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
