@@ -26,6 +26,12 @@ def test_reference_arm_prints_one_json_line():
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["workload"] == "tum_640x480_nf1000" and "model" not in d["config"]
+    ocv = d["cpu_baseline"].get("opencv_dense_stages_only")          # informative bracket: present where cv2 imports
+    try:
+        import cv2  # noqa: F401
+        assert ocv and ocv["value"] > 0 and set(ocv["ms_per_frame_per_core"]) == {"pyramid", "fast", "blur"}
+    except ImportError:
+        assert ocv is None
 
 
 def test_our_arm_fails_loudly_without_a_gpu():
