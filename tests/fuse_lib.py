@@ -235,8 +235,8 @@ def sim3_pair_scene(k1, d1, k2, d2, w, h, seed, K):
     max_dist = np.full(npts, 1e3, np.float32)
     # matches found earlier (SearchByBoW): KF1 keypoint i already matched to a point of KF2
     m12 = np.full(n1, -1, np.int32)
-    pre = np.flatnonzero(rng.random(n1) < 0.1)
-    m12[pre] = n1 + rng.integers(0, n2, len(pre))
+    pre = np.flatnonzero(rng.random(n1) < 0.1) if n2 else np.zeros(0, np.int64)
+    m12[pre] = n1 + rng.integers(0, max(n2, 1), len(pre))
     idx_in_kf2 = np.full(npts, -1, np.int32)
     idx_in_kf2[n1:] = np.where(mp2 >= 0, np.arange(n2), -1)
     return dict(R1=np.ascontiguousarray(R1), t1=t1, R2=np.ascontiguousarray(R2), t2=t2, s12=float(s12), R12=np.ascontiguousarray(R12), t12=t12,

@@ -134,3 +134,32 @@ def test_sim3_projection_prologue(scene, th, seed):
     _, _, (q1, q2) = run_search_by_sim3("oracle", k1, d1, k2, d2, s, scene["scale"], BOUNDS, K, th)
     assert _same_queries(q1, outs[0], False) and _same_queries(q2, outs[1], False)
     assert outs[0]["valid"].sum() > 500 and outs[1]["valid"].sum() > 500
+
+
+@needs_ref
+def test_degenerate_inputs_match_the_reference(scene):
+    """Empty point list, all points bad, a key frame without keypoints, an empty partner key frame: restatement = reference."""
+    kps, desc, scale, s2 = scene["kps"], scene["desc"], scene["scale"], scene["inv_sigma2"]
+    base = fuse_scene(kps, desc, W, H, 77, K, BF, False)
+    variants = []
+    v = dict(base); v["list"] = base["list"][:0].copy(); variants.append((v, kps, desc))
+    v = dict(base); v["bad"] = np.ones_like(base["bad"]); variants.append((v, kps, desc))
+    v = dict(base); v["list"] = np.full(50, -1, np.int32); variants.append((v, kps, desc))
+    for v, k, d in variants:
+        for sim3 in (False, True):
+            if sim3 and (v["list"] < 0).any():
+                continue                                                    # the Sim3 overload dereferences every entry
+            a = run_fuse("ref", k, d, v, scale, s2, BOUNDS, K, BF, 3.0, sim3, True)
+            b = run_fuse("oracle", k, d, v, scale, s2, BOUNDS, K, BF, 3.0, sim3, True)
+            assert a[0] == b[0] == 0 and same_state(a[1], b[1])
+    # a key frame without keypoints: nothing to fuse into
+    e = fuse_scene(kps[:0], desc[:0], W, H, 78, K, BF, False)
+    e["list"] = np.zeros(0, np.int32)
+    a = run_fuse("ref", kps[:0], desc[:0], e, scale, s2, BOUNDS, K, BF, 3.0, False, False)
+    b = run_fuse("oracle", kps[:0], desc[:0], e, scale, s2, BOUNDS, K, BF, 3.0, False, False)
+    assert a[0] == b[0] == 0
+    # SearchBySim3 against an empty partner
+    s = sim3_pair_scene(kps, desc, scene["k2"][:0], scene["d2"][:0], W, H, 79, K)
+    a = run_search_by_sim3("ref", kps, desc, scene["k2"][:0], scene["d2"][:0], s, scale, BOUNDS, K, 7.5)
+    b = run_search_by_sim3("oracle", kps, desc, scene["k2"][:0], scene["d2"][:0], s, scale, BOUNDS, K, 7.5)
+    assert a[0] == b[0] == 0 and (a[1] == b[1]).all()

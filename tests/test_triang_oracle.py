@@ -44,3 +44,17 @@ def test_oracle_against_stored_reference_results(scene):
         s = triang_scene(scene["kps"], scene["desc"], W, H, seed, K, scene["scale"], n2)
         nm, m12 = search_for_triangulation("oracle", s, K, scene["scale"], scene["sigma2"], only_stereo, check_ori, mono)
         assert nm == int(g[f"triang_{seed}_n"]) and (m12 == g[f"triang_{seed}_m12"]).all()
+
+
+@needs_ref
+def test_degenerate_inputs_match_the_reference(scene):
+    """A key frame without feature vector, a partner of three features, every feature already holding a map point."""
+    s = triang_scene(scene["kps"], scene["desc"], W, H, 75, K, scene["scale"])
+    empty = dict(s); empty["fv2"] = (np.zeros(0, np.int32), np.zeros(1, np.int32), np.zeros(0, np.int32))
+    full = dict(s); full["has1"] = np.ones_like(s["has1"])
+    tiny = triang_scene(scene["kps"], scene["desc"], W, H, 76, K, scene["scale"], n2=3)
+    for v in (empty, full, tiny):
+        a = search_for_triangulation("ref", v, K, scene["scale"], scene["sigma2"], False, True, False)
+        b = search_for_triangulation("oracle", v, K, scene["scale"], scene["sigma2"], False, True, False)
+        assert a[0] == b[0] and (a[1] == b[1]).all()
+    assert search_for_triangulation("oracle", empty, K, scene["scale"], scene["sigma2"], False, True, False)[0] == 0
